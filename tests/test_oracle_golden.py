@@ -1,0 +1,125 @@
+"""Pin the CPU oracle (oracle/neus_oracle.py) against golden vectors produced by the
+imported, unmodified reference (tools/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import factored_neus_b200 as fn
+from oracle import neus_oracle as O
+
+syn = fn.synthetic
+
+
+def _load(golden_dir, name):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+@pytest.fixture(scope="module")
+def states():
+    return syn.scene_states(seed=4, jitter=0.03)
+
+
+def _close(a, b, atol, what):
+    a = a.detach().numpy() if torch.is_tensor(a) else np.asarray(a)
+    err = np.abs(a.astype(np.float64) - np.asarray(b, dtype=np.float64)).max()
+    assert err <= atol, "%s: max abs err %.3e > %.1e" % (what, err, atol)
+
+
+def test_fields_match_reference(golden_dir, states):
+    g = _load(golden_dir, "fields.npz")
+    x, v = torch.from_numpy(g["x"]), torch.from_numpy(g["v"])
+    out = O.sdf_forward(states["sdf"], x)
+    _close(out, g["sdf_out"], 2e-6, "sdf forward")
+    grad = O.sdf_gradient(states["sdf"], x)
+    _close(grad, g["grad"], 5e-6, "sdf gradient (autograd)")
+    out2, grad2 = O.sdf_gradient_analytic(states["sdf"], x)
+    _close(out2, g["sdf_out"], 2e-6, "sdf forward (analytic)")
+    _close(grad2, g["grad"], 2e-5, "sdf gradient (analytic)")
+    rgb = O.color_forward(states["color"], x, torch.from_numpy(g["grad"]), v, torch.from_numpy(g["sdf_out"][:, 1:]))
+    _close(rgb, g["rgb"], 2e-6, "colour")
+    dens, nrgb = O.nerf_forward(states["nerf"], torch.from_numpy(g["x4"]), v)
+    _close(dens, g["nerf_density"], 2e-6, "nerf density")
+    _close(nrgb, g["nerf_rgb"], 2e-6, "nerf rgb")
+    r, s, d = O.refcolor_forward(states["ref"], x, torch.from_numpy(g["sdf_out"][:, 1:]), v, torch.from_numpy(g["grad"]))
+    _close(r, g["ref_rgb"], 2e-6, "refcolor rgb")
+    _close(s, g["ref_spec"], 2e-6, "refcolor specular")
+    _close(d, g["ref_diff"], 2e-6, "refcolor diffuse")
+
+
+def test_sampling_chain_matches_reference(golden_dir, states):
+    g = _load(golden_dir, "sampling.npz")
+    o, d = torch.from_numpy(g["o"]), torch.from_numpy(g["d"])
+    z, sdf = torch.from_numpy(g["z0"]), torch.from_numpy(g["sdf0"])
+    for i in range(4):
+        w = O.upsample_weights(o, d, z, sdf, 64 * 2 ** i)
+        _close(w, g["w%d" % i], 1e-6, "upsample weights %d" % i)
+        cdf = O.pdf_to_cdf(torch.from_numpy(g["w%d" % i]))
+        assert np.array_equal(cdf.numpy(), g["cdf%d" % i]), "cdf %d not bit-equal" % i
+        u = torch.from_numpy(g["u"]).expand(z.shape[0], -1)
+        samples, inds = O.invert_cdf(z, torch.from_numpy(g["cdf%d" % i]), u)
+        assert np.array_equal(inds.numpy(), g["inds%d" % i]), "searchsorted indices %d" % i
+        new_z = O.up_sample(o, d, z, sdf, 16, 64 * 2 ** i)
+        _close(new_z, g["newz%d" % i], 2e-6, "new z %d" % i)
+        new_z = torch.from_numpy(g["newz%d" % i])
+        z, sdf = O.cat_z_vals(lambda p: O.sdf_value(states["sdf"], p), o, d, z, new_z, sdf, last=(i == 3))
+        _close(z, g["z%d" % (i + 1)], 0.0, "merged z %d" % i)
+        _close(sdf, g["sdf%d" % (i + 1)], 2e-6, "merged sdf %d" % i)
+        z, sdf = torch.from_numpy(g["z%d" % (i + 1)]), torch.from_numpy(g["sdf%d" % (i + 1)])
+
+
+def _digest(t, n_probe=48):
+    flat = t.detach().reshape(-1).double()
+    idx = torch.linspace(0, flat.numel() - 1, min(n_probe, flat.numel())).long()
+    return np.concatenate([[flat.sum().item(), flat.abs().sum().item(), flat.norm().item()], flat[idx].numpy()])
+
+
+@pytest.mark.parametrize("tag,conf,car,mw", [("wmask", O.RENDER_CONF_WMASK, 1.0, 0.1),
+                                             ("womask", O.RENDER_CONF_WOMASK, 0.3, 0.0)])
+def test_render_fwd_bwd_matches_reference(golden_dir, tag, conf, car, mw):
+    g = _load(golden_dir, "render_%s.npz" % tag)
+    st = syn.scene_states(seed=4, jitter=0.03)
+    P = {k: {n: t.clone().requires_grad_(True) for n, t in sd.items()} for k, sd in st.items()}
+    B = g["color_fine"].shape[0]
+    o, d, near, far = syn.make_rays(B, seed=1)
+    true_rgb, mask = syn.make_targets(B, seed=2)
+    # end to end: ray-level outputs are well conditioned; per-sample ones are not (a 1e-7 change of an
+    # up-sampling SDF moves depths drawn from near-empty CDF bins by ~1e-5), so those are compared on
+    # the reference's own depths (z_override) below.
+    e2e = O.render(P, o, d, near, far, conf=conf, perturb_overwrite=0, cos_anneal_ratio=car)
+    for k in ("color_fine", "surface_color", "s_val", "weight_sum", "weight_max", "gradient_error",
+              "specular_color", "diffuse_color"):
+        _close(e2e[k], g[k], 2e-5, "%s e2e %s" % (tag, k))
+    _close(e2e["z_vals"], g["z_vals"], 1e-3, "%s e2e z_vals" % tag)
+    out = O.render(P, o, d, near, far, conf=conf, perturb_overwrite=0, cos_anneal_ratio=car,
+                   z_override=torch.from_numpy(g["z_vals"]))
+    for k in ("color_fine", "surface_color", "s_val", "cdf_fine", "weight_sum", "weight_max", "gradients",
+              "weights", "gradient_error", "inside_sphere", "specular_color", "diffuse_color"):
+        _close(out[k], g[k], 1e-5, "%s %s" % (tag, k))
+    assert np.array_equal(out["sdf_mask"].numpy().astype(np.float32), g["sdf_mask"])
+    loss, _ = O.stage1_loss(out, true_rgb, mask, 0.1, 0.1, mw)
+    assert abs(loss.item() - float(g["loss"])) < 2e-5
+    loss.backward()
+    for net in ("sdf", "color", "var", "ref", "nerf"):
+        for name, t in P[net].items():
+            ref = g["grad.%s.%s" % (net, name)]
+            got = _digest(t.grad if t.grad is not None else torch.zeros_like(t))
+            scale = max(1.0, np.abs(ref[3:]).max())
+            assert np.abs(got[3:] - ref[3:]).max() <= 2e-5 * scale, "%s grad %s.%s" % (tag, net, name)
+            assert abs(got[2] - ref[2]) <= 1e-4 * max(1.0, ref[2]), "%s grad-norm %s.%s" % (tag, net, name)
+
+
+def test_grid_matches_reference(golden_dir, states):
+    g = _load(golden_dir, "grid.npz")
+    u = O.extract_fields(states["sdf"], torch.from_numpy(g["bmin"]), torch.from_numpy(g["bmax"]), 20, chunk=64)
+    _close(u, g["u"], 2e-6, "grid")
+
+
+def test_lvis_trace_matches_reference(golden_dir, states):
+    g = _load(golden_dir, "lvis.npz")
+    P = {k: states[k] for k in ("sdf", "var", "color")}
+    lvis, rad, _, _ = O.trace_visibility(P, torch.from_numpy(g["surf"]), torch.from_numpy(g["normal"]),
+                                         torch.from_numpy(g["r_theta"]), torch.from_numpy(g["rand_z"]))
+    _close(lvis, g["gt_lvis"], 2e-5, "gt_lvis")
+    _close(rad, g["gt_trace_radiance"], 2e-5, "gt_trace_radiance")
