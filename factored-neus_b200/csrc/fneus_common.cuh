@@ -1,0 +1,111 @@
+// Shared device/host helpers for the fneus kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/fneus.h"
+
+namespace fneus {
+
+#define FNEUS_CHECK_LAUNCH()                                   \
+  do {                                                         \
+    cudaError_t e__ = cudaGetLastError();                      \
+    if (e__ != cudaSuccess) return fneus_cuda_error((int)e__); \
+  } while (0)
+
+inline int fneus_cuda_error(int e) { return FNEUS_ERR_CUDA_BASE + e; }
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// Generated A-operand columns: concatenation of up to 4 items, each a raw d-vector per row optionally
+// followed by its positional encoding [sin(2^k v), cos(2^k v)]_k (reference: models/embedder.py:11-36).
+// The encoding is evaluated in registers by whichever kernel consumes it and never stored as a tensor.
+// deriv=1 evaluates (dPE/dv)(v) * tan instead (the T0 * t product of SURVEY.md A.1).
+// ---------------------------------------------------------------------------------------------
+struct GenItem {
+  const float* src;  // [M, dim]
+  const float* tan;  // [M, dim] tangent (deriv mode) or nullptr
+  int dim;
+  int multires;      // 0 -> raw vector only
+  int col0;          // first generated column of this item
+  float scale;       // raw value multiplier (SDFNetwork.scale)
+};
+struct GenSpec {
+  int nitems;
+  int ncols;
+  int deriv;
+  GenItem it[4];
+};
+
+__host__ __device__ inline int pe_dim(int d, int multires) { return d * (1 + 2 * multires); }
+
+inline GenSpec gen_none() {
+  GenSpec g;
+  g.nitems = 0; g.ncols = 0; g.deriv = 0;
+  for (int i = 0; i < 4; i++) g.it[i] = GenItem{nullptr, nullptr, 1, 0, 0, 1.f};
+  return g;
+}
+inline void gen_add(GenSpec& g, const float* src, int dim, int multires, float scale = 1.f,
+                    const float* tan = nullptr) {
+  GenItem& it = g.it[g.nitems++];
+  it.src = src; it.tan = tan; it.dim = dim; it.multires = multires; it.col0 = g.ncols; it.scale = scale;
+  g.ncols += pe_dim(dim, multires);
+}
+
+// decode column j of an item into (component, kind, freq); kind 0 = identity, 1 = sin, 2 = cos
+__device__ __forceinline__ void pe_decode(int jj, int d, int& comp, int& kind, float& freq) {
+  if (jj < d) { comp = jj; kind = 0; freq = 1.f; return; }
+  jj -= d;
+  int k = jj / (2 * d);
+  int r = jj - k * 2 * d;
+  kind = r < d ? 1 : 2;
+  comp = r < d ? r : r - d;
+  freq = (float)(1u << k);
+}
+
+__device__ __forceinline__ float gen_eval(const GenSpec& g, long long m, int j) {
+  int sel = 0;
+#pragma unroll
+  for (int i = 1; i < 4; i++)
+    if (i < g.nitems && j >= g.it[i].col0) sel = i;
+  const float* src = g.it[0].src; const float* tan = g.it[0].tan;
+  int d = g.it[0].dim, c0 = g.it[0].col0; float sc = g.it[0].scale;
+#pragma unroll
+  for (int i = 1; i < 4; i++)
+    if (sel == i) { src = g.it[i].src; tan = g.it[i].tan; d = g.it[i].dim; c0 = g.it[i].col0; sc = g.it[i].scale; }
+  int comp, kind; float freq;
+  pe_decode(j - c0, d, comp, kind, freq);
+  float v = __ldg(src + m * d + comp) * sc;
+  if (!g.deriv) {
+    if (kind == 0) return v;
+    float a = v * freq;
+    return kind == 1 ? sinf(a) : cosf(a);
+  }
+  float t = __ldg(tan + m * d + comp);
+  if (kind == 0) return t;
+  float a = v * freq;
+  return kind == 1 ? freq * cosf(a) * t : -freq * sinf(a) * t;
+}
+
+// Softplus(beta) with torch's threshold 20 (fields.py:72), and its derivative recovered from the
+// stored activation h = softplus(a):  sigma'(a) = 1 - exp(-beta h)   (SURVEY.md A.1).
+__device__ __forceinline__ float softplus_beta(float a, float beta) {
+  float z = a * beta;
+  return z > 20.f ? a : log1pf(expf(z)) / beta;
+}
+__device__ __forceinline__ float softplus_grad_from_pre(float a, float beta) {
+  float z = a * beta;
+  if (z > 20.f) return 1.f;
+  float e = expf(z);
+  return e / (e + 1.f);
+}
+__device__ __forceinline__ float softplus_grad_from_act(float h, float beta) {
+  float z = h * beta;
+  return z > 20.f ? 1.f : -expm1f(-z);
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+}  // namespace fneus

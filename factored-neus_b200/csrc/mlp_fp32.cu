@@ -1,0 +1,391 @@
+// Network-level host orchestration + small elementwise kernels for the FP32 path:
+// SDFNetwork (fields.py:9-111), RenderingNetwork (fields.py:114-175), RefColor (fields.py:271-335).
+// Every dense layer is one launch of the SIMT GEMM engine (gemm_simt.cuh) with a fused epilogue;
+// positional encodings are generated in the GEMM tile loaders.
+#include "gemm_simt.cuh"
+
+namespace fneus {
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms = n > 0 ? n : 148;
+  }
+  return g_num_sms;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+// C[m][col0 + j] = gen(m, j) * scale
+__global__ void append_gen_cols_kernel(GenSpec g, float* C, int ldc, int col0, float scale, long long M) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = M * g.ncols;
+  if (idx >= total) return;
+  long long m = idx / g.ncols;
+  int j = (int)(idx - m * g.ncols);
+  C[m * ldc + col0 + j] = gen_eval(g, m, j) * scale;
+}
+
+// n[m][c] = sum_j [comp_j == c] dPE_j/dx_c (x) * g0[m][j]      (T0^T g0)
+__global__ void normal_from_g0_kernel(const float* x, int d, int multires, float scale, const float* g0, int ldg,
+                                      float* n_out, long long M) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  for (int c = 0; c < d; c++) {
+    float v = x[m * d + c] * scale;
+    float acc = g0[m * ldg + c];
+    for (int k = 0; k < multires; k++) {
+      float f = (float)(1u << k);
+      float s, co;
+      sincosf(v * f, &s, &co);
+      acc += f * co * g0[m * ldg + d * (1 + 2 * k) + c] - f * s * g0[m * ldg + d * (2 + 2 * k) + c];
+    }
+    n_out[m * d + c] = acc;
+  }
+}
+
+// out[k] += sum_m w[m]*wscale * X[m][k] (w == nullptr -> 1); osum += sum_m w[m]*wscale
+__global__ void colsum_kernel(const float* X, int ldx, int K, const float* w, float wscale, float* out, float* osum,
+                              long long M, int m_per_block) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  long long mbeg = (long long)blockIdx.y * m_per_block;
+  long long mend = mbeg + m_per_block < M ? mbeg + m_per_block : M;
+  float acc = 0.f, ws = 0.f;
+  for (long long m = mbeg; m < mend; m++) {
+    float wm = w ? __ldg(w + m) * wscale : 1.f;
+    if (k < K) acc += wm * __ldg(X + m * ldx + k);
+    ws += wm;
+  }
+  if (k < K) atomicAdd(out + k, acc);
+  if (osum && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(osum, ws);
+}
+
+// out0[m] = (dot(H[m,:K], w) + b) * scale     one warp per row
+__global__ void rowdot_kernel(const float* H, int ldh, int K, const float* w, const float* b, float scale,
+                              float* out0, long long M) {
+  long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  int lane = threadIdx.x % 32;
+  if (m >= M) return;
+  float acc = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    float4 h = __ldg(reinterpret_cast<const float4*>(H + m * ldh + k));
+    if (k + 0 < K) acc = fmaf(h.x, __ldg(w + k + 0), acc);
+    if (k + 1 < K) acc = fmaf(h.y, __ldg(w + k + 1), acc);
+    if (k + 2 < K) acc = fmaf(h.z, __ldg(w + k + 2), acc);
+    if (k + 3 < K) acc = fmaf(h.w, __ldg(w + k + 3), acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out0[m] = (acc + __ldg(b)) * scale;
+}
+
+// out[m][j] = in[m][col0 + j], j < ncols
+__global__ void extract_cols_kernel(const float* in, int ldi, int col0, int ncols, float* out, int ldo, long long M) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * ncols) return;
+  long long m = idx / ncols;
+  int j = (int)(idx - m * ncols);
+  out[m * ldo + j] = in[m * ldi + col0 + j];
+}
+
+// a[m][j] = dy[m][j] * y[m][j] * (1 - y[m][j])   (sigmoid backward) into a padded buffer
+__global__ void sigmoid_bwd_kernel(const float* dy, const float* y, int n, float* a, int lda, long long M) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * lda) return;
+  long long m = idx / lda;
+  int j = (int)(idx - m * lda);
+  float v = 0.f;
+  if (j < n) { float yy = y[m * n + j]; v = dy[m * n + j] * yy * (1.f - yy); }
+  a[idx] = v;
+}
+
+static inline int ew_blocks(long long n) { return cdiv(n, 256); }
+
+// ------------------------------------------------------------------------------------------------
+// SDF network
+// ------------------------------------------------------------------------------------------------
+struct SdfPlan {
+  int L;          // number of hidden layers; linears 0..L
+  int e;          // embedded input width
+  int in[20], out[20], ldin[20], ldout[20];
+  long long woff[20], boff[20];
+  long long pack;
+  int ldmax;
+  int skip;
+  bool ok;
+};
+
+static SdfPlan sdf_plan(const fneus_sdf_cfg* c) {
+  SdfPlan p;
+  p.ok = c && c->n_layers >= 1 && c->n_layers < 18 && c->d_in >= 1 && c->d_in <= 4 && c->d_hidden >= 4 &&
+         c->d_out >= 1 && c->multires >= 0 && c->multires <= 12;
+  if (!p.ok) return p;
+  p.L = c->n_layers;
+  p.e = pe_dim(c->d_in, c->multires);
+  p.skip = c->skip_layer;
+  if (p.skip == 0 || p.skip >= p.L) p.ok = false;   // skip in 1..L-1 (or <0 = none)
+  if (p.skip > 0 && c->d_hidden - p.e < 1) p.ok = false;
+  long long off = 0;
+  p.ldmax = 4;
+  for (int l = 0; l <= p.L; l++) {
+    p.in[l] = l == 0 ? p.e : c->d_hidden;
+    p.out[l] = l == p.L ? c->d_out : ((l + 1 == p.skip) ? c->d_hidden - p.e : c->d_hidden);
+    p.ldin[l] = round_up(p.in[l], 4);
+    p.ldout[l] = round_up(p.out[l], 4);
+    p.woff[l] = off; off += (long long)p.out[l] * p.in[l];
+    p.boff[l] = off; off += p.out[l];
+    if (p.ldin[l] > p.ldmax) p.ldmax = p.ldin[l];
+    if (l < p.L && p.ldout[l] > p.ldmax) p.ldmax = p.ldout[l];
+  }
+  p.pack = off;
+  return p;
+}
+
+// saved layout: H_1..H_L ([M, ldin[l]]), Q_0..Q_{L-1} ([M, ldout[l]])
+static long long sdf_saved_per_point(const SdfPlan& p) {
+  long long s = 0;
+  for (int l = 1; l <= p.L; l++) s += p.ldin[l];
+  for (int l = 0; l < p.L; l++) s += p.ldout[l];
+  return s;
+}
+static long long sdf_scratch_per_point(const SdfPlan& p) { return 4LL * p.ldmax + 2LL * round_up(p.e, 4); }
+
+struct SdfBufs {
+  float* H[20];
+  float* Q[20];
+};
+static SdfBufs sdf_carve(const SdfPlan& p, float* saved, long long M) {
+  SdfBufs b;
+  float* ptr = saved;
+  for (int l = 1; l <= p.L; l++) { b.H[l] = ptr; ptr += M * p.ldin[l]; }
+  for (int l = 0; l < p.L; l++) { b.Q[l] = ptr; ptr += M * p.ldout[l]; }
+  b.H[0] = nullptr;
+  return b;
+}
+
+static GenSpec sdf_gen(const fneus_sdf_cfg* c, const float* x, const float* tan) {
+  GenSpec g = gen_none();
+  gen_add(g, x, c->d_in, c->multires, c->scale, tan);
+  g.deriv = tan ? 1 : 0;
+  return g;
+}
+
+// value chain. If bufs != nullptr activations go to bufs->H (saved) else ping-pong in scratch.
+static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, const float* x, long long M,
+                           float* sdf_out, float* feat_out, SdfBufs* bufs, float* scratch, cudaStream_t st) {
+  const float rsqrt2 = 0.70710678118654752440f;
+  float* pp[2] = {scratch, scratch + M * p.ldmax};
+  const float* Hin = nullptr;
+  for (int l = 0; l <= p.L; l++) {
+    ASeg a = l == 0 ? aseg_gen(sdf_gen(c, x, nullptr)) : aseg_mem(Hin, p.ldin[l], p.in[l]);
+    const float* W = w + p.woff[l];
+    const float* b = w + p.boff[l];
+    Epi e = epi_default();
+    e.beta = c->beta;
+    e.bias = b;
+    if (l < p.L) {
+      float* Hout = bufs ? bufs->H[l + 1] : pp[(l + 1) & 1];
+      e.mode = EPI_SOFTPLUS;
+      e.C = Hout; e.ldc = p.ldin[l + 1];
+      e.oscale = (l + 1 == p.skip) ? rsqrt2 : 1.f;
+      if (bufs && l == p.L - 1) {
+        e.mode = EPI_SOFTPLUS_Q;
+        e.Q = bufs->Q[l]; e.ldq = p.ldout[l];
+        e.rvec = w + p.woff[p.L];   // row 0 of the last linear
+      }
+      launch_gemm_fwd(a, W, p.in[l], 0, M, p.out[l], e, st);
+      if (l + 1 == p.skip) {
+        GenSpec g = sdf_gen(c, x, nullptr);
+        append_gen_cols_kernel<<<ew_blocks(M * g.ncols), 256, 0, st>>>(g, Hout, p.ldin[l + 1], p.out[l], rsqrt2, M);
+      }
+      Hin = Hout;
+    } else if (feat_out) {
+      e.mode = EPI_SDF_OUT;
+      e.out0 = sdf_out; e.out0_scale = 1.f / c->scale;
+      e.C = feat_out; e.ldc = c->d_out - 1;
+      launch_gemm_fwd(a, W, p.in[l], 0, M, p.out[l], e, st);
+    } else {
+      rowdot_kernel<<<ew_blocks(M * 32), 256, 0, st>>>(Hin, p.ldin[l], p.in[l], W, b, 1.f / c->scale, sdf_out, M);
+    }
+  }
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+}  // namespace fneus
+
+using namespace fneus;
+
+extern "C" {
+
+long long fneus_sdf_pack_floats(const fneus_sdf_cfg* cfg) {
+  SdfPlan p = sdf_plan(cfg);
+  return p.ok ? p.pack : -1;
+}
+long long fneus_sdf_saved_floats(const fneus_sdf_cfg* cfg, long long n) {
+  SdfPlan p = sdf_plan(cfg);
+  return p.ok ? sdf_saved_per_point(p) * n : -1;
+}
+long long fneus_sdf_scratch_floats(const fneus_sdf_cfg* cfg, long long n) {
+  SdfPlan p = sdf_plan(cfg);
+  return p.ok ? sdf_scratch_per_point(p) * n : -1;
+}
+
+int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long n, float* sdf_out,
+                  float* feat_out, float* scratch, long long scratch_floats, void* stream) {
+  SdfPlan p = sdf_plan(cfg);
+  if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
+  if (n == 0) return FNEUS_OK;
+  if (!wpack || !x || !sdf_out || !scratch) return FNEUS_ERR_NULL;
+  if (n < 0) return FNEUS_ERR_BAD_SHAPE;
+  long long per = 2LL * p.ldmax;
+  long long chunk = scratch_floats / per;
+  if (chunk >= 128) chunk = chunk / 128 * 128;
+  if (chunk < 1) return FNEUS_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (long long m0 = 0; m0 < n; m0 += chunk) {
+    long long M = n - m0 < chunk ? n - m0 : chunk;
+    int rc = sdf_value_chain(cfg, p, wpack, x + m0 * cfg->d_in, M, sdf_out + m0,
+                             feat_out ? feat_out + m0 * (cfg->d_out - 1) : nullptr, nullptr, scratch, st);
+    if (rc) return rc;
+  }
+  return FNEUS_OK;
+}
+
+int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long M, float* sdf_out,
+                       float* feat_out, float* normal_out, float* saved, float* scratch, void* stream) {
+  SdfPlan p = sdf_plan(cfg);
+  if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
+  if (M == 0) return FNEUS_OK;
+  if (!wpack || !x || !sdf_out || !feat_out || !saved || !scratch) return FNEUS_ERR_NULL;
+  if (M < 0) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
+  SdfBufs b = sdf_carve(p, saved, M);
+  int rc = sdf_value_chain(cfg, p, wpack, x, M, sdf_out, feat_out, &b, scratch, st);
+  if (rc) return rc;
+  if (!normal_out) return FNEUS_OK;   // value-only graph (SDFNetwork.forward under autograd)
+  // reverse chain for the normal: g_l = q_l W_l, q_{l-1} = s_{l-1} * g_l
+  const int e4 = round_up(p.e, 4);
+  float* g0e = scratch + 4LL * M * p.ldmax;
+  float* g0 = g0e + M * e4;
+  for (int l = p.L - 1; l >= 1; l--) {
+    ASeg a = aseg_mem(b.Q[l], p.ldout[l], p.out[l]);
+    Epi e = epi_default();
+    e.beta = cfg->beta;
+    e.mode = EPI_SPMUL;
+    e.H = b.H[l]; e.ldh = p.ldin[l];
+    e.C = b.Q[l - 1]; e.ldc = p.ldout[l - 1];
+    if (l == p.skip) {
+      e.hscale = sqrt2; e.oscale = rsqrt2;
+      e.csplit = p.out[l - 1];
+      e.C2 = g0e; e.ldc2 = e4;
+    }
+    launch_gemm_bwd_data(a, wpack + p.woff[l], p.in[l], 0, M, p.in[l], e, st);
+  }
+  {
+    ASeg a = aseg_mem(b.Q[0], p.ldout[0], p.out[0]);
+    Epi e = epi_default();
+    e.mode = EPI_LINEAR_ADD;
+    e.Q = p.skip > 0 ? g0e : nullptr; e.ldq = e4;
+    e.C = g0; e.ldc = e4;
+    launch_gemm_bwd_data(a, wpack + p.woff[0], p.in[0], 0, M, p.in[0], e, st);
+  }
+  normal_from_g0_kernel<<<ew_blocks(M), 256, 0, st>>>(x, cfg->d_in, cfg->multires, cfg->scale, g0, e4, normal_out, M);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long M, const float* d_sdf,
+                  const float* d_feat, const float* d_normal, float* saved, float* scratch, float* d_wpack,
+                  void* stream) {
+  SdfPlan p = sdf_plan(cfg);
+  if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
+  if (M == 0) return FNEUS_OK;
+  if (!wpack || !x || !saved || !scratch || !d_wpack) return FNEUS_ERR_NULL;
+  if (M < 0) return FNEUS_ERR_BAD_SHAPE;
+  if (d_feat && ((cfg->d_out - 1) % 4 != 0)) return FNEUS_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sms = num_sms();
+  const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
+  SdfBufs b = sdf_carve(p, saved, M);
+  float* gbuf[2] = {scratch, scratch + M * p.ldmax};
+  float* abuf[2] = {scratch + 2LL * M * p.ldmax, scratch + 3LL * M * p.ldmax};
+  const int L = p.L;
+
+  if (d_normal) {
+    // double-backward sweep: gbar_0 = T0 nbar ; qbar_l = gbar_l W_l^T ; dW_l += q_l^T gbar_l ;
+    // gbar_{l+1} = s_l qbar_l ; e_l = beta (1-s_l) q_l qbar_l (written over q_l)
+    for (int l = 0; l < L; l++) {
+      ASeg a = l == 0 ? aseg_gen(sdf_gen(cfg, x, d_normal)) : aseg_mem(gbuf[l & 1], p.ldin[l], p.in[l]);
+      launch_gemm_wgrad(b.Q[l], p.ldout[l], a, d_wpack + p.woff[l], p.in[l], 0, nullptr, M, p.out[l], sms, st);
+      Epi e = epi_default();
+      e.beta = cfg->beta;
+      e.mode = EPI_SWEEP;
+      e.H = b.H[l + 1]; e.ldh = p.ldin[l + 1];
+      e.Q = b.Q[l]; e.ldq = p.ldout[l];
+      float* gout = gbuf[(l + 1) & 1];
+      e.C = gout; e.ldc = p.ldin[l + 1];
+      if (l + 1 == p.skip) { e.hscale = sqrt2; e.oscale = rsqrt2; }
+      launch_gemm_fwd(a, wpack + p.woff[l], p.in[l], 0, M, p.out[l], e, st);
+      if (l + 1 == p.skip) {
+        GenSpec g = sdf_gen(cfg, x, d_normal);
+        append_gen_cols_kernel<<<ew_blocks(M * g.ncols), 256, 0, st>>>(g, gout, p.ldin[l + 1], p.out[l], rsqrt2, M);
+      }
+    }
+    // q_L = e_0 (row 0 of the last linear): dW_L[0,:] += sum_m gbar_L
+    {
+      int mpb = 256;
+      dim3 grid(cdiv(p.in[L], 256), cdiv(M, mpb));
+      colsum_kernel<<<grid, 256, 0, st>>>(gbuf[L & 1], p.ldin[L], p.in[L], nullptr, 1.f, d_wpack + p.woff[L],
+                                          nullptr, M, mpb);
+    }
+  }
+  // value-path backward with the augmented abar_l
+  float* dWL = d_wpack + p.woff[L];
+  float* dbL = d_wpack + p.boff[L];
+  if (d_sdf) {
+    int mpb = 256;
+    dim3 grid(cdiv(p.in[L], 256), cdiv(M, mpb));
+    colsum_kernel<<<grid, 256, 0, st>>>(b.H[L], p.ldin[L], p.in[L], d_sdf, 1.f / cfg->scale, dWL, dbL, M, mpb);
+  }
+  if (d_feat) {
+    launch_gemm_wgrad(d_feat, cfg->d_out - 1, aseg_mem(b.H[L], p.ldin[L], p.in[L]), dWL, p.in[L], 1, dbL, M,
+                      cfg->d_out - 1, sms, st);
+  }
+  {
+    ASeg a = aseg_mem(d_feat, cfg->d_out - 1, d_feat ? cfg->d_out - 1 : 0, /*wred=*/1);
+    if (!d_feat) { a.mem = wpack; a.ldm = 4; }
+    Epi e = epi_default();
+    e.beta = cfg->beta;
+    e.mode = EPI_SDF_BWD;
+    e.H = b.H[L]; e.ldh = p.ldin[L];
+    if (L == p.skip) { e.hscale = sqrt2; e.oscale = rsqrt2; e.csplit = p.out[L - 1]; }
+    e.rs = d_sdf; e.rvec = wpack + p.woff[L]; e.rscale = 1.f / cfg->scale;
+    e.Q = d_normal ? b.Q[L - 1] : nullptr; e.ldq = p.ldout[L - 1];
+    e.C = abuf[(L - 1) & 1]; e.ldc = p.ldout[L - 1];
+    launch_gemm_bwd_data(a, wpack + p.woff[L], p.in[L], 0, M, p.in[L], e, st);
+  }
+  for (int l = L - 1; l >= 0; l--) {
+    float* al = abuf[l & 1];
+    ASeg h = l == 0 ? aseg_gen(sdf_gen(cfg, x, nullptr)) : aseg_mem(b.H[l], p.ldin[l], p.in[l]);
+    launch_gemm_wgrad(al, p.ldout[l], h, d_wpack + p.woff[l], p.in[l], 0, d_wpack + p.boff[l], M, p.out[l], sms, st);
+    if (l == 0) break;
+    ASeg a = aseg_mem(al, p.ldout[l], p.out[l]);
+    Epi e = epi_default();
+    e.beta = cfg->beta;
+    e.mode = EPI_SDF_BWD;
+    e.H = b.H[l]; e.ldh = p.ldin[l];
+    if (l == p.skip) { e.hscale = sqrt2; e.oscale = rsqrt2; e.csplit = p.out[l - 1]; }
+    e.Q = d_normal ? b.Q[l - 1] : nullptr; e.ldq = p.ldout[l - 1];
+    e.C = abuf[(l - 1) & 1]; e.ldc = p.ldout[l - 1];
+    launch_gemm_bwd_data(a, wpack + p.woff[l], p.in[l], 0, M, p.in[l], e, st);
+  }
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+}  // extern "C"

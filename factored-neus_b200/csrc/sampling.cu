@@ -1,0 +1,299 @@
+// Hierarchical sampling kernels (renderer.py:43-77 sample_pdf, :152-189 up_sample, :191-205 cat_z_vals,
+// :224-236 section geometry; duplicates calLvis.py:25-90).  One warp per ray: coalesced loads into a
+// per-warp shared-memory row, shuffle scans for the transmittance product and the CDF sum, binary
+// search per importance sample.  No gradients flow through any of this (renderer.py:426 no_grad).
+#include "fneus_common.cuh"
+
+namespace fneus {
+
+constexpr int SAMP_WARPS = 4;
+
+__device__ __forceinline__ float warp_incl_scan_mul(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v *= t;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_incl_scan_add(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// first index i in [0,n) with c[i] > u  (torch.searchsorted(..., right=True)), n if none
+__device__ __forceinline__ int upper_bound(const float* c, int n, float u) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (c[mid] > u) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+// number of entries < v  (lower bound) in sorted c[0..n)
+__device__ __forceinline__ int count_less(const float* c, int n, float v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (c[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int count_leq(const float* c, int n, float v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (c[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void invert_cdf_warp(const float* sz, const float* scdf, int n, int k,
+                                                const float* u_table, float* out, long long* inds, int lane) {
+  for (int m = lane; m < k; m += 32) {
+    float u = __ldg(u_table + m);
+    int idx = upper_bound(scdf, n, u);
+    int lo = idx - 1 > 0 ? idx - 1 : 0;
+    int hi = idx < n - 1 ? idx : n - 1;
+    float den = scdf[hi] - scdf[lo];
+    if (den < 1e-5f) den = 1.f;
+    float t = (u - scdf[lo]) / den;
+    out[m] = __fadd_rn(sz[lo], __fmul_rn(t, sz[hi] - sz[lo]));
+    if (inds) inds[m] = idx;
+  }
+}
+
+__global__ void __launch_bounds__(SAMP_WARPS * 32)
+upsample_step_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                     const float* __restrict__ z, const float* __restrict__ sdf, long long B, int n, int k,
+                     float inv_s, const float* __restrict__ u_table, float* __restrict__ new_z,
+                     float* __restrict__ cdf_out, long long* __restrict__ inds_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long long ray = (long long)blockIdx.x * SAMP_WARPS + warp;
+  if (ray >= B) return;
+  float* sz = smem + (size_t)warp * 3 * n;
+  float* sf = sz + n;
+  float* sc = sf + n;   // alpha, then cdf
+  for (int j = lane; j < n; j += 32) {
+    sz[j] = __ldg(z + ray * n + j);
+    sf[j] = __ldg(sdf + ray * n + j);
+  }
+  __syncwarp();
+  const float ox = rays_o[ray * 3], oy = rays_o[ray * 3 + 1], oz = rays_o[ray * 3 + 2];
+  const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+  auto radius = [&](float t) {
+    float px = __fadd_rn(ox, __fmul_rn(dx, t)), py = __fadd_rn(oy, __fmul_rn(dy, t)),
+          pz = __fadd_rn(oz, __fmul_rn(dz, t));
+    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+  };
+  auto slope = [&](int j) { return (sf[j + 1] - sf[j]) / (sz[j + 1] - sz[j] + 1e-5f); };
+  const int ni = n - 1;  // intervals
+  // pass 1: alpha_j, transmittance scan, weights; accumulate sum(w + 1e-5)
+  float carry = 1.f, wsum = 0.f;
+  for (int c0 = 0; c0 < ni; c0 += 32) {
+    int j = c0 + lane;
+    float alpha = 0.f;
+    if (j < ni) {
+      bool inside = (radius(sz[j]) < 1.0f) || (radius(sz[j + 1]) < 1.0f);
+      float cosv = slope(j);
+      float prev = j == 0 ? 0.f : slope(j - 1);
+      float cm = fminf(prev, cosv);
+      cm = fminf(fmaxf(cm, -1e3f), 0.f) * (inside ? 1.f : 0.f);
+      float dist = sz[j + 1] - sz[j];
+      float mid = (sf[j] + sf[j + 1]) * 0.5f;
+      float half = __fmul_rn(__fmul_rn(cm, dist), 0.5f);
+      float pc = sigmoidf_(__fmul_rn(mid - half, inv_s));
+      float nc = sigmoidf_(__fmul_rn(mid + half, inv_s));
+      alpha = (pc - nc + 1e-5f) / (pc + 1e-5f);
+    }
+    float fac = j < ni ? (1.f - alpha + 1e-7f) : 1.f;
+    float incl = warp_incl_scan_mul(fac, lane);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    float T = carry * excl;
+    float w = alpha * T + 1e-5f;
+    if (j < ni) { sc[j + 1] = w; wsum += w; }
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+  wsum = warp_sum(wsum);
+  __syncwarp();
+  // pass 2: cdf = [0, cumsum(w / wsum)]
+  float run = 0.f;
+  for (int c0 = 0; c0 < ni; c0 += 32) {
+    int j = c0 + lane;
+    float p = j < ni ? sc[j + 1] / wsum : 0.f;
+    float incl = warp_incl_scan_add(p, lane);
+    if (j < ni) sc[j + 1] = run + incl;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) sc[0] = 0.f;
+  __syncwarp();
+  if (cdf_out)
+    for (int j = lane; j < n; j += 32) cdf_out[ray * n + j] = sc[j];
+  invert_cdf_warp(sz, sc, n, k, u_table, new_z + ray * k, inds_out ? inds_out + ray * k : nullptr, lane);
+}
+
+__global__ void __launch_bounds__(SAMP_WARPS * 32)
+inverse_cdf_kernel(const float* __restrict__ bins, const float* __restrict__ cdf, const float* __restrict__ u_table,
+                   long long B, int n, int k, float* __restrict__ out, long long* __restrict__ inds) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long long ray = (long long)blockIdx.x * SAMP_WARPS + warp;
+  if (ray >= B) return;
+  float* sz = smem + (size_t)warp * 2 * n;
+  float* sc = sz + n;
+  for (int j = lane; j < n; j += 32) { sz[j] = bins[ray * n + j]; sc[j] = cdf[ray * n + j]; }
+  __syncwarp();
+  invert_cdf_warp(sz, sc, n, k, u_table, out + ray * k, inds ? inds + ray * k : nullptr, lane);
+}
+
+__global__ void __launch_bounds__(SAMP_WARPS * 32)
+merge_sorted_kernel(const float* __restrict__ z, const float* __restrict__ new_z, const float* __restrict__ sdf,
+                    const float* __restrict__ new_sdf, long long B, int n, int k, float* __restrict__ z_out,
+                    float* __restrict__ sdf_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long long ray = (long long)blockIdx.x * SAMP_WARPS + warp;
+  if (ray >= B) return;
+  float* sa = smem + (size_t)warp * (n + k);
+  float* sb = sa + n;
+  for (int j = lane; j < n; j += 32) sa[j] = z[ray * n + j];
+  for (int j = lane; j < k; j += 32) sb[j] = new_z[ray * k + j];
+  __syncwarp();
+  const bool carry = sdf && new_sdf && sdf_out;
+  float* zo = z_out + ray * (n + k);
+  float* so = carry ? sdf_out + ray * (n + k) : nullptr;
+  for (int i = lane; i < n; i += 32) {
+    int pos = i + count_less(sb, k, sa[i]);
+    zo[pos] = sa[i];
+    if (carry) so[pos] = sdf[ray * n + i];
+  }
+  for (int j = lane; j < k; j += 32) {
+    int pos = j + count_leq(sa, n, sb[j]);
+    zo[pos] = sb[j];
+    if (carry) so[pos] = new_sdf[ray * k + j];
+  }
+}
+
+__global__ void ray_points_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ z,
+                                  long long total, int n, float* __restrict__ pts) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  long long b = idx / n;
+  float t = z[idx];
+#pragma unroll
+  for (int c = 0; c < 3; c++) pts[idx * 3 + c] = __fadd_rn(o[b * 3 + c], __fmul_rn(d[b * 3 + c], t));
+}
+
+__global__ void core_geometry_kernel(const float* __restrict__ o, const float* __restrict__ d,
+                                     const float* __restrict__ z, long long total, int n, float sample_dist,
+                                     float* __restrict__ dists, float* __restrict__ mid_z, float* __restrict__ pts,
+                                     float* __restrict__ dirs) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  long long b = idx / n;
+  int j = (int)(idx - b * n);
+  float zj = z[idx];
+  float dist = j + 1 < n ? z[idx + 1] - zj : sample_dist;
+  float mid = __fadd_rn(zj, __fmul_rn(dist, 0.5f));
+  if (dists) dists[idx] = dist;
+  if (mid_z) mid_z[idx] = mid;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    float dc = d[b * 3 + c];
+    pts[idx * 3 + c] = __fadd_rn(o[b * 3 + c], __fmul_rn(dc, mid));
+    if (dirs) dirs[idx * 3 + c] = dc;
+  }
+}
+
+}  // namespace fneus
+
+using namespace fneus;
+
+extern "C" {
+
+int fneus_ray_points(const float* rays_o, const float* rays_d, const float* z, long long B, int n, float* pts,
+                     void* stream) {
+  if (B == 0 || n == 0) return FNEUS_OK;
+  if (!rays_o || !rays_d || !z || !pts) return FNEUS_ERR_NULL;
+  if (B < 0 || n < 0) return FNEUS_ERR_BAD_SHAPE;
+  long long total = B * n;
+  ray_points_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z, total, n, pts);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_upsample_step(const float* rays_o, const float* rays_d, const float* z, const float* sdf, long long B,
+                        int n, int k, float inv_s, const float* u_table, float* new_z, float* cdf_out,
+                        long long* inds_out, void* stream) {
+  if (B == 0 || k == 0) return FNEUS_OK;
+  if (!rays_o || !rays_d || !z || !sdf || !u_table || !new_z) return FNEUS_ERR_NULL;
+  if (B < 0 || n < 2 || k < 0 || n > 4096) return FNEUS_ERR_BAD_SHAPE;
+  size_t smem = (size_t)SAMP_WARPS * 3 * n * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(upsample_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fneus_cuda_error((int)e);
+  }
+  upsample_step_kernel<<<cdiv(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      rays_o, rays_d, z, sdf, B, n, k, inv_s, u_table, new_z, cdf_out, inds_out);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_inverse_cdf(const float* bins, const float* cdf, const float* u_table, long long B, int n, int k,
+                      float* samples_out, long long* inds_out, void* stream) {
+  if (B == 0 || k == 0) return FNEUS_OK;
+  if (!bins || !cdf || !u_table || !samples_out) return FNEUS_ERR_NULL;
+  if (B < 0 || n < 1 || k < 0 || n > 4096) return FNEUS_ERR_BAD_SHAPE;
+  size_t smem = (size_t)SAMP_WARPS * 2 * n * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(inverse_cdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fneus_cuda_error((int)e);
+  }
+  inverse_cdf_kernel<<<cdiv(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, cdf, u_table, B, n,
+                                                                                         k, samples_out, inds_out);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_merge_sorted(const float* z, const float* new_z, const float* sdf, const float* new_sdf, long long B, int n,
+                       int k, float* z_out, float* sdf_out, void* stream) {
+  if (B == 0) return FNEUS_OK;
+  if (!z || !new_z || !z_out) return FNEUS_ERR_NULL;
+  if ((sdf == nullptr) != (new_sdf == nullptr)) return FNEUS_ERR_NULL;
+  if (sdf && !sdf_out) return FNEUS_ERR_NULL;
+  if (B < 0 || n < 0 || k < 0 || n + k > 8192) return FNEUS_ERR_BAD_SHAPE;
+  size_t smem = (size_t)SAMP_WARPS * (n + k) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(merge_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fneus_cuda_error((int)e);
+  }
+  merge_sorted_kernel<<<cdiv(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(z, new_z, sdf, new_sdf, B,
+                                                                                        n, k, z_out, sdf_out);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_core_geometry(const float* rays_o, const float* rays_d, const float* z, long long B, int n,
+                        float sample_dist, float* dists, float* mid_z, float* pts, float* dirs, void* stream) {
+  if (B == 0 || n == 0) return FNEUS_OK;
+  if (!rays_o || !rays_d || !z || !pts) return FNEUS_ERR_NULL;
+  if (B < 0 || n < 0) return FNEUS_ERR_BAD_SHAPE;
+  long long total = B * n;
+  core_geometry_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z, total, n, sample_dist,
+                                                                          dists, mid_z, pts, dirs);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,285 @@
+"""torch.autograd.Function wrappers around the C ABI (include/fneus.h).
+
+Each Function allocates outputs/workspaces with torch (device memory + stream
+plumbing only) and hands raw pointers to libfneus_b200.so; the arithmetic is all
+in the CUDA library.  Gradients are returned for the flat *effective* weight packs;
+weight-norm stays in front as differentiable torch ops.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def _f32c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+def _need_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("factored-neus_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
+
+
+def _empty(n, like):
+    return torch.empty(int(n), dtype=torch.float32, device=like.device)
+
+
+# ---------------------------------------------------------------------------------------------
+# SDF network
+# ---------------------------------------------------------------------------------------------
+def sdf_forward_nograd(cfg, wflat, x, want_feat, max_chunk=1 << 18):
+    """SDFNetwork.forward / .sdf without a graph (fields.py:74-95).  Returns (sdf [N,1], feat|None)."""
+    _need_cuda(x, "x")
+    x = _f32c(x)
+    w = _f32c(wflat)
+    N = x.shape[0]
+    sdf = torch.empty(N, 1, dtype=torch.float32, device=x.device)
+    feat = torch.empty(N, cfg.d_out - 1, dtype=torch.float32, device=x.device) if want_feat else None
+    chunk = max(1, min(N, max_chunk))
+    per_point = 2 * max(4, -(-cfg.d_hidden // 4) * 4, -(-(cfg.d_in * (1 + 2 * cfg.multires)) // 4) * 4,
+                        -(-cfg.d_out // 4) * 4)
+    scratch = _empty(per_point * chunk, x)
+    L.check(L.lib().fneus_sdf_fwd(cfg, L.ptr(w), L.ptr(x), N, L.ptr(sdf), L.ptr(feat), L.ptr(scratch),
+                                  scratch.numel(), L.stream_ptr()), "fneus_sdf_fwd")
+    return sdf, feat
+
+
+class SdfValueGrad(torch.autograd.Function):
+    """(wflat, x) -> (sdf [N,1], feat [N,d_out-1], normal [N,3]); fields.py:74-111 with create_graph=True
+    semantics: all three outputs are differentiable w.r.t. the weights (double backward for the normal)."""
+
+    @staticmethod
+    def forward(ctx, wflat, x, cfg, want_normal):
+        _need_cuda(x, "x")
+        xc, w = _f32c(x), _f32c(wflat)
+        N = xc.shape[0]
+        lib = L.lib()
+        sdf = torch.empty(N, 1, dtype=torch.float32, device=x.device)
+        feat = torch.empty(N, cfg.d_out - 1, dtype=torch.float32, device=x.device)
+        normal = torch.empty(N, 3, dtype=torch.float32, device=x.device) if want_normal else None
+        saved = _empty(lib.fneus_sdf_saved_floats(cfg, N), x)
+        scratch = _empty(lib.fneus_sdf_scratch_floats(cfg, N), x)
+        L.check(lib.fneus_sdf_fwd_grad(cfg, L.ptr(w), L.ptr(xc), N, L.ptr(sdf), L.ptr(feat), L.ptr(normal),
+                                       L.ptr(saved), L.ptr(scratch), L.stream_ptr()), "fneus_sdf_fwd_grad")
+        ctx.cfg, ctx.want_normal, ctx.consumed = cfg, want_normal, False
+        ctx.save_for_backward(w, xc, saved)
+        if not want_normal:
+            normal = torch.zeros(0, 3, dtype=torch.float32, device=x.device)
+            ctx.mark_non_differentiable(normal)
+        return sdf, feat, normal
+
+    @staticmethod
+    def backward(ctx, d_sdf, d_feat, d_normal):
+        if ctx.consumed:
+            raise RuntimeError("fneus SdfValueGrad: backward twice is not supported (saved activations are "
+                               "consumed in place)")
+        ctx.consumed = True
+        w, xc, saved = ctx.saved_tensors
+        cfg = ctx.cfg
+        N = xc.shape[0]
+        lib = L.lib()
+        dw = torch.zeros_like(w)
+        scratch = _empty(lib.fneus_sdf_scratch_floats(cfg, N), xc)
+        d_sdf, d_feat = _f32c(d_sdf), _f32c(d_feat)
+        d_normal = _f32c(d_normal) if ctx.want_normal else None
+        L.check(lib.fneus_sdf_bwd(cfg, L.ptr(w), L.ptr(xc), N, L.ptr(d_sdf), L.ptr(d_feat), L.ptr(d_normal),
+                                  L.ptr(saved), L.ptr(scratch), L.ptr(dw), L.stream_ptr()), "fneus_sdf_bwd")
+        return dw, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# colour network
+# ---------------------------------------------------------------------------------------------
+class ColorMLP(torch.autograd.Function):
+    """RenderingNetwork.forward (fields.py:150-175): grads for weights, normals and features."""
+
+    @staticmethod
+    def forward(ctx, wflat, points, normals, view_dirs, feats, cfg):
+        _need_cuda(points, "points")
+        w, p, n, v, f = _f32c(wflat), _f32c(points), _f32c(normals), _f32c(view_dirs), _f32c(feats)
+        N = p.shape[0]
+        lib = L.lib()
+        rgb = torch.empty(N, cfg.d_out, dtype=torch.float32, device=p.device)
+        need_graph = any(ctx.needs_input_grad)
+        saved = _empty(lib.fneus_color_saved_floats(cfg, N), p) if need_graph else None
+        scratch = None if need_graph else _empty(lib.fneus_color_scratch_floats(cfg, N), p)
+        L.check(lib.fneus_color_fwd(cfg, L.ptr(w), L.ptr(p), L.ptr(n), L.ptr(v), L.ptr(f), N, L.ptr(rgb),
+                                    L.ptr(saved), L.ptr(scratch), L.stream_ptr()), "fneus_color_fwd")
+        ctx.cfg = cfg
+        if need_graph:
+            ctx.save_for_backward(w, p, n, v, f, rgb, saved)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, d_rgb):
+        w, p, n, v, f, rgb, saved = ctx.saved_tensors
+        cfg = ctx.cfg
+        N = p.shape[0]
+        lib = L.lib()
+        dw = torch.zeros_like(w)
+        d_n = torch.empty_like(n)
+        d_f = torch.empty_like(f)
+        scratch = _empty(lib.fneus_color_scratch_floats(cfg, N), p)
+        L.check(lib.fneus_color_bwd(cfg, L.ptr(w), L.ptr(p), L.ptr(n), L.ptr(v), L.ptr(f), N, L.ptr(rgb),
+                                    L.ptr(_f32c(d_rgb)), L.ptr(d_n), L.ptr(d_f), L.ptr(saved), L.ptr(scratch),
+                                    L.ptr(dw), L.stream_ptr()), "fneus_color_bwd")
+        return dw, None, d_n, None, d_f, None
+
+
+class RefColorMLP(torch.autograd.Function):
+    """RefColor.forward (fields.py:303-335) -> (rgb, specular_rgb, diffuse_rgb)."""
+
+    @staticmethod
+    def forward(ctx, wflat, points, feats, dirs, normals, cfg):
+        _need_cuda(points, "points")
+        w, p, f, d, n = _f32c(wflat), _f32c(points), _f32c(feats), _f32c(dirs), _f32c(normals)
+        N = p.shape[0]
+        lib = L.lib()
+        outs = [torch.empty(N, 3, dtype=torch.float32, device=p.device) for _ in range(3)]
+        saved = _empty(lib.fneus_ref_saved_floats(cfg, N), p)
+        L.check(lib.fneus_ref_fwd(cfg, L.ptr(w), L.ptr(p), L.ptr(f), L.ptr(d), L.ptr(n), N, L.ptr(outs[0]),
+                                  L.ptr(outs[1]), L.ptr(outs[2]), L.ptr(saved), None, L.stream_ptr()),
+                "fneus_ref_fwd")
+        ctx.cfg = cfg
+        ctx.save_for_backward(w, p, f, d, n, saved)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_spec, d_diff):
+        w, p, f, d, n, saved = ctx.saved_tensors
+        cfg = ctx.cfg
+        N = p.shape[0]
+        lib = L.lib()
+        dw = torch.zeros_like(w)
+        d_f = torch.empty_like(f)
+        d_n = torch.empty_like(n)
+        scratch = _empty(lib.fneus_ref_scratch_floats(cfg, N), p)
+        L.check(lib.fneus_ref_bwd(cfg, L.ptr(w), L.ptr(p), L.ptr(f), L.ptr(d), L.ptr(n), N, L.ptr(_f32c(d_rgb)),
+                                  L.ptr(_f32c(d_spec)), L.ptr(_f32c(d_diff)), L.ptr(d_f), L.ptr(d_n),
+                                  L.ptr(saved), L.ptr(scratch), L.ptr(dw), L.stream_ptr()), "fneus_ref_bwd")
+        return dw, None, d_f, None, d_n, None
+
+
+# ---------------------------------------------------------------------------------------------
+# sampling (no grad)
+# ---------------------------------------------------------------------------------------------
+def ray_points(rays_o, rays_d, z):
+    B, n = z.shape
+    pts = torch.empty(B * n, 3, dtype=torch.float32, device=z.device)
+    L.check(L.lib().fneus_ray_points(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), B, n, L.ptr(pts), L.stream_ptr()),
+            "fneus_ray_points")
+    return pts
+
+
+def upsample_step(rays_o, rays_d, z, sdf, k, inv_s, u_table, debug=False):
+    B, n = z.shape
+    new_z = torch.empty(B, k, dtype=torch.float32, device=z.device)
+    cdf = torch.empty(B, n, dtype=torch.float32, device=z.device) if debug else None
+    inds = torch.empty(B, k, dtype=torch.int64, device=z.device) if debug else None
+    L.check(L.lib().fneus_upsample_step(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(sdf), B, n, k, float(inv_s),
+                                        L.ptr(u_table), L.ptr(new_z), L.ptr(cdf), L.ptr(inds), L.stream_ptr()),
+            "fneus_upsample_step")
+    return (new_z, cdf, inds) if debug else new_z
+
+
+def inverse_cdf(bins, cdf, u_table):
+    B, n = bins.shape
+    k = u_table.numel()
+    out = torch.empty(B, k, dtype=torch.float32, device=bins.device)
+    inds = torch.empty(B, k, dtype=torch.int64, device=bins.device)
+    L.check(L.lib().fneus_inverse_cdf(L.ptr(bins), L.ptr(cdf), L.ptr(u_table), B, n, k, L.ptr(out), L.ptr(inds),
+                                      L.stream_ptr()), "fneus_inverse_cdf")
+    return out, inds
+
+
+def merge_sorted(z, new_z, sdf=None, new_sdf=None):
+    B, n = z.shape
+    k = new_z.shape[1]
+    z_out = torch.empty(B, n + k, dtype=torch.float32, device=z.device)
+    sdf_out = torch.empty(B, n + k, dtype=torch.float32, device=z.device) if sdf is not None else None
+    L.check(L.lib().fneus_merge_sorted(L.ptr(z), L.ptr(new_z), L.ptr(sdf), L.ptr(new_sdf), B, n, k, L.ptr(z_out),
+                                       L.ptr(sdf_out), L.stream_ptr()), "fneus_merge_sorted")
+    return z_out, sdf_out
+
+
+def core_geometry(rays_o, rays_d, z, sample_dist):
+    B, n = z.shape
+    dev = z.device
+    dists = torch.empty(B, n, dtype=torch.float32, device=dev)
+    mid_z = torch.empty(B, n, dtype=torch.float32, device=dev)
+    pts = torch.empty(B * n, 3, dtype=torch.float32, device=dev)
+    dirs = torch.empty(B * n, 3, dtype=torch.float32, device=dev)
+    L.check(L.lib().fneus_core_geometry(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), B, n, float(sample_dist),
+                                        L.ptr(dists), L.ptr(mid_z), L.ptr(pts), L.ptr(dirs), L.stream_ptr()),
+            "fneus_core_geometry")
+    return dists, mid_z, pts, dirs
+
+
+# ---------------------------------------------------------------------------------------------
+# compositing
+# ---------------------------------------------------------------------------------------------
+class Composite(torch.autograd.Function):
+    """renderer.py:245-274,328-332,350-372 fused; differentiable in sdf, normals, rgb, inv_s, bg_alpha, bg_color.
+
+    Returns (color [B,3], weights [B,n_tot], weight_sum [B,1], weight_max [B,1], cdf [B,n_in],
+    inside [B,n_in], gradient_error [], hit_idx [B] int32, w_pair [B,2])."""
+
+    @staticmethod
+    def forward(ctx, sdf, normals, rgb, inv_s, bg_alpha, bg_color, dists, pts, rays_d, bg_rgb, n_in, n_out, car):
+        _need_cuda(sdf, "sdf")
+        dev = sdf.device
+        sdf_c, nrm_c, rgb_c = _f32c(sdf).reshape(-1), _f32c(normals).reshape(-1, 3), _f32c(rgb).reshape(-1, 3)
+        inv_c = _f32c(inv_s).reshape(-1)[:1].contiguous()
+        bga, bgc = _f32c(bg_alpha), _f32c(bg_color)
+        dists_c, pts_c, rd_c, bgr = _f32c(dists), _f32c(pts), _f32c(rays_d), _f32c(bg_rgb)
+        if bgr is not None:
+            bgr = bgr.reshape(-1)[:3].contiguous()
+        B = rd_c.shape[0]
+        n_tot = n_in + n_out
+        f32 = dict(dtype=torch.float32, device=dev)
+        color = torch.empty(B, 3, **f32)
+        weights = torch.empty(B, n_tot, **f32)
+        wsum = torch.empty(B, 1, **f32)
+        wmax = torch.empty(B, 1, **f32)
+        cdf = torch.empty(B, n_in, **f32)
+        inside = torch.empty(B, n_in, **f32)
+        eik = torch.empty(B, 2, **f32)
+        hit = torch.empty(B, dtype=torch.int32, device=dev)
+        wpair = torch.empty(B, 2, **f32)
+        L.check(L.lib().fneus_composite_fwd(
+            L.ptr(sdf_c), L.ptr(nrm_c), L.ptr(rgb_c), L.ptr(dists_c), L.ptr(pts_c), L.ptr(rd_c), L.ptr(bga),
+            L.ptr(bgc), L.ptr(bgr), B, n_in, n_out, L.ptr(inv_c), float(car), L.ptr(color), L.ptr(weights),
+            L.ptr(wsum), L.ptr(wmax), L.ptr(cdf), L.ptr(inside), L.ptr(eik), L.ptr(hit), L.ptr(wpair),
+            L.stream_ptr()), "fneus_composite_fwd")
+        tot = eik.sum(0)
+        denom = (tot[1] + 1e-5).reshape(1)
+        grad_err = (tot[0] / denom[0]).reshape(())
+        ctx.save_for_backward(sdf_c, nrm_c, rgb_c, inv_c, bga, bgc, dists_c, pts_c, rd_c, bgr, hit, denom)
+        ctx.dims = (B, n_in, n_out, float(car))
+        ctx.shapes = (sdf.shape, normals.shape, rgb.shape, inv_s.shape)
+        ctx.mark_non_differentiable(wmax, cdf, inside, hit)
+        ctx.set_materialize_grads(False)
+        return color, weights, wsum, wmax, cdf, inside, grad_err, hit, wpair
+
+    @staticmethod
+    def backward(ctx, d_color, d_weights, d_wsum, _wmax, _cdf, _inside, d_eik, _hit, d_wpair):
+        sdf_c, nrm_c, rgb_c, inv_c, bga, bgc, dists_c, pts_c, rd_c, bgr, hit, denom = ctx.saved_tensors
+        B, n_in, n_out, car = ctx.dims
+        d_sdf = torch.empty_like(sdf_c)
+        d_nrm = torch.empty_like(nrm_c)
+        d_rgb = torch.empty_like(rgb_c)
+        d_inv = torch.empty(B, dtype=torch.float32, device=sdf_c.device)
+        d_bga = torch.empty_like(bga) if bga is not None else None
+        d_bgc = torch.empty_like(bgc) if bgc is not None else None
+        d_eik_c = _f32c(d_eik).reshape(1) if d_eik is not None else None
+        L.check(L.lib().fneus_composite_bwd(
+            L.ptr(sdf_c), L.ptr(nrm_c), L.ptr(rgb_c), L.ptr(dists_c), L.ptr(pts_c), L.ptr(rd_c), L.ptr(bga),
+            L.ptr(bgc), L.ptr(bgr), B, n_in, n_out, L.ptr(inv_c), car, L.ptr(hit), L.ptr(_f32c(d_color)),
+            L.ptr(_f32c(d_weights)), L.ptr(_f32c(d_wsum)), L.ptr(_f32c(d_wpair)), L.ptr(d_eik_c), L.ptr(denom),
+            L.ptr(d_sdf), L.ptr(d_nrm), L.ptr(d_rgb), L.ptr(d_inv), L.ptr(d_bga), L.ptr(d_bgc), L.stream_ptr()),
+            "fneus_composite_bwd")
+        s_sdf, s_nrm, s_rgb, s_inv = ctx.shapes
+        d_inv_s = d_inv.sum().reshape(s_inv)
+        return (d_sdf.reshape(s_sdf), d_nrm.reshape(s_nrm), d_rgb.reshape(s_rgb), d_inv_s, d_bga, d_bgc,
+                None, None, None, None, None, None, None)

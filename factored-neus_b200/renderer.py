@@ -1,0 +1,205 @@
+"""Drop-in ``NeuSRenderer`` (reference: models/renderer.py:80-500) on the CUDA library.
+
+Same constructor kwargs, attribute names, method names and output dictionaries as the reference;
+the arithmetic runs in libfneus_b200.so through ``ops``.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class NeuSRenderer:
+    def __init__(self, n_samples, n_importance, n_outside, up_sample_steps, perturb, nerf=None, sdf_network=None,
+                 deviation_network=None, color_network=None, refColor_network=None, lvis_network=None,
+                 indiLgt_network=None, mateIllu_network=None):
+        self.nerf = nerf
+        self.sdf_network = sdf_network
+        self.deviation_network = deviation_network
+        self.color_network = color_network
+        self.refColor_network = refColor_network
+        self.lvis_network = lvis_network
+        self.indiLgt_network = indiLgt_network
+        self.mateIllu_network = mateIllu_network
+        self.n_samples = n_samples
+        self.n_importance = n_importance
+        self.n_outside = n_outside
+        self.up_sample_steps = up_sample_steps
+        self.perturb = perturb
+        self._tables = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _linspace(self, lo, hi, n, device):
+        """Small constant tables come from torch.linspace on the device under test."""
+        key = (float(lo), float(hi), int(n), str(device))
+        t = self._tables.get(key)
+        if t is None:
+            t = torch.linspace(lo, hi, n, device=device, dtype=torch.float32).contiguous()
+            self._tables[key] = t
+        return t
+
+    def _sdf_nograd(self, pts):
+        net = self.sdf_network
+        return ops.sdf_forward_nograd(net.cfg, net.flat_weights().detach(), pts, want_feat=False)[0]
+
+    # ------------------------------------------------------------------ sampling
+    def up_sample(self, rays_o, rays_d, z_vals, sdf, n_importance, inv_s):
+        """renderer.py:152-189."""
+        B, n = z_vals.shape
+        u = self._linspace(0.5 / n_importance, 1.0 - 0.5 / n_importance, n_importance, z_vals.device)
+        with torch.no_grad():
+            return ops.upsample_step(rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous(),
+                                     sdf.reshape(B, n).contiguous(), n_importance, float(inv_s), u)
+
+    def cat_z_vals(self, rays_o, rays_d, z_vals, new_z_vals, sdf, last=False):
+        """renderer.py:191-205 (merge of two sorted lists; the new SDF values ride along)."""
+        B, n = z_vals.shape
+        with torch.no_grad():
+            if last:
+                z, _ = ops.merge_sorted(z_vals.contiguous(), new_z_vals.contiguous())
+                return z, sdf
+            pts = ops.ray_points(rays_o.contiguous(), rays_d.contiguous(), new_z_vals.contiguous())
+            new_sdf = self._sdf_nograd(pts).reshape(B, -1)
+            return ops.merge_sorted(z_vals.contiguous(), new_z_vals.contiguous(), sdf.reshape(B, n).contiguous(),
+                                    new_sdf.contiguous())
+
+    def _hierarchical(self, rays_o, rays_d, z_vals):
+        B = z_vals.shape[0]
+        with torch.no_grad():
+            pts = ops.ray_points(rays_o, rays_d, z_vals)
+            sdf = self._sdf_nograd(pts).reshape(B, self.n_samples)
+            for i in range(self.up_sample_steps):
+                new_z = self.up_sample(rays_o, rays_d, z_vals, sdf, self.n_importance // self.up_sample_steps,
+                                       64 * 2 ** i)
+                z_vals, sdf = self.cat_z_vals(rays_o, rays_d, z_vals, new_z, sdf,
+                                              last=(i + 1 == self.up_sample_steps))
+        return z_vals
+
+    # ------------------------------------------------------------------ core
+    def render_core(self, rays_o, rays_d, z_vals, sample_dist, sdf_network, deviation_network, color_network,
+                    refColor_network, background_alpha=None, background_sampled_color=None, background_rgb=None,
+                    cos_anneal_ratio=0.0):
+        """renderer.py:208-389."""
+        B, n = z_vals.shape
+        dev = z_vals.device
+        rays_o, rays_d, z_vals = rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous()
+        dists, mid_z, pts, dirs = ops.core_geometry(rays_o, rays_d, z_vals, sample_dist)
+
+        sdf, feat, normals = sdf_network.value_feature_normal(pts, want_normal=True)
+        inv_s = deviation_network(torch.zeros([1, 3], device=dev))[:, :1].clip(1e-6, 1e6)       # [1,1]
+        rgb = color_network(pts, normals, dirs, feat)                                             # [B*n,3]
+
+        n_out = 0 if background_alpha is None else background_alpha.shape[1] - n
+        color, weights, wsum, wmax, cdf, inside, grad_err, hit_idx, w_pair = ops.Composite.apply(
+            sdf, normals, rgb, inv_s, background_alpha, background_sampled_color, dists, pts, rays_d,
+            background_rgb, n, n_out, float(cos_anneal_ratio))
+
+        # surface term (renderer.py:284-343) with fixed shapes: every ray evaluates RefColor at the two
+        # bracketing samples, rays without a sign change are masked to the reference's default of ones.
+        hit = hit_idx >= 0
+        idx = hit_idx.clamp(min=1).long()
+        base = torch.arange(B, device=dev) * n
+        rows = torch.stack([base + idx - 1, base + idx], dim=1).reshape(-1)                      # [2B]
+        r_rgb, r_spec, r_diff = self._ref_rows(refColor_network, pts, feat, dirs, normals, rows)
+        w0, w1 = w_pair[:, :1], w_pair[:, 1:]
+        den = w0 + w1
+        ones = torch.ones(B, 3, device=dev)
+
+        def blend(c):
+            c = c.reshape(B, 2, 3)
+            return torch.where(hit[:, None], (c[:, 0] * w0 + c[:, 1] * w1) / den, ones)
+
+        return {
+            "color": color,
+            "surface_color": blend(r_rgb),
+            "sdf_mask": hit,
+            "sdf": sdf,
+            "dists": dists,
+            "gradients": normals.reshape(B, n, 3),
+            "s_val": (1.0 / inv_s).expand(B * n, 1),
+            "mid_z_vals": mid_z,
+            "weights": weights,
+            "cdf": cdf,
+            "gradient_error": grad_err,
+            "inside_sphere": inside,
+            "specular_color": blend(r_spec),
+            "diffuse_color": blend(r_diff),
+        }
+
+    @staticmethod
+    def _ref_rows(net, pts, feat, dirs, normals, rows):
+        d = net(pts.index_select(0, rows), feat.index_select(0, rows), dirs.index_select(0, rows),
+                normals.index_select(0, rows))
+        return d["rgb"], d["specular_rgb"], d["diffuse_rgb"]
+
+    # ------------------------------------------------------------------ render
+    def render(self, rays_o, rays_d, near, far, perturb_overwrite=-1, background_rgb=None, cos_anneal_ratio=0.0):
+        """renderer.py:391-500."""
+        if not rays_o.is_cuda:
+            raise RuntimeError("factored-neus_b200.NeuSRenderer.render needs CUDA tensors (no CPU fallback)")
+        dev = rays_o.device
+        rays_o, rays_d = rays_o.float().contiguous(), rays_d.float().contiguous()
+        batch_size = len(rays_o)
+        sample_dist = 2.0 / self.n_samples
+        z_vals = near + (far - near) * self._linspace(0.0, 1.0, self.n_samples, dev)[None, :]
+
+        z_vals_outside = None
+        if self.n_outside > 0:
+            z_vals_outside = self._linspace(1e-3, 1.0 - 1.0 / (self.n_outside + 1.0), self.n_outside, dev)
+
+        n_samples = self.n_samples
+        perturb = self.perturb
+        if perturb_overwrite >= 0:
+            perturb = perturb_overwrite
+        if perturb > 0:
+            t_rand = torch.rand([batch_size, 1], device=dev) - 0.5
+            z_vals = z_vals + t_rand * 2.0 / self.n_samples
+            if self.n_outside > 0:
+                mids = 0.5 * (z_vals_outside[..., 1:] + z_vals_outside[..., :-1])
+                upper = torch.cat([mids, z_vals_outside[..., -1:]], -1)
+                lower = torch.cat([z_vals_outside[..., :1], mids], -1)
+                t_rand = torch.rand([batch_size, z_vals_outside.shape[-1]], device=dev)
+                z_vals_outside = lower[None, :] + (upper - lower)[None, :] * t_rand
+        if self.n_outside > 0:
+            z_vals_outside = far / torch.flip(z_vals_outside, dims=[-1]) + 1.0 / self.n_samples
+
+        background_alpha = None
+        background_sampled_color = None
+        z_vals = z_vals.contiguous()
+        if self.n_importance > 0:
+            z_vals = self._hierarchical(rays_o, rays_d, z_vals)
+            n_samples = self.n_samples + self.n_importance
+
+        if self.n_outside > 0:
+            zo = z_vals_outside.expand(batch_size, self.n_outside).contiguous()
+            z_vals_feed, _ = ops.merge_sorted(z_vals, zo)
+            ret_outside = self.render_core_outside(rays_o, rays_d, z_vals_feed, sample_dist, self.nerf)
+            background_sampled_color = ret_outside["sampled_color"]
+            background_alpha = ret_outside["alpha"]
+
+        ret_fine = self.render_core(rays_o, rays_d, z_vals, sample_dist, self.sdf_network, self.deviation_network,
+                                    self.color_network, self.refColor_network, background_rgb=background_rgb,
+                                    background_alpha=background_alpha,
+                                    background_sampled_color=background_sampled_color,
+                                    cos_anneal_ratio=cos_anneal_ratio)
+        weights = ret_fine["weights"]
+        s_val = ret_fine["s_val"].reshape(batch_size, n_samples).mean(dim=-1, keepdim=True)
+        return {
+            "color_fine": ret_fine["color"],
+            "surface_color": ret_fine["surface_color"],
+            "sdf_mask": ret_fine["sdf_mask"],
+            "s_val": s_val,
+            "cdf_fine": ret_fine["cdf"],
+            "weight_sum": weights.sum(dim=-1, keepdim=True),
+            "weight_max": torch.max(weights, dim=-1, keepdim=True)[0],
+            "gradients": ret_fine["gradients"],
+            "weights": weights,
+            "gradient_error": ret_fine["gradient_error"],
+            "inside_sphere": ret_fine["inside_sphere"],
+            "specular_color": ret_fine["specular_color"],
+            "diffuse_color": ret_fine["diffuse_color"],
+        }
+
+    def render_core_outside(self, rays_o, rays_d, z_vals, sample_dist, nerf, background_rgb=None):
+        raise NotImplementedError("outside NeRF path is not wired yet")

@@ -1,0 +1,166 @@
+/* fneus.h -- C ABI of libfneus_b200.so: the B200-native (sm_100a) kernels behind the Factored-NeuS
+ * per-ray volume-rendering hot path.
+ *
+ * The reference has no FFI layer: its seam is the Python class NeuSRenderer (models/renderer.py:80-110) and
+ * the nn.Module fields (models/fields.py).  Each entry point below replaces the ATen op chain of one
+ * reference function (cited per declaration) and is what the reference-side binding (INTEGRATION.md:
+ * a ctypes stub inside models/renderer.py / models/fields.py) would call.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to FP32 unless stated; tensors are row-major and contiguous;
+ *  - the callee never allocates, frees or synchronises; workspaces are sized by the *_floats queries and
+ *    owned by the caller; every call takes the CUDA stream to launch on (void* = cudaStream_t);
+ *  - return value: 0 = ok, otherwise an fneus_status (never throws, never exits);
+ *    fneus_status_string() decodes it;
+ *  - weight packs are flat FP32 buffers of EFFECTIVE weights (weight-norm g*v/|v| already applied by the
+ *    host), layer after layer: W_l [out_l, in_l] row-major then b_l [out_l]; gradient packs have the same
+ *    layout and are ACCUMULATED into (the caller zero-fills them).
+ */
+#ifndef FNEUS_H_
+#define FNEUS_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  FNEUS_OK = 0,
+  FNEUS_ERR_BAD_SHAPE = 1,
+  FNEUS_ERR_MISALIGNED = 2,
+  FNEUS_ERR_UNSUPPORTED = 3,
+  FNEUS_ERR_NULL = 4,
+  FNEUS_ERR_WORKSPACE = 5,
+  FNEUS_ERR_CUDA_BASE = 1000 /* 1000 + cudaError_t */
+} fneus_status;
+
+const char* fneus_status_string(int status);
+int fneus_abi_version(void);
+int fneus_num_sms(void);
+
+/* ---- SDF network (fields.py:9-111) ------------------------------------------------------------ */
+typedef struct {
+  int d_in;       /* 3 */
+  int d_hidden;   /* 256 */
+  int n_layers;   /* 8 hidden layers -> n_layers+1 linears */
+  int d_out;      /* 257: col 0 = sdf, 1.. = feature */
+  int multires;   /* 6 */
+  int skip_layer; /* 4: input of this linear is cat([h, PE(x)])/sqrt(2); -1 = none */
+  float scale;    /* 1.0 */
+  float beta;     /* Softplus beta = 100 */
+} fneus_sdf_cfg;
+
+long long fneus_sdf_pack_floats(const fneus_sdf_cfg* cfg);
+long long fneus_sdf_saved_floats(const fneus_sdf_cfg* cfg, long long n_points);
+long long fneus_sdf_scratch_floats(const fneus_sdf_cfg* cfg, long long n_points);
+
+/* SDFNetwork.forward / .sdf (fields.py:74-95), no graph.  sdf_out [n]; feat_out [n, d_out-1] or NULL
+ * (sdf only).  Points are processed in chunks that fit scratch_floats. */
+int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long n_points,
+                  float* sdf_out, float* feat_out, float* scratch, long long scratch_floats, void* stream);
+
+/* SDFNetwork.forward + .gradient (fields.py:74-111) in one pass: value, feature and the analytic
+ * normal d sdf/d x [n,3] (normal_out NULL = value only); `saved` keeps the activations the backward needs. */
+int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long n_points,
+                       float* sdf_out, float* feat_out, float* normal_out, float* saved, float* scratch,
+                       void* stream);
+
+/* Backward of fneus_sdf_fwd_grad incl. the double-backward through the normal (autograd of fields.py:100-111
+ * with create_graph=True).  Any of d_sdf [n], d_feat [n,d_out-1], d_normal [n,3] may be NULL.
+ * Destroys `saved`. */
+int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long n_points,
+                  const float* d_sdf, const float* d_feat, const float* d_normal, float* saved, float* scratch,
+                  float* d_wpack, void* stream);
+
+/* ---- ReLU MLPs: RenderingNetwork (fields.py:114-175), RefColor (fields.py:271-335), NeRF (fields.py:178-259)
+ * share one description: first-layer input = [generated block | feature block]. ------------------- */
+typedef struct {
+  int d_feature;     /* 256 */
+  int d_hidden;      /* 256 */
+  int n_layers;      /* 4 hidden -> n_layers+1 linears */
+  int d_out;         /* 3 */
+  int multires_view; /* 4 */
+} fneus_color_cfg;
+
+long long fneus_color_pack_floats(const fneus_color_cfg* cfg);
+long long fneus_color_saved_floats(const fneus_color_cfg* cfg, long long n_points);
+long long fneus_color_scratch_floats(const fneus_color_cfg* cfg, long long n_points);
+
+/* RenderingNetwork.forward, mode 'idr', squeeze_out (fields.py:150-175): rgb_out [n,3]. saved may be NULL
+ * (inference; scratch then also holds the activations). */
+int fneus_color_fwd(const fneus_color_cfg* cfg, const float* wpack, const float* points, const float* normals,
+                    const float* view_dirs, const float* feats, long long n_points, float* rgb_out,
+                    float* saved, float* scratch, void* stream);
+/* Backward: d_rgb [n,3] -> d_normals [n,3], d_feats [n,d_feature] (overwritten), d_wpack (accumulated). */
+int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float* points, const float* normals,
+                    const float* view_dirs, const float* feats, long long n_points, const float* rgb,
+                    const float* d_rgb, float* d_normals, float* d_feats, float* saved, float* scratch,
+                    float* d_wpack, void* stream);
+
+/* RefColor.forward (fields.py:303-335).  Pack order: net_cd.{0,2,4,6,8}, viewdir_mlp.{0..3}, net_cs.0.
+ * Outputs rgb/specular_rgb/diffuse_rgb [n,3]. */
+typedef struct {
+  int d_feature; /* 256 */
+  int d_hidden;  /* 256 */
+} fneus_ref_cfg;
+long long fneus_ref_pack_floats(const fneus_ref_cfg* cfg);
+long long fneus_ref_saved_floats(const fneus_ref_cfg* cfg, long long n_points);
+long long fneus_ref_scratch_floats(const fneus_ref_cfg* cfg, long long n_points);
+int fneus_ref_fwd(const fneus_ref_cfg* cfg, const float* wpack, const float* points, const float* feats,
+                  const float* dirs, const float* normals, long long n_points, float* rgb_out, float* spec_out,
+                  float* diff_out, float* saved, float* scratch, void* stream);
+int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* points, const float* feats,
+                  const float* dirs, const float* normals, long long n_points, const float* d_rgb,
+                  const float* d_spec, const float* d_diff, float* d_feats, float* d_normals, float* saved,
+                  float* scratch, float* d_wpack, void* stream);
+
+/* ---- sampling (renderer.py:43-77,152-205, 391-447) -------------------------------------------- */
+/* pts[b*n+j] = o[b] + d[b]*z[b,j]   (renderer.py:159,194,428) */
+int fneus_ray_points(const float* rays_o, const float* rays_d, const float* z, long long n_rays, int n,
+                     float* pts_out, void* stream);
+/* One hierarchical up-sampling step (NeuSRenderer.up_sample + sample_pdf(det=True)): z, sdf [B,n] ->
+ * new_z [B,k].  u_table [k] = torch.linspace(0.5/k, 1-0.5/k, k) supplied by the host (bit pattern of the
+ * device's own linspace).  Optional debug outputs cdf_out [B,n], inds_out [B,k] (int64). */
+int fneus_upsample_step(const float* rays_o, const float* rays_d, const float* z, const float* sdf,
+                        long long n_rays, int n, int k, float inv_s, const float* u_table, float* new_z,
+                        float* cdf_out, long long* inds_out, void* stream);
+/* Inverse-CDF alone (renderer.py:64-77): searchsorted(right=True) + interpolation on a SUPPLIED cdf. */
+int fneus_inverse_cdf(const float* bins, const float* cdf, const float* u_table, long long n_rays, int n, int k,
+                      float* samples_out, long long* inds_out, void* stream);
+/* cat_z_vals (renderer.py:191-205) as a merge of two sorted lists; carries sdf along when both sdf and
+ * new_sdf are given (NULL,NULL = last step / depth-only merge). */
+int fneus_merge_sorted(const float* z, const float* new_z, const float* sdf, const float* new_sdf,
+                       long long n_rays, int n, int k, float* z_out, float* sdf_out, void* stream);
+/* Section geometry of render_core (renderer.py:224-236): dists, mid_z, mid points [B*n,3], dirs [B*n,3]. */
+int fneus_core_geometry(const float* rays_o, const float* rays_d, const float* z, long long n_rays, int n,
+                        float sample_dist, float* dists, float* mid_z, float* pts, float* dirs, void* stream);
+
+/* ---- alpha / transmittance / compositing (renderer.py:245-274,350-372) -------------------------- */
+/* n_in = inside samples (128), n_out = extra outside samples (0 or 32).  inv_s: DEVICE scalar
+ * clip(exp(10*variance),1e-6,1e6) (renderer.py:245; no host sync).   bg_alpha [B,n_in+n_out],
+ * bg_color [B,n_in+n_out,3] (NULL when n_out==0 and no background model), bg_rgb [3] or NULL.
+ * Outputs: color [B,3], weights [B,n_in+n_out], weight_sum [B], weight_max [B], cdf [B,n_in],
+ * inside [B,n_in], eik_part [B,2] (sum relax*(|g|-1)^2, sum relax), hit_idx [B] int32 (-1 = no surface hit),
+ * w_pair [B,2] (inside-weights at hit_idx-1, hit_idx, +1e-5; 1 when no hit). */
+int fneus_composite_fwd(const float* sdf, const float* normals, const float* rgb, const float* dists,
+                        const float* pts, const float* rays_d, const float* bg_alpha, const float* bg_color,
+                        const float* bg_rgb, long long n_rays, int n_in, int n_out, const float* inv_s,
+                        float cos_anneal_ratio, float* color, float* weights, float* weight_sum,
+                        float* weight_max, float* cdf, float* inside, float* eik_part, int* hit_idx,
+                        float* w_pair, void* stream);
+/* Backward.  Upstream: d_color [B,3], d_weights [B,n_in+n_out] (NULL ok), d_weight_sum [B] (NULL ok),
+ * d_w_pair [B,2] (NULL ok), d_eik scalar pointer (device, d loss / d gradient_error; NULL ok) with
+ * eik_denom = sum relax + 1e-5 over the WHOLE batch (device scalar).
+ * Outputs: d_sdf [B*n_in], d_normals [B*n_in,3], d_rgb [B*n_in,3], d_inv_s [B] (per-ray partials),
+ * d_bg_alpha / d_bg_color (NULL ok). */
+int fneus_composite_bwd(const float* sdf, const float* normals, const float* rgb, const float* dists,
+                        const float* pts, const float* rays_d, const float* bg_alpha, const float* bg_color,
+                        const float* bg_rgb, long long n_rays, int n_in, int n_out, const float* inv_s,
+                        float cos_anneal_ratio, const int* hit_idx, const float* d_color,
+                        const float* d_weights, const float* d_weight_sum, const float* d_w_pair,
+                        const float* d_eik, const float* eik_denom, float* d_sdf, float* d_normals,
+                        float* d_rgb, float* d_inv_s, float* d_bg_alpha, float* d_bg_color, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FNEUS_H_ */

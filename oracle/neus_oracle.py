@@ -311,6 +311,25 @@ def first_hit(sdf_bn, inside):
     return mask, idx
 
 
+def neus_alpha(sdf, grads, dirs, dists, inv_s, cos_anneal_ratio):
+    """renderer.py:248-268: sdf [N,1], grads/dirs [N,3], dists [B,n] -> (alpha [B,n], prev_cdf [N,1])."""
+    B, n = dists.shape
+    true_cos = (dirs * grads).sum(-1, keepdim=True)
+    iter_cos = -(torch.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal_ratio)
+                 + torch.relu(-true_cos) * cos_anneal_ratio)
+    d1 = dists.reshape(-1, 1)
+    c_prev = torch.sigmoid((sdf - iter_cos * d1 * 0.5) * inv_s)
+    c_next = torch.sigmoid((sdf + iter_cos * d1 * 0.5) * inv_s)
+    alpha = ((c_prev - c_next + 1e-5) / (c_prev + 1e-5)).reshape(B, n).clip(0.0, 1.0)
+    return alpha, c_prev
+
+
+def transmittance_weights(alpha):
+    """renderer.py:360: w = alpha * exclusive_cumprod(1 - alpha + 1e-7)."""
+    B = alpha.shape[0]
+    return alpha * torch.cumprod(torch.cat([torch.ones(B, 1, dtype=alpha.dtype), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+
+
 def render_core(P: Dict[str, Params], rays_o, rays_d, z, sample_dist, background_alpha=None,
                 background_sampled_color=None, background_rgb=None, cos_anneal_ratio=0.0,
                 sdf_conf=SDF_CONF, color_conf=COLOR_CONF):
@@ -327,13 +346,7 @@ def render_core(P: Dict[str, Params], rays_o, rays_d, z, sample_dist, background
     grads = sdf_gradient(P["sdf"], pts, sdf_conf)
     inv_s = inv_s_of(P["var"]["variance"]).reshape(1, 1)
 
-    true_cos = (dirs * grads).sum(-1, keepdim=True)
-    iter_cos = -(torch.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal_ratio)
-                 + torch.relu(-true_cos) * cos_anneal_ratio)
-    d1 = dists.reshape(-1, 1)
-    c_prev = torch.sigmoid((sdf - iter_cos * d1 * 0.5) * inv_s)
-    c_next = torch.sigmoid((sdf + iter_cos * d1 * 0.5) * inv_s)
-    alpha = ((c_prev - c_next + 1e-5) / (c_prev + 1e-5)).reshape(B, n).clip(0.0, 1.0)
+    alpha, c_prev = neus_alpha(sdf, grads, dirs, dists, inv_s, cos_anneal_ratio)
 
     r = torch.linalg.norm(pts, ord=2, dim=-1).reshape(B, n)
     inside = (r < 1.0).to(dt)

@@ -1,0 +1,87 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/fneus.h declares, host-only
+queries work, and the drop-in modules keep the reference's parameter names/shapes.  No kernels are launched."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import factored_neus_b200 as fn
+from factored_neus_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+syn = fn.synthetic
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "fneus.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(fneus_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(L.LIB_PATH), "run __graft_entry__.build() first"
+    h = ctypes.CDLL(L.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(h, s), "libfneus_b200.so does not export %s" % s
+    assert set(L.declared_symbols()) == set(syms), "ctypes table and header disagree: %s" % (
+        set(L.declared_symbols()) ^ set(syms))
+
+
+def test_status_strings_and_version():
+    lib = L.lib()
+    assert lib.fneus_abi_version() >= 1
+    assert lib.fneus_status_string(0) == b"ok"
+    assert b"null" in lib.fneus_status_string(4)
+    with pytest.raises(RuntimeError):
+        L.check(3, "unit")
+
+
+def test_pack_sizes_match_reference_parameter_counts():
+    lib = L.lib()
+    sdf = fn.SDFNetwork(**syn.SDF_CONF)
+    col = fn.RenderingNetwork(**syn.COLOR_CONF)
+    ref = fn.RefColor()
+    # 524 544 weights + biases for the SDF net; colour 273 414 params (incl. weight_g);
+    assert lib.fneus_sdf_pack_floats(sdf.cfg) == sdf.flat_weights().numel() == 524544 + 8 * 256 - 39 + 257
+    assert lib.fneus_color_pack_floats(col.cfg) == col.flat_weights().numel()
+    assert lib.fneus_ref_pack_floats(ref.cfg) == ref.flat_weights().numel() == 543492
+    assert lib.fneus_sdf_saved_floats(sdf.cfg, 10) > 0 and lib.fneus_sdf_scratch_floats(sdf.cfg, 10) > 0
+    bad = L.SdfCfg(d_in=3, d_hidden=256, n_layers=40, d_out=257, multires=6, skip_layer=4, scale=1.0, beta=100.0)
+    assert lib.fneus_sdf_pack_floats(bad) == -1
+
+
+def test_state_dict_keys_match_reference_layout():
+    st = syn.scene_states(seed=4)
+    sdf = fn.SDFNetwork(**syn.SDF_CONF)
+    col = fn.RenderingNetwork(**syn.COLOR_CONF)
+    ref = fn.RefColor()
+    var = fn.SingleVarianceNetwork(0.3)
+    for mod, key in ((sdf, "sdf"), (col, "color"), (ref, "ref"), (var, "var")):
+        sd = mod.state_dict()
+        assert set(sd.keys()) == set(st[key].keys()), key
+        for k in sd:
+            assert tuple(sd[k].shape) == tuple(st[key][k].shape), (key, k)
+        mod.load_state_dict(st[key])
+    assert sdf.lin3.weight_v.shape == (217, 256) and sdf.lin8.weight_g.shape == (257, 1)
+    assert sum(p.numel() for p in sdf.parameters()) == 529076 + 0  # SURVEY.md 8a-2 (weights+biases) + weight_g
+
+
+def test_geometric_init_follows_reference_statistics():
+    torch.manual_seed(0)
+    sdf = fn.SDFNetwork(**syn.SDF_CONF)
+    assert float(sdf.lin0.weight_v[:, 3:].abs().max()) == 0.0
+    assert float(sdf.lin4.weight_v[:, -36:].abs().max()) == 0.0
+    assert abs(float(sdf.lin8.weight_v.mean()) - (3.14159265 ** 0.5) / 16.0) < 1e-3
+    assert float(sdf.lin8.bias[0]) == -0.5
+    w = sdf.lin2.effective()
+    assert torch.allclose(w, sdf.lin2.weight_v, atol=1e-6)
+
+
+def test_no_cpu_fallback():
+    sdf = fn.SDFNetwork(**syn.SDF_CONF)
+    with pytest.raises(RuntimeError):
+        sdf.sdf(torch.zeros(4, 3))

@@ -1,0 +1,321 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+fixtures.  Tolerances follow BASELINE.json north_star: FP32 path <= 1e-4 max-abs on colours, SDF gradients
+and weight gradients; searchsorted indices bit-exact given identical CDFs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import factored_neus_b200 as fn
+from factored_neus_b200 import ops
+from oracle import neus_oracle as O
+from util import assert_close, build_modules, compare_param_grads, grad_params, max_err, syn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FP32_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def states():
+    return syn.scene_states(seed=4, jitter=0.03)
+
+
+def _golden(golden_dir, name):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def _cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------ sampling
+def test_searchsorted_indices_bit_exact(golden_dir):
+    g = _golden(golden_dir, "sampling.npz")
+    u = _cu(g["u"])
+    for i in range(4):
+        bins, cdf = _cu(g["z%d" % i]), _cu(g["cdf%d" % i])
+        samples, inds = ops.inverse_cdf(bins, cdf, u)
+        assert np.array_equal(inds.cpu().numpy(), g["inds%d" % i]), "indices differ at step %d" % i
+        ref, _ = O.invert_cdf(torch.from_numpy(g["z%d" % i]), torch.from_numpy(g["cdf%d" % i]),
+                              torch.from_numpy(g["u"]).expand(bins.shape[0], -1))
+        assert_close(samples, ref, 1e-6, "inverse-cdf samples %d" % i)
+
+
+def test_inverse_cdf_random_bit_exact():
+    """Larger randomised check incl. flat (repeated) CDF entries and the n=512,k=32 lvis shape."""
+    gen = torch.Generator().manual_seed(3)
+    for B, n, k in ((257, 64, 16), (64, 112, 16), (33, 512, 32), (5, 2, 4)):
+        w = torch.rand(B, n - 1, generator=gen)
+        w[w < 0.3] = 0.0
+        cdf = torch.cat([torch.zeros(B, 1), torch.cumsum(w / w.sum(-1, keepdim=True).clamp_min(1e-9), -1)], -1)
+        bins = torch.sort(torch.rand(B, n, generator=gen), -1)[0]
+        u = torch.linspace(0.5 / k, 1 - 0.5 / k, k)
+        ref_s, ref_i = O.invert_cdf(bins, cdf, u.expand(B, k))
+        s, i = ops.inverse_cdf(bins.to(DEV), cdf.to(DEV), u.to(DEV))
+        assert torch.equal(i.cpu(), ref_i), "indices differ for shape %s" % ((B, n, k),)
+        assert_close(s, ref_s, 1e-6, "samples %s" % ((B, n, k),))
+
+
+def test_upsample_and_merge_chain(golden_dir):
+    g = _golden(golden_dir, "sampling.npz")
+    o, d = _cu(g["o"]), _cu(g["d"])
+    u = _cu(g["u"])
+    for i in range(4):
+        z, sdf = _cu(g["z%d" % i]), _cu(g["sdf%d" % i])
+        new_z, cdf, inds = ops.upsample_step(o, d, z, sdf, 16, 64 * 2 ** i, u, debug=True)
+        assert_close(cdf, g["cdf%d" % i], 2e-6, "cdf %d" % i)
+        # interpolation in near-empty bins amplifies cdf rounding: compare on the bins' scale
+        assert_close(new_z, g["newz%d" % i], 2e-4, "new z %d" % i)
+        frac_same = (inds.cpu().numpy() == g["inds%d" % i]).mean()
+        assert frac_same > 0.99, "only %.3f of indices agree" % frac_same
+        nz = _cu(g["newz%d" % i])
+        if i < 3:
+            pts = ops.ray_points(o, d, nz)
+            assert_close(pts.reshape(-1, 16, 3), (g["o"][:, None, :] + g["d"][:, None, :] * g["newz%d" % i][..., None]),
+                         0.0, "ray points")
+            # carry the reference's new sdf values through the merge
+            ref_new_sdf = O.sdf_value(syn.scene_states(seed=4, jitter=0.03)["sdf"],
+                                      torch.from_numpy(pts.cpu().numpy())).reshape(-1, 16)
+            zz, ss = ops.merge_sorted(z, nz, sdf, ref_new_sdf.to(DEV))
+            assert_close(ss, g["sdf%d" % (i + 1)], 2e-6, "merged sdf %d" % i)
+        else:
+            zz, _ = ops.merge_sorted(z, nz)
+        assert np.array_equal(zz.cpu().numpy(), g["z%d" % (i + 1)]), "merged z %d" % i
+
+
+def test_merge_sorted_properties():
+    gen = torch.Generator().manual_seed(0)
+    for B, n, k in ((1000, 64, 16), (7, 128, 32), (3, 1, 1)):
+        a = torch.sort(torch.rand(B, n, generator=gen), -1)[0]
+        b = torch.sort(torch.rand(B, k, generator=gen), -1)[0]
+        b[:, 0] = a[:, 0]                                           # ties
+        sa, sb = torch.rand(B, n, generator=gen), torch.rand(B, k, generator=gen)
+        z, s = ops.merge_sorted(a.to(DEV), b.to(DEV), sa.to(DEV), sb.to(DEV))
+        ref, idx = torch.sort(torch.cat([a, b], -1), -1, stable=True)
+        assert torch.equal(z.cpu(), ref)
+        assert torch.equal(s.cpu(), torch.cat([sa, sb], -1).gather(-1, idx))
+
+
+# ------------------------------------------------------------------------------------------ fields
+def test_fields_forward(golden_dir, states):
+    g = _golden(golden_dir, "fields.npz")
+    m = build_modules(states, DEV)
+    x, v = _cu(g["x"]), _cu(g["v"])
+    with torch.no_grad():
+        out = m["sdf"](x)
+        assert_close(out, g["sdf_out"], 1e-5, "sdf forward (no-grad path)")
+        assert_close(m["sdf"].sdf(x), g["sdf_out"][:, :1], 1e-5, "sdf() (no-grad path)")
+    sdf, feat, nrm = m["sdf"].value_feature_normal(x)
+    assert_close(sdf, g["sdf_out"][:, :1], 1e-5, "sdf value")
+    assert_close(feat, g["sdf_out"][:, 1:], 1e-5, "sdf feature")
+    assert_close(nrm, g["grad"], 2e-5, "sdf normal")
+    assert_close(m["sdf"].gradient(x), g["grad"][:, None, :], 2e-5, "sdf.gradient")
+    rgb = m["color"](x, _cu(g["grad"]), v, _cu(g["sdf_out"][:, 1:]))
+    assert_close(rgb, g["rgb"], 1e-5, "colour")
+    rd = m["ref"](x, _cu(g["sdf_out"][:, 1:]), v, _cu(g["grad"]))
+    assert_close(rd["rgb"], g["ref_rgb"], 1e-5, "refcolor rgb")
+    assert_close(rd["specular_rgb"], g["ref_spec"], 1e-5, "refcolor specular")
+    assert_close(rd["diffuse_rgb"], g["ref_diff"], 1e-5, "refcolor diffuse")
+
+
+@pytest.mark.parametrize("N", [1, 130, 1000])
+def test_sdf_backward_incl_double_backward(states, N):
+    """d/dW of a random functional of (sdf, feature, normal) -- the normal term is the second-order path
+    (SoftplusBackwardBackward in the reference)."""
+    gen = torch.Generator().manual_seed(N)
+    x = (torch.rand(N, 3, generator=gen) * 2 - 1)
+    c_s, c_f, c_n = torch.randn(N, 1, generator=gen), torch.randn(N, 256, generator=gen) * 0.1, \
+        torch.randn(N, 3, generator=gen)
+    P = grad_params(states)
+    out = O.sdf_forward(P["sdf"], x)
+    nrm = O.sdf_gradient(P["sdf"], x)
+    ((out[:, :1] * c_s).sum() + (out[:, 1:] * c_f).sum() + (nrm * c_n).sum()).backward()
+    m = build_modules(states, DEV)
+    sdf, feat, n2 = m["sdf"].value_feature_normal(x.to(DEV))
+    ((sdf * c_s.to(DEV)).sum() + (feat * c_f.to(DEV)).sum() + (n2 * c_n.to(DEV)).sum()).backward()
+    scale = max(1.0, max(float(t.grad.abs().max()) for t in P["sdf"].values()))
+    compare_param_grads(m, P, ["sdf"], FP32_TOL * scale, 1e-4, "sdf N=%d" % N)
+
+
+def test_sdf_backward_value_only(states):
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.rand(300, 3, generator=gen) * 2 - 1)
+    c = torch.randn(300, 257, generator=gen) * 0.1
+    P = grad_params(states)
+    (O.sdf_forward(P["sdf"], x) * c).sum().backward()
+    m = build_modules(states, DEV)
+    (m["sdf"](x.to(DEV)) * c.to(DEV)).sum().backward()
+    scale = max(1.0, max(float(t.grad.abs().max()) for t in P["sdf"].values()))
+    compare_param_grads(m, P, ["sdf"], FP32_TOL * scale, 1e-4, "sdf value-only")
+
+
+def test_color_and_refcolor_backward(states):
+    gen = torch.Generator().manual_seed(9)
+    N = 300
+    x = torch.rand(N, 3, generator=gen) * 2 - 1
+    v = torch.nn.functional.normalize(torch.randn(N, 3, generator=gen), dim=-1)
+    nrm = torch.randn(N, 3, generator=gen)
+    feat = torch.randn(N, 256, generator=gen) * 0.3
+    c = torch.randn(N, 3, generator=gen)
+    P = grad_params(states)
+    n_o, f_o = nrm.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    (O.color_forward(P["color"], x, n_o, v, f_o) * c).sum().backward()
+    m = build_modules(states, DEV)
+    n_g, f_g = nrm.to(DEV).requires_grad_(True), feat.to(DEV).requires_grad_(True)
+    (m["color"](x.to(DEV), n_g, v.to(DEV), f_g) * c.to(DEV)).sum().backward()
+    assert_close(n_g.grad, n_o.grad, FP32_TOL, "colour d_normals")
+    assert_close(f_g.grad, f_o.grad, FP32_TOL, "colour d_features")
+    compare_param_grads(m, P, ["color"], FP32_TOL, 1e-4, "colour")
+
+    n_o, f_o = nrm.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    r, s, d = O.refcolor_forward(P["ref"], x, f_o, v, n_o)
+    c2, c3 = torch.randn(N, 3, generator=gen), torch.randn(N, 3, generator=gen)
+    ((r * c).sum() + (s * c2).sum() + (d * c3).sum()).backward()
+    n_g, f_g = nrm.to(DEV).requires_grad_(True), feat.to(DEV).requires_grad_(True)
+    rd = m["ref"](x.to(DEV), f_g, v.to(DEV), n_g)
+    ((rd["rgb"] * c.to(DEV)).sum() + (rd["specular_rgb"] * c2.to(DEV)).sum()
+     + (rd["diffuse_rgb"] * c3.to(DEV)).sum()).backward()
+    assert_close(n_g.grad, n_o.grad, FP32_TOL, "refcolor d_normals", rtol=1e-4)
+    assert_close(f_g.grad, f_o.grad, FP32_TOL, "refcolor d_features", rtol=1e-4)
+    compare_param_grads(m, P, ["ref"], FP32_TOL, 1e-4, "refcolor")
+
+
+# ------------------------------------------------------------------------------------------ composite
+@pytest.mark.parametrize("n_out,car,use_bg_rgb", [(0, 1.0, False), (0, 0.3, True), (32, 0.3, False)])
+def test_composite_fwd_bwd(n_out, car, use_bg_rgb):
+    gen = torch.Generator().manual_seed(11 + n_out)
+    B, n = 37, 128
+    o, d, near, far = syn.make_rays(B, seed=3)
+    z = torch.sort(near + (far - near) * torch.rand(B, n, generator=gen), -1)[0]
+    dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((B, 1), 2.0 / 64)], -1)
+    pts = (o[:, None, :] + d[:, None, :] * (z + dists * 0.5)[..., None]).reshape(-1, 3)
+    sdf = (pts.norm(dim=-1, keepdim=True) - 0.5 + 0.02 * torch.randn(B * n, 1, generator=gen))
+    nrm = torch.nn.functional.normalize(pts, dim=-1) * (1 + 0.2 * torch.randn(B * n, 1, generator=gen))
+    rgb = torch.rand(B * n, 3, generator=gen)
+    var = torch.tensor(0.3)
+    bga = torch.rand(B, n + n_out, generator=gen) * 0.2 if n_out else None
+    bgc = torch.rand(B, n + n_out, 3, generator=gen) if n_out else None
+    bgr = torch.tensor([[0.7, 0.8, 0.9]]) if use_bg_rgb else None
+    c_col, c_w = torch.randn(B, 3, generator=gen), torch.randn(B, n + n_out, generator=gen) * 0.1
+    c_pair = torch.randn(B, 2, generator=gen)
+
+    def run_oracle():
+        leaves = [t.clone().requires_grad_(True) for t in (sdf, nrm, rgb, var)]
+        bl = [t.clone().requires_grad_(True) for t in (bga, bgc)] if n_out else [None, None]
+        s_, n_, c_, v_ = leaves
+        inv_s = O.inv_s_of(v_).reshape(1, 1)
+        dirs = d[:, None, :].expand(B, n, 3).reshape(-1, 3)
+        alpha, c_prev = O.neus_alpha(s_, n_, dirs, dists, inv_s, car)
+        r = pts.norm(dim=-1).reshape(B, n)
+        inside, relax = (r < 1.0).float(), (r < 1.2).float()
+        hit, idx = O.first_hit(s_.reshape(B, n).detach(), inside)
+        w_in = O.transmittance_weights(alpha * inside)
+        ii = idx.clamp_min(1)
+        pair = torch.stack([w_in.gather(1, (ii - 1)[:, None]), w_in.gather(1, ii[:, None])], 1).reshape(B, 2) + 1e-5
+        pair = torch.where(hit[:, None], pair, torch.ones_like(pair))
+        col = c_.reshape(B, n, 3)
+        if n_out:
+            alpha = torch.cat([alpha * inside + bl[0][:, :n] * (1 - inside), bl[0][:, n:]], -1)
+            col = torch.cat([col * inside[..., None] + bl[1][:, :n] * (1 - inside)[..., None], bl[1][:, n:]], 1)
+        w = O.transmittance_weights(alpha)
+        color = (col * w[..., None]).sum(1)
+        if bgr is not None:
+            color = color + bgr * (1 - w.sum(-1, keepdim=True))
+        g3 = n_.reshape(B, n, 3)
+        eik = (relax * (g3.norm(dim=-1) - 1) ** 2).sum() / (relax.sum() + 1e-5)
+        loss = (color * c_col).sum() + (w * c_w).sum() + 0.7 * eik + (pair * c_pair).sum() + w.sum() * 0.3
+        loss.backward()
+        return dict(color=color, weights=w, cdf=c_prev.reshape(B, n), inside=inside, eik=eik, hit=hit, idx=idx,
+                    pair=pair), [t.grad for t in leaves], [t.grad if t is not None else None for t in bl]
+
+    ref, gl, gb = run_oracle()
+    cu = lambda t: None if t is None else t.to(DEV)
+    leaves = [t.to(DEV).requires_grad_(True) for t in (sdf, nrm, rgb, var)]
+    bl = [t.to(DEV).requires_grad_(True) for t in (bga, bgc)] if n_out else [None, None]
+    inv_s = torch.exp(leaves[3] * 10.0).clip(1e-6, 1e6).reshape(1, 1)
+    color, w, wsum, wmax, cdf, inside, eik, hit_idx, pair = ops.Composite.apply(
+        leaves[0], leaves[1], leaves[2], inv_s, bl[0], bl[1], cu(dists), cu(pts), cu(d), cu(bgr), n, n_out, car)
+    assert_close(color, ref["color"], 1e-5, "color")
+    assert_close(w, ref["weights"], 1e-5, "weights")
+    assert_close(wsum, ref["weights"].sum(-1, keepdim=True), 1e-5, "weight_sum")
+    assert_close(wmax, ref["weights"].max(-1, keepdim=True)[0], 1e-5, "weight_max")
+    assert_close(cdf, ref["cdf"], 1e-5, "cdf")
+    assert torch.equal(inside.cpu(), ref["inside"])
+    assert_close(eik, ref["eik"], 1e-5, "gradient_error")
+    assert torch.equal((hit_idx >= 0).cpu(), ref["hit"])
+    assert torch.equal(hit_idx.cpu()[ref["hit"]].long(), ref["idx"][ref["hit"]])
+    assert_close(pair, ref["pair"], 1e-5, "w_pair")
+    loss = (color * cu(c_col)).sum() + (w * cu(c_w)).sum() + 0.7 * eik + (pair * cu(c_pair)).sum() + wsum.sum() * 0.3
+    loss.backward()
+    for name, a, b in zip(("d_sdf", "d_normals", "d_rgb", "d_variance"), leaves, gl):
+        assert_close(a.grad, b, FP32_TOL, name, rtol=1e-4)
+    if n_out:
+        assert_close(bl[0].grad, gb[0], FP32_TOL, "d_bg_alpha", rtol=1e-4)
+        assert_close(bl[1].grad, gb[1], FP32_TOL, "d_bg_color", rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------ render
+def _stage1(out, true_rgb, mask, mw):
+    return O.stage1_loss(out, true_rgb, mask, 0.1, 0.1, mw)[0]
+
+
+def test_render_core_fwd_bwd_wmask(golden_dir, states):
+    """Full wmask step on the reference's own depths: outputs vs golden (reference) and vs oracle,
+    every parameter gradient vs the oracle's autograd."""
+    g = _golden(golden_dir, "render_wmask.npz")
+    B = g["color_fine"].shape[0]
+    o, d, near, far = syn.make_rays(B, seed=1)
+    true_rgb, mask = syn.make_targets(B, seed=2)
+    z = torch.from_numpy(g["z_vals"])
+    P = grad_params(states)
+    ref = O.render(P, o, d, near, far, conf=O.RENDER_CONF_WMASK, perturb_overwrite=0, cos_anneal_ratio=1.0,
+                   z_override=z)
+    _stage1(ref, true_rgb, mask, 0.1).backward()
+
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    R = m["renderer"]
+    core = R.render_core(o.to(DEV), d.to(DEV), z.to(DEV), 2.0 / 64, m["sdf"], m["var"], m["color"], m["ref"],
+                         cos_anneal_ratio=1.0)
+    w = core["weights"]
+    out = dict(color_fine=core["color"], surface_color=core["surface_color"], sdf_mask=core["sdf_mask"],
+               weight_sum=w.sum(-1, keepdim=True), gradient_error=core["gradient_error"])
+    for k, gk in (("color", "color_fine"), ("surface_color", "surface_color"), ("cdf", "cdf_fine"),
+                  ("gradients", "gradients"), ("weights", "weights"), ("gradient_error", "gradient_error"),
+                  ("inside_sphere", "inside_sphere"), ("specular_color", "specular_color"),
+                  ("diffuse_color", "diffuse_color")):
+        assert_close(core[k], g[gk], FP32_TOL, "render_core %s vs reference golden" % k)
+    assert np.array_equal(core["sdf_mask"].cpu().numpy().astype(np.float32), g["sdf_mask"])
+    loss = _stage1(out, true_rgb.to(DEV), mask.to(DEV), 0.1)
+    assert abs(loss.item() - float(g["loss"])) < 1e-4
+    loss.backward()
+    worst = compare_param_grads(m, P, ["sdf", "color", "var", "ref"], FP32_TOL, 1e-3, "wmask")
+    print("wmask worst param-grad abs err %.3e" % worst)
+
+
+def test_render_end_to_end_wmask(golden_dir, states):
+    g = _golden(golden_dir, "render_wmask.npz")
+    B = g["color_fine"].shape[0]
+    o, d, near, far = syn.make_rays(B, seed=1)
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    out = m["renderer"].render(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), perturb_overwrite=0,
+                               cos_anneal_ratio=1.0)
+    for k in ("color_fine", "surface_color", "s_val", "weight_sum", "weight_max", "gradient_error",
+              "specular_color", "diffuse_color"):
+        assert_close(out[k], g[k], FP32_TOL, "render %s vs reference golden" % k)
+    assert set(out.keys()) == {"color_fine", "surface_color", "sdf_mask", "s_val", "cdf_fine", "weight_sum",
+                               "weight_max", "gradients", "weights", "gradient_error", "inside_sphere",
+                               "specular_color", "diffuse_color"}
+    assert out["gradients"].shape == (B, 128, 3) and out["weights"].shape == (B, 128)
+    assert out["sdf_mask"].dtype == torch.bool
+
+
+def test_render_perturbed_runs_and_is_sane(states):
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    o, d, near, far = syn.make_rays(512, seed=1)
+    out = m["renderer"].render(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), cos_anneal_ratio=1.0)
+    assert torch.isfinite(out["color_fine"]).all()
+    ws = out["weight_sum"]
+    assert float(ws.min()) >= -1e-5 and float(ws.max()) <= 1.0 + 1e-4
+    assert int(out["sdf_mask"].sum()) > 256
