@@ -53,6 +53,9 @@ _SIGNATURES = {
     "fneus_status_string": (ctypes.c_char_p, [c_int]),
     "fneus_abi_version": (c_int, []),
     "fneus_num_sms": (c_int, []),
+    "fneus_prof_classes": (c_int, []),
+    "fneus_prof_enable": (c_int, [c_int]),
+    "fneus_prof_collect": (c_int, [_P, _P, _P, _P]),
     "fneus_sdf_pack_floats": (_LL, [POINTER(SdfCfg)]),
     "fneus_sdf_saved_floats": (_LL, [POINTER(SdfCfg), _LL]),
     "fneus_sdf_scratch_floats": (_LL, [POINTER(SdfCfg), _LL]),

@@ -2,6 +2,7 @@
 // :328-332 inside-sphere weights, :350-372 background mix, transmittance product, compositing, eikonal term)
 // and its closed-form backward.  One warp per ray, lane-strided samples, shuffle scans.
 #include "fneus_common.cuh"
+#include "prof.cuh"
 
 namespace fneus {
 
@@ -367,9 +368,11 @@ int fneus_composite_fwd(const float* sdf, const float* normals, const float* rgb
   if ((n_out > 0) && (!bg_alpha || !bg_color)) return FNEUS_ERR_NULL;
   if ((bg_alpha == nullptr) != (bg_color == nullptr)) return FNEUS_ERR_NULL;
   size_t smem = (size_t)COMP_WARPS * n_in * sizeof(float);
+  prof_begin(PC_COMPOSITE, 0.0, (double)B * ((n_in + n_out) * 44.0 + 100.0), (cudaStream_t)stream);
   composite_fwd_kernel<<<cdiv(B, COMP_WARPS), COMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
       sdf, normals, rgb, dists, pts, rays_d, bg_alpha, bg_color, bg_rgb, B, n_in, n_out, inv_s, cos_anneal_ratio,
       color, weights, weight_sum, weight_max, cdf, inside, eik_part, hit_idx, w_pair);
+  prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -392,10 +395,12 @@ int fneus_composite_bwd(const float* sdf, const float* normals, const float* rgb
     cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fneus_cuda_error((int)e);
   }
+  prof_begin(PC_COMPOSITE, 0.0, (double)B * ((n_in + n_out) * 64.0 + 100.0), (cudaStream_t)stream);
   composite_bwd_kernel<<<cdiv(B, COMP_WARPS), COMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
       sdf, normals, rgb, dists, pts, rays_d, bg_alpha, bg_color, bg_rgb, B, n_in, n_out, inv_s, cos_anneal_ratio,
       hit_idx, d_color, d_weights, d_weight_sum, d_w_pair, d_eik, eik_denom, d_sdf, d_normals, d_rgb, d_inv_s,
       d_bg_alpha, d_bg_color);
+  prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }

@@ -10,6 +10,7 @@
 // register micro-tile, register-prefetch double buffering.
 #pragma once
 #include "fneus_common.cuh"
+#include "prof.cuh"
 
 namespace fneus {
 
@@ -373,14 +374,18 @@ inline void launch_gemm_fwd(const ASeg& a, const float* W, int ldw, int wout0, l
                             cudaStream_t st) {
   if (M <= 0 || N <= 0) return;
   dim3 grid(cdiv(M, GB_M), cdiv(N, GB_N));
+  prof_begin(PC_GEMM_FWD, 2.0 * (double)M * N * (a.gen.ncols + a.kmem), 0.0, st);
   gemm_mk_kernel<true><<<grid, GB_THREADS, 0, st>>>(a, W, ldw, wout0, (int)M, N, e);
+  prof_end(st);
 }
 // backward-data: C[M,N] = epi(A[M, Kred] * W[wred.., wout0:wout0+N])
 inline void launch_gemm_bwd_data(const ASeg& a, const float* W, int ldw, int wout0, long long M, int N,
                                  const Epi& e, cudaStream_t st) {
   if (M <= 0 || N <= 0) return;
   dim3 grid(cdiv(M, GB_M), cdiv(N, GB_N));
+  prof_begin(PC_GEMM_BWD_DATA, 2.0 * (double)M * N * (a.gen.ncols + a.kmem), 0.0, st);
   gemm_mk_kernel<false><<<grid, GB_THREADS, 0, st>>>(a, W, ldw, wout0, (int)M, N, e);
+  prof_end(st);
 }
 inline void launch_gemm_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, int ldw, int wout0, float* db,
                               long long M, int N, int num_sms, cudaStream_t st) {
@@ -395,7 +400,9 @@ inline void launch_gemm_wgrad(const float* dY, int ldy, const ASeg& a, float* dW
   int mps = round_up(cdiv(M, splits), GB_K);
   splits = cdiv(M, mps);
   dim3 grid(tiles, splits);
+  prof_begin(PC_GEMM_WGRAD, 2.0 * (double)M * N * (a.gen.ncols + a.kmem), 0.0, st);
   gemm_wgrad_kernel<<<grid, GB_THREADS, 0, st>>>(dY, ldy, a, dW, ldw, wout0, db, (int)M, N, mps);
+  prof_end(st);
 }
 
 }  // namespace fneus

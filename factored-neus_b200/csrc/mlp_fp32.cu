@@ -3,6 +3,7 @@
 // Every dense layer is one launch of the SIMT GEMM engine (gemm_simt.cuh) with a fused epilogue;
 // positional encodings are generated in the GEMM tile loaders.
 #include "gemm_simt.cuh"
+#include "prof.cuh"
 
 namespace fneus {
 
@@ -199,7 +200,9 @@ static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float
       launch_gemm_fwd(a, W, p.in[l], 0, M, p.out[l], e, st);
       if (l + 1 == p.skip) {
         GenSpec g = sdf_gen(c, x, nullptr);
+        prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
         append_gen_cols_kernel<<<ew_blocks(M * g.ncols), 256, 0, st>>>(g, Hout, p.ldin[l + 1], p.out[l], rsqrt2, M);
+        prof_end(st);
       }
       Hin = Hout;
     } else if (feat_out) {
@@ -208,7 +211,9 @@ static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float
       e.C = feat_out; e.ldc = c->d_out - 1;
       launch_gemm_fwd(a, W, p.in[l], 0, M, p.out[l], e, st);
     } else {
+      prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
       rowdot_kernel<<<ew_blocks(M * 32), 256, 0, st>>>(Hin, p.ldin[l], p.in[l], W, b, 1.f / c->scale, sdf_out, M);
+      prof_end(st);
     }
   }
   FNEUS_CHECK_LAUNCH();
@@ -294,7 +299,9 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
     e.C = g0; e.ldc = e4;
     launch_gemm_bwd_data(a, wpack + p.woff[0], p.in[0], 0, M, p.in[0], e, st);
   }
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   normal_from_g0_kernel<<<ew_blocks(M), 256, 0, st>>>(x, cfg->d_in, cfg->multires, cfg->scale, g0, e4, normal_out, M);
+  prof_end(st);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -333,15 +340,19 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
       launch_gemm_fwd(a, wpack + p.woff[l], p.in[l], 0, M, p.out[l], e, st);
       if (l + 1 == p.skip) {
         GenSpec g = sdf_gen(cfg, x, d_normal);
+        prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
         append_gen_cols_kernel<<<ew_blocks(M * g.ncols), 256, 0, st>>>(g, gout, p.ldin[l + 1], p.out[l], rsqrt2, M);
+        prof_end(st);
       }
     }
     // q_L = e_0 (row 0 of the last linear): dW_L[0,:] += sum_m gbar_L
     {
       int mpb = 256;
       dim3 grid(cdiv(p.in[L], 256), cdiv(M, mpb));
+      prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
       colsum_kernel<<<grid, 256, 0, st>>>(gbuf[L & 1], p.ldin[L], p.in[L], nullptr, 1.f, d_wpack + p.woff[L],
                                           nullptr, M, mpb);
+      prof_end(st);
     }
   }
   // value-path backward with the augmented abar_l
@@ -350,7 +361,9 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   if (d_sdf) {
     int mpb = 256;
     dim3 grid(cdiv(p.in[L], 256), cdiv(M, mpb));
+    prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
     colsum_kernel<<<grid, 256, 0, st>>>(b.H[L], p.ldin[L], p.in[L], d_sdf, 1.f / cfg->scale, dWL, dbL, M, mpb);
+    prof_end(st);
   }
   if (d_feat) {
     launch_gemm_wgrad(d_feat, cfg->d_out - 1, aseg_mem(b.H[L], p.ldin[L], p.in[L]), dWL, p.in[L], 1, dbL, M,

@@ -1,6 +1,7 @@
 // RenderingNetwork (fields.py:114-175) and RefColor (fields.py:271-335, math_utils.py:12-22,138-144):
 // ReLU MLPs whose first-layer input is [generated block | feature block].  FP32 path on the SIMT GEMM engine.
 #include "gemm_simt.cuh"
+#include "prof.cuh"
 
 namespace fneus {
 
@@ -265,11 +266,15 @@ int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float*
   float* ab1 = ab0 + M * p.ldh;
   float* dsmall = ab1 + M * p.ldh;
   float* alast = dsmall + M * lds;
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   sigmoid_bwd_kernel<<<ew_blocks2(M * 4), 256, 0, st>>>(d_rgb, rgb, cfg->d_out, alast, 4, M);
+  prof_end(st);
   relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh,
                  alast, 4, ab0, ab1, d_normals ? dsmall : nullptr, lds, d_feats, cfg->d_feature, 0, M, st);
   if (d_normals)
+    prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
     extract_cols_kernel<<<ew_blocks2(M * 3), 256, 0, st>>>(dsmall, lds, p.gen_cols - 3, 3, d_normals, 3, M);
+    prof_end(st);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -325,7 +330,9 @@ int fneus_ref_fwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   (void)scratch;
   cudaStream_t st = (cudaStream_t)stream;
   RefBufs b = ref_carve(p, saved, M);
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_prep_kernel<<<ew_blocks2(M), 256, 0, st>>>(dirs, normals, b.refl, M);
+  prof_end(st);
   relu_chain_fwd(wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, EPI_SIGMOID, b.yd, 3, M, st);
   // viewdir_mlp: 4 x (Linear+ReLU); then net_cs Linear+Sigmoid
   {
@@ -334,7 +341,9 @@ int fneus_ref_fwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
     relu_chain_fwd(wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, EPI_SIGMOID, b.ys,
                    1, M, st);
   }
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_final_kernel<<<ew_blocks2(M * 3), 256, 0, st>>>(b.yd, b.ys, rgb_out, spec_out, diff_out, M);
+  prof_end(st);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -356,13 +365,17 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   float* ds_cs = ds_cd + M * 32;
   float* a_cd = ds_cs + M * 36;
   float* a_cs = a_cd + M * 4;
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_final_bwd_kernel<<<ew_blocks2(M), 256, 0, st>>>(b.yd, b.ys, d_rgb, d_spec, d_diff, a_cd, a_cs, M);
+  prof_end(st);
   relu_chain_bwd(wpack, d_wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, a_cd, 4, ab0, ab1,
                  ds_cd, 32, d_feats, cfg->d_feature, 0, M, st);
   Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
   relu_chain_bwd(wpack, d_wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, a_cs, 4, ab0,
                  ab1, ds_cs, 36, d_feats, cfg->d_feature, 1, M, st);
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_dn_kernel<<<ew_blocks2(M), 256, 0, st>>>(dirs, normals, b.refl, ds_cd, 32, ds_cs, 36, d_normals, M);
+  prof_end(st);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }

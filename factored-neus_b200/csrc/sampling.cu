@@ -3,6 +3,7 @@
 // per-warp shared-memory row, shuffle scans for the transmittance product and the CDF sum, binary
 // search per importance sample.  No gradients flow through any of this (renderer.py:426 no_grad).
 #include "fneus_common.cuh"
+#include "prof.cuh"
 
 namespace fneus {
 
@@ -228,7 +229,9 @@ int fneus_ray_points(const float* rays_o, const float* rays_d, const float* z, l
   if (!rays_o || !rays_d || !z || !pts) return FNEUS_ERR_NULL;
   if (B < 0 || n < 0) return FNEUS_ERR_BAD_SHAPE;
   long long total = B * n;
+  prof_begin(PC_SAMPLING, 0.0, (double)total * 16.0, (cudaStream_t)stream);
   ray_points_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z, total, n, pts);
+  prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -244,8 +247,10 @@ int fneus_upsample_step(const float* rays_o, const float* rays_d, const float* z
     cudaError_t e = cudaFuncSetAttribute(upsample_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fneus_cuda_error((int)e);
   }
+  prof_begin(PC_SAMPLING, 0.0, (double)B * (n * 8.0 + k * 4.0 + 24.0), (cudaStream_t)stream);
   upsample_step_kernel<<<cdiv(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
       rays_o, rays_d, z, sdf, B, n, k, inv_s, u_table, new_z, cdf_out, inds_out);
+  prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -260,8 +265,10 @@ int fneus_inverse_cdf(const float* bins, const float* cdf, const float* u_table,
     cudaError_t e = cudaFuncSetAttribute(inverse_cdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fneus_cuda_error((int)e);
   }
+  prof_begin(PC_SAMPLING, 0.0, (double)B * (n * 8.0 + k * 12.0), (cudaStream_t)stream);
   inverse_cdf_kernel<<<cdiv(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, cdf, u_table, B, n,
                                                                                          k, samples_out, inds_out);
+  prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -278,8 +285,10 @@ int fneus_merge_sorted(const float* z, const float* new_z, const float* sdf, con
     cudaError_t e = cudaFuncSetAttribute(merge_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fneus_cuda_error((int)e);
   }
+  prof_begin(PC_SAMPLING, 0.0, (double)B * (n + k) * (sdf ? 16.0 : 8.0), (cudaStream_t)stream);
   merge_sorted_kernel<<<cdiv(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(z, new_z, sdf, new_sdf, B,
                                                                                         n, k, z_out, sdf_out);
+  prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -290,8 +299,10 @@ int fneus_core_geometry(const float* rays_o, const float* rays_d, const float* z
   if (!rays_o || !rays_d || !z || !pts) return FNEUS_ERR_NULL;
   if (B < 0 || n < 0) return FNEUS_ERR_BAD_SHAPE;
   long long total = B * n;
+  prof_begin(PC_SAMPLING, 0.0, (double)total * 36.0, (cudaStream_t)stream);
   core_geometry_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z, total, n, sample_dist,
                                                                           dists, mid_z, pts, dirs);
+  prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }

@@ -223,7 +223,9 @@ class Composite(torch.autograd.Function):
     """renderer.py:245-274,328-332,350-372 fused; differentiable in sdf, normals, rgb, inv_s, bg_alpha, bg_color.
 
     Returns (color [B,3], weights [B,n_tot], weight_sum [B,1], weight_max [B,1], cdf [B,n_in],
-    inside [B,n_in], gradient_error [], hit_idx [B] int32, w_pair [B,2])."""
+    inside [B,n_in], eik_num [], eik_den [], hit_idx [B] int32, w_pair [B,2]) where the eikonal term of
+    renderer.py:370-372 is eik_num / (eik_den + 1e-5) (kept apart so that ray-sharded data parallelism can
+    normalise by the batch-global denominator)."""
 
     @staticmethod
     def forward(ctx, sdf, normals, rgb, inv_s, bg_alpha, bg_color, dists, pts, rays_d, bg_rgb, n_in, n_out, car):
@@ -253,17 +255,17 @@ class Composite(torch.autograd.Function):
             L.ptr(wsum), L.ptr(wmax), L.ptr(cdf), L.ptr(inside), L.ptr(eik), L.ptr(hit), L.ptr(wpair),
             L.stream_ptr()), "fneus_composite_fwd")
         tot = eik.sum(0)
-        denom = (tot[1] + 1e-5).reshape(1)
-        grad_err = (tot[0] / denom[0]).reshape(())
+        eik_num, eik_den = tot[0].reshape(()), tot[1].reshape(())
+        denom = torch.ones(1, dtype=torch.float32, device=dev)
         ctx.save_for_backward(sdf_c, nrm_c, rgb_c, inv_c, bga, bgc, dists_c, pts_c, rd_c, bgr, hit, denom)
         ctx.dims = (B, n_in, n_out, float(car))
         ctx.shapes = (sdf.shape, normals.shape, rgb.shape, inv_s.shape)
-        ctx.mark_non_differentiable(wmax, cdf, inside, hit)
+        ctx.mark_non_differentiable(wmax, cdf, inside, hit, eik_den)
         ctx.set_materialize_grads(False)
-        return color, weights, wsum, wmax, cdf, inside, grad_err, hit, wpair
+        return color, weights, wsum, wmax, cdf, inside, eik_num, eik_den, hit, wpair
 
     @staticmethod
-    def backward(ctx, d_color, d_weights, d_wsum, _wmax, _cdf, _inside, d_eik, _hit, d_wpair):
+    def backward(ctx, d_color, d_weights, d_wsum, _wmax, _cdf, _inside, d_eik, _eik_den, _hit, d_wpair):
         sdf_c, nrm_c, rgb_c, inv_c, bga, bgc, dists_c, pts_c, rd_c, bgr, hit, denom = ctx.saved_tensors
         B, n_in, n_out, car = ctx.dims
         d_sdf = torch.empty_like(sdf_c)

@@ -91,9 +91,11 @@ class NeuSRenderer:
         rgb = color_network(pts, normals, dirs, feat)                                             # [B*n,3]
 
         n_out = 0 if background_alpha is None else background_alpha.shape[1] - n
-        color, weights, wsum, wmax, cdf, inside, grad_err, hit_idx, w_pair = ops.Composite.apply(
+        color, weights, wsum, wmax, cdf, inside, eik_num, eik_den, hit_idx, w_pair = ops.Composite.apply(
             sdf, normals, rgb, inv_s, background_alpha, background_sampled_color, dists, pts, rays_d,
             background_rgb, n, n_out, float(cos_anneal_ratio))
+        grad_err = eik_num / (eik_den + 1e-5)
+        self.last_eikonal_parts = (eik_num, eik_den)     # for exact loss normalisation across ray shards
 
         # surface term (renderer.py:284-343) with fixed shapes: every ray evaluates RefColor at the two
         # bracketing samples, rays without a sign change are masked to the reference's default of ones.

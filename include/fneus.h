@@ -37,6 +37,14 @@ const char* fneus_status_string(int status);
 int fneus_abi_version(void);
 int fneus_num_sms(void);
 
+/* Profiling hooks used by bench.py: when enabled every kernel launch is bracketed by CUDA events on its own
+ * stream.  fneus_prof_collect synchronises those events and ADDS per-class milliseconds, launch counts and
+ * algorithmic flops/bytes into arrays of length fneus_prof_classes() (classes: 0 gemm fwd, 1 gemm bwd-data,
+ * 2 gemm bwd-weight, 3 sampling, 4 compositing, 5 elementwise, 6 tensor-core MLP), then resets. */
+int fneus_prof_classes(void);
+int fneus_prof_enable(int on);
+int fneus_prof_collect(double* ms, long long* launches, double* flops, double* bytes);
+
 /* ---- SDF network (fields.py:9-111) ------------------------------------------------------------ */
 typedef struct {
   int d_in;       /* 3 */

@@ -91,9 +91,10 @@ def test_merge_sorted_properties():
         a = torch.sort(torch.rand(B, n, generator=gen), -1)[0]
         b = torch.sort(torch.rand(B, k, generator=gen), -1)[0]
         b[:, 0] = a[:, 0]                                           # ties
+        b = torch.sort(b, -1)[0]
         sa, sb = torch.rand(B, n, generator=gen), torch.rand(B, k, generator=gen)
         z, s = ops.merge_sorted(a.to(DEV), b.to(DEV), sa.to(DEV), sb.to(DEV))
-        ref, idx = torch.sort(torch.cat([a, b], -1), -1, stable=True)
+        ref, idx = torch.sort(torch.cat([a, b], -1), dim=-1, stable=True)
         assert torch.equal(z.cpu(), ref)
         assert torch.equal(s.cpu(), torch.cat([sa, sb], -1).gather(-1, idx))
 
@@ -235,8 +236,9 @@ def test_composite_fwd_bwd(n_out, car, use_bg_rgb):
     leaves = [t.to(DEV).requires_grad_(True) for t in (sdf, nrm, rgb, var)]
     bl = [t.to(DEV).requires_grad_(True) for t in (bga, bgc)] if n_out else [None, None]
     inv_s = torch.exp(leaves[3] * 10.0).clip(1e-6, 1e6).reshape(1, 1)
-    color, w, wsum, wmax, cdf, inside, eik, hit_idx, pair = ops.Composite.apply(
+    color, w, wsum, wmax, cdf, inside, eik_num, eik_den, hit_idx, pair = ops.Composite.apply(
         leaves[0], leaves[1], leaves[2], inv_s, bl[0], bl[1], cu(dists), cu(pts), cu(d), cu(bgr), n, n_out, car)
+    eik = eik_num / (eik_den + 1e-5)
     assert_close(color, ref["color"], 1e-5, "color")
     assert_close(w, ref["weights"], 1e-5, "weights")
     assert_close(wsum, ref["weights"].sum(-1, keepdim=True), 1e-5, "weight_sum")
