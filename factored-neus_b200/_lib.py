@@ -33,6 +33,11 @@ class RefCfg(Structure):
     _fields_ = [("d_feature", c_int), ("d_hidden", c_int)]
 
 
+class NerfCfg(Structure):
+    _fields_ = [("D", c_int), ("W", c_int), ("d_in", c_int), ("d_in_view", c_int), ("multires", c_int),
+                ("multires_view", c_int), ("skip", c_int)]
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> factored-neus_b200/libfneus_b200.so"""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
@@ -72,6 +77,14 @@ _SIGNATURES = {
     "fneus_ref_scratch_floats": (_LL, [POINTER(RefCfg), _LL]),
     "fneus_ref_fwd": (c_int, [POINTER(RefCfg), _P, _P, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P]),
     "fneus_ref_bwd": (c_int, [POINTER(RefCfg), _P, _P, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fneus_nerf_pack_floats": (_LL, [POINTER(NerfCfg)]),
+    "fneus_nerf_saved_floats": (_LL, [POINTER(NerfCfg), _LL]),
+    "fneus_nerf_scratch_floats": (_LL, [POINTER(NerfCfg), _LL]),
+    "fneus_nerf_fwd": (c_int, [POINTER(NerfCfg), _P, _P, _P, _LL, _P, _P, _P, _P]),
+    "fneus_nerf_bwd": (c_int, [POINTER(NerfCfg), _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P]),
+    "fneus_outside_geometry": (c_int, [_P, _P, _P, _LL, c_int, c_float, _P, _P, _P, _P]),
+    "fneus_outside_alpha_fwd": (c_int, [_P, _P, _P, _LL, _P, _P, _P]),
+    "fneus_outside_alpha_bwd": (c_int, [_P, _P, _P, _P, _P, _LL, _P, _P, _P]),
     "fneus_ray_points": (c_int, [_P, _P, _P, _LL, c_int, _P, _P]),
     "fneus_upsample_step": (c_int, [_P, _P, _P, _P, _LL, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
     "fneus_inverse_cdf": (c_int, [_P, _P, _P, _LL, c_int, c_int, _P, _P, _P]),

@@ -33,7 +33,7 @@ enum EpiMode {
   EPI_SPMUL,        // primary: C = s(H) * acc * oscale ; secondary (n>=csplit): C2 = acc * oscale
   EPI_SWEEP,        // s = s(H); C = s*acc*oscale ; Q = beta*(1-s)*Q*acc
   EPI_SDF_BWD,      // primary: C = s(H) * (acc + rs[m]*rvec[n]*rscale) * oscale + Q[m][n]
-  EPI_RELUMASK,     // primary: C = H>0 ? acc : 0 ; secondary: C2 (+)= (H2 ? (H2>0 ? acc : 0) : acc)
+  EPI_RELUMASK,     // primary: C = H>0 ? acc (+ rs[m]*rvec[n]*rscale) : 0 ; secondary: C2 (+)= (H2 ? (H2>0 ? acc : 0) : acc)
   EPI_LINEAR_ADD,   // C = acc + Q[m][n]   (Q read-only addend, may be null)
 };
 
@@ -116,7 +116,11 @@ __device__ __forceinline__ void epilogue_store(const Epi& e, long long m, int n,
     } break;
     case EPI_RELUMASK: {
       if (n < e.csplit) {
-        if (e.C) e.C[m * e.ldc + n] = e.H ? (__ldg(e.H + m * e.ldh + n) > 0.f ? acc : 0.f) : acc;
+        if (e.C) {
+          float v = acc;
+          if (e.rs) v += __ldg(e.rs + m) * __ldg(e.rvec + n) * e.rscale;
+          e.C[m * e.ldc + n] = e.H ? (__ldg(e.H + m * e.ldh + n) > 0.f ? v : 0.f) : v;
+        }
       } else if (e.C2) {
         int c = n - e.csplit;
         float v = e.H2 ? (__ldg(e.H2 + m * e.ldh2 + c) > 0.f ? acc : 0.f) : acc;

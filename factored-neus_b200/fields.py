@@ -151,6 +151,44 @@ class RenderingNetwork(nn.Module):
         return ops.ColorMLP.apply(self.flat_weights(), points, normals, view_dirs, feature_vectors, self.cfg)
 
 
+class NeRF(nn.Module):
+    """models/fields.py:178-259 (use_viewdirs=True)."""
+
+    def __init__(self, D=8, W=256, d_in=3, d_in_view=3, multires=0, multires_view=0, output_ch=4, skips=[4],
+                 use_viewdirs=False):
+        super().__init__()
+        if not use_viewdirs:
+            raise ValueError("fneus NeRF: only use_viewdirs=True is implemented (the reference asserts it too)")
+        if len(skips) > 1:
+            raise ValueError("fneus NeRF: at most one skip")
+        self.D, self.W, self.d_in, self.d_in_view = D, W, d_in, d_in_view
+        self.input_ch = d_in * (1 + 2 * multires) if multires > 0 else d_in
+        self.input_ch_view = d_in_view * (1 + 2 * multires_view) if multires_view > 0 else d_in_view
+        self.skips, self.use_viewdirs = skips, use_viewdirs
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(self.input_ch, W)] +
+            [nn.Linear(W, W) if i not in skips else nn.Linear(W + self.input_ch, W) for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(self.input_ch_view + W, W // 2)])
+        self.feature_linear = nn.Linear(W, W)
+        self.alpha_linear = nn.Linear(W, 1)
+        self.rgb_linear = nn.Linear(W // 2, 3)
+        self.cfg = L.NerfCfg(D=D, W=W, d_in=d_in, d_in_view=d_in_view, multires=multires,
+                             multires_view=multires_view, skip=(skips[0] if skips else -1))
+
+    def flat_weights(self):
+        parts = []
+        for lin in self.pts_linears:
+            parts += [lin.weight.reshape(-1), lin.bias.reshape(-1)]
+        parts += [self.alpha_linear.weight.reshape(-1), self.feature_linear.weight.reshape(-1),
+                  self.alpha_linear.bias.reshape(-1), self.feature_linear.bias.reshape(-1)]
+        for lin in (self.views_linears[0], self.rgb_linear):
+            parts += [lin.weight.reshape(-1), lin.bias.reshape(-1)]
+        return torch.cat(parts)
+
+    def forward(self, input_pts, input_views):
+        return ops.NerfMLP.apply(self.flat_weights(), input_pts, input_views, self.cfg)
+
+
 class SingleVarianceNetwork(nn.Module):
     """models/fields.py:262-268."""
 

@@ -161,6 +161,76 @@ class RefColorMLP(torch.autograd.Function):
         return dw, None, d_f, None, d_n, None
 
 
+class NerfMLP(torch.autograd.Function):
+    """NeRF.forward with view directions (fields.py:233-259) -> (raw density [N,1], raw rgb [N,3])."""
+
+    @staticmethod
+    def forward(ctx, wflat, pts, views, cfg):
+        _need_cuda(pts, "pts")
+        w, p, v = _f32c(wflat), _f32c(pts), _f32c(views)
+        N = p.shape[0]
+        lib = L.lib()
+        dens = torch.empty(N, 1, dtype=torch.float32, device=p.device)
+        rgb = torch.empty(N, 3, dtype=torch.float32, device=p.device)
+        saved = _empty(lib.fneus_nerf_saved_floats(cfg, N), p)
+        L.check(lib.fneus_nerf_fwd(cfg, L.ptr(w), L.ptr(p), L.ptr(v), N, L.ptr(dens), L.ptr(rgb), L.ptr(saved),
+                                   L.stream_ptr()), "fneus_nerf_fwd")
+        ctx.cfg = cfg
+        ctx.save_for_backward(w, p, v, saved)
+        return dens, rgb
+
+    @staticmethod
+    def backward(ctx, d_dens, d_rgb):
+        w, p, v, saved = ctx.saved_tensors
+        cfg = ctx.cfg
+        N = p.shape[0]
+        lib = L.lib()
+        dw = torch.zeros_like(w)
+        scratch = _empty(lib.fneus_nerf_scratch_floats(cfg, N), p)
+        L.check(lib.fneus_nerf_bwd(cfg, L.ptr(w), L.ptr(p), L.ptr(v), N, L.ptr(_f32c(d_dens)), L.ptr(_f32c(d_rgb)),
+                                   L.ptr(saved), L.ptr(scratch), L.ptr(dw), L.stream_ptr()), "fneus_nerf_bwd")
+        return dw, None, None, None
+
+
+class OutsideAlpha(torch.autograd.Function):
+    """renderer.py:131-134: (density [N], rgb_raw [N,3], dists [N]) -> (alpha [N], color [N,3])."""
+
+    @staticmethod
+    def forward(ctx, density, rgb_raw, dists):
+        dn, rg, ds = _f32c(density).reshape(-1), _f32c(rgb_raw).reshape(-1, 3), _f32c(dists).reshape(-1)
+        N = dn.shape[0]
+        alpha = torch.empty_like(dn)
+        color = torch.empty_like(rg)
+        L.check(L.lib().fneus_outside_alpha_fwd(L.ptr(dn), L.ptr(rg), L.ptr(ds), N, L.ptr(alpha), L.ptr(color),
+                                                L.stream_ptr()), "fneus_outside_alpha_fwd")
+        ctx.save_for_backward(dn, color, ds)
+        ctx.shapes = (density.shape, rgb_raw.shape)
+        return alpha, color
+
+    @staticmethod
+    def backward(ctx, d_alpha, d_color):
+        dn, color, ds = ctx.saved_tensors
+        N = dn.shape[0]
+        d_dn = torch.empty_like(dn)
+        d_rg = torch.empty_like(color)
+        L.check(L.lib().fneus_outside_alpha_bwd(L.ptr(dn), L.ptr(color), L.ptr(ds), L.ptr(_f32c(d_alpha).reshape(-1)),
+                                                L.ptr(_f32c(d_color).reshape(-1, 3)), N, L.ptr(d_dn), L.ptr(d_rg),
+                                                L.stream_ptr()), "fneus_outside_alpha_bwd")
+        return d_dn.reshape(ctx.shapes[0]), d_rg.reshape(ctx.shapes[1]), None
+
+
+def outside_geometry(rays_o, rays_d, z, sample_dist):
+    B, n = z.shape
+    dev = z.device
+    dists = torch.empty(B, n, dtype=torch.float32, device=dev)
+    pts4 = torch.empty(B * n, 4, dtype=torch.float32, device=dev)
+    dirs = torch.empty(B * n, 3, dtype=torch.float32, device=dev)
+    L.check(L.lib().fneus_outside_geometry(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), B, n, float(sample_dist),
+                                           L.ptr(dists), L.ptr(pts4), L.ptr(dirs), L.stream_ptr()),
+            "fneus_outside_geometry")
+    return dists, pts4, dirs
+
+
 # ---------------------------------------------------------------------------------------------
 # sampling (no grad)
 # ---------------------------------------------------------------------------------------------

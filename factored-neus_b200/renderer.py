@@ -204,4 +204,19 @@ class NeuSRenderer:
         }
 
     def render_core_outside(self, rays_o, rays_d, z_vals, sample_dist, nerf, background_rgb=None):
-        raise NotImplementedError("outside NeRF path is not wired yet")
+        """renderer.py:112-149."""
+        B, n = z_vals.shape
+        dists, pts4, dirs = ops.outside_geometry(rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous(),
+                                                 sample_dist)
+        if self.n_outside <= 0:
+            pts4 = pts4[:, :3].contiguous()
+        density, rgb_raw = nerf(pts4, dirs)
+        alpha, color = ops.OutsideAlpha.apply(density.reshape(-1), rgb_raw, dists.reshape(-1))
+        alpha = alpha.reshape(B, n)
+        sampled_color = color.reshape(B, n, 3)
+        weights = alpha * torch.cumprod(torch.cat([torch.ones([B, 1], device=alpha.device), 1.0 - alpha + 1e-7], -1),
+                                        -1)[:, :-1]
+        color_out = (weights[:, :, None] * sampled_color).sum(dim=1)
+        if background_rgb is not None:
+            color_out = color_out + background_rgb * (1.0 - weights.sum(dim=-1, keepdim=True))
+        return {"color": color_out, "sampled_color": sampled_color, "alpha": alpha, "weights": weights}

@@ -121,6 +121,37 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
                   const float* d_spec, const float* d_diff, float* d_feats, float* d_normals, float* saved,
                   float* scratch, float* d_wpack, void* stream);
 
+/* ---- outside NeRF (fields.py:178-259) + render_core_outside (renderer.py:112-149), womask configuration.
+ * Pack order: pts_linears.0..D-1, head = [alpha_linear ; feature_linear] (W [1+W, W] then b [1+W]),
+ * views_linears.0, rgb_linear.  No input gradients (sample positions carry none, renderer.py:426). */
+typedef struct {
+  int D;             /* 8 */
+  int W;             /* 256 */
+  int d_in;          /* 4 (inverted-sphere point) */
+  int d_in_view;     /* 3 */
+  int multires;      /* 10 */
+  int multires_view; /* 4 */
+  int skip;          /* 4: embedded input is concatenated after pts_linears[skip]; -1 = none */
+} fneus_nerf_cfg;
+long long fneus_nerf_pack_floats(const fneus_nerf_cfg* cfg);
+long long fneus_nerf_saved_floats(const fneus_nerf_cfg* cfg, long long n_points);
+long long fneus_nerf_scratch_floats(const fneus_nerf_cfg* cfg, long long n_points);
+/* NeRF.forward (use_viewdirs): pts [n,d_in], views [n,3] -> raw density [n], raw rgb [n,3]. */
+int fneus_nerf_fwd(const fneus_nerf_cfg* cfg, const float* wpack, const float* pts, const float* views,
+                   long long n_points, float* density_out, float* rgb_out, float* saved, void* stream);
+int fneus_nerf_bwd(const fneus_nerf_cfg* cfg, const float* wpack, const float* pts, const float* views,
+                   long long n_points, const float* d_density, const float* d_rgb, float* saved, float* scratch,
+                   float* d_wpack, void* stream);
+/* renderer.py:116-128: dists [B,n], pts4 = [p/|p|, 1/|p|] with |p| clipped to [1,1e10] ([B*n,4]), dirs [B*n,3] */
+int fneus_outside_geometry(const float* rays_o, const float* rays_d, const float* z, long long n_rays, int n,
+                           float sample_dist, float* dists, float* pts4, float* dirs, void* stream);
+/* renderer.py:131-134: alpha = 1-exp(-softplus(density)*dists), color = sigmoid(rgb); and the backward. */
+int fneus_outside_alpha_fwd(const float* density, const float* rgb_raw, const float* dists, long long total,
+                            float* alpha, float* color, void* stream);
+int fneus_outside_alpha_bwd(const float* density, const float* color, const float* dists, const float* d_alpha,
+                            const float* d_color, long long total, float* d_density, float* d_rgb_raw,
+                            void* stream);
+
 /* ---- sampling (renderer.py:43-77,152-205, 391-447) -------------------------------------------- */
 /* pts[b*n+j] = o[b] + d[b]*z[b,j]   (renderer.py:159,194,428) */
 int fneus_ray_points(const float* rays_o, const float* rays_d, const float* z, long long n_rays, int n,

@@ -394,11 +394,12 @@ def render_core(P: Dict[str, Params], rays_o, rays_d, z, sample_dist, background
         color = color + background_rgb * (1.0 - wsum)
     g3 = grads.reshape(B, n, 3)
     eik = (torch.linalg.norm(g3, ord=2, dim=-1) - 1.0) ** 2
-    eik = (relax * eik).sum() / (relax.sum() + 1e-5)
+    eik_num, eik_den = (relax * eik).sum(), relax.sum()
+    eik = eik_num / (eik_den + 1e-5)
     return dict(color=color, surface_color=surf_c, sdf_mask=hit, sdf=sdf, dists=dists, gradients=g3,
                 s_val=(1.0 / inv_s).expand(B * n, 1), mid_z_vals=mid_z, weights=weights,
                 cdf=c_prev.reshape(B, n), gradient_error=eik, inside_sphere=inside,
-                specular_color=spec_c, diffuse_color=diff_c)
+                specular_color=spec_c, diffuse_color=diff_c, eik_num=eik_num, eik_den=eik_den)
 
 
 # ---------------------------------------------------------------------------
@@ -474,7 +475,7 @@ def render(P, rays_o, rays_d, near, far, conf=RENDER_CONF_WMASK, perturb_overwri
                 weight_sum=w.sum(-1, keepdim=True), weight_max=w.max(-1, keepdim=True)[0],
                 gradients=r["gradients"], weights=w, gradient_error=r["gradient_error"],
                 inside_sphere=r["inside_sphere"], specular_color=r["specular_color"],
-                diffuse_color=r["diffuse_color"], z_vals=z)
+                diffuse_color=r["diffuse_color"], z_vals=z, eik_num=r["eik_num"], eik_den=r["eik_den"])
 
 
 # ---------------------------------------------------------------------------

@@ -321,3 +321,76 @@ def test_render_perturbed_runs_and_is_sane(states):
     ws = out["weight_sum"]
     assert float(ws.min()) >= -1e-5 and float(ws.max()) <= 1.0 + 1e-4
     assert int(out["sdf_mask"].sum()) > 256
+
+
+# ------------------------------------------------------------------------------------------ womask
+def test_nerf_forward_backward(golden_dir, states):
+    g = _golden(golden_dir, "fields.npz")
+    m = build_modules(states, DEV)
+    x4, v = _cu(g["x4"]), _cu(g["v"])
+    dens, rgb = m["nerf"](x4, v)
+    assert_close(dens, g["nerf_density"], 1e-5, "nerf density vs reference golden")
+    assert_close(rgb, g["nerf_rgb"], 1e-5, "nerf rgb vs reference golden")
+    gen = torch.Generator().manual_seed(2)
+    N = 700
+    p4 = torch.rand(N, 4, generator=gen) * 2 - 1
+    vv = torch.nn.functional.normalize(torch.randn(N, 3, generator=gen), dim=-1)
+    c1, c3 = torch.randn(N, 1, generator=gen), torch.randn(N, 3, generator=gen)
+    P = grad_params(states)
+    d_o, r_o = O.nerf_forward(P["nerf"], p4, vv)
+    ((d_o * c1).sum() + (r_o * c3).sum()).backward()
+    d_g, r_g = m["nerf"](p4.to(DEV), vv.to(DEV))
+    assert_close(d_g, d_o, 1e-5, "nerf density")
+    assert_close(r_g, r_o, 1e-5, "nerf rgb")
+    ((d_g * c1.to(DEV)).sum() + (r_g * c3.to(DEV)).sum()).backward()
+    compare_param_grads(m, P, ["nerf"], FP32_TOL, 1e-4, "nerf")
+
+
+def test_render_core_fwd_bwd_womask(golden_dir, states):
+    """womask (n_outside=32, cos_anneal 0.3): outputs vs the reference golden, all grads vs the oracle."""
+    g = _golden(golden_dir, "render_womask.npz")
+    B = g["color_fine"].shape[0]
+    o, d, near, far = syn.make_rays(B, seed=1)
+    true_rgb, mask = syn.make_targets(B, seed=2)
+    z = torch.from_numpy(g["z_vals"])
+    P = grad_params(states)
+    ref = O.render(P, o, d, near, far, conf=O.RENDER_CONF_WOMASK, perturb_overwrite=0, cos_anneal_ratio=0.3,
+                   z_override=z)
+    _stage1(ref, true_rgb, mask, 0.0).backward()
+
+    m = build_modules(states, DEV, syn.RENDER_CONF_WOMASK)
+    R = m["renderer"]
+    od, dd, zd = o.to(DEV), d.to(DEV), z.to(DEV)
+    z_out = O.outside_z(far, 32, 64).to(DEV).contiguous()
+    z_feed, _ = ops.merge_sorted(zd, z_out)
+    assert_close(z_feed, torch.sort(torch.cat([z, O.outside_z(far, 32, 64)], -1), -1)[0], 0.0, "z_feed")
+    ro = R.render_core_outside(od, dd, z_feed, 2.0 / 64, m["nerf"])
+    core = R.render_core(od, dd, zd, 2.0 / 64, m["sdf"], m["var"], m["color"], m["ref"],
+                         background_alpha=ro["alpha"], background_sampled_color=ro["sampled_color"],
+                         cos_anneal_ratio=0.3)
+    w = core["weights"]
+    assert w.shape == (B, 160)
+    for k, gk in (("color", "color_fine"), ("surface_color", "surface_color"), ("cdf", "cdf_fine"),
+                  ("gradients", "gradients"), ("weights", "weights"), ("gradient_error", "gradient_error"),
+                  ("inside_sphere", "inside_sphere")):
+        assert_close(core[k], g[gk], FP32_TOL, "womask render_core %s vs reference golden" % k)
+    out = dict(color_fine=core["color"], surface_color=core["surface_color"], sdf_mask=core["sdf_mask"],
+               weight_sum=w.sum(-1, keepdim=True), gradient_error=core["gradient_error"])
+    loss = _stage1(out, true_rgb.to(DEV), mask.to(DEV), 0.0)
+    assert abs(loss.item() - float(g["loss"])) < 1e-4
+    loss.backward()
+    compare_param_grads(m, P, ["sdf", "color", "var", "ref", "nerf"], FP32_TOL, 1e-3, "womask")
+
+
+def test_render_end_to_end_womask(golden_dir, states):
+    g = _golden(golden_dir, "render_womask.npz")
+    B = g["color_fine"].shape[0]
+    o, d, near, far = syn.make_rays(B, seed=1)
+    m = build_modules(states, DEV, syn.RENDER_CONF_WOMASK)
+    out = m["renderer"].render(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), perturb_overwrite=0,
+                               cos_anneal_ratio=0.3)
+    for k in ("color_fine", "surface_color", "s_val", "weight_sum", "weight_max", "gradient_error"):
+        assert_close(out[k], g[k], FP32_TOL, "womask render %s vs reference golden" % k)
+    assert out["weights"].shape == (B, 160) and out["gradients"].shape == (B, 128, 3)
+    out2 = m["renderer"].render(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), cos_anneal_ratio=0.3)
+    assert torch.isfinite(out2["color_fine"]).all()
