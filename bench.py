@@ -184,6 +184,8 @@ def run_ours(args):
         return loss
 
     lib = L.lib()
+    from factored_neus_b200 import ops as _ops
+    _ops.set_precision(args.precision)
     for _ in range(max(3, args.warmup)):
         step(dev_batch)
     torch.cuda.synchronize()
@@ -250,18 +252,21 @@ def run_ours(args):
         line = {
             "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
             "config": {"workload": "wmask stage-1 train step (render fwd + loss + bwd incl. SDF double backward + "
                                    "Adam), 64+64 samples, 4 up-sample steps, sphere-SDF scene at geometric init",
                        "rays_per_gpu_per_step": B, "global_rays_per_step": B * world, "parallelism": "dp%d" % world,
                        "l2": "256 MiB flush between timed iterations; per-step working set ~1.5 GB >> 126 MB L2",
-                       "precision_path": "fp32-simt"},
+                       "precision_path": "bf16 operands on tcgen05, fp32 accumulate/activations" if args.precision == "bf16"
+                       else "fp32-simt"},
             "e2e": {"value": e2e_v, "unit": "rays/s", "h2d_bytes_per_step": host.numel() * 4 * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tf_sust"], "traffic": None, "peak_source": pk["src"],
-                         "kernel": "gemm_mk_kernel/gemm_wgrad_kernel (dense MLP layers)",
+                         "kernel": ("tc_gemm_mk_kernel/tc_gemm_wgrad_kernel (tcgen05 dense MLP layers)" if args.precision == "bf16"
+                                    else "gemm_mk_kernel/gemm_wgrad_kernel (dense MLP layers)"),
                          "kernel_share_of_step": gemm_ms / dev_ms,
                          "step_algorithmic_tflops": FLOP_PER_RAY_TRAIN_WMASK * value / 1e12},
             "kernel_classes": per_class,
@@ -284,6 +289,8 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=128, help="rays per step of the CPU reference arm")
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="dense layers: bf16 = tcgen05 tensor cores (FP32 accumulate), fp32 = CUDA-core anchor")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -58,6 +58,9 @@ _SIGNATURES = {
     "fneus_status_string": (ctypes.c_char_p, [c_int]),
     "fneus_abi_version": (c_int, []),
     "fneus_num_sms": (c_int, []),
+    "fneus_set_precision": (c_int, [c_int]),
+    "fneus_get_precision": (c_int, []),
+    "fneus_debug_gemm": (c_int, [c_int, _P, c_int, _P, c_int, _P, _LL, c_int, c_int, _P, c_int, _P]),
     "fneus_prof_classes": (c_int, []),
     "fneus_prof_enable": (c_int, [c_int]),
     "fneus_prof_collect": (c_int, [_P, _P, _P, _P]),
@@ -65,6 +68,7 @@ _SIGNATURES = {
     "fneus_sdf_saved_floats": (_LL, [POINTER(SdfCfg), _LL]),
     "fneus_sdf_scratch_floats": (_LL, [POINTER(SdfCfg), _LL]),
     "fneus_sdf_fwd": (c_int, [POINTER(SdfCfg), _P, _P, _LL, _P, _P, _P, _LL, _P]),
+    "fneus_sdf_grid": (c_int, [POINTER(SdfCfg), _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _LL, _P]),
     "fneus_sdf_fwd_grad": (c_int, [POINTER(SdfCfg), _P, _P, _LL, _P, _P, _P, _P, _P, _P]),
     "fneus_sdf_bwd": (c_int, [POINTER(SdfCfg), _P, _P, _LL, _P, _P, _P, _P, _P, _P, _P]),
     "fneus_color_pack_floats": (_LL, [POINTER(ColorCfg)]),

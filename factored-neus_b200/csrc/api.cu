@@ -1,6 +1,5 @@
 // Status decoding and version entry points of the C ABI (include/fneus.h).
-#include "fneus_common.cuh"
-#include "prof.cuh"
+#include "gemm_tc.cuh"
 
 namespace fneus { int num_sms(); }
 
@@ -56,6 +55,40 @@ int fneus_prof_collect(double* ms, long long* launches, double* flops, double* b
     if (launches) launches[c] += s.launches[c];
     s.launches[c] = 0;
   }
+  return FNEUS_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+// 0 = FP32 SIMT (exactness anchor, default), 1 = BF16 tcgen05 tensor cores with FP32 accumulation
+int fneus_set_precision(int mode) {
+  if (mode != 0 && mode != 1) return FNEUS_ERR_UNSUPPORTED;
+  fneus::precision_mode() = mode;
+  return FNEUS_OK;
+}
+int fneus_get_precision(void) { return fneus::precision_mode(); }
+
+// Raw dense-layer contractions in the current precision mode (test hook for the two GEMM engines).
+// kind 0: C[M,N] = A[M,K] W[N,K]^T + bias ; kind 1: C[M,N] = A[M,K] W[K,N] ; kind 2: C[N,K] += Y[M,N]^T A[M,K],
+// bias[N] += colsum(Y)  (for kind 2 the `W` argument is Y with leading dimension ldw).
+int fneus_debug_gemm(int kind, const float* A, int lda, const float* W, int ldw, float* bias, long long M, int N,
+                     int K, float* C, int ldc, void* stream) {
+  using namespace fneus;
+  if (!A || !W || !C) return FNEUS_ERR_NULL;
+  if (lda % 4 != 0) return FNEUS_ERR_MISALIGNED;
+  cudaStream_t st = (cudaStream_t)stream;
+  ASeg a = aseg_mem(A, lda, K);
+  Epi e = epi_default();
+  e.C = C; e.ldc = ldc;
+  if (kind == 0) { e.bias = bias; launch_gemm_fwd(a, W, ldw, 0, M, N, e, st); }
+  else if (kind == 1) launch_gemm_bwd_data(a, W, ldw, 0, M, N, e, st);
+  else if (kind == 2) {
+    if (ldw % 4 != 0) return FNEUS_ERR_MISALIGNED;
+    launch_gemm_wgrad(W, ldw, a, C, ldc, 0, bias, M, N, num_sms(), st);
+  } else return FNEUS_ERR_UNSUPPORTED;
+  FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
 

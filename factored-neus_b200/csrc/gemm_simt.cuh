@@ -374,7 +374,7 @@ inline ASeg aseg_gen_mem(const GenSpec& g, int wred_gen, const float* mem, int l
 }
 
 // forward: C[M,N] = epi(A * W[wout0:wout0+N, :]^T)
-inline void launch_gemm_fwd(const ASeg& a, const float* W, int ldw, int wout0, long long M, int N, const Epi& e,
+inline void launch_simt_fwd(const ASeg& a, const float* W, int ldw, int wout0, long long M, int N, const Epi& e,
                             cudaStream_t st) {
   if (M <= 0 || N <= 0) return;
   dim3 grid(cdiv(M, GB_M), cdiv(N, GB_N));
@@ -383,7 +383,7 @@ inline void launch_gemm_fwd(const ASeg& a, const float* W, int ldw, int wout0, l
   prof_end(st);
 }
 // backward-data: C[M,N] = epi(A[M, Kred] * W[wred.., wout0:wout0+N])
-inline void launch_gemm_bwd_data(const ASeg& a, const float* W, int ldw, int wout0, long long M, int N,
+inline void launch_simt_bwd_data(const ASeg& a, const float* W, int ldw, int wout0, long long M, int N,
                                  const Epi& e, cudaStream_t st) {
   if (M <= 0 || N <= 0) return;
   dim3 grid(cdiv(M, GB_M), cdiv(N, GB_N));
@@ -391,7 +391,7 @@ inline void launch_gemm_bwd_data(const ASeg& a, const float* W, int ldw, int wou
   gemm_mk_kernel<false><<<grid, GB_THREADS, 0, st>>>(a, W, ldw, wout0, (int)M, N, e);
   prof_end(st);
 }
-inline void launch_gemm_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, int ldw, int wout0, float* db,
+inline void launch_simt_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, int ldw, int wout0, float* db,
                               long long M, int N, int num_sms, cudaStream_t st) {
   if (M <= 0 || N <= 0) return;
   int ktiles = cdiv(a.gen.ncols, GB_N) + cdiv(a.kmem, GB_N);

@@ -2,7 +2,7 @@
 // SDFNetwork (fields.py:9-111), RenderingNetwork (fields.py:114-175), RefColor (fields.py:271-335).
 // Every dense layer is one launch of the SIMT GEMM engine (gemm_simt.cuh) with a fused epilogue;
 // positional encodings are generated in the GEMM tile loaders.
-#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "prof.cuh"
 
 namespace fneus {
@@ -103,6 +103,20 @@ __global__ void sigmoid_bwd_kernel(const float* dy, const float* y, int n, float
   a[idx] = v;
 }
 
+// pts[i] = (X[ix], Y[iy], Z[iz]) for the flat ij-meshgrid index i0 + i (renderer.py:16-26)
+__global__ void grid_points_kernel(const float* __restrict__ ax, const float* __restrict__ ay,
+                                   const float* __restrict__ az, int ny, int nz, long long i0, long long count,
+                                   float* __restrict__ pts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  long long g = i0 + i;
+  int iz = (int)(g % nz);
+  long long t = g / nz;
+  int iy = (int)(t % ny);
+  long long ix = t / ny;
+  pts[i * 3] = ax[ix]; pts[i * 3 + 1] = ay[iy]; pts[i * 3 + 2] = az[iz];
+}
+
 static inline int ew_blocks(long long n) { return cdiv(n, 256); }
 
 // ------------------------------------------------------------------------------------------------
@@ -176,7 +190,8 @@ static GenSpec sdf_gen(const fneus_sdf_cfg* c, const float* x, const float* tan)
 
 // value chain. If bufs != nullptr activations go to bufs->H (saved) else ping-pong in scratch.
 static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, const float* x, long long M,
-                           float* sdf_out, float* feat_out, SdfBufs* bufs, float* scratch, cudaStream_t st) {
+                           float* sdf_out, float* feat_out, SdfBufs* bufs, float* scratch, cudaStream_t st,
+                           float out_sign = 1.f) {
   const float rsqrt2 = 0.70710678118654752440f;
   float* pp[2] = {scratch, scratch + M * p.ldmax};
   const float* Hin = nullptr;
@@ -207,12 +222,12 @@ static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float
       Hin = Hout;
     } else if (feat_out) {
       e.mode = EPI_SDF_OUT;
-      e.out0 = sdf_out; e.out0_scale = 1.f / c->scale;
+      e.out0 = sdf_out; e.out0_scale = out_sign / c->scale;
       e.C = feat_out; e.ldc = c->d_out - 1;
       launch_gemm_fwd(a, W, p.in[l], 0, M, p.out[l], e, st);
     } else {
       prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
-      rowdot_kernel<<<ew_blocks(M * 32), 256, 0, st>>>(Hin, p.ldin[l], p.in[l], W, b, 1.f / c->scale, sdf_out, M);
+      rowdot_kernel<<<ew_blocks(M * 32), 256, 0, st>>>(Hin, p.ldin[l], p.in[l], W, b, out_sign / c->scale, sdf_out, M);
       prof_end(st);
     }
   }
@@ -255,6 +270,31 @@ int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     long long M = n - m0 < chunk ? n - m0 : chunk;
     int rc = sdf_value_chain(cfg, p, wpack, x + m0 * cfg->d_in, M, sdf_out + m0,
                              feat_out ? feat_out + m0 * (cfg->d_out - 1) : nullptr, nullptr, scratch, st);
+    if (rc) return rc;
+  }
+  return FNEUS_OK;
+}
+
+int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax, const float* ay, const float* az,
+                   int nx, int ny, int nz, int ix0, int ix1, float* u_out, float* scratch, long long scratch_floats,
+                   void* stream) {
+  SdfPlan p = sdf_plan(cfg);
+  if (!p.ok || cfg->d_in != 3) return FNEUS_ERR_UNSUPPORTED;
+  if (!wpack || !ax || !ay || !az || !u_out || !scratch) return FNEUS_ERR_NULL;
+  if (nx < 1 || ny < 1 || nz < 1 || ix0 < 0 || ix1 > nx || ix0 > ix1) return FNEUS_ERR_BAD_SHAPE;
+  long long per = 2LL * p.ldmax + 3;
+  long long chunk = scratch_floats / per;
+  if (chunk >= 128) chunk = chunk / 128 * 128;
+  if (chunk < 1) return FNEUS_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long i0 = (long long)ix0 * ny * nz, i1 = (long long)ix1 * ny * nz;
+  for (long long b = i0; b < i1; b += chunk) {
+    long long M = i1 - b < chunk ? i1 - b : chunk;
+    float* pts = scratch + 2LL * chunk * p.ldmax;
+    prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+    grid_points_kernel<<<ew_blocks(M), 256, 0, st>>>(ax, ay, az, ny, nz, b, M, pts);
+    prof_end(st);
+    int rc = sdf_value_chain(cfg, p, wpack, pts, M, u_out + (b - i0), nullptr, nullptr, scratch, st, -1.f);
     if (rc) return rc;
   }
   return FNEUS_OK;

@@ -1,6 +1,6 @@
 // RenderingNetwork (fields.py:114-175) and RefColor (fields.py:271-335, math_utils.py:12-22,138-144):
 // ReLU MLPs whose first-layer input is [generated block | feature block].  FP32 path on the SIMT GEMM engine.
-#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "prof.cuh"
 
 namespace fneus {

@@ -2,7 +2,7 @@
 // FP32 path on the SIMT GEMM engine.  Pack order (effective = plain weights, NeRF has no weight-norm):
 //   pts_linears.0..D-1, head = [alpha_linear ; feature_linear] (W [1+W, W] then b [1+W]), views_linears.0,
 //   rgb_linear.
-#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "prof.cuh"
 
 namespace fneus {

@@ -26,6 +26,38 @@ def _empty(n, like):
 
 
 # ---------------------------------------------------------------------------------------------
+# precision switch + raw GEMM test hook
+# ---------------------------------------------------------------------------------------------
+def set_precision(mode):
+    """'fp32' (CUDA-core exactness anchor, default) or 'bf16' (tcgen05 tensor cores, FP32 accumulate)."""
+    m = {"fp32": 0, "bf16": 1, 0: 0, 1: 1}[mode]
+    L.check(L.lib().fneus_set_precision(m), "fneus_set_precision")
+
+
+def get_precision():
+    return "bf16" if L.lib().fneus_get_precision() == 1 else "fp32"
+
+
+def debug_gemm(kind, A, W, bias=None, out=None):
+    """kind 0: A[M,K] @ W[N,K].T + bias ; 1: A[M,K] @ W[K,N] ; 2: out[N,K] += W(=Y)[M,N].T @ A[M,K], bias += colsum(Y).
+    A (and Y) need a leading dimension that is a multiple of 4."""
+    assert A.stride(1) == 1 and W.stride(1) == 1 and A.dtype == torch.float32 and W.dtype == torch.float32
+    M, K = A.shape
+    if kind == 0:
+        N = W.shape[0]
+        C = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    elif kind == 1:
+        N = W.shape[1]
+        C = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    else:
+        N = W.shape[1]
+        C = out if out is not None else torch.zeros(N, K, dtype=torch.float32, device=A.device)
+    L.check(L.lib().fneus_debug_gemm(kind, A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), L.ptr(bias), M, N, K,
+                                     L.ptr(C), C.stride(0), L.stream_ptr()), "fneus_debug_gemm")
+    return C
+
+
+# ---------------------------------------------------------------------------------------------
 # SDF network
 # ---------------------------------------------------------------------------------------------
 def sdf_forward_nograd(cfg, wflat, x, want_feat, max_chunk=1 << 18):
@@ -43,6 +75,24 @@ def sdf_forward_nograd(cfg, wflat, x, want_feat, max_chunk=1 << 18):
     L.check(L.lib().fneus_sdf_fwd(cfg, L.ptr(w), L.ptr(x), N, L.ptr(sdf), L.ptr(feat), L.ptr(scratch),
                                   scratch.numel(), L.stream_ptr()), "fneus_sdf_fwd")
     return sdf, feat
+
+
+def sdf_grid(cfg, wflat, ax, ay, az, ix0=0, ix1=None, max_chunk=1 << 18):
+    """-sdf on the ij-meshgrid of three axis tables (renderer.py:14-29), x-slab [ix0, ix1)."""
+    _need_cuda(ax, "ax")
+    w = _f32c(wflat)
+    nx, ny, nz = ax.numel(), ay.numel(), az.numel()
+    ix1 = nx if ix1 is None else ix1
+    u = torch.empty(ix1 - ix0, ny, nz, dtype=torch.float32, device=ax.device)
+    n = (ix1 - ix0) * ny * nz
+    chunk = max(1, min(n, max_chunk))
+    per_point = 2 * max(4, -(-cfg.d_hidden // 4) * 4, -(-(cfg.d_in * (1 + 2 * cfg.multires)) // 4) * 4,
+                        -(-cfg.d_out // 4) * 4) + 3
+    scratch = _empty(per_point * chunk, ax)
+    L.check(L.lib().fneus_sdf_grid(cfg, L.ptr(w), L.ptr(_f32c(ax)), L.ptr(_f32c(ay)), L.ptr(_f32c(az)), nx, ny, nz,
+                                   ix0, ix1, L.ptr(u), L.ptr(scratch), scratch.numel(), L.stream_ptr()),
+            "fneus_sdf_grid")
+    return u
 
 
 class SdfValueGrad(torch.autograd.Function):

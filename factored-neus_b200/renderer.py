@@ -203,6 +203,30 @@ class NeuSRenderer:
             "diffuse_color": ret_fine["diffuse_color"],
         }
 
+    # ------------------------------------------------------------------ grid query / mesh
+    def extract_fields(self, bound_min, bound_max, resolution, ix0=0, ix1=None):
+        """renderer.py:14-29: u = -sdf on the regular grid, as a device tensor [ix1-ix0, R, R] (x-slab)."""
+        net = self.sdf_network
+        dev = next(net.parameters()).device
+        axes = [torch.linspace(float(bound_min[a]), float(bound_max[a]), resolution, device=dev) for a in range(3)]
+        with torch.no_grad():
+            return ops.sdf_grid(net.cfg, net.flat_weights().detach(), axes[0], axes[1], axes[2], ix0, ix1)
+
+    def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0):
+        """renderer.py:32-40,729-734.  The SDF grid is evaluated on the GPU; marching cubes is the reference's
+        third-party CPU dependency (PyMCubes) and is used as-is when installed."""
+        u = self.extract_fields(bound_min, bound_max, resolution).cpu().numpy()
+        try:
+            import mcubes
+        except ImportError as e:
+            raise RuntimeError("extract_geometry: PyMCubes (mcubes) is not installed; use extract_fields() for the "
+                               "SDF grid") from e
+        vertices, triangles = mcubes.marching_cubes(u, threshold)
+        b_max = bound_max.detach().cpu().numpy()
+        b_min = bound_min.detach().cpu().numpy()
+        vertices = vertices / (resolution - 1.0) * (b_max - b_min)[None, :] + b_min[None, :]
+        return vertices, triangles
+
     def render_core_outside(self, rays_o, rays_d, z_vals, sample_dist, nerf, background_rgb=None):
         """renderer.py:112-149."""
         B, n = z_vals.shape

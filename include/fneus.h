@@ -37,6 +37,15 @@ const char* fneus_status_string(int status);
 int fneus_abi_version(void);
 int fneus_num_sms(void);
 
+/* Compute precision of the dense layers: 0 = FP32 on CUDA cores (exactness anchor, <=1e-4 vs the reference,
+ * default), 1 = BF16 operands on tcgen05 tensor cores with FP32 accumulation in TMEM (<=2e-2). */
+int fneus_set_precision(int mode);
+int fneus_get_precision(void);
+/* Test hook: one raw dense-layer contraction in the current precision mode.  kind 0: C[M,N] = A[M,K] W[N,K]^T
+ * + bias; kind 1: C[M,N] = A[M,K] W[K,N]; kind 2: C[N,K] += Y[M,N]^T A[M,K], bias[N] += colsum(Y) (W := Y). */
+int fneus_debug_gemm(int kind, const float* A, int lda, const float* W, int ldw, float* bias, long long M, int N,
+                     int K, float* C, int ldc, void* stream);
+
 /* Profiling hooks used by bench.py: when enabled every kernel launch is bracketed by CUDA events on its own
  * stream.  fneus_prof_collect synchronises those events and ADDS per-class milliseconds, launch counts and
  * algorithmic flops/bytes into arrays of length fneus_prof_classes() (classes: 0 gemm fwd, 1 gemm bwd-data,
@@ -65,6 +74,13 @@ long long fneus_sdf_scratch_floats(const fneus_sdf_cfg* cfg, long long n_points)
  * (sdf only).  Points are processed in chunks that fit scratch_floats. */
 int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long n_points,
                   float* sdf_out, float* feat_out, float* scratch, long long scratch_floats, void* stream);
+
+/* extract_fields (renderer.py:14-29): u[ix,iy,iz] = -sdf(ax[ix], ay[iy], az[iz]) for ix in [ix0, ix1) (an x-slab,
+ * the unit of multi-GPU sharding); ax/ay/az are the per-axis torch.linspace tables on the device;
+ * u_out [(ix1-ix0)*ny*nz]. */
+int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax, const float* ay, const float* az,
+                   int nx, int ny, int nz, int ix0, int ix1, float* u_out, float* scratch,
+                   long long scratch_floats, void* stream);
 
 /* SDFNetwork.forward + .gradient (fields.py:74-111) in one pass: value, feature and the analytic
  * normal d sdf/d x [n,3] (normal_out NULL = value only); `saved` keeps the activations the backward needs. */

@@ -394,3 +394,14 @@ def test_render_end_to_end_womask(golden_dir, states):
     assert out["weights"].shape == (B, 160) and out["gradients"].shape == (B, 128, 3)
     out2 = m["renderer"].render(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), cos_anneal_ratio=0.3)
     assert torch.isfinite(out2["color_fine"]).all()
+
+
+def test_grid_query_matches_reference(golden_dir, states):
+    g = _golden(golden_dir, "grid.npz")
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    R = m["renderer"]
+    bmin, bmax = torch.from_numpy(g["bmin"]), torch.from_numpy(g["bmax"])
+    u = R.extract_fields(bmin, bmax, 20)
+    assert_close(u, g["u"], 1e-5, "grid vs reference golden")
+    slab = R.extract_fields(bmin, bmax, 20, ix0=5, ix1=9)               # x-slab sharding (multi-GPU unit)
+    assert torch.equal(slab, u[5:9])

@@ -1,0 +1,109 @@
+"""BF16 tcgen05 path: raw GEMM checks against torch on bf16-rounded operands, then the network/render parity at the
+north_star tolerance for the tensor-core path (<= 2e-2 max-abs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import factored_neus_b200 as fn
+from factored_neus_b200 import ops
+from oracle import neus_oracle as O
+from util import assert_close, build_modules, grad_params, max_err, syn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BF16_TOL = 2e-2
+
+
+@pytest.fixture()
+def bf16_mode():
+    ops.set_precision("bf16")
+    yield
+    ops.set_precision("fp32")
+
+
+def _r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _pad4(t):
+    M, K = t.shape
+    ld = (K + 3) // 4 * 4
+    buf = torch.zeros(M, ld, dtype=t.dtype, device=t.device)
+    buf[:, :K] = t
+    return buf[:, :K]
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (300, 256, 256), (1000, 217, 39), (257, 48, 64), (640, 289, 256),
+                                   (130, 3, 128), (64, 1, 256), (4096, 256, 289)])
+def test_tc_gemm_forward(bf16_mode, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    C = ops.debug_gemm(0, _pad4(A), W, b)
+    ref = _r(A).double() @ _r(W).double().t() + b.double()
+    assert_close(C, ref, 2e-4, "tc fwd %s" % ((M, N, K),), rtol=1e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (300, 256, 217), (513, 39, 256), (640, 289, 256), (200, 256, 3),
+                                   (100, 340, 256)])
+def test_tc_gemm_bwd_data(bf16_mode, M, N, K):
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(K, N, generator=g) / K ** 0.5).to(DEV)
+    C = ops.debug_gemm(1, _pad4(A), W)
+    ref = _r(A).double() @ _r(W).double()
+    assert_close(C, ref, 2e-4, "tc bwd-data %s" % ((M, N, K),), rtol=1e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 256), (1000, 256, 256), (5000, 217, 256), (333, 257, 39), (900, 3, 128),
+                                   (2048, 256, 289), (70, 128, 600)])
+def test_tc_gemm_wgrad(bf16_mode, M, N, K):
+    g = torch.Generator().manual_seed(M + 7 * N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    Y = torch.randn(M, N, generator=g).to(DEV)
+    db = torch.zeros(N, device=DEV)
+    C = ops.debug_gemm(2, _pad4(A), _pad4(Y), db)
+    ref = _r(Y).double().t() @ _r(A).double()
+    assert_close(C, ref, 2e-3, "tc wgrad %s" % ((M, N, K),), rtol=2e-4)
+    assert_close(db, Y.double().sum(0), 1e-3, "tc wgrad bias", rtol=1e-5)
+
+
+def test_bf16_fields_and_render(bf16_mode, golden_dir):
+    """Whole wmask step on tensor cores: outputs within 2e-2 of the reference golden / oracle; gradients within
+    2e-2 relative to each tensor's scale."""
+    states = syn.scene_states(seed=4, jitter=0.03)
+    g = {k: v for k, v in np.load(os.path.join(golden_dir, "render_wmask.npz")).items()}
+    B = g["color_fine"].shape[0]
+    o, d, near, far = syn.make_rays(B, seed=1)
+    true_rgb, mask = syn.make_targets(B, seed=2)
+    z = torch.from_numpy(g["z_vals"])
+    P = grad_params(states)
+    ref = O.render(P, o, d, near, far, conf=O.RENDER_CONF_WMASK, perturb_overwrite=0, cos_anneal_ratio=1.0,
+                   z_override=z)
+    O.stage1_loss(ref, true_rgb, mask, 0.1, 0.1, 0.1)[0].backward()
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    R = m["renderer"]
+    core = R.render_core(o.to(DEV), d.to(DEV), z.to(DEV), 2.0 / 64, m["sdf"], m["var"], m["color"], m["ref"],
+                         cos_anneal_ratio=1.0)
+    for k, gk in (("color", "color_fine"), ("surface_color", "surface_color"), ("gradients", "gradients"),
+                  ("weights", "weights"), ("gradient_error", "gradient_error")):
+        print("bf16 %s max err %.3e" % (k, max_err(core[k], g[gk])))
+        assert_close(core[k], g[gk], BF16_TOL, "bf16 render_core %s" % k)
+    w = core["weights"]
+    out = dict(color_fine=core["color"], surface_color=core["surface_color"], sdf_mask=core["sdf_mask"],
+               weight_sum=w.sum(-1, keepdim=True), gradient_error=core["gradient_error"])
+    loss = O.stage1_loss(out, true_rgb.to(DEV), mask.to(DEV), 0.1, 0.1, 0.1)[0]
+    assert abs(loss.item() - float(g["loss"])) < BF16_TOL
+    loss.backward()
+    for net in ("sdf", "color", "var", "ref"):
+        for name, p in m[net].named_parameters():
+            refg = P[net][name].grad
+            refg = torch.zeros_like(P[net][name]) if refg is None else refg
+            scale = max(1e-3, float(refg.abs().max()))
+            err = max_err(p.grad, refg)
+            assert err <= BF16_TOL * max(1.0, scale) , "bf16 grad %s.%s err %.3e (scale %.3e)" % (net, name, err, scale)
+    out2 = R.render(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), perturb_overwrite=0, cos_anneal_ratio=1.0)
+    assert_close(out2["color_fine"], g["color_fine"], BF16_TOL, "bf16 e2e color_fine")
