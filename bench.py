@@ -162,7 +162,7 @@ def run_ours(args):
                         color_network=nets[2], refColor_network=nets[3])
     params = [p for n in nets for p in n.parameters()]
     bucket = GradBucket(params)
-    opt = torch.optim.Adam(params, lr=5e-4, fused=True)
+    opt = torch.optim.Adam(params, lr=5e-4, fused=True, capturable=True)
 
     o, d, near, far = syn.make_rays(B, seed=1 + rank)
     true_rgb, mask = syn.make_targets(B, seed=100 + rank)
@@ -186,6 +186,11 @@ def run_ours(args):
     lib = L.lib()
     from factored_neus_b200 import ops as _ops
     _ops.set_precision(args.precision)
+    # every step (warm-up, capture, replay, eager) runs on one non-default stream so that autograd's
+    # AccumulateGrad nodes and the flat gradient bucket live on the capture stream
+    work_stream = torch.cuda.Stream()
+    work_stream.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(work_stream)
     for _ in range(max(3, args.warmup)):
         step(dev_batch)
     torch.cuda.synchronize()
@@ -195,13 +200,35 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---------------- whole-step CUDA graph (fixed shapes; removes ~2k launches of host overhead per step) ----
+    graph, static_batch, static_loss = None, dev_batch.clone(), None
+    if not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=work_stream):
+                static_loss = step(static_batch)
+            graph.replay()
+            torch.cuda.synchronize()
+            if not torch.isfinite(static_loss).all():
+                raise RuntimeError("non-finite loss from the graphed step")
+        except Exception as ex:
+            # a failed capture leaves the CUDA RNG in capture mode: re-run this process eagerly instead
+            if rank == 0:
+                print("bench: CUDA graph capture failed (%s); re-running with --no-graph" % str(ex).splitlines()[0],
+                      file=sys.stderr)
+            if world == 1:
+                os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
+            raise
+
+    def run_step(batch):
+        if graph is None:
+            return step(batch)
+        if batch is not static_batch:
+            static_batch.copy_(batch, non_blocking=True)
+        graph.replay()
+        return static_loss
+
     # ---------------- device-resident timed region (value) -------------------------------------
-    ncls = lib.fneus_prof_classes()
-    import ctypes
-    ms_c = (ctypes.c_double * ncls)(); ln_c = (ctypes.c_longlong * ncls)()
-    fl_c = (ctypes.c_double * ncls)(); by_c = (ctypes.c_double * ncls)()
-    lib.fneus_prof_collect(None, None, None, None)
-    lib.fneus_prof_enable(1)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -209,14 +236,31 @@ def run_ours(args):
     for i in range(args.steps):
         flush.zero_()                                                       # L2 flush between timed iterations
         ev[i][0].record()
-        step(dev_batch)
+        run_step(static_batch)
         ev[i][1].record()
     barrier()
-    sampler.stop_flag = True
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---------------- per-kernel CUDA-event pass (roofline): same step, eager launches bracketed by events ----
+    ncls = lib.fneus_prof_classes()
+    import ctypes
+    ms_c = (ctypes.c_double * ncls)(); ln_c = (ctypes.c_longlong * ncls)()
+    fl_c = (ctypes.c_double * ncls)(); by_c = (ctypes.c_double * ncls)()
+    lib.fneus_prof_collect(None, None, None, None)
+    lib.fneus_prof_enable(1)
+    prof_steps = min(args.steps, 5)
+    pev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    barrier()
+    pev[0].record()
+    for i in range(prof_steps):
+        step(dev_batch)
+    pev[1].record()
+    barrier()
+    sampler.stop_flag = True
+    prof_ms = pev[0].elapsed_time(pev[1])
     L.check(lib.fneus_prof_collect(ms_c, ln_c, fl_c, by_c), "prof_collect")
     lib.fneus_prof_enable(0)
-    launches = int(sum(ln_c))
+    launches = int(sum(ln_c)) // max(1, prof_steps) * args.steps
 
     # ---------------- end-to-end timed region (host buffers) -----------------------------------
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -227,7 +271,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         batch = host.to(dev, non_blocking=True)                             # H2D of this step's rays [B,10]
-        loss = step(batch)
+        loss = run_step(batch)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)        # D2H of the step's result
         torch.cuda.synchronize()
         t_e2e += time.perf_counter() - t0
@@ -243,8 +287,8 @@ def run_ours(args):
         value = total_rays / (dev_ms * 1e-3)
         e2e_v = total_rays / (e2e_ms * 1e-3)
         names = ["gemm_fwd", "gemm_bwd_data", "gemm_wgrad", "sampling", "composite", "elementwise", "tc_mlp"]
-        per_class = {names[c]: {"ms_per_step": ms_c[c] / args.steps, "launches_per_step": ln_c[c] / args.steps,
-                                "gflop_per_step": fl_c[c] / args.steps / 1e9} for c in range(ncls)}
+        per_class = {names[c]: {"ms_per_step": ms_c[c] / prof_steps, "launches_per_step": ln_c[c] / prof_steps,
+                                "gflop_per_step": fl_c[c] / prof_steps / 1e9} for c in range(ncls)}
         # dominant kernel: the dense-layer GEMMs (one kernel template, three operand layouts)
         gemm_ms = ms_c[0] + ms_c[1] + ms_c[2] + ms_c[6]
         gemm_fl = fl_c[0] + fl_c[1] + fl_c[2] + fl_c[6]
@@ -258,6 +302,7 @@ def run_ours(args):
                                    "Adam), 64+64 samples, 4 up-sample steps, sphere-SDF scene at geometric init",
                        "rays_per_gpu_per_step": B, "global_rays_per_step": B * world, "parallelism": "dp%d" % world,
                        "l2": "256 MiB flush between timed iterations; per-step working set ~1.5 GB >> 126 MB L2",
+                       "cuda_graph": graph is not None,
                        "precision_path": "bf16 operands on tcgen05, fp32 accumulate/activations" if args.precision == "bf16"
                        else "fp32-simt"},
             "e2e": {"value": e2e_v, "unit": "rays/s", "h2d_bytes_per_step": host.numel() * 4 * world,
@@ -267,7 +312,9 @@ def run_ours(args):
                          "frac": achieved / pk["tf_sust"], "traffic": None, "peak_source": pk["src"],
                          "kernel": ("tc_gemm_mk_kernel/tc_gemm_wgrad_kernel (tcgen05 dense MLP layers)" if args.precision == "bf16"
                                     else "gemm_mk_kernel/gemm_wgrad_kernel (dense MLP layers)"),
-                         "kernel_share_of_step": gemm_ms / dev_ms,
+                         "kernel_share_of_step": (gemm_ms / prof_steps) / (dev_ms / args.steps),
+                         "measured": "CUDA events around every launch of %d eager steps (%.2f ms/step with events)"
+                                     % (prof_steps, prof_ms / prof_steps),
                          "step_algorithmic_tflops": FLOP_PER_RAY_TRAIN_WMASK * value / 1e12},
             "kernel_classes": per_class,
             "clocks": sampler.summary(),
@@ -289,6 +336,7 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=128, help="rays per step of the CPU reference arm")
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the whole-step CUDA graph")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="dense layers: bf16 = tcgen05 tensor cores (FP32 accumulate), fp32 = CUDA-core anchor")
     args = ap.parse_args()

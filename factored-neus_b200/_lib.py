@@ -60,6 +60,7 @@ _SIGNATURES = {
     "fneus_num_sms": (c_int, []),
     "fneus_set_precision": (c_int, [c_int]),
     "fneus_get_precision": (c_int, []),
+    "fneus_debug_flags": (c_int, [c_int]),
     "fneus_debug_gemm": (c_int, [c_int, _P, c_int, _P, c_int, _P, _LL, c_int, c_int, _P, c_int, _P]),
     "fneus_prof_classes": (c_int, []),
     "fneus_prof_enable": (c_int, [c_int]),

@@ -39,6 +39,9 @@ struct GenSpec {
   int deriv;
   GenItem it[4];
 };
+__device__ __forceinline__ void sincos_any(float a, bool fast, float* s, float* c) {
+  if (fast) { *s = __sinf(a); *c = __cosf(a); } else { sincosf(a, s, c); }
+}
 
 __host__ __device__ inline int pe_dim(int d, int multires) { return d * (1 + 2 * multires); }
 
@@ -107,5 +110,42 @@ __device__ __forceinline__ float softplus_grad_from_act(float h, float beta) {
   return z > 20.f ? 1.f : -expm1f(-z);
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// MUFU-based, branch-free variants for the BF16 tensor-core path (results are consumed at BF16 precision; the
+// FP32 anchor path keeps the accurate library versions above).  One ex2/lg2/rcp.approx.ftz each, no range fix-ups,
+// so that the epilogue's rows interleave freely (the branchy versions serialised on their dependent chains).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float softplus_beta_fast(float a, float beta, float inv_beta) {
+  float z = a * beta;
+  float sp = lg2_approx(1.f + ex2_approx(fminf(z, 30.f) * 1.4426950408889634f)) * (0.6931471805599453f * inv_beta);
+  return z > 20.f ? a : sp;
+}
+__device__ __forceinline__ float softplus_grad_from_pre_fast(float a, float beta) {
+  float z = a * beta;
+  float sg = rcp_approx(1.f + ex2_approx(fmaxf(-z, -30.f) * 1.4426950408889634f));
+  return z > 20.f ? 1.f : sg;
+}
+__device__ __forceinline__ float softplus_grad_from_act_fast(float h, float beta) {
+  float z = h * beta;
+  float sg = 1.f - ex2_approx(-z * 1.4426950408889634f);
+  return z > 20.f ? 1.f : sg;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  return rcp_approx(1.f + ex2_approx(fminf(-x, 80.f) * 1.4426950408889634f));
+}
 
 }  // namespace fneus

@@ -50,6 +50,7 @@ struct Epi {
   const float* rs; float rscale;
   float beta;
   float* out0; float out0_scale;
+  int dbg;
 };
 
 inline Epi epi_default() {
@@ -57,13 +58,47 @@ inline Epi epi_default() {
   e.mode = EPI_LINEAR; e.bias = nullptr; e.oscale = 1.f; e.C = nullptr; e.ldc = 0; e.C2 = nullptr; e.ldc2 = 0;
   e.csplit = 1 << 30; e.accumulate2 = 0; e.H = nullptr; e.ldh = 0; e.hscale = 1.f; e.H2 = nullptr; e.ldh2 = 0;
   e.Q = nullptr; e.ldq = 0; e.rvec = nullptr; e.rs = nullptr; e.rscale = 1.f; e.beta = 100.f; e.out0 = nullptr;
-  e.out0_scale = 1.f;
+  e.out0_scale = 1.f; e.dbg = 0;
   return e;
 }
 
 constexpr int GB_M = 128, GB_N = 128, GB_K = 16, GB_PAD = 4, GB_THREADS = 256;
 
-__device__ __forceinline__ void epilogue_store(const Epi& e, long long m, int n, float acc) {
+// Addresses of the auxiliary operands the epilogue of element (m, n) reads (nullptr = none); split from the
+// arithmetic so that tile epilogues can issue all their loads before consuming them.
+__device__ __forceinline__ void epilogue_aux(const Epi& e, long long m, int n, const float*& hp, const float*& qp) {
+  hp = nullptr; qp = nullptr;
+  switch (e.mode) {
+    case EPI_SPMUL:
+      if (n < e.csplit) hp = e.H + m * e.ldh + n;
+      break;
+    case EPI_SWEEP:
+      hp = e.H + m * e.ldh + n; qp = e.Q + m * e.ldq + n;
+      break;
+    case EPI_SDF_BWD:
+      if (n < e.csplit) { hp = e.H + m * e.ldh + n; if (e.Q) qp = e.Q + m * e.ldq + n; }
+      break;
+    case EPI_RELUMASK:
+      if (n < e.csplit) { if (e.H && e.C) hp = e.H + m * e.ldh + n; }
+      else if (e.C2) {
+        if (e.H2) hp = e.H2 + m * e.ldh2 + (n - e.csplit);
+        if (e.accumulate2) qp = e.C2 + m * e.ldc2 + (n - e.csplit);
+      }
+      break;
+    case EPI_LINEAR_ADD:
+      if (e.Q) qp = e.Q + m * e.ldq + n;
+      break;
+    default: break;
+  }
+}
+
+// h, q: values at the addresses reported by epilogue_aux (ignored when that address was nullptr)
+template <bool FAST = false>
+__device__ __forceinline__ void epilogue_apply(const Epi& e, long long m, int n, float acc, float h, float q) {
+  auto sp = [&](float v) { return FAST ? softplus_beta_fast(v, e.beta, 1.f / e.beta) : softplus_beta(v, e.beta); };
+  auto sp_pre = [&](float v) { return FAST ? softplus_grad_from_pre_fast(v, e.beta) : softplus_grad_from_pre(v, e.beta); };
+  auto sp_act = [&](float v) { return FAST ? softplus_grad_from_act_fast(v, e.beta) : softplus_grad_from_act(v, e.beta); };
+  auto sg = [&](float v) { return FAST ? sigmoid_fast(v) : sigmoidf_(v); };
   switch (e.mode) {
     case EPI_LINEAR: {
       float v = acc + (e.bias ? __ldg(e.bias + n) : 0.f);
@@ -75,16 +110,16 @@ __device__ __forceinline__ void epilogue_store(const Epi& e, long long m, int n,
     } break;
     case EPI_SIGMOID: {
       float v = acc + (e.bias ? __ldg(e.bias + n) : 0.f);
-      e.C[m * e.ldc + n] = sigmoidf_(v);
+      e.C[m * e.ldc + n] = sg(v);
     } break;
     case EPI_SOFTPLUS: {
       float v = acc + __ldg(e.bias + n);
-      e.C[m * e.ldc + n] = softplus_beta(v, e.beta) * e.oscale;
+      e.C[m * e.ldc + n] = sp(v) * e.oscale;
     } break;
     case EPI_SOFTPLUS_Q: {
       float v = acc + __ldg(e.bias + n);
-      e.C[m * e.ldc + n] = softplus_beta(v, e.beta) * e.oscale;
-      e.Q[m * e.ldq + n] = softplus_grad_from_pre(v, e.beta) * __ldg(e.rvec + n);
+      e.C[m * e.ldc + n] = sp(v) * e.oscale;
+      e.Q[m * e.ldq + n] = sp_pre(v) * __ldg(e.rvec + n);
     } break;
     case EPI_SDF_OUT: {
       float v = acc + __ldg(e.bias + n);
@@ -93,24 +128,23 @@ __device__ __forceinline__ void epilogue_store(const Epi& e, long long m, int n,
     } break;
     case EPI_SPMUL: {
       if (n < e.csplit) {
-        float s = softplus_grad_from_act(__ldg(e.H + m * e.ldh + n) * e.hscale, e.beta);
+        float s = sp_act(h * e.hscale);
         e.C[m * e.ldc + n] = s * acc * e.oscale;
       } else if (e.C2) {
         e.C2[m * e.ldc2 + (n - e.csplit)] = acc * e.oscale;
       }
     } break;
     case EPI_SWEEP: {
-      float s = softplus_grad_from_act(__ldg(e.H + m * e.ldh + n) * e.hscale, e.beta);
+      float s = sp_act(h * e.hscale);
       e.C[m * e.ldc + n] = s * acc * e.oscale;
-      float q = e.Q[m * e.ldq + n];
       e.Q[m * e.ldq + n] = e.beta * (1.f - s) * q * acc;
     } break;
     case EPI_SDF_BWD: {
       if (n < e.csplit) {
-        float s = softplus_grad_from_act(__ldg(e.H + m * e.ldh + n) * e.hscale, e.beta);
+        float s = sp_act(h * e.hscale);
         float v = acc;
         if (e.rs) v += __ldg(e.rs + m) * __ldg(e.rvec + n) * e.rscale;
-        float add = e.Q ? e.Q[m * e.ldq + n] : 0.f;
+        float add = e.Q ? q : 0.f;
         e.C[m * e.ldc + n] = s * v * e.oscale + add;
       }
     } break;
@@ -119,20 +153,28 @@ __device__ __forceinline__ void epilogue_store(const Epi& e, long long m, int n,
         if (e.C) {
           float v = acc;
           if (e.rs) v += __ldg(e.rs + m) * __ldg(e.rvec + n) * e.rscale;
-          e.C[m * e.ldc + n] = e.H ? (__ldg(e.H + m * e.ldh + n) > 0.f ? v : 0.f) : v;
+          e.C[m * e.ldc + n] = e.H ? (h > 0.f ? v : 0.f) : v;
         }
       } else if (e.C2) {
         int c = n - e.csplit;
-        float v = e.H2 ? (__ldg(e.H2 + m * e.ldh2 + c) > 0.f ? acc : 0.f) : acc;
-        if (e.accumulate2) v += e.C2[m * e.ldc2 + c];
+        float v = e.H2 ? (h > 0.f ? acc : 0.f) : acc;
+        if (e.accumulate2) v += q;
         e.C2[m * e.ldc2 + c] = v;
       }
     } break;
     case EPI_LINEAR_ADD: {
-      float v = acc + (e.Q ? e.Q[m * e.ldq + n] : 0.f);
+      float v = acc + (e.Q ? q : 0.f);
       e.C[m * e.ldc + n] = v * e.oscale;
     } break;
   }
+}
+
+__device__ __forceinline__ void epilogue_store(const Epi& e, long long m, int n, float acc) {
+  const float *hp, *qp;
+  epilogue_aux(e, m, n, hp, qp);
+  float h = hp ? __ldg(hp) : 0.f;
+  float q = qp ? *qp : 0.f;
+  epilogue_apply<false>(e, m, n, acc, h, q);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@
 
 namespace fneus {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 2, TC_THREADS = 160;
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 2, TC_THREADS = 192;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BK * 2;            // 32 KB (max)
 
@@ -36,6 +36,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -121,6 +133,139 @@ __device__ __forceinline__ void sts_mnmajor(uint8_t* tile, int kk, int n, float4
   *reinterpret_cast<uint2*>(tile + off) = pack_bf16x4(v);
 }
 
+// Warp-local transpose of a 32(rows) x 32(cols) accumulator chunk through shared memory so that the fused epilogue
+// touches global memory with lanes along the contiguous (column) axis.
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+
+// Fused epilogue of one 32-row x 32-column accumulator chunk held (transposed) in this warp's shared-memory
+// buffer: lane = column, so every global access is a coalesced 128-byte row segment.  MODE is a template
+// parameter (one specialised loop per epilogue kind), per-column constants (bias, rvec, split side, pointers)
+// are hoisted, auxiliary operands of 8 rows are fetched before use.  MUFU-based softplus/sigmoid.
+template <int MODE>
+__device__ __forceinline__ void epilogue_rows(const Epi& e, uint32_t wb, long long mrow0, int rows, int n, int lane) {
+  const bool prim = n < e.csplit;
+  const float beta = e.beta, inv_beta = 1.f / e.beta, oscale = e.oscale, hscale = e.hscale;
+  float bias_n = 0.f, rvec_n = 0.f;
+  if (MODE == EPI_LINEAR || MODE == EPI_RELU || MODE == EPI_SIGMOID || MODE == EPI_SOFTPLUS ||
+      MODE == EPI_SOFTPLUS_Q || MODE == EPI_SDF_OUT)
+    bias_n = e.bias ? __ldg(e.bias + n) : 0.f;
+  if (MODE == EPI_SOFTPLUS_Q) rvec_n = __ldg(e.rvec + n);
+  const bool rank1 = (MODE == EPI_SDF_BWD || MODE == EPI_RELUMASK) && e.rs != nullptr && prim;
+  if (rank1) rvec_n = __ldg(e.rvec + n) * e.rscale;
+
+  // primary / secondary destinations and auxiliary sources for THIS column
+  float* dst = nullptr; long long ldd = 0;
+  const float* hsrc = nullptr; long long ldh = 0;
+  float* qptr = nullptr; long long ldq = 0;       // read (and for SWEEP written) auxiliary
+  bool q_is_acc = false;                           // RELUMASK secondary accumulate: q aliases the destination
+  if (MODE == EPI_SDF_OUT) {
+    if (n == 0) { dst = e.out0 + mrow0; ldd = 1; }
+    else if (e.C) { dst = e.C + mrow0 * e.ldc + (n - 1); ldd = e.ldc; }
+  } else if (prim) {
+    if (e.C) { dst = e.C + mrow0 * e.ldc + n; ldd = e.ldc; }
+    if (MODE == EPI_SPMUL || MODE == EPI_SWEEP || MODE == EPI_SDF_BWD || (MODE == EPI_RELUMASK && e.H && e.C)) {
+      hsrc = e.H + mrow0 * e.ldh + n; ldh = e.ldh;
+    }
+    if ((MODE == EPI_SWEEP) || ((MODE == EPI_SDF_BWD || MODE == EPI_LINEAR_ADD) && e.Q)) {
+      qptr = e.Q + mrow0 * e.ldq + n; ldq = e.ldq;
+    }
+    if (MODE == EPI_SOFTPLUS_Q) { qptr = e.Q + mrow0 * e.ldq + n; ldq = e.ldq; }
+  } else {
+    const int c = n - e.csplit;
+    if ((MODE == EPI_SPMUL || MODE == EPI_RELUMASK) && e.C2) { dst = e.C2 + mrow0 * e.ldc2 + c; ldd = e.ldc2; }
+    if (MODE == EPI_RELUMASK && e.C2) {
+      if (e.H2) { hsrc = e.H2 + mrow0 * e.ldh2 + c; ldh = e.ldh2; }
+      if (e.accumulate2) { qptr = dst; ldq = ldd; q_is_acc = true; }
+    }
+  }
+  const bool need_q_load = (MODE == EPI_SWEEP || MODE == EPI_SDF_BWD || MODE == EPI_LINEAR_ADD || q_is_acc) && qptr;
+  const float* rs = rank1 ? e.rs + mrow0 : nullptr;
+
+#pragma unroll 1
+  for (int r0 = 0; r0 < rows; r0 += 8) {
+    float acc[8], h[8], q[8], rsv[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const bool ok = r0 + r < rows;
+      acc[r] = lds_f32(wb + (uint32_t)((r0 + r) * 33 + lane) * 4u);
+      h[r] = (hsrc && ok) ? __ldg(hsrc + (long long)(r0 + r) * ldh) : 0.f;
+      q[r] = (need_q_load && ok) ? qptr[(long long)(r0 + r) * ldq] : 0.f;
+      rsv[r] = (rs && ok) ? __ldg(rs + r0 + r) : 0.f;
+    }
+    // branch-free arithmetic for all 8 rows first (independent chains interleave), predicated stores after
+    float y[8], y2[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      float a = acc[r];
+      y2[r] = 0.f;
+      if (MODE == EPI_LINEAR) y[r] = (a + bias_n) * oscale;
+      else if (MODE == EPI_RELU) y[r] = fmaxf(a + bias_n, 0.f);
+      else if (MODE == EPI_SIGMOID) y[r] = sigmoid_fast(a + bias_n);
+      else if (MODE == EPI_SOFTPLUS) y[r] = softplus_beta_fast(a + bias_n, beta, inv_beta) * oscale;
+      else if (MODE == EPI_SOFTPLUS_Q) {
+        float v = a + bias_n;
+        y[r] = softplus_beta_fast(v, beta, inv_beta) * oscale;
+        y2[r] = softplus_grad_from_pre_fast(v, beta) * rvec_n;
+      } else if (MODE == EPI_SDF_OUT) y[r] = (n == 0) ? (a + bias_n) * e.out0_scale : (a + bias_n);
+      else if (MODE == EPI_SPMUL) y[r] = prim ? softplus_grad_from_act_fast(h[r] * hscale, beta) * a * oscale : a * oscale;
+      else if (MODE == EPI_SWEEP) {
+        float sg = softplus_grad_from_act_fast(h[r] * hscale, beta);
+        y[r] = sg * a * oscale;
+        y2[r] = beta * (1.f - sg) * q[r] * a;
+      } else if (MODE == EPI_SDF_BWD) {
+        float sg = softplus_grad_from_act_fast(h[r] * hscale, beta);
+        y[r] = sg * (a + rsv[r] * rvec_n) * oscale + q[r];
+      } else if (MODE == EPI_RELUMASK) {
+        float v = a + rsv[r] * rvec_n;
+        if (hsrc) v = h[r] > 0.f ? v : 0.f;
+        y[r] = v + q[r];
+      } else y[r] = (a + q[r]) * oscale;   // EPI_LINEAR_ADD
+    }
+    const bool st_ok = dst != nullptr && !(MODE == EPI_SDF_BWD && !prim);
+    const bool st2_ok = (MODE == EPI_SOFTPLUS_Q || MODE == EPI_SWEEP) && qptr != nullptr;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const long long ro = r0 + r;
+      if (st_ok && r0 + r < rows) dst[ro * ldd] = y[r];
+      if (st2_ok && r0 + r < rows) qptr[ro * ldq] = y2[r];
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_chunk(const Epi& e, float* wbuf, const float* v, long long mrow0, int M,
+                                               int ncol0, int nvalid_cols, int lane) {
+  const uint32_t wb = smem_u32(wbuf);
+#pragma unroll
+  for (int j = 0; j < 32; j++) sts_f32(wb + (uint32_t)(lane * 33 + j) * 4u, v[j]);
+  __syncwarp();
+  long long left = (long long)M - mrow0;
+  const int rows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+  if (lane < nvalid_cols && rows > 0 && !(e.dbg & 8)) {
+    const int n = ncol0 + lane;
+    switch (e.mode) {
+      case EPI_LINEAR: epilogue_rows<EPI_LINEAR>(e, wb, mrow0, rows, n, lane); break;
+      case EPI_RELU: epilogue_rows<EPI_RELU>(e, wb, mrow0, rows, n, lane); break;
+      case EPI_SIGMOID: epilogue_rows<EPI_SIGMOID>(e, wb, mrow0, rows, n, lane); break;
+      case EPI_SOFTPLUS: epilogue_rows<EPI_SOFTPLUS>(e, wb, mrow0, rows, n, lane); break;
+      case EPI_SOFTPLUS_Q: epilogue_rows<EPI_SOFTPLUS_Q>(e, wb, mrow0, rows, n, lane); break;
+      case EPI_SDF_OUT: epilogue_rows<EPI_SDF_OUT>(e, wb, mrow0, rows, n, lane); break;
+      case EPI_SPMUL: epilogue_rows<EPI_SPMUL>(e, wb, mrow0, rows, n, lane); break;
+      case EPI_SWEEP: epilogue_rows<EPI_SWEEP>(e, wb, mrow0, rows, n, lane); break;
+      case EPI_SDF_BWD: epilogue_rows<EPI_SDF_BWD>(e, wb, mrow0, rows, n, lane); break;
+      case EPI_RELUMASK: epilogue_rows<EPI_RELUMASK>(e, wb, mrow0, rows, n, lane); break;
+      case EPI_LINEAR_ADD: epilogue_rows<EPI_LINEAR_ADD>(e, wb, mrow0, rows, n, lane); break;
+    }
+  }
+  __syncwarp();
+}
+
 struct TcSmem {
   uint64_t full[TC_STAGES];
   uint64_t empty[TC_STAGES];
@@ -142,7 +287,8 @@ __device__ __forceinline__ float4 ldw4(const float* p, bool v0, bool v1, bool v2
 // ---------------------------------------------------------------------------------------------
 template <bool WT>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-tc_gemm_mk_kernel(ASeg a, const float* __restrict__ W, int ldw, int wout0, int M, int N, Epi e) {
+tc_gemm_mk_kernel(ASeg a, const float* __restrict__ W, int ldw, int wout0, int M, int N, Epi e,
+                  const uint8_t* __restrict__ wimg) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA[TC_STAGES];
@@ -165,7 +311,7 @@ tc_gemm_mk_kernel(ASeg a, const float* __restrict__ W, int ldw, int wout0, int M
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TC_STAGES; s++) { mbar_init(&ctl->full[s], 128); mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < TC_STAGES; s++) { mbar_init(&ctl->full[s], wimg ? 129 : 128); mbar_init(&ctl->empty[s], 1); }
     mbar_init(&ctl->accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -175,7 +321,19 @@ tc_gemm_mk_kernel(ASeg a, const float* __restrict__ W, int ldw, int wout0, int M
   tc_fence_after();
   const uint32_t tmem_d = ctl->tmem_base;
 
-  if (warp < 4) {
+  if (warp == 5) {
+    // ------------------------------ weight-image loader (bulk async copies) ------------------------------
+    if (wimg && lane == 0) {
+      const uint32_t bytes = WT ? (uint32_t)Nc * 128u : (uint32_t)((Nc + 63) / 64) * 8192u;
+      const uint8_t* src = wimg + (size_t)blockIdx.y * KB * TC_B_BYTES;
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % TC_STAGES;
+        if (kb >= TC_STAGES) mbar_wait(&ctl->empty[s], ((kb / TC_STAGES) - 1) & 1);
+        mbar_arrive_expect_tx(&ctl->full[s], bytes);
+        bulk_g2s(sB[s], src + (size_t)kb * TC_B_BYTES, bytes, &ctl->full[s]);
+      }
+    }
+  } else if (warp < 4) {
     // ------------------------------ producers ------------------------------
     for (int kb = 0; kb < KB; kb++) {
       const int s = kb % TC_STAGES;
@@ -185,14 +343,28 @@ tc_gemm_mk_kernel(ASeg a, const float* __restrict__ W, int ldw, int wout0, int M
       const int kmax = phase == 0 ? a.gen.ncols : a.kmem;
       const int wred0 = phase == 0 ? a.wred_gen : a.wred_mem;
       // A tile: 128 rows x 64 k
-#pragma unroll 4
-      for (int it = 0; it < 16; it++) {
-        int idx = it * 128 + tid;
-        int r = idx >> 4, k = (idx & 15) << 2;
-        float4 v = load_a4(a, phase, m0 + r, M, k0 + k);
-        sts_kmajor(sA[s], r, k, v);
+      if (phase == 0) {
+#pragma unroll 1
+        for (int it = 0; it < 16; it++) {
+          int idx = it * 128 + tid;
+          sts_kmajor(sA[s], idx >> 4, (idx & 15) << 2, load_a4(a, 0, m0 + (idx >> 4), M, k0 + ((idx & 15) << 2)));
+        }
+      } else {
+        float4 av[16];
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+          int idx = it * 128 + tid;
+          av[it] = load_a4(a, 1, m0 + (idx >> 4), M, k0 + ((idx & 15) << 2));
+        }
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+          int idx = it * 128 + tid;
+          sts_kmajor(sA[s], idx >> 4, (idx & 15) << 2, av[it]);
+        }
       }
-      if (WT) {
+      if (wimg) {
+        // B tile arrives by bulk copy (warp 5)
+      } else if (WT) {
         // B tile K-major: rows n (Nc), 64 k ; W[(wout0+n)*ldw + wred0 + k]
         for (int idx = tid; idx < Nc * 16; idx += 128) {
           int r = idx >> 4, k = (idx & 15) << 2;
@@ -220,21 +392,20 @@ tc_gemm_mk_kernel(ASeg a, const float* __restrict__ W, int ldw, int wout0, int M
     // ------------------------------ epilogue ------------------------------
     mbar_wait(&ctl->accum, 0);
     tc_fence_after();
-    const long long m = m0 + tid;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float* wbuf = reinterpret_cast<float*>(sB[0]) + warp * (32 * 33);     // stage buffers are free now
+#pragma unroll 1
     for (int c0 = 0; c0 < Nc; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_d + lane_base + c0, v);
-      if (m < M) {
+      if (KB == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          int n = n0 + c0 + j;
-          if (c0 + j < nvalid) epilogue_store(e, m, n, KB > 0 ? v[j] : 0.f);
-        }
+        for (int j = 0; j < 32; j++) v[j] = 0.f;
       }
+      epilogue_chunk(e, wbuf, v, m0 + warp * 32, M, n0 + c0, nvalid - c0, lane);
     }
     tc_fence_before();
-  } else if (lane == 0) {
+  } else if (warp == 4 && lane == 0) {
     // ------------------------------ MMA issuer ------------------------------
     const uint32_t idesc = make_idesc(Nc, 0, WT ? 0 : 1);
     for (int kb = 0; kb < KB; kb++) {
@@ -316,46 +487,75 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __res
       if (kb >= TC_STAGES) mbar_wait(&ctl->empty[s], ((kb / TC_STAGES) - 1) & 1);
       const long long mb = mbeg + (long long)kb * TC_BK;
       // A operand (dY^T), MN-major: 64 m-rows x 128 n
-#pragma unroll 4
-      for (int it = 0; it < 16; it++) {
-        int mr = it * 4 + (tid >> 5);
-        long long m = mb + mr;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < mend && bn < nvalid) {
-          v = __ldg(reinterpret_cast<const float4*>(dY + m * ldy + n0 + bn));
+      {
+        float4 yv[16];
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+          long long m = mb + it * 4 + (tid >> 5);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < mend && bn < nvalid) v = __ldg(reinterpret_cast<const float4*>(dY + m * ldy + n0 + bn));
+          yv[it] = v;
+        }
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+          float4 v = yv[it];
           if (bn + 1 >= nvalid) v.y = 0.f;
           if (bn + 2 >= nvalid) v.z = 0.f;
           if (bn + 3 >= nvalid) v.w = 0.f;
+          if (do_bias) { bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w; }
+          sts_mnmajor(sA[s], it * 4 + (tid >> 5), bn, v);
         }
-        if (do_bias) { bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w; }
-        sts_mnmajor(sA[s], mr, bn, v);
       }
-      // B operand (A rows), MN-major: 64 m-rows x Nc k
-      const int nq = Nc >> 2;
-      for (int idx = tid; idx < 64 * nq; idx += 128) {
-        int mr = idx / nq, k = (idx - mr * nq) << 2;
-        long long m = mb + mr;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < mend) v = load_a4(a, phase, m, M, k0 + k);
-        sts_mnmajor(sB[s], mr, k, v);
+      // B operand (A rows), MN-major: 64 m-rows x Nc k ; thread -> column group (tid % 64)*4, rows (tid/64) + 2*it
+      if (phase == 1) {
+        const int kq = (tid & 63) << 2;
+        if (kq < Nc) {
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            float4 xv[16];
+#pragma unroll
+            for (int it = 0; it < 16; it++) {
+              long long m = mb + (tid >> 6) + 2 * (half * 16 + it);
+              xv[it] = (m < mend) ? load_a4(a, 1, m, M, k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int it = 0; it < 16; it++) sts_mnmajor(sB[s], (tid >> 6) + 2 * (half * 16 + it), kq, xv[it]);
+          }
+        }
+      } else {
+        const int nq = Nc >> 2;
+#pragma unroll 1
+        for (int idx = tid; idx < 64 * nq; idx += 128) {
+          int mr = idx / nq, k = (idx - mr * nq) << 2;
+          long long m = mb + mr;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < mend) v = load_a4(a, 0, m, M, k0 + k);
+          sts_mnmajor(sB[s], mr, k, v);
+        }
       }
       fence_proxy_async();
       mbar_arrive(&ctl->full[s]);
     }
     mbar_wait(&ctl->accum, 0);
     tc_fence_after();
-    const int n = n0 + tid;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float* wbuf = reinterpret_cast<float*>(sB[0]) + warp * (32 * 33);
     if (KB > 0) {
       for (int c0 = 0; c0 < Nc; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_d + lane_base + c0, v);
-        if (tid < nvalid) {
-          float* dst = dW + (long long)(wout0 + n) * ldw + wred0 + k0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (c0 + j < kvalid) atomicAdd(dst + j, v[j]);
+        for (int j = 0; j < 32; j++) wbuf[lane * 33 + j] = v[j];
+        __syncwarp();
+        if (c0 + lane < kvalid) {
+#pragma unroll 4
+          for (int r = 0; r < 32; r++) {
+            int nn = warp * 32 + r;
+            if (nn < nvalid)
+              atomicAdd(dW + (long long)(wout0 + n0 + nn) * ldw + wred0 + k0 + c0 + lane, wbuf[r * 33 + lane]);
+          }
         }
+        __syncwarp();
       }
       if (do_bias) {
         if (bn + 0 < nvalid) atomicAdd(db + wout0 + n0 + bn + 0, bsum.x);
@@ -365,7 +565,7 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __res
       }
     }
     tc_fence_before();
-  } else if (lane == 0) {
+  } else if (warp == 4 && lane == 0) {
     const uint32_t idesc = make_idesc(Nc, 1, 1);
     for (int kb = 0; kb < KB; kb++) {
       const int s = kb % TC_STAGES;
@@ -390,31 +590,290 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent, warp-specialised variant of tc_gemm_mk (needs a weight image): one CTA per SM loops over
+// output tiles; the epilogue of tile i (8 warps) overlaps the operand loads + MMAs of tile i+1 through two
+// TMEM accumulator stages (2 x 256 columns).
+//   warps 0-7  : A producers, two groups of 4 handling alternate reduction blocks (two blocks of loads in flight)
+//   warp  8    : MMA issuer (+ TMEM alloc)        warp 9 : weight-image bulk-copy loader
+//   warps 10-17: epilogue, two groups of 4 (TMEM lane quarter = warp % 4) handling alternate 32-column chunks
+// ---------------------------------------------------------------------------------------------
+constexpr int P_STAGES = 4, P_THREADS = 576;
+inline int& tc_debug_flags() { static int f = 0; return f; }   // bit0: no A loads, bit1: no epilogue, bit2: no MMA
+struct PSmem {
+  uint64_t full[P_STAGES];
+  uint64_t empty[P_STAGES];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+constexpr int P_WBUF_BYTES = 8 * 32 * 33 * 4;
+constexpr int P_SMEM_BYTES = P_STAGES * (TC_A_BYTES + TC_B_BYTES) + P_WBUF_BYTES + 1024 + 256;
+
+template <bool WT>
+__global__ void __launch_bounds__(P_THREADS, 1)
+tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restrict__ wimg, int dbg) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA[P_STAGES];
+  uint8_t* sB[P_STAGES];
+#pragma unroll
+  for (int s = 0; s < P_STAGES; s++) {
+    sA[s] = base + s * (TC_A_BYTES + TC_B_BYTES);
+    sB[s] = sA[s] + TC_A_BYTES;
+  }
+  float* wbuf_all = reinterpret_cast<float*>(base + P_STAGES * (TC_A_BYTES + TC_B_BYTES));
+  PSmem* ctl = reinterpret_cast<PSmem*>(base + P_STAGES * (TC_A_BYTES + TC_B_BYTES) + P_WBUF_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_m = (M + TC_BM - 1) / TC_BM;
+  const int tiles_n = (N + 255) / 256;
+  const int ntiles = tiles_m * tiles_n;
+  const int kb_gen = (a.gen.ncols + TC_BK - 1) / TC_BK;
+  const int kb_mem = (a.kmem + TC_BK - 1) / TC_BK;
+  const int KB = kb_gen + kb_mem;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < P_STAGES; s++) { mbar_init(&ctl->full[s], 129); mbar_init(&ctl->empty[s], 1); }
+#pragma unroll
+    for (int s = 0; s < 2; s++) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_empty[s], 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp < 8) {
+    // ------------------------------ A producers ------------------------------
+    const int grp = warp >> 2, ptid = tid & 127;
+    int kbg = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const long long m0 = (long long)(t % tiles_m) * TC_BM;
+      for (int kb = 0; kb < KB; kb++, kbg++) {
+        if ((kbg & 1) != grp) continue;
+        const int s = kbg % P_STAGES;
+        if (kbg >= P_STAGES) mbar_wait(&ctl->empty[s], ((kbg / P_STAGES) - 1) & 1);
+        const int phase = kb < kb_gen ? 0 : 1;
+        const int k0 = (phase == 0 ? kb : kb - kb_gen) * TC_BK;
+        if (phase == 0) {
+#pragma unroll 1
+          for (int it = 0; it < 16; it++) {
+            int idx = it * 128 + ptid;
+            sts_kmajor(sA[s], idx >> 4, (idx & 15) << 2, load_a4(a, 0, m0 + (idx >> 4), M, k0 + ((idx & 15) << 2)));
+          }
+        } else if (!(dbg & 1)) {
+          float4 av[16];
+#pragma unroll
+          for (int it = 0; it < 16; it++) {
+            int idx = it * 128 + ptid;
+            av[it] = load_a4(a, 1, m0 + (idx >> 4), M, k0 + ((idx & 15) << 2));
+          }
+#pragma unroll
+          for (int it = 0; it < 16; it++) {
+            int idx = it * 128 + ptid;
+            sts_kmajor(sA[s], idx >> 4, (idx & 15) << 2, av[it]);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&ctl->full[s]);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------ weight-image loader ------------------------------
+    if (lane == 0) {
+      int kbg = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int nchunk = t / tiles_m;
+        const int nvalid = min(256, N - nchunk * 256);
+        const int Nc = (nvalid + 15) & ~15;
+        const uint32_t bytes = WT ? (uint32_t)Nc * 128u : (uint32_t)((Nc + 63) / 64) * 8192u;
+        const uint8_t* src = wimg + (size_t)nchunk * KB * TC_B_BYTES;
+        for (int kb = 0; kb < KB; kb++, kbg++) {
+          const int s = kbg % P_STAGES;
+          if (kbg >= P_STAGES) mbar_wait(&ctl->empty[s], ((kbg / P_STAGES) - 1) & 1);
+          mbar_arrive_expect_tx(&ctl->full[s], bytes);
+          bulk_g2s(sB[s], src + (size_t)kb * TC_B_BYTES, bytes, &ctl->full[s]);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      int kbg = 0, it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+        const int nchunk = t / tiles_m;
+        const int nvalid = min(256, N - nchunk * 256);
+        const int Nc = (nvalid + 15) & ~15;
+        const uint32_t idesc = make_idesc(Nc, 0, WT ? 0 : 1);
+        const int as = it & 1;
+        if (it >= 2) mbar_wait(&ctl->acc_empty[as], ((it >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * 256;
+        for (int kb = 0; kb < KB; kb++, kbg++) {
+          const int s = kbg % P_STAGES;
+          mbar_wait(&ctl->full[s], (kbg / P_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA[s]), b_addr = smem_u32(sB[s]);
+          if (!(dbg & 4)) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              uint64_t ad = make_desc(a_addr + k * 32, 16, 1024);
+              uint64_t bd = WT ? make_desc(b_addr + k * 32, 16, 1024) : make_desc(b_addr + k * 2048, 8192, 1024);
+              umma_bf16(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1 : 0);
+            }
+          }
+          umma_commit(&ctl->empty[s]);
+        }
+        umma_commit(&ctl->acc_full[as]);
+      }
+      tc_fence_before();
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int ew = warp - 10;                  // 0..7
+    const int grp = ew >> 2;                   // column-chunk parity handled by this warp
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    float* wbuf = wbuf_all + ew * (32 * 33);
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+      const long long m0 = (long long)(t % tiles_m) * TC_BM;
+      const int n0 = (t / tiles_m) * 256;
+      const int nvalid = min(256, N - n0);
+      const int Nc = (nvalid + 15) & ~15;
+      const int as = it & 1;
+      mbar_wait(&ctl->acc_full[as], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(quarter * 32) << 16);
+      if (!(dbg & 2)) {
+#pragma unroll 1
+        for (int c0 = grp * 32; c0 < Nc; c0 += 64) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          epilogue_chunk(e, wbuf, v, m0 + quarter * 32, M, n0 + c0, nvalid - c0, lane);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&ctl->acc_empty[as]);
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight images: BF16 copies of a layer's weights laid out as the exact shared-memory tiles the MMA reads
+// (tile = one 256-column chunk x one 64-deep reduction block, 32 KB, 128B-swizzled), so a B tile is one bulk copy.
+// WT : tile rows = output features n, K-major.   !WT: tile rows = reduction index (W rows), MN-major.
+// ---------------------------------------------------------------------------------------------
+inline size_t wimg_bytes(int N, int kgen, int kmem) {
+  return (size_t)cdiv(N, 256) * (cdiv(kgen, TC_BK) + cdiv(kmem, TC_BK)) * TC_B_BYTES;
+}
+template <bool WT>
+__global__ void pack_wimg_kernel(const float* __restrict__ W, int ldw, int wout0, int N, int wred_gen, int kgen,
+                                 int wred_mem, int kmem, uint8_t* __restrict__ img) {
+  const int kb_gen = (kgen + TC_BK - 1) / TC_BK, kb_mem = (kmem + TC_BK - 1) / TC_BK;
+  const int KB = kb_gen + kb_mem;
+  const long long total = (long long)((N + 255) / 256) * KB * 2048;   // 16-byte chunks
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int tile = (int)(idx / 2048), within = (int)(idx % 2048);
+  const int nchunk = tile / KB, kb = tile % KB;
+  const int phase = kb < kb_gen ? 0 : 1;
+  const int k0 = (phase == 0 ? kb : kb - kb_gen) * TC_BK;
+  const int kmax = phase == 0 ? kgen : kmem;
+  const int wred0 = phase == 0 ? wred_gen : wred_mem;
+  const int n0 = nchunk * 256;
+  float v[8];
+  int off;
+  if (WT) {
+    const int r = within >> 3, c = within & 7;              // row n, 16B chunk along k
+    const int n = n0 + r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      int k = k0 + c * 8 + i;
+      v[i] = (n < N && k < kmax) ? __ldg(W + (long long)(wout0 + n) * ldw + wred0 + k) : 0.f;
+    }
+    off = (r >> 3) * 1024 + (r & 7) * 128 + (((c ^ (r & 7)) & 7) << 4);
+  } else {
+    const int nb = within >> 9, rem = within & 511;         // 64-column block, k-row, 16B chunk along n
+    const int kr = rem >> 3, c = rem & 7;
+    const int k = k0 + kr;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      int n = n0 + nb * 64 + c * 8 + i;
+      v[i] = (n < N && k < kmax) ? __ldg(W + (long long)(wred0 + k) * ldw + wout0 + n) : 0.f;
+    }
+    off = nb * 8192 + (kr >> 3) * 1024 + (kr & 7) * 128 + (((c ^ (kr & 7)) & 7) << 4);
+  }
+  uint2 lo = pack_bf16x4(make_float4(v[0], v[1], v[2], v[3]));
+  uint2 hi = pack_bf16x4(make_float4(v[4], v[5], v[6], v[7]));
+  *reinterpret_cast<uint4*>(img + (size_t)tile * TC_B_BYTES + off) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+}
+// transposed = false: image for C = A W^T (forward);  true: image for C = A W (input-gradient chains)
+inline void launch_pack_wimg(bool for_bwd_data, const float* W, int ldw, int wout0, int N, int wred_gen, int kgen,
+                             int wred_mem, int kmem, uint8_t* img, cudaStream_t st) {
+  long long total = (long long)cdiv(N, 256) * (cdiv(kgen, TC_BK) + cdiv(kmem, TC_BK)) * 2048;
+  if (total == 0) return;
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  if (for_bwd_data) pack_wimg_kernel<false><<<cdiv(total, 256), 256, 0, st>>>(W, ldw, wout0, N, wred_gen, kgen, wred_mem, kmem, img);
+  else pack_wimg_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(W, ldw, wout0, N, wred_gen, kgen, wred_mem, kmem, img);
+  prof_end(st);
+}
+
 constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 + 256;
 
+inline int tc_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
 inline int tc_prepare() {
   static int done = 0;
   if (done) return 0;
   cudaError_t e1 = cudaFuncSetAttribute(tc_gemm_mk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaError_t e2 = cudaFuncSetAttribute(tc_gemm_mk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaError_t e3 = cudaFuncSetAttribute(tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return 1;
+  cudaError_t e4 = cudaFuncSetAttribute(tc_gemm_mk_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+  cudaError_t e5 = cudaFuncSetAttribute(tc_gemm_mk_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) return 1;
   done = 1;
   return 0;
 }
 
 inline void launch_tc_fwd(const ASeg& a, const float* W, int ldw, int wout0, long long M, int N, const Epi& e,
-                          cudaStream_t st) {
+                          cudaStream_t st, const uint8_t* wimg) {
   dim3 grid(cdiv(M, TC_BM), cdiv(N, 256));
   prof_begin(PC_TC_MLP, 2.0 * (double)M * N * (a.gen.ncols + a.kmem), 0.0, st);
-  tc_gemm_mk_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, W, ldw, wout0, (int)M, N, e);
+  if (wimg && a.gen.ncols + a.kmem > 0) {
+    int ntiles = grid.x * grid.y, sms = tc_num_sms();
+    Epi e2 = e; e2.dbg = tc_debug_flags();
+    tc_gemm_mk_persistent_kernel<true><<<ntiles < sms ? ntiles : sms, P_THREADS, P_SMEM_BYTES, st>>>(a, (int)M, N, e2, wimg, tc_debug_flags());
+  } else {
+    tc_gemm_mk_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, W, ldw, wout0, (int)M, N, e, wimg);
+  }
   prof_end(st);
 }
 inline void launch_tc_bwd_data(const ASeg& a, const float* W, int ldw, int wout0, long long M, int N, const Epi& e,
-                               cudaStream_t st) {
+                               cudaStream_t st, const uint8_t* wimg) {
   dim3 grid(cdiv(M, TC_BM), cdiv(N, 256));
   prof_begin(PC_TC_MLP, 2.0 * (double)M * N * (a.gen.ncols + a.kmem), 0.0, st);
-  tc_gemm_mk_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, W, ldw, wout0, (int)M, N, e);
+  if (wimg && a.gen.ncols + a.kmem > 0) {
+    int ntiles = grid.x * grid.y, sms = tc_num_sms();
+    tc_gemm_mk_persistent_kernel<false><<<ntiles < sms ? ntiles : sms, P_THREADS, P_SMEM_BYTES, st>>>(a, (int)M, N, e, wimg, tc_debug_flags());
+  } else {
+    tc_gemm_mk_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, W, ldw, wout0, (int)M, N, e, wimg);
+  }
   prof_end(st);
 }
 inline void launch_tc_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, int ldw, int wout0, float* db,
@@ -439,16 +898,37 @@ inline void launch_tc_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, 
 // ---------------------------------------------------------------------------------------------
 inline int& precision_mode() { static int m = 0; return m; }
 
+// A bump allocator over a caller-provided byte region for the weight images of one ABI call.
+struct ImgArena {
+  uint8_t* base; size_t cap, used;
+  uint8_t* take(size_t bytes) {
+    size_t off = (used + 1023) & ~(size_t)1023;
+    if (!base || off + bytes > cap) return nullptr;
+    used = off + bytes;
+    return base + off;
+  }
+};
+// Build (when in BF16 mode and the arena has room) the image a later launch_gemm_fwd / launch_gemm_bwd_data with the
+// same (W, wout0, N, segments) will consume; returns nullptr in FP32 mode (callers just pass it through).
+inline const uint8_t* make_wimg(ImgArena& ar, bool for_bwd_data, const float* W, int ldw, int wout0, int N,
+                                int wred_gen, int kgen, int wred_mem, int kmem, cudaStream_t st) {
+  if (precision_mode() != 1) return nullptr;
+  uint8_t* img = ar.take(wimg_bytes(N, kgen, kmem));
+  if (!img) return nullptr;
+  launch_pack_wimg(for_bwd_data, W, ldw, wout0, N, wred_gen, kgen, wred_mem, kmem, img, st);
+  return img;
+}
+
 inline void launch_gemm_fwd(const ASeg& a, const float* W, int ldw, int wout0, long long M, int N, const Epi& e,
-                            cudaStream_t st) {
+                            cudaStream_t st, const uint8_t* wimg = nullptr) {
   if (M <= 0 || N <= 0) return;
-  if (precision_mode() == 1 && tc_prepare() == 0) launch_tc_fwd(a, W, ldw, wout0, M, N, e, st);
+  if (precision_mode() == 1 && tc_prepare() == 0) launch_tc_fwd(a, W, ldw, wout0, M, N, e, st, wimg);
   else launch_simt_fwd(a, W, ldw, wout0, M, N, e, st);
 }
 inline void launch_gemm_bwd_data(const ASeg& a, const float* W, int ldw, int wout0, long long M, int N,
-                                 const Epi& e, cudaStream_t st) {
+                                 const Epi& e, cudaStream_t st, const uint8_t* wimg = nullptr) {
   if (M <= 0 || N <= 0) return;
-  if (precision_mode() == 1 && tc_prepare() == 0) launch_tc_bwd_data(a, W, ldw, wout0, M, N, e, st);
+  if (precision_mode() == 1 && tc_prepare() == 0) launch_tc_bwd_data(a, W, ldw, wout0, M, N, e, st, wimg);
   else launch_simt_bwd_data(a, W, ldw, wout0, M, N, e, st);
 }
 inline void launch_gemm_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, int ldw, int wout0, float* db,

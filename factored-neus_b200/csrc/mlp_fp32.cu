@@ -159,6 +159,16 @@ static SdfPlan sdf_plan(const fneus_sdf_cfg* c) {
   return p;
 }
 
+// bytes of BF16 weight images one SDF pass may build (forward + input-gradient form of every layer)
+static size_t sdf_img_bytes(const SdfPlan& p) {
+  size_t b = 0;
+  for (int l = 0; l <= p.L; l++) {
+    b += wimg_bytes(p.out[l], l == 0 ? p.in[l] : 0, l == 0 ? 0 : p.in[l]) + 1024;
+    b += wimg_bytes(p.in[l], 0, p.out[l]) + 1024;
+  }
+  return b + 4096;
+}
+
 // saved layout: H_1..H_L ([M, ldin[l]]), Q_0..Q_{L-1} ([M, ldout[l]])
 static long long sdf_saved_per_point(const SdfPlan& p) {
   long long s = 0;
@@ -167,6 +177,9 @@ static long long sdf_saved_per_point(const SdfPlan& p) {
   return s;
 }
 static long long sdf_scratch_per_point(const SdfPlan& p) { return 4LL * p.ldmax + 2LL * round_up(p.e, 4); }
+static long long sdf_scratch_floats(const SdfPlan& p, long long n) {
+  return sdf_scratch_per_point(p) * n + (long long)(sdf_img_bytes(p) / 4) + 256;
+}
 
 struct SdfBufs {
   float* H[20];
@@ -191,7 +204,7 @@ static GenSpec sdf_gen(const fneus_sdf_cfg* c, const float* x, const float* tan)
 // value chain. If bufs != nullptr activations go to bufs->H (saved) else ping-pong in scratch.
 static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, const float* x, long long M,
                            float* sdf_out, float* feat_out, SdfBufs* bufs, float* scratch, cudaStream_t st,
-                           float out_sign = 1.f) {
+                           float out_sign, ImgArena& ar) {
   const float rsqrt2 = 0.70710678118654752440f;
   float* pp[2] = {scratch, scratch + M * p.ldmax};
   const float* Hin = nullptr;
@@ -202,6 +215,11 @@ static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float
     Epi e = epi_default();
     e.beta = c->beta;
     e.bias = b;
+    const bool tc_split_last = (l == p.L) && feat_out && precision_mode() == 1;
+    const uint8_t* img = (l < p.L || tc_split_last)
+        ? make_wimg(ar, false, W, p.in[l], tc_split_last ? 1 : 0, tc_split_last ? p.out[l] - 1 : p.out[l], 0,
+                    l == 0 ? p.in[l] : 0, 0, l == 0 ? 0 : p.in[l], st)
+        : nullptr;
     if (l < p.L) {
       float* Hout = bufs ? bufs->H[l + 1] : pp[(l + 1) & 1];
       e.mode = EPI_SOFTPLUS;
@@ -212,7 +230,7 @@ static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float
         e.Q = bufs->Q[l]; e.ldq = p.ldout[l];
         e.rvec = w + p.woff[p.L];   // row 0 of the last linear
       }
-      launch_gemm_fwd(a, W, p.in[l], 0, M, p.out[l], e, st);
+      launch_gemm_fwd(a, W, p.in[l], 0, M, p.out[l], e, st, img);
       if (l + 1 == p.skip) {
         GenSpec g = sdf_gen(c, x, nullptr);
         prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
@@ -220,6 +238,15 @@ static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float
         prof_end(st);
       }
       Hin = Hout;
+    } else if (tc_split_last) {
+      // tensor-core path: sdf row by a row-dot, the feature rows as one <=256-wide GEMM (no 1-column N chunk)
+      prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+      rowdot_kernel<<<ew_blocks(M * 32), 256, 0, st>>>(Hin, p.ldin[l], p.in[l], W, b, out_sign / c->scale, sdf_out, M);
+      prof_end(st);
+      e.mode = EPI_LINEAR;
+      e.bias = b + 1;
+      e.C = feat_out; e.ldc = c->d_out - 1;
+      launch_gemm_fwd(a, W, p.in[l], 1, M, p.out[l] - 1, e, st, img);
     } else if (feat_out) {
       e.mode = EPI_SDF_OUT;
       e.out0 = sdf_out; e.out0_scale = out_sign / c->scale;
@@ -251,7 +278,7 @@ long long fneus_sdf_saved_floats(const fneus_sdf_cfg* cfg, long long n) {
 }
 long long fneus_sdf_scratch_floats(const fneus_sdf_cfg* cfg, long long n) {
   SdfPlan p = sdf_plan(cfg);
-  return p.ok ? sdf_scratch_per_point(p) * n : -1;
+  return p.ok ? sdf_scratch_floats(p, n) : -1;
 }
 
 int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long n, float* sdf_out,
@@ -262,14 +289,24 @@ int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   if (!wpack || !x || !sdf_out || !scratch) return FNEUS_ERR_NULL;
   if (n < 0) return FNEUS_ERR_BAD_SHAPE;
   long long per = 2LL * p.ldmax;
-  long long chunk = scratch_floats / per;
+  long long img_floats = (long long)(sdf_img_bytes(p) / 4) + 256;
+  ImgArena ar{nullptr, 0, 0};
+  long long avail = scratch_floats;
+  if (precision_mode() == 1 && scratch_floats > img_floats + per * 128) {
+    avail = scratch_floats - img_floats;
+    ar.base = reinterpret_cast<uint8_t*>(scratch + avail);
+    ar.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ar.base) + 1023) & ~(uintptr_t)1023);
+    ar.cap = (size_t)(img_floats - 256) * 4;
+  }
+  long long chunk = avail / per;
   if (chunk >= 128) chunk = chunk / 128 * 128;
   if (chunk < 1) return FNEUS_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   for (long long m0 = 0; m0 < n; m0 += chunk) {
     long long M = n - m0 < chunk ? n - m0 : chunk;
+    ar.used = 0;
     int rc = sdf_value_chain(cfg, p, wpack, x + m0 * cfg->d_in, M, sdf_out + m0,
-                             feat_out ? feat_out + m0 * (cfg->d_out - 1) : nullptr, nullptr, scratch, st);
+                             feat_out ? feat_out + m0 * (cfg->d_out - 1) : nullptr, nullptr, scratch, st, 1.f, ar);
     if (rc) return rc;
   }
   return FNEUS_OK;
@@ -283,7 +320,15 @@ int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax
   if (!wpack || !ax || !ay || !az || !u_out || !scratch) return FNEUS_ERR_NULL;
   if (nx < 1 || ny < 1 || nz < 1 || ix0 < 0 || ix1 > nx || ix0 > ix1) return FNEUS_ERR_BAD_SHAPE;
   long long per = 2LL * p.ldmax + 3;
-  long long chunk = scratch_floats / per;
+  long long img_floats = (long long)(sdf_img_bytes(p) / 4) + 256;
+  ImgArena ar{nullptr, 0, 0};
+  long long avail = scratch_floats;
+  if (precision_mode() == 1 && scratch_floats > img_floats + per * 128) {
+    avail = scratch_floats - img_floats;
+    ar.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(scratch + avail) + 1023) & ~(uintptr_t)1023);
+    ar.cap = (size_t)(img_floats - 256) * 4;
+  }
+  long long chunk = avail / per;
   if (chunk >= 128) chunk = chunk / 128 * 128;
   if (chunk < 1) return FNEUS_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -294,7 +339,8 @@ int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax
     prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
     grid_points_kernel<<<ew_blocks(M), 256, 0, st>>>(ax, ay, az, ny, nz, b, M, pts);
     prof_end(st);
-    int rc = sdf_value_chain(cfg, p, wpack, pts, M, u_out + (b - i0), nullptr, nullptr, scratch, st, -1.f);
+    ar.used = 0;
+    int rc = sdf_value_chain(cfg, p, wpack, pts, M, u_out + (b - i0), nullptr, nullptr, scratch, st, -1.f, ar);
     if (rc) return rc;
   }
   return FNEUS_OK;
@@ -310,7 +356,13 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
   cudaStream_t st = (cudaStream_t)stream;
   const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
   SdfBufs b = sdf_carve(p, saved, M);
-  int rc = sdf_value_chain(cfg, p, wpack, x, M, sdf_out, feat_out, &b, scratch, st);
+  ImgArena ar{nullptr, 0, 0};
+  if (precision_mode() == 1) {
+    ar.base = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(scratch + sdf_scratch_per_point(p) * M) + 1023) & ~(uintptr_t)1023);
+    ar.cap = sdf_img_bytes(p) - 1024;
+  }
+  int rc = sdf_value_chain(cfg, p, wpack, x, M, sdf_out, feat_out, &b, scratch, st, 1.f, ar);
   if (rc) return rc;
   if (!normal_out) return FNEUS_OK;   // value-only graph (SDFNetwork.forward under autograd)
   // reverse chain for the normal: g_l = q_l W_l, q_{l-1} = s_{l-1} * g_l
@@ -329,7 +381,8 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
       e.csplit = p.out[l - 1];
       e.C2 = g0e; e.ldc2 = e4;
     }
-    launch_gemm_bwd_data(a, wpack + p.woff[l], p.in[l], 0, M, p.in[l], e, st);
+    launch_gemm_bwd_data(a, wpack + p.woff[l], p.in[l], 0, M, p.in[l], e, st,
+                         make_wimg(ar, true, wpack + p.woff[l], p.in[l], 0, p.in[l], 0, 0, 0, p.out[l], st));
   }
   {
     ASeg a = aseg_mem(b.Q[0], p.ldout[0], p.out[0]);
@@ -337,7 +390,8 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
     e.mode = EPI_LINEAR_ADD;
     e.Q = p.skip > 0 ? g0e : nullptr; e.ldq = e4;
     e.C = g0; e.ldc = e4;
-    launch_gemm_bwd_data(a, wpack + p.woff[0], p.in[0], 0, M, p.in[0], e, st);
+    launch_gemm_bwd_data(a, wpack + p.woff[0], p.in[0], 0, M, p.in[0], e, st,
+                         make_wimg(ar, true, wpack + p.woff[0], p.in[0], 0, p.in[0], 0, 0, 0, p.out[0], st));
   }
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   normal_from_g0_kernel<<<ew_blocks(M), 256, 0, st>>>(x, cfg->d_in, cfg->multires, cfg->scale, g0, e4, normal_out, M);
@@ -362,6 +416,12 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   float* gbuf[2] = {scratch, scratch + M * p.ldmax};
   float* abuf[2] = {scratch + 2LL * M * p.ldmax, scratch + 3LL * M * p.ldmax};
   const int L = p.L;
+  ImgArena ar{nullptr, 0, 0};
+  if (precision_mode() == 1) {
+    ar.base = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(scratch + sdf_scratch_per_point(p) * M) + 1023) & ~(uintptr_t)1023);
+    ar.cap = sdf_img_bytes(p) - 1024;
+  }
 
   if (d_normal) {
     // double-backward sweep: gbar_0 = T0 nbar ; qbar_l = gbar_l W_l^T ; dW_l += q_l^T gbar_l ;
@@ -377,7 +437,9 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
       float* gout = gbuf[(l + 1) & 1];
       e.C = gout; e.ldc = p.ldin[l + 1];
       if (l + 1 == p.skip) { e.hscale = sqrt2; e.oscale = rsqrt2; }
-      launch_gemm_fwd(a, wpack + p.woff[l], p.in[l], 0, M, p.out[l], e, st);
+      launch_gemm_fwd(a, wpack + p.woff[l], p.in[l], 0, M, p.out[l], e, st,
+                      make_wimg(ar, false, wpack + p.woff[l], p.in[l], 0, p.out[l], 0, l == 0 ? p.in[l] : 0, 0,
+                                l == 0 ? 0 : p.in[l], st));
       if (l + 1 == p.skip) {
         GenSpec g = sdf_gen(cfg, x, d_normal);
         prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
@@ -420,7 +482,9 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     e.rs = d_sdf; e.rvec = wpack + p.woff[L]; e.rscale = 1.f / cfg->scale;
     e.Q = d_normal ? b.Q[L - 1] : nullptr; e.ldq = p.ldout[L - 1];
     e.C = abuf[(L - 1) & 1]; e.ldc = p.ldout[L - 1];
-    launch_gemm_bwd_data(a, wpack + p.woff[L], p.in[L], 0, M, p.in[L], e, st);
+    launch_gemm_bwd_data(a, wpack + p.woff[L], p.in[L], 0, M, p.in[L], e, st,
+                         d_feat ? make_wimg(ar, true, wpack + p.woff[L], p.in[L], 0, p.in[L], 0, 0, 1, cfg->d_out - 1, st)
+                                : nullptr);
   }
   for (int l = L - 1; l >= 0; l--) {
     float* al = abuf[l & 1];
@@ -435,7 +499,8 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     if (l == p.skip) { e.hscale = sqrt2; e.oscale = rsqrt2; e.csplit = p.out[l - 1]; }
     e.Q = d_normal ? b.Q[l - 1] : nullptr; e.ldq = p.ldout[l - 1];
     e.C = abuf[(l - 1) & 1]; e.ldc = p.ldout[l - 1];
-    launch_gemm_bwd_data(a, wpack + p.woff[l], p.in[l], 0, M, p.in[l], e, st);
+    launch_gemm_bwd_data(a, wpack + p.woff[l], p.in[l], 0, M, p.in[l], e, st,
+                         make_wimg(ar, true, wpack + p.woff[l], p.in[l], 0, p.in[l], 0, 0, 0, p.out[l], st));
   }
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;

@@ -14,15 +14,34 @@ struct Lin { long long woff, boff; int in, out; };
 
 // ReLU chain forward: layer 0 from `a0`, hidden activations to Hs[1..n] ([M, ldh]), last layer with `last_mode`
 // into out ([M, ld_out]).
+static size_t relu_chain_img_bytes(const Lin* lin, int n_lin, int gen0) {
+  size_t b = 0;
+  for (int l = 0; l < n_lin; l++) {
+    b += wimg_bytes(lin[l].out, l == 0 ? gen0 : 0, l == 0 ? lin[l].in - gen0 : lin[l].in) + 1024;
+    b += wimg_bytes(lin[l].in, 0, lin[l].out) + 1024;
+  }
+  return b + 4096;
+}
+static ImgArena arena_at(float* after_floats, size_t cap_bytes) {
+  ImgArena ar{nullptr, 0, 0};
+  if (precision_mode() == 1 && after_floats) {
+    ar.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(after_floats) + 1023) & ~(uintptr_t)1023);
+    ar.cap = cap_bytes - 1024;
+  }
+  return ar;
+}
+
 static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs, int ldh,
-                           int last_mode, float* out, int ld_out, long long M, cudaStream_t st) {
+                           int last_mode, float* out, int ld_out, long long M, cudaStream_t st, ImgArena& ar) {
   for (int l = 0; l < n_lin; l++) {
     ASeg a = l == 0 ? a0 : aseg_mem(Hs[l], ldh, lin[l].in);
     Epi e = epi_default();
     e.bias = w + lin[l].boff;
     if (l < n_lin - 1) { e.mode = EPI_RELU; e.C = Hs[l + 1]; e.ldc = ldh; }
     else { e.mode = last_mode; e.C = out; e.ldc = ld_out; }
-    launch_gemm_fwd(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].out, e, st);
+    launch_gemm_fwd(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].out, e, st,
+                    make_wimg(ar, false, w + lin[l].woff, lin[l].in, 0, lin[l].out, a.wred_gen, a.gen.ncols,
+                              a.wred_mem, a.kmem, st));
   }
 }
 
@@ -31,7 +50,7 @@ static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg
 static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs,
                            int ldh, const float* a_last, int ld_last, float* abuf0, float* abuf1, float* dsmall,
                            int ld_small, float* d_feats, int ld_feats, int accumulate_feats, long long M,
-                           cudaStream_t st) {
+                           cudaStream_t st, ImgArena& ar) {
   const int sms = num_sms();
   const float* al = a_last;
   int ld_al = ld_last;
@@ -45,14 +64,16 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
     if (l > 0) {
       e.H = Hs[l]; e.ldh = ldh;
       e.C = ab[l & 1]; e.ldc = ldh;
-      launch_gemm_bwd_data(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].in, e, st);
+      launch_gemm_bwd_data(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].in, e, st,
+                           make_wimg(ar, true, w + lin[l].woff, lin[l].in, 0, lin[l].in, 0, 0, 0, lin[l].out, st));
       al = ab[l & 1]; ld_al = ldh;
     } else if (dsmall || d_feats) {
       e.H = nullptr;
       e.C = dsmall; e.ldc = ld_small;
       e.csplit = a0.gen.ncols;
       e.C2 = d_feats; e.ldc2 = ld_feats; e.accumulate2 = accumulate_feats;
-      launch_gemm_bwd_data(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].in, e, st);
+      launch_gemm_bwd_data(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].in, e, st,
+                           make_wimg(ar, true, w + lin[l].woff, lin[l].in, 0, lin[l].in, 0, 0, 0, lin[l].out, st));
     }
   }
 }
@@ -228,9 +249,10 @@ long long fneus_color_saved_floats(const fneus_color_cfg* cfg, long long n) {
 }
 long long fneus_color_scratch_floats(const fneus_color_cfg* cfg, long long n) {
   ColorPlan p = color_plan(cfg);
+  if (!p.ok) return -1;
   long long per = (long long)cfg->n_layers * p.ldh;
   long long bwd = 2LL * p.ldh + round_up(p.gen_cols, 4) + 4;
-  return p.ok ? (per > bwd ? per : bwd) * n : -1;
+  return (per > bwd ? per : bwd) * n + (long long)(relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols) / 4) + 256;
 }
 
 int fneus_color_fwd(const fneus_color_cfg* cfg, const float* wpack, const float* points, const float* normals,
@@ -244,8 +266,11 @@ int fneus_color_fwd(const fneus_color_cfg* cfg, const float* wpack, const float*
   float* base = saved ? saved : scratch;
   float* Hs[12];
   for (int l = 1; l <= cfg->n_layers; l++) Hs[l] = base + (long long)(l - 1) * M * p.ldh;
+  long long per = (long long)cfg->n_layers * p.ldh, bwd = 2LL * p.ldh + round_up(p.gen_cols, 4) + 4;
+  ImgArena ar = arena_at(scratch ? scratch + (per > bwd ? per : bwd) * M : nullptr,
+                         relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
   relu_chain_fwd(wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh, EPI_SIGMOID,
-                 rgb_out, cfg->d_out, M, st);
+                 rgb_out, cfg->d_out, M, st, ar);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -269,8 +294,10 @@ int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float*
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   sigmoid_bwd_kernel<<<ew_blocks2(M * 4), 256, 0, st>>>(d_rgb, rgb, cfg->d_out, alast, 4, M);
   prof_end(st);
+  long long per = (long long)cfg->n_layers * p.ldh, bwdf = 2LL * p.ldh + round_up(p.gen_cols, 4) + 4;
+  ImgArena ar = arena_at(scratch + (per > bwdf ? per : bwdf) * M, relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
   relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh,
-                 alast, 4, ab0, ab1, d_normals ? dsmall : nullptr, lds, d_feats, cfg->d_feature, 0, M, st);
+                 alast, 4, ab0, ab1, d_normals ? dsmall : nullptr, lds, d_feats, cfg->d_feature, 0, M, st, ar);
   if (d_normals)
     prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
     extract_cols_kernel<<<ew_blocks2(M * 3), 256, 0, st>>>(dsmall, lds, p.gen_cols - 3, 3, d_normals, 3, M);
@@ -291,7 +318,10 @@ long long fneus_ref_saved_floats(const fneus_ref_cfg* cfg, long long n) {
 // scratch: 2 abufs, dsmall_cd [M,32], dsmall_cs [M,36], a_cd [M,4], a_cs [M,4]
 long long fneus_ref_scratch_floats(const fneus_ref_cfg* cfg, long long n) {
   RefPlan p = ref_plan(cfg);
-  return p.ok ? (2LL * p.ldh + 32 + 36 + 8) * n : -1;
+  if (!p.ok) return -1;
+  Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
+  return (2LL * p.ldh + 32 + 36 + 8) * n +
+         (long long)((relu_chain_img_bytes(p.cd, 5, 30) + relu_chain_img_bytes(chain, 5, 33)) / 4) + 256;
 }
 
 namespace {
@@ -327,19 +357,21 @@ int fneus_ref_fwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   if (M == 0) return FNEUS_OK;
   if (!wpack || !points || !feats || !dirs || !normals || !rgb_out || !spec_out || !diff_out || !saved)
     return FNEUS_ERR_NULL;
-  (void)scratch;
   cudaStream_t st = (cudaStream_t)stream;
   RefBufs b = ref_carve(p, saved, M);
+  Lin chain0[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
+  ImgArena ar = arena_at(scratch ? scratch + (2LL * p.ldh + 32 + 36 + 8) * M : nullptr,
+                         relu_chain_img_bytes(p.cd, 5, 30) + relu_chain_img_bytes(chain0, 5, 33));
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_prep_kernel<<<ew_blocks2(M), 256, 0, st>>>(dirs, normals, b.refl, M);
   prof_end(st);
-  relu_chain_fwd(wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, EPI_SIGMOID, b.yd, 3, M, st);
+  relu_chain_fwd(wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, EPI_SIGMOID, b.yd, 3, M, st, ar);
   // viewdir_mlp: 4 x (Linear+ReLU); then net_cs Linear+Sigmoid
   {
     Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
     // hidden layer outputs G1..G4 are all ReLU'd; the chain helper applies ReLU to all but the last linear.
     relu_chain_fwd(wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, EPI_SIGMOID, b.ys,
-                   1, M, st);
+                   1, M, st, ar);
   }
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_final_kernel<<<ew_blocks2(M * 3), 256, 0, st>>>(b.yd, b.ys, rgb_out, spec_out, diff_out, M);
@@ -368,11 +400,13 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_final_bwd_kernel<<<ew_blocks2(M), 256, 0, st>>>(b.yd, b.ys, d_rgb, d_spec, d_diff, a_cd, a_cs, M);
   prof_end(st);
-  relu_chain_bwd(wpack, d_wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, a_cd, 4, ab0, ab1,
-                 ds_cd, 32, d_feats, cfg->d_feature, 0, M, st);
   Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
+  ImgArena ar = arena_at(scratch + (2LL * p.ldh + 32 + 36 + 8) * M,
+                         relu_chain_img_bytes(p.cd, 5, 30) + relu_chain_img_bytes(chain, 5, 33));
+  relu_chain_bwd(wpack, d_wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, a_cd, 4, ab0, ab1,
+                 ds_cd, 32, d_feats, cfg->d_feature, 0, M, st, ar);
   relu_chain_bwd(wpack, d_wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, a_cs, 4, ab0,
-                 ab1, ds_cs, 36, d_feats, cfg->d_feature, 1, M, st);
+                 ab1, ds_cs, 36, d_feats, cfg->d_feature, 1, M, st, ar);
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_dn_kernel<<<ew_blocks2(M), 256, 0, st>>>(dirs, normals, b.refl, ds_cd, 32, ds_cs, 36, d_normals, M);
   prof_end(st);

@@ -21,6 +21,9 @@ def _need_cuda(t, name):
         raise RuntimeError("factored-neus_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
 
 
+_IMG_SLACK_FLOATS = 1 << 20      # room for the BF16 weight images of one SDF pass (tensor-core mode)
+
+
 def _empty(n, like):
     return torch.empty(int(n), dtype=torch.float32, device=like.device)
 
@@ -71,7 +74,7 @@ def sdf_forward_nograd(cfg, wflat, x, want_feat, max_chunk=1 << 18):
     chunk = max(1, min(N, max_chunk))
     per_point = 2 * max(4, -(-cfg.d_hidden // 4) * 4, -(-(cfg.d_in * (1 + 2 * cfg.multires)) // 4) * 4,
                         -(-cfg.d_out // 4) * 4)
-    scratch = _empty(per_point * chunk, x)
+    scratch = _empty(per_point * chunk + _IMG_SLACK_FLOATS, x)
     L.check(L.lib().fneus_sdf_fwd(cfg, L.ptr(w), L.ptr(x), N, L.ptr(sdf), L.ptr(feat), L.ptr(scratch),
                                   scratch.numel(), L.stream_ptr()), "fneus_sdf_fwd")
     return sdf, feat
@@ -88,7 +91,7 @@ def sdf_grid(cfg, wflat, ax, ay, az, ix0=0, ix1=None, max_chunk=1 << 18):
     chunk = max(1, min(n, max_chunk))
     per_point = 2 * max(4, -(-cfg.d_hidden // 4) * 4, -(-(cfg.d_in * (1 + 2 * cfg.multires)) // 4) * 4,
                         -(-cfg.d_out // 4) * 4) + 3
-    scratch = _empty(per_point * chunk, ax)
+    scratch = _empty(per_point * chunk + _IMG_SLACK_FLOATS, ax)
     L.check(L.lib().fneus_sdf_grid(cfg, L.ptr(w), L.ptr(_f32c(ax)), L.ptr(_f32c(ay)), L.ptr(_f32c(az)), nx, ny, nz,
                                    ix0, ix1, L.ptr(u), L.ptr(scratch), scratch.numel(), L.stream_ptr()),
             "fneus_sdf_grid")
@@ -153,7 +156,7 @@ class ColorMLP(torch.autograd.Function):
         rgb = torch.empty(N, cfg.d_out, dtype=torch.float32, device=p.device)
         need_graph = any(ctx.needs_input_grad)
         saved = _empty(lib.fneus_color_saved_floats(cfg, N), p) if need_graph else None
-        scratch = None if need_graph else _empty(lib.fneus_color_scratch_floats(cfg, N), p)
+        scratch = _empty(lib.fneus_color_scratch_floats(cfg, N), p)
         L.check(lib.fneus_color_fwd(cfg, L.ptr(w), L.ptr(p), L.ptr(n), L.ptr(v), L.ptr(f), N, L.ptr(rgb),
                                     L.ptr(saved), L.ptr(scratch), L.stream_ptr()), "fneus_color_fwd")
         ctx.cfg = cfg
@@ -188,8 +191,9 @@ class RefColorMLP(torch.autograd.Function):
         lib = L.lib()
         outs = [torch.empty(N, 3, dtype=torch.float32, device=p.device) for _ in range(3)]
         saved = _empty(lib.fneus_ref_saved_floats(cfg, N), p)
+        scratch = _empty(lib.fneus_ref_scratch_floats(cfg, N), p)
         L.check(lib.fneus_ref_fwd(cfg, L.ptr(w), L.ptr(p), L.ptr(f), L.ptr(d), L.ptr(n), N, L.ptr(outs[0]),
-                                  L.ptr(outs[1]), L.ptr(outs[2]), L.ptr(saved), None, L.stream_ptr()),
+                                  L.ptr(outs[1]), L.ptr(outs[2]), L.ptr(saved), L.ptr(scratch), L.stream_ptr()),
                 "fneus_ref_fwd")
         ctx.cfg = cfg
         ctx.save_for_backward(w, p, f, d, n, saved)

@@ -31,7 +31,7 @@ def stage1_loss_sharded(renderer, out, true_rgb, mask, surface_weight=0.1, igr_w
     hit = out["sdf_mask"]
     hit_f = hit.to(true_rgb.dtype)[:, None]
     eik_num, eik_den = renderer.last_eikonal_parts
-    n_local = torch.tensor(float(mask.shape[0]), device=mask.device)
+    n_local = mask.new_full((), float(mask.shape[0]))          # fill kernel: CUDA-graph capturable
     den = torch.stack([mask.sum(), (mask * hit_f).sum(), eik_den.detach(), n_local])
     if world > 1:
         dist.all_reduce(den, group=group)

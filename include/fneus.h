@@ -41,6 +41,8 @@ int fneus_num_sms(void);
  * default), 1 = BF16 operands on tcgen05 tensor cores with FP32 accumulation in TMEM (<=2e-2). */
 int fneus_set_precision(int mode);
 int fneus_get_precision(void);
+/* Bisect switches of the persistent tensor-core kernel (profiling only; results are wrong when non-zero). */
+int fneus_debug_flags(int flags);
 /* Test hook: one raw dense-layer contraction in the current precision mode.  kind 0: C[M,N] = A[M,K] W[N,K]^T
  * + bias; kind 1: C[M,N] = A[M,K] W[K,N]; kind 2: C[N,K] += Y[M,N]^T A[M,K], bias[N] += colsum(Y) (W := Y). */
 int fneus_debug_gemm(int kind, const float* A, int lda, const float* W, int ldw, float* bias, long long M, int N,
