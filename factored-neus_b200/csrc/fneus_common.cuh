@@ -93,6 +93,34 @@ __device__ __forceinline__ float gen_eval(const GenSpec& g, long long m, int j) 
   return kind == 1 ? freq * cosf(a) * t : -freq * sinf(a) * t;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Activation images (BF16 tensor-core mode): a matrix X[M, K] stored as BF16 tiles of 128 rows x 64 columns
+// (16 KB) in exactly the 128B-swizzled K-major shared-memory layout tcgen05.mma reads, tiles ordered
+// [row block][column block].  One tile = one bulk async copy; the same bytes are a valid MN-major operand of
+// the weight-gradient GEMM (rows = reduction index).  In the host orchestration an image is passed as a
+// (float*) base pointer with a NEGATIVE leading dimension -kbs (kbs = column blocks per row block).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t img_off(long long m, int k, int kbs) {
+  return ((size_t)(m >> 7) * kbs + (k >> 6)) * 16384 + (size_t)(((m & 127) >> 3) * 1024 + (m & 7) * 128 +
+         ((((k & 63) >> 3) ^ (int)(m & 7)) << 4) + ((k & 7) << 1));
+}
+__host__ __device__ inline long long mat_floats(long long M, int width, bool img) {
+  if (!img) return M * (long long)round_up(width, 4);
+  return ((M + 127) / 128) * (long long)((width + 63) / 64) * 4096;
+}
+inline int mat_ld(int width, bool img) { return img ? -((width + 63) / 64) : round_up(width, 4); }
+__device__ __forceinline__ float mat_get(const float* p, int ld, long long m, int k) {
+  if (ld >= 0) return p[m * ld + k];
+  unsigned short b = *reinterpret_cast<const unsigned short*>(reinterpret_cast<const uint8_t*>(p) + img_off(m, k, -ld));
+  return __uint_as_float((unsigned)b << 16);
+}
+__device__ __forceinline__ void mat_put(float* p, int ld, long long m, int k, float v) {
+  if (ld >= 0) { p[m * ld + k] = v; return; }
+  unsigned u = __float_as_uint(v);
+  u += 0x7FFFu + ((u >> 16) & 1u);                    // round to nearest even (finite inputs)
+  *reinterpret_cast<unsigned short*>(reinterpret_cast<uint8_t*>(p) + img_off(m, k, -ld)) = (unsigned short)(u >> 16);
+}
+
 // Softplus(beta) with torch's threshold 20 (fields.py:72), and its derivative recovered from the
 // stored activation h = softplus(a):  sigma'(a) = 1 - exp(-beta h)   (SURVEY.md A.1).
 __device__ __forceinline__ float softplus_beta(float a, float beta) {

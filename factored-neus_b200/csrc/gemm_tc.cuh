@@ -431,9 +431,26 @@ tc_gemm_mk_kernel(ASeg a, const float* __restrict__ W, int ldw, int wout0, int M
   }
 }
 
+// sum over the 64 reduction rows of column n (0..127) of a BF16 MN-major dY^T tile in shared memory
+__device__ __forceinline__ float wgrad_col_sum(const uint8_t* sA, int n) {
+  const uint8_t* tile = sA + (n >> 6) * 8192 + ((n & 7) << 1);
+  const int ch = (n & 63) >> 3;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int kk = 0; kk < 64; kk++) {
+    unsigned short b16 = *reinterpret_cast<const unsigned short*>(tile + (kk >> 3) * 1024 + (kk & 7) * 128 +
+                                                                 (((ch ^ (kk & 7)) & 7) << 4));
+    acc += __uint_as_float((unsigned)b16 << 16);
+  }
+  return acc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // dW[(wout0+n)*ldw + wred + k] += sum_m dY[m][n] * A[m][k] ; db += sum_m dY[m][n]
-// grid.x = n_tiles(128) * k_chunks(256 per phase), grid.y = splits over m
+// grid.x = n_tiles(128) * k_chunks(256 per phase), grid.y = splits over m (multiples of 64 rows).
+// Operands that are BF16 activation images (negative leading dimension) arrive by bulk async copies issued by
+// warp 5 (their tile bytes ARE the MN-major shared-memory operand); FP32 row-major / generated operands are
+// converted by the four producer warps.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 2)
 tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __restrict__ dW, int ldw, int wout0,
@@ -465,11 +482,17 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __res
   long long mend = mbeg + m_per_split;
   if (mend > M) mend = M;
   const int KB = mbeg < mend ? (int)((mend - mbeg + TC_BK - 1) / TC_BK) : 0;
-  const bool do_bias = db != nullptr && kc == 0;
+  const bool y_img = ldy < 0;
+  const bool x_img = phase == 1 && a.ldm < 0;
+  const bool need_prod = !(y_img && x_img);
+  const bool do_bias = db != nullptr && kc == 0 && !y_img;
+  // image dY: the bias gradient is summed from the shared-memory tile by warps 0-3 (they hold the stage open)
+  const bool bias_smem = db != nullptr && kc == 0 && y_img;
 
   if (tid == 0) {
+    const int cnt = (need_prod ? 128 : 0) + ((y_img || x_img) ? 1 : 0);
 #pragma unroll
-    for (int s = 0; s < TC_STAGES; s++) { mbar_init(&ctl->full[s], 128); mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < TC_STAGES; s++) { mbar_init(&ctl->full[s], cnt); mbar_init(&ctl->empty[s], bias_smem ? 129 : 1); }
     mbar_init(&ctl->accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -479,67 +502,102 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __res
   tc_fence_after();
   const uint32_t tmem_d = ctl->tmem_base;
 
-  if (warp < 4) {
-    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int bn = (tid & 31) << 2;            // this thread always loads dY columns n0+bn..+3
-    for (int kb = 0; kb < KB; kb++) {
-      const int s = kb % TC_STAGES;
-      if (kb >= TC_STAGES) mbar_wait(&ctl->empty[s], ((kb / TC_STAGES) - 1) & 1);
-      const long long mb = mbeg + (long long)kb * TC_BK;
-      // A operand (dY^T), MN-major: 64 m-rows x 128 n
-      {
-        float4 yv[16];
-#pragma unroll
-        for (int it = 0; it < 16; it++) {
-          long long m = mb + it * 4 + (tid >> 5);
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < mend && bn < nvalid) v = __ldg(reinterpret_cast<const float4*>(dY + m * ldy + n0 + bn));
-          yv[it] = v;
-        }
-#pragma unroll
-        for (int it = 0; it < 16; it++) {
-          float4 v = yv[it];
-          if (bn + 1 >= nvalid) v.y = 0.f;
-          if (bn + 2 >= nvalid) v.z = 0.f;
-          if (bn + 3 >= nvalid) v.w = 0.f;
-          if (do_bias) { bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w; }
-          sts_mnmajor(sA[s], it * 4 + (tid >> 5), bn, v);
-        }
+  if (warp == 5) {
+    if (lane == 0 && (y_img || x_img)) {
+      const int ykbs = -ldy, xkbs = -a.ldm;
+      const int yblocks = y_img ? min(2, ykbs - nt * 2) : 0;
+      const int xblocks = x_img ? min((Nc + 63) / 64, xkbs - (k0 >> 6)) : 0;
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % TC_STAGES;
+        if (kb >= TC_STAGES) mbar_wait(&ctl->empty[s], ((kb / TC_STAGES) - 1) & 1);
+        const long long mblk = (mbeg >> 6) + kb;               // 64-row block index
+        const size_t half = (size_t)(mblk & 1) * 8192;
+        mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)(yblocks + xblocks) * 8192u);
+        for (int b = 0; b < yblocks; b++)
+          bulk_g2s(sA[s] + b * 8192, reinterpret_cast<const uint8_t*>(dY) + ((size_t)(mblk >> 1) * ykbs + nt * 2 + b) * 16384 + half,
+                   8192, &ctl->full[s]);
+        for (int b = 0; b < xblocks; b++)
+          bulk_g2s(sB[s] + b * 8192, reinterpret_cast<const uint8_t*>(a.mem) + ((size_t)(mblk >> 1) * xkbs + (k0 >> 6) + b) * 16384 + half,
+                   8192, &ctl->full[s]);
       }
-      // B operand (A rows), MN-major: 64 m-rows x Nc k ; thread -> column group (tid % 64)*4, rows (tid/64) + 2*it
-      if (phase == 1) {
-        const int kq = (tid & 63) << 2;
-        if (kq < Nc) {
+    }
+  } else if (warp < 4) {
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float bcol = 0.f;
+    const int bn = (tid & 31) << 2;            // this thread always loads dY columns n0+bn..+3
+    if (need_prod) {
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % TC_STAGES;
+        if (kb >= TC_STAGES) mbar_wait(&ctl->empty[s], ((kb / TC_STAGES) - 1) & 1);
+        const long long mb = mbeg + (long long)kb * TC_BK;
+        if (!y_img) {
+          // A operand (dY^T), MN-major: 64 m-rows x 128 n
+          float4 yv[16];
 #pragma unroll
-          for (int half = 0; half < 2; half++) {
-            float4 xv[16];
+          for (int it = 0; it < 16; it++) {
+            long long m = mb + it * 4 + (tid >> 5);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < mend && bn < nvalid) v = __ldg(reinterpret_cast<const float4*>(dY + m * ldy + n0 + bn));
+            yv[it] = v;
+          }
 #pragma unroll
-            for (int it = 0; it < 16; it++) {
-              long long m = mb + (tid >> 6) + 2 * (half * 16 + it);
-              xv[it] = (m < mend) ? load_a4(a, 1, m, M, k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int it = 0; it < 16; it++) sts_mnmajor(sB[s], (tid >> 6) + 2 * (half * 16 + it), kq, xv[it]);
+          for (int it = 0; it < 16; it++) {
+            float4 v = yv[it];
+            if (bn + 1 >= nvalid) v.y = 0.f;
+            if (bn + 2 >= nvalid) v.z = 0.f;
+            if (bn + 3 >= nvalid) v.w = 0.f;
+            if (do_bias) { bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w; }
+            sts_mnmajor(sA[s], it * 4 + (tid >> 5), bn, v);
           }
         }
-      } else {
-        const int nq = Nc >> 2;
+        // B operand (A rows), MN-major: 64 m-rows x Nc k ; thread -> column group (tid % 64)*4, rows (tid/64) + 2*it
+        if (phase == 1 && !x_img) {
+          const int kq = (tid & 63) << 2;
+          if (kq < Nc) {
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+              float4 xv[16];
+#pragma unroll
+              for (int it = 0; it < 16; it++) {
+                long long m = mb + (tid >> 6) + 2 * (half * 16 + it);
+                xv[it] = (m < mend) ? load_a4(a, 1, m, M, k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int it = 0; it < 16; it++) sts_mnmajor(sB[s], (tid >> 6) + 2 * (half * 16 + it), kq, xv[it]);
+            }
+          }
+        } else if (phase == 0) {
+          const int nq = Nc >> 2;
 #pragma unroll 1
-        for (int idx = tid; idx < 64 * nq; idx += 128) {
-          int mr = idx / nq, k = (idx - mr * nq) << 2;
-          long long m = mb + mr;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < mend) v = load_a4(a, 0, m, M, k0 + k);
-          sts_mnmajor(sB[s], mr, k, v);
+          for (int idx = tid; idx < 64 * nq; idx += 128) {
+            int mr = idx / nq, k = (idx - mr * nq) << 2;
+            long long m = mb + mr;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < mend) v = load_a4(a, 0, m, M, k0 + k);
+            sts_mnmajor(sB[s], mr, k, v);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&ctl->full[s]);
+        if (bias_smem) {
+          mbar_wait(&ctl->full[s], (kb / TC_STAGES) & 1);
+          bcol += wgrad_col_sum(sA[s], tid);
+          mbar_arrive(&ctl->empty[s]);
         }
       }
-      fence_proxy_async();
-      mbar_arrive(&ctl->full[s]);
+    } else if (bias_smem) {
+      for (int kb = 0; kb < KB; kb++) {
+        const int s = kb % TC_STAGES;
+        mbar_wait(&ctl->full[s], (kb / TC_STAGES) & 1);
+        bcol += wgrad_col_sum(sA[s], tid);
+        mbar_arrive(&ctl->empty[s]);
+      }
     }
     mbar_wait(&ctl->accum, 0);
     tc_fence_after();
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     float* wbuf = reinterpret_cast<float*>(sB[0]) + warp * (32 * 33);
+    if (bias_smem && KB > 0 && tid < nvalid) atomicAdd(db + wout0 + n0 + tid, bcol);
     if (KB > 0) {
       for (int c0 = 0; c0 < Nc; c0 += 32) {
         float v[32];
@@ -594,9 +652,11 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __res
 // Persistent, warp-specialised variant of tc_gemm_mk (needs a weight image): one CTA per SM loops over
 // output tiles; the epilogue of tile i (8 warps) overlaps the operand loads + MMAs of tile i+1 through two
 // TMEM accumulator stages (2 x 256 columns).
-//   warps 0-7  : A producers, two groups of 4 handling alternate reduction blocks (two blocks of loads in flight)
-//   warp  8    : MMA issuer (+ TMEM alloc)        warp 9 : weight-image bulk-copy loader
-//   warps 10-17: epilogue, two groups of 4 (TMEM lane quarter = warp % 4) handling alternate 32-column chunks
+//   warps 0-7  : A producers for generated / FP32 row-major operands, two groups of 4 on alternate reduction blocks
+//   warp  8    : MMA issuer (+ TMEM alloc)
+//   warp  9    : bulk-copy loader: weight-image tile and, when A is a BF16 activation image, the A tile too
+//   warps 10-17: epilogue, one thread per accumulator row (TMEM lane), 16 columns at a time, vector I/O on
+//                FP32 row-major tensors and on BF16 activation images; two groups on alternate 32-column chunks
 // ---------------------------------------------------------------------------------------------
 constexpr int P_STAGES = 4, P_THREADS = 576;
 inline int& tc_debug_flags() { static int f = 0; return f; }   // bit0: no A loads, bit1: no epilogue, bit2: no MMA
@@ -607,8 +667,161 @@ struct PSmem {
   uint64_t acc_empty[2];
   uint32_t tmem_base;
 };
-constexpr int P_WBUF_BYTES = 8 * 32 * 33 * 4;
-constexpr int P_SMEM_BYTES = P_STAGES * (TC_A_BYTES + TC_B_BYTES) + P_WBUF_BYTES + 1024 + 256;
+constexpr int P_VEC_FLOATS = 2 * 1024;                 // staged bias / rvec (N <= 1024)
+constexpr int P_SMEM_BYTES = P_STAGES * (TC_A_BYTES + TC_B_BYTES) + P_VEC_FLOATS * 4 + 1024 + 256;
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// 16 consecutive columns [c, c+16) (c % 16 == 0) of row m.  Image: two 16-byte chunks of BF16.  FP32 row-major:
+// four float4 when aligned, else scalar.  Only columns j < nv are guaranteed meaningful for FP32 sources.
+__device__ __forceinline__ void row_load16(const float* p, int ld, long long m, int c, int nv, float* out) {
+  if (ld < 0) {
+    const int kbs = -ld, r7 = (int)(m & 7);
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(p) + ((size_t)(m >> 7) * kbs + (c >> 6)) * 16384 +
+                          (((m & 127) >> 3) * 1024 + r7 * 128);
+    const int ch = (c & 63) >> 3;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (((ch + i) ^ r7) << 4)));
+      uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        out[i * 8 + 2 * t] = __uint_as_float(w[t] << 16);
+        out[i * 8 + 2 * t + 1] = __uint_as_float(w[t] & 0xFFFF0000u);
+      }
+    }
+  } else {
+    const float* q = p + m * ld + c;
+    if (nv >= 16 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float4 f = __ldg(reinterpret_cast<const float4*>(q) + i);
+        out[4 * i] = f.x; out[4 * i + 1] = f.y; out[4 * i + 2] = f.z; out[4 * i + 3] = f.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j++) out[j] = j < nv ? __ldg(q + j) : 0.f;
+    }
+  }
+}
+// Store columns j < nv of the 16-column group; image destinations always get the full group (the caller zeroes the
+// tail) so that the padding columns of an image stay finite.
+__device__ __forceinline__ void row_store16(float* p, int ld, long long m, int c, int nv, const float* v) {
+  if (ld < 0) {
+    const int kbs = -ld, r7 = (int)(m & 7);
+    uint8_t* base = reinterpret_cast<uint8_t*>(p) + ((size_t)(m >> 7) * kbs + (c >> 6)) * 16384 +
+                    (((m & 127) >> 3) * 1024 + r7 * 128);
+    const int ch = (c & 63) >> 3;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      uint2 lo = pack_bf16x4(make_float4(v[i * 8], v[i * 8 + 1], v[i * 8 + 2], v[i * 8 + 3]));
+      uint2 hi = pack_bf16x4(make_float4(v[i * 8 + 4], v[i * 8 + 5], v[i * 8 + 6], v[i * 8 + 7]));
+      *reinterpret_cast<uint4*>(base + (((ch + i) ^ r7) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
+  } else {
+    float* q = p + m * ld + c;
+    if (nv >= 16 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        reinterpret_cast<float4*>(q)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j++)
+        if (j < nv) q[j] = v[j];
+    }
+  }
+}
+
+// One accumulator row (global row m), 16 columns starting at global column n.  sb / sr: staged bias and rvec.
+template <int MODE>
+__device__ __forceinline__ void epilogue_row16(const Epi& e, long long m, int n, int N, const float* a, const float* sb,
+                                               const float* sr) {
+  const float beta = e.beta, inv_beta = 1.f / e.beta, oscale = e.oscale, hscale = e.hscale;
+  const int lim = (N < e.csplit ? N : e.csplit) - n;        // primary columns of this group: j < lim
+  constexpr bool kNeedH = MODE == EPI_SPMUL || MODE == EPI_SWEEP || MODE == EPI_SDF_BWD || MODE == EPI_RELUMASK;
+  constexpr bool kNeedQ = MODE == EPI_SWEEP || MODE == EPI_SDF_BWD || MODE == EPI_LINEAR_ADD;
+  float h[16], q[16], y[16];
+  const bool has_h = kNeedH && e.H != nullptr && lim > 0;
+  const bool has_q = kNeedQ && e.Q != nullptr && lim > 0;
+  if (has_h) row_load16(e.H, e.ldh, m, n, lim, h);
+  if (has_q) row_load16(e.Q, e.ldq, m, n, lim, q);
+  const float rs = ((MODE == EPI_SDF_BWD || MODE == EPI_RELUMASK) && e.rs) ? __ldg(e.rs + m) * e.rscale : 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    float acc = a[j], hv = has_h ? h[j] : 0.f, qv = has_q ? q[j] : 0.f, out = 0.f, out2 = 0.f;
+    if (MODE == EPI_LINEAR) out = (acc + sb[n + j]) * oscale;
+    else if (MODE == EPI_RELU) out = fmaxf(acc + sb[n + j], 0.f);
+    else if (MODE == EPI_SIGMOID) out = sigmoid_fast(acc + sb[n + j]);
+    else if (MODE == EPI_SOFTPLUS) out = softplus_beta_fast(acc + sb[n + j], beta, inv_beta) * oscale;
+    else if (MODE == EPI_SOFTPLUS_Q) {
+      float v = acc + sb[n + j];
+      out = softplus_beta_fast(v, beta, inv_beta) * oscale;
+      out2 = softplus_grad_from_pre_fast(v, beta) * sr[n + j];
+    } else if (MODE == EPI_SPMUL) out = softplus_grad_from_act_fast(hv * hscale, beta) * acc * oscale;
+    else if (MODE == EPI_SWEEP) {
+      float sg = softplus_grad_from_act_fast(hv * hscale, beta);
+      out = sg * acc * oscale;
+      out2 = beta * (1.f - sg) * qv * acc;
+    } else if (MODE == EPI_SDF_BWD) {
+      float sg = softplus_grad_from_act_fast(hv * hscale, beta);
+      out = sg * (acc + rs * sr[n + j]) * oscale + qv;
+    } else if (MODE == EPI_RELUMASK) {
+      float v = acc + rs * sr[n + j];
+      out = has_h ? (hv > 0.f ? v : 0.f) : v;
+    } else if (MODE == EPI_LINEAR_ADD) out = (acc + qv) * oscale;
+    y[j] = j < lim ? out : 0.f;
+    q[j] = j < lim ? out2 : 0.f;
+  }
+  if (e.C != nullptr && (lim > 0 || e.ldc < 0)) row_store16(e.C, e.ldc, m, n, lim, y);
+  if ((MODE == EPI_SOFTPLUS_Q || MODE == EPI_SWEEP) && (lim > 0 || e.ldq < 0)) row_store16(e.Q, e.ldq, m, n, lim, q);
+  // secondary part (columns >= csplit): rare, element-wise
+  if ((MODE == EPI_SPMUL || MODE == EPI_RELUMASK) && e.C2 != nullptr && n + 16 > e.csplit) {
+#pragma unroll 1
+    for (int j = 0; j < 16; j++) {
+      const int nn = n + j;
+      if (nn < e.csplit || nn >= N) continue;
+      const int c = nn - e.csplit;
+      float v = a[j];
+      if (MODE == EPI_SPMUL) v *= oscale;
+      else {
+        if (e.H2) v = mat_get(e.H2, e.ldh2, m, c) > 0.f ? v : 0.f;
+        if (e.accumulate2) v += mat_get(e.C2, e.ldc2, m, c);
+      }
+      mat_put(e.C2, e.ldc2, m, c, v);
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_tile(const Epi& e, uint32_t taddr, long long m, int M, int n0, int Nc, int N,
+                                              int grp, int cover, const float* sb, const float* sr) {
+  // cover: columns (relative to n0) that must be written even beyond Nc (image padding), multiple of 32
+#pragma unroll 1
+  for (int c0 = grp * 32; c0 < cover; c0 += 64) {
+#pragma unroll 1
+    for (int hseg = 0; hseg < 32; hseg += 16) {
+      float a[16];
+      if (c0 + hseg < Nc) tmem_ld16(taddr + c0 + hseg, a);
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) a[j] = 0.f;
+      }
+      if (m < M) epilogue_row16<MODE>(e, m, n0 + c0 + hseg, N, a, sb, sr);
+    }
+  }
+}
 
 template <bool WT>
 __global__ void __launch_bounds__(P_THREADS, 1)
@@ -622,8 +835,8 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
     sA[s] = base + s * (TC_A_BYTES + TC_B_BYTES);
     sB[s] = sA[s] + TC_A_BYTES;
   }
-  float* wbuf_all = reinterpret_cast<float*>(base + P_STAGES * (TC_A_BYTES + TC_B_BYTES));
-  PSmem* ctl = reinterpret_cast<PSmem*>(base + P_STAGES * (TC_A_BYTES + TC_B_BYTES) + P_WBUF_BYTES);
+  float* svec = reinterpret_cast<float*>(base + P_STAGES * (TC_A_BYTES + TC_B_BYTES));
+  PSmem* ctl = reinterpret_cast<PSmem*>(base + P_STAGES * (TC_A_BYTES + TC_B_BYTES) + P_VEC_FLOATS * 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_m = (M + TC_BM - 1) / TC_BM;
@@ -632,6 +845,7 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
   const int kb_gen = (a.gen.ncols + TC_BK - 1) / TC_BK;
   const int kb_mem = (a.kmem + TC_BK - 1) / TC_BK;
   const int KB = kb_gen + kb_mem;
+  const bool a_img = a.ldm < 0;
 
   if (tid == 0) {
 #pragma unroll
@@ -639,6 +853,11 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
 #pragma unroll
     for (int s = 0; s < 2; s++) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_empty[s], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // stage the per-column vectors of the epilogue (bias, rvec) once
+  for (int i = tid; i < 1024; i += P_THREADS) {
+    svec[i] = (e.bias && i < N) ? __ldg(e.bias + i) : 0.f;
+    svec[1024 + i] = (e.rvec && i < N) ? __ldg(e.rvec + i) : 0.f;
   }
   if (warp == 8) tmem_alloc(&ctl->tmem_base, 512);
   tc_fence_before();
@@ -664,7 +883,8 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
             int idx = it * 128 + ptid;
             sts_kmajor(sA[s], idx >> 4, (idx & 15) << 2, load_a4(a, 0, m0 + (idx >> 4), M, k0 + ((idx & 15) << 2)));
           }
-        } else if (!(dbg & 1)) {
+          fence_proxy_async();
+        } else if (!a_img && !(dbg & 1)) {
           float4 av[16];
 #pragma unroll
           for (int it = 0; it < 16; it++) {
@@ -676,17 +896,17 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
             int idx = it * 128 + ptid;
             sts_kmajor(sA[s], idx >> 4, (idx & 15) << 2, av[it]);
           }
+          fence_proxy_async();
         }
-        fence_proxy_async();
         mbar_arrive(&ctl->full[s]);
       }
     }
   } else if (warp == 9) {
-    // ------------------------------ weight-image loader ------------------------------
+    // ------------------------------ bulk-copy loader ------------------------------
     if (lane == 0) {
       int kbg = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int nchunk = t / tiles_m;
+        const int nchunk = t / tiles_m, mt = t % tiles_m;
         const int nvalid = min(256, N - nchunk * 256);
         const int Nc = (nvalid + 15) & ~15;
         const uint32_t bytes = WT ? (uint32_t)Nc * 128u : (uint32_t)((Nc + 63) / 64) * 8192u;
@@ -694,7 +914,11 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
         for (int kb = 0; kb < KB; kb++, kbg++) {
           const int s = kbg % P_STAGES;
           if (kbg >= P_STAGES) mbar_wait(&ctl->empty[s], ((kbg / P_STAGES) - 1) & 1);
-          mbar_arrive_expect_tx(&ctl->full[s], bytes);
+          const bool img_blk = a_img && kb >= kb_gen && !(dbg & 1);
+          mbar_arrive_expect_tx(&ctl->full[s], bytes + (img_blk ? (uint32_t)TC_A_BYTES : 0u));
+          if (img_blk)
+            bulk_g2s(sA[s], reinterpret_cast<const uint8_t*>(a.mem) + ((size_t)mt * (-a.ldm) + (kb - kb_gen)) * TC_A_BYTES,
+                     TC_A_BYTES, &ctl->full[s]);
           bulk_g2s(sB[s], src + (size_t)kb * TC_B_BYTES, bytes, &ctl->full[s]);
         }
       }
@@ -733,26 +957,37 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
     }
   } else {
     // ------------------------------ epilogue ------------------------------
-    const int ew = warp - 10;                  // 0..7
-    const int grp = ew >> 2;                   // column-chunk parity handled by this warp
+    const int grp = (warp - 10) >> 2;          // column-chunk parity handled by this warp
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    float* wbuf = wbuf_all + ew * (32 * 33);
+    const float* sb = svec;
+    const float* sr = svec + 1024;
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
-      const long long m0 = (long long)(t % tiles_m) * TC_BM;
+      const long long m = (long long)(t % tiles_m) * TC_BM + quarter * 32 + lane;
       const int n0 = (t / tiles_m) * 256;
       const int nvalid = min(256, N - n0);
       const int Nc = (nvalid + 15) & ~15;
+      // image destinations: cover their padding columns inside this CTA's 256-column range with zeros
+      int cover = (Nc + 31) & ~31;
+      if (e.ldc < 0 && e.C) cover = max(cover, min(256, (-e.ldc) * 64 - n0));
+      if (e.ldq < 0 && e.Q && (e.mode == EPI_SOFTPLUS_Q || e.mode == EPI_SWEEP)) cover = max(cover, min(256, (-e.ldq) * 64 - n0));
       const int as = it & 1;
       mbar_wait(&ctl->acc_full[as], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(quarter * 32) << 16);
       if (!(dbg & 2)) {
-#pragma unroll 1
-        for (int c0 = grp * 32; c0 < Nc; c0 += 64) {
-          float v[32];
-          tmem_ld32(taddr + c0, v);
-          epilogue_chunk(e, wbuf, v, m0 + quarter * 32, M, n0 + c0, nvalid - c0, lane);
+        switch (e.mode) {
+          case EPI_LINEAR: epilogue_tile<EPI_LINEAR>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          case EPI_RELU: epilogue_tile<EPI_RELU>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          case EPI_SIGMOID: epilogue_tile<EPI_SIGMOID>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          case EPI_SOFTPLUS: epilogue_tile<EPI_SOFTPLUS>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          case EPI_SOFTPLUS_Q: epilogue_tile<EPI_SOFTPLUS_Q>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          case EPI_SPMUL: epilogue_tile<EPI_SPMUL>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          case EPI_SWEEP: epilogue_tile<EPI_SWEEP>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          case EPI_SDF_BWD: epilogue_tile<EPI_SDF_BWD>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          case EPI_RELUMASK: epilogue_tile<EPI_RELUMASK>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          case EPI_LINEAR_ADD: epilogue_tile<EPI_LINEAR_ADD>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          default: break;                    // EPI_SDF_OUT is never routed to the persistent kernel
         }
       }
       tc_fence_before();
@@ -826,6 +1061,9 @@ inline void launch_pack_wimg(bool for_bwd_data, const float* W, int ldw, int wou
   prof_end(st);
 }
 
+void launch_colsum(const float* X, int ldx, int K, const float* w, float wscale, float* out, float* osum, long long M,
+                   cudaStream_t st);
+
 constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 + 256;
 
 inline int tc_num_sms() {
@@ -855,10 +1093,9 @@ inline void launch_tc_fwd(const ASeg& a, const float* W, int ldw, int wout0, lon
                           cudaStream_t st, const uint8_t* wimg) {
   dim3 grid(cdiv(M, TC_BM), cdiv(N, 256));
   prof_begin(PC_TC_MLP, 2.0 * (double)M * N * (a.gen.ncols + a.kmem), 0.0, st);
-  if (wimg && a.gen.ncols + a.kmem > 0) {
+  if (wimg && a.gen.ncols + a.kmem > 0 && e.mode != EPI_SDF_OUT && N <= 1024) {
     int ntiles = grid.x * grid.y, sms = tc_num_sms();
-    Epi e2 = e; e2.dbg = tc_debug_flags();
-    tc_gemm_mk_persistent_kernel<true><<<ntiles < sms ? ntiles : sms, P_THREADS, P_SMEM_BYTES, st>>>(a, (int)M, N, e2, wimg, tc_debug_flags());
+    tc_gemm_mk_persistent_kernel<true><<<ntiles < sms ? ntiles : sms, P_THREADS, P_SMEM_BYTES, st>>>(a, (int)M, N, e, wimg, tc_debug_flags());
   } else {
     tc_gemm_mk_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, W, ldw, wout0, (int)M, N, e, wimg);
   }
@@ -868,7 +1105,7 @@ inline void launch_tc_bwd_data(const ASeg& a, const float* W, int ldw, int wout0
                                cudaStream_t st, const uint8_t* wimg) {
   dim3 grid(cdiv(M, TC_BM), cdiv(N, 256));
   prof_begin(PC_TC_MLP, 2.0 * (double)M * N * (a.gen.ncols + a.kmem), 0.0, st);
-  if (wimg && a.gen.ncols + a.kmem > 0) {
+  if (wimg && a.gen.ncols + a.kmem > 0 && e.mode != EPI_SDF_OUT && N <= 1024) {
     int ntiles = grid.x * grid.y, sms = tc_num_sms();
     tc_gemm_mk_persistent_kernel<false><<<ntiles < sms ? ntiles : sms, P_THREADS, P_SMEM_BYTES, st>>>(a, (int)M, N, e, wimg, tc_debug_flags());
   } else {

@@ -27,7 +27,7 @@ __global__ void append_gen_cols_kernel(GenSpec g, float* C, int ldc, int col0, f
   if (idx >= total) return;
   long long m = idx / g.ncols;
   int j = (int)(idx - m * g.ncols);
-  C[m * ldc + col0 + j] = gen_eval(g, m, j) * scale;
+  mat_put(C, ldc, m, col0 + j, gen_eval(g, m, j) * scale);
 }
 
 // n[m][c] = sum_j [comp_j == c] dPE_j/dx_c (x) * g0[m][j]      (T0^T g0)
@@ -57,26 +57,30 @@ __global__ void colsum_kernel(const float* X, int ldx, int K, const float* w, fl
   float acc = 0.f, ws = 0.f;
   for (long long m = mbeg; m < mend; m++) {
     float wm = w ? __ldg(w + m) * wscale : 1.f;
-    if (k < K) acc += wm * __ldg(X + m * ldx + k);
+    if (k < K) acc += wm * mat_get(X, ldx, m, k);
     ws += wm;
   }
   if (k < K) atomicAdd(out + k, acc);
   if (osum && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(osum, ws);
 }
 
-// out0[m] = (dot(H[m,:K], w) + b) * scale     one warp per row
+// out0[m] = (dot(H[m,:K], w) + b) * scale     one warp per row (H: FP32 row-major or BF16 activation image)
 __global__ void rowdot_kernel(const float* H, int ldh, int K, const float* w, const float* b, float scale,
                               float* out0, long long M) {
   long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   int lane = threadIdx.x % 32;
   if (m >= M) return;
   float acc = 0.f;
-  for (int k = lane * 4; k < K; k += 128) {
-    float4 h = __ldg(reinterpret_cast<const float4*>(H + m * ldh + k));
-    if (k + 0 < K) acc = fmaf(h.x, __ldg(w + k + 0), acc);
-    if (k + 1 < K) acc = fmaf(h.y, __ldg(w + k + 1), acc);
-    if (k + 2 < K) acc = fmaf(h.z, __ldg(w + k + 2), acc);
-    if (k + 3 < K) acc = fmaf(h.w, __ldg(w + k + 3), acc);
+  if (ldh >= 0) {
+    for (int k = lane * 4; k < K; k += 128) {
+      float4 h = __ldg(reinterpret_cast<const float4*>(H + m * ldh + k));
+      if (k + 0 < K) acc = fmaf(h.x, __ldg(w + k + 0), acc);
+      if (k + 1 < K) acc = fmaf(h.y, __ldg(w + k + 1), acc);
+      if (k + 2 < K) acc = fmaf(h.z, __ldg(w + k + 2), acc);
+      if (k + 3 < K) acc = fmaf(h.w, __ldg(w + k + 3), acc);
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) acc = fmaf(mat_get(H, ldh, m, k), __ldg(w + k), acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -119,6 +123,16 @@ __global__ void grid_points_kernel(const float* __restrict__ ax, const float* __
 
 static inline int ew_blocks(long long n) { return cdiv(n, 256); }
 
+void launch_colsum(const float* X, int ldx, int K, const float* w, float wscale, float* out, float* osum, long long M,
+                   cudaStream_t st) {
+  if (M <= 0 || K <= 0) return;
+  int mpb = 256;
+  dim3 grid(cdiv(K, 256), cdiv(M, mpb));
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, K, w, wscale, out, osum, M, mpb);
+  prof_end(st);
+}
+
 // ------------------------------------------------------------------------------------------------
 // SDF network
 // ------------------------------------------------------------------------------------------------
@@ -128,8 +142,10 @@ struct SdfPlan {
   int in[20], out[20], ldin[20], ldout[20];
   long long woff[20], boff[20];
   long long pack;
-  int ldmax;
+  int ldmax;      // FP32 row-major leading dimension of the widest activation
+  int wmax;       // widest activation (columns)
   int skip;
+  bool img;       // activations are BF16 images (tensor-core mode); ldin/ldout are then -kbs
   bool ok;
 };
 
@@ -144,16 +160,19 @@ static SdfPlan sdf_plan(const fneus_sdf_cfg* c) {
   if (p.skip == 0 || p.skip >= p.L) p.ok = false;   // skip in 1..L-1 (or <0 = none)
   if (p.skip > 0 && c->d_hidden - p.e < 1) p.ok = false;
   long long off = 0;
-  p.ldmax = 4;
+  p.ldmax = 4; p.wmax = 4;
+  p.img = precision_mode() == 1;
   for (int l = 0; l <= p.L; l++) {
     p.in[l] = l == 0 ? p.e : c->d_hidden;
     p.out[l] = l == p.L ? c->d_out : ((l + 1 == p.skip) ? c->d_hidden - p.e : c->d_hidden);
-    p.ldin[l] = round_up(p.in[l], 4);
-    p.ldout[l] = round_up(p.out[l], 4);
+    p.ldin[l] = mat_ld(p.in[l], p.img && l > 0);
+    p.ldout[l] = mat_ld(p.out[l], p.img && l < p.L);
     p.woff[l] = off; off += (long long)p.out[l] * p.in[l];
     p.boff[l] = off; off += p.out[l];
-    if (p.ldin[l] > p.ldmax) p.ldmax = p.ldin[l];
-    if (l < p.L && p.ldout[l] > p.ldmax) p.ldmax = p.ldout[l];
+    if (round_up(p.in[l], 4) > p.ldmax) p.ldmax = round_up(p.in[l], 4);
+    if (l < p.L && round_up(p.out[l], 4) > p.ldmax) p.ldmax = round_up(p.out[l], 4);
+    if (l > 0 && p.in[l] > p.wmax) p.wmax = p.in[l];
+    if (l < p.L && p.out[l] > p.wmax) p.wmax = p.out[l];
   }
   p.pack = off;
   return p;
@@ -170,15 +189,23 @@ static size_t sdf_img_bytes(const SdfPlan& p) {
 }
 
 // saved layout: H_1..H_L ([M, ldin[l]]), Q_0..Q_{L-1} ([M, ldout[l]])
-static long long sdf_saved_per_point(const SdfPlan& p) {
+static long long sdf_saved_floats(const SdfPlan& p, long long M) {
   long long s = 0;
-  for (int l = 1; l <= p.L; l++) s += p.ldin[l];
-  for (int l = 0; l < p.L; l++) s += p.ldout[l];
-  return s;
+  for (int l = 1; l <= p.L; l++) s += mat_floats(M, p.in[l], p.img);
+  for (int l = 0; l < p.L; l++) s += mat_floats(M, p.out[l], p.img);
+  return s + 1024;
 }
-static long long sdf_scratch_per_point(const SdfPlan& p) { return 4LL * p.ldmax + 2LL * round_up(p.e, 4); }
+static long long sdf_buf_floats(const SdfPlan& p, long long M) { return mat_floats(M, p.wmax, p.img) + 256; }
+// 4 ping-pong activation buffers + two [M, e] FP32 side buffers; the weight-image arena follows
+static long long sdf_scratch_main(const SdfPlan& p, long long M) {
+  return 4LL * sdf_buf_floats(p, M) + 2LL * M * round_up(p.e, 4) + 256;
+}
 static long long sdf_scratch_floats(const SdfPlan& p, long long n) {
-  return sdf_scratch_per_point(p) * n + (long long)(sdf_img_bytes(p) / 4) + 256;
+  return sdf_scratch_main(p, n) + (long long)(sdf_img_bytes(p) / 4) + 256;
+}
+// activation images need zero padding rows (they are summed over by the weight-gradient GEMM)
+static void sdf_zero_images(const SdfPlan& p, float* ptr, long long floats, long long M, cudaStream_t st) {
+  if (p.img && (M & 127)) cudaMemsetAsync(ptr, 0, (size_t)floats * 4, st);
 }
 
 struct SdfBufs {
@@ -188,8 +215,10 @@ struct SdfBufs {
 static SdfBufs sdf_carve(const SdfPlan& p, float* saved, long long M) {
   SdfBufs b;
   float* ptr = saved;
-  for (int l = 1; l <= p.L; l++) { b.H[l] = ptr; ptr += M * p.ldin[l]; }
-  for (int l = 0; l < p.L; l++) { b.Q[l] = ptr; ptr += M * p.ldout[l]; }
+  auto align = [](float* q) { return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(q) + 1023) & ~(uintptr_t)1023); };
+  ptr = align(ptr);
+  for (int l = 1; l <= p.L; l++) { b.H[l] = ptr; ptr += mat_floats(M, p.in[l], p.img); }
+  for (int l = 0; l < p.L; l++) { b.Q[l] = ptr; ptr += mat_floats(M, p.out[l], p.img); }
   b.H[0] = nullptr;
   return b;
 }
@@ -206,7 +235,7 @@ static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float
                            float* sdf_out, float* feat_out, SdfBufs* bufs, float* scratch, cudaStream_t st,
                            float out_sign, ImgArena& ar) {
   const float rsqrt2 = 0.70710678118654752440f;
-  float* pp[2] = {scratch, scratch + M * p.ldmax};
+  float* pp[2] = {scratch, scratch + sdf_buf_floats(p, M)};
   const float* Hin = nullptr;
   for (int l = 0; l <= p.L; l++) {
     ASeg a = l == 0 ? aseg_gen(sdf_gen(c, x, nullptr)) : aseg_mem(Hin, p.ldin[l], p.in[l]);
@@ -274,7 +303,7 @@ long long fneus_sdf_pack_floats(const fneus_sdf_cfg* cfg) {
 }
 long long fneus_sdf_saved_floats(const fneus_sdf_cfg* cfg, long long n) {
   SdfPlan p = sdf_plan(cfg);
-  return p.ok ? sdf_saved_per_point(p) * n : -1;
+  return p.ok ? sdf_saved_floats(p, n) : -1;
 }
 long long fneus_sdf_scratch_floats(const fneus_sdf_cfg* cfg, long long n) {
   SdfPlan p = sdf_plan(cfg);
@@ -288,23 +317,24 @@ int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   if (n == 0) return FNEUS_OK;
   if (!wpack || !x || !sdf_out || !scratch) return FNEUS_ERR_NULL;
   if (n < 0) return FNEUS_ERR_BAD_SHAPE;
-  long long per = 2LL * p.ldmax;
+  long long per128 = 2LL * sdf_buf_floats(p, 128);           // scratch floats per 128 points (upper bound)
   long long img_floats = (long long)(sdf_img_bytes(p) / 4) + 256;
   ImgArena ar{nullptr, 0, 0};
-  long long avail = scratch_floats;
-  if (precision_mode() == 1 && scratch_floats > img_floats + per * 128) {
-    avail = scratch_floats - img_floats;
-    ar.base = reinterpret_cast<uint8_t*>(scratch + avail);
-    ar.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ar.base) + 1023) & ~(uintptr_t)1023);
+  long long avail = scratch_floats - 1024;
+  if (p.img) {
+    if (scratch_floats < img_floats + per128 + 2048) return FNEUS_ERR_WORKSPACE;
+    avail = scratch_floats - img_floats - 1024;
+    ar.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(scratch + avail) + 1023) & ~(uintptr_t)1023);
     ar.cap = (size_t)(img_floats - 256) * 4;
   }
-  long long chunk = avail / per;
-  if (chunk >= 128) chunk = chunk / 128 * 128;
-  if (chunk < 1) return FNEUS_ERR_WORKSPACE;
+  long long chunk = avail / per128 * 128;
+  if (chunk < 128) return FNEUS_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
+  scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
   for (long long m0 = 0; m0 < n; m0 += chunk) {
     long long M = n - m0 < chunk ? n - m0 : chunk;
     ar.used = 0;
+    sdf_zero_images(p, scratch, 2LL * sdf_buf_floats(p, M), M, st);
     int rc = sdf_value_chain(cfg, p, wpack, x + m0 * cfg->d_in, M, sdf_out + m0,
                              feat_out ? feat_out + m0 * (cfg->d_out - 1) : nullptr, nullptr, scratch, st, 1.f, ar);
     if (rc) return rc;
@@ -319,23 +349,25 @@ int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax
   if (!p.ok || cfg->d_in != 3) return FNEUS_ERR_UNSUPPORTED;
   if (!wpack || !ax || !ay || !az || !u_out || !scratch) return FNEUS_ERR_NULL;
   if (nx < 1 || ny < 1 || nz < 1 || ix0 < 0 || ix1 > nx || ix0 > ix1) return FNEUS_ERR_BAD_SHAPE;
-  long long per = 2LL * p.ldmax + 3;
+  long long per128 = 2LL * sdf_buf_floats(p, 128) + 3 * 128;
   long long img_floats = (long long)(sdf_img_bytes(p) / 4) + 256;
   ImgArena ar{nullptr, 0, 0};
-  long long avail = scratch_floats;
-  if (precision_mode() == 1 && scratch_floats > img_floats + per * 128) {
-    avail = scratch_floats - img_floats;
+  long long avail = scratch_floats - 1024;
+  if (p.img) {
+    if (scratch_floats < img_floats + per128 + 2048) return FNEUS_ERR_WORKSPACE;
+    avail = scratch_floats - img_floats - 1024;
     ar.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(scratch + avail) + 1023) & ~(uintptr_t)1023);
     ar.cap = (size_t)(img_floats - 256) * 4;
   }
-  long long chunk = avail / per;
-  if (chunk >= 128) chunk = chunk / 128 * 128;
-  if (chunk < 1) return FNEUS_ERR_WORKSPACE;
+  long long chunk = avail / per128 * 128;
+  if (chunk < 128) return FNEUS_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
+  scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
   long long i0 = (long long)ix0 * ny * nz, i1 = (long long)ix1 * ny * nz;
   for (long long b = i0; b < i1; b += chunk) {
     long long M = i1 - b < chunk ? i1 - b : chunk;
-    float* pts = scratch + 2LL * chunk * p.ldmax;
+    float* pts = scratch + 2LL * sdf_buf_floats(p, chunk);
+    sdf_zero_images(p, scratch, 2LL * sdf_buf_floats(p, M), M, st);
     prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
     grid_points_kernel<<<ew_blocks(M), 256, 0, st>>>(ax, ay, az, ny, nz, b, M, pts);
     prof_end(st);
@@ -356,10 +388,11 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
   cudaStream_t st = (cudaStream_t)stream;
   const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
   SdfBufs b = sdf_carve(p, saved, M);
+  sdf_zero_images(p, saved, sdf_saved_floats(p, M), M, st);
   ImgArena ar{nullptr, 0, 0};
-  if (precision_mode() == 1) {
+  if (p.img) {
     ar.base = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(scratch + sdf_scratch_per_point(p) * M) + 1023) & ~(uintptr_t)1023);
+        (reinterpret_cast<uintptr_t>(scratch + sdf_scratch_main(p, M)) + 1023) & ~(uintptr_t)1023);
     ar.cap = sdf_img_bytes(p) - 1024;
   }
   int rc = sdf_value_chain(cfg, p, wpack, x, M, sdf_out, feat_out, &b, scratch, st, 1.f, ar);
@@ -367,7 +400,7 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
   if (!normal_out) return FNEUS_OK;   // value-only graph (SDFNetwork.forward under autograd)
   // reverse chain for the normal: g_l = q_l W_l, q_{l-1} = s_{l-1} * g_l
   const int e4 = round_up(p.e, 4);
-  float* g0e = scratch + 4LL * M * p.ldmax;
+  float* g0e = scratch + 4LL * sdf_buf_floats(p, M);
   float* g0 = g0e + M * e4;
   for (int l = p.L - 1; l >= 1; l--) {
     ASeg a = aseg_mem(b.Q[l], p.ldout[l], p.out[l]);
@@ -413,13 +446,16 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   const int sms = num_sms();
   const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
   SdfBufs b = sdf_carve(p, saved, M);
-  float* gbuf[2] = {scratch, scratch + M * p.ldmax};
-  float* abuf[2] = {scratch + 2LL * M * p.ldmax, scratch + 3LL * M * p.ldmax};
+  scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
+  const long long bf = sdf_buf_floats(p, M);
+  float* gbuf[2] = {scratch, scratch + bf};
+  float* abuf[2] = {scratch + 2 * bf, scratch + 3 * bf};
+  sdf_zero_images(p, scratch, 4 * bf, M, st);
   const int L = p.L;
   ImgArena ar{nullptr, 0, 0};
-  if (precision_mode() == 1) {
+  if (p.img) {
     ar.base = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(scratch + sdf_scratch_per_point(p) * M) + 1023) & ~(uintptr_t)1023);
+        (reinterpret_cast<uintptr_t>(scratch + sdf_scratch_main(p, M)) + 1023) & ~(uintptr_t)1023);
     ar.cap = sdf_img_bytes(p) - 1024;
   }
 
@@ -448,25 +484,12 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
       }
     }
     // q_L = e_0 (row 0 of the last linear): dW_L[0,:] += sum_m gbar_L
-    {
-      int mpb = 256;
-      dim3 grid(cdiv(p.in[L], 256), cdiv(M, mpb));
-      prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
-      colsum_kernel<<<grid, 256, 0, st>>>(gbuf[L & 1], p.ldin[L], p.in[L], nullptr, 1.f, d_wpack + p.woff[L],
-                                          nullptr, M, mpb);
-      prof_end(st);
-    }
+    launch_colsum(gbuf[L & 1], p.ldin[L], p.in[L], nullptr, 1.f, d_wpack + p.woff[L], nullptr, M, st);
   }
   // value-path backward with the augmented abar_l
   float* dWL = d_wpack + p.woff[L];
   float* dbL = d_wpack + p.boff[L];
-  if (d_sdf) {
-    int mpb = 256;
-    dim3 grid(cdiv(p.in[L], 256), cdiv(M, mpb));
-    prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
-    colsum_kernel<<<grid, 256, 0, st>>>(b.H[L], p.ldin[L], p.in[L], d_sdf, 1.f / cfg->scale, dWL, dbL, M, mpb);
-    prof_end(st);
-  }
+  if (d_sdf) launch_colsum(b.H[L], p.ldin[L], p.in[L], d_sdf, 1.f / cfg->scale, dWL, dbL, M, st);
   if (d_feat) {
     launch_gemm_wgrad(d_feat, cfg->d_out - 1, aseg_mem(b.H[L], p.ldin[L], p.in[L]), dWL, p.in[L], 1, dbL, M,
                       cfg->d_out - 1, sms, st);

@@ -22,6 +22,13 @@ static size_t relu_chain_img_bytes(const Lin* lin, int n_lin, int gen0) {
   }
   return b + 4096;
 }
+static inline long long hid_floats(long long M, int hid, bool img) { return mat_floats(M, hid, img) + 256; }
+static inline float* align1k(float* q) {
+  return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(q) + 1023) & ~(uintptr_t)1023);
+}
+static inline void zero_if_ragged(bool img, float* ptr, long long floats, long long M, cudaStream_t st) {
+  if (img && (M & 127)) cudaMemsetAsync(ptr, 0, (size_t)floats * 4, st);
+}
 static ImgArena arena_at(float* after_floats, size_t cap_bytes) {
   ImgArena ar{nullptr, 0, 0};
   if (precision_mode() == 1 && after_floats) {
@@ -81,7 +88,7 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
 // ------------------------------------------------------------------------------------------------
 // RenderingNetwork
 // ------------------------------------------------------------------------------------------------
-struct ColorPlan { int n_lin; Lin lin[12]; long long pack; int ldh; int gen_cols; bool ok; };
+struct ColorPlan { int n_lin; Lin lin[12]; long long pack; int hid; int ldh; bool img; int gen_cols; bool ok; };
 static ColorPlan color_plan(const fneus_color_cfg* c) {
   ColorPlan p;
   p.ok = c && c->n_layers >= 1 && c->n_layers <= 10 && c->d_feature > 0 && c->d_feature % 4 == 0 &&
@@ -90,7 +97,7 @@ static ColorPlan color_plan(const fneus_color_cfg* c) {
   if (!p.ok) return p;
   p.n_lin = c->n_layers + 1;
   p.gen_cols = 3 + pe_dim(3, c->multires_view) + 3;
-  p.ldh = c->d_hidden;
+  p.hid = c->d_hidden; p.img = precision_mode() == 1; p.ldh = mat_ld(p.hid, p.img);
   long long off = 0;
   for (int l = 0; l < p.n_lin; l++) {
     p.lin[l].in = l == 0 ? p.gen_cols + c->d_feature : c->d_hidden;
@@ -100,6 +107,11 @@ static ColorPlan color_plan(const fneus_color_cfg* c) {
   }
   p.pack = off;
   return p;
+}
+static long long color_scratch_main(const fneus_color_cfg* c, const ColorPlan& p, long long n) {
+  long long per = (long long)c->n_layers * hid_floats(n, p.hid, p.img);
+  long long bwd = 2LL * hid_floats(n, p.hid, p.img) + n * (round_up(p.gen_cols, 4) + 4);
+  return (per > bwd ? per : bwd) + 2048;
 }
 static ASeg color_a0(const fneus_color_cfg* c, const ColorPlan& p, const float* pts, const float* nrm,
                      const float* view, const float* feats) {
@@ -113,12 +125,12 @@ static ASeg color_a0(const fneus_color_cfg* c, const ColorPlan& p, const float* 
 // ------------------------------------------------------------------------------------------------
 // RefColor
 // ------------------------------------------------------------------------------------------------
-struct RefPlan { Lin cd[5]; Lin vd[4]; Lin cs; long long pack; int ldh; bool ok; };
+struct RefPlan { Lin cd[5]; Lin vd[4]; Lin cs; long long pack; int hid; int ldh; bool img; bool ok; };
 static RefPlan ref_plan(const fneus_ref_cfg* c) {
   RefPlan p;
   p.ok = c && c->d_feature > 0 && c->d_feature % 4 == 0 && c->d_hidden > 0 && c->d_hidden % 4 == 0;
   if (!p.ok) return p;
-  p.ldh = c->d_hidden;
+  p.hid = c->d_hidden; p.img = precision_mode() == 1; p.ldh = mat_ld(p.hid, p.img);
   long long off = 0;
   auto put = [&](Lin& l, int in, int out) {
     l.in = in; l.out = out; l.woff = off; off += (long long)in * out; l.boff = off; off += out;
@@ -133,6 +145,9 @@ static RefPlan ref_plan(const fneus_ref_cfg* c) {
   return p;
 }
 
+static long long ref_scratch_main(const RefPlan& p, long long n) {
+  return 2LL * hid_floats(n, p.hid, p.img) + (32 + 36 + 8) * n + 2048;
+}
 __device__ __forceinline__ float srgb_f(float c) {
   const float eps = 1.1920928955078125e-07f;
   return c <= 0.0031308f ? (323.0f / 25.0f) * c : (211.0f * powf(fmaxf(eps, c), 5.0f / 12.0f) - 11.0f) / 200.0f;
@@ -245,14 +260,12 @@ long long fneus_color_pack_floats(const fneus_color_cfg* cfg) {
 // saved: H_1..H_n ; scratch: 2 abufs + dsmall + a_last
 long long fneus_color_saved_floats(const fneus_color_cfg* cfg, long long n) {
   ColorPlan p = color_plan(cfg);
-  return p.ok ? (long long)cfg->n_layers * p.ldh * n : -1;
+  return p.ok ? (long long)cfg->n_layers * hid_floats(n, p.hid, p.img) + 1024 : -1;
 }
 long long fneus_color_scratch_floats(const fneus_color_cfg* cfg, long long n) {
   ColorPlan p = color_plan(cfg);
   if (!p.ok) return -1;
-  long long per = (long long)cfg->n_layers * p.ldh;
-  long long bwd = 2LL * p.ldh + round_up(p.gen_cols, 4) + 4;
-  return (per > bwd ? per : bwd) * n + (long long)(relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols) / 4) + 256;
+  return color_scratch_main(cfg, p, n) + (long long)(relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols) / 4) + 256;
 }
 
 int fneus_color_fwd(const fneus_color_cfg* cfg, const float* wpack, const float* points, const float* normals,
@@ -263,11 +276,12 @@ int fneus_color_fwd(const fneus_color_cfg* cfg, const float* wpack, const float*
   if (M == 0) return FNEUS_OK;
   if (!wpack || !points || !normals || !view_dirs || !feats || !rgb_out || (!saved && !scratch)) return FNEUS_ERR_NULL;
   cudaStream_t st = (cudaStream_t)stream;
-  float* base = saved ? saved : scratch;
+  float* base = align1k(saved ? saved : scratch);
   float* Hs[12];
-  for (int l = 1; l <= cfg->n_layers; l++) Hs[l] = base + (long long)(l - 1) * M * p.ldh;
-  long long per = (long long)cfg->n_layers * p.ldh, bwd = 2LL * p.ldh + round_up(p.gen_cols, 4) + 4;
-  ImgArena ar = arena_at(scratch ? scratch + (per > bwd ? per : bwd) * M : nullptr,
+  const long long hf = hid_floats(M, p.hid, p.img);
+  for (int l = 1; l <= cfg->n_layers; l++) Hs[l] = base + (long long)(l - 1) * hf;
+  zero_if_ragged(p.img, base, (long long)cfg->n_layers * hf, M, st);
+  ImgArena ar = arena_at(scratch ? scratch + color_scratch_main(cfg, p, M) : nullptr,
                          relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
   relu_chain_fwd(wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh, EPI_SIGMOID,
                  rgb_out, cfg->d_out, M, st, ar);
@@ -285,17 +299,18 @@ int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float*
     return FNEUS_ERR_NULL;
   cudaStream_t st = (cudaStream_t)stream;
   float* Hs[12];
-  for (int l = 1; l <= cfg->n_layers; l++) Hs[l] = saved + (long long)(l - 1) * M * p.ldh;
+  const long long hf = hid_floats(M, p.hid, p.img);
+  for (int l = 1; l <= cfg->n_layers; l++) Hs[l] = align1k(saved) + (long long)(l - 1) * hf;
   const int lds = round_up(p.gen_cols, 4);
-  float* ab0 = scratch;
-  float* ab1 = ab0 + M * p.ldh;
-  float* dsmall = ab1 + M * p.ldh;
+  float* ab0 = align1k(scratch);
+  float* ab1 = ab0 + hf;
+  float* dsmall = ab1 + hf;
+  zero_if_ragged(p.img, ab0, 2 * hf, M, st);
   float* alast = dsmall + M * lds;
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   sigmoid_bwd_kernel<<<ew_blocks2(M * 4), 256, 0, st>>>(d_rgb, rgb, cfg->d_out, alast, 4, M);
   prof_end(st);
-  long long per = (long long)cfg->n_layers * p.ldh, bwdf = 2LL * p.ldh + round_up(p.gen_cols, 4) + 4;
-  ImgArena ar = arena_at(scratch + (per > bwdf ? per : bwdf) * M, relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
+  ImgArena ar = arena_at(scratch + color_scratch_main(cfg, p, M), relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
   relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh,
                  alast, 4, ab0, ab1, d_normals ? dsmall : nullptr, lds, d_feats, cfg->d_feature, 0, M, st, ar);
   if (d_normals)
@@ -313,14 +328,14 @@ long long fneus_ref_pack_floats(const fneus_ref_cfg* cfg) {
 // saved: cd H1..H4, cs G1..G4, yd [M,4], ys [M,4], refl [M,4]
 long long fneus_ref_saved_floats(const fneus_ref_cfg* cfg, long long n) {
   RefPlan p = ref_plan(cfg);
-  return p.ok ? (8LL * p.ldh + 12) * n : -1;
+  return p.ok ? 8LL * hid_floats(n, p.hid, p.img) + 12 * n + 2048 : -1;
 }
 // scratch: 2 abufs, dsmall_cd [M,32], dsmall_cs [M,36], a_cd [M,4], a_cs [M,4]
 long long fneus_ref_scratch_floats(const fneus_ref_cfg* cfg, long long n) {
   RefPlan p = ref_plan(cfg);
   if (!p.ok) return -1;
   Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
-  return (2LL * p.ldh + 32 + 36 + 8) * n +
+  return ref_scratch_main(p, n) +
          (long long)((relu_chain_img_bytes(p.cd, 5, 30) + relu_chain_img_bytes(chain, 5, 33)) / 4) + 256;
 }
 
@@ -328,9 +343,9 @@ namespace {
 struct RefBufs { float* H[5]; float* G[5]; float* yd; float* ys; float* refl; };
 RefBufs ref_carve(const RefPlan& p, float* saved, long long M) {
   RefBufs b;
-  float* ptr = saved;
-  for (int i = 1; i <= 4; i++) { b.H[i] = ptr; ptr += M * p.ldh; }
-  for (int i = 1; i <= 4; i++) { b.G[i] = ptr; ptr += M * p.ldh; }
+  float* ptr = align1k(saved);
+  for (int i = 1; i <= 4; i++) { b.H[i] = ptr; ptr += hid_floats(M, p.hid, p.img); }
+  for (int i = 1; i <= 4; i++) { b.G[i] = ptr; ptr += hid_floats(M, p.hid, p.img); }
   b.yd = ptr; ptr += M * 4; b.ys = ptr; ptr += M * 4; b.refl = ptr;
   return b;
 }
@@ -360,7 +375,8 @@ int fneus_ref_fwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   cudaStream_t st = (cudaStream_t)stream;
   RefBufs b = ref_carve(p, saved, M);
   Lin chain0[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
-  ImgArena ar = arena_at(scratch ? scratch + (2LL * p.ldh + 32 + 36 + 8) * M : nullptr,
+  zero_if_ragged(p.img, align1k(saved), 8LL * hid_floats(M, p.hid, p.img), M, st);
+  ImgArena ar = arena_at(scratch ? scratch + ref_scratch_main(p, M) : nullptr,
                          relu_chain_img_bytes(p.cd, 5, 30) + relu_chain_img_bytes(chain0, 5, 33));
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_prep_kernel<<<ew_blocks2(M), 256, 0, st>>>(dirs, normals, b.refl, M);
@@ -391,9 +407,10 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
     return FNEUS_ERR_NULL;
   cudaStream_t st = (cudaStream_t)stream;
   RefBufs b = ref_carve(p, saved, M);
-  float* ab0 = scratch;
-  float* ab1 = ab0 + M * p.ldh;
-  float* ds_cd = ab1 + M * p.ldh;
+  float* ab0 = align1k(scratch);
+  float* ab1 = ab0 + hid_floats(M, p.hid, p.img);
+  float* ds_cd = ab1 + hid_floats(M, p.hid, p.img);
+  zero_if_ragged(p.img, ab0, 2 * hid_floats(M, p.hid, p.img), M, st);
   float* ds_cs = ds_cd + M * 32;
   float* a_cd = ds_cs + M * 36;
   float* a_cs = a_cd + M * 4;
@@ -401,7 +418,7 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   ref_final_bwd_kernel<<<ew_blocks2(M), 256, 0, st>>>(b.yd, b.ys, d_rgb, d_spec, d_diff, a_cd, a_cs, M);
   prof_end(st);
   Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
-  ImgArena ar = arena_at(scratch + (2LL * p.ldh + 32 + 36 + 8) * M,
+  ImgArena ar = arena_at(scratch + ref_scratch_main(p, M),
                          relu_chain_img_bytes(p.cd, 5, 30) + relu_chain_img_bytes(chain, 5, 33));
   relu_chain_bwd(wpack, d_wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, a_cd, 4, ab0, ab1,
                  ds_cd, 32, d_feats, cfg->d_feature, 0, M, st, ar);
