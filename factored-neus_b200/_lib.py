@@ -65,6 +65,9 @@ _SIGNATURES = {
     "fneus_prof_classes": (c_int, []),
     "fneus_prof_enable": (c_int, [c_int]),
     "fneus_prof_collect": (c_int, [_P, _P, _P, _P]),
+    "fneus_pack_max_segments": (c_int, []),
+    "fneus_pack_fwd": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "fneus_pack_bwd": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "fneus_sdf_pack_floats": (_LL, [POINTER(SdfCfg)]),
     "fneus_sdf_saved_floats": (_LL, [POINTER(SdfCfg), _LL]),
     "fneus_sdf_scratch_floats": (_LL, [POINTER(SdfCfg), _LL]),

@@ -4,4 +4,5 @@
 #include "nerf.cu"
 #include "sampling.cu"
 #include "composite.cu"
+#include "pack.cu"
 #include "api.cu"

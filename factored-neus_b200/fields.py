@@ -46,6 +46,11 @@ class PlainLinear(nn.Module):
 
 
 def _flat_pack(layers):
+    """Flat pack [W0, b0, W1, b1, ...] of effective weights: one fused CUDA launch (weight-norm included) on the
+    GPU; plain torch ops for parameters that still live on the CPU (no kernels are involved there)."""
+    first = layers[0].bias
+    if first.is_cuda:
+        return ops.pack_weights(layers)
     parts = []
     for lin in layers:
         w = lin.effective() if hasattr(lin, "effective") else lin.weight
@@ -176,6 +181,21 @@ class NeRF(nn.Module):
                              multires_view=multires_view, skip=(skips[0] if skips else -1))
 
     def flat_weights(self):
+        if self.rgb_linear.bias.is_cuda:
+            params, layout = [], []
+
+            def add(t):
+                r, c = (t.shape if t.dim() == 2 else (1, t.numel()))
+                layout.append(("copy", -1, len(params), r, c))
+                params.append(t)
+
+            for lin in self.pts_linears:
+                add(lin.weight); add(lin.bias)
+            add(self.alpha_linear.weight); add(self.feature_linear.weight)
+            add(self.alpha_linear.bias); add(self.feature_linear.bias)
+            for lin in (self.views_linears[0], self.rgb_linear):
+                add(lin.weight); add(lin.bias)
+            return ops.PackWeights.apply(layout, *params)
         parts = []
         for lin in self.pts_linears:
             parts += [lin.weight.reshape(-1), lin.bias.reshape(-1)]

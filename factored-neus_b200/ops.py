@@ -61,6 +61,80 @@ def debug_gemm(kind, A, W, bias=None, out=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# flat weight packs (weight-norm fused), one launch forward and one backward
+# ---------------------------------------------------------------------------------------------
+class PackWeights(torch.autograd.Function):
+    """(layout, *params) -> flat FP32 pack.  ``layout`` = list of (kind, i_g, i_v, rows, cols) over ``params``:
+    kind 'wn' -> W = g*v/|v|_row (torch weight_norm, fields.py:67-68), 'copy' -> the tensor itself.
+
+    Backward writes dg/dv/db in one launch.  If every parameter already owns a contiguous ``.grad`` buffer
+    (e.g. views into ``parallel.GradBucket``) the kernel accumulates into those buffers directly and autograd
+    receives no gradient tensors (saves one AccumulateGrad kernel per parameter)."""
+
+    @staticmethod
+    def forward(ctx, layout, *params):
+        import ctypes
+        dev = params[0].device
+        _need_cuda(params[0], "parameters")
+        n = len(layout)
+        total = sum(r * c for (_, _, _, r, c) in layout)
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        ps = [p.detach() for p in params]
+        for p in ps:
+            assert p.is_contiguous() and p.dtype == torch.float32
+        PT = ctypes.c_void_p * n
+        g = PT(*[(ps[ig].data_ptr() if kind == "wn" else None) for (kind, ig, iv, r, c) in layout])
+        v = PT(*[ps[iv].data_ptr() for (kind, ig, iv, r, c) in layout])
+        offs, o = [], 0
+        for (_, _, _, r, c) in layout:
+            offs.append(o)
+            o += r * c
+        off = (ctypes.c_longlong * n)(*offs)
+        rows = (ctypes.c_int * n)(*[r for (_, _, _, r, c) in layout])
+        cols = (ctypes.c_int * n)(*[c for (_, _, _, r, c) in layout])
+        L.check(L.lib().fneus_pack_fwd(n, g, v, off, rows, cols, L.ptr(flat), L.stream_ptr()), "fneus_pack_fwd")
+        ctx.layout, ctx.params, ctx.meta = layout, params, (g, v, off, rows, cols)
+        return flat
+
+    @staticmethod
+    def backward(ctx, dflat):
+        import ctypes
+        layout, params = ctx.layout, ctx.params
+        g, v, off, rows, cols = ctx.meta
+        n = len(layout)
+        dflat = _f32c(dflat)
+        direct = all((p.grad is not None and p.grad.is_contiguous()) or not p.requires_grad for p in params)
+        grads = [None] * len(params)
+        if not direct:
+            grads = [torch.zeros_like(p) if p.requires_grad else None for p in params]
+        tgt = (lambda i: (params[i].grad if direct else grads[i]) if params[i].requires_grad else None)
+        PT = ctypes.c_void_p * n
+        dg = PT(*[(tgt(ig).data_ptr() if (kind == "wn" and tgt(ig) is not None) else None)
+                  for (kind, ig, iv, r, c) in layout])
+        dv = PT(*[(tgt(iv).data_ptr() if tgt(iv) is not None else None) for (kind, ig, iv, r, c) in layout])
+        L.check(L.lib().fneus_pack_bwd(n, g, v, dg, dv, off, rows, cols, L.ptr(dflat), 1 if direct else 0,
+                                       L.stream_ptr()), "fneus_pack_bwd")
+        return (None,) + tuple(None if direct else gr for gr in grads)
+
+
+def pack_weights(layers):
+    """layers: list of modules with (weight_g, weight_v, bias) or (weight, bias) -> flat pack [W0, b0, W1, b1, ...]."""
+    params, layout = [], []
+    for lin in layers:
+        if hasattr(lin, "weight_g"):
+            r, c = lin.weight_v.shape
+            layout.append(("wn", len(params), len(params) + 1, r, c))
+            params += [lin.weight_g, lin.weight_v]
+        else:
+            r, c = lin.weight.shape
+            layout.append(("copy", -1, len(params), r, c))
+            params += [lin.weight]
+        layout.append(("copy", -1, len(params), 1, lin.bias.numel()))
+        params += [lin.bias]
+    return PackWeights.apply(layout, *params)
+
+
+# ---------------------------------------------------------------------------------------------
 # SDF network
 # ---------------------------------------------------------------------------------------------
 def sdf_forward_nograd(cfg, wflat, x, want_feat, max_chunk=1 << 18):

@@ -56,6 +56,18 @@ int fneus_prof_classes(void);
 int fneus_prof_enable(int on);
 int fneus_prof_collect(double* ms, long long* launches, double* flops, double* bytes);
 
+/* ---- flat weight packs (host glue of fields.py:67-68,143-144 weight_norm + the per-layer parameter tensors) -----
+ * One launch builds a network's flat pack from its parameter tensors: segment i is either a weight-normalised
+ * matrix (g[i] [rows], v[i] [rows,cols] -> W = g*v/|v|_row) or a plain copy (g[i] == NULL) of v[i], written at
+ * flat + off[i].  The arrays are HOST arrays of DEVICE pointers.  fneus_pack_bwd turns the flat gradient pack
+ * into dg[i] / dv[i] (NULL = skip), overwriting or (accumulate != 0) adding to them. */
+int fneus_pack_max_segments(void);
+int fneus_pack_fwd(int nseg, const float* const* g, const float* const* v, const long long* off, const int* rows,
+                   const int* cols, float* flat, void* stream);
+int fneus_pack_bwd(int nseg, const float* const* g, const float* const* v, float* const* dg, float* const* dv,
+                   const long long* off, const int* rows, const int* cols, const float* dflat, int accumulate,
+                   void* stream);
+
 /* ---- SDF network (fields.py:9-111) ------------------------------------------------------------ */
 typedef struct {
   int d_in;       /* 3 */
