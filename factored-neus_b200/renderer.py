@@ -203,6 +203,52 @@ class NeuSRenderer:
             "diffuse_color": ret_fine["diffuse_color"],
         }
 
+    # ------------------------------------------------------------------ stage 2: light visibility
+    def lvis_mateIllu_render_util(self, rays_o, rays_d, near, far):
+        """renderer.py:503-564: unperturbed up-sampling, SDF at the 128 section mid-points."""
+        dev = rays_o.device
+        rays_o, rays_d = rays_o.float().contiguous(), rays_d.float().contiguous()
+        B = len(rays_o)
+        sample_dist = 2.0 / self.n_samples
+        z_vals = (near + (far - near) * self._linspace(0.0, 1.0, self.n_samples, dev)[None, :]).contiguous()
+        n_samples = self.n_samples
+        if self.n_importance > 0:
+            z_vals = self._hierarchical(rays_o, rays_d, z_vals)
+            n_samples = self.n_samples + self.n_importance
+        dists, mid_z, pts, _ = ops.core_geometry(rays_o, rays_d, z_vals, sample_dist)
+        with torch.no_grad():
+            sdf = self._sdf_nograd(pts)
+        inside = (torch.linalg.norm(pts, ord=2, dim=-1).reshape(B, n_samples) < 1.0).float()
+        return {"n_samples": n_samples, "mid_z_vals": mid_z, "sdf": sdf,
+                "inside_sphere_mask": inside.sum(dim=-1) > 0.0}
+
+    def lvis_render(self, rays_o, rays_d, near, far, r_theta=None, rand_z=None):
+        """renderer.py:567-627 (fixed shapes: rays without a surface hit are masked to the default of ones)."""
+        from .lvis import cal_indiLgt
+        B = len(rays_o)
+        dev = rays_o.device
+        util = self.lvis_mateIllu_render_util(rays_o, rays_d, near, far)
+        n, mid_z = util["n_samples"], util["mid_z_vals"]
+        sdf_bn = util["sdf"].reshape(B, n)
+        neg = sdf_bn < 0
+        idx = torch.where(neg.any(-1), neg.float().argmax(-1), torch.full((B,), n, device=dev, dtype=torch.long))
+        sdf_mask = (idx < n) & (idx >= 1) & util["inside_sphere_mask"]
+        ii = idx.clamp(1, n - 1)[:, None]
+        z_lo, z_hi = mid_z.gather(1, ii - 1), mid_z.gather(1, ii)
+        s_lo, s_hi = sdf_bn.gather(1, ii - 1), sdf_bn.gather(1, ii)
+        z_surf = (s_lo * z_hi - s_hi * z_lo) / (s_lo - s_hi + 1e-10)
+        pts_surf = (rays_o + rays_d * z_surf).contiguous()
+        n_surf = self.sdf_network.gradient(pts_surf).reshape(-1, 3)
+        res = cal_indiLgt(pts_surf, n_surf, self.sdf_network, self.deviation_network, self.color_network,
+                          self.lvis_network, self.indiLgt_network, r_theta=r_theta, rand_z=rand_z)
+        m1, m3 = sdf_mask[:, None], sdf_mask[:, None, None]
+        ones1, ones3 = torch.ones(B, 4, device=dev), torch.ones(B, 4, 3, device=dev)
+        return {"gt_lvis": torch.where(m1, res["gt_lvis"], ones1),
+                "pre_lvis": torch.where(m1, res["pre_lvis"], ones1),
+                "gt_trace_radiance": torch.where(m3, res["gt_trace_radiance"], ones3),
+                "pre_trace_radiance": torch.where(m3, res["pre_trace_radiance"], ones3),
+                "sdf_mask": sdf_mask}
+
     # ------------------------------------------------------------------ grid query / mesh
     def extract_fields(self, bound_min, bound_max, resolution, ix0=0, ix1=None):
         """renderer.py:14-29: u = -sdf on the regular grid, as a device tensor [ix1-ix0, R, R] (x-slab)."""

@@ -405,3 +405,34 @@ def test_grid_query_matches_reference(golden_dir, states):
     assert_close(u, g["u"], 1e-5, "grid vs reference golden")
     slab = R.extract_fields(bmin, bmax, 20, ix0=5, ix1=9)               # x-slab sharding (multi-GPU unit)
     assert torch.equal(slab, u[5:9])
+
+
+def test_lvis_trace_matches_reference(golden_dir, states):
+    """Stage-2 ground truth (calLvis.cal_indiLgt gt_lvis / gt_trace_radiance) vs the reference golden."""
+    from factored_neus_b200 import lvis as LV
+    g = _golden(golden_dir, "lvis.npz")
+    m = build_modules(states, DEV)
+    lv, rad, dirs = LV.trace_visibility(_cu(g["surf"]), _cu(g["normal"]), m["sdf"], m["var"], m["color"],
+                                        _cu(g["r_theta"]), _cu(g["rand_z"]))
+    assert_close(lv, g["gt_lvis"], FP32_TOL, "gt_lvis vs reference golden")
+    assert_close(rad, g["gt_trace_radiance"], FP32_TOL, "gt_trace_radiance vs reference golden")
+
+
+def test_lvis_render_shapes(states):
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    R = m["renderer"]
+
+    class _L(torch.nn.Module):
+        def forward(self, p, v):
+            return torch.sigmoid(p.sum(-1, keepdim=True))
+
+    class _I(torch.nn.Module):
+        def forward(self, p):
+            return torch.ones(p.shape[0], 24, 7, device=p.device)
+
+    R.lvis_network, R.indiLgt_network = _L(), _I()
+    o, d, near, far = syn.make_rays(64, seed=1)
+    out = R.lvis_render(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV))
+    assert out["gt_lvis"].shape == (64, 4) and out["gt_trace_radiance"].shape == (64, 4, 3)
+    assert out["sdf_mask"].dtype == torch.bool and int(out["sdf_mask"].sum()) > 32
+    assert float(out["gt_lvis"].min()) >= -1e-4 and float(out["gt_lvis"].max()) <= 1.0 + 1e-4
