@@ -323,7 +323,12 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(args.cpu_rays)
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators captured inside a CUDA graph can stall destroy_process_group(): the result is out,
+        # so flush and leave without the collective teardown
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():
