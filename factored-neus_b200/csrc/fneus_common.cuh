@@ -121,6 +121,37 @@ __device__ __forceinline__ void mat_put(float* p, int ld, long long m, int k, fl
   *reinterpret_cast<unsigned short*>(reinterpret_cast<uint8_t*>(p) + img_off(m, k, -ld)) = (unsigned short)(u >> 16);
 }
 
+// Row-wise generation of all generated columns of row m: emit(column, value).  One accurate sincosf per
+// component and per third octave, the octaves in between by angle doubling (error <= ~4 ulp growth, far below
+// BF16 resolution) -- used by the tensor-core producers, where per-column sinf/cosf dominated layer 0.
+template <class Emit>
+__device__ __forceinline__ void gen_row(const GenSpec& g, long long m, Emit emit) {
+#pragma unroll 1
+  for (int i = 0; i < g.nitems; i++) {
+    const GenItem it = g.it[i];
+#pragma unroll 1
+    for (int c = 0; c < it.dim; c++) {
+      const float v = __ldg(it.src + m * it.dim + c) * it.scale;
+      const float t = g.deriv ? __ldg(it.tan + m * it.dim + c) : 0.f;
+      emit(it.col0 + c, g.deriv ? t : v);
+      float sn = 0.f, cs = 1.f;
+#pragma unroll 1
+      for (int k = 0; k < it.multires; k++) {
+        const float f = (float)(1u << k);
+        if (k % 3 == 0) sincosf(v * f, &sn, &cs);
+        else { float s2 = 2.f * sn * cs; cs = 1.f - 2.f * sn * sn; sn = s2; }
+        emit(it.col0 + it.dim * (1 + 2 * k) + c, g.deriv ? f * cs * t : sn);
+        emit(it.col0 + it.dim * (2 + 2 * k) + c, g.deriv ? -f * sn * t : cs);
+      }
+    }
+  }
+}
+__device__ __forceinline__ unsigned short f32_to_bf16_bits(float v) {
+  unsigned u = __float_as_uint(v);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (unsigned short)(u >> 16);
+}
+
 // Softplus(beta) with torch's threshold 20 (fields.py:72), and its derivative recovered from the
 // stored activation h = softplus(a):  sigma'(a) = 1 - exp(-beta h)   (SURVEY.md A.1).
 __device__ __forceinline__ float softplus_beta(float a, float beta) {

@@ -567,14 +567,23 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __res
             }
           }
         } else if (phase == 0) {
-          const int nq = Nc >> 2;
-#pragma unroll 1
-          for (int idx = tid; idx < 64 * nq; idx += 128) {
-            int mr = idx / nq, k = (idx - mr * nq) << 2;
-            long long m = mb + mr;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < mend) v = load_a4(a, 0, m, M, k0 + k);
-            sts_mnmajor(sB[s], mr, k, v);
+          // generated columns, MN-major: one reduction row per thread (64 rows), zero then fill
+          if (tid < 64) {
+            const int r7 = tid & 7;
+            uint8_t* rowp = sB[s] + (tid >> 3) * 1024 + r7 * 128;
+            const int nblk = (Nc + 63) >> 6;
+            for (int b = 0; b < nblk; b++)
+#pragma unroll
+              for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(rowp + b * 8192 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+            const long long m = mb + tid;
+            if (m < mend) {
+              gen_row(a.gen, m, [&](int j, float val) {
+                const int jj = j - k0;
+                if (jj >= 0 && jj < Nc)
+                  *reinterpret_cast<unsigned short*>(rowp + (jj >> 6) * 8192 + (((((jj & 63) >> 3) ^ r7) & 7) << 4) +
+                                                     ((jj & 7) << 1)) = f32_to_bf16_bits(val);
+              });
+            }
           }
         }
         fence_proxy_async();
@@ -878,10 +887,19 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
         const int phase = kb < kb_gen ? 0 : 1;
         const int k0 = (phase == 0 ? kb : kb - kb_gen) * TC_BK;
         if (phase == 0) {
-#pragma unroll 1
-          for (int it = 0; it < 16; it++) {
-            int idx = it * 128 + ptid;
-            sts_kmajor(sA[s], idx >> 4, (idx & 15) << 2, load_a4(a, 0, m0 + (idx >> 4), M, k0 + ((idx & 15) << 2)));
+          // generated columns: one row per thread, zero the 128-byte row segment then fill the valid columns
+          const int r7 = ptid & 7;
+          uint8_t* rowp = sA[s] + (ptid >> 3) * 1024 + r7 * 128;
+#pragma unroll
+          for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(rowp + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+          const long long m = m0 + ptid;
+          if (m < M) {
+            gen_row(a.gen, m, [&](int j, float val) {
+              const int jj = j - k0;
+              if (jj >= 0 && jj < TC_BK)
+                *reinterpret_cast<unsigned short*>(rowp + ((((jj >> 3) ^ r7) & 7) << 4) + ((jj & 7) << 1)) =
+                    f32_to_bf16_bits(val);
+            });
           }
           fence_proxy_async();
         } else if (!a_img && !(dbg & 1)) {
