@@ -1068,19 +1068,61 @@ __global__ void pack_wimg_kernel(const float* __restrict__ W, int ldw, int wout0
   uint2 hi = pack_bf16x4(make_float4(v[4], v[5], v[6], v[7]));
   *reinterpret_cast<uint4*>(img + (size_t)tile * TC_B_BYTES + off) = make_uint4(lo.x, lo.y, hi.x, hi.y);
 }
-// transposed = false: image for C = A W^T (forward);  true: image for C = A W (input-gradient chains)
-inline void launch_pack_wimg(bool for_bwd_data, const float* W, int ldw, int wout0, int N, int wred_gen, int kgen,
-                             int wred_mem, int kmem, uint8_t* img, cudaStream_t st) {
-  long long total = (long long)cdiv(N, 256) * (cdiv(kgen, TC_BK) + cdiv(kmem, TC_BK)) * 2048;
-  if (total == 0) return;
-  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
-  if (for_bwd_data) pack_wimg_kernel<false><<<cdiv(total, 256), 256, 0, st>>>(W, ldw, wout0, N, wred_gen, kgen, wred_mem, kmem, img);
-  else pack_wimg_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(W, ldw, wout0, N, wred_gen, kgen, wred_mem, kmem, img);
-  prof_end(st);
-}
+// Several layers' images in one launch: blockIdx.y = job.
+constexpr int PACK_MAX_JOBS = 24;
+struct PackJob {
+  const float* W; uint8_t* img;
+  int ldw, wout0, N, wred_gen, kgen, wred_mem, kmem, for_bwd_data;
+};
+struct PackJobs { int n; PackJob job[PACK_MAX_JOBS]; };
 
-void launch_colsum(const float* X, int ldx, int K, const float* w, float wscale, float* out, float* osum, long long M,
-                   cudaStream_t st);
+template <bool WT>
+__device__ __forceinline__ void pack_wimg_chunk(const PackJob& j, long long idx) {
+  const float* __restrict__ W = j.W;
+  const int ldw = j.ldw, wout0 = j.wout0, N = j.N;
+  const int kb_gen = (j.kgen + TC_BK - 1) / TC_BK, kb_mem = (j.kmem + TC_BK - 1) / TC_BK;
+  const int KB = kb_gen + kb_mem;
+  const int tile = (int)(idx / 2048), within = (int)(idx % 2048);
+  const int nchunk = tile / KB, kb = tile % KB;
+  const int phase = kb < kb_gen ? 0 : 1;
+  const int k0 = (phase == 0 ? kb : kb - kb_gen) * TC_BK;
+  const int kmax = phase == 0 ? j.kgen : j.kmem;
+  const int wred0 = phase == 0 ? j.wred_gen : j.wred_mem;
+  const int n0 = nchunk * 256;
+  float v[8];
+  int off;
+  if (WT) {
+    const int r = within >> 3, c = within & 7;
+    const int n = n0 + r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      int k = k0 + c * 8 + i;
+      v[i] = (n < N && k < kmax) ? __ldg(W + (long long)(wout0 + n) * ldw + wred0 + k) : 0.f;
+    }
+    off = (r >> 3) * 1024 + (r & 7) * 128 + (((c ^ (r & 7)) & 7) << 4);
+  } else {
+    const int nb = within >> 9, rem = within & 511;
+    const int kr = rem >> 3, c = rem & 7;
+    const int k = k0 + kr;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      int n = n0 + nb * 64 + c * 8 + i;
+      v[i] = (n < N && k < kmax) ? __ldg(W + (long long)(wred0 + k) * ldw + wout0 + n) : 0.f;
+    }
+    off = nb * 8192 + (kr >> 3) * 1024 + (kr & 7) * 128 + (((c ^ (kr & 7)) & 7) << 4);
+  }
+  uint2 lo = pack_bf16x4(make_float4(v[0], v[1], v[2], v[3]));
+  uint2 hi = pack_bf16x4(make_float4(v[4], v[5], v[6], v[7]));
+  *reinterpret_cast<uint4*>(j.img + (size_t)tile * TC_B_BYTES + off) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+}
+__global__ void pack_wimg_multi_kernel(PackJobs jobs) {
+  const PackJob& j = jobs.job[blockIdx.y];
+  const long long total = (long long)((j.N + 255) / 256) * ((j.kgen + TC_BK - 1) / TC_BK + (j.kmem + TC_BK - 1) / TC_BK) * 2048;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    if (j.for_bwd_data) pack_wimg_chunk<false>(j, idx);
+    else pack_wimg_chunk<true>(j, idx);
+  }
+}
 
 constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 + 256;
 
@@ -1153,24 +1195,40 @@ inline void launch_tc_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, 
 // ---------------------------------------------------------------------------------------------
 inline int& precision_mode() { static int m = 0; return m; }
 
-// A bump allocator over a caller-provided byte region for the weight images of one ABI call.
+// A bump allocator over a caller-provided byte region for the weight images of one ABI call.  make_wimg only
+// RECORDS the packing job; ImgArena::flush packs every recorded image in one launch and must be called before the
+// first GEMM that consumes one (images depend only on the weights, so a pass declares all of them up front).
 struct ImgArena {
   uint8_t* base; size_t cap, used;
+  PackJobs jobs;
   uint8_t* take(size_t bytes) {
     size_t off = (used + 1023) & ~(size_t)1023;
     if (!base || off + bytes > cap) return nullptr;
     used = off + bytes;
     return base + off;
   }
+  void flush(cudaStream_t st) {
+    if (jobs.n == 0) return;
+    prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+    pack_wimg_multi_kernel<<<dim3(32, jobs.n), 256, 0, st>>>(jobs);
+    prof_end(st);
+    jobs.n = 0;
+  }
 };
-// Build (when in BF16 mode and the arena has room) the image a later launch_gemm_fwd / launch_gemm_bwd_data with the
-// same (W, wout0, N, segments) will consume; returns nullptr in FP32 mode (callers just pass it through).
+inline ImgArena arena_make(uint8_t* base, size_t cap) {
+  ImgArena ar;
+  ar.base = base; ar.cap = cap; ar.used = 0; ar.jobs.n = 0;
+  return ar;
+}
 inline const uint8_t* make_wimg(ImgArena& ar, bool for_bwd_data, const float* W, int ldw, int wout0, int N,
                                 int wred_gen, int kgen, int wred_mem, int kmem, cudaStream_t st) {
   if (precision_mode() != 1) return nullptr;
   uint8_t* img = ar.take(wimg_bytes(N, kgen, kmem));
   if (!img) return nullptr;
-  launch_pack_wimg(for_bwd_data, W, ldw, wout0, N, wred_gen, kgen, wred_mem, kmem, img, st);
+  if (ar.jobs.n == PACK_MAX_JOBS) ar.flush(st);
+  PackJob& j = ar.jobs.job[ar.jobs.n++];
+  j.W = W; j.img = img; j.ldw = ldw; j.wout0 = wout0; j.N = N; j.wred_gen = wred_gen; j.kgen = kgen;
+  j.wred_mem = wred_mem; j.kmem = kmem; j.for_bwd_data = for_bwd_data ? 1 : 0;
   return img;
 }
 

@@ -230,10 +230,28 @@ static GenSpec sdf_gen(const fneus_sdf_cfg* c, const float* x, const float* tan)
   return g;
 }
 
+// All weight images one pass needs, declared up front and packed by ONE launch (ImgArena::flush).
+struct SdfImgs { const uint8_t* F[20]; const uint8_t* B[20]; };
+static SdfImgs sdf_make_images(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, bool fwd, bool fwd_split_last,
+                               bool bwd_hidden, bool bwd_last, ImgArena& ar, cudaStream_t st) {
+  SdfImgs im;
+  for (int l = 0; l <= p.L; l++) { im.F[l] = nullptr; im.B[l] = nullptr; }
+  if (precision_mode() != 1) return im;
+  for (int l = 0; l <= p.L; l++) {
+    const float* W = w + p.woff[l];
+    if (fwd && l < p.L) im.F[l] = make_wimg(ar, false, W, p.in[l], 0, p.out[l], 0, l == 0 ? p.in[l] : 0, 0, l == 0 ? 0 : p.in[l], st);
+    if (fwd && l == p.L && fwd_split_last) im.F[l] = make_wimg(ar, false, W, p.in[l], 1, p.out[l] - 1, 0, 0, 0, p.in[l], st);
+    if (bwd_hidden && l < p.L) im.B[l] = make_wimg(ar, true, W, p.in[l], 0, p.in[l], 0, 0, 0, p.out[l], st);
+    if (bwd_last && l == p.L) im.B[l] = make_wimg(ar, true, W, p.in[l], 0, p.in[l], 0, 0, 1, c->d_out - 1, st);
+  }
+  ar.flush(st);
+  return im;
+}
+
 // value chain. If bufs != nullptr activations go to bufs->H (saved) else ping-pong in scratch.
 static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, const float* x, long long M,
                            float* sdf_out, float* feat_out, SdfBufs* bufs, float* scratch, cudaStream_t st,
-                           float out_sign, ImgArena& ar) {
+                           float out_sign, const SdfImgs& im) {
   const float rsqrt2 = 0.70710678118654752440f;
   float* pp[2] = {scratch, scratch + sdf_buf_floats(p, M)};
   const float* Hin = nullptr;
@@ -245,10 +263,7 @@ static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float
     e.beta = c->beta;
     e.bias = b;
     const bool tc_split_last = (l == p.L) && feat_out && precision_mode() == 1;
-    const uint8_t* img = (l < p.L || tc_split_last)
-        ? make_wimg(ar, false, W, p.in[l], tc_split_last ? 1 : 0, tc_split_last ? p.out[l] - 1 : p.out[l], 0,
-                    l == 0 ? p.in[l] : 0, 0, l == 0 ? 0 : p.in[l], st)
-        : nullptr;
+    const uint8_t* img = im.F[l];
     if (l < p.L) {
       float* Hout = bufs ? bufs->H[l + 1] : pp[(l + 1) & 1];
       e.mode = EPI_SOFTPLUS;
@@ -319,7 +334,7 @@ int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   if (n < 0) return FNEUS_ERR_BAD_SHAPE;
   long long per128 = 2LL * sdf_buf_floats(p, 128);           // scratch floats per 128 points (upper bound)
   long long img_floats = (long long)(sdf_img_bytes(p) / 4) + 256;
-  ImgArena ar{nullptr, 0, 0};
+  ImgArena ar = arena_make(nullptr, 0);
   long long avail = scratch_floats - 1024;
   if (p.img) {
     if (scratch_floats < img_floats + per128 + 2048) return FNEUS_ERR_WORKSPACE;
@@ -331,12 +346,12 @@ int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   if (chunk < 128) return FNEUS_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
+  SdfImgs im = sdf_make_images(cfg, p, wpack, true, feat_out != nullptr, false, false, ar, st);
   for (long long m0 = 0; m0 < n; m0 += chunk) {
     long long M = n - m0 < chunk ? n - m0 : chunk;
-    ar.used = 0;
     sdf_zero_images(p, scratch, 2LL * sdf_buf_floats(p, M), M, st);
     int rc = sdf_value_chain(cfg, p, wpack, x + m0 * cfg->d_in, M, sdf_out + m0,
-                             feat_out ? feat_out + m0 * (cfg->d_out - 1) : nullptr, nullptr, scratch, st, 1.f, ar);
+                             feat_out ? feat_out + m0 * (cfg->d_out - 1) : nullptr, nullptr, scratch, st, 1.f, im);
     if (rc) return rc;
   }
   return FNEUS_OK;
@@ -351,7 +366,7 @@ int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax
   if (nx < 1 || ny < 1 || nz < 1 || ix0 < 0 || ix1 > nx || ix0 > ix1) return FNEUS_ERR_BAD_SHAPE;
   long long per128 = 2LL * sdf_buf_floats(p, 128) + 3 * 128;
   long long img_floats = (long long)(sdf_img_bytes(p) / 4) + 256;
-  ImgArena ar{nullptr, 0, 0};
+  ImgArena ar = arena_make(nullptr, 0);
   long long avail = scratch_floats - 1024;
   if (p.img) {
     if (scratch_floats < img_floats + per128 + 2048) return FNEUS_ERR_WORKSPACE;
@@ -364,6 +379,7 @@ int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax
   cudaStream_t st = (cudaStream_t)stream;
   scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
   long long i0 = (long long)ix0 * ny * nz, i1 = (long long)ix1 * ny * nz;
+  SdfImgs im = sdf_make_images(cfg, p, wpack, true, false, false, false, ar, st);
   for (long long b = i0; b < i1; b += chunk) {
     long long M = i1 - b < chunk ? i1 - b : chunk;
     float* pts = scratch + 2LL * sdf_buf_floats(p, chunk);
@@ -371,8 +387,7 @@ int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax
     prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
     grid_points_kernel<<<ew_blocks(M), 256, 0, st>>>(ax, ay, az, ny, nz, b, M, pts);
     prof_end(st);
-    ar.used = 0;
-    int rc = sdf_value_chain(cfg, p, wpack, pts, M, u_out + (b - i0), nullptr, nullptr, scratch, st, -1.f, ar);
+    int rc = sdf_value_chain(cfg, p, wpack, pts, M, u_out + (b - i0), nullptr, nullptr, scratch, st, -1.f, im);
     if (rc) return rc;
   }
   return FNEUS_OK;
@@ -389,13 +404,14 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
   const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
   SdfBufs b = sdf_carve(p, saved, M);
   sdf_zero_images(p, saved, sdf_saved_floats(p, M), M, st);
-  ImgArena ar{nullptr, 0, 0};
+  ImgArena ar = arena_make(nullptr, 0);
   if (p.img) {
     ar.base = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(scratch + sdf_scratch_main(p, M)) + 1023) & ~(uintptr_t)1023);
     ar.cap = sdf_img_bytes(p) - 1024;
   }
-  int rc = sdf_value_chain(cfg, p, wpack, x, M, sdf_out, feat_out, &b, scratch, st, 1.f, ar);
+  SdfImgs im = sdf_make_images(cfg, p, wpack, true, true, normal_out != nullptr, false, ar, st);
+  int rc = sdf_value_chain(cfg, p, wpack, x, M, sdf_out, feat_out, &b, scratch, st, 1.f, im);
   if (rc) return rc;
   if (!normal_out) return FNEUS_OK;   // value-only graph (SDFNetwork.forward under autograd)
   // reverse chain for the normal: g_l = q_l W_l, q_{l-1} = s_{l-1} * g_l
@@ -414,8 +430,7 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
       e.csplit = p.out[l - 1];
       e.C2 = g0e; e.ldc2 = e4;
     }
-    launch_gemm_bwd_data(a, wpack + p.woff[l], p.in[l], 0, M, p.in[l], e, st,
-                         make_wimg(ar, true, wpack + p.woff[l], p.in[l], 0, p.in[l], 0, 0, 0, p.out[l], st));
+    launch_gemm_bwd_data(a, wpack + p.woff[l], p.in[l], 0, M, p.in[l], e, st, im.B[l]);
   }
   {
     ASeg a = aseg_mem(b.Q[0], p.ldout[0], p.out[0]);
@@ -423,8 +438,7 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
     e.mode = EPI_LINEAR_ADD;
     e.Q = p.skip > 0 ? g0e : nullptr; e.ldq = e4;
     e.C = g0; e.ldc = e4;
-    launch_gemm_bwd_data(a, wpack + p.woff[0], p.in[0], 0, M, p.in[0], e, st,
-                         make_wimg(ar, true, wpack + p.woff[0], p.in[0], 0, p.in[0], 0, 0, 0, p.out[0], st));
+    launch_gemm_bwd_data(a, wpack + p.woff[0], p.in[0], 0, M, p.in[0], e, st, im.B[0]);
   }
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   normal_from_g0_kernel<<<ew_blocks(M), 256, 0, st>>>(x, cfg->d_in, cfg->multires, cfg->scale, g0, e4, normal_out, M);
@@ -452,13 +466,14 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   float* abuf[2] = {scratch + 2 * bf, scratch + 3 * bf};
   sdf_zero_images(p, scratch, 4 * bf, M, st);
   const int L = p.L;
-  ImgArena ar{nullptr, 0, 0};
+  ImgArena ar = arena_make(nullptr, 0);
   if (p.img) {
     ar.base = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(scratch + sdf_scratch_main(p, M)) + 1023) & ~(uintptr_t)1023);
     ar.cap = sdf_img_bytes(p) - 1024;
   }
 
+  SdfImgs im = sdf_make_images(cfg, p, wpack, d_normal != nullptr, false, true, d_feat != nullptr, ar, st);
   if (d_normal) {
     // double-backward sweep: gbar_0 = T0 nbar ; qbar_l = gbar_l W_l^T ; dW_l += q_l^T gbar_l ;
     // gbar_{l+1} = s_l qbar_l ; e_l = beta (1-s_l) q_l qbar_l (written over q_l)
@@ -473,9 +488,7 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
       float* gout = gbuf[(l + 1) & 1];
       e.C = gout; e.ldc = p.ldin[l + 1];
       if (l + 1 == p.skip) { e.hscale = sqrt2; e.oscale = rsqrt2; }
-      launch_gemm_fwd(a, wpack + p.woff[l], p.in[l], 0, M, p.out[l], e, st,
-                      make_wimg(ar, false, wpack + p.woff[l], p.in[l], 0, p.out[l], 0, l == 0 ? p.in[l] : 0, 0,
-                                l == 0 ? 0 : p.in[l], st));
+      launch_gemm_fwd(a, wpack + p.woff[l], p.in[l], 0, M, p.out[l], e, st, im.F[l]);
       if (l + 1 == p.skip) {
         GenSpec g = sdf_gen(cfg, x, d_normal);
         prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
@@ -505,9 +518,7 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     e.rs = d_sdf; e.rvec = wpack + p.woff[L]; e.rscale = 1.f / cfg->scale;
     e.Q = d_normal ? b.Q[L - 1] : nullptr; e.ldq = p.ldout[L - 1];
     e.C = abuf[(L - 1) & 1]; e.ldc = p.ldout[L - 1];
-    launch_gemm_bwd_data(a, wpack + p.woff[L], p.in[L], 0, M, p.in[L], e, st,
-                         d_feat ? make_wimg(ar, true, wpack + p.woff[L], p.in[L], 0, p.in[L], 0, 0, 1, cfg->d_out - 1, st)
-                                : nullptr);
+    launch_gemm_bwd_data(a, wpack + p.woff[L], p.in[L], 0, M, p.in[L], e, st, im.B[L]);
   }
   for (int l = L - 1; l >= 0; l--) {
     float* al = abuf[l & 1];
@@ -522,8 +533,7 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     if (l == p.skip) { e.hscale = sqrt2; e.oscale = rsqrt2; e.csplit = p.out[l - 1]; }
     e.Q = d_normal ? b.Q[l - 1] : nullptr; e.ldq = p.ldout[l - 1];
     e.C = abuf[(l - 1) & 1]; e.ldc = p.ldout[l - 1];
-    launch_gemm_bwd_data(a, wpack + p.woff[l], p.in[l], 0, M, p.in[l], e, st,
-                         make_wimg(ar, true, wpack + p.woff[l], p.in[l], 0, p.in[l], 0, 0, 0, p.out[l], st));
+    launch_gemm_bwd_data(a, wpack + p.woff[l], p.in[l], 0, M, p.in[l], e, st, im.B[l]);
   }
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;

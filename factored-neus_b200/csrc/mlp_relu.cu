@@ -30,7 +30,7 @@ static inline void zero_if_ragged(bool img, float* ptr, long long floats, long l
   if (img && (M & 127)) cudaMemsetAsync(ptr, 0, (size_t)floats * 4, st);
 }
 static ImgArena arena_at(float* after_floats, size_t cap_bytes) {
-  ImgArena ar{nullptr, 0, 0};
+  ImgArena ar = arena_make(nullptr, 0);
   if (precision_mode() == 1 && after_floats) {
     ar.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(after_floats) + 1023) & ~(uintptr_t)1023);
     ar.cap = cap_bytes - 1024;
@@ -40,15 +40,20 @@ static ImgArena arena_at(float* after_floats, size_t cap_bytes) {
 
 static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs, int ldh,
                            int last_mode, float* out, int ld_out, long long M, cudaStream_t st, ImgArena& ar) {
+  const uint8_t* img[16];
+  for (int l = 0; l < n_lin; l++) {
+    ASeg a = l == 0 ? a0 : aseg_mem(Hs[l], ldh, lin[l].in);
+    img[l] = make_wimg(ar, false, w + lin[l].woff, lin[l].in, 0, lin[l].out, a.wred_gen, a.gen.ncols, a.wred_mem,
+                       a.kmem, st);
+  }
+  ar.flush(st);
   for (int l = 0; l < n_lin; l++) {
     ASeg a = l == 0 ? a0 : aseg_mem(Hs[l], ldh, lin[l].in);
     Epi e = epi_default();
     e.bias = w + lin[l].boff;
     if (l < n_lin - 1) { e.mode = EPI_RELU; e.C = Hs[l + 1]; e.ldc = ldh; }
     else { e.mode = last_mode; e.C = out; e.ldc = ld_out; }
-    launch_gemm_fwd(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].out, e, st,
-                    make_wimg(ar, false, w + lin[l].woff, lin[l].in, 0, lin[l].out, a.wred_gen, a.gen.ncols,
-                              a.wred_mem, a.kmem, st));
+    launch_gemm_fwd(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].out, e, st, img[l]);
   }
 }
 
@@ -62,6 +67,11 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
   const float* al = a_last;
   int ld_al = ld_last;
   float* ab[2] = {abuf0, abuf1};
+  const uint8_t* img[16];
+  for (int l = n_lin - 1; l >= 0; l--)
+    img[l] = (l > 0 || dsmall || d_feats)
+                 ? make_wimg(ar, true, w + lin[l].woff, lin[l].in, 0, lin[l].in, 0, 0, 0, lin[l].out, st) : nullptr;
+  ar.flush(st);
   for (int l = n_lin - 1; l >= 0; l--) {
     ASeg h = l == 0 ? a0 : aseg_mem(Hs[l], ldh, lin[l].in);
     launch_gemm_wgrad(al, ld_al, h, dw + lin[l].woff, lin[l].in, 0, dw + lin[l].boff, M, lin[l].out, sms, st);
@@ -71,16 +81,14 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
     if (l > 0) {
       e.H = Hs[l]; e.ldh = ldh;
       e.C = ab[l & 1]; e.ldc = ldh;
-      launch_gemm_bwd_data(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].in, e, st,
-                           make_wimg(ar, true, w + lin[l].woff, lin[l].in, 0, lin[l].in, 0, 0, 0, lin[l].out, st));
+      launch_gemm_bwd_data(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].in, e, st, img[l]);
       al = ab[l & 1]; ld_al = ldh;
     } else if (dsmall || d_feats) {
       e.H = nullptr;
       e.C = dsmall; e.ldc = ld_small;
       e.csplit = a0.gen.ncols;
       e.C2 = d_feats; e.ldc2 = ld_feats; e.accumulate2 = accumulate_feats;
-      launch_gemm_bwd_data(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].in, e, st,
-                           make_wimg(ar, true, w + lin[l].woff, lin[l].in, 0, lin[l].in, 0, 0, 0, lin[l].out, st));
+      launch_gemm_bwd_data(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].in, e, st, img[l]);
     }
   }
 }
