@@ -815,10 +815,10 @@ __device__ __forceinline__ void epilogue_row16(const Epi& e, long long m, int n,
 
 template <int MODE>
 __device__ __forceinline__ void epilogue_tile(const Epi& e, uint32_t taddr, long long m, int M, int n0, int Nc, int N,
-                                              int grp, int cover, const float* sb, const float* sr) {
+                                              int grp, int ngroups, int cover, const float* sb, const float* sr) {
   // cover: columns (relative to n0) that must be written even beyond Nc (image padding), multiple of 32
 #pragma unroll 1
-  for (int c0 = grp * 32; c0 < cover; c0 += 64) {
+  for (int c0 = grp * 32; c0 < cover; c0 += 32 * ngroups) {
 #pragma unroll 1
     for (int hseg = 0; hseg < 32; hseg += 16) {
       float a[16];
@@ -855,12 +855,16 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
   const int kb_mem = (a.kmem + TC_BK - 1) / TC_BK;
   const int KB = kb_gen + kb_mem;
   const bool a_img = a.ldm < 0;
+  // when every reduction block of A arrives by bulk copy the 8 producer warps have nothing to produce: they join
+  // the epilogue (4 column groups instead of 2), halving its per-tile latency chain
+  const bool extra_epi = a_img && kb_gen == 0;
+  const int ngroups = extra_epi ? 4 : 2;
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < P_STAGES; s++) { mbar_init(&ctl->full[s], 129); mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < P_STAGES; s++) { mbar_init(&ctl->full[s], extra_epi ? 1 : 129); mbar_init(&ctl->empty[s], 1); }
 #pragma unroll
-    for (int s = 0; s < 2; s++) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_empty[s], 256); }
+    for (int s = 0; s < 2; s++) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_empty[s], 128 * ngroups); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // stage the per-column vectors of the epilogue (bias, rvec) once
@@ -874,7 +878,7 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp < 8) {
+  if (warp < 8 && !extra_epi) {
     // ------------------------------ A producers ------------------------------
     const int grp = warp >> 2, ptid = tid & 127;
     int kbg = 0;
@@ -975,7 +979,7 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
     }
   } else {
     // ------------------------------ epilogue ------------------------------
-    const int grp = (warp - 10) >> 2;          // column-chunk parity handled by this warp
+    const int grp = warp >= 10 ? (warp - 10) >> 2 : 2 + (warp >> 2);   // column-chunk group of this warp
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const float* sb = svec;
     const float* sr = svec + 1024;
@@ -995,16 +999,16 @@ tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restr
       const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(quarter * 32) << 16);
       if (!(dbg & 2)) {
         switch (e.mode) {
-          case EPI_LINEAR: epilogue_tile<EPI_LINEAR>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
-          case EPI_RELU: epilogue_tile<EPI_RELU>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
-          case EPI_SIGMOID: epilogue_tile<EPI_SIGMOID>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
-          case EPI_SOFTPLUS: epilogue_tile<EPI_SOFTPLUS>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
-          case EPI_SOFTPLUS_Q: epilogue_tile<EPI_SOFTPLUS_Q>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
-          case EPI_SPMUL: epilogue_tile<EPI_SPMUL>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
-          case EPI_SWEEP: epilogue_tile<EPI_SWEEP>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
-          case EPI_SDF_BWD: epilogue_tile<EPI_SDF_BWD>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
-          case EPI_RELUMASK: epilogue_tile<EPI_RELUMASK>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
-          case EPI_LINEAR_ADD: epilogue_tile<EPI_LINEAR_ADD>(e, taddr, m, M, n0, Nc, N, grp, cover, sb, sr); break;
+          case EPI_LINEAR: epilogue_tile<EPI_LINEAR>(e, taddr, m, M, n0, Nc, N, grp, ngroups, cover, sb, sr); break;
+          case EPI_RELU: epilogue_tile<EPI_RELU>(e, taddr, m, M, n0, Nc, N, grp, ngroups, cover, sb, sr); break;
+          case EPI_SIGMOID: epilogue_tile<EPI_SIGMOID>(e, taddr, m, M, n0, Nc, N, grp, ngroups, cover, sb, sr); break;
+          case EPI_SOFTPLUS: epilogue_tile<EPI_SOFTPLUS>(e, taddr, m, M, n0, Nc, N, grp, ngroups, cover, sb, sr); break;
+          case EPI_SOFTPLUS_Q: epilogue_tile<EPI_SOFTPLUS_Q>(e, taddr, m, M, n0, Nc, N, grp, ngroups, cover, sb, sr); break;
+          case EPI_SPMUL: epilogue_tile<EPI_SPMUL>(e, taddr, m, M, n0, Nc, N, grp, ngroups, cover, sb, sr); break;
+          case EPI_SWEEP: epilogue_tile<EPI_SWEEP>(e, taddr, m, M, n0, Nc, N, grp, ngroups, cover, sb, sr); break;
+          case EPI_SDF_BWD: epilogue_tile<EPI_SDF_BWD>(e, taddr, m, M, n0, Nc, N, grp, ngroups, cover, sb, sr); break;
+          case EPI_RELUMASK: epilogue_tile<EPI_RELUMASK>(e, taddr, m, M, n0, Nc, N, grp, ngroups, cover, sb, sr); break;
+          case EPI_LINEAR_ADD: epilogue_tile<EPI_LINEAR_ADD>(e, taddr, m, M, n0, Nc, N, grp, ngroups, cover, sb, sr); break;
           default: break;                    // EPI_SDF_OUT is never routed to the persistent kernel
         }
       }
