@@ -3,6 +3,7 @@
 // Every dense layer is one launch of the SIMT GEMM engine (gemm_simt.cuh) with a fused epilogue;
 // positional encodings are generated in the GEMM tile loaders.
 #include "gemm_tc.cuh"
+#include "sdf_fused.cuh"
 #include "prof.cuh"
 
 namespace fneus {
@@ -62,6 +63,47 @@ __global__ void colsum_kernel(const float* X, int ldx, int K, const float* w, fl
   }
   if (k < K) atomicAdd(out + k, acc);
   if (osum && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(osum, ws);
+}
+
+// Column sums of a BF16 activation image: block = (column block of 64, range of rows); thread t owns the logical
+// 16-byte column group t%8 (8 columns) and rows t/8 + 32 i, so every load is one 16-byte chunk and a warp reads
+// four full 128-byte image rows per instruction.
+__global__ void colsum_img_kernel(const uint8_t* __restrict__ img, int kbs, int K, const float* __restrict__ w,
+                                  float wscale, float* __restrict__ out, float* __restrict__ osum, long long M,
+                                  int rows_per_block) {
+  const int cb = blockIdx.x;                       // column block
+  const long long mbeg = (long long)blockIdx.y * rows_per_block;
+  const long long mend = mbeg + rows_per_block < M ? mbeg + rows_per_block : M;
+  const int g = threadIdx.x & 7, rsub = threadIdx.x >> 3;     // 256 threads: 32 row lanes x 8 column groups
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float ws = 0.f;
+  for (long long m = mbeg + rsub; m < mend; m += 32) {
+    const float wm = w ? __ldg(w + m) * wscale : 1.f;
+    const uint8_t* p = img + ((size_t)(m >> 7) * kbs + cb) * 16384 + (((m & 127) >> 3) * 1024 + (m & 7) * 128) +
+                       (((g ^ (int)(m & 7)) & 7) << 4);
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    uint32_t v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      acc[2 * t] += wm * __uint_as_float(v[t] << 16);
+      acc[2 * t + 1] += wm * __uint_as_float(v[t] & 0xFFFF0000u);
+    }
+    if (g == 0) ws += wm;
+  }
+  __shared__ float red[64];
+  __shared__ float redw;
+  if (threadIdx.x < 64) red[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) redw = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; i++) atomicAdd(&red[g * 8 + i], acc[i]);
+  if (g == 0) atomicAdd(&redw, ws);
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    int k = cb * 64 + threadIdx.x;
+    if (k < K) atomicAdd(out + k, red[threadIdx.x]);
+  }
+  if (osum && cb == 0 && threadIdx.x == 0) atomicAdd(osum, redw);
 }
 
 // out0[m] = (dot(H[m,:K], w) + b) * scale     one warp per row (H: FP32 row-major or BF16 activation image)
@@ -126,10 +168,16 @@ static inline int ew_blocks(long long n) { return cdiv(n, 256); }
 void launch_colsum(const float* X, int ldx, int K, const float* w, float wscale, float* out, float* osum, long long M,
                    cudaStream_t st) {
   if (M <= 0 || K <= 0) return;
-  int mpb = 256;
-  dim3 grid(cdiv(K, 256), cdiv(M, mpb));
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
-  colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, K, w, wscale, out, osum, M, mpb);
+  if (ldx < 0) {
+    int rpb = 512;
+    dim3 grid(cdiv(K, 64), cdiv(M, rpb));
+    colsum_img_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(X), -ldx, K, w, wscale, out, osum, M, rpb);
+  } else {
+    int mpb = 256;
+    dim3 grid(cdiv(K, 256), cdiv(M, mpb));
+    colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, K, w, wscale, out, osum, M, mpb);
+  }
   prof_end(st);
 }
 
@@ -248,6 +296,40 @@ static SdfImgs sdf_make_images(const fneus_sdf_cfg* c, const SdfPlan& p, const f
   return im;
 }
 
+static bool sdf_fused_ok(const SdfPlan& p) {
+  if (p.L < 2 || p.L > FZ_MAXL || p.e > TC_BK) return false;
+  for (int l = 0; l < p.L; l++)
+    if (p.in[l] > 256 || p.out[l] > 256) return false;
+  if (p.skip > 0 && p.out[p.skip - 1] + p.e > 256) return false;
+  return true;
+}
+static int sdf_fused_launch(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, const float* x, long long M,
+                            float* sdf_out, float out_sign, const SdfImgs& im, cudaStream_t st) {
+  static int prepared = 0;
+  if (!prepared) {
+    cudaError_t e = cudaFuncSetAttribute(sdf_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM_BYTES);
+    if (e != cudaSuccess) return fneus_cuda_error((int)e);
+    prepared = 1;
+  }
+  FusedSdfArgs g;
+  g.L = p.L;
+  for (int l = 0; l < p.L; l++) {
+    g.in[l] = p.in[l]; g.out[l] = p.out[l]; g.img[l] = im.F[l]; g.bias[l] = w + p.boff[l];
+  }
+  g.w_last = w + p.woff[p.L]; g.b_last = w + p.boff[p.L];
+  g.skip = p.skip; g.beta = c->beta; g.scale = c->scale; g.out_sign = out_sign;
+  g.gen = sdf_gen(c, x, nullptr);
+  g.x = x; g.sdf_out = sdf_out; g.M = M;
+  long long npairs = ((M + 127) / 128 + 1) / 2;
+  int grid = (int)(npairs < tc_num_sms() ? npairs : tc_num_sms());
+  double flops = 0;
+  for (int l = 0; l < p.L; l++) flops += 2.0 * M * p.in[l] * p.out[l];
+  prof_begin(PC_TC_MLP, flops + 2.0 * M * p.in[p.L], 0.0, st);
+  sdf_fused_fwd_kernel<<<grid, FZ_THREADS, FZ_SMEM_BYTES, st>>>(g);
+  prof_end(st);
+  return FNEUS_OK;
+}
+
 // value chain. If bufs != nullptr activations go to bufs->H (saved) else ping-pong in scratch.
 static int sdf_value_chain(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, const float* x, long long M,
                            float* sdf_out, float* feat_out, SdfBufs* bufs, float* scratch, cudaStream_t st,
@@ -347,6 +429,12 @@ int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   cudaStream_t st = (cudaStream_t)stream;
   scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
   SdfImgs im = sdf_make_images(cfg, p, wpack, true, feat_out != nullptr, false, false, ar, st);
+  if (p.img && !feat_out && sdf_fused_ok(p) && im.F[0]) {
+    int rc = sdf_fused_launch(cfg, p, wpack, x, n, sdf_out, 1.f, im, st);
+    if (rc) return rc;
+    FNEUS_CHECK_LAUNCH();
+    return FNEUS_OK;
+  }
   for (long long m0 = 0; m0 < n; m0 += chunk) {
     long long M = n - m0 < chunk ? n - m0 : chunk;
     sdf_zero_images(p, scratch, 2LL * sdf_buf_floats(p, M), M, st);
@@ -380,6 +468,7 @@ int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax
   scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
   long long i0 = (long long)ix0 * ny * nz, i1 = (long long)ix1 * ny * nz;
   SdfImgs im = sdf_make_images(cfg, p, wpack, true, false, false, false, ar, st);
+  const bool fused = p.img && sdf_fused_ok(p) && im.F[0];
   for (long long b = i0; b < i1; b += chunk) {
     long long M = i1 - b < chunk ? i1 - b : chunk;
     float* pts = scratch + 2LL * sdf_buf_floats(p, chunk);
@@ -387,7 +476,8 @@ int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax
     prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
     grid_points_kernel<<<ew_blocks(M), 256, 0, st>>>(ax, ay, az, ny, nz, b, M, pts);
     prof_end(st);
-    int rc = sdf_value_chain(cfg, p, wpack, pts, M, u_out + (b - i0), nullptr, nullptr, scratch, st, -1.f, im);
+    int rc = fused ? sdf_fused_launch(cfg, p, wpack, pts, M, u_out + (b - i0), -1.f, im, st)
+                   : sdf_value_chain(cfg, p, wpack, pts, M, u_out + (b - i0), nullptr, nullptr, scratch, st, -1.f, im);
     if (rc) return rc;
   }
   return FNEUS_OK;

@@ -107,3 +107,29 @@ def test_bf16_fields_and_render(bf16_mode, golden_dir):
             assert err <= BF16_TOL * max(1.0, scale) , "bf16 grad %s.%s err %.3e (scale %.3e)" % (net, name, err, scale)
     out2 = R.render(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), perturb_overwrite=0, cos_anneal_ratio=1.0)
     assert_close(out2["color_fine"], g["color_fine"], BF16_TOL, "bf16 e2e color_fine")
+
+
+@pytest.mark.parametrize("N", [1, 130, 1000, 33000])
+def test_bf16_fused_sdf_forward(bf16_mode, N):
+    """Fused on-chip SDF forward (sdf only, no graph) vs the oracle: <= 2e-2 (north_star BF16 tolerance)."""
+    states = syn.scene_states(seed=4, jitter=0.03)
+    m = build_modules(states, DEV)
+    gen = torch.Generator().manual_seed(N)
+    x = torch.rand(N, 3, generator=gen) * 2 - 1
+    ref = O.sdf_value(states["sdf"], x)
+    with torch.no_grad():
+        got = m["sdf"].sdf(x.to(DEV))
+    err = max_err(got, ref)
+    print("fused bf16 sdf N=%d max err %.3e" % (N, err))
+    assert_close(got, ref, BF16_TOL, "fused sdf forward N=%d" % N)
+    # agreement with the layer-wise tensor-core path (value_feature_normal) at BF16 rounding level
+    sdf2, _, _ = m["sdf"].value_feature_normal(x.to(DEV), want_normal=False)
+    assert_close(got, sdf2, 5e-3, "fused vs layer-wise bf16")
+
+
+def test_bf16_grid_query(bf16_mode, golden_dir):
+    g = {k: v for k, v in np.load(os.path.join(golden_dir, "grid.npz")).items()}
+    states = syn.scene_states(seed=4, jitter=0.03)
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    u = m["renderer"].extract_fields(torch.from_numpy(g["bmin"]), torch.from_numpy(g["bmax"]), 20)
+    assert_close(u, g["u"], BF16_TOL, "bf16 grid vs reference golden")

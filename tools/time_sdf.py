@@ -26,3 +26,19 @@ def run(prec, flags, reps=10):
 for prec, flags, label in (("fp32", 0, "fp32 simt"), ("bf16", 0, "bf16 full"), ("bf16", 1, "no A loads"), ("bf16", 2, "no epilogue"),
                            ("bf16", 4, "no MMA"), ("bf16", 1 + 8, "no A, epi transposes only"), ("bf16", 1 + 16, "no A, epi no stores"), ("bf16", 3, "no A, no epilogue"), ("bf16", 7, "nothing")):
     print("%-20s %8.3f ms per SDF forward of %d points (9 layers)" % (label, run(prec, flags), N))
+
+def run_sdf_only(prec, reps=10):
+    ops.set_precision(prec)
+    for _ in range(3):
+        ops.sdf_forward_nograd(sdf.cfg, w, x, want_feat=False)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        ops.sdf_forward_nograd(sdf.cfg, w, x, want_feat=False)
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+for prec in ("fp32", "bf16"):
+    t = run_sdf_only(prec)
+    print("%-20s %8.3f ms per sdf-only forward of %d points -> %.1f M pts/s, %.1f TFLOP/s" % (
+        prec + " sdf only", t, N, N / t / 1e3, N * 983552 / t / 1e9))
