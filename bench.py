@@ -186,6 +186,8 @@ def run_ours(args):
     lib = L.lib()
     from factored_neus_b200 import ops as _ops
     _ops.set_precision(args.precision)
+    if args.debug_flags:
+        lib.fneus_debug_flags(args.debug_flags)
     # every step (warm-up, capture, replay, eager) runs on one non-default stream so that autograd's
     # AccumulateGrad nodes and the flat gradient bucket live on the capture stream
     work_stream = torch.cuda.Stream()
@@ -341,6 +343,7 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=128, help="rays per step of the CPU reference arm")
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-flags", type=int, default=0, help="library tuning/bisect flags (development only)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the whole-step CUDA graph")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="dense layers: bf16 = tcgen05 tensor cores (FP32 accumulate), fp32 = CUDA-core anchor")

@@ -70,7 +70,12 @@ int fneus_set_precision(int mode) {
 }
 int fneus_get_precision(void) { return fneus::precision_mode(); }
 // debug/bisect switches of the persistent tensor-core kernel (bit0: skip A loads, bit1: skip epilogue, bit2: skip MMA)
-int fneus_debug_flags(int flags) { fneus::tc_debug_flags() = flags; return FNEUS_OK; }
+int fneus_debug_flags(int flags) {
+  fneus::tc_debug_flags() = flags & 0xFF;
+  int w = (flags >> 8) & 0xF;                      // bits 8-11: weight-gradient CTAs per SM (tuning knob), 0 = keep
+  if (w) fneus::tc_wgrad_ctas_per_sm() = w;
+  return FNEUS_OK;
+}
 
 // Raw dense-layer contractions in the current precision mode (test hook for the two GEMM engines).
 // kind 0: C[M,N] = A[M,K] W[N,K]^T + bias ; kind 1: C[M,N] = A[M,K] W[K,N] ; kind 2: C[N,K] += Y[M,N]^T A[M,K],

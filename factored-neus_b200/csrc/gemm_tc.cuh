@@ -1130,6 +1130,7 @@ __global__ void pack_wimg_multi_kernel(PackJobs jobs) {
 
 constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 + 256;
 
+inline int& tc_wgrad_ctas_per_sm() { static int v = 2; return v; }
 inline int tc_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -1182,7 +1183,7 @@ inline void launch_tc_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, 
   int kchunks = cdiv(a.gen.ncols, 256) + cdiv(a.kmem, 256);
   if (kchunks == 0) return;
   int tiles = cdiv(N, 128) * kchunks;
-  int splits = (2 * num_sms + tiles - 1) / tiles;
+  int splits = (tc_wgrad_ctas_per_sm() * num_sms + tiles - 1) / tiles;   // RED traffic grows with the split count
   int max_splits = cdiv(M, 4 * TC_BK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
