@@ -3,5 +3,6 @@ per-ray volume-rendering hot path behind the reference's NeuSRenderer / fields A
 (reference: models/renderer.py, models/fields.py).  CUDA only -- there is no CPU fallback."""
 from . import synthetic  # noqa: F401
 from . import _lib  # noqa: F401
-from .fields import SDFNetwork, RenderingNetwork, SingleVarianceNetwork, RefColor, NeRF  # noqa: F401
+from .fields import (SDFNetwork, RenderingNetwork, SingleVarianceNetwork, RefColor, NeRF, Lvis,  # noqa: F401
+                     IndirectLight)
 from .renderer import NeuSRenderer  # noqa: F401

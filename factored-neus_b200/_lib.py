@@ -33,6 +33,11 @@ class RefCfg(Structure):
     _fields_ = [("d_feature", c_int), ("d_hidden", c_int)]
 
 
+class MlpCfg(Structure):
+    _fields_ = [("n_inputs", c_int), ("in_dim", c_int * 2), ("in_multires", c_int * 2), ("d_hidden", c_int),
+                ("n_layers", c_int), ("d_out", c_int), ("last_act", c_int)]
+
+
 class NerfCfg(Structure):
     _fields_ = [("D", c_int), ("W", c_int), ("d_in", c_int), ("d_in_view", c_int), ("multires", c_int),
                 ("multires_view", c_int), ("skip", c_int)]
@@ -85,6 +90,11 @@ _SIGNATURES = {
     "fneus_ref_scratch_floats": (_LL, [POINTER(RefCfg), _LL]),
     "fneus_ref_fwd": (c_int, [POINTER(RefCfg), _P, _P, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P]),
     "fneus_ref_bwd": (c_int, [POINTER(RefCfg), _P, _P, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fneus_mlp_pack_floats": (_LL, [POINTER(MlpCfg)]),
+    "fneus_mlp_saved_floats": (_LL, [POINTER(MlpCfg), _LL]),
+    "fneus_mlp_scratch_floats": (_LL, [POINTER(MlpCfg), _LL]),
+    "fneus_mlp_fwd": (c_int, [POINTER(MlpCfg), _P, _P, _P, _LL, _P, _P, _P, _P]),
+    "fneus_mlp_bwd": (c_int, [POINTER(MlpCfg), _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P]),
     "fneus_nerf_pack_floats": (_LL, [POINTER(NerfCfg)]),
     "fneus_nerf_saved_floats": (_LL, [POINTER(NerfCfg), _LL]),
     "fneus_nerf_scratch_floats": (_LL, [POINTER(NerfCfg), _LL]),

@@ -9,6 +9,14 @@ int num_sms();
 __global__ void extract_cols_kernel(const float*, int, int, int, float*, int, long long);
 __global__ void sigmoid_bwd_kernel(const float*, const float*, int, float*, int, long long);
 static inline int ew_blocks2(long long n) { return cdiv(n, 256); }
+// a[m][j] = j < n ? in[m][j] : 0   (re-layout of a [M, n] gradient into a padded [M, lda] buffer)
+__global__ void pad_rows_kernel(const float* in, int n, float* a, int lda, long long M) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * lda) return;
+  long long m = idx / lda;
+  int j = (int)(idx - m * lda);
+  a[idx] = j < n ? in[m * n + j] : 0.f;
+}
 
 struct Lin { long long woff, boff; int in, out; };
 
@@ -435,6 +443,105 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_dn_kernel<<<ew_blocks2(M), 256, 0, st>>>(dirs, normals, b.refl, ds_cd, 32, ds_cs, 36, d_normals, M);
   prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Generic positional-encoded ReLU MLP: Lvis (fields.py:338-369: [PE10(pts), PE4(view)] -> 256x4 -> 1, sigmoid) and
+// IndirectLight's trunk (fields.py:372-399: PE10(pts) -> 512x4 -> 144, linear).  No input gradients.
+// ------------------------------------------------------------------------------------------------
+namespace fneus {
+struct MlpPlan { int n_lin; Lin lin[12]; long long pack; int hid; int ldh; bool img; int gen_cols; bool ok; };
+static MlpPlan mlp_plan(const fneus_mlp_cfg* c) {
+  MlpPlan p;
+  p.ok = c && c->n_inputs >= 1 && c->n_inputs <= 2 && c->n_layers >= 1 && c->n_layers <= 10 && c->d_hidden > 0 &&
+         c->d_hidden % 4 == 0 && c->d_out >= 1 && c->d_out <= 1024 && c->d_hidden <= 1024;
+  if (!p.ok) return p;
+  p.gen_cols = 0;
+  for (int i = 0; i < c->n_inputs; i++) {
+    if (c->in_dim[i] < 1 || c->in_dim[i] > 4 || c->in_multires[i] < 0 || c->in_multires[i] > 12) { p.ok = false; return p; }
+    p.gen_cols += pe_dim(c->in_dim[i], c->in_multires[i]);
+  }
+  p.n_lin = c->n_layers + 1;
+  p.hid = c->d_hidden; p.img = precision_mode() == 1; p.ldh = mat_ld(p.hid, p.img);
+  long long off = 0;
+  for (int l = 0; l < p.n_lin; l++) {
+    p.lin[l].in = l == 0 ? p.gen_cols : c->d_hidden;
+    p.lin[l].out = l == p.n_lin - 1 ? c->d_out : c->d_hidden;
+    p.lin[l].woff = off; off += (long long)p.lin[l].in * p.lin[l].out;
+    p.lin[l].boff = off; off += p.lin[l].out;
+  }
+  p.pack = off;
+  return p;
+}
+static ASeg mlp_a0(const fneus_mlp_cfg* c, const float* in0, const float* in1) {
+  GenSpec g = gen_none();
+  gen_add(g, in0, c->in_dim[0], c->in_multires[0]);
+  if (c->n_inputs > 1) gen_add(g, in1, c->in_dim[1], c->in_multires[1]);
+  return aseg_gen(g);
+}
+static long long mlp_scratch_main(const fneus_mlp_cfg* c, const MlpPlan& p, long long n) {
+  return 2LL * hid_floats(n, p.hid, p.img) + n * (round_up(c->d_out, 4) + 4) + 2048;
+}
+}  // namespace fneus
+
+extern "C" {
+
+long long fneus_mlp_pack_floats(const fneus_mlp_cfg* cfg) { MlpPlan p = mlp_plan(cfg); return p.ok ? p.pack : -1; }
+long long fneus_mlp_saved_floats(const fneus_mlp_cfg* cfg, long long n) {
+  MlpPlan p = mlp_plan(cfg);
+  return p.ok ? (long long)cfg->n_layers * hid_floats(n, p.hid, p.img) + 1024 : -1;
+}
+long long fneus_mlp_scratch_floats(const fneus_mlp_cfg* cfg, long long n) {
+  MlpPlan p = mlp_plan(cfg);
+  return p.ok ? mlp_scratch_main(cfg, p, n) + (long long)(relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols) / 4) + 256 : -1;
+}
+
+int fneus_mlp_fwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0, const float* in1, long long M,
+                  float* out, float* saved, float* scratch, void* stream) {
+  MlpPlan p = mlp_plan(cfg);
+  if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
+  if (M == 0) return FNEUS_OK;
+  if (!wpack || !in0 || (cfg->n_inputs > 1 && !in1) || !out || !saved || !scratch) return FNEUS_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* base = align1k(saved);
+  float* Hs[12];
+  const long long hf = hid_floats(M, p.hid, p.img);
+  for (int l = 1; l <= cfg->n_layers; l++) Hs[l] = base + (long long)(l - 1) * hf;
+  zero_if_ragged(p.img, base, (long long)cfg->n_layers * hf, M, st);
+  ImgArena ar = arena_at(scratch + mlp_scratch_main(cfg, p, M), relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
+  relu_chain_fwd(wpack, p.lin, p.n_lin, mlp_a0(cfg, in0, in1), Hs, p.ldh, cfg->last_act == 1 ? EPI_SIGMOID : EPI_LINEAR,
+                 out, cfg->d_out, M, st, ar);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_mlp_bwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0, const float* in1, long long M,
+                  const float* out, const float* d_out, float* saved, float* scratch, float* d_wpack, void* stream) {
+  MlpPlan p = mlp_plan(cfg);
+  if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
+  if (M == 0) return FNEUS_OK;
+  if (!wpack || !in0 || (cfg->n_inputs > 1 && !in1) || !out || !d_out || !saved || !scratch || !d_wpack)
+    return FNEUS_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long hf = hid_floats(M, p.hid, p.img);
+  float* Hs[12];
+  for (int l = 1; l <= cfg->n_layers; l++) Hs[l] = align1k(saved) + (long long)(l - 1) * hf;
+  float* ab0 = align1k(scratch);
+  float* ab1 = ab0 + hf;
+  float* alast = ab1 + hf;
+  const int ldl = round_up(cfg->d_out, 4);
+  zero_if_ragged(p.img, ab0, 2 * hf, M, st);
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  if (cfg->last_act == 1) sigmoid_bwd_kernel<<<ew_blocks2(M * ldl), 256, 0, st>>>(d_out, out, cfg->d_out, alast, ldl, M);
+  else pad_rows_kernel<<<ew_blocks2(M * ldl), 256, 0, st>>>(d_out, cfg->d_out, alast, ldl, M);
+  prof_end(st);
+  ImgArena ar = arena_at(scratch + mlp_scratch_main(cfg, p, M), relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
+  relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, mlp_a0(cfg, in0, in1), Hs, p.ldh, alast, ldl, ab0, ab1, nullptr, 4,
+                 nullptr, 4, 0, M, st, ar);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }

@@ -240,3 +240,46 @@ class RefColor(nn.Module):
     def forward(self, pts, x, dirs, n):
         rgb, spec, diff = ops.RefColorMLP.apply(self.flat_weights(), pts, x, dirs, n, self.cfg)
         return {"rgb": rgb, "specular_rgb": spec, "diffuse_rgb": diff}
+
+
+class Lvis(nn.Module):
+    """models/fields.py:338-369: predicted light visibility, [PE10(pts), PE4(view)] -> 256x4 ReLU -> 1 sigmoid."""
+
+    def __init__(self):
+        super().__init__()
+        self.lvis = nn.Sequential(nn.Linear(90, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 256),
+                                  nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 1), nn.Sigmoid())
+        self.cfg = L.MlpCfg(n_inputs=2, in_dim=(3, 3), in_multires=(10, 4), d_hidden=256, n_layers=4, d_out=1,
+                            last_act=1)
+
+    def flat_weights(self):
+        return _flat_pack([self.lvis[i] for i in (0, 2, 4, 6, 8)])
+
+    def forward(self, pts, view):
+        return ops.PlainMLP.apply(self.flat_weights(), pts, view, self.cfg)
+
+
+class IndirectLight(nn.Module):
+    """models/fields.py:372-413: PE10(pts) -> 512x4 ReLU -> 144 = 24 spherical Gaussians x 6, then the lobe /
+    sharpness / amplitude parametrisation (tiny, torch)."""
+
+    def __init__(self, num_lgt_sgs=24):
+        super().__init__()
+        self.num_lgt_sgs = num_lgt_sgs
+        self.indi = nn.Sequential(nn.Linear(63, 512), nn.ReLU(), nn.Linear(512, 512), nn.ReLU(), nn.Linear(512, 512),
+                                  nn.ReLU(), nn.Linear(512, 512), nn.ReLU(), nn.Linear(512, num_lgt_sgs * 6))
+        self.cfg = L.MlpCfg(n_inputs=1, in_dim=(3, 0), in_multires=(10, 0), d_hidden=512, n_layers=4,
+                            d_out=num_lgt_sgs * 6, last_act=0)
+
+    def flat_weights(self):
+        return _flat_pack([self.indi[i] for i in (0, 2, 4, 6, 8)])
+
+    def forward(self, pts):
+        output = ops.PlainMLP.apply(self.flat_weights(), pts, None, self.cfg).reshape(-1, self.num_lgt_sgs, 6)
+        lobes = torch.sigmoid(output[..., :2])
+        theta, phi = lobes[..., :1] * 2 * np.pi, lobes[..., 1:2] * 2 * np.pi
+        lgt_lobes = torch.cat([torch.cos(theta) * torch.sin(phi), torch.sin(theta) * torch.sin(phi), torch.cos(phi)],
+                              dim=-1)
+        sharp = torch.sigmoid(output[..., 2:3]) * 30 + 0.1
+        amp = torch.relu(output[..., 3:])
+        return torch.cat([lgt_lobes, sharp, amp], dim=-1)

@@ -289,6 +289,39 @@ class RefColorMLP(torch.autograd.Function):
         return dw, None, d_f, None, d_n, None
 
 
+class PlainMLP(torch.autograd.Function):
+    """Positional-encoded ReLU MLP without input gradients (Lvis, IndirectLight trunk): (wflat, in0, in1|None)."""
+
+    @staticmethod
+    def forward(ctx, wflat, in0, in1, cfg):
+        _need_cuda(in0, "input")
+        w, a, b = _f32c(wflat), _f32c(in0), _f32c(in1)
+        N = a.shape[0]
+        lib = L.lib()
+        out = torch.empty(N, cfg.d_out, dtype=torch.float32, device=a.device)
+        saved = _empty(lib.fneus_mlp_saved_floats(cfg, N), a)
+        scratch = _empty(lib.fneus_mlp_scratch_floats(cfg, N), a)
+        L.check(lib.fneus_mlp_fwd(cfg, L.ptr(w), L.ptr(a), L.ptr(b), N, L.ptr(out), L.ptr(saved), L.ptr(scratch),
+                                  L.stream_ptr()), "fneus_mlp_fwd")
+        ctx.cfg = cfg
+        ctx.save_for_backward(w, a, b if b is not None else a, out, saved)
+        ctx.has_b = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        w, a, b, out, saved = ctx.saved_tensors
+        cfg = ctx.cfg
+        N = a.shape[0]
+        lib = L.lib()
+        dw = torch.zeros_like(w)
+        scratch = _empty(lib.fneus_mlp_scratch_floats(cfg, N), a)
+        L.check(lib.fneus_mlp_bwd(cfg, L.ptr(w), L.ptr(a), L.ptr(b) if ctx.has_b else None, N, L.ptr(out),
+                                  L.ptr(_f32c(d_out)), L.ptr(saved), L.ptr(scratch), L.ptr(dw), L.stream_ptr()),
+                "fneus_mlp_bwd")
+        return dw, None, None, None
+
+
 class NerfMLP(torch.autograd.Function):
     """NeRF.forward with view directions (fields.py:233-259) -> (raw density [N,1], raw rgb [N,3])."""
 

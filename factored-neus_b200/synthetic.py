@@ -138,6 +138,26 @@ def refcolor_state(seed=3, d_feature=256, d_hidden=256, dtype=torch.float32):
     return sd
 
 
+def _relu_stack_state(prefix, seed, d_in, d_hidden, d_out, dtype):
+    rs = np.random.RandomState(seed)
+    sd = {}
+    dims = [d_in, d_hidden, d_hidden, d_hidden, d_hidden, d_out]
+    for i in range(5):
+        w, b = _default_linear(rs, dims[i + 1], dims[i])
+        sd["%s.%d.weight" % (prefix, 2 * i)], sd["%s.%d.bias" % (prefix, 2 * i)] = _t(w, dtype), _t(b, dtype)
+    return sd
+
+
+def lvis_state(seed=5, dtype=torch.float32):
+    """Lvis (fields.py:338-369), Lazy first layer materialised: in = 63 + 27."""
+    return _relu_stack_state("lvis", seed, 90, 256, 1, dtype)
+
+
+def indirect_light_state(seed=6, num_lgt_sgs=24, dtype=torch.float32):
+    """IndirectLight (fields.py:372-413), Lazy first layer materialised: in = 63."""
+    return _relu_stack_state("indi", seed, 63, 512, num_lgt_sgs * 6, dtype)
+
+
 def scene_states(seed=4, jitter=0.0, dtype=torch.float32, sdf_conf=SDF_CONF, color_conf=COLOR_CONF,
                  nerf_conf=NERF_CONF):
     """All networks of one synthetic scene: {'sdf','var','color','ref','nerf'} -> state dict."""

@@ -151,6 +151,27 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
                   const float* d_spec, const float* d_diff, float* d_feats, float* d_normals, float* saved,
                   float* scratch, float* d_wpack, void* stream);
 
+/* ---- generic positional-encoded ReLU MLP without input gradients: Lvis (fields.py:338-369) and the trunk of
+ * IndirectLight (fields.py:372-399).  Input = [PE(in0) | PE(in1)] (n_inputs 1 or 2, include_input encodings), n_layers
+ * hidden ReLU layers of d_hidden, output d_out with last_act 0 = linear, 1 = sigmoid. */
+typedef struct {
+  int n_inputs;
+  int in_dim[2];
+  int in_multires[2];
+  int d_hidden;
+  int n_layers;
+  int d_out;
+  int last_act;
+} fneus_mlp_cfg;
+long long fneus_mlp_pack_floats(const fneus_mlp_cfg* cfg);
+long long fneus_mlp_saved_floats(const fneus_mlp_cfg* cfg, long long n_points);
+long long fneus_mlp_scratch_floats(const fneus_mlp_cfg* cfg, long long n_points);
+int fneus_mlp_fwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0, const float* in1,
+                  long long n_points, float* out, float* saved, float* scratch, void* stream);
+int fneus_mlp_bwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0, const float* in1,
+                  long long n_points, const float* out, const float* d_out, float* saved, float* scratch,
+                  float* d_wpack, void* stream);
+
 /* ---- outside NeRF (fields.py:178-259) + render_core_outside (renderer.py:112-149), womask configuration.
  * Pack order: pts_linears.0..D-1, head = [alpha_linear ; feature_linear] (W [1+W, W] then b [1+W]),
  * views_linears.0, rgb_linear.  No input gradients (sample positions carry none, renderer.py:426). */

@@ -617,3 +617,26 @@ def surface_points(P, rays_o, rays_d, near, far, conf=RENDER_CONF_WMASK, sdf_con
     p_s = rays_o + rays_d * z_s
     n_s = sdf_gradient(P["sdf"], p_s, sdf_conf)
     return hit, p_s, n_s
+
+
+# ---------------------------------------------------------------------------
+# stage-2 prediction networks -- fields.py:338-413
+# ---------------------------------------------------------------------------
+def lvis_forward(p: Params, pts, view):
+    h = torch.cat([embed(pts, 10), embed(view, 4)], dim=-1)
+    for i in range(4):
+        h = torch.relu(_lin(p, "lvis.%d" % (2 * i), h, False))
+    return torch.sigmoid(_lin(p, "lvis.8", h, False))
+
+
+def indirect_light_forward(p: Params, pts, num_lgt_sgs=24):
+    h = embed(pts, 10)
+    for i in range(4):
+        h = torch.relu(_lin(p, "indi.%d" % (2 * i), h, False))
+    out = _lin(p, "indi.8", h, False).reshape(-1, num_lgt_sgs, 6)
+    lobes = torch.sigmoid(out[..., :2])
+    theta, phi = lobes[..., :1] * 2 * math.pi, lobes[..., 1:2] * 2 * math.pi
+    axis = torch.cat([torch.cos(theta) * torch.sin(phi), torch.sin(theta) * torch.sin(phi), torch.cos(phi)], dim=-1)
+    sharp = torch.sigmoid(out[..., 2:3]) * 30 + 0.1
+    amp = torch.relu(out[..., 3:])
+    return torch.cat([axis, sharp, amp], dim=-1)

@@ -436,3 +436,36 @@ def test_lvis_render_shapes(states):
     assert out["gt_lvis"].shape == (64, 4) and out["gt_trace_radiance"].shape == (64, 4, 3)
     assert out["sdf_mask"].dtype == torch.bool and int(out["sdf_mask"].sum()) > 32
     assert float(out["gt_lvis"].min()) >= -1e-4 and float(out["gt_lvis"].max()) <= 1.0 + 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [80, 333])
+def test_stage2_networks_fwd_bwd(golden_dir, N):
+    """Lvis / IndirectLight through fneus_mlp_fwd/bwd vs the oracle (and the reference fixture at N=80)."""
+    g = dict(np.load(os.path.join(golden_dir, "stage2_nets.npz")))
+    rs = np.random.RandomState(13 if N == 80 else 14)
+    pts = torch.from_numpy(rs.uniform(-1, 1, (N, 3)).astype(np.float32))
+    view = torch.from_numpy(rs.standard_normal((N, 3)).astype(np.float32))
+    view = view / view.norm(dim=-1, keepdim=True)
+    pv = torch.from_numpy(rs.standard_normal((N, 1)).astype(np.float32))
+    ps = torch.from_numpy(rs.standard_normal((N, 24, 7)).astype(np.float32))
+    lv, il = fn.Lvis(), fn.IndirectLight()
+    lv.load_state_dict(syn.lvis_state()); il.load_state_dict(syn.indirect_light_state())
+    lv, il = lv.to(DEV), il.to(DEV)
+    vis = lv(pts.to(DEV), view.to(DEV))
+    sgs = il(pts.to(DEV))
+    (vis * pv.to(DEV)).sum().backward()
+    (sgs * ps.to(DEV)).sum().backward()
+    Pl = {n: t.clone().requires_grad_(True) for n, t in syn.lvis_state().items()}
+    Pi = {n: t.clone().requires_grad_(True) for n, t in syn.indirect_light_state().items()}
+    vis_o, sgs_o = O.lvis_forward(Pl, pts, view), O.indirect_light_forward(Pi, pts)
+    (vis_o * pv).sum().backward()
+    (sgs_o * ps).sum().backward()
+    assert_close(vis, vis_o, 1e-5, "lvis")
+    assert_close(sgs, sgs_o, 1e-4, "indirect-light SGs")
+    if N == 80:
+        assert_close(vis, g["vis"], 1e-5, "lvis vs reference")
+        assert_close(sgs, g["sgs"], 1e-4, "SGs vs reference")
+    for mod, P, tag in ((lv, Pl, "lvis"), (il, Pi, "indi")):
+        for name, p in mod.named_parameters():
+            assert_close(p.grad, P[name].grad, 1e-4, "grad %s.%s" % (tag, name), rtol=1e-4)

@@ -133,3 +133,38 @@ def test_bf16_grid_query(bf16_mode, golden_dir):
     m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
     u = m["renderer"].extract_fields(torch.from_numpy(g["bmin"]), torch.from_numpy(g["bmax"]), 20)
     assert_close(u, g["u"], BF16_TOL, "bf16 grid vs reference golden")
+
+
+@pytest.mark.gpu
+def test_bf16_stage2_networks(bf16_mode):
+    """Lvis / IndirectLight in BF16 tensor-core mode: values <= 2e-2, weight gradients <= 2e-2 relative (norm-wise)."""
+    N = 1000
+    rs = np.random.RandomState(21)
+    pts = torch.from_numpy(rs.uniform(-1, 1, (N, 3)).astype(np.float32))
+    view = torch.from_numpy(rs.standard_normal((N, 3)).astype(np.float32))
+    view = view / view.norm(dim=-1, keepdim=True)
+    pv = torch.from_numpy(rs.standard_normal((N, 1)).astype(np.float32))
+    lv, il = fn.Lvis(), fn.IndirectLight()
+    lv.load_state_dict(syn.lvis_state()); il.load_state_dict(syn.indirect_light_state())
+    lv, il = lv.to(DEV), il.to(DEV)
+    vis = lv(pts.to(DEV), view.to(DEV))
+    out = ops.PlainMLP.apply(il.flat_weights(), pts.to(DEV), None, il.cfg)
+    (vis * pv.to(DEV)).sum().backward()
+    pw = torch.from_numpy(rs.standard_normal((N, 144)).astype(np.float32))
+    (out * pw.to(DEV)).sum().backward()
+    Pl = {n: t.clone().requires_grad_(True) for n, t in syn.lvis_state().items()}
+    Pi = {n: t.clone().requires_grad_(True) for n, t in syn.indirect_light_state().items()}
+    vis_o = O.lvis_forward(Pl, pts, view)
+    h = O.embed(pts, 10)
+    for i in range(4):
+        h = torch.relu(torch.nn.functional.linear(h, Pi["indi.%d.weight" % (2 * i)], Pi["indi.%d.bias" % (2 * i)]))
+    out_o = torch.nn.functional.linear(h, Pi["indi.8.weight"], Pi["indi.8.bias"])
+    (vis_o * pv).sum().backward()
+    (out_o * pw).sum().backward()
+    assert_close(vis, vis_o, 2e-2, "lvis bf16")
+    assert_close(out, out_o, 2e-2, "indirect-light trunk bf16")
+    for mod, P, tag in ((lv, Pl, "lvis"), (il, Pi, "indi")):
+        for name, p in mod.named_parameters():
+            ref = P[name].grad
+            rel = float((p.grad.cpu() - ref).norm() / ref.norm().clamp_min(1e-6))
+            assert rel <= 2e-2, "bf16 grad %s.%s rel %.3e" % (tag, name, rel)

@@ -123,3 +123,24 @@ def test_lvis_trace_matches_reference(golden_dir, states):
                                          torch.from_numpy(g["r_theta"]), torch.from_numpy(g["rand_z"]))
     _close(lvis, g["gt_lvis"], 2e-5, "gt_lvis")
     _close(rad, g["gt_trace_radiance"], 2e-5, "gt_trace_radiance")
+
+
+def test_stage2_networks_match_reference(golden_dir):
+    """Lvis / IndirectLight (fields.py:338-413): values and weight gradients of the probe loss."""
+    g = _load(golden_dir, "stage2_nets.npz")
+    pts, view = torch.from_numpy(g["pts"]), torch.from_numpy(g["view"])
+    Pl = {n: t.clone().requires_grad_(True) for n, t in syn.lvis_state().items()}
+    Pi = {n: t.clone().requires_grad_(True) for n, t in syn.indirect_light_state().items()}
+    vis = O.lvis_forward(Pl, pts, view)
+    sgs = O.indirect_light_forward(Pi, pts)
+    _close(vis, g["vis"], 1e-6, "lvis")
+    _close(sgs, g["sgs"], 2e-5, "indirect-light SGs")
+    (vis * torch.from_numpy(g["probe_v"])).sum().backward()
+    (sgs * torch.from_numpy(g["probe_s"])).sum().backward()
+    for tag, P in (("lvis", Pl), ("indi", Pi)):
+        for name, t in P.items():
+            ref = g["g.%s.%s" % (tag, name)]
+            got = _digest(t.grad)
+            scale = max(1.0, np.abs(ref[3:]).max())
+            assert np.abs(got[3:] - ref[3:]).max() <= 2e-5 * scale, "grad %s.%s" % (tag, name)
+            assert abs(got[2] - ref[2]) <= 1e-4 * max(1.0, ref[2]), "grad-norm %s.%s" % (tag, name)

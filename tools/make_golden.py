@@ -61,12 +61,39 @@ def grad_digest(named_params, n_probe=48):
     return out
 
 
+def stage2_networks(fields, syn, gdir):
+    """Lvis / IndirectLight (fields.py:338-413): forward values and weight-gradient digests of a probe loss."""
+    np_ = lambda t: t.detach().cpu().numpy()
+    rs = np.random.RandomState(13)
+    pts = torch.from_numpy(rs.uniform(-1, 1, (80, 3)).astype(np.float32))
+    view = torch.from_numpy(rs.standard_normal((80, 3)).astype(np.float32))
+    view = view / view.norm(dim=-1, keepdim=True)
+    probe_v = torch.from_numpy(rs.standard_normal((80, 1)).astype(np.float32))
+    probe_s = torch.from_numpy(rs.standard_normal((80, 24, 7)).astype(np.float32))
+    lv, il = fields.Lvis(), fields.IndirectLight()
+    lv(pts, view); il(pts)                                       # materialise the Lazy layers
+    lv.load_state_dict(syn.lvis_state()); il.load_state_dict(syn.indirect_light_state())
+    vis = lv(pts, view)
+    (vis * probe_v).sum().backward()
+    sgs = il(pts)
+    (sgs * probe_s).sum().backward()
+    save = dict(pts=np_(pts), view=np_(view), probe_v=np_(probe_v), probe_s=np_(probe_s), vis=np_(vis), sgs=np_(sgs))
+    for k, val in grad_digest(lv.named_parameters()).items():
+        save["g.lvis." + k] = val
+    for k, val in grad_digest(il.named_parameters()).items():
+        save["g.indi." + k] = val
+    np.savez_compressed(os.path.join(gdir, "stage2_nets.npz"), **save)
+
+
 def main():
     syn = __import__("factored_neus_b200").synthetic
     fields, renderer, calLvis = import_reference()
     gdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gdir, exist_ok=True)
     np_ = lambda t: t.detach().cpu().numpy()
+    stage2_networks(fields, syn, gdir)
+    if "--only-stage2" in sys.argv:
+        return
 
     # ---------------- networks, per-function (full-size wmask shapes, jittered weights) -------------
     states = syn.scene_states(seed=4, jitter=0.03)
