@@ -452,9 +452,9 @@ __device__ __forceinline__ float wgrad_col_sum(const uint8_t* sA, int n) {
 // warp 5 (their tile bytes ARE the MN-major shared-memory operand); FP32 row-major / generated operands are
 // converted by the four producer warps.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 2)
-tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __restrict__ dW, int ldw, int wout0,
-                     float* __restrict__ db, int M, int N, int m_per_split) {
+__device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy, const ASeg& a, float* __restrict__ dW,
+                                           int ldw, int wout0, float* __restrict__ db, int M, int N, int m_per_split,
+                                           const int bx, const int by) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA[TC_STAGES];
@@ -469,7 +469,7 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __res
 
   const int kc_gen = (a.gen.ncols + 255) / 256, kc_mem = (a.kmem + 255) / 256;
   const int kchunks = kc_gen + kc_mem;
-  const int nt = blockIdx.x / kchunks, kc = blockIdx.x % kchunks;
+  const int nt = bx / kchunks, kc = bx % kchunks;
   const int n0 = nt * 128;
   const int phase = kc < kc_gen ? 0 : 1;
   const int k0 = (phase == 0 ? kc : kc - kc_gen) * 256;
@@ -478,7 +478,7 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __res
   const int kvalid = min(256, kmax - k0);
   const int Nc = (kvalid + 15) & ~15;
   const int nvalid = min(128, N - n0);
-  const long long mbeg = (long long)blockIdx.y * m_per_split;
+  const long long mbeg = (long long)by * m_per_split;
   long long mend = mbeg + m_per_split;
   if (mend > M) mend = M;
   const int KB = mbeg < mend ? (int)((mend - mbeg + TC_BK - 1) / TC_BK) : 0;
@@ -655,6 +655,29 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, ASeg a, float* __res
     tc_fence_after();
     tmem_dealloc(tmem_d, 256);
   }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, const __grid_constant__ ASeg a, float* __restrict__ dW,
+                     int ldw, int wout0, float* __restrict__ db, int M, int N, int m_per_split) {
+  wgrad_body(dY, ldy, a, dW, ldw, wout0, db, M, N, m_per_split, blockIdx.x, blockIdx.y);
+}
+
+// Grouped variant: the weight gradients of all layers of one chain in ONE launch (blockIdx.z = job).  Every job
+// shares M; a job's unused (tile, split) slots of the common grid exit immediately.
+constexpr int WG_MAX_JOBS = 12;
+struct WgradJob {
+  const float* dY; int ldy;
+  ASeg a;
+  float* dW; int ldw, wout0;
+  float* db;
+  int N, m_per_split, tiles, splits;
+};
+struct WgradJobs { int n; int M; WgradJob job[WG_MAX_JOBS]; };
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_wgrad_group_kernel(const __grid_constant__ WgradJobs jobs) {
+  const WgradJob& j = jobs.job[blockIdx.z];
+  if ((int)blockIdx.x >= j.tiles || (int)blockIdx.y >= j.splits) return;
+  wgrad_body(j.dY, j.ldy, j.a, j.dW, j.ldw, j.wout0, j.db, jobs.M, j.N, j.m_per_split, blockIdx.x, blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1147,6 +1170,8 @@ inline int tc_prepare() {
   cudaError_t e1 = cudaFuncSetAttribute(tc_gemm_mk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaError_t e2 = cudaFuncSetAttribute(tc_gemm_mk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaError_t e3 = cudaFuncSetAttribute(tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (e3 == cudaSuccess)
+    e3 = cudaFuncSetAttribute(tc_gemm_wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaError_t e4 = cudaFuncSetAttribute(tc_gemm_mk_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
   cudaError_t e5 = cudaFuncSetAttribute(tc_gemm_mk_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) return 1;
@@ -1194,6 +1219,47 @@ inline void launch_tc_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, 
   tc_gemm_wgrad_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(dY, ldy, a, dW, ldw, wout0, db, (int)M, N, mps);
   prof_end(st);
 }
+
+// Collects the weight-gradient GEMMs of a chain and launches them together (tensor-core mode only).  The split
+// count over M is chosen for the whole group: about `waves` full waves of CTAs in total, so that the RED traffic
+// (one 128 x 256 FP32 tile per CTA) stays small next to the operand traffic.
+inline int& tc_wgrad_group_waves() { static int v = 2; return v; }
+struct WgradGroup {
+  WgradJobs jobs;
+  double flops;
+  int num_sms;
+  void reset(long long M, int sms) { jobs.n = 0; jobs.M = (int)M; flops = 0.0; num_sms = sms; }
+  void add(const float* dY, int ldy, const ASeg& a, float* dW, int ldw, int wout0, float* db, int N, cudaStream_t st) {
+    const long long M = jobs.M;
+    int kchunks = cdiv(a.gen.ncols, 256) + cdiv(a.kmem, 256);
+    if (kchunks == 0 || M <= 0 || N <= 0) return;
+    if (jobs.n == WG_MAX_JOBS) flush(st);
+    WgradJob& j = jobs.job[jobs.n++];
+    j.dY = dY; j.ldy = ldy; j.a = a; j.dW = dW; j.ldw = ldw; j.wout0 = wout0; j.db = db; j.N = N;
+    j.tiles = cdiv(N, 128) * kchunks;
+    flops += 2.0 * (double)M * N * (a.gen.ncols + a.kmem);
+  }
+  void flush(cudaStream_t st) {
+    if (jobs.n == 0) return;
+    const long long M = jobs.M;
+    int total_tiles = 0, max_tiles = 0;
+    for (int i = 0; i < jobs.n; i++) {
+      total_tiles += jobs.job[i].tiles;
+      if (jobs.job[i].tiles > max_tiles) max_tiles = jobs.job[i].tiles;
+    }
+    int splits = (tc_wgrad_group_waves() * tc_wgrad_ctas_per_sm() * num_sms + total_tiles - 1) / total_tiles;
+    const int max_s = cdiv(M, 4 * TC_BK);
+    if (splits > max_s) splits = max_s;
+    if (splits < 1) splits = 1;
+    const int mps = round_up(cdiv(M, splits), TC_BK);
+    splits = cdiv(M, mps);
+    for (int i = 0; i < jobs.n; i++) { jobs.job[i].m_per_split = mps; jobs.job[i].splits = splits; }
+    prof_begin(PC_TC_MLP, flops, 0.0, st);
+    tc_gemm_wgrad_group_kernel<<<dim3(max_tiles, splits, jobs.n), TC_THREADS, TC_SMEM_BYTES, st>>>(jobs);
+    prof_end(st);
+    reset(M, num_sms);
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // precision dispatch: 0 = FP32 SIMT (exactness anchor), 1 = BF16 tcgen05 (FP32 accumulate)

@@ -2,6 +2,8 @@
 // ReLU MLPs whose first-layer input is [generated block | feature block].  FP32 path on the SIMT GEMM engine.
 #include "gemm_tc.cuh"
 #include "prof.cuh"
+#include "chain_fused.cuh"
+#include <string.h>
 
 namespace fneus {
 
@@ -28,7 +30,7 @@ static size_t relu_chain_img_bytes(const Lin* lin, int n_lin, int gen0) {
     b += wimg_bytes(lin[l].out, l == 0 ? gen0 : 0, l == 0 ? lin[l].in - gen0 : lin[l].in) + 1024;
     b += wimg_bytes(lin[l].in, 0, lin[l].out) + 1024;
   }
-  return b + 4096;
+  return b + 8192;
 }
 static inline long long hid_floats(long long M, int hid, bool img) { return mat_floats(M, hid, img) + 256; }
 static inline float* align1k(float* q) {
@@ -46,15 +48,57 @@ static ImgArena arena_at(float* after_floats, size_t cap_bytes) {
   return ar;
 }
 
+// First-operand image ([generated blocks | memory blocks], at most CH_SLOT_BLOCKS of 64 columns) kept for the
+// layer-0 weight gradient, and the per-layer dY images of the fused backward chain.
+static inline long long a0_img_floats(long long M) { return mat_floats(M, CH_SLOT_BLOCKS * 64, true) + 256; }
+
+static bool chain_fusable(const Lin* lin, int n_lin, const ASeg& a0, int hid) {
+  if (precision_mode() != 1 || tc_prepare() != 0 || chain_prepare() != 0) return false;
+  if (tc_debug_flags() & 8) return false;                        // debug: layered execution
+  if (n_lin < 2 || n_lin + 2 > CH_MAXS || a0.gen.deriv) return false;
+  const int kb0 = cdiv(a0.gen.ncols, TC_BK) + cdiv(a0.kmem, TC_BK);
+  if (kb0 < 1 || kb0 > CH_SLOT_BLOCKS || hid > 256) return false;
+  for (int l = 0; l < n_lin; l++) {
+    if (lin[l].out > 256) return false;
+    if (l > 0 && lin[l].in != hid) return false;
+    if (l < n_lin - 1 && lin[l].out != hid) return false;
+  }
+  return true;
+}
+
 static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs, int ldh,
-                           int last_mode, float* out, int ld_out, long long M, cudaStream_t st, ImgArena& ar) {
+                           int last_mode, float* out, int ld_out, long long M, cudaStream_t st, ImgArena& ar,
+                           float* a0_img = nullptr) {
   const uint8_t* img[16];
+  bool all_img = true;
   for (int l = 0; l < n_lin; l++) {
     ASeg a = l == 0 ? a0 : aseg_mem(Hs[l], ldh, lin[l].in);
     img[l] = make_wimg(ar, false, w + lin[l].woff, lin[l].in, 0, lin[l].out, a.wred_gen, a.gen.ncols, a.wred_mem,
                        a.kmem, st);
+    all_img = all_img && img[l] != nullptr;
   }
   ar.flush(st);
+  if (all_img && ldh < 0 && (last_mode == EPI_SIGMOID || last_mode == EPI_LINEAR) &&
+      -ldh == cdiv(lin[0].out, TC_BK) && chain_fusable(lin, n_lin, a0, lin[0].out)) {
+    ChainArgs g;
+    memset(&g, 0, sizeof(g));
+    double flops = 0.0;
+    g.nsteps = n_lin;
+    for (int l = 0; l < n_lin; l++) {
+      ChainStep& S = g.st[l];
+      const bool last = l == n_lin - 1;
+      S.wimg = img[l]; S.bias = w + lin[l].boff;
+      S.img_out = last ? nullptr : Hs[l + 1];
+      S.out = last ? out : nullptr;
+      S.KB = l == 0 ? cdiv(a0.gen.ncols, TC_BK) + cdiv(a0.kmem, TC_BK) : cdiv(lin[l].in, TC_BK);
+      S.N = lin[l].out; S.mode = last ? CH_OUT : CH_RELU; S.bmn = 0;
+      S.ldo = ld_out; S.act = last_mode == EPI_SIGMOID ? 1 : 0; S.accumulate = 0;
+      flops += 2.0 * (double)M * lin[l].in * lin[l].out;
+    }
+    g.gen = a0.gen; g.mem = a0.mem; g.ldm = a0.ldm; g.kmem = a0.kmem; g.a0_img = a0_img; g.M = M;
+    chain_launch(g, flops, st);
+    return;
+  }
   for (int l = 0; l < n_lin; l++) {
     ASeg a = l == 0 ? a0 : aseg_mem(Hs[l], ldh, lin[l].in);
     Epi e = epi_default();
@@ -67,14 +111,92 @@ static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg
 
 // ReLU chain backward. a_last = gradient wrt the last linear's pre-activation ([M, ld_last]).
 // Layer-0 input gradient: generated block -> dsmall ([M, ld_small], may be null), feature block -> d_feats.
+// dybuf: (n_lin - 1) hidden-sized buffers (the layered path ping-pongs between the first two).
+// a0_img: image of the first operand written by the fused forward (null: regenerate it in the layer-0 wgrad).
 static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs,
-                           int ldh, const float* a_last, int ld_last, float* abuf0, float* abuf1, float* dsmall,
+                           int ldh, const float* a_last, int ld_last, float* dybuf, long long dy_stride, float* dsmall,
                            int ld_small, float* d_feats, int ld_feats, int accumulate_feats, long long M,
-                           cudaStream_t st, ImgArena& ar) {
+                           cudaStream_t st, ImgArena& ar, const float* a0_img = nullptr) {
   const int sms = num_sms();
+  const bool fused = ldh < 0 && -ldh == cdiv(lin[0].out, TC_BK) && chain_fusable(lin, n_lin, a0, lin[0].out) &&
+                     lin[n_lin - 1].out <= TC_BK * CH_SLOT_BLOCKS &&
+                     (ld_small & 3) == 0 && (ld_feats & 3) == 0;
+  if (fused) {
+    // ---- weight images: MN-major W_l for l >= 1; layer 0 split into its feature and generated column ranges ----
+    const uint8_t* img[16];
+    bool all_img = true;
+    for (int l = n_lin - 1; l >= 1; l--) {
+      img[l] = make_wimg(ar, true, w + lin[l].woff, lin[l].in, 0, lin[l].in, 0, 0, 0, lin[l].out, st);
+      all_img = all_img && img[l] != nullptr;
+    }
+    const uint8_t* img_feat = nullptr;
+    const uint8_t* img_gen = nullptr;
+    if (d_feats && a0.kmem > 0) {
+      img_feat = make_wimg(ar, true, w + lin[0].woff, lin[0].in, a0.wred_mem, a0.kmem, 0, 0, 0, lin[0].out, st);
+      all_img = all_img && img_feat != nullptr;
+    }
+    if (dsmall && a0.gen.ncols > 0) {
+      img_gen = make_wimg(ar, true, w + lin[0].woff, lin[0].in, a0.wred_gen, a0.gen.ncols, 0, 0, 0, lin[0].out, st);
+      all_img = all_img && img_gen != nullptr;
+    }
+    if (all_img) {
+      ar.flush(st);
+      ChainArgs g;
+      memset(&g, 0, sizeof(g));
+      double flops = 0.0;
+      int ns = 0;
+      for (int l = n_lin - 1; l >= 1; l--) {
+        ChainStep& S = g.st[ns++];
+        S.wimg = img[l]; S.KB = cdiv(lin[l].out, TC_BK); S.N = lin[l].in; S.mode = CH_MASK; S.bmn = 1;
+        S.mask = Hs[l]; S.mask_kbs = -ldh;
+        S.img_out = dybuf + (long long)(l - 1) * dy_stride;          // dz_{l-1} = (dz_l W_l) * [h_l > 0]
+        flops += 2.0 * (double)M * lin[l].in * lin[l].out;
+      }
+      if (img_feat) {
+        ChainStep& S = g.st[ns++];
+        S.wimg = img_feat; S.KB = cdiv(lin[0].out, TC_BK); S.N = a0.kmem; S.mode = CH_OUT; S.bmn = 1;
+        S.out = d_feats; S.ldo = ld_feats; S.accumulate = accumulate_feats;
+        flops += 2.0 * (double)M * a0.kmem * lin[0].out;
+      }
+      if (img_gen) {
+        ChainStep& S = g.st[ns++];
+        S.wimg = img_gen; S.KB = cdiv(lin[0].out, TC_BK); S.N = a0.gen.ncols; S.mode = CH_OUT; S.bmn = 1;
+        S.out = dsmall; S.ldo = ld_small;
+        flops += 2.0 * (double)M * a0.gen.ncols * lin[0].out;
+      }
+      g.nsteps = ns;
+      g.gen = gen_none(); g.mem = a_last; g.ldm = ld_last; g.kmem = lin[n_lin - 1].out; g.M = M;
+      chain_launch(g, flops, st);
+      // ---- all weight gradients in one grouped launch ----
+      WgradGroup wg;
+      wg.reset(M, sms);
+      for (int l = n_lin - 1; l >= 0; l--) {
+        const float* dy = l == n_lin - 1 ? a_last : dybuf + (long long)l * dy_stride;    // dz_l
+        const int ldy = l == n_lin - 1 ? ld_last : ldh;
+        float* dW = dw + lin[l].woff;
+        float* db = dw + lin[l].boff;
+        if (l > 0) wg.add(dy, ldy, aseg_mem(Hs[l], ldh, lin[l].in), dW, lin[l].in, 0, db, lin[l].out, st);
+        else if (a0_img == nullptr) wg.add(dy, ldy, a0, dW, lin[l].in, 0, db, lin[l].out, st);
+        else {
+          const int kbg = cdiv(a0.gen.ncols, TC_BK), kb0 = kbg + cdiv(a0.kmem, TC_BK);
+          bool bias_done = false;
+          if (a0.kmem > 0) {
+            wg.add(dy, ldy, aseg_mem(a0_img + (size_t)kbg * (TC_A_BYTES / 4), -kb0, a0.kmem, a0.wred_mem), dW, lin[l].in, 0,
+                   db, lin[l].out, st);
+            bias_done = true;
+          }
+          if (a0.gen.ncols > 0)
+            wg.add(dy, ldy, aseg_mem(a0_img, -kb0, a0.gen.ncols, a0.wred_gen), dW, lin[l].in, 0, bias_done ? nullptr : db,
+                   lin[l].out, st);
+        }
+      }
+      wg.flush(st);
+      return;
+    }
+  }
   const float* al = a_last;
   int ld_al = ld_last;
-  float* ab[2] = {abuf0, abuf1};
+  float* ab[2] = {dybuf, dybuf + dy_stride};
   const uint8_t* img[16];
   for (int l = n_lin - 1; l >= 0; l--)
     img[l] = (l > 0 || dsmall || d_feats)
@@ -126,7 +248,8 @@ static ColorPlan color_plan(const fneus_color_cfg* c) {
 }
 static long long color_scratch_main(const fneus_color_cfg* c, const ColorPlan& p, long long n) {
   long long per = (long long)c->n_layers * hid_floats(n, p.hid, p.img);
-  long long bwd = 2LL * hid_floats(n, p.hid, p.img) + n * (round_up(p.gen_cols, 4) + 4);
+  long long bwd = (long long)(c->n_layers > 2 ? c->n_layers : 2) * hid_floats(n, p.hid, p.img) +
+                  n * (round_up(p.gen_cols, 4) + 4);
   return (per > bwd ? per : bwd) + 2048;
 }
 static ASeg color_a0(const fneus_color_cfg* c, const ColorPlan& p, const float* pts, const float* nrm,
@@ -162,7 +285,7 @@ static RefPlan ref_plan(const fneus_ref_cfg* c) {
 }
 
 static long long ref_scratch_main(const RefPlan& p, long long n) {
-  return 2LL * hid_floats(n, p.hid, p.img) + (32 + 36 + 8) * n + 2048;
+  return 4LL * hid_floats(n, p.hid, p.img) + (32 + 36 + 8) * n + 2048;
 }
 __device__ __forceinline__ float srgb_f(float c) {
   const float eps = 1.1920928955078125e-07f;
@@ -276,7 +399,7 @@ long long fneus_color_pack_floats(const fneus_color_cfg* cfg) {
 // saved: H_1..H_n ; scratch: 2 abufs + dsmall + a_last
 long long fneus_color_saved_floats(const fneus_color_cfg* cfg, long long n) {
   ColorPlan p = color_plan(cfg);
-  return p.ok ? (long long)cfg->n_layers * hid_floats(n, p.hid, p.img) + 1024 : -1;
+  return p.ok ? (long long)cfg->n_layers * hid_floats(n, p.hid, p.img) + (p.img ? a0_img_floats(n) : 0) + 1024 : -1;
 }
 long long fneus_color_scratch_floats(const fneus_color_cfg* cfg, long long n) {
   ColorPlan p = color_plan(cfg);
@@ -300,7 +423,7 @@ int fneus_color_fwd(const fneus_color_cfg* cfg, const float* wpack, const float*
   ImgArena ar = arena_at(scratch ? scratch + color_scratch_main(cfg, p, M) : nullptr,
                          relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
   relu_chain_fwd(wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh, EPI_SIGMOID,
-                 rgb_out, cfg->d_out, M, st, ar);
+                 rgb_out, cfg->d_out, M, st, ar, (saved && p.img) ? base + (long long)cfg->n_layers * hf : nullptr);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -318,21 +441,23 @@ int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float*
   const long long hf = hid_floats(M, p.hid, p.img);
   for (int l = 1; l <= cfg->n_layers; l++) Hs[l] = align1k(saved) + (long long)(l - 1) * hf;
   const int lds = round_up(p.gen_cols, 4);
+  const int nbuf = cfg->n_layers > 2 ? cfg->n_layers : 2;
   float* ab0 = align1k(scratch);
-  float* ab1 = ab0 + hf;
-  float* dsmall = ab1 + hf;
-  zero_if_ragged(p.img, ab0, 2 * hf, M, st);
+  float* dsmall = ab0 + nbuf * hf;
+  zero_if_ragged(p.img, ab0, nbuf * hf, M, st);
   float* alast = dsmall + M * lds;
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   sigmoid_bwd_kernel<<<ew_blocks2(M * 4), 256, 0, st>>>(d_rgb, rgb, cfg->d_out, alast, 4, M);
   prof_end(st);
   ImgArena ar = arena_at(scratch + color_scratch_main(cfg, p, M), relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
   relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh,
-                 alast, 4, ab0, ab1, d_normals ? dsmall : nullptr, lds, d_feats, cfg->d_feature, 0, M, st, ar);
-  if (d_normals)
+                 alast, 4, ab0, hf, d_normals ? dsmall : nullptr, lds, d_feats, cfg->d_feature, 0, M, st, ar,
+                 p.img ? align1k(saved) + (long long)cfg->n_layers * hf : nullptr);
+  if (d_normals) {
     prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
     extract_cols_kernel<<<ew_blocks2(M * 3), 256, 0, st>>>(dsmall, lds, p.gen_cols - 3, 3, d_normals, 3, M);
     prof_end(st);
+  }
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -344,7 +469,7 @@ long long fneus_ref_pack_floats(const fneus_ref_cfg* cfg) {
 // saved: cd H1..H4, cs G1..G4, yd [M,4], ys [M,4], refl [M,4]
 long long fneus_ref_saved_floats(const fneus_ref_cfg* cfg, long long n) {
   RefPlan p = ref_plan(cfg);
-  return p.ok ? 8LL * hid_floats(n, p.hid, p.img) + 12 * n + 2048 : -1;
+  return p.ok ? 8LL * hid_floats(n, p.hid, p.img) + 12 * n + 2048 + (p.img ? 2 * a0_img_floats(n) + 512 : 0) : -1;
 }
 // scratch: 2 abufs, dsmall_cd [M,32], dsmall_cs [M,36], a_cd [M,4], a_cs [M,4]
 long long fneus_ref_scratch_floats(const fneus_ref_cfg* cfg, long long n) {
@@ -356,13 +481,15 @@ long long fneus_ref_scratch_floats(const fneus_ref_cfg* cfg, long long n) {
 }
 
 namespace {
-struct RefBufs { float* H[5]; float* G[5]; float* yd; float* ys; float* refl; };
+struct RefBufs { float* H[5]; float* G[5]; float* yd; float* ys; float* refl; float* a0_cd; float* a0_cs; };
 RefBufs ref_carve(const RefPlan& p, float* saved, long long M) {
   RefBufs b;
   float* ptr = align1k(saved);
   for (int i = 1; i <= 4; i++) { b.H[i] = ptr; ptr += hid_floats(M, p.hid, p.img); }
   for (int i = 1; i <= 4; i++) { b.G[i] = ptr; ptr += hid_floats(M, p.hid, p.img); }
-  b.yd = ptr; ptr += M * 4; b.ys = ptr; ptr += M * 4; b.refl = ptr;
+  b.yd = ptr; ptr += M * 4; b.ys = ptr; ptr += M * 4; b.refl = ptr; ptr += M * 4;
+  b.a0_cd = b.a0_cs = nullptr;
+  if (p.img) { b.a0_cd = align1k(ptr); b.a0_cs = b.a0_cd + a0_img_floats(M); }
   return b;
 }
 ASeg ref_cd_a0(const fneus_ref_cfg* c, const float* pts, const float* nrm, const float* feats) {
@@ -397,13 +524,14 @@ int fneus_ref_fwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_prep_kernel<<<ew_blocks2(M), 256, 0, st>>>(dirs, normals, b.refl, M);
   prof_end(st);
-  relu_chain_fwd(wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, EPI_SIGMOID, b.yd, 3, M, st, ar);
+  relu_chain_fwd(wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, EPI_SIGMOID, b.yd, 3, M, st, ar,
+                 b.a0_cd);
   // viewdir_mlp: 4 x (Linear+ReLU); then net_cs Linear+Sigmoid
   {
     Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
     // hidden layer outputs G1..G4 are all ReLU'd; the chain helper applies ReLU to all but the last linear.
     relu_chain_fwd(wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, EPI_SIGMOID, b.ys,
-                   1, M, st, ar);
+                   1, M, st, ar, b.a0_cs);
   }
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_final_kernel<<<ew_blocks2(M * 3), 256, 0, st>>>(b.yd, b.ys, rgb_out, spec_out, diff_out, M);
@@ -423,10 +551,10 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
     return FNEUS_ERR_NULL;
   cudaStream_t st = (cudaStream_t)stream;
   RefBufs b = ref_carve(p, saved, M);
+  const long long hf = hid_floats(M, p.hid, p.img);
   float* ab0 = align1k(scratch);
-  float* ab1 = ab0 + hid_floats(M, p.hid, p.img);
-  float* ds_cd = ab1 + hid_floats(M, p.hid, p.img);
-  zero_if_ragged(p.img, ab0, 2 * hid_floats(M, p.hid, p.img), M, st);
+  float* ds_cd = ab0 + 4 * hf;
+  zero_if_ragged(p.img, ab0, 4 * hf, M, st);
   float* ds_cs = ds_cd + M * 32;
   float* a_cd = ds_cs + M * 36;
   float* a_cs = a_cd + M * 4;
@@ -436,10 +564,10 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
   ImgArena ar = arena_at(scratch + ref_scratch_main(p, M),
                          relu_chain_img_bytes(p.cd, 5, 30) + relu_chain_img_bytes(chain, 5, 33));
-  relu_chain_bwd(wpack, d_wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, a_cd, 4, ab0, ab1,
-                 ds_cd, 32, d_feats, cfg->d_feature, 0, M, st, ar);
+  relu_chain_bwd(wpack, d_wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, a_cd, 4, ab0, hf,
+                 ds_cd, 32, d_feats, cfg->d_feature, 0, M, st, ar, b.a0_cd);
   relu_chain_bwd(wpack, d_wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, a_cs, 4, ab0,
-                 ab1, ds_cs, 36, d_feats, cfg->d_feature, 1, M, st, ar);
+                 hf, ds_cs, 36, d_feats, cfg->d_feature, 1, M, st, ar, b.a0_cs);
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_dn_kernel<<<ew_blocks2(M), 256, 0, st>>>(dirs, normals, b.refl, ds_cd, 32, ds_cs, 36, d_normals, M);
   prof_end(st);
@@ -484,7 +612,8 @@ static ASeg mlp_a0(const fneus_mlp_cfg* c, const float* in0, const float* in1) {
   return aseg_gen(g);
 }
 static long long mlp_scratch_main(const fneus_mlp_cfg* c, const MlpPlan& p, long long n) {
-  return 2LL * hid_floats(n, p.hid, p.img) + n * (round_up(c->d_out, 4) + 4) + 2048;
+  return (long long)(c->n_layers > 2 ? c->n_layers : 2) * hid_floats(n, p.hid, p.img) + n * (round_up(c->d_out, 4) + 4) +
+         2048;
 }
 }  // namespace fneus
 
@@ -493,7 +622,7 @@ extern "C" {
 long long fneus_mlp_pack_floats(const fneus_mlp_cfg* cfg) { MlpPlan p = mlp_plan(cfg); return p.ok ? p.pack : -1; }
 long long fneus_mlp_saved_floats(const fneus_mlp_cfg* cfg, long long n) {
   MlpPlan p = mlp_plan(cfg);
-  return p.ok ? (long long)cfg->n_layers * hid_floats(n, p.hid, p.img) + 1024 : -1;
+  return p.ok ? (long long)cfg->n_layers * hid_floats(n, p.hid, p.img) + (p.img ? a0_img_floats(n) : 0) + 1024 : -1;
 }
 long long fneus_mlp_scratch_floats(const fneus_mlp_cfg* cfg, long long n) {
   MlpPlan p = mlp_plan(cfg);
@@ -514,7 +643,7 @@ int fneus_mlp_fwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0
   zero_if_ragged(p.img, base, (long long)cfg->n_layers * hf, M, st);
   ImgArena ar = arena_at(scratch + mlp_scratch_main(cfg, p, M), relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
   relu_chain_fwd(wpack, p.lin, p.n_lin, mlp_a0(cfg, in0, in1), Hs, p.ldh, cfg->last_act == 1 ? EPI_SIGMOID : EPI_LINEAR,
-                 out, cfg->d_out, M, st, ar);
+                 out, cfg->d_out, M, st, ar, p.img ? base + (long long)cfg->n_layers * hf : nullptr);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -530,18 +659,18 @@ int fneus_mlp_bwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0
   const long long hf = hid_floats(M, p.hid, p.img);
   float* Hs[12];
   for (int l = 1; l <= cfg->n_layers; l++) Hs[l] = align1k(saved) + (long long)(l - 1) * hf;
+  const int nbuf = cfg->n_layers > 2 ? cfg->n_layers : 2;
   float* ab0 = align1k(scratch);
-  float* ab1 = ab0 + hf;
-  float* alast = ab1 + hf;
+  float* alast = ab0 + nbuf * hf;
   const int ldl = round_up(cfg->d_out, 4);
-  zero_if_ragged(p.img, ab0, 2 * hf, M, st);
+  zero_if_ragged(p.img, ab0, nbuf * hf, M, st);
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   if (cfg->last_act == 1) sigmoid_bwd_kernel<<<ew_blocks2(M * ldl), 256, 0, st>>>(d_out, out, cfg->d_out, alast, ldl, M);
   else pad_rows_kernel<<<ew_blocks2(M * ldl), 256, 0, st>>>(d_out, cfg->d_out, alast, ldl, M);
   prof_end(st);
   ImgArena ar = arena_at(scratch + mlp_scratch_main(cfg, p, M), relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
-  relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, mlp_a0(cfg, in0, in1), Hs, p.ldh, alast, ldl, ab0, ab1, nullptr, 4,
-                 nullptr, 4, 0, M, st, ar);
+  relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, mlp_a0(cfg, in0, in1), Hs, p.ldh, alast, ldl, ab0, hf, nullptr, 4,
+                 nullptr, 4, 0, M, st, ar, p.img ? align1k(saved) + (long long)cfg->n_layers * hf : nullptr);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }

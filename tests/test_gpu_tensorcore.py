@@ -171,3 +171,56 @@ def test_bf16_stage2_networks(bf16_mode):
             err = max_err(p.grad, ref)
             print("bf16 grad %s.%s: max err %.3e, scale %.3e, norm-rel %.3e" % (tag, name, err, scale, rel))
             assert err <= BF16_TOL * scale, "bf16 grad %s.%s err %.3e (scale %.3e)" % (tag, name, err, scale)
+
+
+def _color_ref_run(m, x, nrm, v, feat, probe):
+    """colour + RefColor forward/backward on given inputs; returns outputs and all gradients (CPU)."""
+    for net in ("color", "ref"):
+        for p in m[net].parameters():
+            p.grad = None
+    n_ = nrm.clone().requires_grad_(True)
+    f_ = feat.clone().requires_grad_(True)
+    rgb = m["color"](x, n_, v, f_)
+    rd = m["ref"](x, f_, v, n_)
+    loss = (rgb * probe).sum() + (rd["rgb"] * probe).sum() + 0.5 * (rd["specular_rgb"] * probe).sum() \
+        + 0.25 * (rd["diffuse_rgb"] * probe).sum()
+    loss.backward()
+    res = {"rgb": rgb, "ref_rgb": rd["rgb"], "spec": rd["specular_rgb"], "diff": rd["diffuse_rgb"],
+           "d_normals": n_.grad, "d_feats": f_.grad}
+    for net in ("color", "ref"):
+        for name, p in m[net].named_parameters():
+            res["g.%s.%s" % (net, name)] = p.grad.clone()
+    return {k: t.detach().float().cpu() for k, t in res.items()}
+
+
+@pytest.mark.parametrize("N", [300, 1000, 5000])
+def test_bf16_fused_chains_match_layered(bf16_mode, N):
+    """Fused on-chip ReLU chains (forward, backward-data, grouped weight gradients) vs the layer-by-layer tensor-core
+    path on the same BF16 images: same arithmetic up to accumulation order, so agreement is far tighter than the
+    2e-2 BF16 gate.  Tile counts: 3 (odd: half-empty pair), 8 with a ragged last tile, 40."""
+    states = syn.scene_states(seed=4, jitter=0.03)
+    m = build_modules(states, DEV)
+    rs = np.random.RandomState(N)
+    x = torch.from_numpy(rs.uniform(-1, 1, (N, 3)).astype(np.float32)).to(DEV)
+    v = torch.from_numpy(rs.standard_normal((N, 3)).astype(np.float32))
+    v = (v / v.norm(dim=-1, keepdim=True)).to(DEV)
+    nrm = torch.from_numpy(rs.standard_normal((N, 3)).astype(np.float32)).to(DEV)
+    feat = torch.from_numpy((0.3 * rs.standard_normal((N, 256))).astype(np.float32)).to(DEV)
+    probe = torch.from_numpy(rs.uniform(0.5, 1.5, (N, 3)).astype(np.float32)).to(DEV)
+    lib = fn._lib.lib()
+    try:
+        lib.fneus_debug_flags(8)                     # layered execution
+        ref = _color_ref_run(m, x, nrm, v, feat, probe)
+    finally:
+        lib.fneus_debug_flags(0)
+    got = _color_ref_run(m, x, nrm, v, feat, probe)
+    for k in ref:
+        scale = max(1e-3, float(ref[k].abs().max()))
+        err = max_err(got[k], ref[k])
+        assert err <= 4e-3 * scale, "fused vs layered %s: err %.3e (scale %.3e)" % (k, err, scale)
+    # and against the FP32 oracle at the BF16 gate
+    P = grad_params(states)
+    n_ = nrm.cpu().clone().requires_grad_(True)
+    f_ = feat.cpu().clone().requires_grad_(True)
+    rgb_o = O.color_forward(P["color"], x.cpu(), n_, v.cpu(), f_)
+    assert_close(got["rgb"], rgb_o, BF16_TOL, "fused colour vs oracle")
