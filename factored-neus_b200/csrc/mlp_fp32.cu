@@ -3,7 +3,9 @@
 // Every dense layer is one launch of the SIMT GEMM engine (gemm_simt.cuh) with a fused epilogue;
 // positional encodings are generated in the GEMM tile loaders.
 #include "gemm_tc.cuh"
+#include <string.h>
 #include "sdf_fused.cuh"
+#include "sdf_chain.cuh"
 #include "prof.cuh"
 
 namespace fneus {
@@ -241,12 +243,15 @@ static long long sdf_saved_floats(const SdfPlan& p, long long M) {
   long long s = 0;
   for (int l = 1; l <= p.L; l++) s += mat_floats(M, p.in[l], p.img);
   for (int l = 0; l < p.L; l++) s += mat_floats(M, p.out[l], p.img);
+  if (p.img) s += mat_floats(M, TC_BK, true) + 256;      // image of PE(x) for the layer-0 weight gradient
   return s + 1024;
 }
 static long long sdf_buf_floats(const SdfPlan& p, long long M) { return mat_floats(M, p.wmax, p.img) + 256; }
-// 4 ping-pong activation buffers + two [M, e] FP32 side buffers; the weight-image arena follows
+// activation buffers (4 ping-pong ones layer by layer; gbar_0..L, e_0..L-1, abar_0..L-1 for the fused backward) + two
+// [M, e] FP32 side buffers; the weight-image arena follows
+static int sdf_nbuf(const SdfPlan& p) { return p.img && 3 * p.L + 1 > 4 ? 3 * p.L + 1 : 4; }
 static long long sdf_scratch_main(const SdfPlan& p, long long M) {
-  return 4LL * sdf_buf_floats(p, M) + 2LL * M * round_up(p.e, 4) + 256;
+  return (long long)sdf_nbuf(p) * sdf_buf_floats(p, M) + 2LL * M * round_up(p.e, 4) + 256;
 }
 static long long sdf_scratch_floats(const SdfPlan& p, long long n) {
   return sdf_scratch_main(p, n) + (long long)(sdf_img_bytes(p) / 4) + 256;
@@ -267,7 +272,7 @@ static SdfBufs sdf_carve(const SdfPlan& p, float* saved, long long M) {
   ptr = align(ptr);
   for (int l = 1; l <= p.L; l++) { b.H[l] = ptr; ptr += mat_floats(M, p.in[l], p.img); }
   for (int l = 0; l < p.L; l++) { b.Q[l] = ptr; ptr += mat_floats(M, p.out[l], p.img); }
-  b.H[0] = nullptr;
+  b.H[0] = p.img ? align(ptr) : nullptr;                  // PE(x) image (fused forward only)
   return b;
 }
 
@@ -328,6 +333,23 @@ static int sdf_fused_launch(const fneus_sdf_cfg* c, const SdfPlan& p, const floa
   sdf_fused_fwd_kernel<<<grid, FZ_THREADS, FZ_SMEM_BYTES, st>>>(g);
   prof_end(st);
   return FNEUS_OK;
+}
+
+// Fused-chain eligibility (sdf_chain.cuh): 256-wide hidden layers, one 64-column PE block, a feature block as wide
+// as the last hidden layer (FEATQ rewrites the operand column for column).
+static bool sdf_chain_ok(const fneus_sdf_cfg* c, const SdfPlan& p) {
+  if (!p.img || precision_mode() != 1 || tc_prepare() != 0 || sdf_chain_prepare() != 0) return false;
+  if (tc_debug_flags() & 16) return false;                       // debug: layered execution
+  if (!sdf_fused_ok(p) || 2 * p.L + 1 > SC_MAXS || p.L + 1 > SC_BIAS_SLOTS) return false;
+  if (c->d_out - 1 != p.in[p.L] || p.in[p.L] > 256 || (c->d_out - 1) % 4 != 0) return false;
+  return true;
+}
+static SdfStep sdf_step(int mode, const uint8_t* wimg, int KB, int N, int bmn) {
+  SdfStep S;
+  memset(&S, 0, sizeof(S));
+  S.mode = mode; S.wimg = wimg; S.KB = KB; S.N = N; S.bmn = bmn; S.src = SRC_CHAIN;
+  S.csplit = N; S.bias_slot = -1; S.hscale = 1.f; S.oscale = 1.f; S.ldo = 4;
+  return S;
 }
 
 // value chain. If bufs != nullptr activations go to bufs->H (saved) else ping-pong in scratch.
@@ -493,7 +515,6 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
   cudaStream_t st = (cudaStream_t)stream;
   const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
   SdfBufs b = sdf_carve(p, saved, M);
-  sdf_zero_images(p, saved, sdf_saved_floats(p, M), M, st);
   ImgArena ar = arena_make(nullptr, 0);
   if (p.img) {
     ar.base = reinterpret_cast<uint8_t*>(
@@ -501,12 +522,68 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
     ar.cap = sdf_img_bytes(p) - 1024;
   }
   SdfImgs im = sdf_make_images(cfg, p, wpack, true, true, normal_out != nullptr, false, ar, st);
+  if (sdf_chain_ok(cfg, p) && im.F[p.L] != nullptr && (!normal_out || im.B[0] != nullptr)) {
+    const int L = p.L, e4 = round_up(p.e, 4);
+    const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
+    float* g0e = scratch + (long long)sdf_nbuf(p) * sdf_buf_floats(p, M);
+    float* g0 = g0e + M * e4;
+    SdfChainArgs g;
+    memset(&g, 0, sizeof(g));
+    double flops = 0.0;
+    int ns = 0;
+    for (int l = 0; l < L; l++) {
+      SdfStep S = sdf_step(SC_SOFTPLUS, im.F[l], l == 0 ? 1 : cdiv(p.in[l], TC_BK), p.out[l], 0);
+      S.bias = wpack + p.boff[l]; S.bias_slot = l;
+      S.img_out = b.H[l + 1];
+      S.src = l == 0 ? SRC_PE : SRC_CHAIN;
+      if (l + 1 == p.skip) { S.oscale = rsqrt2; S.append = 1; }
+      if (l == L - 1) { S.dot = 1; S.e_out = b.Q[L - 1]; }
+      g.st[ns++] = S;
+      flops += 2.0 * (double)M * p.in[l] * p.out[l];
+    }
+    {
+      SdfStep S = sdf_step(SC_FEATQ, im.F[L], cdiv(p.in[L], TC_BK), cfg->d_out - 1, 0);
+      S.bias = wpack + p.boff[L] + 1; S.bias_slot = L;
+      S.out = feat_out; S.ldo = cfg->d_out - 1;
+      S.q = b.Q[L - 1];
+      g.st[ns++] = S;
+      flops += 2.0 * (double)M * p.in[L] * p.out[L];
+    }
+    if (normal_out) {
+      for (int l = L - 1; l >= 1; l--) {
+        SdfStep S = sdf_step(SC_SPMUL, im.B[l], cdiv(p.out[l], TC_BK), p.in[l], 1);
+        S.h = b.H[l]; S.img_out = b.Q[l - 1];
+        if (l == p.skip) { S.hscale = sqrt2; S.oscale = rsqrt2; S.csplit = p.out[l - 1]; S.out = g0e; S.ldo = e4; }
+        g.st[ns++] = S;
+        flops += 2.0 * (double)M * p.in[l] * p.out[l];
+      }
+      SdfStep S = sdf_step(SC_G0, im.B[0], cdiv(p.out[0], TC_BK), p.in[0], 1);
+      S.out = g0; S.ldo = e4; S.q = p.skip > 0 ? g0e : nullptr;
+      g.st[ns++] = S;
+      flops += 2.0 * (double)M * p.in[0] * p.out[0];
+    }
+    g.nsteps = ns;
+    g.gen = sdf_gen(cfg, x, nullptr); g.gen_t = g.gen;
+    g.pe_img = b.H[0];
+    g.rvec = wpack + p.woff[L]; g.b_last = wpack + p.boff[L];
+    g.sdf_out = sdf_out; g.sdf_scale = 1.f / cfg->scale;
+    g.beta = cfg->beta; g.M = M;
+    sdf_chain_launch(g, flops, st);
+    if (normal_out) {
+      prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+      normal_from_g0_kernel<<<ew_blocks(M), 256, 0, st>>>(x, cfg->d_in, cfg->multires, cfg->scale, g0, e4, normal_out, M);
+      prof_end(st);
+    }
+    FNEUS_CHECK_LAUNCH();
+    return FNEUS_OK;
+  }
+  sdf_zero_images(p, saved, sdf_saved_floats(p, M), M, st);
   int rc = sdf_value_chain(cfg, p, wpack, x, M, sdf_out, feat_out, &b, scratch, st, 1.f, im);
   if (rc) return rc;
   if (!normal_out) return FNEUS_OK;   // value-only graph (SDFNetwork.forward under autograd)
   // reverse chain for the normal: g_l = q_l W_l, q_{l-1} = s_{l-1} * g_l
   const int e4 = round_up(p.e, 4);
-  float* g0e = scratch + 4LL * sdf_buf_floats(p, M);
+  float* g0e = scratch + (long long)sdf_nbuf(p) * sdf_buf_floats(p, M);
   float* g0 = g0e + M * e4;
   for (int l = p.L - 1; l >= 1; l--) {
     ASeg a = aseg_mem(b.Q[l], p.ldout[l], p.out[l]);
@@ -564,6 +641,63 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   }
 
   SdfImgs im = sdf_make_images(cfg, p, wpack, d_normal != nullptr, false, true, d_feat != nullptr, ar, st);
+  if (d_normal && d_feat && b.H[0] != nullptr && sdf_chain_ok(cfg, p) && im.F[0] != nullptr && im.B[L] != nullptr) {
+    float* G[20]; float* E[20]; float* A[20];
+    for (int l = 0; l <= L; l++) G[l] = scratch + (long long)l * bf;
+    for (int l = 0; l < L; l++) { E[l] = scratch + (long long)(L + 1 + l) * bf; A[l] = scratch + (long long)(2 * L + 1 + l) * bf; }
+    SdfChainArgs g;
+    memset(&g, 0, sizeof(g));
+    double flops = 0.0;
+    int ns = 0;
+    for (int l = 0; l < L; l++) {
+      SdfStep S = sdf_step(SC_SWEEP, im.F[l], l == 0 ? 1 : cdiv(p.in[l], TC_BK), p.out[l], 0);
+      S.src = l == 0 ? SRC_TAN : SRC_CHAIN;
+      S.h = b.H[l + 1]; S.q = b.Q[l]; S.e_out = E[l]; S.img_out = G[l + 1];
+      if (l + 1 == p.skip) { S.hscale = sqrt2; S.oscale = rsqrt2; S.append = 1; }
+      g.st[ns++] = S;
+      flops += 2.0 * (double)M * p.in[l] * p.out[l];
+    }
+    {
+      SdfStep S = sdf_step(SC_SDFBWD, im.B[L], cdiv(cfg->d_out - 1, TC_BK), p.in[L], 1);
+      S.src = SRC_MEM;
+      S.h = b.H[L]; S.q = E[L - 1]; S.img_out = A[L - 1];
+      S.use_rs = d_sdf != nullptr ? 1 : 0;
+      g.st[ns++] = S;
+      flops += 2.0 * (double)M * p.in[L] * (cfg->d_out - 1);
+    }
+    for (int l = L - 1; l >= 1; l--) {
+      SdfStep S = sdf_step(SC_SDFBWD, im.B[l], cdiv(p.out[l], TC_BK), p.in[l], 1);
+      S.h = b.H[l]; S.q = E[l - 1]; S.img_out = A[l - 1];
+      if (l == p.skip) { S.hscale = sqrt2; S.oscale = rsqrt2; S.csplit = p.out[l - 1]; }
+      g.st[ns++] = S;
+      flops += 2.0 * (double)M * p.in[l] * p.out[l];
+    }
+    g.nsteps = ns;
+    g.gen = sdf_gen(cfg, x, nullptr); g.gen_t = sdf_gen(cfg, x, d_normal);
+    g.pe_img = G[0];
+    g.mem = d_feat; g.ldm = cfg->d_out - 1; g.kmem = cfg->d_out - 1;
+    g.rvec = wpack + p.woff[L]; g.b_last = wpack + p.boff[L];
+    g.rs = d_sdf; g.rscale = 1.f / cfg->scale;
+    g.beta = cfg->beta; g.M = M;
+    sdf_chain_launch(g, flops, st);
+    // weight gradients: dW_l += q_l^T gbar_l + abar_l^T h_l, db_l += colsum abar_l ; last linear: features and row 0
+    WgradGroup wg;
+    wg.reset(M, sms);
+    for (int l = 0; l < L; l++)
+      wg.add(b.Q[l], p.ldout[l], aseg_mem(G[l], l == 0 ? -1 : p.ldin[l], p.in[l]), d_wpack + p.woff[l], p.in[l], 0, nullptr,
+             p.out[l], st);
+    for (int l = L - 1; l >= 0; l--)
+      wg.add(A[l], p.ldout[l], aseg_mem(l == 0 ? b.H[0] : b.H[l], l == 0 ? -1 : p.ldin[l], p.in[l]), d_wpack + p.woff[l],
+             p.in[l], 0, d_wpack + p.boff[l], p.out[l], st);
+    wg.add(d_feat, cfg->d_out - 1, aseg_mem(b.H[L], p.ldin[L], p.in[L]), d_wpack + p.woff[L], p.in[L], 1,
+           d_wpack + p.boff[L], cfg->d_out - 1, st);
+    wg.flush(st);
+    launch_colsum(G[L], p.ldin[L], p.in[L], nullptr, 1.f, d_wpack + p.woff[L], nullptr, M, st);
+    if (d_sdf)
+      launch_colsum(b.H[L], p.ldin[L], p.in[L], d_sdf, 1.f / cfg->scale, d_wpack + p.woff[L], d_wpack + p.boff[L], M, st);
+    FNEUS_CHECK_LAUNCH();
+    return FNEUS_OK;
+  }
   if (d_normal) {
     // double-backward sweep: gbar_0 = T0 nbar ; qbar_l = gbar_l W_l^T ; dW_l += q_l^T gbar_l ;
     // gbar_{l+1} = s_l qbar_l ; e_l = beta (1-s_l) q_l qbar_l (written over q_l)

@@ -224,3 +224,60 @@ def test_bf16_fused_chains_match_layered(bf16_mode, N):
     f_ = feat.cpu().clone().requires_grad_(True)
     rgb_o = O.color_forward(P["color"], x.cpu(), n_, v.cpu(), f_)
     assert_close(got["rgb"], rgb_o, BF16_TOL, "fused colour vs oracle")
+
+
+def _sdf_run(m, x, p_sdf, p_feat, p_nrm):
+    for p in m["sdf"].parameters():
+        p.grad = None
+    sdf, feat, nrm = m["sdf"].value_feature_normal(x, want_normal=True)
+    ((sdf * p_sdf).sum() + (feat * p_feat).sum() + (nrm * p_nrm).sum()).backward()
+    res = {"sdf": sdf, "feat": feat, "normal": nrm}
+    for name, p in m["sdf"].named_parameters():
+        res["g." + name] = p.grad.clone()
+    return {k: t.detach().float().cpu() for k, t in res.items()}
+
+
+@pytest.mark.parametrize("N", [300, 1000, 5000])
+def test_bf16_fused_sdf_chains_match_layered(bf16_mode, N):
+    """Fused SDF forward (value + analytic gradient) and backward (double-backward sweep + value path, grouped weight
+    gradients) vs the layer-by-layer tensor-core path, and vs the FP32 oracle at the BF16 gate."""
+    states = syn.scene_states(seed=4, jitter=0.03)
+    m = build_modules(states, DEV)
+    rs = np.random.RandomState(N + 1)
+    x = torch.from_numpy(rs.uniform(-1, 1, (N, 3)).astype(np.float32)).to(DEV)
+    p_sdf = torch.from_numpy(rs.uniform(0.5, 1.5, (N, 1)).astype(np.float32)).to(DEV)
+    p_feat = torch.from_numpy(rs.uniform(-1, 1, (N, 256)).astype(np.float32)).to(DEV) * 0.05
+    p_nrm = torch.from_numpy(rs.uniform(0.5, 1.5, (N, 3)).astype(np.float32)).to(DEV)
+    lib = fn._lib.lib()
+    try:
+        lib.fneus_debug_flags(16)                    # layered execution of the SDF chains
+        ref = _sdf_run(m, x, p_sdf, p_feat, p_nrm)
+    finally:
+        lib.fneus_debug_flags(0)
+    got = _sdf_run(m, x, p_sdf, p_feat, p_nrm)
+    bad = []
+    for k in ref:
+        scale = max(1e-3, float(ref[k].abs().max()))
+        err = max_err(got[k], ref[k])
+        print("fused vs layered %s: err %.3e (scale %.3e)" % (k, err, scale))
+        if err > 1.5e-2 * scale:
+            bad.append(k)
+    P = grad_params(states)["sdf"]
+    xo = x.cpu()
+    out_o = O.sdf_forward(P, xo)
+    nrm_o = O.sdf_gradient(P, xo)
+    assert_close(got["sdf"], out_o[:, :1].detach(), BF16_TOL, "fused sdf vs oracle")
+    assert_close(got["feat"], out_o[:, 1:].detach(), BF16_TOL, "fused feature vs oracle")
+    assert_close(got["normal"], nrm_o.detach(), BF16_TOL, "fused normal vs oracle")
+    print("normal vs oracle: fused %.3e layered %.3e" % (max_err(got["normal"], nrm_o.detach()),
+                                                         max_err(ref["normal"], nrm_o.detach())))
+    ((out_o[:, :1] * p_sdf.cpu()).sum() + (out_o[:, 1:] * p_feat.cpu()).sum() + (nrm_o * p_nrm.cpu()).sum()).backward()
+    for name, t in P.items():
+        refg = t.grad
+        scale = max(1e-3, float(refg.abs().max()))
+        err = max_err(got["g." + name], refg)
+        err_l = max_err(ref["g." + name], refg)
+        print("vs oracle %s: fused %.3e layered %.3e (scale %.3e)" % (name, err, err_l, scale))
+        if err > BF16_TOL * max(1.0, scale):
+            bad.append("oracle:" + name)
+    assert not bad, "fused SDF chain mismatches: %s" % bad
