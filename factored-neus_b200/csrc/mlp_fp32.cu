@@ -342,6 +342,8 @@ static bool sdf_chain_ok(const fneus_sdf_cfg* c, const SdfPlan& p) {
   if (tc_debug_flags() & 16) return false;                       // debug: layered execution
   if (!sdf_fused_ok(p) || 2 * p.L + 1 > SC_MAXS || p.L + 1 > SC_BIAS_SLOTS) return false;
   if (c->d_out - 1 != p.in[p.L] || p.in[p.L] > 256 || (c->d_out - 1) % 4 != 0) return false;
+  for (int l = 0; l < p.L; l++)                                  // every activation image is 4 blocks wide
+    if (cdiv(p.out[l], TC_BK) != 4 || cdiv(p.in[l + 1], TC_BK) != 4) return false;
   return true;
 }
 static SdfStep sdf_step(int mode, const uint8_t* wimg, int KB, int N, int bmn) {
@@ -523,10 +525,8 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
   }
   SdfImgs im = sdf_make_images(cfg, p, wpack, true, true, normal_out != nullptr, false, ar, st);
   if (sdf_chain_ok(cfg, p) && im.F[p.L] != nullptr && (!normal_out || im.B[0] != nullptr)) {
-    const int L = p.L, e4 = round_up(p.e, 4);
+    const int L = p.L;
     const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
-    float* g0e = scratch + (long long)sdf_nbuf(p) * sdf_buf_floats(p, M);
-    float* g0 = g0e + M * e4;
     SdfChainArgs g;
     memset(&g, 0, sizeof(g));
     double flops = 0.0;
@@ -537,7 +537,7 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
       S.img_out = b.H[l + 1];
       S.src = l == 0 ? SRC_PE : SRC_CHAIN;
       if (l + 1 == p.skip) { S.oscale = rsqrt2; S.append = 1; }
-      if (l == L - 1) { S.dot = 1; S.e_out = b.Q[L - 1]; }
+      if (l == L - 1) S.dot = 1;
       g.st[ns++] = S;
       flops += 2.0 * (double)M * p.in[l] * p.out[l];
     }
@@ -545,7 +545,8 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
       SdfStep S = sdf_step(SC_FEATQ, im.F[L], cdiv(p.in[L], TC_BK), cfg->d_out - 1, 0);
       S.bias = wpack + p.boff[L] + 1; S.bias_slot = L;
       S.out = feat_out; S.ldo = cfg->d_out - 1;
-      S.q = b.Q[L - 1];
+      S.img_out = b.Q[L - 1];
+      S.sync_stores = normal_out ? 1 : 0;             // the reverse chain reads the h images back
       g.st[ns++] = S;
       flops += 2.0 * (double)M * p.in[L] * p.out[L];
     }
@@ -553,12 +554,14 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
       for (int l = L - 1; l >= 1; l--) {
         SdfStep S = sdf_step(SC_SPMUL, im.B[l], cdiv(p.out[l], TC_BK), p.in[l], 1);
         S.h = b.H[l]; S.img_out = b.Q[l - 1];
-        if (l == p.skip) { S.hscale = sqrt2; S.oscale = rsqrt2; S.csplit = p.out[l - 1]; S.out = g0e; S.ldo = e4; }
+        S.wait_sync = l == L - 1 ? 1 : 0;
+        if (l == p.skip) { S.hscale = sqrt2; S.oscale = rsqrt2; S.csplit = p.out[l - 1]; }
         g.st[ns++] = S;
         flops += 2.0 * (double)M * p.in[l] * p.out[l];
       }
       SdfStep S = sdf_step(SC_G0, im.B[0], cdiv(p.out[0], TC_BK), p.in[0], 1);
-      S.out = g0; S.ldo = e4; S.q = p.skip > 0 ? g0e : nullptr;
+      S.out = normal_out;
+      S.csplit = p.skip > 0 ? p.out[p.skip - 1] : 0;   // where the parked skip part starts
       g.st[ns++] = S;
       flops += 2.0 * (double)M * p.in[0] * p.out[0];
     }
@@ -569,11 +572,6 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
     g.sdf_out = sdf_out; g.sdf_scale = 1.f / cfg->scale;
     g.beta = cfg->beta; g.M = M;
     sdf_chain_launch(g, flops, st);
-    if (normal_out) {
-      prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
-      normal_from_g0_kernel<<<ew_blocks(M), 256, 0, st>>>(x, cfg->d_in, cfg->multires, cfg->scale, g0, e4, normal_out, M);
-      prof_end(st);
-    }
     FNEUS_CHECK_LAUNCH();
     return FNEUS_OK;
   }
@@ -654,12 +652,13 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
       S.src = l == 0 ? SRC_TAN : SRC_CHAIN;
       S.h = b.H[l + 1]; S.q = b.Q[l]; S.e_out = E[l]; S.img_out = G[l + 1];
       if (l + 1 == p.skip) { S.hscale = sqrt2; S.oscale = rsqrt2; S.append = 1; }
+      if (l == L - 1) S.sync_stores = 1;               // the value-path backward reads the e images back
       g.st[ns++] = S;
       flops += 2.0 * (double)M * p.in[l] * p.out[l];
     }
     {
       SdfStep S = sdf_step(SC_SDFBWD, im.B[L], cdiv(cfg->d_out - 1, TC_BK), p.in[L], 1);
-      S.src = SRC_MEM;
+      S.src = SRC_MEM; S.wait_sync = 1;
       S.h = b.H[L]; S.q = E[L - 1]; S.img_out = A[L - 1];
       S.use_rs = d_sdf != nullptr ? 1 : 0;
       g.st[ns++] = S;

@@ -1,27 +1,32 @@
-// Fused SDF chains (BF16 tensor-core mode): the three layer sequences of the SDF network that a training step runs
-// on the render_core points, each as ONE persistent kernel over pairs of 128-point tiles, operand on chip between
-// layers (shared memory BF16 <-> TMEM FP32), weights streamed as pre-packed images:
+// Fused SDF chains (BF16 tensor-core mode): the layer sequences of the SDF network that a training step runs on the
+// render_core points, each as ONE persistent kernel, one 128-point tile at a time per CTA, the running operand on
+// chip between layers (shared memory BF16 <-> TMEM FP32), weights streamed as pre-packed images:
 //
 //   forward  : value chain h_{l+1} = softplus(W_l h_l + b_l) (fields.py:74-95), sdf = h_L . W_L[0] and the feature
-//              GEMM, then the reverse chain of the analytic gradient q_{l-1} = s_l * (q_l W_l) down to g_0
-//              (fields.py:101-111 as reverse-mode) -- 2L+1 GEMM steps
+//              GEMM, then the reverse chain of the analytic gradient q_{l-1} = s_l * (q_l W_l) down to g_0 and the
+//              normal (fields.py:101-111 as reverse-mode) -- 2L+1 GEMM steps
 //   backward : the double-backward sweep gbar_{l+1} = s_l * (gbar_l W_l^T), e_l = beta (1 - s_l) q_l (gbar_l W_l^T),
 //              then the value-path backward abar_{l-1} = s_l * (abar_l W_l) + e_{l-1} -- 2L GEMM steps
 //
-// Every activation a later pass or the weight-gradient GEMMs need is written once as a BF16 image, by the thread
-// that owns the row; a thread only ever reads back image bytes it wrote itself (same row, same column chunks), so
-// no cross-thread visibility is involved.  The weight gradients run afterwards as grouped tensor-core launches.
+// ALL bulk traffic goes through the async copy engine, never through per-thread global accesses (a thread-per-row
+// access touches 32 different 128-byte lines per warp instruction and serialises in L1): weight half-tiles and the
+// auxiliary activation blocks (h_l, q_l / e_l, 128 rows x 64 columns = 16 KB) arrive by bulk copies into rings,
+// results leave as bulk stores of the operand blocks themselves (their bytes ARE the activation image) and of the
+// auxiliary blocks rewritten in place (e_l over h_l).  FP32 row-major outputs (features) are transposed through
+// shared memory and written as whole lines.  q_{L-1} and the positional-encoding part of the skip gradient wait in
+// the 256 spare TMEM columns instead of HBM.
 //
-//   warp 0      : MMA issuer (+ TMEM alloc: one 256-column accumulator per tile of the pair)
-//   warp 1      : weight-image loader, ring of 4 half-tiles (128 output columns x 64 reduction, 16 KB)
-//   warps 2-17  : 8 per tile, thread = one row (TMEM lane), 16 columns at a time, the next chunk's auxiliary
-//                 image rows prefetched into registers while the current chunk is computed
+//   warp 0      : MMA issuer (+ TMEM alloc: 256 accumulator columns + 256 spare)
+//   warp 1      : weight-image loader, ring of 5 half-tiles (128 output columns x 64 reduction, 16 KB)
+//   warp 2      : auxiliary-block loader (2 slots of h + q blocks)
+//   warp 3      : storer: bulk shared->global of finished blocks, releases the slots
+//   warps 4-19  : epilogue, thread = one row (TMEM lane) x one of four 16-column groups per 64-column block
 #pragma once
 #include "chain_fused.cuh"
 
 namespace fneus {
 
-constexpr int SC_THREADS = 576, SC_WSTAGES = 4, SC_MAXS = 20, SC_SLOT_BLOCKS = 4, SC_BIAS_SLOTS = 12;
+constexpr int SC_THREADS = 640, SC_WSTAGES = 5, SC_MAXS = 20, SC_BIAS_SLOTS = 10, SC_EPI_THREADS = 512;
 enum SdfStepMode { SC_SOFTPLUS = 0, SC_FEATQ, SC_SPMUL, SC_G0, SC_SWEEP, SC_SDFBWD };
 enum SdfStepSrc { SRC_CHAIN = 0, SRC_PE, SRC_TAN, SRC_MEM };
 
@@ -30,11 +35,13 @@ struct SdfStep {
   const float* bias;    // SOFTPLUS / FEATQ
   float* img_out;       // image of the step's result (4 blocks per tile) or null
   const float* h;       // SPMUL / SWEEP / SDFBWD: image of the forward activation the softplus derivative comes from
-  const float* q;       // SWEEP / FEATQ: image q_l ; SDFBWD: image e_{l-1} ; G0: FP32 [M, ldo] addend (or null)
-  float* e_out;         // SWEEP: image e_l ; SOFTPLUS with dot: image q_{L-1}
-  float* out;           // FEATQ: features FP32 [M, ldo] ; G0: g_0 FP32 [M, ldo] ; SPMUL at the skip: PE part FP32 [M, ldo]
+  const float* q;       // SWEEP: image q_l ; SDFBWD: image e_{l-1}
+  float* e_out;         // SWEEP: image e_l (rewritten over the h block in shared memory)
+  float* out;           // FEATQ: features FP32 [M, ldo] ; G0: normal FP32 [M, d_in]
   int KB, N, mode, bmn, src;
   int ldo, csplit, append, dot, use_rs, bias_slot;
+  int sync_stores;      // storer: wait for full completion of every store so far after this step (later steps read them back)
+  int wait_sync;        // aux loader: wait for that completion before this step's first load
   float hscale, oscale;
 };
 struct SdfChainArgs {
@@ -55,11 +62,14 @@ struct SdfChainArgs {
 };
 struct SCSmem {
   uint64_t wfull[SC_WSTAGES], wempty[SC_WSTAGES];
-  uint64_t a_ready[2], acc_full[2];
+  uint64_t a_ready, acc_full, op_free, st_sync;
+  uint64_t aux_full[2], aux_empty[2], blk_done[2];
   uint32_t tmem_base;
 };
-constexpr int SC_SLOT_BYTES = SC_SLOT_BLOCKS * TC_A_BYTES;
-constexpr int SC_SMEM_BYTES = 2 * SC_SLOT_BYTES + SC_WSTAGES * CH_WBYTES + (SC_BIAS_SLOTS * 256 + 256 + 256) * 4 + 1024 + 256;
+constexpr int SC_OP_BYTES = 4 * TC_A_BYTES;                      // operand: 128 rows x 256 columns BF16
+constexpr int SC_AUX_BYTES = 4 * TC_A_BYTES;                     // 2 slots x (h block + q block)
+constexpr int SC_SMEM_BYTES = SC_OP_BYTES + SC_WSTAGES * CH_WBYTES + SC_AUX_BYTES +
+                              (SC_BIAS_SLOTS * 256 + 256 + 128) * 4 + 1024 + 256;
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float* out) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -74,27 +84,50 @@ __device__ __forceinline__ uint4 f32x8_to_bf16(const float* y) {
   const uint2 hi = pack_bf16x4(make_float4(y[4], y[5], y[6], y[7]));
   return make_uint4(lo.x, lo.y, hi.x, hi.y);
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// number of 64-column blocks a step's epilogue walks (every role derives it the same way)
+__device__ __forceinline__ int sdf_step_blocks(const SdfStep& S) { return S.mode == SC_G0 ? 1 : 4; }
 
 __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_constant__ SdfChainArgs g) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sAt[2] = {base, base + SC_SLOT_BYTES};
-  uint8_t* sW0 = base + 2 * SC_SLOT_BYTES;
-  float* sbias = reinterpret_cast<float*>(sW0 + SC_WSTAGES * CH_WBYTES);             // [SC_BIAS_SLOTS][256]
-  float* srvec = sbias + SC_BIAS_SLOTS * 256;                                        // [256]
-  float* sdot = srvec + 256;                                                         // [2][128]
-  SCSmem* ctl = reinterpret_cast<SCSmem*>(sdot + 256);
+  uint8_t* sOp = base;
+  uint8_t* sW0 = base + SC_OP_BYTES;
+  uint8_t* sAux = sW0 + SC_WSTAGES * CH_WBYTES;                  // slot i: h block at 2i, q block at 2i+1 (16 KB each)
+  float* sbias = reinterpret_cast<float*>(sAux + SC_AUX_BYTES);  // [SC_BIAS_SLOTS][256]
+  float* srvec = sbias + SC_BIAS_SLOTS * 256;                    // [256]
+  float* sdot = srvec + 256;                                     // [128]
+  SCSmem* ctl = reinterpret_cast<SCSmem*>(sdot + 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ntiles = (g.M + 127) / 128;
-  const long long npairs = (ntiles + 1) / 2;
   const float rsqrt2 = 0.70710678118654752440f;
 
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < SC_WSTAGES; s++) { mbar_init(&ctl->wfull[s], 1); mbar_init(&ctl->wempty[s], 1); }
+    mbar_init(&ctl->a_ready, SC_EPI_THREADS);
+    mbar_init(&ctl->acc_full, 1);
+    mbar_init(&ctl->op_free, 1);
+    mbar_init(&ctl->st_sync, 1);
 #pragma unroll
-    for (int t = 0; t < 2; t++) { mbar_init(&ctl->a_ready[t], 256); mbar_init(&ctl->acc_full[t], 1); }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&ctl->aux_full[i], 1);
+      mbar_init(&ctl->aux_empty[i], 1);
+      mbar_init(&ctl->blk_done[i], SC_EPI_THREADS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int s = 0; s < g.nsteps; s++) {
@@ -113,7 +146,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
     // ------------------------------ weight loader ------------------------------
     if (lane == 0) {
       int kbg = 0;
-      for (long long p = blockIdx.x; p < npairs; p += gridDim.x) {
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int s = 0; s < g.nsteps; s++) {
           const SdfStep& S = g.st[s];
           const int Nc = (S.N + 15) & ~15;
@@ -135,12 +168,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       int kbg = 0, lg = 0;
-      for (long long p = blockIdx.x; p < npairs; p += gridDim.x) {
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int s = 0; s < g.nsteps; s++, lg++) {
           const SdfStep& S = g.st[s];
           const int Nc = (S.N + 15) & ~15;
-          mbar_wait(&ctl->a_ready[0], lg & 1);
-          mbar_wait(&ctl->a_ready[1], lg & 1);
+          mbar_wait(&ctl->a_ready, lg & 1);
           tc_fence_after();
           for (int kb = 0; kb < S.KB; kb++) {
             for (int h = 0; h * 128 < Nc; h++, kbg++) {
@@ -150,142 +182,166 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
               mbar_wait(&ctl->wfull[stg], (kbg / SC_WSTAGES) & 1);
               tc_fence_after();
               const uint32_t b_addr = smem_u32(sW0 + stg * CH_WBYTES);
+              const uint32_t a_addr = smem_u32(sOp) + kb * TC_A_BYTES;
 #pragma unroll
-              for (int t = 0; t < 2; t++) {
-                const uint32_t a_addr = smem_u32(sAt[t]) + kb * TC_A_BYTES;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                  const uint64_t bd = S.bmn ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
-                  umma_bf16(tmem_base + t * 256 + h * 128, make_desc(a_addr + k * 32, 16, 1024), bd, idesc,
-                            (kb > 0 || k > 0) ? 1 : 0);
-                }
+              for (int k = 0; k < 4; k++) {
+                const uint64_t bd = S.bmn ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
+                umma_bf16(tmem_base + h * 128, make_desc(a_addr + k * 32, 16, 1024), bd, idesc, (kb > 0 || k > 0) ? 1 : 0);
               }
               umma_commit(&ctl->wempty[stg]);
             }
           }
-          umma_commit(&ctl->acc_full[0]);
-          umma_commit(&ctl->acc_full[1]);
+          umma_commit(&ctl->acc_full);
         }
       }
       tc_fence_before();
     }
+  } else if (warp == 2) {
+    // ------------------------------ auxiliary-block loader ------------------------------
+    if (lane == 0) {
+      int c = 0, nsync = 0;                         // c: global block counter (slot = c & 1)
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int s = 0; s < g.nsteps; s++) {
+          const SdfStep& S = g.st[s];
+          const int nb = sdf_step_blocks(S);
+          const bool has_h = S.h != nullptr, has_q = S.q != nullptr;
+          if (S.wait_sync) { mbar_wait(&ctl->st_sync, nsync & 1); nsync++; }
+          for (int b = 0; b < nb; b++, c++) {
+            const int slot = c & 1;
+            if (c >= 2) mbar_wait(&ctl->aux_empty[slot], ((c >> 1) - 1) & 1);
+            const bool ld = (has_h || has_q) && b * 64 < S.N;
+            if (ld) {
+              mbar_arrive_expect_tx(&ctl->aux_full[slot], (uint32_t)((has_h ? 1 : 0) + (has_q ? 1 : 0)) * TC_A_BYTES);
+              const size_t off = ((size_t)tile * 4 + b) * TC_A_BYTES;
+              if (has_h) bulk_g2s(sAux + (2 * slot) * TC_A_BYTES, reinterpret_cast<const uint8_t*>(S.h) + off, TC_A_BYTES, &ctl->aux_full[slot]);
+              if (has_q) bulk_g2s(sAux + (2 * slot + 1) * TC_A_BYTES, reinterpret_cast<const uint8_t*>(S.q) + off, TC_A_BYTES, &ctl->aux_full[slot]);
+            } else {
+              mbar_arrive(&ctl->aux_full[slot]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------ storer ------------------------------
+    if (lane == 0) {
+      int c = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int s = 0; s < g.nsteps; s++) {
+          const SdfStep& S = g.st[s];
+          const int nb = sdf_step_blocks(S);
+          for (int b = 0; b < nb; b++, c++) {
+            const int slot = c & 1;
+            mbar_wait(&ctl->blk_done[slot], (c >> 1) & 1);
+            const size_t off = ((size_t)tile * 4 + b) * TC_A_BYTES;
+            bool any = false;
+            if (S.img_out != nullptr) { bulk_s2g(reinterpret_cast<uint8_t*>(S.img_out) + off, sOp + b * TC_A_BYTES, TC_A_BYTES); any = true; }
+            if (S.e_out != nullptr) { bulk_s2g(reinterpret_cast<uint8_t*>(S.e_out) + off, sAux + (2 * slot) * TC_A_BYTES, TC_A_BYTES); any = true; }
+            if (any) { bulk_commit(); bulk_wait_read0(); }
+            mbar_arrive(&ctl->aux_empty[slot]);
+          }
+          if (S.sync_stores) { bulk_wait0(); mbar_arrive(&ctl->st_sync); }
+          mbar_arrive(&ctl->op_free);
+        }
+      }
+      bulk_wait0();
+    }
   } else {
     // ------------------------------ operand builders / epilogue ------------------------------
-    const int t = (warp - 2) >> 3;                 // tile of the pair
-    const int wslot = (warp - 2) & 7;
-    const int grp = wslot >> 2;                    // column interleave group (0/1)
-    const int quarter = warp & 3;
+    const int et = tid - 128;                      // 0..511
+    const int ew = et >> 5;                        // epilogue warp 0..15
+    const int cg = ew >> 2;                        // 16-column group inside a 64-column block
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;             // row within the tile == TMEM lane
     const int r7 = r & 7;
     const int rowoff = (r >> 3) * 1024 + r7 * 128; // byte offset of the row inside a 128 x 64 BF16 block
-    uint8_t* rowA = sAt[t] + rowoff;
-    const uint32_t taddr = tmem_base + t * 256 + ((uint32_t)(quarter * 32) << 16);
+    const int ch0 = (((2 * cg) ^ r7) & 7) << 4, ch1 = (((2 * cg + 1) ^ r7) & 7) << 4;   // the thread's two 16-byte chunks
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float beta = g.beta, inv_beta = 1.f / g.beta;
-    int lg = 0;
-    for (long long p = blockIdx.x; p < npairs; p += gridDim.x) {
-      const long long tile = 2 * p + t;
-      const bool tile_ok = tile < ntiles;
+    int lg = 0, c = 0, nfree = 0;                  // nfree: op_free phases consumed
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long m = tile * 128 + r;
-      const bool valid = tile_ok && m < g.M;
-      const size_t tile_img = (size_t)(tile_ok ? tile : 0) * SC_SLOT_BLOCKS * TC_A_BYTES + rowoff;   // 4-block images
-
+      const bool valid = m < g.M;
       for (int s = 0; s < g.nsteps; s++, lg++) {
         const SdfStep& S = g.st[s];
+        // The operand blocks of the previous step are being stored: nothing may overwrite them before the storer has
+        // read them (one op_free phase per step).
+        const bool first_overall = lg == 0;
         // ---- operand for this step, when it does not come from the previous step's epilogue ----
-        if (S.src == SRC_PE || S.src == SRC_TAN) {
-          if (grp == 0) {
+        if (S.src != SRC_CHAIN) {
+          if (!first_overall) { mbar_wait(&ctl->op_free, nfree & 1); nfree++; }
+          if (S.src == SRC_PE || S.src == SRC_TAN) {
+            if (cg == 0) {
+              uint8_t* rowA = sOp + rowoff;
 #pragma unroll
-            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(rowA + c * 16) = make_uint4(0u, 0u, 0u, 0u);
-            if (valid)
-              gen_row(S.src == SRC_PE ? g.gen : g.gen_t, m, [&](int j, float val) {
-                if (j < TC_BK)
-                  *reinterpret_cast<unsigned short*>(rowA + ((((j >> 3) ^ r7) & 7) << 4) + ((j & 7) << 1)) = f32_to_bf16_bits(val);
-              });
-            if (g.pe_img != nullptr && tile_ok) {
-              uint8_t* dst = reinterpret_cast<uint8_t*>(g.pe_img) + (size_t)tile * TC_A_BYTES + rowoff;
+              for (int k = 0; k < 8; k++) *reinterpret_cast<uint4*>(rowA + k * 16) = make_uint4(0u, 0u, 0u, 0u);
+              if (valid)
+                gen_row(S.src == SRC_PE ? g.gen : g.gen_t, m, [&](int j, float val) {
+                  if (j < TC_BK)
+                    *reinterpret_cast<unsigned short*>(rowA + ((((j >> 3) ^ r7) & 7) << 4) + ((j & 7) << 1)) = f32_to_bf16_bits(val);
+                });
+              if (g.pe_img != nullptr) {
+                uint8_t* dst = reinterpret_cast<uint8_t*>(g.pe_img) + (size_t)tile * TC_A_BYTES + rowoff;
 #pragma unroll
-              for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(dst + c * 16) = *reinterpret_cast<const uint4*>(rowA + c * 16);
-            }
-          }
-        } else if (S.src == SRC_MEM) {
-          const bool vec_ok = (g.ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mem) & 15) == 0;
-          const int nch = ((g.kmem + TC_BK - 1) / TC_BK) * 8;
-          for (int rr = wslot * 16; rr < wslot * 16 + 16; rr++) {
-            const long long mm = tile * 128 + rr;
-            const bool rv = tile_ok && mm < g.M;
-            const float* src = g.mem + mm * g.ldm;
-            uint8_t* drow = sAt[t] + (rr >> 3) * 1024 + (rr & 7) * 128;
-            for (int ch = lane; ch < nch; ch += 32) {
-              const int c = ch * 8;
-              float v[8];
-              if (rv && vec_ok && c + 8 <= g.kmem) {
-                const float4 lo = __ldg(reinterpret_cast<const float4*>(src + c));
-                const float4 hi = __ldg(reinterpret_cast<const float4*>(src + c + 4));
-                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++) v[j] = (rv && c + j < g.kmem) ? __ldg(src + c + j) : 0.f;
+                for (int k = 0; k < 8; k++) *reinterpret_cast<uint4*>(dst + k * 16) = *reinterpret_cast<const uint4*>(rowA + k * 16);
               }
-              *reinterpret_cast<uint4*>(drow + (ch >> 3) * TC_A_BYTES + ((((ch & 7) ^ (rr & 7)) & 7) << 4)) = f32x8_to_bf16(v);
+            }
+          } else {
+            // FP32 row-major source: each warp converts 8 rows, a lane 8 consecutive columns at a time (whole lines)
+            const bool vec_ok = (g.ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mem) & 15) == 0;
+            const int nch = ((g.kmem + TC_BK - 1) / TC_BK) * 8;
+            for (int rr = ew * 8; rr < ew * 8 + 8; rr++) {
+              const long long mm = tile * 128 + rr;
+              const bool rv = mm < g.M;
+              const float* src = g.mem + mm * g.ldm;
+              uint8_t* drow = sOp + (rr >> 3) * 1024 + (rr & 7) * 128;
+              for (int ch = lane; ch < nch; ch += 32) {
+                const int cc = ch * 8;
+                float v[8];
+                if (rv && vec_ok && cc + 8 <= g.kmem) {
+                  const float4 lo = __ldg(reinterpret_cast<const float4*>(src + cc));
+                  const float4 hi = __ldg(reinterpret_cast<const float4*>(src + cc + 4));
+                  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; j++) v[j] = (rv && cc + j < g.kmem) ? __ldg(src + cc + j) : 0.f;
+                }
+                *reinterpret_cast<uint4*>(drow + (ch >> 3) * TC_A_BYTES + ((((ch & 7) ^ (rr & 7)) & 7) << 4)) = f32x8_to_bf16(v);
+              }
             }
           }
-        }
-        if (s == 0 || S.src != SRC_CHAIN) {
           tc_fence_before();
           fence_proxy_async();
-          mbar_arrive(&ctl->a_ready[t]);
+          mbar_arrive(&ctl->a_ready);
         }
 
         const int N = S.N, Nc = (N + 15) & ~15, mode = S.mode;
-        const bool writes_operand = mode != SC_G0;
-        const int cover = writes_operand ? 256 : ((Nc + 31) & ~31);
+        const int nb = sdf_step_blocks(S);
         const float* sb = sbias + (S.bias_slot >= 0 ? S.bias_slot : 0) * 256;
-        const bool need_h = (mode == SC_SPMUL || mode == SC_SWEEP || mode == SC_SDFBWD) && tile_ok;
-        const bool need_q = (mode == SC_SWEEP || mode == SC_SDFBWD || mode == SC_FEATQ) && S.q != nullptr && tile_ok;
-        const uint8_t* hp = reinterpret_cast<const uint8_t*>(S.h) + tile_img;
-        const uint8_t* qp = reinterpret_cast<const uint8_t*>(S.q) + tile_img;
-        uint8_t* op = reinterpret_cast<uint8_t*>(S.img_out) + tile_img;
-        uint8_t* ep = reinterpret_cast<uint8_t*>(S.e_out) + tile_img;
-        const bool st_img = S.img_out != nullptr && tile_ok;
         const float hscale = S.hscale, oscale = S.oscale;
         const float rsv = (mode == SC_SDFBWD && S.use_rs && valid) ? __ldg(g.rs + m) * g.rscale : 0.f;
         float dot = 0.f;
 
-        // auxiliary rows of the first chunk are requested before the accumulator is waited for
-        uint4 ah0 = make_uint4(0u, 0u, 0u, 0u), ah1 = ah0, aq0 = ah0, aq1 = ah0;
-        {
-          const int n = grp * 32;
-          const int o0 = (n >> 6) * TC_A_BYTES + (((((n & 63) >> 3)) ^ r7) << 4);
-          const int o1 = (n >> 6) * TC_A_BYTES + (((((n & 63) >> 3) + 1) ^ r7) << 4);
-          if (need_h && n < N) { ah0 = __ldcg(reinterpret_cast<const uint4*>(hp + o0)); ah1 = __ldcg(reinterpret_cast<const uint4*>(hp + o1)); }
-          if (need_q && n < N) { aq0 = __ldcg(reinterpret_cast<const uint4*>(qp + o0)); aq1 = __ldcg(reinterpret_cast<const uint4*>(qp + o1)); }
-        }
-        if (mode == SC_G0 && S.q != nullptr) slot_bar(t);   // the addend's columns were written by both column groups
-        mbar_wait(&ctl->acc_full[t], lg & 1);
+        mbar_wait(&ctl->acc_full, lg & 1);
         tc_fence_after();
+        if (S.src == SRC_CHAIN && !first_overall) { mbar_wait(&ctl->op_free, nfree & 1); nfree++; }
 
 #pragma unroll 1
-        for (int n = grp * 32; n < cover; n = ((n & 16) ? n + 48 : n + 16)) {
-          const int o0 = (n >> 6) * TC_A_BYTES + (((((n & 63) >> 3)) ^ r7) << 4);
-          const int o1 = (n >> 6) * TC_A_BYTES + (((((n & 63) >> 3) + 1) ^ r7) << 4);
-          float a[16], hv[16], qv[16], y[16];
-          bf16x8_to_f32(ah0, hv); bf16x8_to_f32(ah1, hv + 8);
-          bf16x8_to_f32(aq0, qv); bf16x8_to_f32(aq1, qv + 8);
-          {
-            // prefetch the next chunk's auxiliary rows
-            const int nn = (n & 16) ? n + 48 : n + 16;
-            const int p0 = (nn >> 6) * TC_A_BYTES + (((((nn & 63) >> 3)) ^ r7) << 4);
-            const int p1 = (nn >> 6) * TC_A_BYTES + (((((nn & 63) >> 3) + 1) ^ r7) << 4);
-            const bool more = nn < cover && nn < N;
-            if (need_h && more) { ah0 = __ldcg(reinterpret_cast<const uint4*>(hp + p0)); ah1 = __ldcg(reinterpret_cast<const uint4*>(hp + p1)); }
-            if (need_q && more) { aq0 = __ldcg(reinterpret_cast<const uint4*>(qp + p0)); aq1 = __ldcg(reinterpret_cast<const uint4*>(qp + p1)); }
-          }
+        for (int b = 0; b < nb; b++, c++) {
+          const int slot = c & 1;
+          const int n = b * 64 + cg * 16;
+          uint8_t* opb = sOp + b * TC_A_BYTES + rowoff;                    // the row inside operand block b
+          uint8_t* hb = sAux + (2 * slot) * TC_A_BYTES + rowoff;           // ... inside the slot's h block
+          const uint8_t* qb = sAux + (2 * slot + 1) * TC_A_BYTES + rowoff; // ... inside the slot's q block
+          mbar_wait(&ctl->aux_full[slot], (c >> 1) & 1);
+          float a[16];
           if (n < Nc) tmem_ld16(taddr + n, a);
           else {
 #pragma unroll
             for (int j = 0; j < 16; j++) a[j] = 0.f;
           }
           if (mode == SC_SOFTPLUS) {
+            float qv[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) {
               float v = softplus_beta_fast(a[j] + sb[n + j], beta, inv_beta);
@@ -294,103 +350,168 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
                 dot += v * srvec[n + j];
                 qv[j] = softplus_grad_from_act_fast(v, beta) * srvec[n + j];   // q_{L-1} from the unrounded activation
               }
-              y[j] = v * oscale;
+              a[j] = v * oscale;
             }
-            if (S.dot && S.e_out != nullptr && tile_ok) {
-              *reinterpret_cast<uint4*>(ep + o0) = f32x8_to_bf16(qv);
-              *reinterpret_cast<uint4*>(ep + o1) = f32x8_to_bf16(qv + 8);
-            }
+            if (S.dot) tmem_st16(taddr + 256 + n, qv);                         // waits in the spare TMEM columns
           } else if (mode == SC_FEATQ) {
-            if (valid && n < N) {
-              float f[16];
+            // features: FP32 through a swizzled [128][64] staging tile (the slot's 32 KB), written out as whole lines
+            float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
 #pragma unroll
-              for (int j = 0; j < 16; j++) f[j] = a[j] + sb[n + j];
-              row_store16(S.out, S.ldo, m, n, N - n, f);
-            }
-            // the reverse chain starts from q_{L-1}, written to its image by the previous step (same thread, same chunk)
+            for (int i = 0; i < 4; i++)
+              *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
+                  make_float4(a[4 * i] + sb[n + 4 * i], a[4 * i + 1] + sb[n + 4 * i + 1], a[4 * i + 2] + sb[n + 4 * i + 2],
+                              a[4 * i + 3] + sb[n + 4 * i + 3]);
+            tmem_ld16(taddr + 256 + n, a);
 #pragma unroll
-            for (int j = 0; j < 16; j++) y[j] = (valid && n + j < N) ? qv[j] : 0.f;
+            for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? a[j] : 0.f;
           } else if (mode == SC_SPMUL) {
+            if (S.csplit < N && n + 16 > S.csplit) {
+              // positional-encoding part of the skip gradient: parked in the spare TMEM columns until G0
+              float gz[16];
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-              const float sg = softplus_grad_from_act_fast(hv[j] * hscale, beta);
-              y[j] = (valid && n + j < S.csplit) ? sg * a[j] * oscale : 0.f;
+              for (int j = 0; j < 16; j++) gz[j] = a[j] * oscale;
+              tmem_st16(taddr + 256 + n, gz);
             }
-            if (S.out != nullptr && valid && n + 16 > S.csplit) {
-#pragma unroll 1
-              for (int j = 0; j < 16; j++) {
-                const int nn = n + j;
-                if (nn >= S.csplit && nn < N) S.out[m * S.ldo + nn - S.csplit] = a[j] * oscale;
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+              float hv[8];
+              bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const float sg = softplus_grad_from_act_fast(hv[j] * hscale, beta);
+                a[hf * 8 + j] = (valid && n + hf * 8 + j < S.csplit) ? sg * a[hf * 8 + j] * oscale : 0.f;
               }
             }
           } else if (mode == SC_G0) {
-            if (valid) {
-#pragma unroll 1
+            // g_0 = q_0 W_0 (+ the parked skip part): 128 x 64 FP32 staging, then one thread per row forms the normal
+            float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
+            if (S.csplit > 0) {
+              // parked columns csplit .. csplit+N-1 of the skip step <-> g_0 columns 0 .. N-1
+              const int c0 = (S.csplit + n) & ~15, sh = (S.csplit + n) & 15;
+              float p0[16], p1[16];
+#pragma unroll
+              for (int j = 0; j < 16; j++) { p0[j] = 0.f; p1[j] = 0.f; }
+              if (c0 < 256) tmem_ld16(taddr + 256 + c0, p0);
+              if (c0 + 16 < 256) tmem_ld16(taddr + 256 + c0 + 16, p1);
+#pragma unroll
               for (int j = 0; j < 16; j++) {
-                const int nn = n + j;
-                if (nn < N) S.out[m * S.ldo + nn] = a[j] + (S.q != nullptr ? __ldcg(S.q + m * S.ldo + nn) : 0.f);
+                const int k = j + sh;
+                float v = 0.f;
+#pragma unroll
+                for (int u = 0; u < 32; u++)
+                  if (u == k) v = u < 16 ? p0[u & 15] : p1[u & 15];
+                if (n + j < N && S.csplit + n + j < 256) a[j] += v;
               }
             }
-          } else if (mode == SC_SWEEP) {
-            float e[16];
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-              const float sg = softplus_grad_from_act_fast(hv[j] * hscale, beta);
-              const bool ok = valid && n + j < N;
-              y[j] = ok ? sg * a[j] * oscale : 0.f;
-              e[j] = ok ? beta * (1.f - sg) * qv[j] * a[j] : 0.f;
-            }
-            if (S.e_out != nullptr && tile_ok) {
-              *reinterpret_cast<uint4*>(ep + o0) = f32x8_to_bf16(e);
-              *reinterpret_cast<uint4*>(ep + o1) = f32x8_to_bf16(e + 8);
+            for (int i = 0; i < 4; i++)
+              *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
+                  make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+          } else if (mode == SC_SWEEP) {
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+              float hv[8], qv[8], e[8];
+              bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
+              bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const float sg = softplus_grad_from_act_fast(hv[j] * hscale, beta);
+                const bool ok = valid && n + hf * 8 + j < N;
+                const float acc = a[hf * 8 + j];
+                a[hf * 8 + j] = ok ? sg * acc * oscale : 0.f;
+                e[j] = ok ? beta * (1.f - sg) * qv[j] * acc : 0.f;
+              }
+              *reinterpret_cast<uint4*>(hb + (hf ? ch1 : ch0)) = f32x8_to_bf16(e);   // e_l leaves from where h_{l+1} arrived
             }
           } else {  // SC_SDFBWD
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-              const float sg = softplus_grad_from_act_fast(hv[j] * hscale, beta);
-              y[j] = (valid && n + j < S.csplit) ? sg * (a[j] + rsv * srvec[n + j]) * oscale + qv[j] : 0.f;
-            }
-          }
-          if (writes_operand) {
-            const uint4 c0 = f32x8_to_bf16(y), c1 = f32x8_to_bf16(y + 8);
-            *reinterpret_cast<uint4*>(rowA + o0) = c0;
-            *reinterpret_cast<uint4*>(rowA + o1) = c1;
-            if (st_img) {
-              *reinterpret_cast<uint4*>(op + o0) = c0;
-              *reinterpret_cast<uint4*>(op + o1) = c1;
-            }
-          }
-        }
-        if (S.append) {
-          // skip connection (fields.py:83-84): PE columns (value or tangent form) follow the N hidden columns, once
-          // BOTH column groups of the tile have written their chunks; the image gets the touched 16-byte chunks again
-          slot_bar(t);
-          if (grp == 1) {
-            if (valid)
-              gen_row(mode == SC_SWEEP ? g.gen_t : g.gen, m, [&](int j, float val) {
-                const int col = N + j;
-                if (col < 256)
-                  *reinterpret_cast<unsigned short*>(rowA + (col >> 6) * TC_A_BYTES + (((((col & 63) >> 3) ^ r7) & 7) << 4) +
-                                                     ((col & 7) << 1)) = f32_to_bf16_bits(val * rsqrt2);
-              });
-            if (st_img) {
-              for (int ch = N >> 3; ch < 32; ch++) {
-                const int o = (ch >> 3) * TC_A_BYTES + ((((ch & 7) ^ r7) & 7) << 4);
-                *reinterpret_cast<uint4*>(op + o) = *reinterpret_cast<const uint4*>(rowA + o);
+            for (int hf = 0; hf < 2; hf++) {
+              float hv[8], qv[8];
+              bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
+              bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const float sg = softplus_grad_from_act_fast(hv[j] * hscale, beta);
+                const int nn = n + hf * 8 + j;
+                a[hf * 8 + j] = (valid && nn < S.csplit) ? sg * (a[hf * 8 + j] + rsv * srvec[nn]) * oscale + qv[j] : 0.f;
               }
             }
           }
+          if (mode != SC_G0) {
+            *reinterpret_cast<uint4*>(opb + ch0) = f32x8_to_bf16(a);
+            *reinterpret_cast<uint4*>(opb + ch1) = f32x8_to_bf16(a + 8);
+          }
+          if (S.append && b == 3) {
+            // skip connection (fields.py:83-84): PE columns (value or tangent form) follow the N hidden columns once
+            // every column group has written its chunk of the last block
+            epi_bar();
+            if (cg == 0 && valid)
+              gen_row(mode == SC_SWEEP ? g.gen_t : g.gen, m, [&](int j, float val) {
+                const int col = N + j;
+                if (col < 256)
+                  *reinterpret_cast<unsigned short*>(sOp + (col >> 6) * TC_A_BYTES + rowoff + (((((col & 63) >> 3) ^ r7) & 7) << 4) +
+                                                     ((col & 7) << 1)) = f32_to_bf16_bits(val * rsqrt2);
+              });
+          }
+          if (mode == SC_FEATQ || mode == SC_G0) {
+            epi_bar();
+            const float* T = reinterpret_cast<const float*>(sAux + (2 * slot) * TC_A_BYTES);
+            if (mode == SC_FEATQ) {
+              // warp ew writes rows 8 ew .. 8 ew + 7: two rows (2 x 256 B) per instruction
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int rr = ew * 8 + 2 * i + (lane >> 4), q4 = lane & 15;
+                const long long mm = tile * 128 + rr;
+                const int col = b * 64 + q4 * 4;
+                if (mm < g.M && col < N) {
+                  const float4 v = *reinterpret_cast<const float4*>(T + rr * 64 + ((q4 ^ (rr & 15)) << 2));
+                  float* dst = S.out + mm * S.ldo + col;
+                  if (col + 4 <= N && (S.ldo & 3) == 0) *reinterpret_cast<float4*>(dst) = v;
+                  else {
+                    dst[0] = v.x;
+                    if (col + 1 < N) dst[1] = v.y;
+                    if (col + 2 < N) dst[2] = v.z;
+                    if (col + 3 < N) dst[3] = v.w;
+                  }
+                }
+              }
+            } else if (et < 128) {
+              // thread et = row: normal = J_PE(x)^T g_0 (fields.py:101-111)
+              const int rr = et;
+              const long long mm = tile * 128 + rr;
+              if (mm < g.M) {
+                const GenItem it = g.gen.it[0];
+                for (int cc = 0; cc < it.dim; cc++) {
+                  const float v = __ldg(it.src + mm * it.dim + cc) * it.scale;
+                  auto G0 = [&](int col) { return T[rr * 64 + ((((col >> 2) ^ (rr & 15)) << 2) | (col & 3))]; };
+                  float acc = G0(cc);
+                  for (int k = 0; k < it.multires; k++) {
+                    const float f = (float)(1u << k);
+                    float sn, cs;
+                    sincosf(v * f, &sn, &cs);
+                    acc += f * cs * G0(it.dim * (1 + 2 * k) + cc) - f * sn * G0(it.dim * (2 + 2 * k) + cc);
+                  }
+                  S.out[mm * it.dim + cc] = acc;
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive(&ctl->blk_done[slot]);
         }
         if (S.dot) {
-          if (grp == 0) sdot[t * 128 + r] = dot;
-          slot_bar(t);
-          if (grp == 1 && valid)
-            g.sdf_out[m] = (sdot[t * 128 + r] + dot + __ldg(g.b_last)) * g.sdf_scale;
+          // sdf = h_L . W_L[0] + b: the four column groups of a row meet in shared memory
+          if (cg == 0) sdot[r] = dot;
+          epi_bar();
+          if (cg != 0) atomicAdd(&sdot[r], dot);
+          epi_bar();
+          if (cg == 0 && valid) g.sdf_out[m] = (sdot[r] + __ldg(g.b_last)) * g.sdf_scale;
         }
-        tc_fence_before();
         if (s + 1 < g.nsteps && g.st[s + 1].src == SRC_CHAIN) {
+          tc_fence_before();
           fence_proxy_async();
-          mbar_arrive(&ctl->a_ready[t]);
+          mbar_arrive(&ctl->a_ready);
         }
       }
     }
@@ -411,9 +532,9 @@ inline int sdf_chain_prepare() {
   return 0;
 }
 inline void sdf_chain_launch(const SdfChainArgs& g, double flops, cudaStream_t st) {
-  const long long npairs = ((g.M + 127) / 128 + 1) / 2;
+  const long long ntiles = (g.M + 127) / 128;
   const int sms = tc_num_sms();
-  const int grid = (int)(npairs < sms ? npairs : sms);
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
   prof_begin(PC_TC_MLP, flops, 0.0, st);
   sdf_chain_kernel<<<grid, SC_THREADS, SC_SMEM_BYTES, st>>>(g);
   prof_end(st);
