@@ -65,7 +65,13 @@ _SIGNATURES = {
     "fneus_num_sms": (c_int, []),
     "fneus_set_precision": (c_int, [c_int]),
     "fneus_get_precision": (c_int, []),
+    "fneus_surface_blend_fwd": (c_int, [_P, _P, _P, _P, _P, _LL, _P, _P, _P, _P]),
+    "fneus_surface_blend_bwd": (c_int, [_P, _P, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fneus_loss_norms": (c_int, [_P, _P, _P, _LL, c_int, _P, _P]),
+    "fneus_stage1_loss": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, c_int, c_float, c_float, c_float, _P, _P, _P,
+                                  _P, _P, _P]),
     "fneus_debug_flags": (c_int, [c_int]),
+    "fneus_debug_timeline": (c_int, [_P, c_int]),
     "fneus_debug_gemm": (c_int, [c_int, _P, c_int, _P, c_int, _P, _LL, c_int, c_int, _P, c_int, _P]),
     "fneus_prof_classes": (c_int, []),
     "fneus_prof_enable": (c_int, [c_int]),

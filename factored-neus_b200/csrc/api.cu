@@ -70,6 +70,11 @@ int fneus_set_precision(int mode) {
 }
 int fneus_get_precision(void) { return fneus::precision_mode(); }
 // debug/bisect switches of the persistent tensor-core kernel (bit0: skip A loads, bit1: skip epilogue, bit2: skip MMA)
+int fneus_debug_timeline(unsigned long long* host_dst, int n) {
+  if (!host_dst || n <= 0 || n > 8192) return FNEUS_ERR_BAD_SHAPE;
+  cudaError_t e = cudaMemcpyFromSymbol(host_dst, fneus::g_sc_dbg, (size_t)n * 8, (size_t)(8192 - n) * 8 * 0);
+  return e == cudaSuccess ? FNEUS_OK : fneus::fneus_cuda_error((int)e);
+}
 int fneus_debug_flags(int flags) {
   fneus::tc_debug_flags() = flags & 0xFF;
   int w = (flags >> 8) & 0xF;                      // bits 8-11: weight-gradient CTAs per SM (tuning knob), 0 = keep

@@ -5,4 +5,5 @@
 #include "sampling.cu"
 #include "composite.cu"
 #include "pack.cu"
+#include "loss.cu"
 #include "api.cu"

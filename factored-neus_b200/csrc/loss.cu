@@ -1,0 +1,206 @@
+// Per-ray tail of the training step: surface-colour blend of the two bracketing RefColor evaluations
+// (renderer.py:328-343) and the stage-1 loss with its gradients (exp_runner.py:134-177).  These are [B]-sized
+// element-wise chains and reductions; each is ONE launch here instead of dozens of framework kernels.
+#include "fneus_common.cuh"
+#include "prof.cuh"
+
+namespace fneus {
+
+// ---- surface blend: out_k = hit ? (c0_k w0 + c1_k w1) / (w0 + w1) : 1, for k over the three colour sets --------------
+__global__ void surface_blend_fwd_kernel(const float* __restrict__ c_rgb, const float* __restrict__ c_spec,
+                                         const float* __restrict__ c_diff, const float* __restrict__ w_pair,
+                                         const int* __restrict__ hit_idx, int B, float* __restrict__ o_rgb,
+                                         float* __restrict__ o_spec, float* __restrict__ o_diff) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 3) return;
+  const int b = i / 3, k = i - b * 3;
+  const bool hit = hit_idx[b] >= 0;
+  const float w0 = w_pair[2 * b], w1 = w_pair[2 * b + 1], den = w0 + w1;
+  const float* cs[3] = {c_rgb, c_spec, c_diff};
+  float* os[3] = {o_rgb, o_spec, o_diff};
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    const float c0 = cs[s][(2 * b) * 3 + k], c1 = cs[s][(2 * b + 1) * 3 + k];
+    os[s][i] = hit ? (c0 * w0 + c1 * w1) / den : 1.f;
+  }
+}
+// one thread per ray: d_c (both rows, three sets) and d_w_pair
+__global__ void surface_blend_bwd_kernel(const float* __restrict__ c_rgb, const float* __restrict__ c_spec,
+                                         const float* __restrict__ c_diff, const float* __restrict__ w_pair,
+                                         const int* __restrict__ hit_idx, int B, const float* __restrict__ g_rgb,
+                                         const float* __restrict__ g_spec, const float* __restrict__ g_diff,
+                                         float* __restrict__ d_rgb, float* __restrict__ d_spec,
+                                         float* __restrict__ d_diff, float* __restrict__ d_w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const bool hit = hit_idx[b] >= 0;
+  const float w0 = w_pair[2 * b], w1 = w_pair[2 * b + 1], den = w0 + w1;
+  const float* cs[3] = {c_rgb, c_spec, c_diff};
+  const float* gs[3] = {g_rgb, g_spec, g_diff};
+  float* ds[3] = {d_rgb, d_spec, d_diff};
+  float dw0 = 0.f, dw1 = 0.f;
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float g = (hit && gs[s] != nullptr) ? gs[s][b * 3 + k] : 0.f;
+      const float c0 = cs[s][(2 * b) * 3 + k], c1 = cs[s][(2 * b + 1) * 3 + k];
+      float a0 = 0.f, a1 = 0.f;
+      if (hit) {
+        // out = (c0 w0 + c1 w1) / den : d/dc0 = w0/den, d/dw0 = c0/den - num/den^2
+        const float num = c0 * w0 + c1 * w1;
+        const float gd = g / den;
+        a0 = gd * w0; a1 = gd * w1;
+        const float t = gd * (num / den);
+        dw0 += gd * c0 - t;
+        dw1 += gd * c1 - t;
+      }
+      ds[s][(2 * b) * 3 + k] = a0;
+      ds[s][(2 * b + 1) * 3 + k] = a1;
+    }
+  }
+  d_w[2 * b] = dw0;
+  d_w[2 * b + 1] = dw1;
+}
+
+// ---- loss normalisers: den = [sum mask, sum mask*hit, eik_den, B] -----------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
+  return t;
+}
+__device__ __forceinline__ float mask_of(const float* mask, int b, int use_mask) {
+  return use_mask ? (mask[b] > 0.5f ? 1.f : 0.f) : 1.f;
+}
+__global__ void loss_norms_kernel(const float* __restrict__ mask, const int* __restrict__ hit_idx,
+                                  const float* __restrict__ eik_den, int B, int use_mask, float* __restrict__ den) {
+  __shared__ float red[32];
+  float s0 = 0.f, s1 = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float m = mask_of(mask, b, use_mask);
+    s0 += m;
+    s1 += hit_idx[b] >= 0 ? m : 0.f;
+  }
+  s0 = block_sum(s0, red);
+  s1 = block_sum(s1, red);
+  if (threadIdx.x == 0) { den[0] = s0; den[1] = s1; den[2] = *eik_den; den[3] = (float)B; }
+}
+
+// ---- loss + gradients (single CTA; B is a ray batch) ------------------------------------------------------------------
+// parts = [loss, color_loss, surface_loss, eikonal_loss, mask_loss]
+__global__ void stage1_loss_kernel(const float* __restrict__ color, const float* __restrict__ surf,
+                                   const float* __restrict__ wsum, const float* __restrict__ true_rgb,
+                                   const float* __restrict__ mask, const int* __restrict__ hit_idx,
+                                   const float* __restrict__ eik_num, const float* __restrict__ den, int B, int use_mask,
+                                   float surface_w, float igr_w, float mask_w, float* __restrict__ parts,
+                                   float* __restrict__ d_color, float* __restrict__ d_surf, float* __restrict__ d_wsum,
+                                   float* __restrict__ d_eik_num) {
+  __shared__ float red[32];
+  const float mask_sum = den[0] + 1e-5f, mask_sdf_sum = den[1] + 1e-5f, relax_sum = den[2] + 1e-5f, n_global = den[3];
+  float lc = 0.f, ls = 0.f, lm = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float m = mask_of(mask, b, use_mask);
+    const float h = hit_idx[b] >= 0 ? 1.f : 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float t = true_rgb[b * 3 + k];
+      const float ec = (color[b * 3 + k] - t) * m;
+      lc += fabsf(ec);
+      d_color[b * 3 + k] = (ec > 0.f ? 1.f : (ec < 0.f ? -1.f : 0.f)) * m / mask_sum;
+      const float es = surface_w * (surf[b * 3 + k] - t) * m * h;
+      ls += fabsf(es);
+      d_surf[b * 3 + k] = (es > 0.f ? 1.f : (es < 0.f ? -1.f : 0.f)) * surface_w * m * h / mask_sdf_sum;
+    }
+    // binary cross entropy on the clipped opacity (torch clamps each log at -100)
+    const float w = wsum[b];
+    const float wc = fminf(fmaxf(w, 1e-3f), 1.f - 1e-3f);
+    lm += -(m * fmaxf(logf(wc), -100.f) + (1.f - m) * fmaxf(logf(1.f - wc), -100.f));
+    const float pass = (w >= 1e-3f && w <= 1.f - 1e-3f) ? 1.f : 0.f;
+    d_wsum[b] = mask_w * pass * (-(m / wc) + (1.f - m) / (1.f - wc)) / n_global;
+  }
+  lc = block_sum(lc, red);
+  ls = block_sum(ls, red);
+  lm = block_sum(lm, red);
+  if (threadIdx.x == 0) {
+    const float color_loss = lc / mask_sum, surf_loss = ls / mask_sdf_sum, eik_loss = *eik_num / relax_sum,
+                mask_loss = lm / n_global;
+    parts[0] = color_loss + surf_loss + eik_loss * igr_w + mask_loss * mask_w;
+    parts[1] = color_loss; parts[2] = surf_loss; parts[3] = eik_loss; parts[4] = mask_loss;
+    *d_eik_num = igr_w / relax_sum;
+  }
+}
+
+}  // namespace fneus
+
+using namespace fneus;
+
+extern "C" {
+
+int fneus_surface_blend_fwd(const float* c_rgb, const float* c_spec, const float* c_diff, const float* w_pair,
+                            const int* hit_idx, long long B, float* o_rgb, float* o_spec, float* o_diff, void* stream) {
+  if (B == 0) return FNEUS_OK;
+  if (!c_rgb || !c_spec || !c_diff || !w_pair || !hit_idx || !o_rgb || !o_spec || !o_diff) return FNEUS_ERR_NULL;
+  if (B < 0 || B > (1 << 28)) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_COMPOSITE, 0.0, 0.0, st);
+  surface_blend_fwd_kernel<<<cdiv(B * 3, 256), 256, 0, st>>>(c_rgb, c_spec, c_diff, w_pair, hit_idx, (int)B, o_rgb, o_spec,
+                                                             o_diff);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_surface_blend_bwd(const float* c_rgb, const float* c_spec, const float* c_diff, const float* w_pair,
+                            const int* hit_idx, long long B, const float* g_rgb, const float* g_spec,
+                            const float* g_diff, float* d_rgb, float* d_spec, float* d_diff, float* d_w_pair,
+                            void* stream) {
+  if (B == 0) return FNEUS_OK;
+  if (!c_rgb || !c_spec || !c_diff || !w_pair || !hit_idx || !d_rgb || !d_spec || !d_diff || !d_w_pair)
+    return FNEUS_ERR_NULL;
+  if (B < 0 || B > (1 << 28)) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_COMPOSITE, 0.0, 0.0, st);
+  surface_blend_bwd_kernel<<<cdiv(B, 128), 128, 0, st>>>(c_rgb, c_spec, c_diff, w_pair, hit_idx, (int)B, g_rgb, g_spec,
+                                                         g_diff, d_rgb, d_spec, d_diff, d_w_pair);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_loss_norms(const float* mask, const int* hit_idx, const float* eik_den, long long B, int use_mask,
+                     float* den4, void* stream) {
+  if (!mask || !hit_idx || !eik_den || !den4) return FNEUS_ERR_NULL;
+  if (B < 0 || B > (1 << 28)) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_COMPOSITE, 0.0, 0.0, st);
+  loss_norms_kernel<<<1, 1024, 0, st>>>(mask, hit_idx, eik_den, (int)B, use_mask, den4);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_stage1_loss(const float* color, const float* surface_color, const float* weight_sum, const float* true_rgb,
+                      const float* mask, const int* hit_idx, const float* eik_num, const float* den4, long long B,
+                      int use_mask, float surface_weight, float igr_weight, float mask_weight, float* parts5,
+                      float* d_color, float* d_surface_color, float* d_weight_sum, float* d_eik_num, void* stream) {
+  if (!color || !surface_color || !weight_sum || !true_rgb || !mask || !hit_idx || !eik_num || !den4 || !parts5 ||
+      !d_color || !d_surface_color || !d_weight_sum || !d_eik_num)
+    return FNEUS_ERR_NULL;
+  if (B < 0 || B > (1 << 28)) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_COMPOSITE, 0.0, 0.0, st);
+  stage1_loss_kernel<<<1, 1024, 0, st>>>(color, surface_color, weight_sum, true_rgb, mask, hit_idx, eik_num, den4, (int)B,
+                                         use_mask, surface_weight, igr_weight, mask_weight, parts5, d_color,
+                                         d_surface_color, d_weight_sum, d_eik_num);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+}  // extern "C"

@@ -308,8 +308,15 @@ static bool sdf_fused_ok(const SdfPlan& p) {
   if (p.skip > 0 && p.out[p.skip - 1] + p.e > 256) return false;
   return true;
 }
+static bool sdf_chain_ok(const fneus_sdf_cfg* c, const SdfPlan& p);
+static void sdf_chain_value_launch(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, const float* x, long long M,
+                                   float* sdf_out, float* feat_out, float out_sign, const SdfImgs& im, cudaStream_t st);
 static int sdf_fused_launch(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, const float* x, long long M,
                             float* sdf_out, float out_sign, const SdfImgs& im, cudaStream_t st) {
+  if (sdf_chain_ok(c, p)) {
+    sdf_chain_value_launch(c, p, w, x, M, sdf_out, nullptr, out_sign, im, st);
+    return FNEUS_OK;
+  }
   static int prepared = 0;
   if (!prepared) {
     cudaError_t e = cudaFuncSetAttribute(sdf_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM_BYTES);
@@ -352,6 +359,39 @@ static SdfStep sdf_step(int mode, const uint8_t* wimg, int KB, int N, int bmn) {
   S.mode = mode; S.wimg = wimg; S.KB = KB; S.N = N; S.bmn = bmn; S.src = SRC_CHAIN;
   S.csplit = N; S.bias_slot = -1; S.hscale = 1.f; S.oscale = 1.f; S.ldo = 4;
   return S;
+}
+
+// No-grad value chain through the fused kernel: sdf (and optionally the features), nothing saved.
+static void sdf_chain_value_launch(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, const float* x, long long M,
+                                   float* sdf_out, float* feat_out, float out_sign, const SdfImgs& im, cudaStream_t st) {
+  const int L = p.L;
+  const float rsqrt2 = 0.70710678118654752440f;
+  SdfChainArgs g;
+  memset(&g, 0, sizeof(g));
+  double flops = 2.0 * (double)M * p.in[L];
+  int ns = 0;
+  for (int l = 0; l < L; l++) {
+    SdfStep S = sdf_step(SC_SOFTPLUS, im.F[l], l == 0 ? 1 : cdiv(p.in[l], TC_BK), p.out[l], 0);
+    S.bias = w + p.boff[l]; S.bias_slot = l;
+    S.src = l == 0 ? SRC_PE : SRC_CHAIN;
+    if (l + 1 == p.skip) { S.oscale = rsqrt2; S.append = 1; }
+    if (l == L - 1) S.dot = 1;
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * p.in[l] * p.out[l];
+  }
+  if (feat_out) {
+    SdfStep S = sdf_step(SC_FEATQ, im.F[L], cdiv(p.in[L], TC_BK), c->d_out - 1, 0);
+    S.bias = w + p.boff[L] + 1; S.bias_slot = L;
+    S.out = feat_out; S.ldo = c->d_out - 1;
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * p.in[L] * (c->d_out - 1);
+  }
+  g.nsteps = ns;
+  g.gen = sdf_gen(c, x, nullptr); g.gen_t = g.gen;
+  g.rvec = w + p.woff[L]; g.b_last = w + p.boff[L];
+  g.sdf_out = sdf_out; g.sdf_scale = out_sign / c->scale;
+  g.beta = c->beta; g.M = M; g.dbg = 0;
+  sdf_chain_launch(g, flops, st);
 }
 
 // value chain. If bufs != nullptr activations go to bufs->H (saved) else ping-pong in scratch.
@@ -456,6 +496,11 @@ int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   if (p.img && !feat_out && sdf_fused_ok(p) && im.F[0]) {
     int rc = sdf_fused_launch(cfg, p, wpack, x, n, sdf_out, 1.f, im, st);
     if (rc) return rc;
+    FNEUS_CHECK_LAUNCH();
+    return FNEUS_OK;
+  }
+  if (feat_out && im.F[0] && im.F[p.L] && sdf_chain_ok(cfg, p)) {
+    sdf_chain_value_launch(cfg, p, wpack, x, n, sdf_out, feat_out, 1.f, im, st);
     FNEUS_CHECK_LAUNCH();
     return FNEUS_OK;
   }
@@ -570,7 +615,7 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
     g.pe_img = b.H[0];
     g.rvec = wpack + p.woff[L]; g.b_last = wpack + p.boff[L];
     g.sdf_out = sdf_out; g.sdf_scale = 1.f / cfg->scale;
-    g.beta = cfg->beta; g.M = M;
+    g.beta = cfg->beta; g.M = M; g.dbg = (tc_debug_flags() & 64) ? 1 : 0;
     sdf_chain_launch(g, flops, st);
     FNEUS_CHECK_LAUNCH();
     return FNEUS_OK;
@@ -677,7 +722,7 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     g.mem = d_feat; g.ldm = cfg->d_out - 1; g.kmem = cfg->d_out - 1;
     g.rvec = wpack + p.woff[L]; g.b_last = wpack + p.boff[L];
     g.rs = d_sdf; g.rscale = 1.f / cfg->scale;
-    g.beta = cfg->beta; g.M = M;
+    g.beta = cfg->beta; g.M = M; g.dbg = (tc_debug_flags() & 64) ? 1 : 0;
     sdf_chain_launch(g, flops, st);
     // weight gradients: dW_l += q_l^T gbar_l + abar_l^T h_l, db_l += colsum abar_l ; last linear: features and row 0
     WgradGroup wg;

@@ -58,8 +58,13 @@ struct SdfChainArgs {
   float sdf_scale;      // out_sign / scale
   const float* rs;      // SDFBWD with use_rs: d_sdf [M]
   float rscale, beta;
+  int dbg;              // record the debug timeline (CTA 0)
   long long M;
 };
+// debug timeline (fneus_debug_flags bit 6): clock64 stamps of CTA 0's first epilogue thread and MMA thread
+__device__ unsigned long long g_sc_dbg[8192];
+#define SC_STAMP(slot) do { if (dbg_on) { g_sc_dbg[dbg_i] = ((unsigned long long)(slot) << 56) | (clock64() & 0x00FFFFFFFFFFFFFFull); dbg_i = dbg_i < 8190 ? dbg_i + 1 : dbg_i; } } while (0)
+
 struct SCSmem {
   uint64_t wfull[SC_WSTAGES], wempty[SC_WSTAGES];
   uint64_t a_ready, acc_full, op_free, st_sync;
@@ -94,6 +99,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
       "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// Branch-free epilogue forms (results are consumed at BF16 precision):
+//   s(h)  = 1 - exp(-beta h)  = 1 - 2^(ksg h)             (saturates to 1 by itself; h >= 0)
+//   sp(v) = max(log2(1 + 2^(min(kz v, 43))) * kinv, v)    (softplus >= v, and equals v in FP32 beyond the clamp)
+__device__ __forceinline__ float sg_fast(float h, float ksg) { return 1.f - ex2_approx(h * ksg); }
+__device__ __forceinline__ float sp_fast(float v, float kz, float kinv) {
+  return fmaxf(lg2_approx(1.f + ex2_approx(fminf(v * kz, 43.f))) * kinv, v);
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
@@ -259,6 +271,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float beta = g.beta, inv_beta = 1.f / g.beta;
     int lg = 0, c = 0, nfree = 0;                  // nfree: op_free phases consumed
+    const bool dbg_on = g.dbg != 0 && blockIdx.x == 0 && et == 0;
+    int dbg_i = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long m = tile * 128 + r;
       const bool valid = m < g.M;
@@ -318,13 +332,19 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
         const int N = S.N, Nc = (N + 15) & ~15, mode = S.mode;
         const int nb = sdf_step_blocks(S);
         const float* sb = sbias + (S.bias_slot >= 0 ? S.bias_slot : 0) * 256;
-        const float hscale = S.hscale, oscale = S.oscale;
+        const float oscale = S.oscale;
+        const float ksg = -beta * S.hscale * 1.4426950408889634f;       // s(h) = 1 - 2^(ksg h)
+        const float kz = beta * 1.4426950408889634f, kinv = 0.6931471805599453f * inv_beta;
+        const int lim = (mode == SC_SPMUL || mode == SC_SDFBWD) ? S.csplit : N;
         const float rsv = (mode == SC_SDFBWD && S.use_rs && valid) ? __ldg(g.rs + m) * g.rscale : 0.f;
         float dot = 0.f;
 
+        SC_STAMP(1);
         mbar_wait(&ctl->acc_full, lg & 1);
         tc_fence_after();
+        SC_STAMP(2);
         if (S.src == SRC_CHAIN && !first_overall) { mbar_wait(&ctl->op_free, nfree & 1); nfree++; }
+        SC_STAMP(3);
 
 #pragma unroll 1
         for (int b = 0; b < nb; b++, c++) {
@@ -333,7 +353,10 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           uint8_t* opb = sOp + b * TC_A_BYTES + rowoff;                    // the row inside operand block b
           uint8_t* hb = sAux + (2 * slot) * TC_A_BYTES + rowoff;           // ... inside the slot's h block
           const uint8_t* qb = sAux + (2 * slot + 1) * TC_A_BYTES + rowoff; // ... inside the slot's q block
+          SC_STAMP(4);
           mbar_wait(&ctl->aux_full[slot], (c >> 1) & 1);
+          SC_STAMP(5);
+          const bool full = valid && n + 16 <= lim;                        // no per-element masks needed
           float a[16];
           if (n < Nc) tmem_ld16(taddr + n, a);
           else {
@@ -341,18 +364,24 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
             for (int j = 0; j < 16; j++) a[j] = 0.f;
           }
           if (mode == SC_SOFTPLUS) {
-            float qv[16];
+            if (S.dot) {
+              float qv[16];
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-              float v = softplus_beta_fast(a[j] + sb[n + j], beta, inv_beta);
-              v = (valid && n + j < N) ? v : 0.f;
-              if (S.dot) {
-                dot += v * srvec[n + j];
-                qv[j] = softplus_grad_from_act_fast(v, beta) * srvec[n + j];   // q_{L-1} from the unrounded activation
+              for (int j = 0; j < 16; j++) {
+                float v = sp_fast(a[j] + sb[n + j], kz, kinv);
+                v = (valid && n + j < N) ? v : 0.f;
+                dot = fmaf(v, srvec[n + j], dot);
+                qv[j] = sg_fast(v, ksg) * srvec[n + j];                          // q_{L-1} from the unrounded activation
+                a[j] = v * oscale;
               }
-              a[j] = v * oscale;
+              tmem_st16(taddr + 256 + n, qv);                                    // waits in the spare TMEM columns
+            } else if (full) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) a[j] = sp_fast(a[j] + sb[n + j], kz, kinv) * oscale;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? sp_fast(a[j] + sb[n + j], kz, kinv) * oscale : 0.f;
             }
-            if (S.dot) tmem_st16(taddr + 256 + n, qv);                         // waits in the spare TMEM columns
           } else if (mode == SC_FEATQ) {
             // features: FP32 through a swizzled [128][64] staging tile (the slot's 32 KB), written out as whole lines
             float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
@@ -376,10 +405,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
             for (int hf = 0; hf < 2; hf++) {
               float hv[8];
               bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
+              if (full) {
 #pragma unroll
-              for (int j = 0; j < 8; j++) {
-                const float sg = softplus_grad_from_act_fast(hv[j] * hscale, beta);
-                a[hf * 8 + j] = (valid && n + hf * 8 + j < S.csplit) ? sg * a[hf * 8 + j] * oscale : 0.f;
+                for (int j = 0; j < 8; j++) a[hf * 8 + j] = sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                  a[hf * 8 + j] = (valid && n + hf * 8 + j < S.csplit) ? sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale : 0.f;
               }
             }
           } else if (mode == SC_G0) {
@@ -415,11 +447,16 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
               bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);
 #pragma unroll
               for (int j = 0; j < 8; j++) {
-                const float sg = softplus_grad_from_act_fast(hv[j] * hscale, beta);
-                const bool ok = valid && n + hf * 8 + j < N;
+                const float sg = sg_fast(hv[j], ksg);
                 const float acc = a[hf * 8 + j];
-                a[hf * 8 + j] = ok ? sg * acc * oscale : 0.f;
-                e[j] = ok ? beta * (1.f - sg) * qv[j] * acc : 0.f;
+                const float yv = sg * acc * oscale;
+                const float ev = fmaf(-beta, sg, beta) * qv[j] * acc;
+                if (full) { a[hf * 8 + j] = yv; e[j] = ev; }
+                else {
+                  const bool ok = valid && n + hf * 8 + j < N;
+                  a[hf * 8 + j] = ok ? yv : 0.f;
+                  e[j] = ok ? ev : 0.f;
+                }
               }
               *reinterpret_cast<uint4*>(hb + (hf ? ch1 : ch0)) = f32x8_to_bf16(e);   // e_l leaves from where h_{l+1} arrived
             }
@@ -431,9 +468,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
               bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);
 #pragma unroll
               for (int j = 0; j < 8; j++) {
-                const float sg = softplus_grad_from_act_fast(hv[j] * hscale, beta);
                 const int nn = n + hf * 8 + j;
-                a[hf * 8 + j] = (valid && nn < S.csplit) ? sg * (a[hf * 8 + j] + rsv * srvec[nn]) * oscale + qv[j] : 0.f;
+                const float yv = fmaf(sg_fast(hv[j], ksg) * oscale, fmaf(rsv, srvec[nn], a[hf * 8 + j]), qv[j]);
+                a[hf * 8 + j] = (full || (valid && nn < S.csplit)) ? yv : 0.f;
               }
             }
           }
@@ -499,6 +536,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(&ctl->blk_done[slot]);
+          SC_STAMP(6);
         }
         if (S.dot) {
           // sdf = h_L . W_L[0] + b: the four column groups of a row meet in shared memory
@@ -513,8 +551,10 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           fence_proxy_async();
           mbar_arrive(&ctl->a_ready);
         }
+        SC_STAMP(7);
       }
     }
+    if (dbg_on) g_sc_dbg[8191] = dbg_i;
   }
   __syncthreads();
   if (warp == 0) {

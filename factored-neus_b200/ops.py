@@ -516,3 +516,74 @@ class Composite(torch.autograd.Function):
         d_inv_s = d_inv.sum().reshape(s_inv)
         return (d_sdf.reshape(s_sdf), d_nrm.reshape(s_nrm), d_rgb.reshape(s_rgb), d_inv_s, d_bga, d_bgc,
                 None, None, None, None, None, None, None)
+
+
+class SurfaceBlend(torch.autograd.Function):
+    """renderer.py:328-343 for the three RefColor outputs at once: c_* [2B,3] (rows 2b, 2b+1), w_pair [B,2],
+    hit_idx [B] int32 -> three [B,3] colours (ones where the ray has no sign change)."""
+
+    @staticmethod
+    def forward(ctx, c_rgb, c_spec, c_diff, w_pair, hit_idx):
+        _need_cuda(c_rgb, "c_rgb")
+        cr, cs, cd, w = _f32c(c_rgb), _f32c(c_spec), _f32c(c_diff), _f32c(w_pair)
+        B = w.shape[0]
+        outs = [torch.empty(B, 3, dtype=torch.float32, device=w.device) for _ in range(3)]
+        L.check(L.lib().fneus_surface_blend_fwd(L.ptr(cr), L.ptr(cs), L.ptr(cd), L.ptr(w), L.ptr(hit_idx), B,
+                                                L.ptr(outs[0]), L.ptr(outs[1]), L.ptr(outs[2]), L.stream_ptr()),
+                "fneus_surface_blend_fwd")
+        ctx.save_for_backward(cr, cs, cd, w, hit_idx)
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_spec, g_diff):
+        cr, cs, cd, w, hit_idx = ctx.saved_tensors
+        B = w.shape[0]
+        ds = [torch.empty_like(cr), torch.empty_like(cs), torch.empty_like(cd)]
+        dw = torch.empty_like(w)
+        L.check(L.lib().fneus_surface_blend_bwd(L.ptr(cr), L.ptr(cs), L.ptr(cd), L.ptr(w), L.ptr(hit_idx), B,
+                                                L.ptr(_f32c(g_rgb)), L.ptr(_f32c(g_spec)), L.ptr(_f32c(g_diff)),
+                                                L.ptr(ds[0]), L.ptr(ds[1]), L.ptr(ds[2]), L.ptr(dw), L.stream_ptr()),
+                "fneus_surface_blend_bwd")
+        return ds[0], ds[1], ds[2], dw, None
+
+
+def loss_norms(mask, hit_idx, eik_den, use_mask):
+    """den4 = [sum mask, sum mask*hit, eik_den, n_rays] (exp_runner.py:146,160; renderer.py:372)."""
+    _need_cuda(mask, "mask")
+    m = _f32c(mask).reshape(-1)
+    den = torch.empty(4, dtype=torch.float32, device=m.device)
+    L.check(L.lib().fneus_loss_norms(L.ptr(m), L.ptr(hit_idx), L.ptr(_f32c(eik_den).reshape(1)), m.shape[0],
+                                     1 if use_mask else 0, L.ptr(den), L.stream_ptr()), "fneus_loss_norms")
+    return den
+
+
+class Stage1Loss(torch.autograd.Function):
+    """exp_runner.py:134-177 in one launch: returns parts5 = [loss, color, surface, eikonal, mask]; gradients flow to
+    color_fine, surface_color, weight_sum and eik_num through parts5[0] only."""
+
+    @staticmethod
+    def forward(ctx, color, surf, wsum, eik_num, true_rgb, mask, hit_idx, den4, use_mask, sw, iw, mw):
+        _need_cuda(color, "color_fine")
+        c, s_, w = _f32c(color), _f32c(surf), _f32c(wsum).reshape(-1)
+        e = _f32c(eik_num).reshape(1)
+        t, m = _f32c(true_rgb), _f32c(mask).reshape(-1)
+        B = c.shape[0]
+        parts = torch.empty(5, dtype=torch.float32, device=c.device)
+        dc, ds, dw = torch.empty_like(c), torch.empty_like(s_), torch.empty_like(w)
+        de = torch.empty(1, dtype=torch.float32, device=c.device)
+        L.check(L.lib().fneus_stage1_loss(L.ptr(c), L.ptr(s_), L.ptr(w), L.ptr(t), L.ptr(m), L.ptr(hit_idx), L.ptr(e),
+                                          L.ptr(den4), B, 1 if use_mask else 0, float(sw), float(iw), float(mw),
+                                          L.ptr(parts), L.ptr(dc), L.ptr(ds), L.ptr(dw), L.ptr(de), L.stream_ptr()),
+                "fneus_stage1_loss")
+        ctx.save_for_backward(dc, ds, dw, de)
+        ctx.shapes = (color.shape, surf.shape, wsum.shape, eik_num.shape)
+        return parts
+
+    @staticmethod
+    def backward(ctx, g_parts):
+        dc, ds, dw, de = ctx.saved_tensors
+        g = g_parts[0]
+        sc, ss, sw_, se = ctx.shapes
+        return ((dc * g).reshape(sc), (ds * g).reshape(ss), (dw * g).reshape(sw_), (de * g).reshape(se),
+                None, None, None, None, None, None, None, None)

@@ -27,10 +27,23 @@ def stage1_loss_sharded(renderer, out, true_rgb, mask, surface_weight=0.1, igr_w
     """exp_runner.py:134-177 on a ray shard with batch-global normalisers.  Returns (loss_local, stats): the
     SUM over ranks of loss_local is the reference's full-batch loss."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    eik_num, eik_den = renderer.last_eikonal_parts
+    if out["color_fine"].is_cuda:
+        # product path: normalisers, then loss + gradients, one launch each (csrc/loss.cu)
+        from . import ops
+        hit_idx = renderer.last_hit_idx
+        use_mask = mask_weight > 0.0
+        den = ops.loss_norms(mask, hit_idx, eik_den.detach(), use_mask)
+        if world > 1:
+            dist.all_reduce(den, group=group)
+        parts = ops.Stage1Loss.apply(out["color_fine"], out["surface_color"], out["weight_sum"], eik_num, true_rgb, mask,
+                                     hit_idx, den, use_mask, surface_weight, igr_weight, mask_weight)
+        stats = parts.detach()
+        return parts[0], dict(color_loss=stats[1], surface_loss=stats[2], eikonal=stats[3], mask_loss=stats[4])
+    # host-logic path (CPU tensors: the gloo world_size-2 test of the sharding arithmetic)
     mask = (mask > 0.5).to(true_rgb.dtype) if mask_weight > 0.0 else torch.ones_like(mask)
     hit = out["sdf_mask"]
     hit_f = hit.to(true_rgb.dtype)[:, None]
-    eik_num, eik_den = renderer.last_eikonal_parts
     n_local = mask.new_full((), float(mask.shape[0]))          # fill kernel: CUDA-graph capturable
     den = torch.stack([mask.sum(), (mask * hit_f).sum(), eik_den.detach(), n_local])
     if world > 1:

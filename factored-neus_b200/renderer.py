@@ -104,17 +104,13 @@ class NeuSRenderer:
         base = torch.arange(B, device=dev) * n
         rows = torch.stack([base + idx - 1, base + idx], dim=1).reshape(-1)                      # [2B]
         r_rgb, r_spec, r_diff = self._ref_rows(refColor_network, pts, feat, dirs, normals, rows)
-        w0, w1 = w_pair[:, :1], w_pair[:, 1:]
-        den = w0 + w1
-        ones = torch.ones(B, 3, device=dev)
-
-        def blend(c):
-            c = c.reshape(B, 2, 3)
-            return torch.where(hit[:, None], (c[:, 0] * w0 + c[:, 1] * w1) / den, ones)
+        surf_rgb, surf_spec, surf_diff = ops.SurfaceBlend.apply(r_rgb, r_spec, r_diff, w_pair, hit_idx)
+        self.last_hit_idx = hit_idx
+        self.last_weight_sum = wsum
 
         return {
             "color": color,
-            "surface_color": blend(r_rgb),
+            "surface_color": surf_rgb,
             "sdf_mask": hit,
             "sdf": sdf,
             "dists": dists,
@@ -125,8 +121,9 @@ class NeuSRenderer:
             "cdf": cdf,
             "gradient_error": grad_err,
             "inside_sphere": inside,
-            "specular_color": blend(r_spec),
-            "diffuse_color": blend(r_diff),
+            "weight_sum": wsum,
+            "specular_color": surf_spec,
+            "diffuse_color": surf_diff,
         }
 
     @staticmethod
@@ -193,7 +190,7 @@ class NeuSRenderer:
             "sdf_mask": ret_fine["sdf_mask"],
             "s_val": s_val,
             "cdf_fine": ret_fine["cdf"],
-            "weight_sum": weights.sum(dim=-1, keepdim=True),
+            "weight_sum": ret_fine["weight_sum"],
             "weight_max": torch.max(weights, dim=-1, keepdim=True)[0],
             "gradients": ret_fine["gradients"],
             "weights": weights,

@@ -43,6 +43,8 @@ int fneus_set_precision(int mode);
 int fneus_get_precision(void);
 /* Bisect switches of the persistent tensor-core kernel (profiling only; results are wrong when non-zero). */
 int fneus_debug_flags(int flags);
+/* debug: copy the first n entries (n <= 8192) of the fused-chain timeline buffer (clock stamps, flag bit 6) */
+int fneus_debug_timeline(unsigned long long* host_dst, int n);
 /* Test hook: one raw dense-layer contraction in the current precision mode.  kind 0: C[M,N] = A[M,K] W[N,K]^T
  * + bias; kind 1: C[M,N] = A[M,K] W[K,N]; kind 2: C[N,K] += Y[M,N]^T A[M,K], bias[N] += colsum(Y) (W := Y). */
 int fneus_debug_gemm(int kind, const float* A, int lda, const float* W, int ldw, float* bias, long long M, int N,
@@ -249,6 +251,26 @@ int fneus_composite_bwd(const float* sdf, const float* normals, const float* rgb
                         const float* d_weights, const float* d_weight_sum, const float* d_w_pair,
                         const float* d_eik, const float* eik_denom, float* d_sdf, float* d_normals,
                         float* d_rgb, float* d_inv_s, float* d_bg_alpha, float* d_bg_color, void* stream);
+
+/* ---- per-ray tail of the training step ----------------------------------------------------------------------------
+ * Surface-colour blend of the two bracketing RefColor evaluations per ray (renderer.py:328-343): c_* are [2B,3]
+ * (rows 2b, 2b+1), w_pair [B,2], hit_idx [B] (< 0: no sign change -> ones).  Backward: g_* may be NULL (no gradient). */
+int fneus_surface_blend_fwd(const float* c_rgb, const float* c_spec, const float* c_diff, const float* w_pair,
+                            const int* hit_idx, long long n_rays, float* o_rgb, float* o_spec, float* o_diff,
+                            void* stream);
+int fneus_surface_blend_bwd(const float* c_rgb, const float* c_spec, const float* c_diff, const float* w_pair,
+                            const int* hit_idx, long long n_rays, const float* g_rgb, const float* g_spec,
+                            const float* g_diff, float* d_rgb, float* d_spec, float* d_diff, float* d_w_pair,
+                            void* stream);
+/* Stage-1 loss (exp_runner.py:134-177) on a ray shard.  fneus_loss_norms writes den4 = [sum mask, sum mask*hit,
+ * eik_den, n_rays] (all-reduce it across ray shards before the next call); fneus_stage1_loss writes
+ * parts5 = [loss, color, surface, eikonal, mask] and d loss / d (color_fine, surface_color, weight_sum, eik_num). */
+int fneus_loss_norms(const float* mask, const int* hit_idx, const float* eik_den, long long n_rays, int use_mask,
+                     float* den4, void* stream);
+int fneus_stage1_loss(const float* color, const float* surface_color, const float* weight_sum, const float* true_rgb,
+                      const float* mask, const int* hit_idx, const float* eik_num, const float* den4, long long n_rays,
+                      int use_mask, float surface_weight, float igr_weight, float mask_weight, float* parts5,
+                      float* d_color, float* d_surface_color, float* d_weight_sum, float* d_eik_num, void* stream);
 
 #ifdef __cplusplus
 }

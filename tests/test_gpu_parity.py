@@ -469,3 +469,53 @@ def test_stage2_networks_fwd_bwd(golden_dir, N):
     for mod, P, tag in ((lv, Pl, "lvis"), (il, Pi, "indi")):
         for name, p in mod.named_parameters():
             assert_close(p.grad, P[name].grad, 1e-4, "grad %s.%s" % (tag, name), rtol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,use_mask", [(512, True), (37, True), (300, False)])
+def test_fused_loss_and_surface_blend(B, use_mask):
+    """csrc/loss.cu vs the plain torch restatement (oracle stage1_loss, renderer.py:328-343 blend): values and
+    gradients, FP32 <= 1e-5."""
+    from factored_neus_b200.parallel import stage1_loss_sharded
+    rs = np.random.RandomState(B)
+    f = lambda *s: torch.from_numpy(rs.uniform(0.02, 0.98, s).astype(np.float32))
+    c2 = [f(2 * B, 3) for _ in range(3)]
+    w_pair = f(B, 2)
+    hit_idx = torch.from_numpy(np.where(rs.uniform(size=B) < 0.7, rs.randint(1, 127, B), -1).astype(np.int32))
+    color, wsum, true_rgb = f(B, 3), f(B, 1) * 1.05, f(B, 3)
+    wsum[::7] = 1e-4                                     # outside the BCE clip
+    mask = (torch.from_numpy(rs.uniform(size=(B, 1)).astype(np.float32)) > 0.3).float()
+    eik_num, eik_den = torch.tensor(3.7), torch.tensor(41.0)
+    mw = 0.1 if use_mask else 0.0
+
+    def run(dev):
+        leaves = [t.clone().to(dev).requires_grad_(True) for t in c2 + [w_pair, color, wsum, eik_num]]
+        cr, cs, cd, wp, col, ws, en = leaves
+        hit = (hit_idx >= 0).to(dev)
+        if dev == "cpu":
+            w0, w1 = wp[:, :1], wp[:, 1:]
+            blend = lambda c: torch.where(hit[:, None], (c.reshape(B, 2, 3)[:, 0] * w0 + c.reshape(B, 2, 3)[:, 1] * w1)
+                                          / (w0 + w1), torch.ones(B, 3))
+            s_rgb, s_spec, s_diff = blend(cr), blend(cs), blend(cd)
+        else:
+            s_rgb, s_spec, s_diff = ops.SurfaceBlend.apply(cr, cs, cd, wp, hit_idx.to(dev))
+
+        class R:
+            pass
+        R.last_eikonal_parts = (en, eik_den.to(dev))
+        R.last_hit_idx = hit_idx.to(dev)
+        out = dict(color_fine=col, surface_color=s_rgb, weight_sum=ws, sdf_mask=hit)
+        loss, stats = stage1_loss_sharded(R, out, true_rgb.to(dev), mask.to(dev), 0.1, 0.1, mw)
+        (loss + 0.3 * (s_spec * s_spec).sum() + 0.2 * s_diff.sum()).backward()
+        return loss, stats, [s_rgb, s_spec, s_diff], [t.grad for t in leaves]
+
+    l_ref, st_ref, s_ref, g_ref = run("cpu")
+    l_got, st_got, s_got, g_got = run(DEV)
+    assert abs(l_ref.item() - l_got.item()) <= 1e-5 * max(1.0, abs(l_ref.item()))
+    for k in st_ref:
+        assert abs(float(st_ref[k]) - float(st_got[k])) <= 1e-5 * max(1.0, abs(float(st_ref[k]))), k
+    for a, b in zip(s_got, s_ref):
+        assert_close(a, b.detach(), 1e-5, "surface blend")
+    names = ["c_rgb", "c_spec", "c_diff", "w_pair", "color", "weight_sum", "eik_num"]
+    for n_, a, b in zip(names, g_got, g_ref):
+        assert_close(a, b, 1e-5, "grad " + n_, rtol=1e-4)

@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Per-step timeline of the fused SDF chain kernels (CTA 0, first epilogue thread), from the clock stamps the kernel
+records under debug flag bit 6.  Usage (GPU box):  python tools/timeline_sdf.py [N]"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import factored_neus_b200 as fn  # noqa: E402
+
+syn = fn.synthetic
+
+
+def read_timeline(lib):
+    buf = (ctypes.c_ulonglong * 8192)()
+    fn._lib.check(lib.fneus_debug_timeline(ctypes.cast(buf, ctypes.c_void_p), 8192), "timeline")
+    a = np.frombuffer(buf, dtype=np.uint64).copy()
+    n = int(a[8191])
+    return [(int(v >> np.uint64(56)), int(v & np.uint64((1 << 56) - 1))) for v in a[:n]]
+
+
+def report(tag, tl, mhz=1965.0):
+    print("== %s: %d stamps" % (tag, len(tl)))
+    if not tl:
+        return
+    t0 = tl[0][1]
+    step, rows, cur = 0, [], None
+    for kind, t in tl:
+        us = (t - t0) / mhz
+        if kind == 1:
+            cur = {"start": us, "aux_wait": 0.0, "blk": 0.0, "nblk": 0}
+        elif kind == 2:
+            cur["acc"] = us
+        elif kind == 3:
+            cur["opfree"] = us
+        elif kind == 4:
+            cur["t4"] = us
+        elif kind == 5:
+            cur["aux_wait"] += us - cur["t4"]
+            cur["t5"] = us
+        elif kind == 6:
+            cur["blk"] += us - cur["t5"]
+            cur["nblk"] += 1
+        elif kind == 7:
+            cur["end"] = us
+            rows.append(cur)
+    print(" step   start   wait_mma  wait_opfree  wait_aux  compute   total")
+    for i, r in enumerate(rows[:40]):
+        print("  %2d  %7.2f   %7.2f    %7.2f    %7.2f  %7.2f  %7.2f" % (
+            i, r["start"], r["acc"] - r["start"], r["opfree"] - r["acc"], r["aux_wait"], r["blk"], r["end"] - r["start"]))
+    tot = rows[-1]["end"] - rows[0]["start"]
+    print(" %d steps in %.1f us: wait_mma %.1f, wait_opfree %.1f, wait_aux %.1f, compute %.1f" % (
+        len(rows), tot, sum(r["acc"] - r["start"] for r in rows), sum(r["opfree"] - r["acc"] for r in rows),
+        sum(r["aux_wait"] for r in rows), sum(r["blk"] for r in rows)))
+
+
+def main():
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+    dev = "cuda:0"
+    fn.ops.set_precision("bf16")
+    lib = fn._lib.lib()
+    sdf = fn.SDFNetwork(**syn.SDF_CONF)
+    sdf.load_state_dict(syn.sdf_state(4, syn.SDF_CONF, 0.03))
+    sdf = sdf.to(dev)
+    x = (torch.rand(N, 3, device=dev) * 2 - 1)
+    for it in range(2):
+        lib.fneus_debug_flags(64 if it == 1 else 0)
+        s, f, n = sdf.value_feature_normal(x, want_normal=True)
+        torch.cuda.synchronize()
+        if it == 1:
+            report("forward (value + gradient chain)", read_timeline(lib))
+        (s.sum() + f.sum() * 0.01 + n.sum()).backward()
+        torch.cuda.synchronize()
+        if it == 1:
+            report("backward (sweep + value path)", read_timeline(lib))
+    lib.fneus_debug_flags(0)
+
+
+if __name__ == "__main__":
+    main()
