@@ -141,7 +141,7 @@ def run_ours(args):
     import torch.distributed as dist
     import factored_neus_b200 as fn
     from factored_neus_b200 import _lib as L
-    from factored_neus_b200.parallel import GradBucket, stage1_loss_sharded
+    from factored_neus_b200.parallel import FlatAdam, GradBucket, stage1_loss_sharded
     syn = fn.synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,7 +162,8 @@ def run_ours(args):
                         color_network=nets[2], refColor_network=nets[3])
     params = [p for n in nets for p in n.parameters()]
     bucket = GradBucket(params)
-    opt = torch.optim.Adam(params, lr=5e-4, fused=True, capturable=True)
+    opt = FlatAdam(bucket, lr=5e-4, warm_up_end=5000, end_iter=300000)   # fused flat Adam + on-device LR schedule
+    opt.set_iteration(5000)                                              # past the warm-up: full learning rate
 
     o, d, near, far = syn.make_rays(B, seed=1 + rank)
     true_rgb, mask = syn.make_targets(B, seed=100 + rank)
@@ -177,10 +178,9 @@ def run_ours(args):
         mid = 0.5 * (-b) / a                                                # dataset.near_far_from_sphere
         out = R.render(ro, rd, mid - 1.0, mid + 1.0, cos_anneal_ratio=1.0)
         loss, _ = stage1_loss_sharded(R, out, rgb, m, SURFACE_W, IGR_W, MASK_W)
-        bucket.zero()
         loss.backward()
         bucket.all_reduce()
-        opt.step()
+        opt.step()                                                          # also clears the gradient bucket
         return loss
 
     lib = L.lib()

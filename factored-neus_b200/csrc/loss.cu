@@ -136,6 +136,52 @@ __global__ void stage1_loss_kernel(const float* __restrict__ color, const float*
   }
 }
 
+
+// ---- optimiser of the stage-1 step: torch.optim.Adam (exp_runner.py:118, default betas / eps, no weight decay) over ONE
+// flat FP32 parameter buffer, with the reference's warm-up / cosine learning-rate factor (exp_runner.py:229-238)
+// evaluated on the device from a device-resident iteration counter, so the step is CUDA-graph capturable without any
+// host-written scalar.  state4 = [iterations done, lr used by the last step, 1 - beta1^t, 1 - beta2^t].
+__global__ void adam_tick_kernel(float* __restrict__ state4, float base_lr, float lr_alpha, float warm_up_end,
+                                 float end_iter, float beta1, float beta2) {
+  const float it = state4[0];
+  float f;
+  if (it < warm_up_end) f = it / warm_up_end;
+  else {
+    const float prog = (it - warm_up_end) / fmaxf(1.f, end_iter - warm_up_end);
+    f = (cospif(prog) + 1.f) * 0.5f * (1.f - lr_alpha) + lr_alpha;
+  }
+  const float t = it + 1.f;
+  state4[0] = t;
+  state4[1] = base_lr * f;
+  state4[2] = 1.f - powf(beta1, t);
+  state4[3] = 1.f - powf(beta2, t);
+}
+__global__ void adam_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n4, long long n, const float* __restrict__ state4,
+                                 float beta1, float beta2, float eps, float gscale, int zero_grad) {
+  const float lr = state4[1], bc1 = state4[2], bc2 = state4[3];
+  const float step_size = lr / bc1, rsq_bc2 = 1.f / sqrtf(bc2);
+  auto upd = [&](float& pp, float& gg, float& mm, float& vv) {
+    const float gr = gg * gscale;
+    mm = beta1 * mm + (1.f - beta1) * gr;
+    vv = beta2 * vv + (1.f - beta2) * gr * gr;
+    pp -= step_size * (mm / (sqrtf(vv) * rsq_bc2 + eps));
+    if (zero_grad) gg = 0.f;
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<float4*>(g)[i];
+    float4 Mv = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    upd(P.x, G.x, Mv.x, V.x); upd(P.y, G.y, Mv.y, V.y); upd(P.z, G.z, Mv.z, V.z); upd(P.w, G.w, Mv.w, V.w);
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = Mv;
+    reinterpret_cast<float4*>(v)[i] = V;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = G;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    upd(p[i], g[i], m[i], v[i]);
+}
+
 }  // namespace fneus
 
 using namespace fneus;
@@ -198,6 +244,29 @@ int fneus_stage1_loss(const float* color, const float* surface_color, const floa
   stage1_loss_kernel<<<1, 1024, 0, st>>>(color, surface_color, weight_sum, true_rgb, mask, hit_idx, eik_num, den4, (int)B,
                                          use_mask, surface_weight, igr_weight, mask_weight, parts5, d_color,
                                          d_surface_color, d_weight_sum, d_eik_num);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_adam_step(float* p, float* g, float* m, float* v, long long n, float* state4, float base_lr, float lr_alpha,
+                    float warm_up_end, float end_iter, float beta1, float beta2, float eps, float grad_scale,
+                    int zero_grad, void* stream) {
+  if (n == 0) return FNEUS_OK;
+  if (!p || !g || !m || !v || !state4) return FNEUS_ERR_NULL;
+  if (n < 0) return FNEUS_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return FNEUS_ERR_MISALIGNED;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  adam_tick_kernel<<<1, 1, 0, st>>>(state4, base_lr, lr_alpha, warm_up_end, end_iter, beta1, beta2);
+  prof_end(st);
+  const long long n4 = n / 4;
+  long long blocks = cdiv(n4 > 0 ? n4 : 1, 256);
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  prof_begin(PC_ELEMENTWISE, 0.0, 32.0 * (double)n, st);
+  adam_step_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n4, n, state4, beta1, beta2, eps, grad_scale, zero_grad);
   prof_end(st);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;

@@ -13,11 +13,16 @@
 // auxiliary activation blocks (h_l, q_l / e_l, 128 rows x 64 columns = 16 KB) arrive by bulk copies into rings,
 // results leave as bulk stores of the operand blocks themselves (their bytes ARE the activation image) and of the
 // auxiliary blocks rewritten in place (e_l over h_l).  FP32 row-major outputs (features) are transposed through
-// shared memory and written as whole lines.  q_{L-1} and the positional-encoding part of the skip gradient wait in
-// the 256 spare TMEM columns instead of HBM.
+// shared memory and written as whole lines.  The positional-encoding part of the skip gradient waits in shared
+// memory instead of HBM; q_{L-1} is rebuilt from the pre-activations of layer L-1 still held in TMEM.
 //
-//   warp 0      : MMA issuer (+ TMEM alloc: 256 accumulator columns + 256 spare)
-//   warp 1      : weight-image loader, ring of 5 half-tiles (128 output columns x 64 reduction, 16 KB)
+// Software pipeline: TMEM holds TWO 256-column accumulators.  The epilogue of step s publishes the next operand one
+// 64-column block at a time (a_ready[b]); the MMA issuer starts step s+1 on block 0 into the other accumulator while
+// the epilogue of step s is still working on blocks 1..3, so the tensor pipe runs underneath the epilogue and only
+// the last quarter of a step's MMAs is exposed.
+//
+//   warp 0      : MMA issuer (+ TMEM alloc: 2 x 256 accumulator columns)
+//   warp 1      : weight-image loader, ring of 4 half-tiles (128 output columns x 64 reduction, 16 KB)
 //   warp 2      : auxiliary-block loader (2 slots of h + q blocks)
 //   warp 3      : storer: bulk shared->global of finished blocks, releases the slots
 //   warps 4-19  : epilogue, thread = one row (TMEM lane) x one of four 16-column groups per 64-column block
@@ -26,7 +31,7 @@
 
 namespace fneus {
 
-constexpr int SC_THREADS = 640, SC_WSTAGES = 5, SC_MAXS = 20, SC_BIAS_SLOTS = 10, SC_EPI_THREADS = 512;
+constexpr int SC_THREADS = 640, SC_WSTAGES = 4, SC_MAXS = 20, SC_BIAS_SLOTS = 10, SC_EPI_THREADS = 512;
 enum SdfStepMode { SC_SOFTPLUS = 0, SC_FEATQ, SC_SPMUL, SC_G0, SC_SWEEP, SC_SDFBWD };
 enum SdfStepSrc { SRC_CHAIN = 0, SRC_PE, SRC_TAN, SRC_MEM };
 
@@ -67,14 +72,15 @@ __device__ unsigned long long g_sc_dbg[8192];
 
 struct SCSmem {
   uint64_t wfull[SC_WSTAGES], wempty[SC_WSTAGES];
-  uint64_t a_ready, acc_full, op_free, st_sync;
+  uint64_t a_ready[4], acc_full, op_free, st_sync;
   uint64_t aux_full[2], aux_empty[2], blk_done[2];
   uint32_t tmem_base;
 };
 constexpr int SC_OP_BYTES = 4 * TC_A_BYTES;                      // operand: 128 rows x 256 columns BF16
 constexpr int SC_AUX_BYTES = 4 * TC_A_BYTES;                     // 2 slots x (h block + q block)
+constexpr int SC_PARK_LD = 41;                                   // odd row stride: thread-per-row accesses hit 32 banks
 constexpr int SC_SMEM_BYTES = SC_OP_BYTES + SC_WSTAGES * CH_WBYTES + SC_AUX_BYTES +
-                              (SC_BIAS_SLOTS * 256 + 256 + 128) * 4 + 1024 + 256;
+                              (SC_BIAS_SLOTS * 256 + 256 + 128 + 128 * SC_PARK_LD) * 4 + 1024 + 256;
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float* out) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -121,7 +127,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
   float* sbias = reinterpret_cast<float*>(sAux + SC_AUX_BYTES);  // [SC_BIAS_SLOTS][256]
   float* srvec = sbias + SC_BIAS_SLOTS * 256;                    // [256]
   float* sdot = srvec + 256;                                     // [128]
-  SCSmem* ctl = reinterpret_cast<SCSmem*>(sdot + 128);
+  float* spark = sdot + 128;                                     // [128][SC_PARK_LD]: skip part of the input gradient
+  SCSmem* ctl = reinterpret_cast<SCSmem*>(spark + 128 * SC_PARK_LD);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ntiles = (g.M + 127) / 128;
@@ -130,7 +137,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < SC_WSTAGES; s++) { mbar_init(&ctl->wfull[s], 1); mbar_init(&ctl->wempty[s], 1); }
-    mbar_init(&ctl->a_ready, SC_EPI_THREADS);
+#pragma unroll
+    for (int i = 0; i < 4; i++) mbar_init(&ctl->a_ready[i], SC_EPI_THREADS);
     mbar_init(&ctl->acc_full, 1);
     mbar_init(&ctl->op_free, 1);
     mbar_init(&ctl->st_sync, 1);
@@ -184,9 +192,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
         for (int s = 0; s < g.nsteps; s++, lg++) {
           const SdfStep& S = g.st[s];
           const int Nc = (S.N + 15) & ~15;
-          mbar_wait(&ctl->a_ready, lg & 1);
-          tc_fence_after();
+          const uint32_t acc = tmem_base + (uint32_t)((lg & 1) << 8);
           for (int kb = 0; kb < S.KB; kb++) {
+            // operand block kb is ready as soon as the previous step's epilogue has written it: the MMAs of this
+            // step trail that epilogue block by block (its accumulator is the other TMEM buffer)
+            if (kb < 4) { mbar_wait(&ctl->a_ready[kb], lg & 1); tc_fence_after(); }
             for (int h = 0; h * 128 < Nc; h++, kbg++) {
               const int rows = min(128, Nc - h * 128);
               const uint32_t idesc = make_idesc(rows, 0, S.bmn);
@@ -198,11 +208,12 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
 #pragma unroll
               for (int k = 0; k < 4; k++) {
                 const uint64_t bd = S.bmn ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
-                umma_bf16(tmem_base + h * 128, make_desc(a_addr + k * 32, 16, 1024), bd, idesc, (kb > 0 || k > 0) ? 1 : 0);
+                umma_bf16(acc + h * 128, make_desc(a_addr + k * 32, 16, 1024), bd, idesc, (kb > 0 || k > 0) ? 1 : 0);
               }
               umma_commit(&ctl->wempty[stg]);
             }
           }
+          for (int kb = S.KB; kb < 4; kb++) mbar_wait(&ctl->a_ready[kb], lg & 1);   // keep the phases in step
           umma_commit(&ctl->acc_full);
         }
       }
@@ -326,7 +337,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           }
           tc_fence_before();
           fence_proxy_async();
-          mbar_arrive(&ctl->a_ready);
+#pragma unroll
+          for (int i = 0; i < 4; i++) mbar_arrive(&ctl->a_ready[i]);
         }
 
         const int N = S.N, Nc = (N + 15) & ~15, mode = S.mode;
@@ -338,6 +350,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
         const int lim = (mode == SC_SPMUL || mode == SC_SDFBWD) ? S.csplit : N;
         const float rsv = (mode == SC_SDFBWD && S.use_rs && valid) ? __ldg(g.rs + m) * g.rscale : 0.f;
         float dot = 0.f;
+        const uint32_t tacc = taddr + (uint32_t)((lg & 1) << 8);         // this step's accumulator buffer
+        const bool feeds_next = s + 1 < g.nsteps && g.st[s + 1].src == SRC_CHAIN;
+        const bool pub_blocks = feeds_next && S.mode != SC_FEATQ;        // publish the next operand block by block
 
         SC_STAMP(1);
         mbar_wait(&ctl->acc_full, lg & 1);
@@ -358,23 +373,20 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           SC_STAMP(5);
           const bool full = valid && n + 16 <= lim;                        // no per-element masks needed
           float a[16];
-          if (n < Nc) tmem_ld16(taddr + n, a);
+          if (n < Nc) tmem_ld16(tacc + n, a);
           else {
 #pragma unroll
             for (int j = 0; j < 16; j++) a[j] = 0.f;
           }
           if (mode == SC_SOFTPLUS) {
             if (S.dot) {
-              float qv[16];
 #pragma unroll
               for (int j = 0; j < 16; j++) {
                 float v = sp_fast(a[j] + sb[n + j], kz, kinv);
                 v = (valid && n + j < N) ? v : 0.f;
                 dot = fmaf(v, srvec[n + j], dot);
-                qv[j] = sg_fast(v, ksg) * srvec[n + j];                          // q_{L-1} from the unrounded activation
                 a[j] = v * oscale;
               }
-              tmem_st16(taddr + 256 + n, qv);                                    // waits in the spare TMEM columns
             } else if (full) {
 #pragma unroll
               for (int j = 0; j < 16; j++) a[j] = sp_fast(a[j] + sb[n + j], kz, kinv) * oscale;
@@ -390,16 +402,19 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
               *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
                   make_float4(a[4 * i] + sb[n + 4 * i], a[4 * i + 1] + sb[n + 4 * i + 1], a[4 * i + 2] + sb[n + 4 * i + 2],
                               a[4 * i + 3] + sb[n + 4 * i + 3]);
-            tmem_ld16(taddr + 256 + n, a);
+            // q_{L-1} = s(h_L) * W_L[0] from the unrounded activation: the previous step's pre-activations still sit
+            // in the other accumulator (this step publishes its operand only when all blocks are done)
+            const float* sbp = sbias + (s > 0 && g.st[s - 1].bias_slot >= 0 ? g.st[s - 1].bias_slot : 0) * 256;
+            tmem_ld16(taddr + (uint32_t)(((lg + 1) & 1) << 8) + n, a);
 #pragma unroll
-            for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? a[j] : 0.f;
+            for (int j = 0; j < 16; j++)
+              a[j] = (valid && n + j < N) ? sg_fast(sp_fast(a[j] + sbp[n + j], kz, kinv), ksg) * srvec[n + j] : 0.f;
           } else if (mode == SC_SPMUL) {
             if (S.csplit < N && n + 16 > S.csplit) {
-              // positional-encoding part of the skip gradient: parked in the spare TMEM columns until G0
-              float gz[16];
+              // positional-encoding part of the skip gradient: parked in shared memory until G0
 #pragma unroll
-              for (int j = 0; j < 16; j++) gz[j] = a[j] * oscale;
-              tmem_st16(taddr + 256 + n, gz);
+              for (int j = 0; j < 16; j++)
+                if (n + j >= S.csplit && n + j < N && n + j - S.csplit < SC_PARK_LD) spark[r * SC_PARK_LD + n + j - S.csplit] = a[j] * oscale;
             }
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
@@ -418,22 +433,12 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
             // g_0 = q_0 W_0 (+ the parked skip part): 128 x 64 FP32 staging, then one thread per row forms the normal
             float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
             if (S.csplit > 0) {
-              // parked columns csplit .. csplit+N-1 of the skip step <-> g_0 columns 0 .. N-1
-              const int c0 = (S.csplit + n) & ~15, sh = (S.csplit + n) & 15;
-              float p0[16], p1[16];
+              // parked columns csplit .. csplit+N-1 of the skip step <-> g_0 columns 0 .. N-1 (written by other
+              // column groups of the row: the named barrier orders the shared-memory accesses)
+              epi_bar();
 #pragma unroll
-              for (int j = 0; j < 16; j++) { p0[j] = 0.f; p1[j] = 0.f; }
-              if (c0 < 256) tmem_ld16(taddr + 256 + c0, p0);
-              if (c0 + 16 < 256) tmem_ld16(taddr + 256 + c0 + 16, p1);
-#pragma unroll
-              for (int j = 0; j < 16; j++) {
-                const int k = j + sh;
-                float v = 0.f;
-#pragma unroll
-                for (int u = 0; u < 32; u++)
-                  if (u == k) v = u < 16 ? p0[u & 15] : p1[u & 15];
-                if (n + j < N && S.csplit + n + j < 256) a[j] += v;
-              }
+              for (int j = 0; j < 16; j++)
+                if (n + j < N && n + j < SC_PARK_LD && S.csplit + n + j < 256) a[j] += spark[r * SC_PARK_LD + n + j];
             }
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -536,8 +541,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           tc_fence_before();
           fence_proxy_async();
           mbar_arrive(&ctl->blk_done[slot]);
+          if (pub_blocks) mbar_arrive(&ctl->a_ready[b]);                    // the next step's MMAs may read block b
           SC_STAMP(6);
         }
+        if (feeds_next)
+          for (int b = pub_blocks ? nb : 0; b < 4; b++) mbar_arrive(&ctl->a_ready[b]);
         if (S.dot) {
           // sdf = h_L . W_L[0] + b: the four column groups of a row meet in shared memory
           if (cg == 0) sdot[r] = dot;
@@ -545,11 +553,6 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           if (cg != 0) atomicAdd(&sdot[r], dot);
           epi_bar();
           if (cg == 0 && valid) g.sdf_out[m] = (sdot[r] + __ldg(g.b_last)) * g.sdf_scale;
-        }
-        if (s + 1 < g.nsteps && g.st[s + 1].src == SRC_CHAIN) {
-          tc_fence_before();
-          fence_proxy_async();
-          mbar_arrive(&ctl->a_ready);
         }
         SC_STAMP(7);
       }

@@ -587,3 +587,16 @@ class Stage1Loss(torch.autograd.Function):
         sc, ss, sw_, se = ctx.shapes
         return ((dc * g).reshape(sc), (ds * g).reshape(ss), (dw * g).reshape(sw_), (de * g).reshape(se),
                 None, None, None, None, None, None, None, None)
+
+
+def adam_step(p, g, m, v, state4, base_lr, lr_alpha, warm_up_end, end_iter, beta1=0.9, beta2=0.999, eps=1e-8,
+              grad_scale=1.0, zero_grad=True):
+    """Fused flat Adam with the on-device warm-up/cosine schedule (exp_runner.py:118,229-238); in place."""
+    _need_cuda(p, "params")
+    for t in (p, g, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != p.numel():
+            raise RuntimeError("adam_step: flat contiguous FP32 buffers of equal length expected")
+    L.check(L.lib().fneus_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), L.ptr(state4), float(base_lr),
+                                    float(lr_alpha), float(warm_up_end), float(end_iter), float(beta1), float(beta2),
+                                    float(eps), float(grad_scale), 1 if zero_grad else 0, L.stream_ptr()),
+            "fneus_adam_step")

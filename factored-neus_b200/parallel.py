@@ -79,3 +79,39 @@ class GradBucket:
     def all_reduce(self):
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self.flat, group=self.group)
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8) (exp_runner.py:118) + update_learning_rate
+    (exp_runner.py:229-238) as ONE fused launch over flat buffers: the parameters are re-homed as views of one
+    flat FP32 buffer (their values are kept), the gradients are the GradBucket's flat buffer, and the iteration
+    counter / learning rate live on the device (``state``: [iterations done, last lr, 1-b1^t, 1-b2^t]), so a
+    captured step needs no host-written scalar.  ``step()`` also clears the gradient bucket."""
+
+    def __init__(self, bucket: "GradBucket", lr=5e-4, lr_alpha=0.05, warm_up_end=5000, end_iter=300000,
+                 betas=(0.9, 0.999), eps=1e-8):
+        self.bucket = bucket
+        self.base_lr, self.lr_alpha, self.warm_up_end, self.end_iter = lr, lr_alpha, warm_up_end, end_iter
+        self.betas, self.eps = betas, eps
+        n = bucket.flat.numel()
+        dev = bucket.flat.device
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in bucket.params:
+                k = p.numel()
+                self.flat_p[off: off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off: off + k].view_as(p)
+                off += k
+        self.m = torch.zeros_like(self.flat_p)
+        self.v = torch.zeros_like(self.flat_p)
+        self.state = torch.zeros(4, dtype=torch.float32, device=dev)
+
+    def set_iteration(self, it: int):
+        """Resume support (exp_runner.py:266-275 restores iter_step)."""
+        self.state[0] = float(it)
+
+    def step(self):
+        from . import ops
+        ops.adam_step(self.flat_p, self.bucket.flat, self.m, self.v, self.state, self.base_lr, self.lr_alpha,
+                      self.warm_up_end, self.end_iter, self.betas[0], self.betas[1], self.eps, 1.0, True)

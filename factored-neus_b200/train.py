@@ -3,7 +3,8 @@
 ``Stage1Trainer.step(batch)`` = render + stage-1 loss (exp_runner.py:134-177) + backward + flat-bucket
 all-reduce (ray-sharded data parallelism) + fused Adam with the reference's warm-up / cosine schedule
 (exp_runner.py:229-238).  All shapes are fixed, so the whole step can be captured into ONE CUDA graph
-(``use_graph=True``): the learning rate lives in a device tensor that is updated outside the graph.
+(``use_graph=True``): the iteration counter and learning rate live on the device and are advanced by the
+optimiser launch itself (``parallel.FlatAdam`` -> ``fneus_adam_step``).
 """
 from __future__ import annotations
 
@@ -11,7 +12,7 @@ import math
 
 import torch
 
-from .parallel import GradBucket, stage1_loss_sharded
+from .parallel import FlatAdam, GradBucket, stage1_loss_sharded
 
 
 class Stage1Trainer:
@@ -29,8 +30,7 @@ class Stage1Trainer:
         params = [p for n in self.networks for p in n.parameters()]
         self.device = params[0].device
         self.bucket = GradBucket(params)
-        self.lr = torch.tensor(self._lr_at(0), device=self.device, dtype=torch.float32)
-        self.optimizer = torch.optim.Adam(params, lr=self.lr, fused=True, capturable=True)
+        self.optimizer = FlatAdam(self.bucket, lr=lr, lr_alpha=lr_alpha, warm_up_end=warm_up_end, end_iter=end_iter)
         self.use_graph = use_graph
         self._graph = None
         self._static_batch = torch.zeros(batch_size, 10, device=self.device)
@@ -62,8 +62,7 @@ class Stage1Trainer:
                                    cos_anneal_ratio=self._car)
         loss, stats = stage1_loss_sharded(self.renderer, out, rgb, m, self.surface_weight, self.igr_weight,
                                           self.mask_weight)
-        self.bucket.zero()
-        loss.backward()
+        loss.backward()                                                  # the bucket is cleared by the optimiser step
         self.bucket.all_reduce()
         self.optimizer.step()
         return loss
@@ -71,7 +70,6 @@ class Stage1Trainer:
     def step(self, batch):
         """batch [B,10] = (rays_o, rays_d, true_rgb, mask) as produced by Dataset.gen_random_rays_at
         (dataset.py:133-151).  Returns the (local-shard) loss tensor."""
-        self.lr.fill_(self._lr_at(self.iter_step))
         self._car = self.cos_anneal_ratio()
         if not self.use_graph or self.anneal_end != 0:                     # a moving cos_anneal_ratio is a host scalar
             loss = self._eager_step(batch)

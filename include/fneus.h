@@ -272,6 +272,15 @@ int fneus_stage1_loss(const float* color, const float* surface_color, const floa
                       int use_mask, float surface_weight, float igr_weight, float mask_weight, float* parts5,
                       float* d_color, float* d_surface_color, float* d_weight_sum, float* d_eik_num, void* stream);
 
+/* Optimiser of the stage-1 step (exp_runner.py:118 torch.optim.Adam, :229-238 update_learning_rate): one fused Adam
+ * update over flat FP32 buffers p/g/m/v [n] (16-byte aligned).  state4 (device) = [iterations done, lr of the last
+ * step, 1-beta1^t, 1-beta2^t]; the call first advances it (lr = base_lr * warm-up/cosine factor of the iteration
+ * count BEFORE the step, as the reference updates the rate after each step), then updates p.  g is multiplied by
+ * grad_scale first and cleared afterwards when zero_grad != 0.  No host-written scalars: graph-capturable. */
+int fneus_adam_step(float* p, float* g, float* m, float* v, long long n, float* state4, float base_lr, float lr_alpha,
+                    float warm_up_end, float end_iter, float beta1, float beta2, float eps, float grad_scale,
+                    int zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
