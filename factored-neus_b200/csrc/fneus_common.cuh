@@ -146,6 +146,32 @@ __device__ __forceinline__ void gen_row(const GenSpec& g, long long m, Emit emit
     }
   }
 }
+// The same, restricted to the components (counted across items) congruent to `part` modulo `nparts`: the threads
+// that share a row split its sincosf work.
+template <class Emit>
+__device__ __forceinline__ void gen_row_part(const GenSpec& g, long long m, int part, int nparts, Emit emit) {
+  int q = 0;
+#pragma unroll 1
+  for (int i = 0; i < g.nitems; i++) {
+    const GenItem it = g.it[i];
+#pragma unroll 1
+    for (int c = 0; c < it.dim; c++, q++) {
+      if (q % nparts != part) continue;
+      const float v = __ldg(it.src + m * it.dim + c) * it.scale;
+      const float t = g.deriv ? __ldg(it.tan + m * it.dim + c) : 0.f;
+      emit(it.col0 + c, g.deriv ? t : v);
+      float sn = 0.f, cs = 1.f;
+#pragma unroll 1
+      for (int k = 0; k < it.multires; k++) {
+        const float f = (float)(1u << k);
+        if (k % 3 == 0) sincosf(v * f, &sn, &cs);
+        else { float s2 = 2.f * sn * cs; cs = 1.f - 2.f * sn * sn; sn = s2; }
+        emit(it.col0 + it.dim * (1 + 2 * k) + c, g.deriv ? f * cs * t : sn);
+        emit(it.col0 + it.dim * (2 + 2 * k) + c, g.deriv ? -f * sn * t : cs);
+      }
+    }
+  }
+}
 __device__ __forceinline__ unsigned short f32_to_bf16_bits(float v) {
   unsigned u = __float_as_uint(v);
   u += 0x7FFFu + ((u >> 16) & 1u);

@@ -353,13 +353,6 @@ static bool sdf_chain_ok(const fneus_sdf_cfg* c, const SdfPlan& p) {
     if (cdiv(p.out[l], TC_BK) != 4 || cdiv(p.in[l + 1], TC_BK) != 4) return false;
   return true;
 }
-static SdfStep sdf_step(int mode, const uint8_t* wimg, int KB, int N, int bmn) {
-  SdfStep S;
-  memset(&S, 0, sizeof(S));
-  S.mode = mode; S.wimg = wimg; S.KB = KB; S.N = N; S.bmn = bmn; S.src = SRC_CHAIN;
-  S.csplit = N; S.bias_slot = -1; S.hscale = 1.f; S.oscale = 1.f; S.ldo = 4;
-  return S;
-}
 
 // No-grad value chain through the fused kernel: sdf (and optionally the features), nothing saved.
 static void sdf_chain_value_launch(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, const float* x, long long M,
@@ -391,7 +384,8 @@ static void sdf_chain_value_launch(const fneus_sdf_cfg* c, const SdfPlan& p, con
   g.rvec = w + p.woff[L]; g.b_last = w + p.boff[L];
   g.sdf_out = sdf_out; g.sdf_scale = out_sign / c->scale;
   g.beta = c->beta; g.M = M; g.dbg = 0;
-  sdf_chain_launch(g, flops, st);
+  g.xflags = (tc_debug_flags() >> 8) & 3;
+    sdf_chain_launch(g, flops, st);
 }
 
 // value chain. If bufs != nullptr activations go to bufs->H (saved) else ping-pong in scratch.
@@ -616,6 +610,7 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
     g.rvec = wpack + p.woff[L]; g.b_last = wpack + p.boff[L];
     g.sdf_out = sdf_out; g.sdf_scale = 1.f / cfg->scale;
     g.beta = cfg->beta; g.M = M; g.dbg = (tc_debug_flags() & 64) ? 1 : 0;
+    g.xflags = (tc_debug_flags() >> 8) & 3;
     sdf_chain_launch(g, flops, st);
     FNEUS_CHECK_LAUNCH();
     return FNEUS_OK;
@@ -723,7 +718,8 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     g.rvec = wpack + p.woff[L]; g.b_last = wpack + p.boff[L];
     g.rs = d_sdf; g.rscale = 1.f / cfg->scale;
     g.beta = cfg->beta; g.M = M; g.dbg = (tc_debug_flags() & 64) ? 1 : 0;
-    sdf_chain_launch(g, flops, st);
+    g.xflags = (tc_debug_flags() >> 8) & 3;
+    sdf_chain_launch(g, flops, st, FAM_SDF_BWD);
     // weight gradients: dW_l += q_l^T gbar_l + abar_l^T h_l, db_l += colsum abar_l ; last linear: features and row 0
     WgradGroup wg;
     wg.reset(M, sms);

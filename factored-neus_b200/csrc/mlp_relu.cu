@@ -2,7 +2,7 @@
 // ReLU MLPs whose first-layer input is [generated block | feature block].  FP32 path on the SIMT GEMM engine.
 #include "gemm_tc.cuh"
 #include "prof.cuh"
-#include "chain_fused.cuh"
+#include "sdf_chain.cuh"
 #include <string.h>
 
 namespace fneus {
@@ -48,16 +48,18 @@ static ImgArena arena_at(float* after_floats, size_t cap_bytes) {
   return ar;
 }
 
-// First-operand image ([generated blocks | memory blocks], at most CH_SLOT_BLOCKS of 64 columns) kept for the
+// First-operand image ([generated blocks | memory blocks], at most SC_NAR of 64 columns) kept for the
 // layer-0 weight gradient, and the per-layer dY images of the fused backward chain.
-static inline long long a0_img_floats(long long M) { return mat_floats(M, CH_SLOT_BLOCKS * 64, true) + 256; }
+static inline long long a0_img_floats(long long M) { return mat_floats(M, SC_NAR * 64, true) + 256; }
 
+// Fused-chain eligibility (sdf_chain.cuh, <5, false> instantiation): 256-wide hidden layers (4-block activation
+// images), first operand = at most one generated block + memory blocks, at most 5 blocks in all.
 static bool chain_fusable(const Lin* lin, int n_lin, const ASeg& a0, int hid) {
-  if (precision_mode() != 1 || tc_prepare() != 0 || chain_prepare() != 0) return false;
+  if (precision_mode() != 1 || tc_prepare() != 0 || sdf_chain_prepare() != 0) return false;
   if (tc_debug_flags() & 8) return false;                        // debug: layered execution
-  if (n_lin < 2 || n_lin + 2 > CH_MAXS || a0.gen.deriv) return false;
+  if (n_lin < 2 || n_lin + 2 > SC_MAXS || n_lin > SC_BIAS_SLOTS || a0.gen.deriv) return false;
   const int kb0 = cdiv(a0.gen.ncols, TC_BK) + cdiv(a0.kmem, TC_BK);
-  if (kb0 < 1 || kb0 > CH_SLOT_BLOCKS || hid > 256) return false;
+  if (kb0 < 1 || kb0 > SC_NAR || hid != 256 || a0.gen.ncols > TC_BK || a0.kmem > 256) return false;
   for (int l = 0; l < n_lin; l++) {
     if (lin[l].out > 256) return false;
     if (l > 0 && lin[l].in != hid) return false;
@@ -80,23 +82,26 @@ static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg
   ar.flush(st);
   if (all_img && ldh < 0 && (last_mode == EPI_SIGMOID || last_mode == EPI_LINEAR) &&
       -ldh == cdiv(lin[0].out, TC_BK) && chain_fusable(lin, n_lin, a0, lin[0].out)) {
-    ChainArgs g;
+    SdfChainArgs g;
     memset(&g, 0, sizeof(g));
     double flops = 0.0;
     g.nsteps = n_lin;
     for (int l = 0; l < n_lin; l++) {
-      ChainStep& S = g.st[l];
       const bool last = l == n_lin - 1;
-      S.wimg = img[l]; S.bias = w + lin[l].boff;
+      const int KB = l == 0 ? cdiv(a0.gen.ncols, TC_BK) + cdiv(a0.kmem, TC_BK) : cdiv(lin[l].in, TC_BK);
+      SdfStep S = sdf_step(last ? SC_OUT : SC_RELU, img[l], KB, lin[l].out, 0);
+      S.src = l == 0 ? (a0.gen.ncols > 0 ? SRC_GENMEM : SRC_MEM) : SRC_CHAIN;
+      S.bias = w + lin[l].boff; S.bias_slot = l;
       S.img_out = last ? nullptr : Hs[l + 1];
       S.out = last ? out : nullptr;
-      S.KB = l == 0 ? cdiv(a0.gen.ncols, TC_BK) + cdiv(a0.kmem, TC_BK) : cdiv(lin[l].in, TC_BK);
-      S.N = lin[l].out; S.mode = last ? CH_OUT : CH_RELU; S.bmn = 0;
       S.ldo = ld_out; S.act = last_mode == EPI_SIGMOID ? 1 : 0; S.accumulate = 0;
+      g.st[l] = S;
       flops += 2.0 * (double)M * lin[l].in * lin[l].out;
     }
-    g.gen = a0.gen; g.mem = a0.mem; g.ldm = a0.ldm; g.kmem = a0.kmem; g.a0_img = a0_img; g.M = M;
-    chain_launch(g, flops, st);
+    g.gen = a0.gen; g.gen_t = a0.gen; g.mem = a0.mem; g.ldm = a0.ldm; g.kmem = a0.kmem; g.a0_img = a0_img;
+    g.beta = 1.f; g.M = M; g.dbg = (tc_debug_flags() & 128) ? 1 : 0;
+    g.xflags = (tc_debug_flags() >> 8) & 3;
+    sdf_chain_launch(g, flops, st, FAM_RELU);
     return;
   }
   for (int l = 0; l < n_lin; l++) {
@@ -119,7 +124,7 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
                            cudaStream_t st, ImgArena& ar, const float* a0_img = nullptr) {
   const int sms = num_sms();
   const bool fused = ldh < 0 && -ldh == cdiv(lin[0].out, TC_BK) && chain_fusable(lin, n_lin, a0, lin[0].out) &&
-                     lin[n_lin - 1].out <= TC_BK * CH_SLOT_BLOCKS &&
+                     lin[n_lin - 1].out <= TC_BK * SC_NAR && n_lin >= 2 &&
                      (ld_small & 3) == 0 && (ld_feats & 3) == 0;
   if (fused) {
     // ---- weight images: MN-major W_l for l >= 1; layer 0 split into its feature and generated column ranges ----
@@ -141,32 +146,35 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
     }
     if (all_img) {
       ar.flush(st);
-      ChainArgs g;
+      SdfChainArgs g;
       memset(&g, 0, sizeof(g));
       double flops = 0.0;
       int ns = 0;
       for (int l = n_lin - 1; l >= 1; l--) {
-        ChainStep& S = g.st[ns++];
-        S.wimg = img[l]; S.KB = cdiv(lin[l].out, TC_BK); S.N = lin[l].in; S.mode = CH_MASK; S.bmn = 1;
-        S.mask = Hs[l]; S.mask_kbs = -ldh;
+        SdfStep S = sdf_step(SC_MASK, img[l], cdiv(lin[l].out, TC_BK), lin[l].in, 1);
+        S.src = l == n_lin - 1 ? SRC_MEM : SRC_CHAIN;
+        S.h = Hs[l];
         S.img_out = dybuf + (long long)(l - 1) * dy_stride;          // dz_{l-1} = (dz_l W_l) * [h_l > 0]
+        g.st[ns++] = S;
         flops += 2.0 * (double)M * lin[l].in * lin[l].out;
       }
       if (img_feat) {
-        ChainStep& S = g.st[ns++];
-        S.wimg = img_feat; S.KB = cdiv(lin[0].out, TC_BK); S.N = a0.kmem; S.mode = CH_OUT; S.bmn = 1;
+        SdfStep S = sdf_step(SC_OUT, img_feat, cdiv(lin[0].out, TC_BK), a0.kmem, 1);
         S.out = d_feats; S.ldo = ld_feats; S.accumulate = accumulate_feats;
+        g.st[ns++] = S;
         flops += 2.0 * (double)M * a0.kmem * lin[0].out;
       }
       if (img_gen) {
-        ChainStep& S = g.st[ns++];
-        S.wimg = img_gen; S.KB = cdiv(lin[0].out, TC_BK); S.N = a0.gen.ncols; S.mode = CH_OUT; S.bmn = 1;
+        SdfStep S = sdf_step(SC_OUT, img_gen, cdiv(lin[0].out, TC_BK), a0.gen.ncols, 1);
         S.out = dsmall; S.ldo = ld_small;
+        g.st[ns++] = S;
         flops += 2.0 * (double)M * a0.gen.ncols * lin[0].out;
       }
       g.nsteps = ns;
-      g.gen = gen_none(); g.mem = a_last; g.ldm = ld_last; g.kmem = lin[n_lin - 1].out; g.M = M;
-      chain_launch(g, flops, st);
+      g.gen = gen_none(); g.gen_t = g.gen; g.mem = a_last; g.ldm = ld_last; g.kmem = lin[n_lin - 1].out;
+      g.beta = 1.f; g.M = M; g.dbg = (tc_debug_flags() & 128) ? 1 : 0;
+      g.xflags = (tc_debug_flags() >> 8) & 3;
+    sdf_chain_launch(g, flops, st, FAM_RELU);
       // ---- all weight gradients in one grouped launch ----
       WgradGroup wg;
       wg.reset(M, sms);

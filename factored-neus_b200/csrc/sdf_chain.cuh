@@ -1,12 +1,19 @@
-// Fused SDF chains (BF16 tensor-core mode): the layer sequences of the SDF network that a training step runs on the
-// render_core points, each as ONE persistent kernel, one 128-point tile at a time per CTA, the running operand on
-// chip between layers (shared memory BF16 <-> TMEM FP32), weights streamed as pre-packed images:
+// Fused layer chains (BF16 tensor-core mode): the layer sequences that a training step runs on the render_core points,
+// each as ONE persistent kernel, one 128-point tile at a time per CTA, the running operand on chip between layers
+// (shared memory BF16 <-> TMEM FP32), weights streamed as pre-packed images.  The Softplus SDF network:
 //
 //   forward  : value chain h_{l+1} = softplus(W_l h_l + b_l) (fields.py:74-95), sdf = h_L . W_L[0] and the feature
 //              GEMM, then the reverse chain of the analytic gradient q_{l-1} = s_l * (q_l W_l) down to g_0 and the
 //              normal (fields.py:101-111 as reverse-mode) -- 2L+1 GEMM steps
 //   backward : the double-backward sweep gbar_{l+1} = s_l * (gbar_l W_l^T), e_l = beta (1 - s_l) q_l (gbar_l W_l^T),
 //              then the value-path backward abar_{l-1} = s_l * (abar_l W_l) + e_{l-1} -- 2L GEMM steps
+//
+// and the ReLU networks (RenderingNetwork fields.py:114-175, RefColor fields.py:271-335, Lvis fields.py:338-369):
+//
+//   forward  : [generated PE block | feature blocks] -> ReLU layers (activation images kept for the backward) ->
+//              FP32 output rows (sigmoid)
+//   backward : dz_{l-1} = (dz_l W_l) * [h_l > 0] with the h_l blocks bulk-loaded, then the two input-gradient GEMMs
+//              (feature columns, generated columns) off the same operand
 //
 // ALL bulk traffic goes through the async copy engine, never through per-thread global accesses (a thread-per-row
 // access touches 32 different 128-byte lines per warp instruction and serialises in L1): weight half-tiles and the
@@ -27,13 +34,28 @@
 //   warp 3      : storer: bulk shared->global of finished blocks, releases the slots
 //   warps 4-19  : epilogue, thread = one row (TMEM lane) x one of four 16-column groups per 64-column block
 #pragma once
-#include "chain_fused.cuh"
+#include "gemm_tc.cuh"
 
 namespace fneus {
 
+constexpr int CH_WBYTES = 16384;                                  // one weight half-tile: 128 output columns x 64 reduction
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 constexpr int SC_THREADS = 640, SC_WSTAGES = 4, SC_MAXS = 20, SC_BIAS_SLOTS = 10, SC_EPI_THREADS = 512;
-enum SdfStepMode { SC_SOFTPLUS = 0, SC_FEATQ, SC_SPMUL, SC_G0, SC_SWEEP, SC_SDFBWD };
-enum SdfStepSrc { SRC_CHAIN = 0, SRC_PE, SRC_TAN, SRC_MEM };
+constexpr int SC_NAR = 5;                                         // operand blocks a step may read (a_ready barriers)
+// SDF modes (Softplus network) and the ReLU-network modes (RenderingNetwork / RefColor / Lvis chains):
+//   SC_RELU : y = max(acc + bias, 0) -> next operand (+ image)        SC_MASK : y = acc * [h > 0] -> next operand (+ image)
+//   SC_OUT  : FP32 result rows to HBM (bias, optional sigmoid, optional accumulate); the operand stays as it is
+enum SdfStepMode { SC_SOFTPLUS = 0, SC_FEATQ, SC_SPMUL, SC_G0, SC_SWEEP, SC_SDFBWD, SC_RELU, SC_MASK, SC_OUT };
+// SRC_GENMEM: [one generated block | memory blocks (FP32 row-major, or an activation image when ldm < 0)]
+enum SdfStepSrc { SRC_CHAIN = 0, SRC_PE, SRC_TAN, SRC_MEM, SRC_GENMEM };
 
 struct SdfStep {
   const uint8_t* wimg;  // weight image ([1 n-chunk][KB] tiles of 32 KB)
@@ -45,6 +67,7 @@ struct SdfStep {
   float* out;           // FEATQ: features FP32 [M, ldo] ; G0: normal FP32 [M, d_in]
   int KB, N, mode, bmn, src;
   int ldo, csplit, append, dot, use_rs, bias_slot;
+  int act, accumulate;  // OUT: act 1 = sigmoid ; accumulate: out += result
   int sync_stores;      // storer: wait for full completion of every store so far after this step (later steps read them back)
   int wait_sync;        // aux loader: wait for that completion before this step's first load
   float hscale, oscale;
@@ -57,6 +80,7 @@ struct SdfChainArgs {
   const float* mem;     // SRC_MEM: FP32 [M, ldm], kmem columns
   int ldm, kmem;
   float* pe_img;        // optional 1-block image copy of the SRC_PE / SRC_TAN operand
+  float* a0_img;        // SRC_GENMEM: optional image copy of the whole first operand ([M, 1 + kb_mem blocks])
   const float* rvec;    // row 0 of the last linear [<= 256]
   const float* b_last;  // its bias
   float* sdf_out;       // [M]
@@ -64,6 +88,7 @@ struct SdfChainArgs {
   const float* rs;      // SDFBWD with use_rs: d_sdf [M]
   float rscale, beta;
   int dbg;              // record the debug timeline (CTA 0)
+  int xflags;           // experiment switches (fneus_debug_flags bits 8..): 1 = every thread arrives, 2 = no suspend hint
   long long M;
 };
 // debug timeline (fneus_debug_flags bit 6): clock64 stamps of CTA 0's first epilogue thread and MMA thread
@@ -72,15 +97,23 @@ __device__ unsigned long long g_sc_dbg[8192];
 
 struct SCSmem {
   uint64_t wfull[SC_WSTAGES], wempty[SC_WSTAGES];
-  uint64_t a_ready[4], acc_full, op_free, st_sync;
+  uint64_t a_ready[SC_NAR], acc_full, op_free, st_sync;
   uint64_t aux_full[2], aux_empty[2], blk_done[2];
   uint32_t tmem_base;
 };
-constexpr int SC_OP_BYTES = 4 * TC_A_BYTES;                      // operand: 128 rows x 256 columns BF16
 constexpr int SC_AUX_BYTES = 4 * TC_A_BYTES;                     // 2 slots x (h block + q block)
 constexpr int SC_PARK_LD = 41;                                   // odd row stride: thread-per-row accesses hit 32 banks
-constexpr int SC_SMEM_BYTES = SC_OP_BYTES + SC_WSTAGES * CH_WBYTES + SC_AUX_BYTES +
-                              (SC_BIAS_SLOTS * 256 + 256 + 128 + 128 * SC_PARK_LD) * 4 + 1024 + 256;
+// Three instantiations, each compiling only its own modes (the union was 127 KB of SASS and ran 15% slower on
+// instruction fetch): FAM_SDF_FWD (4 operand blocks = 256 columns, parking area for the skip gradient), FAM_SDF_BWD,
+// FAM_RELU (first operand up to 320 columns: [generated | features]).
+enum ChainFamily { FAM_SDF_FWD = 0, FAM_SDF_BWD = 1, FAM_RELU = 2 };
+template <int FAM>
+constexpr int sc_smem_bytes() {
+  constexpr int OPB = FAM == FAM_RELU ? 5 : 4;
+  constexpr bool PARK = FAM == FAM_SDF_FWD;
+  return OPB * TC_A_BYTES + SC_WSTAGES * CH_WBYTES + SC_AUX_BYTES +
+         (SC_BIAS_SLOTS * 256 + 256 + 128 + (PARK ? 128 * SC_PARK_LD : 0)) * 4 + 1024 + 256;
+}
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float* out) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -116,20 +149,27 @@ __device__ __forceinline__ float sp_fast(float v, float kz, float kinv) {
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // number of 64-column blocks a step's epilogue walks (every role derives it the same way)
-__device__ __forceinline__ int sdf_step_blocks(const SdfStep& S) { return S.mode == SC_G0 ? 1 : 4; }
+__device__ __forceinline__ int sdf_step_blocks(const SdfStep& S) {
+  return S.mode == SC_G0 ? 1 : (S.mode == SC_OUT ? (S.N + 63) >> 6 : 4);
+}
 
+template <int FAM>
 __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_constant__ SdfChainArgs g) {
+  constexpr int OPB = FAM == FAM_RELU ? 5 : 4;
+  constexpr bool PARK = FAM == FAM_SDF_FWD;
+  constexpr bool FWD = FAM == FAM_SDF_FWD, BWD = FAM == FAM_SDF_BWD;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sOp = base;
-  uint8_t* sW0 = base + SC_OP_BYTES;
+  uint8_t* sW0 = base + OPB * TC_A_BYTES;
   uint8_t* sAux = sW0 + SC_WSTAGES * CH_WBYTES;                  // slot i: h block at 2i, q block at 2i+1 (16 KB each)
   float* sbias = reinterpret_cast<float*>(sAux + SC_AUX_BYTES);  // [SC_BIAS_SLOTS][256]
   float* srvec = sbias + SC_BIAS_SLOTS * 256;                    // [256]
   float* sdot = srvec + 256;                                     // [128]
   float* spark = sdot + 128;                                     // [128][SC_PARK_LD]: skip part of the input gradient
-  SCSmem* ctl = reinterpret_cast<SCSmem*>(spark + 128 * SC_PARK_LD);
+  SCSmem* ctl = reinterpret_cast<SCSmem*>(spark + (PARK ? 128 * SC_PARK_LD : 0));
 
+  constexpr bool SDF = FAM != FAM_RELU;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ntiles = (g.M + 127) / 128;
   const float rsqrt2 = 0.70710678118654752440f;
@@ -138,7 +178,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
 #pragma unroll
     for (int s = 0; s < SC_WSTAGES; s++) { mbar_init(&ctl->wfull[s], 1); mbar_init(&ctl->wempty[s], 1); }
 #pragma unroll
-    for (int i = 0; i < 4; i++) mbar_init(&ctl->a_ready[i], SC_EPI_THREADS);
+    for (int i = 0; i < SC_NAR; i++) mbar_init(&ctl->a_ready[i], (g.xflags & 1) ? SC_EPI_THREADS : SC_EPI_THREADS / 32);
     mbar_init(&ctl->acc_full, 1);
     mbar_init(&ctl->op_free, 1);
     mbar_init(&ctl->st_sync, 1);
@@ -146,7 +186,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
     for (int i = 0; i < 2; i++) {
       mbar_init(&ctl->aux_full[i], 1);
       mbar_init(&ctl->aux_empty[i], 1);
-      mbar_init(&ctl->blk_done[i], SC_EPI_THREADS);
+      mbar_init(&ctl->blk_done[i], (g.xflags & 1) ? SC_EPI_THREADS : SC_EPI_THREADS / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -196,7 +236,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           for (int kb = 0; kb < S.KB; kb++) {
             // operand block kb is ready as soon as the previous step's epilogue has written it: the MMAs of this
             // step trail that epilogue block by block (its accumulator is the other TMEM buffer)
-            if (kb < 4) { mbar_wait(&ctl->a_ready[kb], lg & 1); tc_fence_after(); }
+            mbar_wait(&ctl->a_ready[kb], lg & 1);
+            tc_fence_after();
             for (int h = 0; h * 128 < Nc; h++, kbg++) {
               const int rows = min(128, Nc - h * 128);
               const uint32_t idesc = make_idesc(rows, 0, S.bmn);
@@ -213,7 +254,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
               umma_commit(&ctl->wempty[stg]);
             }
           }
-          for (int kb = S.KB; kb < 4; kb++) mbar_wait(&ctl->a_ready[kb], lg & 1);   // keep the phases in step
+          for (int kb = S.KB; kb < SC_NAR; kb++) mbar_wait(&ctl->a_ready[kb], lg & 1);   // keep the phases in step
           umma_commit(&ctl->acc_full);
         }
       }
@@ -282,6 +323,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float beta = g.beta, inv_beta = 1.f / g.beta;
     int lg = 0, c = 0, nfree = 0;                  // nfree: op_free phases consumed
+    const uint32_t whint = (g.xflags & 2) ? 0u : 0x989680u;
+    const bool all_arrive = (g.xflags & 1) != 0;
+    bool a0_pending = false;                       // bulk store of the first operand's image still reading shared memory
     const bool dbg_on = g.dbg != 0 && blockIdx.x == 0 && et == 0;
     int dbg_i = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -294,56 +338,111 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
         const bool first_overall = lg == 0;
         // ---- operand for this step, when it does not come from the previous step's epilogue ----
         if (S.src != SRC_CHAIN) {
-          if (!first_overall) { mbar_wait(&ctl->op_free, nfree & 1); nfree++; }
-          if (S.src == SRC_PE || S.src == SRC_TAN) {
-            if (cg == 0) {
+          if (!first_overall) { mbar_wait_hint(&ctl->op_free, nfree & 1, whint); nfree++; }
+          if (a0_pending) {
+            if (et == 0) bulk_wait_read0();
+            epi_bar();
+            a0_pending = false;
+          }
+          if (SDF && S.src == (FWD ? SRC_PE : SRC_TAN)) {
+            // the four threads of a row clear it, then split its components (sincosf is the cost of this block)
+            uint8_t* rowA = sOp + rowoff;
+            *reinterpret_cast<uint4*>(rowA + ch0) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(rowA + ch1) = make_uint4(0u, 0u, 0u, 0u);
+            epi_bar();
+            if (valid)
+              gen_row_part(FWD ? g.gen : g.gen_t, m, cg, 4, [&](int j, float val) {
+                if (j < TC_BK)
+                  *reinterpret_cast<unsigned short*>(rowA + ((((j >> 3) ^ r7) & 7) << 4) + ((j & 7) << 1)) = f32_to_bf16_bits(val);
+              });
+            if (g.pe_img != nullptr) {
+              epi_bar();
+              uint8_t* dst = reinterpret_cast<uint8_t*>(g.pe_img) + (size_t)tile * TC_A_BYTES + rowoff;
+              *reinterpret_cast<uint4*>(dst + ch0) = *reinterpret_cast<const uint4*>(rowA + ch0);
+              *reinterpret_cast<uint4*>(dst + ch1) = *reinterpret_cast<const uint4*>(rowA + ch1);
+            }
+          } else if (!FWD) {
+            uint8_t* sMem = sOp;                                           // first block of the memory segment
+            if (!SDF && S.src == SRC_GENMEM) {
+              // [one generated block | memory blocks]: the first operand of a ReLU network (fields.py:157,324-331)
+              sMem = sOp + TC_A_BYTES;
               uint8_t* rowA = sOp + rowoff;
-#pragma unroll
-              for (int k = 0; k < 8; k++) *reinterpret_cast<uint4*>(rowA + k * 16) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(rowA + ch0) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(rowA + ch1) = make_uint4(0u, 0u, 0u, 0u);
+              epi_bar();
               if (valid)
-                gen_row(S.src == SRC_PE ? g.gen : g.gen_t, m, [&](int j, float val) {
+                gen_row_part(g.gen, m, cg, 4, [&](int j, float val) {
                   if (j < TC_BK)
                     *reinterpret_cast<unsigned short*>(rowA + ((((j >> 3) ^ r7) & 7) << 4) + ((j & 7) << 1)) = f32_to_bf16_bits(val);
                 });
-              if (g.pe_img != nullptr) {
-                uint8_t* dst = reinterpret_cast<uint8_t*>(g.pe_img) + (size_t)tile * TC_A_BYTES + rowoff;
-#pragma unroll
-                for (int k = 0; k < 8; k++) *reinterpret_cast<uint4*>(dst + k * 16) = *reinterpret_cast<const uint4*>(rowA + k * 16);
-              }
             }
-          } else {
+            const int kb_mem = (g.kmem + TC_BK - 1) / TC_BK;
+            if (!SDF && g.ldm < 0) {
+              // image source: the tile's bytes are the operand blocks
+              const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(g.mem) +
+                                                                (size_t)tile * (size_t)(-g.ldm) * TC_A_BYTES);
+              const int nvec = kb_mem * (TC_A_BYTES / 16);
+              for (int i = et; i < nvec; i += SC_EPI_THREADS) reinterpret_cast<uint4*>(sMem)[i] = __ldg(src + i);
+            }
             // FP32 row-major source: each warp converts 8 rows, a lane 8 consecutive columns at a time (whole lines)
             const bool vec_ok = (g.ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mem) & 15) == 0;
-            const int nch = ((g.kmem + TC_BK - 1) / TC_BK) * 8;
-            for (int rr = ew * 8; rr < ew * 8 + 8; rr++) {
-              const long long mm = tile * 128 + rr;
-              const bool rv = mm < g.M;
-              const float* src = g.mem + mm * g.ldm;
-              uint8_t* drow = sOp + (rr >> 3) * 1024 + (rr & 7) * 128;
-              for (int ch = lane; ch < nch; ch += 32) {
-                const int cc = ch * 8;
-                float v[8];
-                if (rv && vec_ok && cc + 8 <= g.kmem) {
-                  const float4 lo = __ldg(reinterpret_cast<const float4*>(src + cc));
-                  const float4 hi = __ldg(reinterpret_cast<const float4*>(src + cc + 4));
-                  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-                } else {
+            const int nch = g.ldm < 0 ? 0 : kb_mem * 8;
+            // all 8 rows of a warp are loaded before any is converted (16 independent 16-byte loads in flight per lane)
+            for (int ch = lane; ch < nch; ch += 32) {
+              const int cc = ch * 8;
+              const bool fastc = vec_ok && cc + 8 <= g.kmem;
+#pragma unroll 1
+              for (int i0 = 0; i0 < 8; i0 += 4) {
+              float4 lo[4], hi[4];
 #pragma unroll
-                  for (int j = 0; j < 8; j++) v[j] = (rv && cc + j < g.kmem) ? __ldg(src + cc + j) : 0.f;
+              for (int i = 0; i < 4; i++) {
+                const long long mm = tile * 128 + ew * 8 + i0 + i;
+                const float* src = g.mem + mm * g.ldm + cc;
+                if (mm < g.M && fastc) {
+                  lo[i] = __ldg(reinterpret_cast<const float4*>(src));
+                  hi[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                } else {
+                  float v[8];
+#pragma unroll
+                  for (int j = 0; j < 8; j++) v[j] = (mm < g.M && cc + j < g.kmem) ? __ldg(src + j) : 0.f;
+                  lo[i] = make_float4(v[0], v[1], v[2], v[3]);
+                  hi[i] = make_float4(v[4], v[5], v[6], v[7]);
                 }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int rr = ew * 8 + i0 + i;
+                const float v[8] = {lo[i].x, lo[i].y, lo[i].z, lo[i].w, hi[i].x, hi[i].y, hi[i].z, hi[i].w};
+                uint8_t* drow = sMem + (rr >> 3) * 1024 + (rr & 7) * 128;
                 *reinterpret_cast<uint4*>(drow + (ch >> 3) * TC_A_BYTES + ((((ch & 7) ^ (rr & 7)) & 7) << 4)) = f32x8_to_bf16(v);
+              }
               }
             }
           }
           tc_fence_before();
           fence_proxy_async();
+          if (!SDF && (S.src == SRC_GENMEM || S.src == SRC_MEM) && g.a0_img != nullptr) {
+            // image copy of the whole first operand (the layer-0 weight gradient reads it back): one bulk store; its
+            // shared-memory reads are over before anybody overwrites the operand (barrier below)
+            epi_bar();
+            if (et == 0) {
+              const int kb0 = (S.src == SRC_GENMEM ? 1 : 0) + (g.kmem + TC_BK - 1) / TC_BK;
+              bulk_s2g(reinterpret_cast<uint8_t*>(g.a0_img) + (size_t)tile * kb0 * TC_A_BYTES, sOp, (uint32_t)kb0 * TC_A_BYTES);
+              bulk_commit();
+            }
+            a0_pending = true;
+          }
+          __syncwarp();
+          if (lane == 0 || all_arrive) {
 #pragma unroll
-          for (int i = 0; i < 4; i++) mbar_arrive(&ctl->a_ready[i]);
+            for (int i = 0; i < SC_NAR; i++) mbar_arrive(&ctl->a_ready[i]);
+          }
         }
 
         const int N = S.N, Nc = (N + 15) & ~15, mode = S.mode;
         const int nb = sdf_step_blocks(S);
         const float* sb = sbias + (S.bias_slot >= 0 ? S.bias_slot : 0) * 256;
+        const bool hasb = S.bias_slot >= 0;
         const float oscale = S.oscale;
         const float ksg = -beta * S.hscale * 1.4426950408889634f;       // s(h) = 1 - 2^(ksg h)
         const float kz = beta * 1.4426950408889634f, kinv = 0.6931471805599453f * inv_beta;
@@ -352,13 +451,23 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
         float dot = 0.f;
         const uint32_t tacc = taddr + (uint32_t)((lg & 1) << 8);         // this step's accumulator buffer
         const bool feeds_next = s + 1 < g.nsteps && g.st[s + 1].src == SRC_CHAIN;
-        const bool pub_blocks = feeds_next && S.mode != SC_FEATQ;        // publish the next operand block by block
+        const bool pub_blocks = feeds_next && mode != SC_FEATQ && mode != SC_OUT;   // publish the next operand block by block
 
         SC_STAMP(1);
-        mbar_wait(&ctl->acc_full, lg & 1);
+        mbar_wait_hint(&ctl->acc_full, lg & 1, whint);
         tc_fence_after();
         SC_STAMP(2);
-        if (S.src == SRC_CHAIN && !first_overall) { mbar_wait(&ctl->op_free, nfree & 1); nfree++; }
+        if (S.src == SRC_CHAIN && !first_overall) { mbar_wait_hint(&ctl->op_free, nfree & 1, whint); nfree++; }
+        if (a0_pending && mode != SC_OUT) {
+          if (et == 0) bulk_wait_read0();
+          epi_bar();
+          a0_pending = false;
+        }
+        // an OUT step leaves the operand as it is: the next step's MMAs may start at once
+        if (mode == SC_OUT && feeds_next && (lane == 0 || all_arrive)) {
+#pragma unroll
+          for (int i = 0; i < SC_NAR; i++) mbar_arrive(&ctl->a_ready[i]);
+        }
         SC_STAMP(3);
 
 #pragma unroll 1
@@ -369,7 +478,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           uint8_t* hb = sAux + (2 * slot) * TC_A_BYTES + rowoff;           // ... inside the slot's h block
           const uint8_t* qb = sAux + (2 * slot + 1) * TC_A_BYTES + rowoff; // ... inside the slot's q block
           SC_STAMP(4);
-          mbar_wait(&ctl->aux_full[slot], (c >> 1) & 1);
+          mbar_wait_hint(&ctl->aux_full[slot], (c >> 1) & 1, whint);
           SC_STAMP(5);
           const bool full = valid && n + 16 <= lim;                        // no per-element masks needed
           float a[16];
@@ -378,7 +487,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 16; j++) a[j] = 0.f;
           }
-          if (mode == SC_SOFTPLUS) {
+          if (FWD && mode == SC_SOFTPLUS) {
             if (S.dot) {
 #pragma unroll
               for (int j = 0; j < 16; j++) {
@@ -394,7 +503,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? sp_fast(a[j] + sb[n + j], kz, kinv) * oscale : 0.f;
             }
-          } else if (mode == SC_FEATQ) {
+          } else if (FWD && mode == SC_FEATQ) {
             // features: FP32 through a swizzled [128][64] staging tile (the slot's 32 KB), written out as whole lines
             float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
 #pragma unroll
@@ -409,12 +518,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 16; j++)
               a[j] = (valid && n + j < N) ? sg_fast(sp_fast(a[j] + sbp[n + j], kz, kinv), ksg) * srvec[n + j] : 0.f;
-          } else if (mode == SC_SPMUL) {
+          } else if (FWD && mode == SC_SPMUL) {
             if (S.csplit < N && n + 16 > S.csplit) {
               // positional-encoding part of the skip gradient: parked in shared memory until G0
 #pragma unroll
               for (int j = 0; j < 16; j++)
-                if (n + j >= S.csplit && n + j < N && n + j - S.csplit < SC_PARK_LD) spark[r * SC_PARK_LD + n + j - S.csplit] = a[j] * oscale;
+                if (PARK && n + j >= S.csplit && n + j < N && n + j - S.csplit < SC_PARK_LD)
+                  spark[r * SC_PARK_LD + n + j - S.csplit] = a[j] * oscale;
             }
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
@@ -429,7 +539,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
                   a[hf * 8 + j] = (valid && n + hf * 8 + j < S.csplit) ? sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale : 0.f;
               }
             }
-          } else if (mode == SC_G0) {
+          } else if (FWD && mode == SC_G0) {
             // g_0 = q_0 W_0 (+ the parked skip part): 128 x 64 FP32 staging, then one thread per row forms the normal
             float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
             if (S.csplit > 0) {
@@ -438,13 +548,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
               epi_bar();
 #pragma unroll
               for (int j = 0; j < 16; j++)
-                if (n + j < N && n + j < SC_PARK_LD && S.csplit + n + j < 256) a[j] += spark[r * SC_PARK_LD + n + j];
+                if (PARK && n + j < N && n + j < SC_PARK_LD && S.csplit + n + j < 256) a[j] += spark[r * SC_PARK_LD + n + j];
             }
 #pragma unroll
             for (int i = 0; i < 4; i++)
               *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
                   make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
-          } else if (mode == SC_SWEEP) {
+          } else if (BWD && mode == SC_SWEEP) {
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
               float hv[8], qv[8], e[8];
@@ -465,7 +575,50 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
               }
               *reinterpret_cast<uint4*>(hb + (hf ? ch1 : ch0)) = f32x8_to_bf16(e);   // e_l leaves from where h_{l+1} arrived
             }
-          } else {  // SC_SDFBWD
+          } else if (!SDF && mode == SC_RELU) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) a[j] = fmaxf(a[j] + sb[n + j], 0.f);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? fmaxf(a[j] + sb[n + j], 0.f) : 0.f;
+            }
+          } else if (!SDF && mode == SC_MASK) {
+            // dz_{l-1} = (dz_l W_l) * [h_l > 0]: the forward activation block arrived in the slot's h block
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+              float hv[8];
+              bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
+#pragma unroll
+              for (int j = 0; j < 8; j++)
+                a[hf * 8 + j] = (hv[j] > 0.f && (full || (valid && n + hf * 8 + j < N))) ? a[hf * 8 + j] : 0.f;
+            }
+          } else if (!SDF && mode == SC_OUT) {
+            if (N <= 16) {
+              // narrow result (colours, a specular scalar): the row's thread writes it directly
+              if (cg == 0 && b == 0 && valid) {
+                float y[16];
+                if (S.accumulate) row_load16(S.out, S.ldo, m, 0, N, y);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                  float v = a[j] + (hasb ? sb[j] : 0.f);
+                  if (S.act == 1) v = sigmoid_fast(v);
+                  y[j] = S.accumulate ? y[j] + v : v;
+                }
+                row_store16(S.out, S.ldo, m, 0, N, y);
+              }
+            } else {
+              // wide result: FP32 through the slot's swizzled [128][64] staging tile, written out as whole lines
+              float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                float4 v = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+                if (hasb) { v.x += sb[n + 4 * i]; v.y += sb[n + 4 * i + 1]; v.z += sb[n + 4 * i + 2]; v.w += sb[n + 4 * i + 3]; }
+                if (S.act == 1) { v.x = sigmoid_fast(v.x); v.y = sigmoid_fast(v.y); v.z = sigmoid_fast(v.z); v.w = sigmoid_fast(v.w); }
+                *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) = v;
+              }
+            }
+          } else if (BWD) {  // SC_SDFBWD
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
               float hv[8], qv[8];
@@ -479,26 +632,26 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
               }
             }
           }
-          if (mode != SC_G0) {
+          if (mode != SC_G0 && mode != SC_OUT) {
             *reinterpret_cast<uint4*>(opb + ch0) = f32x8_to_bf16(a);
             *reinterpret_cast<uint4*>(opb + ch1) = f32x8_to_bf16(a + 8);
           }
-          if (S.append && b == 3) {
+          if (SDF && S.append && b == 3) {
             // skip connection (fields.py:83-84): PE columns (value or tangent form) follow the N hidden columns once
             // every column group has written its chunk of the last block
             epi_bar();
-            if (cg == 0 && valid)
-              gen_row(mode == SC_SWEEP ? g.gen_t : g.gen, m, [&](int j, float val) {
+            if (valid)
+              gen_row_part(BWD ? g.gen_t : g.gen, m, cg, 4, [&](int j, float val) {
                 const int col = N + j;
                 if (col < 256)
                   *reinterpret_cast<unsigned short*>(sOp + (col >> 6) * TC_A_BYTES + rowoff + (((((col & 63) >> 3) ^ r7) & 7) << 4) +
                                                      ((col & 7) << 1)) = f32_to_bf16_bits(val * rsqrt2);
               });
           }
-          if (mode == SC_FEATQ || mode == SC_G0) {
+          if (FWD ? (mode == SC_FEATQ || mode == SC_G0) : (!SDF && mode == SC_OUT && N > 16)) {
             epi_bar();
             const float* T = reinterpret_cast<const float*>(sAux + (2 * slot) * TC_A_BYTES);
-            if (mode == SC_FEATQ) {
+            if (!SDF || mode == SC_FEATQ) {
               // warp ew writes rows 8 ew .. 8 ew + 7: two rows (2 x 256 B) per instruction
 #pragma unroll
               for (int i = 0; i < 4; i++) {
@@ -508,16 +661,21 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
                 if (mm < g.M && col < N) {
                   const float4 v = *reinterpret_cast<const float4*>(T + rr * 64 + ((q4 ^ (rr & 15)) << 2));
                   float* dst = S.out + mm * S.ldo + col;
-                  if (col + 4 <= N && (S.ldo & 3) == 0) *reinterpret_cast<float4*>(dst) = v;
-                  else {
-                    dst[0] = v.x;
-                    if (col + 1 < N) dst[1] = v.y;
-                    if (col + 2 < N) dst[2] = v.z;
-                    if (col + 3 < N) dst[3] = v.w;
+                  const bool acc_out = mode == SC_OUT && S.accumulate;
+                  if (col + 4 <= N && (S.ldo & 3) == 0) {
+                    if (acc_out) {
+                      const float4 o = *reinterpret_cast<const float4*>(dst);
+                      *reinterpret_cast<float4*>(dst) = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+                    } else *reinterpret_cast<float4*>(dst) = v;
+                  } else {
+                    dst[0] = acc_out ? dst[0] + v.x : v.x;
+                    if (col + 1 < N) dst[1] = acc_out ? dst[1] + v.y : v.y;
+                    if (col + 2 < N) dst[2] = acc_out ? dst[2] + v.z : v.z;
+                    if (col + 3 < N) dst[3] = acc_out ? dst[3] + v.w : v.w;
                   }
                 }
               }
-            } else if (et < 128) {
+            } else if (FWD && et < 128) {
               // thread et = row: normal = J_PE(x)^T g_0 (fields.py:101-111)
               const int rr = et;
               const long long mm = tile * 128 + rr;
@@ -540,13 +698,17 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           }
           tc_fence_before();
           fence_proxy_async();
-          mbar_arrive(&ctl->blk_done[slot]);
-          if (pub_blocks) mbar_arrive(&ctl->a_ready[b]);                    // the next step's MMAs may read block b
+          // one arrival per warp: every lane has fenced its own writes, the warp barrier orders them before the arrive
+          if (!all_arrive) __syncwarp();
+          if (lane == 0 || all_arrive) {
+            mbar_arrive(&ctl->blk_done[slot]);
+            if (pub_blocks) mbar_arrive(&ctl->a_ready[b]);                  // the next step's MMAs may read block b
+          }
           SC_STAMP(6);
         }
-        if (feeds_next)
-          for (int b = pub_blocks ? nb : 0; b < 4; b++) mbar_arrive(&ctl->a_ready[b]);
-        if (S.dot) {
+        if (feeds_next && mode != SC_OUT && (lane == 0 || all_arrive))
+          for (int b = pub_blocks ? nb : 0; b < SC_NAR; b++) mbar_arrive(&ctl->a_ready[b]);
+        if (FWD && S.dot) {
           // sdf = h_L . W_L[0] + b: the four column groups of a row meet in shared memory
           if (cg == 0) sdot[r] = dot;
           epi_bar();
@@ -557,6 +719,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
         SC_STAMP(7);
       }
     }
+    if (et == 0) bulk_wait0();
     if (dbg_on) g_sc_dbg[8191] = dbg_i;
   }
   __syncthreads();
@@ -566,20 +729,35 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
   }
 }
 
+inline SdfStep sdf_step(int mode, const uint8_t* wimg, int KB, int N, int bmn) {
+  SdfStep S;
+  memset(&S, 0, sizeof(S));
+  S.mode = mode; S.wimg = wimg; S.KB = KB; S.N = N; S.bmn = bmn; S.src = SRC_CHAIN;
+  S.csplit = N; S.bias_slot = -1; S.hscale = 1.f; S.oscale = 1.f; S.ldo = 4;
+  return S;
+}
+
 inline int sdf_chain_prepare() {
   static int done = 0;
   if (done) return 0;
-  if (cudaFuncSetAttribute(sdf_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_BYTES) != cudaSuccess)
+  if (cudaFuncSetAttribute(sdf_chain_kernel<FAM_SDF_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           sc_smem_bytes<FAM_SDF_FWD>()) != cudaSuccess ||
+      cudaFuncSetAttribute(sdf_chain_kernel<FAM_SDF_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           sc_smem_bytes<FAM_SDF_BWD>()) != cudaSuccess ||
+      cudaFuncSetAttribute(sdf_chain_kernel<FAM_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           sc_smem_bytes<FAM_RELU>()) != cudaSuccess)
     return 1;
   done = 1;
   return 0;
 }
-inline void sdf_chain_launch(const SdfChainArgs& g, double flops, cudaStream_t st) {
+inline void sdf_chain_launch(const SdfChainArgs& g, double flops, cudaStream_t st, int family = FAM_SDF_FWD) {
   const long long ntiles = (g.M + 127) / 128;
   const int sms = tc_num_sms();
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   prof_begin(PC_TC_MLP, flops, 0.0, st);
-  sdf_chain_kernel<<<grid, SC_THREADS, SC_SMEM_BYTES, st>>>(g);
+  if (family == FAM_RELU) sdf_chain_kernel<FAM_RELU><<<grid, SC_THREADS, sc_smem_bytes<FAM_RELU>(), st>>>(g);
+  else if (family == FAM_SDF_BWD) sdf_chain_kernel<FAM_SDF_BWD><<<grid, SC_THREADS, sc_smem_bytes<FAM_SDF_BWD>(), st>>>(g);
+  else sdf_chain_kernel<FAM_SDF_FWD><<<grid, SC_THREADS, sc_smem_bytes<FAM_SDF_FWD>(), st>>>(g);
   prof_end(st);
 }
 

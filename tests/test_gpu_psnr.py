@@ -18,6 +18,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 ITERS = int(os.environ.get("FNEUS_PSNR_ITERS", "1000"))
 B = 512
+# A single held-out PSNR reading after 1k Adam steps moves by +-0.2 dB when ANY rounding changes (measured: the FP32 path
+# alone moved 51.08 -> 50.86 dB when the optimiser's arithmetic order changed), so the 0.1 dB gate is applied to the
+# mean over the last checkpoints of the run instead of to one reading.
+EVAL_SPAN, EVAL_EVERY = 100, 10
 
 
 def _render_rgb(R, o, d, near, far):
@@ -50,16 +54,22 @@ def test_bf16_training_tracks_fp32_psnr():
         tr = Stage1Trainer(m["renderer"], [m["sdf"], m["var"], m["color"], m["ref"]], B, warm_up_end=100,
                            end_iter=ITERS, use_graph=(prec == "bf16"))
         torch.manual_seed(11)                                              # identical perturbation stream
+        evals = []
         for it in range(ITERS):
             k = int(order[it % len(order)])
             tr.step(train[k * B:(k + 1) * B])
-        torch.cuda.synchronize()
-        pred = _render_rgb(m["renderer"], test[:, :3], test[:, 3:6], rays[2][n_train:], rays[3][n_train:])
-        return _psnr(pred, test[:, 6:9])
+            if it + 1 > ITERS - EVAL_SPAN and (ITERS - 1 - it) % EVAL_EVERY == 0:
+                torch.cuda.synchronize()
+                pred = _render_rgb(m["renderer"], test[:, :3], test[:, 3:6], rays[2][n_train:], rays[3][n_train:])
+                evals.append(_psnr(pred, test[:, 6:9]))
+        return evals
 
-    p32 = run("fp32")
-    p16 = run("bf16")
+    e32 = run("fp32")
+    e16 = run("bf16")
     ops.set_precision("fp32")
+    p32, p16 = sum(e32) / len(e32), sum(e16) / len(e16)
+    print("held-out PSNR at the last %d checkpoints: fp32 %s, bf16 %s" % (
+        len(e32), " ".join("%.2f" % v for v in e32), " ".join("%.2f" % v for v in e16)))
     print("PSNR after %d iterations: fp32 %.3f dB, bf16 %.3f dB, diff %.3f dB" % (ITERS, p32, p16, p16 - p32))
     # gate: the tensor-core path may not LOSE more than 0.1 dB against the FP32 path (it came out 0.13 dB
     # better on the B200 run recorded in profiles/); a large gap in either direction would mean different training

@@ -48,7 +48,7 @@ def report(tag, tl, mhz=1965.0):
             cur["end"] = us
             rows.append(cur)
     print(" step   start   wait_mma  wait_opfree  wait_aux  compute   total")
-    for i, r in enumerate(rows[:40]):
+    for i, r in enumerate(rows[:24]):
         print("  %2d  %7.2f   %7.2f    %7.2f    %7.2f  %7.2f  %7.2f" % (
             i, r["start"], r["acc"] - r["start"], r["opfree"] - r["acc"], r["aux_wait"], r["blk"], r["end"] - r["start"]))
     tot = rows[-1]["end"] - rows[0]["start"]
@@ -66,8 +66,11 @@ def main():
     sdf.load_state_dict(syn.sdf_state(4, syn.SDF_CONF, 0.03))
     sdf = sdf.to(dev)
     x = (torch.rand(N, 3, device=dev) * 2 - 1)
-    for it in range(2):
-        lib.fneus_debug_flags(64 if it == 1 else 0)
+    variants = [(0, "elected arrivals + suspend hint")]
+    for xf, label in variants:
+      print("#### variant:", label)
+      for it in range(2):
+        lib.fneus_debug_flags((64 if it == 1 else 0) | xf)
         s, f, n = sdf.value_feature_normal(x, want_normal=True)
         torch.cuda.synchronize()
         if it == 1:
@@ -76,7 +79,53 @@ def main():
         torch.cuda.synchronize()
         if it == 1:
             report("backward (sweep + value path)", read_timeline(lib))
+      lib.fneus_debug_flags(xf)
+      for it in range(2):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        s, f, n = sdf.value_feature_normal(x, want_normal=True)
+        e[1].record()
+        (s.sum() + f.sum() * 0.01 + n.sum()).backward()
+        e[2].record()
+        torch.cuda.synchronize()
+        print("sdf net [%s]: forward+normal %.3f ms, backward %.3f ms (incl. weight gradients)" % (
+            label, e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
     lib.fneus_debug_flags(0)
+    # colour network (ReLU chain, <5, false> instantiation): debug flag bit 7
+    col = fn.RenderingNetwork(**syn.COLOR_CONF)
+    col.load_state_dict(syn.scene_states(seed=4)["color"])
+    col = col.to(dev)
+    nrm = torch.nn.functional.normalize(torch.randn(N, 3, device=dev), dim=-1).requires_grad_(True)
+    dirs = torch.nn.functional.normalize(torch.randn(N, 3, device=dev), dim=-1)
+    feat = torch.randn(N, 256, device=dev).requires_grad_(True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for it in range(3):
+        lib.fneus_debug_flags(128 if it == 2 else 0)
+        ev[0].record()
+        rgb = col(x, nrm, dirs, feat)
+        ev[1].record()
+        torch.cuda.synchronize()
+        if it == 2:
+            report("colour forward", read_timeline(lib))
+        rgb.sum().backward()
+        ev[2].record()
+        torch.cuda.synchronize()
+        if it == 2:
+            report("colour backward", read_timeline(lib))
+        print("colour net: forward %.3f ms, backward %.3f ms (incl. weight gradients)" % (
+            ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
+    lib.fneus_debug_flags(0)
+    # warm kernel times of the SDF chains
+    for it in range(3):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        s, f, n = sdf.value_feature_normal(x, want_normal=True)
+        e[1].record()
+        (s.sum() + f.sum() * 0.01 + n.sum()).backward()
+        e[2].record()
+        torch.cuda.synchronize()
+        print("sdf net: forward+normal %.3f ms, backward %.3f ms (incl. weight gradients)" % (
+            e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
 
 
 if __name__ == "__main__":
