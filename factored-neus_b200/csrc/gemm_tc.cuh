@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 tc_gemm_mk_kernel(ASeg a, const float* __restrict__ W, int ldw, int wout0, int M, int N, Epi e,
                   const uint8_t* __restrict__ wimg) {
   extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared
+                                                 // address space (an integer round trip turned every access into a generic LD.E / ST.E)
   uint8_t* sA[TC_STAGES];
   uint8_t* sB[TC_STAGES];
 #pragma unroll
@@ -466,7 +467,8 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
                                            int ldw, int wout0, float* __restrict__ db, int M, int N, int m_per_split,
                                            const int bx, const int by) {
   extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared
+                                                 // address space (an integer round trip turned every access into a generic LD.E / ST.E)
   uint8_t* sA[TC_STAGES];
   uint8_t* sB[TC_STAGES];
 #pragma unroll
@@ -869,7 +871,8 @@ template <bool WT>
 __global__ void __launch_bounds__(P_THREADS, 1)
 tc_gemm_mk_persistent_kernel(ASeg a, int M, int N, Epi e, const uint8_t* __restrict__ wimg, int dbg) {
   extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared
+                                                 // address space (an integer round trip turned every access into a generic LD.E / ST.E)
   uint8_t* sA[P_STAGES];
   uint8_t* sB[P_STAGES];
 #pragma unroll

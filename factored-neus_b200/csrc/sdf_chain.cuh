@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
   constexpr bool PARK = FAM == FAM_SDF_FWD;
   constexpr bool FWD = FAM == FAM_SDF_FWD, BWD = FAM == FAM_SDF_BWD;
   extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared
+                                                 // address space (an integer round trip turned every access into a generic LD.E / ST.E)
   uint8_t* sOp = base;
   uint8_t* sW0 = base + OPB * TC_A_BYTES;
   uint8_t* sAux = sW0 + SC_WSTAGES * CH_WBYTES;                  // slot i: h block at 2i, q block at 2i+1 (16 KB each)

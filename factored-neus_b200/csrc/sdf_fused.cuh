@@ -37,7 +37,8 @@ constexpr int FZ_SMEM_BYTES = 2 * FZ_A_BYTES + FZ_WSTAGES * TC_B_BYTES + (FZ_MAX
 
 __global__ void __launch_bounds__(FZ_THREADS, 1) sdf_fused_fwd_kernel(FusedSdfArgs g) {
   extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared
+                                                 // address space (an integer round trip turned every access into a generic LD.E / ST.E)
   uint8_t* sAt[2] = {base, base + FZ_A_BYTES};
   uint8_t* sW[FZ_WSTAGES];
 #pragma unroll
