@@ -36,13 +36,22 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every ~100 ms from before the warm-up (the first nvidia-smi call on a
+    fresh box takes longer than a short timed region) and summarised over the samples taken between ``mark_begin`` and
+    ``mark_end`` (the device-timed, per-kernel and end-to-end regions, which all run the same step)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.t0, self.t1 = None, None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def run(self):
         while not self.stop_flag:
@@ -51,19 +60,25 @@ class ClockSampler(threading.Thread):
                                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in o.strip().split(",")]
                 if len(f) >= 6:
-                    self.rows.append(f)
+                    self.rows.append(f + [time.time()])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 <= r[-1] <= (self.t1 or time.time())]
+        window = "timed regions"
+        if not rows:                       # region shorter than one nvidia-smi call: the samples closest to it
+            mid = 0.5 * ((self.t0 or 0.0) + (self.t1 or time.time()))
+            rows = sorted(self.rows, key=lambda r: abs(r[-1] - mid))[:3]
+            window = "nearest samples"
+        sm = sorted(float(r[0]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "window": window}
 
 
 def run_reference(args):
@@ -183,6 +198,8 @@ def run_ours(args):
         opt.step()                                                          # also clears the gradient bucket
         return loss
 
+    sampler = ClockSampler(local)
+    sampler.start()
     lib = L.lib()
     from factored_neus_b200 import ops as _ops
     _ops.set_precision(args.precision)
@@ -231,9 +248,8 @@ def run_ours(args):
         return static_loss
 
     # ---------------- device-resident timed region (value) -------------------------------------
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         flush.zero_()                                                       # L2 flush between timed iterations
@@ -258,7 +274,6 @@ def run_ours(args):
         step(dev_batch)
     pev[1].record()
     barrier()
-    sampler.stop_flag = True
     prof_ms = pev[0].elapsed_time(pev[1])
     L.check(lib.fneus_prof_collect(ms_c, ln_c, fl_c, by_c), "prof_collect")
     lib.fneus_prof_enable(0)
@@ -278,6 +293,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         t_e2e += time.perf_counter() - t0
     barrier()
+    sampler.mark_end()
+    sampler.stop_flag = True
 
     t = torch.tensor([dev_ms, t_e2e * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
@@ -312,7 +329,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tf_sust"], "traffic": None, "peak_source": pk["src"],
-                         "kernel": ("tc_gemm_mk_kernel/tc_gemm_wgrad_kernel (tcgen05 dense MLP layers)" if args.precision == "bf16"
+                         "kernel": ("sdf_chain_kernel<SDF fwd|SDF bwd|ReLU> + tc_gemm_wgrad_group_kernel (tcgen05 dense MLP layers)" if args.precision == "bf16"
                                     else "gemm_mk_kernel/gemm_wgrad_kernel (dense MLP layers)"),
                          "kernel_share_of_step": (gemm_ms / prof_steps) / (dev_ms / args.steps),
                          "measured": "CUDA events around every launch of %d eager steps (%.2f ms/step with events)"

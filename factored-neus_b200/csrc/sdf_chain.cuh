@@ -88,7 +88,8 @@ struct SdfChainArgs {
   const float* rs;      // SDFBWD with use_rs: d_sdf [M]
   float rscale, beta;
   int dbg;              // record the debug timeline (CTA 0)
-  int xflags;           // experiment switches (fneus_debug_flags bits 8..): 1 = every thread arrives, 2 = no suspend hint
+  int xflags;           // experiment switches (fneus_debug_flags bits 8..): 1 = every thread arrives, 2 = no suspend hint,
+                        // 4 = no accumulator prefetch
   long long M;
 };
 // debug timeline (fneus_debug_flags bit 6): clock64 stamps of CTA 0's first epilogue thread and MMA thread
@@ -138,6 +139,23 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
       "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// Split accumulator load: issue now, wait later (the registers are tied to the wait so nothing reads them early).
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 // Branch-free epilogue forms (results are consumed at BF16 precision):
 //   s(h)  = 1 - exp(-beta h)  = 1 - 2^(ksg h)             (saturates to 1 by itself; h >= 0)
@@ -444,10 +462,14 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
         const int nb = sdf_step_blocks(S);
         const float* sb = sbias + (S.bias_slot >= 0 ? S.bias_slot : 0) * 256;
         const bool hasb = S.bias_slot >= 0;
+        const bool s_append = SDF && S.append != 0, s_dot = FWD && S.dot != 0;
+        const int csplit = S.csplit;
+        // slots are only waited for when the step reads auxiliary blocks or stages through the slot
+        const bool uses_slot = S.h != nullptr || S.q != nullptr || mode == SC_FEATQ || mode == SC_G0 || mode == SC_OUT;
         const float oscale = S.oscale;
         const float ksg = -beta * S.hscale * 1.4426950408889634f;       // s(h) = 1 - 2^(ksg h)
         const float kz = beta * 1.4426950408889634f, kinv = 0.6931471805599453f * inv_beta;
-        const int lim = (mode == SC_SPMUL || mode == SC_SDFBWD) ? S.csplit : N;
+        const int lim = (mode == SC_SPMUL || mode == SC_SDFBWD) ? csplit : N;
         const float rsv = (mode == SC_SDFBWD && S.use_rs && valid) ? __ldg(g.rs + m) * g.rscale : 0.f;
         float dot = 0.f;
         const uint32_t tacc = taddr + (uint32_t)((lg & 1) << 8);         // this step's accumulator buffer
@@ -471,6 +493,12 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
         }
         SC_STAMP(3);
 
+        // Modes that end in the common pack-and-store: the next block's accumulator load is issued before the store /
+        // fence / arrive tail of this block, so the TMEM latency hides underneath it.
+        const bool can_pf = (mode == SC_SOFTPLUS || mode == SC_SPMUL || mode == SC_SWEEP || mode == SC_SDFBWD ||
+                             mode == SC_RELU || mode == SC_MASK) && !(g.xflags & 4);
+        uint32_t ar[16];
+        bool pf = false;                                                   // ar[] is an in-flight load of this block
 #pragma unroll 1
         for (int b = 0; b < nb; b++, c++) {
           const int slot = c & 1;
@@ -479,17 +507,23 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
           uint8_t* hb = sAux + (2 * slot) * TC_A_BYTES + rowoff;           // ... inside the slot's h block
           const uint8_t* qb = sAux + (2 * slot + 1) * TC_A_BYTES + rowoff; // ... inside the slot's q block
           SC_STAMP(4);
-          mbar_wait_hint(&ctl->aux_full[slot], (c >> 1) & 1, whint);
+          if (uses_slot) mbar_wait_hint(&ctl->aux_full[slot], (c >> 1) & 1, whint);
           SC_STAMP(5);
           const bool full = valid && n + 16 <= lim;                        // no per-element masks needed
           float a[16];
-          if (n < Nc) tmem_ld16(tacc + n, a);
-          else {
+          if (!pf) {
+            if (n < Nc) tmem_ld16_issue(tacc + n, ar);
+            else {
 #pragma unroll
-            for (int j = 0; j < 16; j++) a[j] = 0.f;
+              for (int j = 0; j < 16; j++) ar[j] = 0u;
+            }
           }
+          tmem_ld16_wait(ar);
+#pragma unroll
+          for (int j = 0; j < 16; j++) a[j] = __uint_as_float(ar[j]);
+          pf = false;
           if (FWD && mode == SC_SOFTPLUS) {
-            if (S.dot) {
+            if (s_dot) {
 #pragma unroll
               for (int j = 0; j < 16; j++) {
                 float v = sp_fast(a[j] + sb[n + j], kz, kinv);
@@ -520,12 +554,12 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
             for (int j = 0; j < 16; j++)
               a[j] = (valid && n + j < N) ? sg_fast(sp_fast(a[j] + sbp[n + j], kz, kinv), ksg) * srvec[n + j] : 0.f;
           } else if (FWD && mode == SC_SPMUL) {
-            if (S.csplit < N && n + 16 > S.csplit) {
+            if (csplit < N && n + 16 > csplit) {
               // positional-encoding part of the skip gradient: parked in shared memory until G0
 #pragma unroll
               for (int j = 0; j < 16; j++)
-                if (PARK && n + j >= S.csplit && n + j < N && n + j - S.csplit < SC_PARK_LD)
-                  spark[r * SC_PARK_LD + n + j - S.csplit] = a[j] * oscale;
+                if (PARK && n + j >= csplit && n + j < N && n + j - csplit < SC_PARK_LD)
+                  spark[r * SC_PARK_LD + n + j - csplit] = a[j] * oscale;
             }
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
@@ -537,19 +571,19 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
               } else {
 #pragma unroll
                 for (int j = 0; j < 8; j++)
-                  a[hf * 8 + j] = (valid && n + hf * 8 + j < S.csplit) ? sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale : 0.f;
+                  a[hf * 8 + j] = (valid && n + hf * 8 + j < csplit) ? sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale : 0.f;
               }
             }
           } else if (FWD && mode == SC_G0) {
             // g_0 = q_0 W_0 (+ the parked skip part): 128 x 64 FP32 staging, then one thread per row forms the normal
             float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
-            if (S.csplit > 0) {
+            if (csplit > 0) {
               // parked columns csplit .. csplit+N-1 of the skip step <-> g_0 columns 0 .. N-1 (written by other
               // column groups of the row: the named barrier orders the shared-memory accesses)
               epi_bar();
 #pragma unroll
               for (int j = 0; j < 16; j++)
-                if (PARK && n + j < N && n + j < SC_PARK_LD && S.csplit + n + j < 256) a[j] += spark[r * SC_PARK_LD + n + j];
+                if (PARK && n + j < N && n + j < SC_PARK_LD && csplit + n + j < 256) a[j] += spark[r * SC_PARK_LD + n + j];
             }
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -629,15 +663,20 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
               for (int j = 0; j < 8; j++) {
                 const int nn = n + hf * 8 + j;
                 const float yv = fmaf(sg_fast(hv[j], ksg) * oscale, fmaf(rsv, srvec[nn], a[hf * 8 + j]), qv[j]);
-                a[hf * 8 + j] = (full || (valid && nn < S.csplit)) ? yv : 0.f;
+                a[hf * 8 + j] = (full || (valid && nn < csplit)) ? yv : 0.f;
               }
             }
           }
           if (mode != SC_G0 && mode != SC_OUT) {
-            *reinterpret_cast<uint4*>(opb + ch0) = f32x8_to_bf16(a);
-            *reinterpret_cast<uint4*>(opb + ch1) = f32x8_to_bf16(a + 8);
+            const uint4 p0 = f32x8_to_bf16(a), p1 = f32x8_to_bf16(a + 8);
+            if (can_pf && b + 1 < nb && n + 64 < Nc) {
+              tmem_ld16_issue(tacc + n + 64, ar);
+              pf = true;
+            }
+            *reinterpret_cast<uint4*>(opb + ch0) = p0;
+            *reinterpret_cast<uint4*>(opb + ch1) = p1;
           }
-          if (SDF && S.append && b == 3) {
+          if (s_append && b == 3) {
             // skip connection (fields.py:83-84): PE columns (value or tangent form) follow the N hidden columns once
             // every column group has written its chunk of the last block
             epi_bar();
@@ -709,7 +748,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
         }
         if (feeds_next && mode != SC_OUT && (lane == 0 || all_arrive))
           for (int b = pub_blocks ? nb : 0; b < SC_NAR; b++) mbar_arrive(&ctl->a_ready[b]);
-        if (FWD && S.dot) {
+        if (s_dot) {
           // sdf = h_L . W_L[0] + b: the four column groups of a row meet in shared memory
           if (cg == 0) sdot[r] = dot;
           epi_bar();

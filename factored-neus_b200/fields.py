@@ -105,9 +105,10 @@ class SDFNetwork(nn.Module):
     def flat_weights(self):
         return _flat_pack([getattr(self, "lin" + str(l)) for l in range(self.num_layers - 1)])
 
-    def value_feature_normal(self, x, want_normal=True):
-        """One fused pass: (sdf [N,1], feature [N,d_out-1], d sdf/dx [N,3]); all differentiable w.r.t. weights."""
-        return ops.SdfValueGrad.apply(self.flat_weights(), x, self.cfg, want_normal)
+    def value_feature_normal(self, x, want_normal=True, w=None):
+        """One fused pass: (sdf [N,1], feature [N,d_out-1], d sdf/dx [N,3]); all differentiable w.r.t. weights.
+        ``w``: an already packed ``flat_weights()`` tensor of THIS network (the renderer packs once per render)."""
+        return ops.SdfValueGrad.apply(self.flat_weights() if w is None else w, x, self.cfg, want_normal)
 
     def forward(self, inputs, iter_step=0):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):

@@ -41,7 +41,10 @@ class NeuSRenderer:
 
     def _sdf_nograd(self, pts):
         net = self.sdf_network
-        return ops.sdf_forward_nograd(net.cfg, net.flat_weights().detach(), pts, want_feat=False)[0]
+        w = getattr(self, "_w_sdf", None)                    # packed once per render() (weight-norm + flat pack)
+        if w is None:
+            w = net.flat_weights()
+        return ops.sdf_forward_nograd(net.cfg, w.detach(), pts, want_feat=False)[0]
 
     # ------------------------------------------------------------------ sampling
     def up_sample(self, rays_o, rays_d, z_vals, sdf, n_importance, inv_s):
@@ -86,7 +89,8 @@ class NeuSRenderer:
         rays_o, rays_d, z_vals = rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous()
         dists, mid_z, pts, dirs = ops.core_geometry(rays_o, rays_d, z_vals, sample_dist)
 
-        sdf, feat, normals = sdf_network.value_feature_normal(pts, want_normal=True)
+        w_sdf = getattr(self, "_w_sdf", None) if sdf_network is self.sdf_network else None
+        sdf, feat, normals = sdf_network.value_feature_normal(pts, want_normal=True, w=w_sdf)
         inv_s = deviation_network(torch.zeros([1, 3], device=dev))[:, :1].clip(1e-6, 1e6)       # [1,1]
         rgb = color_network(pts, normals, dirs, feat)                                             # [B*n,3]
 
@@ -166,6 +170,8 @@ class NeuSRenderer:
         background_alpha = None
         background_sampled_color = None
         z_vals = z_vals.contiguous()
+        # the SDF weights (weight-norm + flat pack, differentiable) are packed ONCE for the five SDF passes of a render
+        self._w_sdf = self.sdf_network.flat_weights()
         if self.n_importance > 0:
             z_vals = self._hierarchical(rays_o, rays_d, z_vals)
             n_samples = self.n_samples + self.n_importance
@@ -182,6 +188,7 @@ class NeuSRenderer:
                                     background_alpha=background_alpha,
                                     background_sampled_color=background_sampled_color,
                                     cos_anneal_ratio=cos_anneal_ratio)
+        self._w_sdf = None
         weights = ret_fine["weights"]
         s_val = ret_fine["s_val"].reshape(batch_size, n_samples).mean(dim=-1, keepdim=True)
         return {
