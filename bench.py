@@ -162,6 +162,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner) write to file descriptor 1: keep stdout for the ONE JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -340,7 +344,10 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_rays)
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         # NCCL communicators captured inside a CUDA graph can stall destroy_process_group(): the result is out,
         # so flush and leave without the collective teardown

@@ -68,9 +68,12 @@ static bool chain_fusable(const Lin* lin, int n_lin, const ASeg& a0, int hid) {
   return true;
 }
 
+// defer: when non-null and the fused path applies, the chain is NOT launched; its arguments and FLOPs are returned for a
+// paired launch (relu_chain_pair_launch) and `defer->used` is set.
+struct ChainDefer { SdfChainArgs g; double flops; bool used; };
 static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs, int ldh,
                            int last_mode, float* out, int ld_out, long long M, cudaStream_t st, ImgArena& ar,
-                           float* a0_img = nullptr) {
+                           float* a0_img = nullptr, ChainDefer* defer = nullptr) {
   const uint8_t* img[16];
   bool all_img = true;
   for (int l = 0; l < n_lin; l++) {
@@ -101,6 +104,7 @@ static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg
     g.gen = a0.gen; g.gen_t = a0.gen; g.mem = a0.mem; g.ldm = a0.ldm; g.kmem = a0.kmem; g.a0_img = a0_img;
     g.beta = 1.f; g.M = M; g.dbg = (tc_debug_flags() & 128) ? 1 : 0;
     g.xflags = (tc_debug_flags() >> 8) & 7;
+    if (defer) { defer->g = g; defer->flops = flops; defer->used = true; return; }
     sdf_chain_launch(g, flops, st, FAM_RELU);
     return;
   }
@@ -121,7 +125,8 @@ static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg
 static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs,
                            int ldh, const float* a_last, int ld_last, float* dybuf, long long dy_stride, float* dsmall,
                            int ld_small, float* d_feats, int ld_feats, int accumulate_feats, long long M,
-                           cudaStream_t st, ImgArena& ar, const float* a0_img = nullptr) {
+                           cudaStream_t st, ImgArena& ar, const float* a0_img = nullptr, ChainDefer* defer = nullptr,
+                           WgradGroup* shared_wg = nullptr) {
   const int sms = num_sms();
   const bool fused = ldh < 0 && -ldh == cdiv(lin[0].out, TC_BK) && chain_fusable(lin, n_lin, a0, lin[0].out) &&
                      lin[n_lin - 1].out <= TC_BK * SC_NAR && n_lin >= 2 &&
@@ -174,10 +179,12 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
       g.gen = gen_none(); g.gen_t = g.gen; g.mem = a_last; g.ldm = ld_last; g.kmem = lin[n_lin - 1].out;
       g.beta = 1.f; g.M = M; g.dbg = (tc_debug_flags() & 128) ? 1 : 0;
       g.xflags = (tc_debug_flags() >> 8) & 7;
-    sdf_chain_launch(g, flops, st, FAM_RELU);
-      // ---- all weight gradients in one grouped launch ----
-      WgradGroup wg;
-      wg.reset(M, sms);
+      if (defer) { defer->g = g; defer->flops = flops; defer->used = true; }
+      else sdf_chain_launch(g, flops, st, FAM_RELU);
+      // ---- all weight gradients in one grouped launch (the caller's group when chains are paired) ----
+      WgradGroup own_wg;
+      WgradGroup& wg = shared_wg ? *shared_wg : own_wg;
+      if (!shared_wg) wg.reset(M, sms);
       for (int l = n_lin - 1; l >= 0; l--) {
         const float* dy = l == n_lin - 1 ? a_last : dybuf + (long long)l * dy_stride;    // dz_l
         const int ldy = l == n_lin - 1 ? ld_last : ldh;
@@ -198,7 +205,7 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
                    lin[l].out, st);
         }
       }
-      wg.flush(st);
+      if (!shared_wg) wg.flush(st);
       return;
     }
   }
@@ -292,8 +299,14 @@ static RefPlan ref_plan(const fneus_ref_cfg* c) {
   return p;
 }
 
+// 2 x 4 hidden-sized dz buffers (one set per chain: the two chains run concurrently), dsmall_cd [n,32], dsmall_cs [n,36],
+// a_cd / a_cs [n,4], the specular chain's feature gradient [n, d_feature <= 256]
 static long long ref_scratch_main(const RefPlan& p, long long n) {
-  return 4LL * hid_floats(n, p.hid, p.img) + (32 + 36 + 8) * n + 2048;
+  return 8LL * hid_floats(n, p.hid, p.img) + (32 + 36 + 8 + 256) * n + 4096;
+}
+__global__ void add_into_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
 }
 __device__ __forceinline__ float srgb_f(float c) {
   const float eps = 1.1920928955078125e-07f;
@@ -532,14 +545,22 @@ int fneus_ref_fwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_prep_kernel<<<ew_blocks2(M), 256, 0, st>>>(dirs, normals, b.refl, M);
   prof_end(st);
+  // The diffuse and the specular network are independent: on the fused path both chains go out in ONE launch.
+  ChainDefer d_cd, d_cs;
+  d_cd.used = d_cs.used = false;
   relu_chain_fwd(wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, EPI_SIGMOID, b.yd, 3, M, st, ar,
-                 b.a0_cd);
+                 b.a0_cd, &d_cd);
   // viewdir_mlp: 4 x (Linear+ReLU); then net_cs Linear+Sigmoid
   {
     Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
     // hidden layer outputs G1..G4 are all ReLU'd; the chain helper applies ReLU to all but the last linear.
     relu_chain_fwd(wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, EPI_SIGMOID, b.ys,
-                   1, M, st, ar, b.a0_cs);
+                   1, M, st, ar, b.a0_cs, &d_cs);
+  }
+  if (d_cd.used && d_cs.used) relu_chain_pair_launch(d_cd.g, d_cs.g, d_cd.flops + d_cs.flops, st);
+  else {
+    if (d_cd.used) sdf_chain_launch(d_cd.g, d_cd.flops, st, FAM_RELU);
+    if (d_cs.used) sdf_chain_launch(d_cs.g, d_cs.flops, st, FAM_RELU);
   }
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_final_kernel<<<ew_blocks2(M * 3), 256, 0, st>>>(b.yd, b.ys, rgb_out, spec_out, diff_out, M);
@@ -561,22 +582,38 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   RefBufs b = ref_carve(p, saved, M);
   const long long hf = hid_floats(M, p.hid, p.img);
   float* ab0 = align1k(scratch);
-  float* ds_cd = ab0 + 4 * hf;
-  zero_if_ragged(p.img, ab0, 4 * hf, M, st);
+  float* ab1 = ab0 + 4 * hf;
+  float* ds_cd = ab1 + 4 * hf;
+  zero_if_ragged(p.img, ab0, 8 * hf, M, st);
   float* ds_cs = ds_cd + M * 32;
   float* a_cd = ds_cs + M * 36;
   float* a_cs = a_cd + M * 4;
+  float* df_cs = align1k(a_cs + M * 4);                 // [M, d_feature]: the specular chain's feature gradient
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   ref_final_bwd_kernel<<<ew_blocks2(M), 256, 0, st>>>(b.yd, b.ys, d_rgb, d_spec, d_diff, a_cd, a_cs, M);
   prof_end(st);
   Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
   ImgArena ar = arena_at(scratch + ref_scratch_main(p, M),
                          relu_chain_img_bytes(p.cd, 5, 30) + relu_chain_img_bytes(chain, 5, 33));
+  // The two chains are independent: on the fused path both backward-data chains go out in ONE launch (own dz buffers,
+  // own feature-gradient buffer, summed below) and all ten weight-gradient GEMMs in ONE grouped launch.
+  ChainDefer d_cd, d_cs;
+  d_cd.used = d_cs.used = false;
+  const bool pair = cfg->d_feature <= 256 && (cfg->d_feature & 3) == 0;
+  WgradGroup wg;
+  wg.reset(M, num_sms());
   relu_chain_bwd(wpack, d_wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, a_cd, 4, ab0, hf,
-                 ds_cd, 32, d_feats, cfg->d_feature, 0, M, st, ar, b.a0_cd);
-  relu_chain_bwd(wpack, d_wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, a_cs, 4, ab0,
-                 hf, ds_cs, 36, d_feats, cfg->d_feature, 1, M, st, ar, b.a0_cs);
+                 ds_cd, 32, d_feats, cfg->d_feature, 0, M, st, ar, b.a0_cd, pair ? &d_cd : nullptr, pair ? &wg : nullptr);
+  const bool paired = pair && d_cd.used;              // the diffuse chain took the fused path
+  relu_chain_bwd(wpack, d_wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, a_cs, 4,
+                 paired ? ab1 : ab0, hf, ds_cs, 36, paired ? df_cs : d_feats, cfg->d_feature, paired ? 0 : 1, M, st, ar,
+                 b.a0_cs, paired ? &d_cs : nullptr, paired ? &wg : nullptr);
+  if (paired && d_cs.used) relu_chain_pair_launch(d_cd.g, d_cs.g, d_cd.flops + d_cs.flops, st);
+  else if (d_cd.used) sdf_chain_launch(d_cd.g, d_cd.flops, st, FAM_RELU);
+  wg.flush(st);
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  if (paired && d_cs.used)
+    add_into_kernel<<<ew_blocks2(M * cfg->d_feature), 256, 0, st>>>(d_feats, df_cs, M * cfg->d_feature);
   ref_dn_kernel<<<ew_blocks2(M), 256, 0, st>>>(dirs, normals, b.refl, ds_cd, 32, ds_cs, 36, d_normals, M);
   prof_end(st);
   FNEUS_CHECK_LAUNCH();

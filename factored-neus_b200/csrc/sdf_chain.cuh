@@ -171,8 +171,9 @@ __device__ __forceinline__ int sdf_step_blocks(const SdfStep& S) {
   return S.mode == SC_G0 ? 1 : (S.mode == SC_OUT ? (S.N + 63) >> 6 : 4);
 }
 
+// The kernel body for CTA `cta` of `nctas` working on chain `g` (g lives in the kernel parameter space).
 template <int FAM>
-__global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_constant__ SdfChainArgs g) {
+__device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta, const int nctas) {
   constexpr int OPB = FAM == FAM_RELU ? 5 : 4;
   constexpr bool PARK = FAM == FAM_SDF_FWD;
   constexpr bool FWD = FAM == FAM_SDF_FWD, BWD = FAM == FAM_SDF_BWD;
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
     // ------------------------------ weight loader ------------------------------
     if (lane == 0) {
       int kbg = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (long long tile = cta; tile < ntiles; tile += nctas) {
         for (int s = 0; s < g.nsteps; s++) {
           const SdfStep& S = g.st[s];
           const int Nc = (S.N + 15) & ~15;
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       int kbg = 0, lg = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (long long tile = cta; tile < ntiles; tile += nctas) {
         for (int s = 0; s < g.nsteps; s++, lg++) {
           const SdfStep& S = g.st[s];
           const int Nc = (S.N + 15) & ~15;
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
     // ------------------------------ auxiliary-block loader ------------------------------
     if (lane == 0) {
       int c = 0, nsync = 0;                         // c: global block counter (slot = c & 1)
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (long long tile = cta; tile < ntiles; tile += nctas) {
         for (int s = 0; s < g.nsteps; s++) {
           const SdfStep& S = g.st[s];
           const int nb = sdf_step_blocks(S);
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
     // ------------------------------ storer ------------------------------
     if (lane == 0) {
       int c = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (long long tile = cta; tile < ntiles; tile += nctas) {
         for (int s = 0; s < g.nsteps; s++) {
           const SdfStep& S = g.st[s];
           const int nb = sdf_step_blocks(S);
@@ -345,9 +346,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
     const uint32_t whint = (g.xflags & 2) ? 0u : 0x989680u;
     const bool all_arrive = (g.xflags & 1) != 0;
     bool a0_pending = false;                       // bulk store of the first operand's image still reading shared memory
-    const bool dbg_on = g.dbg != 0 && blockIdx.x == 0 && et == 0;
+    const bool dbg_on = g.dbg != 0 && cta == 0 && et == 0;
     int dbg_i = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = cta; tile < ntiles; tile += nctas) {
       const long long m = tile * 128 + r;
       const bool valid = m < g.M;
       for (int s = 0; s < g.nsteps; s++, lg++) {
@@ -769,6 +770,18 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_c
   }
 }
 
+template <int FAM>
+__global__ void __launch_bounds__(SC_THREADS, 1) sdf_chain_kernel(const __grid_constant__ SdfChainArgs g) {
+  chain_body<FAM>(g, blockIdx.x, gridDim.x);
+}
+// Two independent ReLU chains in one launch (RefColor's diffuse and specular networks, fields.py:303-335, are 8 tiles
+// each at 512 rays: alone, either leaves 140 SMs idle): CTAs [0, ctas_a) run chain a, the rest chain b.
+struct SdfChainPair { SdfChainArgs a, b; int ctas_a; };
+__global__ void __launch_bounds__(SC_THREADS, 1) relu_chain_pair_kernel(const __grid_constant__ SdfChainPair p) {
+  const bool first = (int)blockIdx.x < p.ctas_a;
+  chain_body<FAM_RELU>(first ? p.a : p.b, first ? blockIdx.x : blockIdx.x - p.ctas_a, first ? p.ctas_a : gridDim.x - p.ctas_a);
+}
+
 inline SdfStep sdf_step(int mode, const uint8_t* wimg, int KB, int N, int bmn) {
   SdfStep S;
   memset(&S, 0, sizeof(S));
@@ -785,6 +798,8 @@ inline int sdf_chain_prepare() {
       cudaFuncSetAttribute(sdf_chain_kernel<FAM_SDF_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            sc_smem_bytes<FAM_SDF_BWD>()) != cudaSuccess ||
       cudaFuncSetAttribute(sdf_chain_kernel<FAM_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           sc_smem_bytes<FAM_RELU>()) != cudaSuccess ||
+      cudaFuncSetAttribute(relu_chain_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            sc_smem_bytes<FAM_RELU>()) != cudaSuccess)
     return 1;
   done = 1;
@@ -798,6 +813,18 @@ inline void sdf_chain_launch(const SdfChainArgs& g, double flops, cudaStream_t s
   if (family == FAM_RELU) sdf_chain_kernel<FAM_RELU><<<grid, SC_THREADS, sc_smem_bytes<FAM_RELU>(), st>>>(g);
   else if (family == FAM_SDF_BWD) sdf_chain_kernel<FAM_SDF_BWD><<<grid, SC_THREADS, sc_smem_bytes<FAM_SDF_BWD>(), st>>>(g);
   else sdf_chain_kernel<FAM_SDF_FWD><<<grid, SC_THREADS, sc_smem_bytes<FAM_SDF_FWD>(), st>>>(g);
+  prof_end(st);
+}
+
+inline void relu_chain_pair_launch(const SdfChainArgs& a, const SdfChainArgs& b, double flops, cudaStream_t st) {
+  SdfChainPair p;
+  p.a = a; p.b = b;
+  const int sms = tc_num_sms();
+  const long long ta = (a.M + 127) / 128, tb = (b.M + 127) / 128;
+  int ca = (int)(ta < sms / 2 ? ta : sms / 2), cb = (int)(tb < sms - ca ? tb : sms - ca);
+  p.ctas_a = ca;
+  prof_begin(PC_TC_MLP, flops, 0.0, st);
+  relu_chain_pair_kernel<<<ca + cb, SC_THREADS, sc_smem_bytes<FAM_RELU>(), st>>>(p);
   prof_end(st);
 }
 
