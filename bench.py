@@ -332,7 +332,15 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tf_sust"], "traffic": None, "peak_source": pk["src"],
+                         "frac": achieved / pk["tf_sust"],
+                         # DRAM bytes per launch (read + write) of the largest single launch, sdf_chain_kernel<1> on
+                         # 65 536 points, from the ncu --set full capture summarised in profiles/ (not measured live)
+                         "traffic": 1.816e9 if args.precision == "bf16" and B == 512 else None,
+                         "traffic_detail": ({"sdf_chain_kernel<0> fwd": 0.698e9, "sdf_chain_kernel<1> bwd": 1.816e9,
+                                             "tc_gemm_wgrad_group_kernel (12 jobs)": 0.793e9,
+                                             "source": "profiles/r1_final_ncu_chain_kernels.md"}
+                                            if args.precision == "bf16" and B == 512 else None),
+                         "peak_source": pk["src"],
                          "kernel": ("sdf_chain_kernel<SDF fwd|SDF bwd|ReLU> + tc_gemm_wgrad_group_kernel (tcgen05 dense MLP layers)" if args.precision == "bf16"
                                     else "gemm_mk_kernel/gemm_wgrad_kernel (dense MLP layers)"),
                          "kernel_share_of_step": (gemm_ms / prof_steps) / (dev_ms / args.steps),
