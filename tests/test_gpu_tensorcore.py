@@ -281,3 +281,47 @@ def test_bf16_fused_sdf_chains_match_layered(bf16_mode, N):
         if err > BF16_TOL * max(1.0, scale):
             bad.append("oracle:" + name)
     assert not bad, "fused SDF chain mismatches: %s" % bad
+
+
+def test_bf16_chains_full_size_multi_tile_per_cta(bf16_mode):
+    """BASELINE-size pass (512 rays x 128 samples = 65 536 points, plus a ragged tail): 513 tiles on 148 persistent CTAs,
+    i.e. up to four tiles per CTA -- the tile loop, the barrier phases that wrap across tiles and the operand hand-over
+    between the last step of one tile and the first of the next only run at this size.  Fused chains vs the independent
+    layer-by-layer tensor-core path on identical inputs (same arithmetic up to accumulation order)."""
+    N = 65536 + 77
+    states = syn.scene_states(seed=4, jitter=0.03)
+    m = build_modules(states, DEV)
+    rs = np.random.RandomState(7)
+    x = torch.from_numpy(rs.uniform(-1, 1, (N, 3)).astype(np.float32)).to(DEV)
+    lib = fn._lib.lib()
+    # SDF forward (value + analytic gradient) and backward (double-backward sweep + value path + weight gradients)
+    p_sdf = torch.from_numpy(rs.uniform(0.5, 1.5, (N, 1)).astype(np.float32)).to(DEV)
+    p_feat = torch.from_numpy(rs.uniform(-1, 1, (N, 256)).astype(np.float32)).to(DEV) * 0.05
+    p_nrm = torch.from_numpy(rs.uniform(0.5, 1.5, (N, 3)).astype(np.float32)).to(DEV)
+    try:
+        lib.fneus_debug_flags(16)
+        ref = _sdf_run(m, x, p_sdf, p_feat, p_nrm)
+    finally:
+        lib.fneus_debug_flags(0)
+    got = _sdf_run(m, x, p_sdf, p_feat, p_nrm)
+    for k in ref:
+        scale = max(1e-3, float(ref[k].abs().max()))
+        err = max_err(got[k], ref[k])
+        assert err <= 1.5e-2 * scale, "full-size fused vs layered SDF %s: err %.3e (scale %.3e)" % (k, err, scale)
+    assert torch.isfinite(got["normal"]).all() and torch.isfinite(got["feat"]).all()
+    # colour + RefColor chains (paired launch) at the same size
+    v = torch.from_numpy(rs.standard_normal((N, 3)).astype(np.float32))
+    v = (v / v.norm(dim=-1, keepdim=True)).to(DEV)
+    nrm = torch.from_numpy(rs.standard_normal((N, 3)).astype(np.float32)).to(DEV)
+    feat = torch.from_numpy((0.3 * rs.standard_normal((N, 256))).astype(np.float32)).to(DEV)
+    probe = torch.from_numpy(rs.uniform(0.5, 1.5, (N, 3)).astype(np.float32)).to(DEV)
+    try:
+        lib.fneus_debug_flags(8)
+        ref = _color_ref_run(m, x, nrm, v, feat, probe)
+    finally:
+        lib.fneus_debug_flags(0)
+    got = _color_ref_run(m, x, nrm, v, feat, probe)
+    for k in ref:
+        scale = max(1e-3, float(ref[k].abs().max()))
+        err = max_err(got[k], ref[k])
+        assert err <= 4e-3 * scale, "full-size fused vs layered %s: err %.3e (scale %.3e)" % (k, err, scale)
