@@ -156,6 +156,7 @@ def run_ours(args):
     import torch.distributed as dist
     import factored_neus_b200 as fn
     from factored_neus_b200 import _lib as L
+    from factored_neus_b200 import ops as _ops
     from factored_neus_b200.parallel import FlatAdam, GradBucket, stage1_loss_sharded
     syn = fn.synthetic
 
@@ -192,10 +193,8 @@ def run_ours(args):
 
     def step(batch):
         ro, rd, rgb, m = batch[:, :3], batch[:, 3:6], batch[:, 6:9], batch[:, 9:10]
-        a = (rd * rd).sum(-1, keepdim=True)
-        b = 2.0 * (ro * rd).sum(-1, keepdim=True)
-        mid = 0.5 * (-b) / a                                                # dataset.near_far_from_sphere
-        out = R.render(ro, rd, mid - 1.0, mid + 1.0, cos_anneal_ratio=1.0)
+        near, far = _ops.near_far_from_sphere(ro, rd)                       # dataset.near_far_from_sphere
+        out = R.render(ro, rd, near, far, cos_anneal_ratio=1.0)
         loss, _ = stage1_loss_sharded(R, out, rgb, m, SURFACE_W, IGR_W, MASK_W)
         loss.backward()
         bucket.all_reduce()
@@ -205,7 +204,6 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     lib = L.lib()
-    from factored_neus_b200 import ops as _ops
     _ops.set_precision(args.precision)
     if args.debug_flags:
         lib.fneus_debug_flags(args.debug_flags)

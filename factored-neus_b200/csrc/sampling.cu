@@ -217,6 +217,42 @@ __global__ void core_geometry_kernel(const float* __restrict__ o, const float* _
   }
 }
 
+
+// dataset.py:186-192 near_far_from_sphere: mid = 0.5 * (-b) / a with a = sum d^2, b = 2 sum o.d ; near/far = mid -/+ 1
+__global__ void near_far_kernel(const float* __restrict__ o, const float* __restrict__ d, long long B,
+                                float* __restrict__ near, float* __restrict__ far) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  const float ox = o[r * 3], oy = o[r * 3 + 1], oz = o[r * 3 + 2], dx = d[r * 3], dy = d[r * 3 + 1], dz = d[r * 3 + 2];
+  const float a = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  const float b = __fmul_rn(2.0f, __fadd_rn(__fadd_rn(__fmul_rn(ox, dx), __fmul_rn(oy, dy)), __fmul_rn(oz, dz)));
+  const float mid = __fdiv_rn(__fmul_rn(0.5f, -b), a);
+  near[r] = __fsub_rn(mid, 1.0f);
+  far[r] = __fadd_rn(mid, 1.0f);
+}
+// renderer.py:395-408: z = near + (far - near) * linspace(0,1,n) (+ (rand - 0.5) * 2.0 / n_samples when perturbed)
+__global__ void coarse_z_kernel(const float* __restrict__ near, const float* __restrict__ far,
+                                const float* __restrict__ lin, const float* __restrict__ rnd, long long total, int n,
+                                float inv_n_samples, float* __restrict__ z) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long r = idx / n;
+  const int j = (int)(idx - r * n);
+  float v = __fadd_rn(near[r], __fmul_rn(__fsub_rn(far[r], near[r]), lin[j]));
+  // torch divides a tensor by a host scalar as a multiplication by its FP32 reciprocal
+  if (rnd != nullptr) v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fsub_rn(rnd[r], 0.5f), 2.0f), inv_n_samples));
+  z[idx] = v;
+}
+// renderer.py:296-303: flat sample rows (idx - 1, idx) of the two samples bracketing the first sign change
+__global__ void hit_rows_kernel(const int* __restrict__ hit_idx, long long B, int n, long long* __restrict__ rows) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  int i = hit_idx[r];
+  i = i < 1 ? 1 : i;
+  rows[2 * r] = r * n + i - 1;
+  rows[2 * r + 1] = r * n + i;
+}
+
 }  // namespace fneus
 
 using namespace fneus;
@@ -302,6 +338,40 @@ int fneus_core_geometry(const float* rays_o, const float* rays_d, const float* z
   prof_begin(PC_SAMPLING, 0.0, (double)total * 36.0, (cudaStream_t)stream);
   core_geometry_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z, total, n, sample_dist,
                                                                           dists, mid_z, pts, dirs);
+  prof_end((cudaStream_t)stream);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_near_far(const float* rays_o, const float* rays_d, long long B, float* near, float* far, void* stream) {
+  if (B == 0) return FNEUS_OK;
+  if (!rays_o || !rays_d || !near || !far) return FNEUS_ERR_NULL;
+  if (B < 0) return FNEUS_ERR_BAD_SHAPE;
+  prof_begin(PC_SAMPLING, 0.0, (double)B * 32.0, (cudaStream_t)stream);
+  near_far_kernel<<<cdiv(B, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, B, near, far);
+  prof_end((cudaStream_t)stream);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_coarse_z(const float* near, const float* far, const float* lin, const float* rnd, long long B, int n,
+                   float inv_n_samples, float* z, void* stream) {
+  if (B == 0 || n == 0) return FNEUS_OK;
+  if (!near || !far || !lin || !z) return FNEUS_ERR_NULL;
+  if (B < 0 || n < 0) return FNEUS_ERR_BAD_SHAPE;
+  prof_begin(PC_SAMPLING, 0.0, (double)B * n * 4.0, (cudaStream_t)stream);
+  coarse_z_kernel<<<cdiv(B * n, 256), 256, 0, (cudaStream_t)stream>>>(near, far, lin, rnd, B * n, n, inv_n_samples, z);
+  prof_end((cudaStream_t)stream);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_hit_rows(const int* hit_idx, long long B, int n, long long* rows, void* stream) {
+  if (B == 0) return FNEUS_OK;
+  if (!hit_idx || !rows) return FNEUS_ERR_NULL;
+  if (B < 0 || n < 2) return FNEUS_ERR_BAD_SHAPE;
+  prof_begin(PC_SAMPLING, 0.0, (double)B * 20.0, (cudaStream_t)stream);
+  hit_rows_kernel<<<cdiv(B, 256), 256, 0, (cudaStream_t)stream>>>(hit_idx, B, n, rows);
   prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;

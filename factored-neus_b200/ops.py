@@ -600,3 +600,35 @@ def adam_step(p, g, m, v, state4, base_lr, lr_alpha, warm_up_end, end_iter, beta
                                     float(lr_alpha), float(warm_up_end), float(end_iter), float(beta1), float(beta2),
                                     float(eps), float(grad_scale), 1 if zero_grad else 0, L.stream_ptr()),
             "fneus_adam_step")
+
+
+def near_far_from_sphere(rays_o, rays_d):
+    """dataset.py:186-192 in one launch: (near, far) [B,1]."""
+    _need_cuda(rays_o, "rays_o")
+    ro, rd = _f32c(rays_o), _f32c(rays_d)
+    B = ro.shape[0]
+    near = torch.empty(B, 1, dtype=torch.float32, device=ro.device)
+    far = torch.empty(B, 1, dtype=torch.float32, device=ro.device)
+    L.check(L.lib().fneus_near_far(L.ptr(ro), L.ptr(rd), B, L.ptr(near), L.ptr(far), L.stream_ptr()), "fneus_near_far")
+    return near, far
+
+
+def coarse_z(near, far, lin, rnd, n_samples):
+    """renderer.py:395-408: z [B,n] = near + (far - near) * lin (+ (rnd - 0.5) * 2 / n_samples)."""
+    _need_cuda(near, "near")
+    nr, fr = _f32c(near).reshape(-1), _f32c(far).reshape(-1)
+    B, n = nr.shape[0], lin.numel()
+    z = torch.empty(B, n, dtype=torch.float32, device=nr.device)
+    r = _f32c(rnd).reshape(-1) if rnd is not None else None
+    inv_n = float(torch.tensor(1.0, dtype=torch.float32) / torch.tensor(float(n_samples), dtype=torch.float32))
+    L.check(L.lib().fneus_coarse_z(L.ptr(nr), L.ptr(fr), L.ptr(lin), L.ptr(r), B, n, inv_n, L.ptr(z),
+                                   L.stream_ptr()), "fneus_coarse_z")
+    return z
+
+
+def hit_rows(hit_idx, n):
+    """renderer.py:296-303: flat rows (idx-1, idx) per ray, int64 [2B]."""
+    B = hit_idx.shape[0]
+    rows = torch.empty(2 * B, dtype=torch.int64, device=hit_idx.device)
+    L.check(L.lib().fneus_hit_rows(L.ptr(hit_idx), B, int(n), L.ptr(rows), L.stream_ptr()), "fneus_hit_rows")
+    return rows

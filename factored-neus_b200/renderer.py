@@ -91,7 +91,11 @@ class NeuSRenderer:
 
         w_sdf = getattr(self, "_w_sdf", None) if sdf_network is self.sdf_network else None
         sdf, feat, normals = sdf_network.value_feature_normal(pts, want_normal=True, w=w_sdf)
-        inv_s = deviation_network(torch.zeros([1, 3], device=dev))[:, :1].clip(1e-6, 1e6)       # [1,1]
+        if hasattr(deviation_network, "variance"):
+            # SingleVarianceNetwork.forward (fields.py:267-268) on one row: ones * exp(10 variance), without the ones
+            inv_s = torch.exp(deviation_network.variance * 10.0).clip(1e-6, 1e6).reshape(1, 1)
+        else:
+            inv_s = deviation_network(torch.zeros([1, 3], device=dev))[:, :1].clip(1e-6, 1e6)   # [1,1]
         rgb = color_network(pts, normals, dirs, feat)                                             # [B*n,3]
 
         n_out = 0 if background_alpha is None else background_alpha.shape[1] - n
@@ -104,9 +108,7 @@ class NeuSRenderer:
         # surface term (renderer.py:284-343) with fixed shapes: every ray evaluates RefColor at the two
         # bracketing samples, rays without a sign change are masked to the reference's default of ones.
         hit = hit_idx >= 0
-        idx = hit_idx.clamp(min=1).long()
-        base = torch.arange(B, device=dev) * n
-        rows = torch.stack([base + idx - 1, base + idx], dim=1).reshape(-1)                      # [2B]
+        rows = ops.hit_rows(hit_idx, n)                                                          # [2B]
         r_rgb, r_spec, r_diff = self._ref_rows(refColor_network, pts, feat, dirs, normals, rows)
         surf_rgb, surf_spec, surf_diff = ops.SurfaceBlend.apply(r_rgb, r_spec, r_diff, w_pair, hit_idx)
         self.last_hit_idx = hit_idx
@@ -145,7 +147,7 @@ class NeuSRenderer:
         rays_o, rays_d = rays_o.float().contiguous(), rays_d.float().contiguous()
         batch_size = len(rays_o)
         sample_dist = 2.0 / self.n_samples
-        z_vals = near + (far - near) * self._linspace(0.0, 1.0, self.n_samples, dev)[None, :]
+        lin = self._linspace(0.0, 1.0, self.n_samples, dev)
 
         z_vals_outside = None
         if self.n_outside > 0:
@@ -155,9 +157,10 @@ class NeuSRenderer:
         perturb = self.perturb
         if perturb_overwrite >= 0:
             perturb = perturb_overwrite
+        # z = near + (far - near) * lin (+ (rand - 0.5) * 2 / n_samples), one launch (renderer.py:395-408)
+        rnd = torch.rand([batch_size, 1], device=dev) if perturb > 0 else None
+        z_vals = ops.coarse_z(near, far, lin, rnd, self.n_samples)
         if perturb > 0:
-            t_rand = torch.rand([batch_size, 1], device=dev) - 0.5
-            z_vals = z_vals + t_rand * 2.0 / self.n_samples
             if self.n_outside > 0:
                 mids = 0.5 * (z_vals_outside[..., 1:] + z_vals_outside[..., :-1])
                 upper = torch.cat([mids, z_vals_outside[..., -1:]], -1)

@@ -54,11 +54,10 @@ class Stage1Trainer:
 
     def _eager_step(self, batch):
         ro, rd, rgb, m = batch[:, :3], batch[:, 3:6], batch[:, 6:9], batch[:, 9:10]
-        a = (rd * rd).sum(-1, keepdim=True)
-        b = 2.0 * (ro * rd).sum(-1, keepdim=True)
-        mid = 0.5 * (-b) / a                                              # dataset.near_far_from_sphere
+        from . import ops
+        near, far = ops.near_far_from_sphere(ro, rd)                      # dataset.near_far_from_sphere
         bg = torch.ones([1, 3], device=batch.device) if self.use_white_bkgd else None
-        out = self.renderer.render(ro, rd, mid - 1.0, mid + 1.0, background_rgb=bg,
+        out = self.renderer.render(ro, rd, near, far, background_rgb=bg,
                                    cos_anneal_ratio=self._car)
         loss, stats = stage1_loss_sharded(self.renderer, out, rgb, m, self.surface_weight, self.igr_weight,
                                           self.mask_weight)

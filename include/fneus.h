@@ -272,6 +272,17 @@ int fneus_stage1_loss(const float* color, const float* surface_color, const floa
                       int use_mask, float surface_weight, float igr_weight, float mask_weight, float* parts5,
                       float* d_color, float* d_surface_color, float* d_weight_sum, float* d_eik_num, void* stream);
 
+/* Ray set-up glue of the caller and of render (one launch each instead of ~10 framework kernels):
+ *  fneus_near_far   dataset.py:186-192 near_far_from_sphere -> near/far [n_rays]
+ *  fneus_coarse_z   renderer.py:395-408: z [n_rays, n] = near + (far - near) * lin[n] (+ (rnd[n_rays] - 0.5) * 2 * inv_n_samples
+ *                   when rnd != NULL: the caller draws rnd with its own generator)
+ *  fneus_hit_rows   renderer.py:296-303: rows [2 n_rays] (int64) = flat indices of samples idx-1, idx around the first
+ *                   sign change (idx clamped to >= 1; rays without one are masked later by hit_idx < 0) */
+int fneus_near_far(const float* rays_o, const float* rays_d, long long n_rays, float* near, float* far, void* stream);
+int fneus_coarse_z(const float* near, const float* far, const float* lin, const float* rnd, long long n_rays, int n,
+                   float inv_n_samples, float* z, void* stream);
+int fneus_hit_rows(const int* hit_idx, long long n_rays, int n, long long* rows, void* stream);
+
 /* Optimiser of the stage-1 step (exp_runner.py:118 torch.optim.Adam, :229-238 update_learning_rate): one fused Adam
  * update over flat FP32 buffers p/g/m/v [n] (16-byte aligned).  state4 (device) = [iterations done, lr of the last
  * step, 1-beta1^t, 1-beta2^t]; the call first advances it (lr = base_lr * warm-up/cosine factor of the iteration

@@ -519,3 +519,29 @@ def test_fused_loss_and_surface_blend(B, use_mask):
     names = ["c_rgb", "c_spec", "c_diff", "w_pair", "color", "weight_sum", "eik_num"]
     for n_, a, b in zip(names, g_got, g_ref):
         assert_close(a, b, 1e-5, "grad " + n_, rtol=1e-4)
+
+
+def test_ray_setup_glue_kernels_bit_exact():
+    """fneus_near_far / fneus_coarse_z / fneus_hit_rows against the framework expressions they replace
+    (dataset.py:186-192: <= 1 ulp; renderer.py:395-408 and renderer.py:296-303: bit-exact)."""
+    B, n = 777, 64
+    g = torch.Generator().manual_seed(3)
+    o = (2.5 * torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1)).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1).to(DEV)
+    a = torch.sum(d ** 2, dim=-1, keepdim=True)
+    b = 2.0 * torch.sum(o * d, dim=-1, keepdim=True)
+    mid = 0.5 * (-b) / a
+    near, far = ops.near_far_from_sphere(o, d)
+    # torch's 3-element reduction order is its own: a last-bit difference in the two sums is allowed here
+    assert float((near - (mid - 1.0)).abs().max()) <= 5e-7 and float((far - (mid + 1.0)).abs().max()) <= 5e-7
+    lin = torch.linspace(0.0, 1.0, n, device=DEV)
+    z_ref = near + (far - near) * lin[None, :]
+    assert torch.equal(ops.coarse_z(near, far, lin, None, n), z_ref)
+    rnd = torch.rand(B, 1, generator=g).to(DEV)
+    z_ref = z_ref + (rnd - 0.5) * 2.0 / n
+    assert torch.equal(ops.coarse_z(near, far, lin, rnd, n), z_ref)
+    hit = torch.randint(-1, 128, (B,), generator=g, dtype=torch.int32).to(DEV)
+    idx = hit.clamp(min=1).long()
+    base = torch.arange(B, device=DEV) * 128
+    rows_ref = torch.stack([base + idx - 1, base + idx], dim=1).reshape(-1)
+    assert torch.equal(ops.hit_rows(hit, 128), rows_ref)
