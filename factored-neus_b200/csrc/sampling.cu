@@ -158,6 +158,11 @@ inverse_cdf_kernel(const float* __restrict__ bins, const float* __restrict__ cdf
   invert_cdf_warp(sz, sc, n, k, u_table, out + ray * k, inds ? inds + ray * k : nullptr, lane);
 }
 
+// cat_z_vals (renderer.py:191-205) as a rank merge.  Only the k new samples are ranked (binary search into the old row);
+// their output slots are marked in a bitmask, and every output position then finds its source with two popcounts
+// (new element: its ordinal among the set bits; old element: position minus the set bits below it), so all stores are
+// coalesced in output order.  Ties: old samples first, each list in its own order (what a stable sort of the
+// concatenation [old, new] gives).
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
 merge_sorted_kernel(const float* __restrict__ z, const float* __restrict__ new_z, const float* __restrict__ sdf,
                     const float* __restrict__ new_sdf, long long B, int n, int k, float* __restrict__ z_out,
@@ -166,23 +171,57 @@ merge_sorted_kernel(const float* __restrict__ z, const float* __restrict__ new_z
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const long long ray = (long long)blockIdx.x * SAMP_WARPS + warp;
   if (ray >= B) return;
-  float* sa = smem + (size_t)warp * (n + k);
+  const int tot = n + k, W = (tot + 31) >> 5;
+  float* sa = smem + (size_t)warp * (2 * tot + 2 * W);
   float* sb = sa + n;
-  for (int j = lane; j < n; j += 32) sa[j] = z[ray * n + j];
-  for (int j = lane; j < k; j += 32) sb[j] = new_z[ray * k + j];
-  __syncwarp();
+  float* sfa = sb + k;                                   // the riding sdf values: every global load of the ray is issued
+  float* sfb = sfa + n;                                  // up front (memory-level parallelism), nothing is loaded later
+  unsigned* mask = reinterpret_cast<unsigned*>(sfb + k);
+  unsigned* pre = mask + W;                              // set bits in the words below
   const bool carry = sdf && new_sdf && sdf_out;
-  float* zo = z_out + ray * (n + k);
-  float* so = carry ? sdf_out + ray * (n + k) : nullptr;
-  for (int i = lane; i < n; i += 32) {
-    int pos = i + count_less(sb, k, sa[i]);
-    zo[pos] = sa[i];
-    if (carry) so[pos] = sdf[ray * n + i];
+  for (int j = lane; j < n; j += 32) {
+    sa[j] = z[ray * n + j];
+    if (carry) sfa[j] = sdf[ray * n + j];
   }
   for (int j = lane; j < k; j += 32) {
-    int pos = j + count_leq(sa, n, sb[j]);
-    zo[pos] = sb[j];
-    if (carry) so[pos] = new_sdf[ray * k + j];
+    sb[j] = new_z[ray * k + j];
+    if (carry) sfb[j] = new_sdf[ray * k + j];
+  }
+  for (int w = lane; w < W; w += 32) mask[w] = 0u;
+  __syncwarp();
+  for (int j = lane; j < k; j += 32) {
+    const int pos = j + count_leq(sa, n, sb[j]);
+    atomicOr(&mask[pos >> 5], 1u << (pos & 31));
+  }
+  __syncwarp();
+  unsigned run = 0u;
+  for (int w0 = 0; w0 < W; w0 += 32) {
+    const int w = w0 + lane;
+    const unsigned c = w < W ? (unsigned)__popc(mask[w]) : 0u;
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (w < W) pre[w] = run + incl - c;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  float* zo = z_out + ray * tot;
+  float* so = carry ? sdf_out + ray * tot : nullptr;
+  for (int q = lane; q < tot; q += 32) {
+    const unsigned m = mask[q >> 5];
+    const int bit = q & 31;
+    const int below = (int)pre[q >> 5] + __popc(m & ((1u << bit) - 1u));
+    if ((m >> bit) & 1u) {
+      zo[q] = sb[below];
+      if (carry) so[q] = sfb[below];
+    } else {
+      const int i = q - below;
+      zo[q] = sa[i];
+      if (carry) so[q] = sfa[i];
+    }
   }
 }
 
@@ -316,7 +355,7 @@ int fneus_merge_sorted(const float* z, const float* new_z, const float* sdf, con
   if ((sdf == nullptr) != (new_sdf == nullptr)) return FNEUS_ERR_NULL;
   if (sdf && !sdf_out) return FNEUS_ERR_NULL;
   if (B < 0 || n < 0 || k < 0 || n + k > 8192) return FNEUS_ERR_BAD_SHAPE;
-  size_t smem = (size_t)SAMP_WARPS * (n + k) * sizeof(float);
+  size_t smem = (size_t)SAMP_WARPS * (2 * (n + k) + 2 * ((n + k + 31) / 32)) * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(merge_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fneus_cuda_error((int)e);

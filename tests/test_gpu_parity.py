@@ -87,10 +87,13 @@ def test_upsample_and_merge_chain(golden_dir):
 
 def test_merge_sorted_properties():
     gen = torch.Generator().manual_seed(0)
-    for B, n, k in ((1000, 64, 16), (7, 128, 32), (3, 1, 1)):
+    for B, n, k in ((1000, 64, 16), (7, 128, 32), (3, 1, 1), (50, 512, 32), (5, 2000, 100), (9, 33, 70), (4, 31, 1)):
         a = torch.sort(torch.rand(B, n, generator=gen), -1)[0]
         b = torch.sort(torch.rand(B, k, generator=gen), -1)[0]
         b[:, 0] = a[:, 0]                                           # ties
+        if k > 2 and n > 5:
+            b[:, 1] = a[:, 5]
+            b[:, 2] = a[:, 5]                                       # a double tie
         b = torch.sort(b, -1)[0]
         sa, sb = torch.rand(B, n, generator=gen), torch.rand(B, k, generator=gen)
         z, s = ops.merge_sorted(a.to(DEV), b.to(DEV), sa.to(DEV), sb.to(DEV))

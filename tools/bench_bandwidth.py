@@ -19,6 +19,30 @@ syn = fn.synthetic
 
 
 def timeit(f, reps=10):
+    """Device time per call: the calls are captured into one CUDA graph so that host launch overhead (ctypes + allocator,
+    ~20 us per call) does not masquerade as kernel time."""
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            f()
+    torch.cuda.current_stream().wait_stream(stream)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=stream):
+        for _ in range(reps):
+            f()
+    graph.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    graph.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e-3
+
+
+def timeit_eager(f, reps=10):
     for _ in range(3):
         f()
     torch.cuda.synchronize()
@@ -85,7 +109,7 @@ def main():
     def bwd():
         torch.autograd.grad([out[0], out[1]], [sdf, nrm, rgb], [gc, gw], retain_graph=True)
 
-    t = timeit(bwd)
+    t = timeit_eager(bwd)
     # reads the forward's 44 B + upstream d_weights 4, writes d_sdf 4 + d_normal 12 + d_rgb 12 per sample
     report("composite_bwd n=128 (+torch sum)", t, n * (44 + 4 + 4 + 12 + 12) + 100)
     print(json.dumps({"rays": B, "hbm_peak_gbs": peak,
