@@ -384,7 +384,7 @@ static void sdf_chain_value_launch(const fneus_sdf_cfg* c, const SdfPlan& p, con
   g.rvec = w + p.woff[L]; g.b_last = w + p.boff[L];
   g.sdf_out = sdf_out; g.sdf_scale = out_sign / c->scale;
   g.beta = c->beta; g.M = M; g.dbg = 0;
-  g.xflags = (tc_debug_flags() >> 8) & 7;
+  g.xflags = (tc_debug_flags() >> 8) & 15;
     sdf_chain_launch(g, flops, st);
 }
 
@@ -610,7 +610,7 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
     g.rvec = wpack + p.woff[L]; g.b_last = wpack + p.boff[L];
     g.sdf_out = sdf_out; g.sdf_scale = 1.f / cfg->scale;
     g.beta = cfg->beta; g.M = M; g.dbg = (tc_debug_flags() & 64) ? 1 : 0;
-    g.xflags = (tc_debug_flags() >> 8) & 7;
+    g.xflags = (tc_debug_flags() >> 8) & 15;
     sdf_chain_launch(g, flops, st);
     FNEUS_CHECK_LAUNCH();
     return FNEUS_OK;
@@ -718,7 +718,7 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     g.rvec = wpack + p.woff[L]; g.b_last = wpack + p.boff[L];
     g.rs = d_sdf; g.rscale = 1.f / cfg->scale;
     g.beta = cfg->beta; g.M = M; g.dbg = (tc_debug_flags() & 64) ? 1 : 0;
-    g.xflags = (tc_debug_flags() >> 8) & 7;
+    g.xflags = (tc_debug_flags() >> 8) & 15;
     sdf_chain_launch(g, flops, st, FAM_SDF_BWD);
     // weight gradients: dW_l += q_l^T gbar_l + abar_l^T h_l, db_l += colsum abar_l ; last linear: features and row 0
     WgradGroup wg;

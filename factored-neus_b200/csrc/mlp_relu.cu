@@ -103,7 +103,7 @@ static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg
     }
     g.gen = a0.gen; g.gen_t = a0.gen; g.mem = a0.mem; g.ldm = a0.ldm; g.kmem = a0.kmem; g.a0_img = a0_img;
     g.beta = 1.f; g.M = M; g.dbg = (tc_debug_flags() & 128) ? 1 : 0;
-    g.xflags = (tc_debug_flags() >> 8) & 7;
+    g.xflags = (tc_debug_flags() >> 8) & 15;
     if (defer) { defer->g = g; defer->flops = flops; defer->used = true; return; }
     sdf_chain_launch(g, flops, st, FAM_RELU);
     return;
@@ -178,7 +178,7 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
       g.nsteps = ns;
       g.gen = gen_none(); g.gen_t = g.gen; g.mem = a_last; g.ldm = ld_last; g.kmem = lin[n_lin - 1].out;
       g.beta = 1.f; g.M = M; g.dbg = (tc_debug_flags() & 128) ? 1 : 0;
-      g.xflags = (tc_debug_flags() >> 8) & 7;
+      g.xflags = (tc_debug_flags() >> 8) & 15;
       if (defer) { defer->g = g; defer->flops = flops; defer->used = true; }
       else sdf_chain_launch(g, flops, st, FAM_RELU);
       // ---- all weight gradients in one grouped launch (the caller's group when chains are paired) ----

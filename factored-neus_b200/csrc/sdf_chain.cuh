@@ -89,7 +89,7 @@ struct SdfChainArgs {
   float rscale, beta;
   int dbg;              // record the debug timeline (CTA 0)
   int xflags;           // experiment switches (fneus_debug_flags bits 8..): 1 = every thread arrives, 2 = no suspend hint,
-                        // 4 = no accumulator prefetch
+                        // 4 = no accumulator prefetch, 8 = no early start on the first column half
   long long M;
 };
 // debug timeline (fneus_debug_flags bit 6): clock64 stamps of CTA 0's first epilogue thread and MMA thread
@@ -98,7 +98,7 @@ __device__ unsigned long long g_sc_dbg[8192];
 
 struct SCSmem {
   uint64_t wfull[SC_WSTAGES], wempty[SC_WSTAGES];
-  uint64_t a_ready[SC_NAR], acc_full, op_free, st_sync;
+  uint64_t a_ready[SC_NAR], acc_full, acc_half0, op_free, st_sync;
   uint64_t aux_full[2], aux_empty[2], blk_done[2];
   uint32_t tmem_base;
 };
@@ -200,6 +200,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
 #pragma unroll
     for (int i = 0; i < SC_NAR; i++) mbar_init(&ctl->a_ready[i], (g.xflags & 1) ? SC_EPI_THREADS : SC_EPI_THREADS / 32);
     mbar_init(&ctl->acc_full, 1);
+    mbar_init(&ctl->acc_half0, 1);
     mbar_init(&ctl->op_free, 1);
     mbar_init(&ctl->st_sync, 1);
 #pragma unroll
@@ -272,6 +273,9 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                 umma_bf16(acc + h * 128, make_desc(a_addr + k * 32, 16, 1024), bd, idesc, (kb > 0 || k > 0) ? 1 : 0);
               }
               umma_commit(&ctl->wempty[stg]);
+              // output columns 0..127 are complete once the last operand block's first half-tile is done: the epilogue
+              // starts on them while the second half-tile's MMAs (the exposed tail of the step) are still running
+              if (kb == S.KB - 1 && h == 0) umma_commit(&ctl->acc_half0);
             }
           }
           for (int kb = S.KB; kb < SC_NAR; kb++) mbar_wait(&ctl->a_ready[kb], lg & 1);   // keep the phases in step
@@ -478,8 +482,18 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
         const bool pub_blocks = feeds_next && mode != SC_FEATQ && mode != SC_OUT;   // publish the next operand block by block
 
         SC_STAMP(1);
-        mbar_wait_hint(&ctl->acc_full, lg & 1, whint);
+        mbar_wait_hint(&ctl->acc_half0, lg & 1, whint);
         tc_fence_after();
+        bool full_done = false;                                          // acc_full of this step already waited for
+        auto need_full = [&]() {
+          if (!full_done) {
+            mbar_wait_hint(&ctl->acc_full, lg & 1, whint);
+            tc_fence_after();
+            full_done = true;
+          }
+        };
+        // every mode but the in-place ones touches shared state that the step's last MMAs may still read or write
+        if (mode == SC_FEATQ || mode == SC_G0 || mode == SC_OUT || (g.xflags & 8)) need_full();
         SC_STAMP(2);
         if (S.src == SRC_CHAIN && !first_overall) { mbar_wait_hint(&ctl->op_free, nfree & 1, whint); nfree++; }
         if (a0_pending && mode != SC_OUT) {
@@ -508,6 +522,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           uint8_t* hb = sAux + (2 * slot) * TC_A_BYTES + rowoff;           // ... inside the slot's h block
           const uint8_t* qb = sAux + (2 * slot + 1) * TC_A_BYTES + rowoff; // ... inside the slot's q block
           SC_STAMP(4);
+          // columns >= 128, and the operand block the step's last half-tile of MMAs is still reading (block KB-1)
+          if (b >= 2 || b == S.KB - 1) need_full();
           if (uses_slot) mbar_wait_hint(&ctl->aux_full[slot], (c >> 1) & 1, whint);
           SC_STAMP(5);
           const bool full = valid && n + 16 <= lim;                        // no per-element masks needed
@@ -671,6 +687,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           if (mode != SC_G0 && mode != SC_OUT) {
             const uint4 p0 = f32x8_to_bf16(a), p1 = f32x8_to_bf16(a + 8);
             if (can_pf && b + 1 < nb && n + 64 < Nc) {
+              if (b + 1 >= 2) need_full();
               tmem_ld16_issue(tacc + n + 64, ar);
               pf = true;
             }
@@ -747,6 +764,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           }
           SC_STAMP(6);
         }
+        need_full();                                                       // keeps the barrier phases in step
         if (feeds_next && mode != SC_OUT && (lane == 0 || all_arrive))
           for (int b = pub_blocks ? nb : 0; b < SC_NAR; b++) mbar_arrive(&ctl->a_ready[b]);
         if (s_dot) {

@@ -632,3 +632,54 @@ def hit_rows(hit_idx, n):
     rows = torch.empty(2 * B, dtype=torch.int64, device=hit_idx.device)
     L.check(L.lib().fneus_hit_rows(L.ptr(hit_idx), B, int(n), L.ptr(rows), L.stream_ptr()), "fneus_hit_rows")
     return rows
+
+
+class FanOut(torch.autograd.Function):
+    """Identity with two outputs for a big activation that feeds one DENSE consumer (the colour network reads every row
+    of `feature`) and one SPARSE consumer (RefColor reads 2 rows per ray, renderer.py:296-327).  Autograd would
+    materialise the sparse consumer's gradient as a dense zero-filled tensor and add two dense tensors (3 x 67 MB of
+    traffic at 512 rays); here the sparse part is handed over through `stash` by GatherRows.backward and scattered into
+    the dense gradient in place.  The engine runs this node only after BOTH branches have delivered (or skipped) their
+    gradient, so the hand-over needs no ordering assumption."""
+
+    @staticmethod
+    def forward(ctx, x, stash):
+        ctx.stash = stash
+        ctx.set_materialize_grads(False)
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g_dense, g_other):
+        stash = ctx.stash
+        g = g_dense
+        if g_other is not None:
+            g = g_other if g is None else g + g_other
+        pend = stash.pop("rows_grad", None)
+        if pend is not None:
+            rows, vals, shape = pend
+            if g is None:
+                g = torch.zeros(shape, dtype=vals.dtype, device=vals.device)
+            elif not g.is_contiguous():
+                g = g.contiguous()
+            g.index_add_(0, rows, vals)
+        return g, None
+
+
+class GatherRows(torch.autograd.Function):
+    """x.index_select(0, rows) whose backward hands (rows, grad) to the FanOut node that produced x instead of
+    materialising a dense gradient."""
+
+    @staticmethod
+    def forward(ctx, x, rows, stash):
+        ctx.save_for_backward(rows)
+        ctx.stash, ctx.shape = stash, x.shape
+        return x.index_select(0, rows)
+
+    @staticmethod
+    def backward(ctx, g):
+        (rows,) = ctx.saved_tensors
+        prev = ctx.stash.get("rows_grad")
+        if prev is not None:                         # a second gather off the same fan-out: concatenate
+            rows, g = torch.cat([prev[0], rows]), torch.cat([prev[1], g])
+        ctx.stash["rows_grad"] = (rows, g.contiguous(), ctx.shape)
+        return None, None, None

@@ -11,6 +11,9 @@ from . import ops
 
 
 class NeuSRenderer:
+    # route the sparse (RefColor) gradient of `feature` into the colour network's dense one in place (ops.FanOut)
+    fuse_feature_fanout = False   # enabled once verified on the GPU in this tree
+
     def __init__(self, n_samples, n_importance, n_outside, up_sample_steps, perturb, nerf=None, sdf_network=None,
                  deviation_network=None, color_network=None, refColor_network=None, lvis_network=None,
                  indiLgt_network=None, mateIllu_network=None):
@@ -96,7 +99,11 @@ class NeuSRenderer:
             inv_s = torch.exp(deviation_network.variance * 10.0).clip(1e-6, 1e6).reshape(1, 1)
         else:
             inv_s = deviation_network(torch.zeros([1, 3], device=dev))[:, :1].clip(1e-6, 1e6)   # [1,1]
-        rgb = color_network(pts, normals, dirs, feat)                                             # [B*n,3]
+        # `feat` feeds the colour network (all rows) and RefColor (2 rows per ray): see ops.FanOut
+        stash = {}
+        fan = self.fuse_feature_fanout and feat.requires_grad
+        feat_dense, feat_sparse = ops.FanOut.apply(feat, stash) if fan else (feat, feat)
+        rgb = color_network(pts, normals, dirs, feat_dense)                                       # [B*n,3]
 
         n_out = 0 if background_alpha is None else background_alpha.shape[1] - n
         color, weights, wsum, wmax, cdf, inside, eik_num, eik_den, hit_idx, w_pair = ops.Composite.apply(
@@ -109,7 +116,8 @@ class NeuSRenderer:
         # bracketing samples, rays without a sign change are masked to the reference's default of ones.
         hit = hit_idx >= 0
         rows = ops.hit_rows(hit_idx, n)                                                          # [2B]
-        r_rgb, r_spec, r_diff = self._ref_rows(refColor_network, pts, feat, dirs, normals, rows)
+        r_rgb, r_spec, r_diff = self._ref_rows(refColor_network, pts, feat_sparse, dirs, normals, rows,
+                                               stash if fan else None)
         surf_rgb, surf_spec, surf_diff = ops.SurfaceBlend.apply(r_rgb, r_spec, r_diff, w_pair, hit_idx)
         self.last_hit_idx = hit_idx
         self.last_weight_sum = wsum
@@ -133,9 +141,9 @@ class NeuSRenderer:
         }
 
     @staticmethod
-    def _ref_rows(net, pts, feat, dirs, normals, rows):
-        d = net(pts.index_select(0, rows), feat.index_select(0, rows), dirs.index_select(0, rows),
-                normals.index_select(0, rows))
+    def _ref_rows(net, pts, feat, dirs, normals, rows, stash=None):
+        f_rows = feat.index_select(0, rows) if stash is None else ops.GatherRows.apply(feat, rows, stash)
+        d = net(pts.index_select(0, rows), f_rows, dirs.index_select(0, rows), normals.index_select(0, rows))
         return d["rgb"], d["specular_rgb"], d["diffuse_rgb"]
 
     # ------------------------------------------------------------------ render
