@@ -12,7 +12,7 @@ from . import ops
 
 class NeuSRenderer:
     # route the sparse (RefColor) gradient of `feature` into the colour network's dense one in place (ops.FanOut)
-    fuse_feature_fanout = False   # enabled once verified on the GPU in this tree
+    fuse_feature_fanout = True
 
     def __init__(self, n_samples, n_importance, n_outside, up_sample_steps, perturb, nerf=None, sdf_network=None,
                  deviation_network=None, color_network=None, refColor_network=None, lvis_network=None,
