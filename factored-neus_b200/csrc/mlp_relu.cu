@@ -600,6 +600,9 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   ChainDefer d_cd, d_cs;
   d_cd.used = d_cs.used = false;
   const bool pair = cfg->d_feature <= 256 && (cfg->d_feature & 3) == 0;
+  // 2 chains x (4 hidden layers + layer 0 split into its feature and generated parts) = 12 jobs: the shared group must
+  // not flush by itself before the deferred chains have been launched
+  static_assert(WG_MAX_JOBS >= 12, "the paired RefColor backward needs all weight-gradient jobs in one group");
   WgradGroup wg;
   wg.reset(M, num_sms());
   relu_chain_bwd(wpack, d_wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, a_cd, 4, ab0, hf,
