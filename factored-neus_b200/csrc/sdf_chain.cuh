@@ -99,10 +99,13 @@ __device__ unsigned long long g_sc_dbg[8192];
 struct SCSmem {
   uint64_t wfull[SC_WSTAGES], wempty[SC_WSTAGES];
   uint64_t a_ready[SC_NAR], acc_full, acc_half0, op_free, st_sync;
-  uint64_t aux_full[2], aux_empty[2], blk_done[2];
+  uint64_t aux_full[3], aux_empty[3], blk_done[3];
   uint32_t tmem_base;
 };
-constexpr int SC_AUX_BYTES = 4 * TC_A_BYTES;                     // 2 slots x (h block + q block)
+// Auxiliary slots (h block + q block, 32 KB each) and weight stages per family: the backward chain is HBM-bound and
+// needs bytes in flight (Little: 6.5 TB/s x ~1.2 us = 53 KB per SM), so it trades one weight stage for a third slot.
+template <int FAM> __host__ __device__ constexpr int sc_nslot() { return FAM == 1 ? 3 : 2; }
+template <int FAM> __host__ __device__ constexpr int sc_wstages() { return FAM == 1 ? 3 : SC_WSTAGES; }
 constexpr int SC_PARK_LD = 41;                                   // odd row stride: thread-per-row accesses hit 32 banks
 // Three instantiations, each compiling only its own modes (the union was 127 KB of SASS and ran 15% slower on
 // instruction fetch): FAM_SDF_FWD (4 operand blocks = 256 columns, parking area for the skip gradient), FAM_SDF_BWD,
@@ -112,7 +115,7 @@ template <int FAM>
 constexpr int sc_smem_bytes() {
   constexpr int OPB = FAM == FAM_RELU ? 5 : 4;
   constexpr bool PARK = FAM == FAM_SDF_FWD;
-  return OPB * TC_A_BYTES + SC_WSTAGES * CH_WBYTES + SC_AUX_BYTES +
+  return OPB * TC_A_BYTES + sc_wstages<FAM>() * CH_WBYTES + sc_nslot<FAM>() * 2 * TC_A_BYTES +
          (SC_BIAS_SLOTS * 256 + 256 + 128 + (PARK ? 128 * SC_PARK_LD : 0)) * 4 + 1024 + 256;
 }
 
@@ -182,8 +185,9 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                                                  // address space (an integer round trip turned every access into a generic LD.E / ST.E)
   uint8_t* sOp = base;
   uint8_t* sW0 = base + OPB * TC_A_BYTES;
-  uint8_t* sAux = sW0 + SC_WSTAGES * CH_WBYTES;                  // slot i: h block at 2i, q block at 2i+1 (16 KB each)
-  float* sbias = reinterpret_cast<float*>(sAux + SC_AUX_BYTES);  // [SC_BIAS_SLOTS][256]
+  constexpr int NSLOT = sc_nslot<FAM>(), WST = sc_wstages<FAM>();
+  uint8_t* sAux = sW0 + WST * CH_WBYTES;                         // slot i: h block at 2i, q block at 2i+1 (16 KB each)
+  float* sbias = reinterpret_cast<float*>(sAux + NSLOT * 2 * TC_A_BYTES);  // [SC_BIAS_SLOTS][256]
   float* srvec = sbias + SC_BIAS_SLOTS * 256;                    // [256]
   float* sdot = srvec + 256;                                     // [128]
   float* spark = sdot + 128;                                     // [128][SC_PARK_LD]: skip part of the input gradient
@@ -196,7 +200,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < SC_WSTAGES; s++) { mbar_init(&ctl->wfull[s], 1); mbar_init(&ctl->wempty[s], 1); }
+    for (int s = 0; s < WST; s++) { mbar_init(&ctl->wfull[s], 1); mbar_init(&ctl->wempty[s], 1); }
 #pragma unroll
     for (int i = 0; i < SC_NAR; i++) mbar_init(&ctl->a_ready[i], (g.xflags & 1) ? SC_EPI_THREADS : SC_EPI_THREADS / 32);
     mbar_init(&ctl->acc_full, 1);
@@ -204,7 +208,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
     mbar_init(&ctl->op_free, 1);
     mbar_init(&ctl->st_sync, 1);
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NSLOT; i++) {
       mbar_init(&ctl->aux_full[i], 1);
       mbar_init(&ctl->aux_empty[i], 1);
       mbar_init(&ctl->blk_done[i], (g.xflags & 1) ? SC_EPI_THREADS : SC_EPI_THREADS / 32);
@@ -235,8 +239,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
             for (int h = 0; h * 128 < Nc; h++, kbg++) {
               const int rows = min(128, Nc - h * 128);
               const uint32_t bytes = S.bmn ? (uint32_t)((rows + 63) >> 6) * 8192u : (uint32_t)rows * 128u;
-              const int stg = kbg % SC_WSTAGES;
-              if (kbg >= SC_WSTAGES) mbar_wait(&ctl->wempty[stg], ((kbg / SC_WSTAGES) - 1) & 1);
+              const int stg = kbg % WST;
+              if (kbg >= WST) mbar_wait(&ctl->wempty[stg], ((kbg / WST) - 1) & 1);
               mbar_arrive_expect_tx(&ctl->wfull[stg], bytes);
               bulk_g2s(sW0 + stg * CH_WBYTES, S.wimg + (size_t)kb * TC_B_BYTES + (size_t)h * CH_WBYTES, bytes,
                        &ctl->wfull[stg]);
@@ -262,8 +266,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
             for (int h = 0; h * 128 < Nc; h++, kbg++) {
               const int rows = min(128, Nc - h * 128);
               const uint32_t idesc = make_idesc(rows, 0, S.bmn);
-              const int stg = kbg % SC_WSTAGES;
-              mbar_wait(&ctl->wfull[stg], (kbg / SC_WSTAGES) & 1);
+              const int stg = kbg % WST;
+              mbar_wait(&ctl->wfull[stg], (kbg / WST) & 1);
               tc_fence_after();
               const uint32_t b_addr = smem_u32(sW0 + stg * CH_WBYTES);
               const uint32_t a_addr = smem_u32(sOp) + kb * TC_A_BYTES;
@@ -287,7 +291,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
   } else if (warp == 2) {
     // ------------------------------ auxiliary-block loader ------------------------------
     if (lane == 0) {
-      int c = 0, nsync = 0;                         // c: global block counter (slot = c & 1)
+      int c = 0, nsync = 0;                         // c: global block counter (slot = c % NSLOT)
       for (long long tile = cta; tile < ntiles; tile += nctas) {
         for (int s = 0; s < g.nsteps; s++) {
           const SdfStep& S = g.st[s];
@@ -295,8 +299,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           const bool has_h = S.h != nullptr, has_q = S.q != nullptr;
           if (S.wait_sync) { mbar_wait(&ctl->st_sync, nsync & 1); nsync++; }
           for (int b = 0; b < nb; b++, c++) {
-            const int slot = c & 1;
-            if (c >= 2) mbar_wait(&ctl->aux_empty[slot], ((c >> 1) - 1) & 1);
+            const int slot = c % NSLOT;
+            if (c >= NSLOT) mbar_wait(&ctl->aux_empty[slot], ((c / NSLOT) - 1) & 1);
             const bool ld = (has_h || has_q) && b * 64 < S.N;
             if (ld) {
               mbar_arrive_expect_tx(&ctl->aux_full[slot], (uint32_t)((has_h ? 1 : 0) + (has_q ? 1 : 0)) * TC_A_BYTES);
@@ -319,8 +323,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           const SdfStep& S = g.st[s];
           const int nb = sdf_step_blocks(S);
           for (int b = 0; b < nb; b++, c++) {
-            const int slot = c & 1;
-            mbar_wait(&ctl->blk_done[slot], (c >> 1) & 1);
+            const int slot = c % NSLOT;
+            mbar_wait(&ctl->blk_done[slot], (c / NSLOT) & 1);
             const size_t off = ((size_t)tile * 4 + b) * TC_A_BYTES;
             bool any = false;
             if (S.img_out != nullptr) { bulk_s2g(reinterpret_cast<uint8_t*>(S.img_out) + off, sOp + b * TC_A_BYTES, TC_A_BYTES); any = true; }
@@ -516,7 +520,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
         bool pf = false;                                                   // ar[] is an in-flight load of this block
 #pragma unroll 1
         for (int b = 0; b < nb; b++, c++) {
-          const int slot = c & 1;
+          const int slot = c % NSLOT;
           const int n = b * 64 + cg * 16;
           uint8_t* opb = sOp + b * TC_A_BYTES + rowoff;                    // the row inside operand block b
           uint8_t* hb = sAux + (2 * slot) * TC_A_BYTES + rowoff;           // ... inside the slot's h block
@@ -524,7 +528,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           SC_STAMP(4);
           // columns >= 128, and the operand block the step's last half-tile of MMAs is still reading (block KB-1)
           if (b >= 2 || b == S.KB - 1) need_full();
-          if (uses_slot) mbar_wait_hint(&ctl->aux_full[slot], (c >> 1) & 1, whint);
+          if (uses_slot) mbar_wait_hint(&ctl->aux_full[slot], (c / NSLOT) & 1, whint);
           SC_STAMP(5);
           const bool full = valid && n + 16 <= lim;                        // no per-element masks needed
           float a[16];
