@@ -1,0 +1,48 @@
+"""The committed profile evidence stays machine-readable: the summary tools parse the committed ncu exports and the bench
+lines carry the keys the measurement contract names (no GPU needed)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROF = os.path.join(ROOT, "profiles")
+
+
+def test_launch_list_is_dominated_by_the_tensor_core_kernels():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from launch_summary import load
+    seq = load(os.path.join(PROF, "r1_final_launches.csv"))
+    assert len(seq) > 300
+    idx = [i for i, s in enumerate(seq) if "upsample_step" in s[0]]
+    step = seq[idx[-8]:idx[-4]]
+    tot = sum(v for _, v, _ in step)
+    tc = sum(v for k, v, _ in step if "sdf_chain_kernel" in k or "relu_chain_pair" in k or "wgrad_group" in k)
+    assert 0.6 < tc / tot < 0.95
+    assert not any("mlp_chain_kernel" in k for k, _, _ in step)       # the superseded kernel is gone from the path
+
+
+def test_ncu_summary_tool_reads_the_raw_pages():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"),
+                          os.path.join(PROF, "r1_final_ncu_chain_full_raw.csv"),
+                          os.path.join(PROF, "r1_final_ncu_relu_pair_full_raw.csv")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rows = [l for l in out.stdout.splitlines() if l.startswith("| `")]
+    assert len(rows) == 7 and any("sdf_chain_kernel<1>" in r for r in rows)
+
+
+def test_bench_lines_follow_the_contract():
+    for name, gpus in (("r1_final_bench_line.json", 1), ("r1_final_bench_line_2gpu.json", 2),
+                       ("r1_final_bench_line_4gpu.json", 4), ("r1_final_bench_line_8gpu.json", 8)):
+        d = json.loads(open(os.path.join(PROF, name)).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+            assert k in d, (name, k)
+        assert d["n_gpus"] == gpus and d["metric"] == "train_rays_per_s" and d["gpu_launches"] > 0
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"] * 1.02
+        assert 0.0 < d["roofline"]["frac"] < 1.0 and d["roofline"]["bound"] == "tensor"
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if gpus == 1:
+            assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    ref = json.load(open(os.path.join(PROF, "r1_final_reference_arm_line.json")))
+    assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0
