@@ -370,7 +370,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=512, help="rays per GPU per step")
-    ap.add_argument("--ref-rays", type=int, default=128, help="rays per step of the CPU reference arm")
+    ap.add_argument("--ref-rays", type=int, default=512,
+                    help="rays per step of the CPU reference arm (default: the benchmarked 512-ray step, ~1.2 s each)")
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--debug-flags", type=int, default=0, help="library tuning/bisect flags (development only)")
