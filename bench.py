@@ -238,6 +238,8 @@ def run_ours(args):
                 print("bench: CUDA graph capture failed (%s); re-running with --no-graph" % str(ex).splitlines()[0],
                       file=sys.stderr)
             if world == 1:
+                sys.stdout.flush()
+                os.dup2(real_stdout, 1)                                     # the re-executed process prints the JSON line
                 os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
             raise
 
