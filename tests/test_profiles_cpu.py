@@ -46,3 +46,22 @@ def test_bench_lines_follow_the_contract():
             assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     ref = json.load(open(os.path.join(PROF, "r1_final_reference_arm_line.json")))
     assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_clock_sampler_windows_its_samples():
+    """bench.ClockSampler.summary: samples inside [mark_begin, mark_end] decide; with none inside (a timed region shorter
+    than one nvidia-smi call) the nearest samples are reported and labelled as such."""
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    mk = lambda sm, t, pw="Not Active": [str(sm), "1965", "Not Active", "Not Active", "Not Active", pw, t]
+    s.rows = [mk(600, 10.0), mk(1965, 20.0, "Active"), mk(1950, 21.0), mk(700, 30.0)]
+    s.t0, s.t1 = 19.5, 21.5
+    r = s.summary()
+    assert r["sm_mhz"] in (1950.0, 1965.0) and r["samples"] == 2 and r["window"] == "timed regions"
+    assert r["reasons"] == ["sw_power_cap"]
+    s.t0, s.t1 = 24.9, 25.1
+    r = s.summary()
+    assert r["window"] == "nearest samples" and r["samples"] == 3
+    s.rows = []
+    assert s.summary()["reasons"] == ["unavailable"]
