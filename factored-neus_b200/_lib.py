@@ -43,17 +43,33 @@ class NerfCfg(Structure):
                 ("multires_view", c_int), ("skip", c_int)]
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> factored-neus_b200/libfneus_b200.so"""
+def source_digest() -> str:
+    """SHA-256 over every source the library is compiled from (csrc/*, include/fneus.h) and the compiler flags."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
-    hdr = os.path.join(os.path.dirname(_HERE), "include", "fneus.h")
-    newest = max(os.path.getmtime(p) for p in srcs + [hdr])
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+    for p in srcs + [os.path.join(os.path.dirname(_HERE), "include", "fneus.h")]:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> factored-neus_b200/libfneus_b200.so
+
+    The library is rebuilt whenever the digest of its sources differs from the one recorded next to it at the last
+    build (``libfneus_b200.so.digest``; file times are not trusted: a fresh clone or snapshot resets them)."""
+    digest = source_digest()
+    stamp = LIB_PATH + ".digest"
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB_PATH
     cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "libfneus.cu")]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, cwd=CSRC)
+    with open(stamp, "w") as f:
+        f.write(digest + "\n")
     return LIB_PATH
 
 

@@ -364,10 +364,15 @@ int fneus_composite_fwd(const float* sdf, const float* normals, const float* rgb
   if (!sdf || !normals || !rgb || !dists || !pts || !rays_d || !inv_s || !color || !weights || !weight_sum ||
       !weight_max || !cdf || !inside || !eik_part || !hit_idx || !w_pair)
     return FNEUS_ERR_NULL;
-  if (B < 0 || n_in < 1 || n_out < 0 || n_in + n_out > 4096) return FNEUS_ERR_BAD_SHAPE;
+  // same bound as the backward entry: a shape accepted here can always be back-propagated
+  if (B < 0 || n_in < 1 || n_out < 0 || n_in + n_out > 2048) return FNEUS_ERR_BAD_SHAPE;
   if ((n_out > 0) && (!bg_alpha || !bg_color)) return FNEUS_ERR_NULL;
   if ((bg_alpha == nullptr) != (bg_color == nullptr)) return FNEUS_ERR_NULL;
   size_t smem = (size_t)COMP_WARPS * n_in * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fneus_cuda_error((int)e);
+  }
   prof_begin(PC_COMPOSITE, 0.0, (double)B * ((n_in + n_out) * 44.0 + 100.0), (cudaStream_t)stream);
   composite_fwd_kernel<<<cdiv(B, COMP_WARPS), COMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
       sdf, normals, rgb, dists, pts, rays_d, bg_alpha, bg_color, bg_rgb, B, n_in, n_out, inv_s, cos_anneal_ratio,

@@ -5,6 +5,7 @@
 #include "prof.cuh"
 
 namespace fneus {
+int num_sms();
 
 // ---- surface blend: out_k = hit ? (c0_k w0 + c1_k w1) / (w0 + w1) : 1, for k over the three colour sets --------------
 __global__ void surface_blend_fwd_kernel(const float* __restrict__ c_rgb, const float* __restrict__ c_spec,
@@ -264,7 +265,7 @@ int fneus_adam_step(float* p, float* g, float* m, float* v, long long n, float* 
   prof_end(st);
   const long long n4 = n / 4;
   long long blocks = cdiv(n4 > 0 ? n4 : 1, 256);
-  if (blocks > 4 * 148) blocks = 4 * 148;
+  if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
   prof_begin(PC_ELEMENTWISE, 0.0, 32.0 * (double)n, st);
   adam_step_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n4, n, state4, beta1, beta2, eps, grad_scale, zero_grad);
   prof_end(st);

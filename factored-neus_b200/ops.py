@@ -67,9 +67,14 @@ class PackWeights(torch.autograd.Function):
     """(layout, *params) -> flat FP32 pack.  ``layout`` = list of (kind, i_g, i_v, rows, cols) over ``params``:
     kind 'wn' -> W = g*v/|v|_row (torch weight_norm, fields.py:67-68), 'copy' -> the tensor itself.
 
-    Backward writes dg/dv/db in one launch.  If every parameter already owns a contiguous ``.grad`` buffer
-    (e.g. views into ``parallel.GradBucket``) the kernel accumulates into those buffers directly and autograd
-    receives no gradient tensors (saves one AccumulateGrad kernel per parameter)."""
+    Backward writes dg/dv/db in one launch and returns the gradients to autograd like any other Function (hooks,
+    ``torch.autograd.grad`` and DDP reducers see them).
+
+    Direct accumulation is an explicit OPT-IN: parameters registered with ``parallel.GradBucket(direct=True)`` carry
+    ``_fneus_direct_grad`` and own a ``.grad`` view into the flat bucket; only when EVERY trainable parameter of the
+    pack is registered that way does the kernel accumulate straight into those buffers (autograd then receives
+    ``None``: one AccumulateGrad kernel per parameter saved).  In that mode tensor hooks, post-accumulate hooks,
+    ``torch.autograd.grad`` and DDP are not supported for these parameters -- the bucket's all-reduce replaces them."""
 
     @staticmethod
     def forward(ctx, layout, *params):
@@ -103,7 +108,8 @@ class PackWeights(torch.autograd.Function):
         g, v, off, rows, cols = ctx.meta
         n = len(layout)
         dflat = _f32c(dflat)
-        direct = all((p.grad is not None and p.grad.is_contiguous()) or not p.requires_grad for p in params)
+        direct = all((getattr(p, "_fneus_direct_grad", False) and p.grad is not None and p.grad.is_contiguous())
+                     or not p.requires_grad for p in params)
         grads = [None] * len(params)
         if not direct:
             grads = [torch.zeros_like(p) if p.requires_grad else None for p in params]

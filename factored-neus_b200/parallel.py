@@ -60,17 +60,24 @@ def stage1_loss_sharded(renderer, out, true_rgb, mask, surface_weight=0.1, igr_w
 
 
 class GradBucket:
-    """Single flat FP32 gradient bucket over a fixed parameter list; one all-reduce(sum) per step."""
+    """Single flat FP32 gradient bucket over a fixed parameter list; one all-reduce(sum) per step.
 
-    def __init__(self, params, group=None):
+    ``direct=True`` (default) additionally registers the parameters for direct accumulation: the weight-pack
+    backward (``ops.PackWeights``) then adds into the bucket views itself and hands autograd no gradient tensors.
+    Tensor / post-accumulate hooks, ``torch.autograd.grad`` and DDP do not see those gradients; pass
+    ``direct=False`` to keep plain autograd semantics (the ``.grad`` views still alias the bucket)."""
+
+    def __init__(self, params, group=None, direct=True):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.direct = direct
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:          # parameters' .grad become views into the bucket: backward writes in place
             p.grad = self.flat[off: off + p.numel()].view_as(p)
+            p._fneus_direct_grad = bool(direct)
             off += p.numel()
 
     def zero(self):
@@ -106,12 +113,90 @@ class FlatAdam:
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
         self.state = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._host_it = 0                   # host mirror of state[0] (graph replays advance it through step())
+        self._moments_restored = False
+
+    # ---- torch.optim.Adam surface used by the reference's Runner (exp_runner.py:179-181,196,237,261,273) ----
+    def _lr_at(self, it):
+        import math
+        if it < self.warm_up_end:
+            f = it / self.warm_up_end
+        else:
+            prog = (it - self.warm_up_end) / max(1.0, self.end_iter - self.warm_up_end)
+            f = (math.cos(math.pi * prog) + 1.0) * 0.5 * (1 - self.lr_alpha) + self.lr_alpha
+        return self.base_lr * f
+
+    @property
+    def param_groups(self):
+        """One group, like the reference's ``Adam(params_to_train, lr)``.  ``lr`` is the value the NEXT step will use
+        (host restatement of the device schedule; the device-resident schedule is authoritative, so writes to this
+        dict by ``update_learning_rate`` (exp_runner.py:237) are accepted and ignored)."""
+        return [{"lr": self._lr_at(self._host_it), "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0,
+                 "amsgrad": False, "params": list(range(len(self.bucket.params)))}]
+
+    def zero_grad(self, set_to_none=False):
+        """The fused step clears the bucket itself; an explicit call clears it too (the ``.grad`` views stay)."""
+        self.bucket.zero()
+
+    def state_dict(self):
+        """``torch.optim.Adam.state_dict()`` layout (per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``), so that
+        the reference's ``save_checkpoint`` / ``load_checkpoint`` (exp_runner.py:253-278) work unchanged and
+        checkpoints move freely between the two implementations."""
+        it = float(self._host_it)
+        state, off = {}, 0
+        for i, p in enumerate(self.bucket.params):
+            k = p.numel()
+            if it > 0:
+                state[i] = {"step": torch.tensor(it), "exp_avg": self.m[off: off + k].view_as(p).clone(),
+                            "exp_avg_sq": self.v[off: off + k].view_as(p).clone()}
+            off += k
+        return {"state": state, "param_groups": [dict(self.param_groups[0], foreach=None, maximize=False,
+                                                      capturable=False, differentiable=False, fused=None)]}
+
+    def load_state_dict(self, sd):
+        """Accepts this class's own ``state_dict()`` and a reference ``torch.optim.Adam`` one over the same parameter
+        order: restores both moments and the step counter (bias corrections and schedule follow from it)."""
+        groups = sd["param_groups"]
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(self.bucket.params):
+            raise ValueError("FlatAdam.load_state_dict: %d parameters in the checkpoint, %d here"
+                             % (len(order), len(self.bucket.params)))
+        steps, off = set(), 0
+        with torch.no_grad():
+            for idx, p in zip(order, self.bucket.params):
+                k = p.numel()
+                st = sd["state"].get(idx)
+                if st is None:
+                    self.m[off: off + k].zero_()
+                    self.v[off: off + k].zero_()
+                else:
+                    if st["exp_avg"].numel() != k:
+                        raise ValueError("FlatAdam.load_state_dict: parameter %d has %d elements, checkpoint %d"
+                                         % (idx, k, st["exp_avg"].numel()))
+                    self.m[off: off + k].copy_(st["exp_avg"].reshape(-1))
+                    self.v[off: off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(int(float(st["step"])))
+                off += k
+        if len(steps) > 1:
+            raise ValueError("FlatAdam.load_state_dict: parameters disagree on the step count %s" % sorted(steps))
+        self._set_it(steps.pop() if steps else 0)
+        self._moments_restored = True
+
+    def _set_it(self, it):
+        self._host_it = int(it)
+        self.state[0] = float(it)
 
     def set_iteration(self, it: int):
-        """Resume support (exp_runner.py:266-275 restores iter_step)."""
-        self.state[0] = float(it)
+        """Move the schedule / bias-correction counter WITHOUT restoring the moments -- only meaningful at iteration 0
+        or for benchmarking at a given learning rate.  Resuming a run must go through ``load_state_dict``: with zeroed
+        moments and bias corrections already near 1 the first updates would be ~3x a normal Adam step."""
+        if it > 0 and not self._moments_restored and self._host_it == 0:
+            import warnings
+            warnings.warn("FlatAdam.set_iteration(%d) with zeroed moments: use load_state_dict() to resume a run" % it)
+        self._set_it(it)
 
     def step(self):
         from . import ops
         ops.adam_step(self.flat_p, self.bucket.flat, self.m, self.v, self.state, self.base_lr, self.lr_alpha,
                       self.warm_up_end, self.end_iter, self.betas[0], self.betas[1], self.eps, 1.0, True)
+        self._host_it += 1

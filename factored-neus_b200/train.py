@@ -74,6 +74,7 @@ class Stage1Trainer:
             loss = self._eager_step(batch)
         else:
             cur = torch.cuda.current_stream()
+            host_it = self.optimizer._host_it
             self._stream.wait_stream(cur)
             with torch.cuda.stream(self._stream):
                 self._static_batch.copy_(batch, non_blocking=True)
@@ -87,6 +88,7 @@ class Stage1Trainer:
                             self._static_loss = self._eager_step(self._static_batch)
                     self._graph.replay()
             cur.wait_stream(self._stream)
+            self.optimizer._host_it = host_it + 1       # one optimiser step ran, however it was issued (eager/capture+replay)
             loss = self._static_loss
         self.iter_step += 1
         return loss

@@ -118,3 +118,48 @@ def test_fanout_gather_rows_gradients_match_autograd():
     g_s, = torch.autograd.grad(loss_fan(x0, use_dense=False), x0)
     g_s_ref, = torch.autograd.grad((x0.index_select(0, rows) ** 2 * w_rows).sum(), x0)
     assert torch.allclose(g_s, g_s_ref, atol=1e-6)
+
+
+def test_flat_adam_state_dict_round_trips_with_torch_adam():
+    """exp_runner.py:261,273: the reference saves / loads ``optimizer.state_dict()``.  FlatAdam speaks torch.optim.Adam's
+    layout in both directions (host-side bookkeeping only: no kernel runs)."""
+    from factored_neus_b200.parallel import FlatAdam, GradBucket
+    torch.manual_seed(0)
+    shapes = [(5, 3), (5,), (2, 2, 2)]
+    ref = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+    topt = torch.optim.Adam(ref, lr=5e-4)
+    for _ in range(3):
+        for p in ref:
+            p.grad = torch.randn_like(p)
+        topt.step()
+    sd = topt.state_dict()
+    ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    opt = FlatAdam(GradBucket(ours), lr=5e-4, warm_up_end=10, end_iter=100)
+    assert opt.param_groups[0]["lr"] == 0.0 and len(opt.state_dict()["state"]) == 0
+    opt.load_state_dict(sd)
+    assert int(opt.state[0]) == 3 and opt._host_it == 3
+    assert abs(opt.param_groups[0]["lr"] - 5e-4 * 3 / 10) < 1e-12
+    back = opt.state_dict()
+    for i, p in enumerate(ref):
+        assert torch.equal(back["state"][i]["exp_avg"], sd["state"][i]["exp_avg"])
+        assert torch.equal(back["state"][i]["exp_avg_sq"], sd["state"][i]["exp_avg_sq"])
+        assert float(back["state"][i]["step"]) == 3.0
+    topt2 = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ref], lr=5e-4)
+    topt2.load_state_dict(back)                       # and torch accepts ours
+    assert float(topt2.state_dict()["state"][0]["step"]) == 3.0
+    with pytest.raises(ValueError):
+        FlatAdam(GradBucket(ours[:2])).load_state_dict(sd)
+    with pytest.warns(UserWarning):
+        FlatAdam(GradBucket([torch.nn.Parameter(torch.zeros(3))])).set_iteration(50)
+
+
+def test_pack_weights_direct_mode_is_opt_in():
+    """direct accumulation into .grad must be an explicit opt-in (GradBucket(direct=True)), never inferred
+    from the mere presence of a .grad tensor."""
+    from factored_neus_b200.parallel import GradBucket
+    p = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(4))]
+    assert not getattr(p[0], "_fneus_direct_grad", False)
+    GradBucket(p, direct=False)
+    assert p[0].grad is not None and not p[0]._fneus_direct_grad
+    GradBucket(p)
+    assert p[0]._fneus_direct_grad and p[1]._fneus_direct_grad

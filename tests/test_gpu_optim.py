@@ -43,3 +43,49 @@ def test_flat_adam_matches_torch_adam():
     for p, q in zip(ours, ref):
         assert p.data_ptr() >= opt.flat_p.data_ptr()          # parameters are views of the flat buffer
         assert float((p - q).abs().max()) < 2e-6
+
+
+def test_flat_adam_resume_equals_uninterrupted_run():
+    """a resume through state_dict()/load_state_dict() continues exactly (moments + counter), where
+    set_iteration() alone would restart with zero moments."""
+    torch.manual_seed(1)
+    shapes = [(64, 39), (64,), (17, 64)]
+    init = [torch.randn(s, device=DEV) for s in shapes]
+    grads = [[torch.randn(s, device=DEV) for s in shapes] for _ in range(12)]
+
+    def make():
+        ps = [torch.nn.Parameter(t.clone()) for t in init]
+        return ps, FlatAdam(GradBucket(ps), lr=5e-4, warm_up_end=4, end_iter=30)
+
+    def run(ps, opt, its):
+        for it in its:
+            for p, g in zip(ps, grads[it]):
+                p.grad.copy_(g)
+            opt.step()
+
+    pa, oa = make()
+    run(pa, oa, range(12))
+    pb, ob = make()
+    run(pb, ob, range(7))
+    sd = ob.state_dict()
+    pc = [torch.nn.Parameter(p.detach().clone()) for p in pb]
+    oc = FlatAdam(GradBucket(pc), lr=5e-4, warm_up_end=4, end_iter=30)
+    oc.load_state_dict(sd)
+    assert oc.param_groups[0]["lr"] == ob.param_groups[0]["lr"]
+    run(pc, oc, range(7, 12))
+    for a, c in zip(pa, pc):
+        assert float((a - c).abs().max()) == 0.0
+
+
+def test_pack_weights_returns_grads_to_autograd_without_bucket():
+    """Without a GradBucket the weight-pack backward is an ordinary autograd node: torch.autograd.grad sees the
+    gradients and .grad is not touched behind autograd's back."""
+    import factored_neus_b200 as fn
+    syn = fn.synthetic
+    col = fn.RenderingNetwork(**syn.COLOR_CONF).to(DEV)
+    for p in col.parameters():
+        p.grad = torch.zeros_like(p)            # a pre-existing .grad must NOT switch direct mode on
+    w = col.flat_weights()
+    gs = torch.autograd.grad((w * w).sum(), list(col.parameters()))
+    assert all(g is not None and float(g.abs().max()) > 0 for g in gs)
+    assert all(float(p.grad.abs().max()) == 0.0 for p in col.parameters())
