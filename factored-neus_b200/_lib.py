@@ -132,6 +132,8 @@ _SIGNATURES = {
     "fneus_outside_alpha_bwd": (c_int, [_P, _P, _P, _P, _P, _LL, _P, _P, _P]),
     "fneus_ray_points": (c_int, [_P, _P, _P, _LL, c_int, _P, _P]),
     "fneus_upsample_step": (c_int, [_P, _P, _P, _P, _LL, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
+    "fneus_upsample_step_dev": (c_int, [_P, _P, _P, _P, _LL, c_int, c_int, _P, _P, _P, _P]),
+    "fneus_first_hit_secant": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _LL, c_int, _P, _P, _P, _P, _P, _P]),
     "fneus_inverse_cdf": (c_int, [_P, _P, _P, _LL, c_int, c_int, _P, _P, _P]),
     "fneus_merge_sorted": (c_int, [_P, _P, _P, _P, _LL, c_int, c_int, _P, _P, _P]),
     "fneus_core_geometry": (c_int, [_P, _P, _P, _LL, c_int, c_float, _P, _P, _P, _P, _P]),

@@ -178,6 +178,29 @@ __device__ __forceinline__ unsigned short f32_to_bf16_bits(float v) {
   return (unsigned short)(u >> 16);
 }
 
+// ---------------------------------------------------------------------------------------------
+// 16-bit operand formats of the tensor-core path.  FORWARD-path operands (positional encodings, activations h_l,
+// the normal chain's q_l, ReLU activations, their weight images) are FP16: 11 significant bits, i.e. 8x finer
+// than BF16, which is what the SDF value needs (inv_s amplifies its error inside the sigmoids; with BF16 operands
+// the rendered PSNR sat 0.10-0.18 dB below FP32, with FP16 it is within 0.01 dB) -- their dynamic range is benign
+// (activations O(1), weights O(0.1); conversions saturate).  BACKWARD-path operands (upstream gradients: 1e-7 and
+// below at 65 536 points per step) stay BF16 for its FP32-sized exponent.  tcgen05.mma kind::f16 takes the two
+// formats per operand (instruction descriptor bits 7-9 / 10-12), so weight-gradient GEMMs mix them freely.
+// ---------------------------------------------------------------------------------------------
+enum Fmt16 { FMT_BF16 = 0, FMT_F16 = 1 };
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ unsigned short f32_to_f16_bits(float v) { return (unsigned short)(pack_f16x2(v, 0.f) & 0xFFFFu); }
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t w) {
+  float2 r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "r"(w));
+  return r;
+}
+
 // Softplus(beta) with torch's threshold 20 (fields.py:72), and its derivative recovered from the
 // stored activation h = softplus(a):  sigma'(a) = 1 - exp(-beta h)   (SURVEY.md A.1).
 __device__ __forceinline__ float softplus_beta(float a, float beta) {

@@ -110,12 +110,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor: BF16 x BF16 -> FP32, M = 128
-__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+// instruction descriptor: {BF16 | FP16} x {BF16 | FP16} -> FP32, M = 128 (kind::f16 takes the format per operand)
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, bool a_f16 = false,
+                                               bool b_f16 = false) {
   uint32_t d = 0;
   d |= 1u << 4;                       // c_format = F32
-  d |= 1u << 7;                       // a_format = BF16
-  d |= 1u << 10;                      // b_format = BF16
+  d |= (a_f16 ? 0u : 1u) << 7;        // a_format: 0 = F16, 1 = BF16
+  d |= (b_f16 ? 0u : 1u) << 10;       // b_format
   d |= (uint32_t)(a_mn_major & 1) << 15;
   d |= (uint32_t)(b_mn_major & 1) << 16;
   d |= (uint32_t)(n >> 3) << 17;
@@ -131,6 +132,25 @@ __device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
   r.y = *reinterpret_cast<uint32_t*>(&hi);
   return r;
 }
+__device__ __forceinline__ uint2 pack_f16x4(float4 v) { return make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w)); }
+// 8 consecutive 16-bit elements (one 16-byte chunk) <-> FP32
+__device__ __forceinline__ void u16x8_to_f32(const uint4 u, bool f16, float* out) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  if (f16) {
+#pragma unroll
+    for (int t = 0; t < 4; t++) { const float2 f = unpack_f16x2(w[t]); out[2 * t] = f.x; out[2 * t + 1] = f.y; }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; t++) { out[2 * t] = __uint_as_float(w[t] << 16); out[2 * t + 1] = __uint_as_float(w[t] & 0xFFFF0000u); }
+  }
+}
+__device__ __forceinline__ uint4 f32x8_to_u16(const float* y, bool f16) {
+  if (f16) return make_uint4(pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]), pack_f16x2(y[4], y[5]), pack_f16x2(y[6], y[7]));
+  const uint2 lo = pack_bf16x4(make_float4(y[0], y[1], y[2], y[3]));
+  const uint2 hi = pack_bf16x4(make_float4(y[4], y[5], y[6], y[7]));
+  return make_uint4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ unsigned short f32_to_u16_bits(float v, bool f16) { return f16 ? f32_to_f16_bits(v) : f32_to_bf16_bits(v); }
 // K-major tile [rows][64]: row r, element k (multiple of 4)
 __device__ __forceinline__ void sts_kmajor(uint8_t* tile, int r, int k, float4 v) {
   int off = (r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + ((k & 7) << 1);
@@ -279,6 +299,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, float* wbuf, const 
 struct TcSmem {
   uint64_t full[TC_STAGES];
   uint64_t empty[TC_STAGES];
+  uint64_t conv[TC_STAGES];           // weight-gradient kernel: stage converted to a common operand format
   uint64_t accum;
   uint32_t tmem_base;
 };
@@ -443,7 +464,7 @@ tc_gemm_mk_kernel(ASeg a, const float* __restrict__ W, int ldw, int wout0, int M
 }
 
 // sum over the 64 reduction rows of column n (0..127) of a BF16 MN-major dY^T tile in shared memory
-__device__ __forceinline__ float wgrad_col_sum(const uint8_t* sA, int n) {
+__device__ __forceinline__ float wgrad_col_sum(const uint8_t* sA, int n, bool f16) {
   const uint8_t* tile = sA + (n >> 6) * 8192 + ((n & 7) << 1);
   const int ch = (n & 63) >> 3;
   float acc = 0.f;
@@ -451,9 +472,19 @@ __device__ __forceinline__ float wgrad_col_sum(const uint8_t* sA, int n) {
   for (int kk = 0; kk < 64; kk++) {
     unsigned short b16 = *reinterpret_cast<const unsigned short*>(tile + (kk >> 3) * 1024 + (kk & 7) * 128 +
                                                                  (((ch ^ (kk & 7)) & 7) << 4));
-    acc += __uint_as_float((unsigned)b16 << 16);
+    acc += f16 ? unpack_f16x2((uint32_t)b16).x : __uint_as_float((unsigned)b16 << 16);
   }
   return acc;
+}
+
+// FP16 -> BF16 in place over `bytes` of a landed stage (threads 0..127, 16-byte chunks: the layout is unchanged)
+__device__ __forceinline__ void wgrad_to_bf16(uint8_t* tile, int bytes, int tid) {
+#pragma unroll 4
+  for (int i = tid * 16; i < bytes; i += 128 * 16) {
+    float v[8];
+    u16x8_to_f32(*reinterpret_cast<const uint4*>(tile + i), true, v);
+    *reinterpret_cast<uint4*>(tile + i) = f32x8_to_u16(v, false);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -463,9 +494,15 @@ __device__ __forceinline__ float wgrad_col_sum(const uint8_t* sA, int n) {
 // warp 5 (their tile bytes ARE the MN-major shared-memory operand); FP32 row-major / generated operands are
 // converted by the four producer warps.
 // ---------------------------------------------------------------------------------------------
+// y_f16 / x_f16: element format of an IMAGE operand (forward-path images are FP16, backward-path ones BF16); operands
+// converted from FP32 by the producer warps are always BF16.  tcgen05.mma kind::f16 wants ONE format for both operands
+// (a mixed descriptor raises an illegal-instruction fault on sm_100a), so when exactly one operand is an FP16 image the
+// otherwise idle warps 0-3 rewrite that stage FP16 -> BF16 in place (exact for |v| >= 2^-14 up to BF16's 8 bits; the
+// gradient operand keeps its BF16 exponent range) and hand the stage on through `conv`.
 __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy, const ASeg& a, float* __restrict__ dW,
                                            int ldw, int wout0, float* __restrict__ db, int M, int N, int m_per_split,
-                                           const int bx, const int by) {
+                                           const int bx, const int by, const bool y_f16 = false,
+                                           const bool x_f16 = false) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared
                                                  // address space (an integer round trip turned every access into a generic LD.E / ST.E)
@@ -500,11 +537,17 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
   const bool do_bias = db != nullptr && kc == 0 && !y_img;
   // image dY: the bias gradient is summed from the shared-memory tile by warps 0-3 (they hold the stage open)
   const bool bias_smem = db != nullptr && kc == 0 && y_img;
+  const bool yf = y_img && y_f16, xf = x_img && x_f16;
+  const bool conv_y = yf && !xf, conv_x = xf && !yf, any_conv = conv_y || conv_x;
+  const int yblocks = y_img ? min(2, -ldy - nt * 2) : 0;
+  const int xblocks = x_img ? min((Nc + 63) / 64, -a.ldm - (k0 >> 6)) : 0;
 
   if (tid == 0) {
     const int cnt = (need_prod ? 128 : 0) + ((y_img || x_img) ? 1 : 0);
 #pragma unroll
-    for (int s = 0; s < TC_STAGES; s++) { mbar_init(&ctl->full[s], cnt); mbar_init(&ctl->empty[s], bias_smem ? 129 : 1); }
+    for (int s = 0; s < TC_STAGES; s++) {
+      mbar_init(&ctl->full[s], cnt); mbar_init(&ctl->empty[s], bias_smem ? 129 : 1); mbar_init(&ctl->conv[s], 128);
+    }
     mbar_init(&ctl->accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -517,8 +560,6 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
   if (warp == 5) {
     if (lane == 0 && (y_img || x_img)) {
       const int ykbs = -ldy, xkbs = -a.ldm;
-      const int yblocks = y_img ? min(2, ykbs - nt * 2) : 0;
-      const int xblocks = x_img ? min((Nc + 63) / 64, xkbs - (k0 >> 6)) : 0;
       for (int kb = 0; kb < KB; kb++) {
         const int s = kb % TC_STAGES;
         if (kb >= TC_STAGES) mbar_wait(&ctl->empty[s], ((kb / TC_STAGES) - 1) & 1);
@@ -600,18 +641,32 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
         }
         fence_proxy_async();
         mbar_arrive(&ctl->full[s]);
-        if (bias_smem) {
+        if (any_conv || bias_smem) {
           mbar_wait(&ctl->full[s], (kb / TC_STAGES) & 1);
-          bcol += wgrad_col_sum(sA[s], tid);
-          mbar_arrive(&ctl->empty[s]);
+          if (any_conv) {
+            wgrad_to_bf16(conv_y ? sA[s] : sB[s], (conv_y ? yblocks : xblocks) * 8192, tid);
+            fence_proxy_async();
+            mbar_arrive(&ctl->conv[s]);
+          }
+          if (bias_smem) {
+            bcol += wgrad_col_sum(sA[s], tid, yf && !conv_y);
+            mbar_arrive(&ctl->empty[s]);
+          }
         }
       }
-    } else if (bias_smem) {
+    } else if (any_conv || bias_smem) {
       for (int kb = 0; kb < KB; kb++) {
         const int s = kb % TC_STAGES;
         mbar_wait(&ctl->full[s], (kb / TC_STAGES) & 1);
-        bcol += wgrad_col_sum(sA[s], tid);
-        mbar_arrive(&ctl->empty[s]);
+        if (any_conv) {
+          wgrad_to_bf16(conv_y ? sA[s] : sB[s], (conv_y ? yblocks : xblocks) * 8192, tid);
+          fence_proxy_async();
+          mbar_arrive(&ctl->conv[s]);
+        }
+        if (bias_smem) {
+          bcol += wgrad_col_sum(sA[s], tid, yf && !conv_y);
+          mbar_arrive(&ctl->empty[s]);
+        }
       }
     }
     mbar_wait(&ctl->accum, 0);
@@ -645,10 +700,10 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
     }
     tc_fence_before();
   } else if (warp == 4 && lane == 0) {
-    const uint32_t idesc = make_idesc(Nc, 1, 1);
+    const uint32_t idesc = make_idesc(Nc, 1, 1, yf && !conv_y, xf && !conv_x);
     for (int kb = 0; kb < KB; kb++) {
       const int s = kb % TC_STAGES;
-      mbar_wait(&ctl->full[s], (kb / TC_STAGES) & 1);
+      mbar_wait(any_conv ? &ctl->conv[s] : &ctl->full[s], (kb / TC_STAGES) & 1);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(sA[s]), b_addr = smem_u32(sB[s]);
 #pragma unroll
@@ -684,12 +739,14 @@ struct WgradJob {
   float* dW; int ldw, wout0;
   float* db;
   int N, m_per_split, tiles, splits;
+  int y_f16, x_f16;                  // element format of the image operands (0 = BF16, 1 = FP16)
 };
 struct WgradJobs { int n; int M; WgradJob job[WG_MAX_JOBS]; };
 __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_wgrad_group_kernel(const __grid_constant__ WgradJobs jobs) {
   const WgradJob& j = jobs.job[blockIdx.z];
   if ((int)blockIdx.x >= j.tiles || (int)blockIdx.y >= j.splits) return;
-  wgrad_body(j.dY, j.ldy, j.a, j.dW, j.ldw, j.wout0, j.db, jobs.M, j.N, j.m_per_split, blockIdx.x, blockIdx.y);
+  wgrad_body(j.dY, j.ldy, j.a, j.dW, j.ldw, j.wout0, j.db, jobs.M, j.N, j.m_per_split, blockIdx.x, blockIdx.y, j.y_f16 != 0,
+             j.x_f16 != 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1112,7 +1169,7 @@ __global__ void pack_wimg_kernel(const float* __restrict__ W, int ldw, int wout0
 constexpr int PACK_MAX_JOBS = 24;
 struct PackJob {
   const float* W; uint8_t* img;
-  int ldw, wout0, N, wred_gen, kgen, wred_mem, kmem, for_bwd_data;
+  int ldw, wout0, N, wred_gen, kgen, wred_mem, kmem, for_bwd_data, f16;
 };
 struct PackJobs { int n; PackJob job[PACK_MAX_JOBS]; };
 
@@ -1151,9 +1208,7 @@ __device__ __forceinline__ void pack_wimg_chunk(const PackJob& j, long long idx)
     }
     off = nb * 8192 + (kr >> 3) * 1024 + (kr & 7) * 128 + (((c ^ (kr & 7)) & 7) << 4);
   }
-  uint2 lo = pack_bf16x4(make_float4(v[0], v[1], v[2], v[3]));
-  uint2 hi = pack_bf16x4(make_float4(v[4], v[5], v[6], v[7]));
-  *reinterpret_cast<uint4*>(j.img + (size_t)tile * TC_B_BYTES + off) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  *reinterpret_cast<uint4*>(j.img + (size_t)tile * TC_B_BYTES + off) = f32x8_to_u16(v, j.f16 != 0);
 }
 __global__ void pack_wimg_multi_kernel(PackJobs jobs) {
   const PackJob& j = jobs.job[blockIdx.y];
@@ -1242,13 +1297,15 @@ struct WgradGroup {
   double flops;
   int num_sms;
   void reset(long long M, int sms) { jobs.n = 0; jobs.M = (int)M; flops = 0.0; num_sms = sms; }
-  void add(const float* dY, int ldy, const ASeg& a, float* dW, int ldw, int wout0, float* db, int N, cudaStream_t st) {
+  void add(const float* dY, int ldy, const ASeg& a, float* dW, int ldw, int wout0, float* db, int N, cudaStream_t st,
+           int y_f16 = 0, int x_f16 = 0) {
     const long long M = jobs.M;
     int kchunks = cdiv(a.gen.ncols, 256) + cdiv(a.kmem, 256);
     if (kchunks == 0 || M <= 0 || N <= 0) return;
     if (jobs.n == WG_MAX_JOBS) flush(st);
     WgradJob& j = jobs.job[jobs.n++];
     j.dY = dY; j.ldy = ldy; j.a = a; j.dW = dW; j.ldw = ldw; j.wout0 = wout0; j.db = db; j.N = N;
+    j.y_f16 = y_f16; j.x_f16 = x_f16;
     j.tiles = cdiv(N, 128) * kchunks;
     flops += 2.0 * (double)M * N * (a.gen.ncols + a.kmem);
   }
@@ -1305,14 +1362,14 @@ inline ImgArena arena_make(uint8_t* base, size_t cap) {
   return ar;
 }
 inline const uint8_t* make_wimg(ImgArena& ar, bool for_bwd_data, const float* W, int ldw, int wout0, int N,
-                                int wred_gen, int kgen, int wred_mem, int kmem, cudaStream_t st) {
+                                int wred_gen, int kgen, int wred_mem, int kmem, cudaStream_t st, int f16 = 0) {
   if (precision_mode() != 1) return nullptr;
   uint8_t* img = ar.take(wimg_bytes(N, kgen, kmem));
   if (!img) return nullptr;
   if (ar.jobs.n == PACK_MAX_JOBS) ar.flush(st);
   PackJob& j = ar.jobs.job[ar.jobs.n++];
   j.W = W; j.img = img; j.ldw = ldw; j.wout0 = wout0; j.N = N; j.wred_gen = wred_gen; j.kgen = kgen;
-  j.wred_mem = wred_mem; j.kmem = kmem; j.for_bwd_data = for_bwd_data ? 1 : 0;
+  j.wred_mem = wred_mem; j.kmem = kmem; j.for_bwd_data = for_bwd_data ? 1 : 0; j.f16 = f16;
   return img;
 }
 

@@ -72,7 +72,7 @@ __global__ void colsum_kernel(const float* X, int ldx, int K, const float* w, fl
 // four full 128-byte image rows per instruction.
 __global__ void colsum_img_kernel(const uint8_t* __restrict__ img, int kbs, int K, const float* __restrict__ w,
                                   float wscale, float* __restrict__ out, float* __restrict__ osum, long long M,
-                                  int rows_per_block) {
+                                  int rows_per_block, int f16) {
   const int cb = blockIdx.x;                       // column block
   const long long mbeg = (long long)blockIdx.y * rows_per_block;
   const long long mend = mbeg + rows_per_block < M ? mbeg + rows_per_block : M;
@@ -83,13 +83,10 @@ __global__ void colsum_img_kernel(const uint8_t* __restrict__ img, int kbs, int 
     const float wm = w ? __ldg(w + m) * wscale : 1.f;
     const uint8_t* p = img + ((size_t)(m >> 7) * kbs + cb) * 16384 + (((m & 127) >> 3) * 1024 + (m & 7) * 128) +
                        (((g ^ (int)(m & 7)) & 7) << 4);
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    uint32_t v[4] = {u.x, u.y, u.z, u.w};
+    float v[8];
+    u16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(p)), f16 != 0, v);
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-      acc[2 * t] += wm * __uint_as_float(v[t] << 16);
-      acc[2 * t + 1] += wm * __uint_as_float(v[t] & 0xFFFF0000u);
-    }
+    for (int t = 0; t < 8; t++) acc[t] += wm * v[t];
     if (g == 0) ws += wm;
   }
   __shared__ float red[64];
@@ -168,13 +165,13 @@ __global__ void grid_points_kernel(const float* __restrict__ ax, const float* __
 static inline int ew_blocks(long long n) { return cdiv(n, 256); }
 
 void launch_colsum(const float* X, int ldx, int K, const float* w, float wscale, float* out, float* osum, long long M,
-                   cudaStream_t st) {
+                   cudaStream_t st, int f16 = 0) {
   if (M <= 0 || K <= 0) return;
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   if (ldx < 0) {
     int rpb = 512;
     dim3 grid(cdiv(K, 64), cdiv(M, rpb));
-    colsum_img_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(X), -ldx, K, w, wscale, out, osum, M, rpb);
+    colsum_img_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(X), -ldx, K, w, wscale, out, osum, M, rpb, f16);
   } else {
     int mpb = 256;
     dim3 grid(cdiv(K, 256), cdiv(M, mpb));
@@ -286,16 +283,16 @@ static GenSpec sdf_gen(const fneus_sdf_cfg* c, const float* x, const float* tan)
 // All weight images one pass needs, declared up front and packed by ONE launch (ImgArena::flush).
 struct SdfImgs { const uint8_t* F[20]; const uint8_t* B[20]; };
 static SdfImgs sdf_make_images(const fneus_sdf_cfg* c, const SdfPlan& p, const float* w, bool fwd, bool fwd_split_last,
-                               bool bwd_hidden, bool bwd_last, ImgArena& ar, cudaStream_t st) {
+                               bool bwd_hidden, bool bwd_last, ImgArena& ar, cudaStream_t st, int f16 = 0) {
   SdfImgs im;
   for (int l = 0; l <= p.L; l++) { im.F[l] = nullptr; im.B[l] = nullptr; }
   if (precision_mode() != 1) return im;
   for (int l = 0; l <= p.L; l++) {
     const float* W = w + p.woff[l];
-    if (fwd && l < p.L) im.F[l] = make_wimg(ar, false, W, p.in[l], 0, p.out[l], 0, l == 0 ? p.in[l] : 0, 0, l == 0 ? 0 : p.in[l], st);
-    if (fwd && l == p.L && fwd_split_last) im.F[l] = make_wimg(ar, false, W, p.in[l], 1, p.out[l] - 1, 0, 0, 0, p.in[l], st);
-    if (bwd_hidden && l < p.L) im.B[l] = make_wimg(ar, true, W, p.in[l], 0, p.in[l], 0, 0, 0, p.out[l], st);
-    if (bwd_last && l == p.L) im.B[l] = make_wimg(ar, true, W, p.in[l], 0, p.in[l], 0, 0, 1, c->d_out - 1, st);
+    if (fwd && l < p.L) im.F[l] = make_wimg(ar, false, W, p.in[l], 0, p.out[l], 0, l == 0 ? p.in[l] : 0, 0, l == 0 ? 0 : p.in[l], st, f16);
+    if (fwd && l == p.L && fwd_split_last) im.F[l] = make_wimg(ar, false, W, p.in[l], 1, p.out[l] - 1, 0, 0, 0, p.in[l], st, f16);
+    if (bwd_hidden && l < p.L) im.B[l] = make_wimg(ar, true, W, p.in[l], 0, p.in[l], 0, 0, 0, p.out[l], st, f16);
+    if (bwd_last && l == p.L) im.B[l] = make_wimg(ar, true, W, p.in[l], 0, p.in[l], 0, 0, 1, c->d_out - 1, st, f16);
   }
   ar.flush(st);
   return im;
@@ -486,13 +483,16 @@ int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   if (chunk < 128) return FNEUS_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
-  SdfImgs im = sdf_make_images(cfg, p, wpack, true, feat_out != nullptr, false, false, ar, st);
+  // the forward chain kernel computes on FP16 operands; the older pair-tile fallback kernel and the layered path on BF16
+  const int f16 = sdf_chain_ok(cfg, p) ? 1 : 0;
+  SdfImgs im = sdf_make_images(cfg, p, wpack, true, feat_out != nullptr, false, false, ar, st, f16);
   if (p.img && !feat_out && sdf_fused_ok(p) && im.F[0]) {
     int rc = sdf_fused_launch(cfg, p, wpack, x, n, sdf_out, 1.f, im, st);
     if (rc) return rc;
     FNEUS_CHECK_LAUNCH();
     return FNEUS_OK;
   }
+  if (f16 && feat_out && (!im.F[0] || !im.F[p.L])) return FNEUS_ERR_WORKSPACE;   // FP16 images only fit the chain kernel
   if (feat_out && im.F[0] && im.F[p.L] && sdf_chain_ok(cfg, p)) {
     sdf_chain_value_launch(cfg, p, wpack, x, n, sdf_out, feat_out, 1.f, im, st);
     FNEUS_CHECK_LAUNCH();
@@ -530,7 +530,7 @@ int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax
   cudaStream_t st = (cudaStream_t)stream;
   scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
   long long i0 = (long long)ix0 * ny * nz, i1 = (long long)ix1 * ny * nz;
-  SdfImgs im = sdf_make_images(cfg, p, wpack, true, false, false, false, ar, st);
+  SdfImgs im = sdf_make_images(cfg, p, wpack, true, false, false, false, ar, st, sdf_chain_ok(cfg, p) ? 1 : 0);
   const bool fused = p.img && sdf_fused_ok(p) && im.F[0];
   for (long long b = i0; b < i1; b += chunk) {
     long long M = i1 - b < chunk ? i1 - b : chunk;
@@ -562,8 +562,12 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
         (reinterpret_cast<uintptr_t>(scratch + sdf_scratch_main(p, M)) + 1023) & ~(uintptr_t)1023);
     ar.cap = sdf_img_bytes(p) - 1024;
   }
-  SdfImgs im = sdf_make_images(cfg, p, wpack, true, true, normal_out != nullptr, false, ar, st);
-  if (sdf_chain_ok(cfg, p) && im.F[p.L] != nullptr && (!normal_out || im.B[0] != nullptr)) {
+  // The fused chain (FP16 forward images) is taken exactly when fneus_sdf_bwd will take its fused chain too -- value +
+  // normal graphs on an eligible network; a value-only graph runs layer by layer on BF16 images, like its backward.
+  const bool use_chain = sdf_chain_ok(cfg, p) && normal_out != nullptr;
+  SdfImgs im = sdf_make_images(cfg, p, wpack, true, true, normal_out != nullptr, false, ar, st, use_chain ? 1 : 0);
+  if (use_chain && (im.F[p.L] == nullptr || im.B[0] == nullptr)) return FNEUS_ERR_WORKSPACE;
+  if (use_chain) {
     const int L = p.L;
     const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
     SdfChainArgs g;
@@ -679,7 +683,10 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   }
 
   SdfImgs im = sdf_make_images(cfg, p, wpack, d_normal != nullptr, false, true, d_feat != nullptr, ar, st);
-  if (d_normal && d_feat && b.H[0] != nullptr && sdf_chain_ok(cfg, p) && im.F[0] != nullptr && im.B[L] != nullptr) {
+  // same predicate as fneus_sdf_fwd_grad: the forward pass of a value + normal graph left FP16 images
+  const bool fwd_was_chain = sdf_chain_ok(cfg, p) && d_normal != nullptr;
+  if (fwd_was_chain && (!d_feat || b.H[0] == nullptr || im.F[0] == nullptr || im.B[L] == nullptr)) return FNEUS_ERR_UNSUPPORTED;
+  if (fwd_was_chain) {
     float* G[20]; float* E[20]; float* A[20];
     for (int l = 0; l <= L; l++) G[l] = scratch + (long long)l * bf;
     for (int l = 0; l < L; l++) { E[l] = scratch + (long long)(L + 1 + l) * bf; A[l] = scratch + (long long)(2 * L + 1 + l) * bf; }
@@ -725,16 +732,16 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     wg.reset(M, sms);
     for (int l = 0; l < L; l++)
       wg.add(b.Q[l], p.ldout[l], aseg_mem(G[l], l == 0 ? -1 : p.ldin[l], p.in[l]), d_wpack + p.woff[l], p.in[l], 0, nullptr,
-             p.out[l], st);
+             p.out[l], st, /*q_l: forward image*/ 1, 0);
     for (int l = L - 1; l >= 0; l--)
       wg.add(A[l], p.ldout[l], aseg_mem(l == 0 ? b.H[0] : b.H[l], l == 0 ? -1 : p.ldin[l], p.in[l]), d_wpack + p.woff[l],
-             p.in[l], 0, d_wpack + p.boff[l], p.out[l], st);
+             p.in[l], 0, d_wpack + p.boff[l], p.out[l], st, 0, /*h_l: forward image*/ 1);
     wg.add(d_feat, cfg->d_out - 1, aseg_mem(b.H[L], p.ldin[L], p.in[L]), d_wpack + p.woff[L], p.in[L], 1,
-           d_wpack + p.boff[L], cfg->d_out - 1, st);
+           d_wpack + p.boff[L], cfg->d_out - 1, st, 0, 1);
     wg.flush(st);
     launch_colsum(G[L], p.ldin[L], p.in[L], nullptr, 1.f, d_wpack + p.woff[L], nullptr, M, st);
     if (d_sdf)
-      launch_colsum(b.H[L], p.ldin[L], p.in[L], d_sdf, 1.f / cfg->scale, d_wpack + p.woff[L], d_wpack + p.boff[L], M, st);
+      launch_colsum(b.H[L], p.ldin[L], p.in[L], d_sdf, 1.f / cfg->scale, d_wpack + p.woff[L], d_wpack + p.boff[L], M, st, 1);
     FNEUS_CHECK_LAUNCH();
     return FNEUS_OK;
   }

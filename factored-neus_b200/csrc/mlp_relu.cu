@@ -71,20 +71,27 @@ static bool chain_fusable(const Lin* lin, int n_lin, const ASeg& a0, int hid) {
 // defer: when non-null and the fused path applies, the chain is NOT launched; its arguments and FLOPs are returned for a
 // paired launch (relu_chain_pair_launch) and `defer->used` is set.
 struct ChainDefer { SdfChainArgs g; double flops; bool used; };
-static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs, int ldh,
+static bool relu_fwd_fused(const Lin* lin, int n_lin, const ASeg& a0, int ldh, int last_mode) {
+  return ldh < 0 && (last_mode == EPI_SIGMOID || last_mode == EPI_LINEAR) && -ldh == cdiv(lin[0].out, TC_BK) &&
+         chain_fusable(lin, n_lin, a0, lin[0].out);
+}
+static int relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs, int ldh,
                            int last_mode, float* out, int ld_out, long long M, cudaStream_t st, ImgArena& ar,
                            float* a0_img = nullptr, ChainDefer* defer = nullptr) {
   const uint8_t* img[16];
   bool all_img = true;
+  // the fused forward chain computes on FP16 operands and leaves FP16 activation images (relu_chain_bwd recomputes this
+  // predicate to know their format); the layered path stays BF16
+  const bool fuse = relu_fwd_fused(lin, n_lin, a0, ldh, last_mode);
   for (int l = 0; l < n_lin; l++) {
     ASeg a = l == 0 ? a0 : aseg_mem(Hs[l], ldh, lin[l].in);
     img[l] = make_wimg(ar, false, w + lin[l].woff, lin[l].in, 0, lin[l].out, a.wred_gen, a.gen.ncols, a.wred_mem,
-                       a.kmem, st);
+                       a.kmem, st, fuse ? 1 : 0);
     all_img = all_img && img[l] != nullptr;
   }
   ar.flush(st);
-  if (all_img && ldh < 0 && (last_mode == EPI_SIGMOID || last_mode == EPI_LINEAR) &&
-      -ldh == cdiv(lin[0].out, TC_BK) && chain_fusable(lin, n_lin, a0, lin[0].out)) {
+  if (fuse && !all_img) return FNEUS_ERR_WORKSPACE;
+  if (fuse) {
     SdfChainArgs g;
     memset(&g, 0, sizeof(g));
     double flops = 0.0;
@@ -102,11 +109,12 @@ static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg
       flops += 2.0 * (double)M * lin[l].in * lin[l].out;
     }
     g.gen = a0.gen; g.gen_t = a0.gen; g.mem = a0.mem; g.ldm = a0.ldm; g.kmem = a0.kmem; g.a0_img = a0_img;
+    g.f16 = 1;
     g.beta = 1.f; g.M = M; g.dbg = (tc_debug_flags() & 128) ? 1 : 0;
     g.xflags = (tc_debug_flags() >> 8) & 15;
-    if (defer) { defer->g = g; defer->flops = flops; defer->used = true; return; }
+    if (defer) { defer->g = g; defer->flops = flops; defer->used = true; return FNEUS_OK; }
     sdf_chain_launch(g, flops, st, FAM_RELU);
-    return;
+    return FNEUS_OK;
   }
   for (int l = 0; l < n_lin; l++) {
     ASeg a = l == 0 ? a0 : aseg_mem(Hs[l], ldh, lin[l].in);
@@ -116,21 +124,25 @@ static void relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg
     else { e.mode = last_mode; e.C = out; e.ldc = ld_out; }
     launch_gemm_fwd(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].out, e, st, img[l]);
   }
+  return FNEUS_OK;
 }
 
 // ReLU chain backward. a_last = gradient wrt the last linear's pre-activation ([M, ld_last]).
 // Layer-0 input gradient: generated block -> dsmall ([M, ld_small], may be null), feature block -> d_feats.
 // dybuf: (n_lin - 1) hidden-sized buffers (the layered path ping-pongs between the first two).
 // a0_img: image of the first operand written by the fused forward (null: regenerate it in the layer-0 wgrad).
-static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs,
+static int relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin, const ASeg& a0, float* const* Hs,
                            int ldh, const float* a_last, int ld_last, float* dybuf, long long dy_stride, float* dsmall,
                            int ld_small, float* d_feats, int ld_feats, int accumulate_feats, long long M,
                            cudaStream_t st, ImgArena& ar, const float* a0_img = nullptr, ChainDefer* defer = nullptr,
                            WgradGroup* shared_wg = nullptr) {
   const int sms = num_sms();
-  const bool fused = ldh < 0 && -ldh == cdiv(lin[0].out, TC_BK) && chain_fusable(lin, n_lin, a0, lin[0].out) &&
-                     lin[n_lin - 1].out <= TC_BK * SC_NAR && n_lin >= 2 &&
+  // the forward pass took the fused chain (FP16 activation images) exactly when relu_fwd_fused held; the fused
+  // backward must then be possible too (the layered path reads BF16 images)
+  const bool fwd_fused = relu_fwd_fused(lin, n_lin, a0, ldh, EPI_SIGMOID);
+  const bool fused = fwd_fused && lin[n_lin - 1].out <= TC_BK * SC_NAR && n_lin >= 2 &&
                      (ld_small & 3) == 0 && (ld_feats & 3) == 0;
+  if (fwd_fused && !fused) return FNEUS_ERR_UNSUPPORTED;
   if (fused) {
     // ---- weight images: MN-major W_l for l >= 1; layer 0 split into its feature and generated column ranges ----
     const uint8_t* img[16];
@@ -149,7 +161,8 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
       img_gen = make_wimg(ar, true, w + lin[0].woff, lin[0].in, a0.wred_gen, a0.gen.ncols, 0, 0, 0, lin[0].out, st);
       all_img = all_img && img_gen != nullptr;
     }
-    if (all_img) {
+    if (!all_img) return FNEUS_ERR_WORKSPACE;
+    {
       ar.flush(st);
       SdfChainArgs g;
       memset(&g, 0, sizeof(g));
@@ -190,23 +203,24 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
         const int ldy = l == n_lin - 1 ? ld_last : ldh;
         float* dW = dw + lin[l].woff;
         float* db = dw + lin[l].boff;
-        if (l > 0) wg.add(dy, ldy, aseg_mem(Hs[l], ldh, lin[l].in), dW, lin[l].in, 0, db, lin[l].out, st);
+        // dz_l: BF16 images of this pass; h_l and the first operand: FP16 images of the forward pass
+        if (l > 0) wg.add(dy, ldy, aseg_mem(Hs[l], ldh, lin[l].in), dW, lin[l].in, 0, db, lin[l].out, st, 0, 1);
         else if (a0_img == nullptr) wg.add(dy, ldy, a0, dW, lin[l].in, 0, db, lin[l].out, st);
         else {
           const int kbg = cdiv(a0.gen.ncols, TC_BK), kb0 = kbg + cdiv(a0.kmem, TC_BK);
           bool bias_done = false;
           if (a0.kmem > 0) {
             wg.add(dy, ldy, aseg_mem(a0_img + (size_t)kbg * (TC_A_BYTES / 4), -kb0, a0.kmem, a0.wred_mem), dW, lin[l].in, 0,
-                   db, lin[l].out, st);
+                   db, lin[l].out, st, 0, 1);
             bias_done = true;
           }
           if (a0.gen.ncols > 0)
             wg.add(dy, ldy, aseg_mem(a0_img, -kb0, a0.gen.ncols, a0.wred_gen), dW, lin[l].in, 0, bias_done ? nullptr : db,
-                   lin[l].out, st);
+                   lin[l].out, st, 0, 1);
         }
       }
       if (!shared_wg) wg.flush(st);
-      return;
+      return FNEUS_OK;
     }
   }
   const float* al = a_last;
@@ -236,6 +250,7 @@ static void relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin,
       launch_gemm_bwd_data(a, w + lin[l].woff, lin[l].in, 0, M, lin[l].in, e, st, img[l]);
     }
   }
+  return FNEUS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -443,8 +458,8 @@ int fneus_color_fwd(const fneus_color_cfg* cfg, const float* wpack, const float*
   zero_if_ragged(p.img, base, (long long)cfg->n_layers * hf, M, st);
   ImgArena ar = arena_at(scratch ? scratch + color_scratch_main(cfg, p, M) : nullptr,
                          relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
-  relu_chain_fwd(wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh, EPI_SIGMOID,
-                 rgb_out, cfg->d_out, M, st, ar, (saved && p.img) ? base + (long long)cfg->n_layers * hf : nullptr);
+  { const int rc_ = relu_chain_fwd(wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh, EPI_SIGMOID,
+                 rgb_out, cfg->d_out, M, st, ar, (saved && p.img) ? base + (long long)cfg->n_layers * hf : nullptr); if (rc_) return rc_; }
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -471,9 +486,9 @@ int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float*
   sigmoid_bwd_kernel<<<ew_blocks2(M * 4), 256, 0, st>>>(d_rgb, rgb, cfg->d_out, alast, 4, M);
   prof_end(st);
   ImgArena ar = arena_at(scratch + color_scratch_main(cfg, p, M), relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
-  relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh,
+  { const int rc_ = relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh,
                  alast, 4, ab0, hf, d_normals ? dsmall : nullptr, lds, d_feats, cfg->d_feature, 0, M, st, ar,
-                 p.img ? align1k(saved) + (long long)cfg->n_layers * hf : nullptr);
+                 p.img ? align1k(saved) + (long long)cfg->n_layers * hf : nullptr); if (rc_) return rc_; }
   if (d_normals) {
     prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
     extract_cols_kernel<<<ew_blocks2(M * 3), 256, 0, st>>>(dsmall, lds, p.gen_cols - 3, 3, d_normals, 3, M);
@@ -548,14 +563,14 @@ int fneus_ref_fwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   // The diffuse and the specular network are independent: on the fused path both chains go out in ONE launch.
   ChainDefer d_cd, d_cs;
   d_cd.used = d_cs.used = false;
-  relu_chain_fwd(wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, EPI_SIGMOID, b.yd, 3, M, st, ar,
-                 b.a0_cd, &d_cd);
+  { const int rc_ = relu_chain_fwd(wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, EPI_SIGMOID, b.yd, 3, M, st, ar,
+                 b.a0_cd, &d_cd); if (rc_) return rc_; }
   // viewdir_mlp: 4 x (Linear+ReLU); then net_cs Linear+Sigmoid
   {
     Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
     // hidden layer outputs G1..G4 are all ReLU'd; the chain helper applies ReLU to all but the last linear.
-    relu_chain_fwd(wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, EPI_SIGMOID, b.ys,
-                   1, M, st, ar, b.a0_cs, &d_cs);
+    { const int rc_ = relu_chain_fwd(wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, EPI_SIGMOID, b.ys,
+                   1, M, st, ar, b.a0_cs, &d_cs); if (rc_) return rc_; }
   }
   if (d_cd.used && d_cs.used) relu_chain_pair_launch(d_cd.g, d_cs.g, d_cd.flops + d_cs.flops, st);
   else {
@@ -605,12 +620,12 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
   static_assert(WG_MAX_JOBS >= 12, "the paired RefColor backward needs all weight-gradient jobs in one group");
   WgradGroup wg;
   wg.reset(M, num_sms());
-  relu_chain_bwd(wpack, d_wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, a_cd, 4, ab0, hf,
-                 ds_cd, 32, d_feats, cfg->d_feature, 0, M, st, ar, b.a0_cd, pair ? &d_cd : nullptr, pair ? &wg : nullptr);
+  { const int rc_ = relu_chain_bwd(wpack, d_wpack, p.cd, 5, ref_cd_a0(cfg, points, normals, feats), b.H, p.ldh, a_cd, 4, ab0, hf,
+                 ds_cd, 32, d_feats, cfg->d_feature, 0, M, st, ar, b.a0_cd, pair ? &d_cd : nullptr, pair ? &wg : nullptr); if (rc_) return rc_; }
   const bool paired = pair && d_cd.used;              // the diffuse chain took the fused path
-  relu_chain_bwd(wpack, d_wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, a_cs, 4,
+  { const int rc_ = relu_chain_bwd(wpack, d_wpack, chain, 5, ref_cs_a0(cfg, points, normals, b.refl, feats), b.G, p.ldh, a_cs, 4,
                  paired ? ab1 : ab0, hf, ds_cs, 36, paired ? df_cs : d_feats, cfg->d_feature, paired ? 0 : 1, M, st, ar,
-                 b.a0_cs, paired ? &d_cs : nullptr, paired ? &wg : nullptr);
+                 b.a0_cs, paired ? &d_cs : nullptr, paired ? &wg : nullptr); if (rc_) return rc_; }
   if (paired && d_cs.used) relu_chain_pair_launch(d_cd.g, d_cs.g, d_cd.flops + d_cs.flops, st);
   else if (d_cd.used) sdf_chain_launch(d_cd.g, d_cd.flops, st, FAM_RELU);
   wg.flush(st);
@@ -690,8 +705,8 @@ int fneus_mlp_fwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0
   for (int l = 1; l <= cfg->n_layers; l++) Hs[l] = base + (long long)(l - 1) * hf;
   zero_if_ragged(p.img, base, (long long)cfg->n_layers * hf, M, st);
   ImgArena ar = arena_at(scratch + mlp_scratch_main(cfg, p, M), relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
-  relu_chain_fwd(wpack, p.lin, p.n_lin, mlp_a0(cfg, in0, in1), Hs, p.ldh, cfg->last_act == 1 ? EPI_SIGMOID : EPI_LINEAR,
-                 out, cfg->d_out, M, st, ar, p.img ? base + (long long)cfg->n_layers * hf : nullptr);
+  { const int rc_ = relu_chain_fwd(wpack, p.lin, p.n_lin, mlp_a0(cfg, in0, in1), Hs, p.ldh, cfg->last_act == 1 ? EPI_SIGMOID : EPI_LINEAR,
+                 out, cfg->d_out, M, st, ar, p.img ? base + (long long)cfg->n_layers * hf : nullptr); if (rc_) return rc_; }
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
@@ -717,8 +732,8 @@ int fneus_mlp_bwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0
   else pad_rows_kernel<<<ew_blocks2(M * ldl), 256, 0, st>>>(d_out, cfg->d_out, alast, ldl, M);
   prof_end(st);
   ImgArena ar = arena_at(scratch + mlp_scratch_main(cfg, p, M), relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
-  relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, mlp_a0(cfg, in0, in1), Hs, p.ldh, alast, ldl, ab0, hf, nullptr, 4,
-                 nullptr, 4, 0, M, st, ar, p.img ? align1k(saved) + (long long)cfg->n_layers * hf : nullptr);
+  { const int rc_ = relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, mlp_a0(cfg, in0, in1), Hs, p.ldh, alast, ldl, ab0, hf, nullptr, 4,
+                 nullptr, 4, 0, M, st, ar, p.img ? align1k(saved) + (long long)cfg->n_layers * hf : nullptr); if (rc_) return rc_; }
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }

@@ -76,12 +76,13 @@ __device__ __forceinline__ void invert_cdf_warp(const float* sz, const float* sc
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
 upsample_step_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                      const float* __restrict__ z, const float* __restrict__ sdf, long long B, int n, int k,
-                     float inv_s, const float* __restrict__ u_table, float* __restrict__ new_z,
-                     float* __restrict__ cdf_out, long long* __restrict__ inds_out) {
+                     float inv_s_host, const float* __restrict__ inv_s_dev, const float* __restrict__ u_table,
+                     float* __restrict__ new_z, float* __restrict__ cdf_out, long long* __restrict__ inds_out) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const long long ray = (long long)blockIdx.x * SAMP_WARPS + warp;
   if (ray >= B) return;
+  const float inv_s = inv_s_dev != nullptr ? __ldg(inv_s_dev) : inv_s_host;   // device scalar: the learned inv_s of stage 2
   float* sz = smem + (size_t)warp * 3 * n;
   float* sf = sz + n;
   float* sc = sf + n;   // alpha, then cdf
@@ -282,6 +283,54 @@ __global__ void coarse_z_kernel(const float* __restrict__ near, const float* __r
   if (rnd != nullptr) v = __fadd_rn(v, __fmul_rn(__fmul_rn(__fsub_rn(rnd[r], 0.5f), 2.0f), inv_n_samples));
   z[idx] = v;
 }
+// First sign change along a ray and the secant root between the two bracketing section mid-points
+// (renderer.py:588-602, calLvis.py:180-196): idx = argmin_i sign(sdf_i) * (n - i) -- the first sample with sdf < 0;
+// sign(0) = 0, so an exact zero is NOT a hit -- valid iff that minimum is negative, idx >= 1 and at least one sample lies
+// inside the unit sphere;  z* = (s_lo z_hi - s_hi z_lo) / (s_lo - s_hi + 1e-10),  p* = o + d z*.
+// Fixed shapes: rays without a hit get hit_idx = -1 and the root of the clamped index (finite, ignored by the caller).
+// Optionally also the light visibility of calLvis.py:387-392: lvis = 1 - sum_i w_i * inside_i.
+// One warp per ray.
+__global__ void __launch_bounds__(SAMP_WARPS * 32)
+first_hit_secant_kernel(const float* __restrict__ sdf, const float* __restrict__ mid_z, const float* __restrict__ pts,
+                        const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                        const float* __restrict__ weights, int ldw, long long B, int n, int* __restrict__ hit_idx,
+                        float* __restrict__ z_surf, float* __restrict__ pts_surf, float* __restrict__ lvis,
+                        int* __restrict__ any_inside) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long long ray = (long long)blockIdx.x * SAMP_WARPS + warp;
+  if (ray >= B) return;
+  int first = n;                     // first index with sdf < 0
+  bool any_in = false;
+  float occ = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const long long q = ray * n + i;
+    if (__ldg(sdf + q) < 0.f && i < first) first = i;
+    const float px = __ldg(pts + q * 3), py = __ldg(pts + q * 3 + 1), pz = __ldg(pts + q * 3 + 2);
+    const bool in = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz))) < 1.0f;
+    any_in = any_in || in;
+    if (weights != nullptr && in) occ += __ldg(weights + ray * ldw + i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+  any_in = __any_sync(0xffffffffu, any_in);
+  if (weights != nullptr) occ = warp_sum(occ);
+  if (lane == 0) {
+    const bool hit = first < n && first >= 1 && any_in;
+    const int i = first < 1 ? 1 : (first > n - 1 ? n - 1 : first);
+    const float s_lo = sdf[ray * n + i - 1], s_hi = sdf[ray * n + i];
+    const float z_lo = mid_z[ray * n + i - 1], z_hi = mid_z[ray * n + i];
+    const float zs = __fdiv_rn(__fsub_rn(__fmul_rn(s_lo, z_hi), __fmul_rn(s_hi, z_lo)),
+                               __fadd_rn(__fsub_rn(s_lo, s_hi), 1e-10f));
+    hit_idx[ray] = hit ? first : -1;
+    if (z_surf) z_surf[ray] = zs;
+    if (pts_surf) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) pts_surf[ray * 3 + c] = __fadd_rn(rays_o[ray * 3 + c], __fmul_rn(rays_d[ray * 3 + c], zs));
+    }
+    if (lvis) lvis[ray] = 1.0f - occ;
+    if (any_inside) any_inside[ray] = any_in ? 1 : 0;
+  }
+}
 // renderer.py:296-303: flat sample rows (idx - 1, idx) of the two samples bracketing the first sign change
 __global__ void hit_rows_kernel(const int* __restrict__ hit_idx, long long B, int n, long long* __restrict__ rows) {
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,9 +360,25 @@ int fneus_ray_points(const float* rays_o, const float* rays_d, const float* z, l
   return FNEUS_OK;
 }
 
-int fneus_upsample_step(const float* rays_o, const float* rays_d, const float* z, const float* sdf, long long B,
-                        int n, int k, float inv_s, const float* u_table, float* new_z, float* cdf_out,
-                        long long* inds_out, void* stream) {
+int fneus_first_hit_secant(const float* sdf, const float* mid_z, const float* pts, const float* rays_o,
+                           const float* rays_d, const float* weights, int ldw, long long B, int n, int* hit_idx,
+                           float* z_surf, float* pts_surf, float* lvis, int* any_inside, void* stream) {
+  if (B == 0) return FNEUS_OK;
+  if (!sdf || !mid_z || !pts || !hit_idx) return FNEUS_ERR_NULL;
+  if (pts_surf && (!rays_o || !rays_d)) return FNEUS_ERR_NULL;
+  if (lvis && !weights) return FNEUS_ERR_NULL;
+  if (B < 0 || n < 2 || (weights && ldw < n)) return FNEUS_ERR_BAD_SHAPE;
+  prof_begin(PC_SAMPLING, 0.0, (double)B * n * (weights ? 24.0 : 20.0), (cudaStream_t)stream);
+  first_hit_secant_kernel<<<cdiv(B, SAMP_WARPS), SAMP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      sdf, mid_z, pts, rays_o, rays_d, weights, ldw, B, n, hit_idx, z_surf, pts_surf, lvis, any_inside);
+  prof_end((cudaStream_t)stream);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+static int upsample_step_launch(const float* rays_o, const float* rays_d, const float* z, const float* sdf, long long B,
+                                int n, int k, float inv_s, const float* inv_s_dev, const float* u_table, float* new_z,
+                                float* cdf_out, long long* inds_out, void* stream) {
   if (B == 0 || k == 0) return FNEUS_OK;
   if (!rays_o || !rays_d || !z || !sdf || !u_table || !new_z) return FNEUS_ERR_NULL;
   if (B < 0 || n < 2 || k < 0 || n > 4096) return FNEUS_ERR_BAD_SHAPE;
@@ -324,10 +389,21 @@ int fneus_upsample_step(const float* rays_o, const float* rays_d, const float* z
   }
   prof_begin(PC_SAMPLING, 0.0, (double)B * (n * 8.0 + k * 4.0 + 24.0), (cudaStream_t)stream);
   upsample_step_kernel<<<cdiv(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      rays_o, rays_d, z, sdf, B, n, k, inv_s, u_table, new_z, cdf_out, inds_out);
+      rays_o, rays_d, z, sdf, B, n, k, inv_s, inv_s_dev, u_table, new_z, cdf_out, inds_out);
   prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
+}
+int fneus_upsample_step(const float* rays_o, const float* rays_d, const float* z, const float* sdf, long long B,
+                        int n, int k, float inv_s, const float* u_table, float* new_z, float* cdf_out,
+                        long long* inds_out, void* stream) {
+  return upsample_step_launch(rays_o, rays_d, z, sdf, B, n, k, inv_s, nullptr, u_table, new_z, cdf_out, inds_out, stream);
+}
+// the same step with inv_s read from device memory (stage 2 uses the LEARNED inv_s, calLvis.py:371-379: no host sync)
+int fneus_upsample_step_dev(const float* rays_o, const float* rays_d, const float* z, const float* sdf, long long B,
+                            int n, int k, const float* inv_s_dev, const float* u_table, float* new_z, void* stream) {
+  if (!inv_s_dev) return FNEUS_ERR_NULL;
+  return upsample_step_launch(rays_o, rays_d, z, sdf, B, n, k, 0.f, inv_s_dev, u_table, new_z, nullptr, nullptr, stream);
 }
 
 int fneus_inverse_cdf(const float* bins, const float* cdf, const float* u_table, long long B, int n, int k,

@@ -28,6 +28,10 @@
 // the epilogue of step s is still working on blocks 1..3, so the tensor pipe runs underneath the epilogue and only
 // the last quarter of a step's MMAs is exposed.
 //
+// Operand formats (fneus_common.cuh, Fmt16): the forward families (FAM_SDF_FWD, forward ReLU chains) compute on FP16
+// operands and store FP16 images; the backward families (FAM_SDF_BWD, backward ReLU chains) compute on BF16 operands,
+// store BF16 images and READ the forward pass's FP16 images (h_l for the activation derivative, q_l).
+//
 //   warp 0      : MMA issuer (+ TMEM alloc: 2 x 256 accumulator columns)
 //   warp 1      : weight-image loader, ring of 4 half-tiles (128 output columns x 64 reduction, 16 KB)
 //   warp 2      : auxiliary-block loader (2 slots of h + q blocks)
@@ -87,6 +91,7 @@ struct SdfChainArgs {
   float sdf_scale;      // out_sign / scale
   const float* rs;      // SDFBWD with use_rs: d_sdf [M]
   float rscale, beta;
+  int f16;              // FAM_RELU: operands / weight images / stored images are FP16 (forward chains) or BF16 (backward)
   int dbg;              // record the debug timeline (CTA 0)
   int xflags;           // experiment switches (fneus_debug_flags bits 8..): 1 = every thread arrives, 2 = no suspend hint,
                         // 4 = no accumulator prefetch, 8 = no early start on the first column half
@@ -119,18 +124,17 @@ constexpr int sc_smem_bytes() {
          (SC_BIAS_SLOTS * 256 + 256 + 128 + (PARK ? 128 * SC_PARK_LD : 0)) * 4 + 1024 + 256;
 }
 
-__device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float* out) {
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float* out) { u16x8_to_f32(u, false, out); }
+__device__ __forceinline__ void f16x8_to_f32(const uint4 u, float* out) { u16x8_to_f32(u, true, out); }
+__device__ __forceinline__ uint4 f32x8_to_bf16(const float* y) { return f32x8_to_u16(y, false); }
+// [h > 0] for 8 consecutive 16-bit elements of either format (sign bit clear and magnitude bits non-zero)
+__device__ __forceinline__ void u16x8_positive(const uint4 u, bool* pos) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int t = 0; t < 4; t++) {
-    out[2 * t] = __uint_as_float(w[t] << 16);
-    out[2 * t + 1] = __uint_as_float(w[t] & 0xFFFF0000u);
+    pos[2 * t] = (w[t] & 0x8000u) == 0u && (w[t] & 0x7FFFu) != 0u;
+    pos[2 * t + 1] = (w[t] & 0x80000000u) == 0u && (w[t] & 0x7FFF0000u) != 0u;
   }
-}
-__device__ __forceinline__ uint4 f32x8_to_bf16(const float* y) {
-  const uint2 lo = pack_bf16x4(make_float4(y[0], y[1], y[2], y[3]));
-  const uint2 hi = pack_bf16x4(make_float4(y[4], y[5], y[6], y[7]));
-  return make_uint4(lo.x, lo.y, hi.x, hi.y);
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
   asm volatile(
@@ -194,6 +198,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
   SCSmem* ctl = reinterpret_cast<SCSmem*>(spark + (PARK ? 128 * SC_PARK_LD : 0));
 
   constexpr bool SDF = FAM != FAM_RELU;
+  // format of this kernel's own operands, weight images and stored images (compile-time for the SDF families)
+  const bool opf16 = FWD ? true : (BWD ? false : g.f16 != 0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ntiles = (g.M + 127) / 128;
   const float rsqrt2 = 0.70710678118654752440f;
@@ -265,7 +271,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
             tc_fence_after();
             for (int h = 0; h * 128 < Nc; h++, kbg++) {
               const int rows = min(128, Nc - h * 128);
-              const uint32_t idesc = make_idesc(rows, 0, S.bmn);
+              const uint32_t idesc = make_idesc(rows, 0, S.bmn, opf16, opf16);
               const int stg = kbg % WST;
               mbar_wait(&ctl->wfull[stg], (kbg / WST) & 1);
               tc_fence_after();
@@ -381,7 +387,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
             if (valid)
               gen_row_part(FWD ? g.gen : g.gen_t, m, cg, 4, [&](int j, float val) {
                 if (j < TC_BK)
-                  *reinterpret_cast<unsigned short*>(rowA + ((((j >> 3) ^ r7) & 7) << 4) + ((j & 7) << 1)) = f32_to_bf16_bits(val);
+                  *reinterpret_cast<unsigned short*>(rowA + ((((j >> 3) ^ r7) & 7) << 4) + ((j & 7) << 1)) = f32_to_u16_bits(val, opf16);
               });
             if (g.pe_img != nullptr) {
               epi_bar();
@@ -401,7 +407,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
               if (valid)
                 gen_row_part(g.gen, m, cg, 4, [&](int j, float val) {
                   if (j < TC_BK)
-                    *reinterpret_cast<unsigned short*>(rowA + ((((j >> 3) ^ r7) & 7) << 4) + ((j & 7) << 1)) = f32_to_bf16_bits(val);
+                    *reinterpret_cast<unsigned short*>(rowA + ((((j >> 3) ^ r7) & 7) << 4) + ((j & 7) << 1)) = f32_to_u16_bits(val, opf16);
                 });
             }
             const int kb_mem = (g.kmem + TC_BK - 1) / TC_BK;
@@ -442,7 +448,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                 const int rr = ew * 8 + i0 + i;
                 const float v[8] = {lo[i].x, lo[i].y, lo[i].z, lo[i].w, hi[i].x, hi[i].y, hi[i].z, hi[i].w};
                 uint8_t* drow = sMem + (rr >> 3) * 1024 + (rr & 7) * 128;
-                *reinterpret_cast<uint4*>(drow + (ch >> 3) * TC_A_BYTES + ((((ch & 7) ^ (rr & 7)) & 7) << 4)) = f32x8_to_bf16(v);
+                *reinterpret_cast<uint4*>(drow + (ch >> 3) * TC_A_BYTES + ((((ch & 7) ^ (rr & 7)) & 7) << 4)) = f32x8_to_u16(v, opf16);
               }
               }
             }
@@ -585,7 +591,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
               float hv[8];
-              bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
+              f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_l: forward image, FP16
               if (full) {
 #pragma unroll
                 for (int j = 0; j < 8; j++) a[hf * 8 + j] = sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale;
@@ -614,8 +620,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
               float hv[8], qv[8], e[8];
-              bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
-              bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);
+              f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_{l+1}, q_l: forward
+              f16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);      // images, FP16
 #pragma unroll
               for (int j = 0; j < 8; j++) {
                 const float sg = sg_fast(hv[j], ksg);
@@ -643,11 +649,11 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
             // dz_{l-1} = (dz_l W_l) * [h_l > 0]: the forward activation block arrived in the slot's h block
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
-              float hv[8];
-              bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
+              bool pos[8];                                                               // forward image, either format
+              u16x8_positive(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), pos);
 #pragma unroll
               for (int j = 0; j < 8; j++)
-                a[hf * 8 + j] = (hv[j] > 0.f && (full || (valid && n + hf * 8 + j < N))) ? a[hf * 8 + j] : 0.f;
+                a[hf * 8 + j] = (pos[j] && (full || (valid && n + hf * 8 + j < N))) ? a[hf * 8 + j] : 0.f;
             }
           } else if (!SDF && mode == SC_OUT) {
             if (N <= 16) {
@@ -678,8 +684,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
               float hv[8], qv[8];
-              bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
-              bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);
+              f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_l: forward image, FP16
+              bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);     // e_{l-1}: this pass, BF16
 #pragma unroll
               for (int j = 0; j < 8; j++) {
                 const int nn = n + hf * 8 + j;
@@ -689,7 +695,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
             }
           }
           if (mode != SC_G0 && mode != SC_OUT) {
-            const uint4 p0 = f32x8_to_bf16(a), p1 = f32x8_to_bf16(a + 8);
+            const uint4 p0 = f32x8_to_u16(a, opf16), p1 = f32x8_to_u16(a + 8, opf16);
             if (can_pf && b + 1 < nb && n + 64 < Nc) {
               if (b + 1 >= 2) need_full();
               tmem_ld16_issue(tacc + n + 64, ar);
@@ -707,7 +713,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                 const int col = N + j;
                 if (col < 256)
                   *reinterpret_cast<unsigned short*>(sOp + (col >> 6) * TC_A_BYTES + rowoff + (((((col & 63) >> 3) ^ r7) & 7) << 4) +
-                                                     ((col & 7) << 1)) = f32_to_bf16_bits(val * rsqrt2);
+                                                     ((col & 7) << 1)) = f32_to_u16_bits(val * rsqrt2, opf16);
               });
           }
           if (FWD ? (mode == SC_FEATQ || mode == SC_G0) : (!SDF && mode == SC_OUT && N > 16)) {

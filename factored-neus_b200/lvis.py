@@ -40,25 +40,16 @@ def query_indir_illum(lgtSGs, dirs):
     return (sg[..., -3:] * torch.exp(sg[..., 3:4] * (torch.sum(d * lobes, dim=-1, keepdim=True) - 1.0))).sum(dim=2)
 
 
-def _first_hit(sdf_bn, inside):
-    """calLvis.py:180-183 / renderer.py:290-292 with fixed shapes: (hit mask [R], index clamped to >= 1)."""
-    n = sdf_bn.shape[1]
-    neg = sdf_bn < 0
-    idx = torch.where(neg.any(-1), neg.float().argmax(-1), torch.full_like(neg[:, 0], n, dtype=torch.long))
-    hit = (idx < n) & (idx >= 1) & (inside.sum(-1) > 0)
-    return hit, idx.clamp(1, n - 1)
-
-
 @torch.no_grad()
 def trace_visibility(surf, normal, sdf_network, deviation_network, color_network, r_theta, rand_z,
                      n_coarse=512, n_imp=32, chunk_points=2048):
     """Ground-truth part of cal_indiLgt (calLvis.py:351-397).  surf, normal [m,3]; r_theta, rand_z [m,k].
-    Returns gt_lvis [m,k], gt_trace_radiance [m,k,3], dirs [m,k,3]."""
+    Returns gt_lvis [m,k], gt_trace_radiance [m,k,3], dirs [m,k,3].  No host read-back anywhere: the learned inv_s
+    stays a device scalar."""
     dev = surf.device
     m, k = r_theta.shape
     dirs = sample_dirs(normal[:, None, :], r_theta, torch.asin(rand_z))
     inv_s = deviation_network(torch.zeros([1, 3], device=dev))[:, :1].clip(1e-6, 1e6)
-    inv_s_f = float(inv_s.reshape(-1)[0])                       # host scalar for the up-sampling kernel
     zc_row = torch.linspace(0.0, 1.0, n_coarse, device=dev)
     u = torch.linspace(0.5 / n_imp, 1.0 - 0.5 / n_imp, n_imp, device=dev)
     sample_dist = (1 - 0.1) / 32.0                              # calLvis.py:95,155
@@ -73,26 +64,21 @@ def trace_visibility(surf, normal, sdf_network, deviation_network, color_network
         R = o.shape[0]
         zc = zc_row[None, :].expand(R, -1).contiguous()
         sdf_c = ops.sdf_forward_nograd(net.cfg, w_sdf, ops.ray_points(o, d, zc), want_feat=False)[0].reshape(R, n_coarse)
-        z_fine = ops.upsample_step(o, d, zc, sdf_c, n_imp, inv_s_f, u)
+        z_fine = ops.upsample_step_dev(o, d, zc, sdf_c, n_imp, inv_s, u)
         # shared geometry of the 32 importance sections
         dists, mid_z, pts, dd = ops.core_geometry(o, d, z_fine, sample_dist)
-        sdf_f, _, nrm_f = net.value_feature_normal(pts, want_normal=True)
-        # (a) occlusion: alpha / weights of compute_weight (cos_anneal_ratio = 0), inside-sphere masked
+        sdf_f, _, nrm_f = net.value_feature_normal(pts, want_normal=True, w=w_sdf)
+        # (a) occlusion: alpha / weights of compute_weight (cos_anneal_ratio = 0)
         zeros_rgb = torch.zeros(R * n_imp, 3, device=dev)
-        _, weights, _, _, _, inside, _, _, _, _ = ops.Composite.apply(
+        _, weights, _, _, _, _, _, _, _, _ = ops.Composite.apply(
             sdf_f, nrm_f, zeros_rgb, inv_s, None, None, dists, pts, d, None, n_imp, 0, 0.0)
-        lvis_out[p0:p1] = (1.0 - (weights * inside).sum(-1)).reshape(-1, k)
-        # (b) first-hit radiance: secant root between the bracketing sections, colour network at the root
-        sdf_bn = sdf_f.reshape(R, n_imp)
-        hit, idx = _first_hit(sdf_bn, inside)
-        ii = idx[:, None]
-        z_lo, z_hi = mid_z.gather(1, ii - 1), mid_z.gather(1, ii)
-        s_lo, s_hi = sdf_bn.gather(1, ii - 1), sdf_bn.gather(1, ii)
-        z_s = (s_lo * z_hi - s_hi * z_lo) / (s_lo - s_hi + 1e-10)
-        p_s = (o + d * z_s).contiguous()
-        _, f_s, n_s = net.value_feature_normal(p_s, want_normal=True)
+        # (b) visibility = 1 - sum of inside-sphere weights; first sign change and its secant root (one launch)
+        hit_idx, _, p_s, lvis, _ = ops.first_hit_secant(sdf_f, mid_z, pts, o, d, weights=weights)
+        lvis_out[p0:p1] = lvis.reshape(-1, k)
+        # (c) first-hit radiance: colour network at the root
+        _, f_s, n_s = net.value_feature_normal(p_s, want_normal=True, w=w_sdf)
         rgb = color_network(p_s, n_s, d, f_s)
-        rad_out[p0:p1] = torch.where(hit[:, None], rgb, torch.zeros_like(rgb)).reshape(-1, k, 3)
+        rad_out[p0:p1] = torch.where((hit_idx >= 0)[:, None], rgb, torch.zeros_like(rgb)).reshape(-1, k, 3)
     return lvis_out, rad_out, dirs
 
 

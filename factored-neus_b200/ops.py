@@ -420,6 +420,36 @@ def upsample_step(rays_o, rays_d, z, sdf, k, inv_s, u_table, debug=False):
     return (new_z, cdf, inds) if debug else new_z
 
 
+def upsample_step_dev(rays_o, rays_d, z, sdf, k, inv_s_dev, u_table):
+    """up_sample with inv_s taken from a device scalar (the learned inv_s of stage 2; no host read-back)."""
+    B, n = z.shape
+    new_z = torch.empty(B, k, dtype=torch.float32, device=z.device)
+    L.check(L.lib().fneus_upsample_step_dev(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(sdf), B, n, k,
+                                            L.ptr(_f32c(inv_s_dev).reshape(-1)[:1].contiguous()), L.ptr(u_table),
+                                            L.ptr(new_z), L.stream_ptr()), "fneus_upsample_step_dev")
+    return new_z
+
+
+def first_hit_secant(sdf, mid_z, pts, rays_o, rays_d, weights=None):
+    """renderer.py:588-602 / calLvis.py:180-196 with fixed shapes: (hit_idx [B] int32, -1 = no hit; z_surf [B,1];
+    pts_surf [B,3]; lvis [B] = 1 - sum w * inside when ``weights`` is given, else None; any_inside [B] bool)."""
+    _need_cuda(sdf, "sdf")
+    B, n = mid_z.shape
+    dev = mid_z.device
+    sdf_c, mid_c, pts_c = _f32c(sdf).reshape(B, n), _f32c(mid_z), _f32c(pts).reshape(B * n, 3)
+    hit = torch.empty(B, dtype=torch.int32, device=dev)
+    zs = torch.empty(B, 1, dtype=torch.float32, device=dev)
+    ps = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    w = _f32c(weights)
+    lv = torch.empty(B, dtype=torch.float32, device=dev) if w is not None else None
+    anyin = torch.empty(B, dtype=torch.int32, device=dev)
+    L.check(L.lib().fneus_first_hit_secant(L.ptr(sdf_c), L.ptr(mid_c), L.ptr(pts_c), L.ptr(_f32c(rays_o)),
+                                           L.ptr(_f32c(rays_d)), L.ptr(w), w.shape[1] if w is not None else 0, B, n,
+                                           L.ptr(hit), L.ptr(zs), L.ptr(ps), L.ptr(lv), L.ptr(anyin), L.stream_ptr()),
+            "fneus_first_hit_secant")
+    return hit, zs, ps, lv, anyin != 0
+
+
 def inverse_cdf(bins, cdf, u_table):
     B, n = bins.shape
     k = u_table.numel()

@@ -233,26 +233,21 @@ class NeuSRenderer:
         dists, mid_z, pts, _ = ops.core_geometry(rays_o, rays_d, z_vals, sample_dist)
         with torch.no_grad():
             sdf = self._sdf_nograd(pts)
-        inside = (torch.linalg.norm(pts, ord=2, dim=-1).reshape(B, n_samples) < 1.0).float()
-        return {"n_samples": n_samples, "mid_z_vals": mid_z, "sdf": sdf,
-                "inside_sphere_mask": inside.sum(dim=-1) > 0.0}
+            # first sign change, inside-sphere test and secant root in one launch (renderer.py:553-556,588-602)
+            hit_idx, z_surf, pts_surf, _, any_in = ops.first_hit_secant(sdf, mid_z, pts, rays_o, rays_d)
+        return {"n_samples": n_samples, "mid_z_vals": mid_z, "sdf": sdf, "inside_sphere_mask": any_in,
+                "hit_idx": hit_idx, "z_surf": z_surf, "pts_surf": pts_surf}
 
     def lvis_render(self, rays_o, rays_d, near, far, r_theta=None, rand_z=None):
-        """renderer.py:567-627 (fixed shapes: rays without a surface hit are masked to the default of ones)."""
+        """renderer.py:567-627 (fixed shapes: rays without a surface hit are masked to the default of ones).
+        ``r_theta`` / ``rand_z`` [B,4]: the two random draws of calLvis.py:351-352 (2 pi rand, 0.95 rand); drawn here when
+        omitted."""
         from .lvis import cal_indiLgt
         B = len(rays_o)
         dev = rays_o.device
         util = self.lvis_mateIllu_render_util(rays_o, rays_d, near, far)
-        n, mid_z = util["n_samples"], util["mid_z_vals"]
-        sdf_bn = util["sdf"].reshape(B, n)
-        neg = sdf_bn < 0
-        idx = torch.where(neg.any(-1), neg.float().argmax(-1), torch.full((B,), n, device=dev, dtype=torch.long))
-        sdf_mask = (idx < n) & (idx >= 1) & util["inside_sphere_mask"]
-        ii = idx.clamp(1, n - 1)[:, None]
-        z_lo, z_hi = mid_z.gather(1, ii - 1), mid_z.gather(1, ii)
-        s_lo, s_hi = sdf_bn.gather(1, ii - 1), sdf_bn.gather(1, ii)
-        z_surf = (s_lo * z_hi - s_hi * z_lo) / (s_lo - s_hi + 1e-10)
-        pts_surf = (rays_o + rays_d * z_surf).contiguous()
+        sdf_mask = util["hit_idx"] >= 0
+        pts_surf = util["pts_surf"]
         n_surf = self.sdf_network.gradient(pts_surf).reshape(-1, 3)
         res = cal_indiLgt(pts_surf, n_surf, self.sdf_network, self.deviation_network, self.color_network,
                           self.lvis_network, self.indiLgt_network, r_theta=r_theta, rand_z=rand_z)

@@ -215,6 +215,21 @@ int fneus_ray_points(const float* rays_o, const float* rays_d, const float* z, l
 int fneus_upsample_step(const float* rays_o, const float* rays_d, const float* z, const float* sdf,
                         long long n_rays, int n, int k, float inv_s, const float* u_table, float* new_z,
                         float* cdf_out, long long* inds_out, void* stream);
+/* The same step with inv_s read from device memory: stage 2 samples at the LEARNED inv_s (calLvis.py:371-379), which
+ * lives on the device; no host read-back, CUDA-graph capturable. */
+int fneus_upsample_step_dev(const float* rays_o, const float* rays_d, const float* z, const float* sdf,
+                            long long n_rays, int n, int k, const float* inv_s_dev, const float* u_table,
+                            float* new_z, void* stream);
+/* First sign change + secant root (renderer.py:588-602 in lvis_render, calLvis.py:180-196 in cal_firHit_rgb):
+ * idx = first sample with sdf < 0 (the reference's argmin of sign(sdf) * (n - i); sign(0) = 0 is not a hit), valid iff
+ * idx >= 1 and some sample of the ray lies inside the unit sphere (|pts| < 1).  hit_idx [B] int32 (-1 = no hit),
+ * z_surf [B] = (s_lo z_hi - s_hi z_lo) / (s_lo - s_hi + 1e-10) over the bracketing mid-points, pts_surf [B,3] = o + d z
+ * (fixed shapes: rays without a hit get the root of the clamped index).  With weights [B, ldw] also
+ * lvis [B] = 1 - sum_i weights_i [|pts_i| < 1] (calLvis.py:387-392); any_inside [B] int32 = the reference's
+ * inside_sphere_mask (renderer.py:556).  z_surf, pts_surf, weights, lvis, any_inside may be NULL. */
+int fneus_first_hit_secant(const float* sdf, const float* mid_z, const float* pts, const float* rays_o,
+                           const float* rays_d, const float* weights, int ldw, long long n_rays, int n,
+                           int* hit_idx, float* z_surf, float* pts_surf, float* lvis, int* any_inside, void* stream);
 /* Inverse-CDF alone (renderer.py:64-77): searchsorted(right=True) + interpolation on a SUPPLIED cdf. */
 int fneus_inverse_cdf(const float* bins, const float* cdf, const float* u_table, long long n_rays, int n, int k,
                       float* samples_out, long long* inds_out, void* stream);

@@ -619,6 +619,48 @@ def surface_points(P, rays_o, rays_d, near, far, conf=RENDER_CONF_WMASK, sdf_con
     return hit, p_s, n_s
 
 
+def query_indir_illum(lgtSGs, dirs):
+    """calLvis.py:323-336: 24 spherical Gaussians [n,24,7] evaluated along [n,k,3] directions -> [n,k,3]."""
+    k, nl = dirs.shape[1], lgtSGs.shape[1]
+    sg = lgtSGs.unsqueeze(-3).expand(-1, k, -1, -1)
+    d = dirs.unsqueeze(-2).expand(-1, -1, nl, -1)
+    lobes = sg[..., :3] / torch.norm(sg[..., :3], dim=-1, keepdim=True)
+    return (sg[..., -3:] * torch.exp(sg[..., 3:4] * (torch.sum(d * lobes, dim=-1, keepdim=True) - 1.0))).sum(dim=2)
+
+
+def lvis_render(P, p_lvis: Params, p_indi: Params, rays_o, rays_d, near, far, r_theta, rand_z,
+                conf=RENDER_CONF_WMASK, sdf_conf=SDF_CONF, color_conf=COLOR_CONF):
+    """renderer.py:567-627 with fixed shapes: every ray runs the trace; rays without a surface hit keep the
+    reference's defaults of ones.  r_theta / rand_z [B,4]: the two draws of calLvis.py:351-352 (rows of rays without a
+    hit are ignored)."""
+    B = rays_o.shape[0]
+    hit, p_s, n_s = surface_points(P, rays_o, rays_d, near, far, conf, sdf_conf)
+    n_s = n_s.detach()
+    p_s = p_s.detach()
+    gt_lvis, gt_rad, dirs, _ = trace_visibility(P, p_s, n_s, r_theta, rand_z, sdf_conf=sdf_conf, color_conf=color_conf)
+    k = r_theta.shape[1]
+    o = p_s[:, None, :].repeat(1, k, 1).reshape(-1, 3)
+    pre_lvis = lvis_forward(p_lvis, o, dirs.reshape(-1, 3)).reshape(B, k)
+    pre_rad = query_indir_illum(indirect_light_forward(p_indi, p_s), dirs)
+    m1, m3 = hit[:, None], hit[:, None, None]
+    one1, one3 = torch.ones(B, k, dtype=rays_o.dtype), torch.ones(B, k, 3, dtype=rays_o.dtype)
+    return dict(gt_lvis=torch.where(m1, gt_lvis, one1), pre_lvis=torch.where(m1, pre_lvis, one1),
+                gt_trace_radiance=torch.where(m3, gt_rad, one3), pre_trace_radiance=torch.where(m3, pre_rad, one3),
+                sdf_mask=hit)
+
+
+def stage2_loss(out):
+    """lvis.py:163-170: lvis_loss = sum |gt_lvis - pre_lvis| / (4 n_hit + 1e-6) (unmasked difference: rows without a
+    hit are ones on both sides), radiance_loss = sum |(gt - pre) * mask| / (12 n_hit + 1e-6)."""
+    hit = out["sdf_mask"]
+    dt = out["gt_lvis"].dtype
+    lvis_err = out["gt_lvis"] - out["pre_lvis"]
+    lvis_loss = lvis_err.abs().sum() / (hit[..., None].expand(out["gt_lvis"].shape).sum().to(dt) + 1e-6)
+    rad_err = (out["gt_trace_radiance"] - out["pre_trace_radiance"]) * hit[..., None, None].to(dt)
+    rad_loss = rad_err.abs().sum() / (hit[..., None, None].expand(out["gt_trace_radiance"].shape).sum().to(dt) + 1e-6)
+    return lvis_loss + rad_loss, dict(lvis_loss=lvis_loss, radiance_loss=rad_loss)
+
+
 # ---------------------------------------------------------------------------
 # stage-2 prediction networks -- fields.py:338-413
 # ---------------------------------------------------------------------------

@@ -1,4 +1,5 @@
-"""north_star gate for the tensor-core path: PSNR after 1k training iterations within 0.1 dB of the FP32 path.
+"""north_star gate for the tensor-core path, AS WRITTEN: PSNR after 1k training iterations within 0.1 dB of the FP32
+path, end to end (trained AND rendered on the tensor-core path).
 
 Teacher = the same architecture at another random init (seed 123) rendered unperturbed on the FP32 path; both
 students start from seed 4, see the identical ray order and identical perturbation random numbers, and are
@@ -18,10 +19,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 ITERS = int(os.environ.get("FNEUS_PSNR_ITERS", "1000"))
 B = 512
-# A single held-out PSNR reading after 1k Adam steps moves by +-0.2 dB when ANY rounding changes (measured: the FP32 path
-# alone moved 51.08 -> 50.86 dB when the optimiser's arithmetic order changed), so the 0.1 dB gate is applied to the
-# mean over the last checkpoints of the run instead of to one reading.
-EVAL_SPAN, EVAL_EVERY = 100, 10
+# A single held-out PSNR reading after 1k Adam steps moves by +-0.2 dB when ANY rounding changes (two trajectories of a
+# non-convex optimisation diverge), so the reading compared is the mean over the checkpoints of the last 200 iterations.
+EVAL_SPAN, EVAL_EVERY = 200, 10
+GATE_DB = 0.1
 
 
 def _render_rgb(R, o, d, near, far):
@@ -51,9 +52,10 @@ def test_bf16_training_tracks_fp32_psnr():
     def run(prec):
         ops.set_precision(prec)
         m = build_modules(syn.scene_states(seed=4), DEV, syn.RENDER_CONF_WMASK)
+        # both arms run the captured step: identical launch sequence and identical Philox offsets for the perturbation
         tr = Stage1Trainer(m["renderer"], [m["sdf"], m["var"], m["color"], m["ref"]], B, warm_up_end=100,
-                           end_iter=ITERS, use_graph=(prec == "bf16"))
-        torch.manual_seed(11)                                              # identical perturbation stream
+                           end_iter=ITERS, use_graph=True)
+        torch.manual_seed(11)
         evals, evals32 = [], []
         for it in range(ITERS):
             k = int(order[it % len(order)])
@@ -74,23 +76,14 @@ def test_bf16_training_tracks_fp32_psnr():
     mean = lambda v: sum(v) / len(v)
     p32, p16, p16_as32 = mean(e32), mean(e16), mean(e16_as32)
     fmt = lambda v: " ".join("%.2f" % x for x in v)
-    print("held-out PSNR at the last %d checkpoints:\n  fp32-trained, fp32 render: %s\n  bf16-trained, bf16 render: %s\n"
-          "  bf16-trained, fp32 render: %s" % (len(e32), fmt(e32), fmt(e16), fmt(e16_as32)))
-    print("PSNR after %d iterations: fp32 %.3f dB | bf16-trained rendered in fp32 %.3f dB (diff %.3f) | bf16 end to end "
-          "%.3f dB (diff %.3f)" % (ITERS, p32, p16_as32, p16_as32 - p32, p16, p16 - p32))
-    # Gate 1 (north_star, 0.1 dB): what the tensor-core path LEARNS -- its weights rendered by the same FP32 renderer
-    # as the FP32-trained weights.  Two 1 000-step Adam trajectories diverge chaotically (the FP32 path alone moved by
-    # 0.2 dB when the optimiser's summation order changed), so the gate is a significance test on the per-checkpoint
-    # differences: it fails when "within 0.1 dB" can be rejected at two standard errors, not on one noisy mean.
-    diffs = [a - b for a, b in zip(e16_as32, e32)]
-    se = (sum((x - mean(diffs)) ** 2 for x in diffs) / max(1, len(diffs) - 1)) ** 0.5 / max(1, len(diffs)) ** 0.5
-    print("learned-quality difference: %.3f dB +- %.3f (standard error over %d checkpoints)" % (mean(diffs), se, len(diffs)))
-    assert mean(diffs) + 2.0 * se >= -0.1, "bf16-trained PSNR %.3f significantly more than 0.1 dB below fp32-trained %.3f" % (
-        p16_as32, p32)
-    assert mean(diffs) >= -0.25, "bf16-trained PSNR %.3f vs fp32-trained %.3f" % (p16_as32, p32)
-    # Gate 2: the same weights rendered by the BF16 path itself.  BF16 operand rounding puts ~9e-4 RMS on the SDF value
-    # (~5e-4 on the colour), which alone costs 0.1-0.2 dB at 51 dB (MSE 7.6e-6); measured -0.13 .. -0.18 dB on B200.
-    # The strict reading of the 0.1 dB bound is therefore NOT met end to end; the gate here catches
-    # regressions beyond that rounding floor.
-    assert p16 >= p32 - 0.3, "bf16 end-to-end PSNR %.3f more than 0.3 dB below fp32 %.3f" % (p16, p32)
-    assert abs(p16 - p32) <= 0.5, "bf16 PSNR %.3f vs fp32 %.3f: trajectories diverged" % (p16, p32)
+    print("held-out PSNR at the last %d checkpoints:\n  fp32-trained, fp32 render: %s\n  tc-trained,   tc render:   %s\n"
+          "  tc-trained,   fp32 render: %s" % (len(e32), fmt(e32), fmt(e16), fmt(e16_as32)))
+    print("PSNR after %d iterations: fp32 %.3f dB | tensor-core end to end %.3f dB (diff %+.3f) | tensor-core-trained "
+          "rendered in fp32 %.3f dB (diff %+.3f) | render-only rounding cost %+.3f dB"
+          % (ITERS, p32, p16, p16 - p32, p16_as32, p16_as32 - p32, p16 - p16_as32))
+    # The north_star bound as written: end to end, |difference| <= 0.1 dB.
+    assert abs(p16 - p32) <= GATE_DB, "tensor-core end-to-end PSNR %.3f vs fp32 %.3f: outside %.1f dB" % (p16, p32, GATE_DB)
+    # and its two components: what was learned, and what the tensor-core renderer's operand rounding costs on fixed weights
+    assert abs(p16_as32 - p32) <= GATE_DB, "tensor-core-trained weights (fp32 render) %.3f vs fp32 %.3f" % (p16_as32, p32)
+    assert abs(p16 - p16_as32) <= 0.03, "operand rounding of the tensor-core renderer costs %.3f dB on fixed weights" % (
+        p16 - p16_as32)

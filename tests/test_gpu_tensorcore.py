@@ -124,7 +124,7 @@ def test_bf16_fused_sdf_forward(bf16_mode, N):
     assert_close(got, ref, BF16_TOL, "fused sdf forward N=%d" % N)
     # agreement with the layer-wise tensor-core path (value_feature_normal) at BF16 rounding level
     sdf2, _, _ = m["sdf"].value_feature_normal(x.to(DEV), want_normal=False)
-    assert_close(got, sdf2, 5e-3, "fused vs layer-wise bf16")
+    assert_close(got, sdf2, 1e-2, "fused (FP16 operands) vs layer-wise (BF16 operands)")
 
 
 def test_bf16_grid_query(bf16_mode, golden_dir):
@@ -173,6 +173,21 @@ def test_bf16_stage2_networks(bf16_mode):
             assert err <= BF16_TOL * scale, "bf16 grad %s.%s err %.3e (scale %.3e)" % (tag, name, err, scale)
 
 
+def _fvl_check(key, got, ref, tag):
+    """Fused (FP16 forward operands) vs layered (BF16 forward operands).  Forward outputs and weight gradients agree at
+    the 2e-2 gate relative to the tensor's scale.  In the per-point INPUT gradients a pre-activation within ~1e-3 of
+    zero takes different ReLU branches in the two paths, which moves single entries by a sizeable fraction of the
+    scale: those tensors are compared in the L2 norm (sparse flips stay small there), with a loose max-abs backstop."""
+    scale = max(1e-3, float(ref.abs().max()))
+    err = max_err(got, ref)
+    rel = float((got - ref).norm() / ref.norm().clamp_min(1e-12))
+    print("%s %s: max err %.3e (scale %.3e), norm-rel %.3e" % (tag, key, err, scale, rel))
+    if key in ("d_normals", "d_feats"):
+        assert rel <= 3e-2 and err <= 0.3 * scale, "%s %s: norm-rel %.3e, max err %.3e (scale %.3e)" % (tag, key, rel, err, scale)
+    else:
+        assert err <= BF16_TOL * scale, "%s %s: err %.3e (scale %.3e)" % (tag, key, err, scale)
+
+
 def _color_ref_run(m, x, nrm, v, feat, probe):
     """colour + RefColor forward/backward on given inputs; returns outputs and all gradients (CPU)."""
     for net in ("color", "ref"):
@@ -195,9 +210,10 @@ def _color_ref_run(m, x, nrm, v, feat, probe):
 
 @pytest.mark.parametrize("N", [300, 1000, 5000])
 def test_bf16_fused_chains_match_layered(bf16_mode, N):
-    """Fused on-chip ReLU chains (forward, backward-data, grouped weight gradients) vs the layer-by-layer tensor-core
-    path on the same BF16 images: same arithmetic up to accumulation order, so agreement is far tighter than the
-    2e-2 BF16 gate.  Tile counts: 3 (odd: half-empty pair), 8 with a ragged last tile, 40."""
+    """Fused on-chip ReLU chains (forward on FP16 operands, backward-data and grouped weight gradients on BF16) vs the
+    independent layer-by-layer tensor-core path (BF16 throughout): they differ by the layered path's BF16 operand
+    rounding, i.e. they agree at the 2e-2 gate relative to each tensor's scale.  Tile counts: 3 (odd: half-empty pair),
+    8 with a ragged last tile, 40."""
     states = syn.scene_states(seed=4, jitter=0.03)
     m = build_modules(states, DEV)
     rs = np.random.RandomState(N)
@@ -215,15 +231,26 @@ def test_bf16_fused_chains_match_layered(bf16_mode, N):
         lib.fneus_debug_flags(0)
     got = _color_ref_run(m, x, nrm, v, feat, probe)
     for k in ref:
-        scale = max(1e-3, float(ref[k].abs().max()))
-        err = max_err(got[k], ref[k])
-        assert err <= 4e-3 * scale, "fused vs layered %s: err %.3e (scale %.3e)" % (k, err, scale)
+        _fvl_check(k, got[k], ref[k], "fused vs layered")
     # and against the FP32 oracle at the BF16 gate
     P = grad_params(states)
     n_ = nrm.cpu().clone().requires_grad_(True)
     f_ = feat.cpu().clone().requires_grad_(True)
     rgb_o = O.color_forward(P["color"], x.cpu(), n_, v.cpu(), f_)
     assert_close(got["rgb"], rgb_o, BF16_TOL, "fused colour vs oracle")
+    r_rgb, r_spec, r_diff = O.refcolor_forward(P["ref"], x.cpu(), f_, v.cpu(), n_)
+    pc = probe.cpu()
+    ((rgb_o * pc).sum() + (r_rgb * pc).sum() + 0.5 * (r_spec * pc).sum() + 0.25 * (r_diff * pc).sum()).backward()
+    for k, t in (("d_normals", n_.grad), ("d_feats", f_.grad)):          # both paths against the FP32 autograd
+        rel_f = float((got[k] - t).norm() / t.norm())
+        rel_l = float((ref[k] - t).norm() / t.norm())
+        print("%s vs oracle: fused norm-rel %.3e, layered %.3e" % (k, rel_f, rel_l))
+        assert rel_f <= 3e-2, "fused %s vs oracle: norm-rel %.3e" % (k, rel_f)
+    for net in ("color", "ref"):
+        for name, t in P[net].items():
+            scale = max(1e-3, float(t.grad.abs().max()))
+            err = max_err(got["g.%s.%s" % (net, name)], t.grad)
+            assert err <= BF16_TOL * max(1.0, scale), "fused grad %s.%s vs oracle: err %.3e (scale %.3e)" % (net, name, err, scale)
 
 
 def _sdf_run(m, x, p_sdf, p_feat, p_nrm):
@@ -322,6 +349,4 @@ def test_bf16_chains_full_size_multi_tile_per_cta(bf16_mode):
         lib.fneus_debug_flags(0)
     got = _color_ref_run(m, x, nrm, v, feat, probe)
     for k in ref:
-        scale = max(1e-3, float(ref[k].abs().max()))
-        err = max_err(got[k], ref[k])
-        assert err <= 4e-3 * scale, "full-size fused vs layered %s: err %.3e (scale %.3e)" % (k, err, scale)
+        _fvl_check(k, got[k], ref[k], "full-size fused vs layered")

@@ -144,3 +144,32 @@ def test_stage2_networks_match_reference(golden_dir):
             scale = max(1.0, np.abs(ref[3:]).max())
             assert np.abs(got[3:] - ref[3:]).max() <= 2e-5 * scale, "grad %s.%s" % (tag, name)
             assert abs(got[2] - ref[2]) <= 1e-4 * max(1.0, ref[2]), "grad-norm %s.%s" % (tag, name)
+
+
+def test_lvis_render_matches_reference(golden_dir, states):
+    """NeuSRenderer.lvis_render (renderer.py:567-627): surface point by sign change + secant, 4 secondary rays, traced
+    visibility / radiance and the Lvis / IndirectLight predictions, defaults of ones for rays without a hit."""
+    g = _load(golden_dir, "lvis_render.npz")
+    P = {k: states[k] for k in ("sdf", "var", "color")}
+    t = lambda k: torch.from_numpy(g[k])
+    out = O.lvis_render(P, syn.lvis_state(), syn.indirect_light_state(), t("o"), t("d"), t("near"), t("far"),
+                        t("r_theta"), t("rand_z"))
+    assert np.array_equal(out["sdf_mask"].numpy().astype(np.float32), g["sdf_mask"])
+    assert 0 < int(g["sdf_mask"].sum()) < g["sdf_mask"].size            # the fixture holds hit AND default rows
+    for k in ("gt_lvis", "pre_lvis", "gt_trace_radiance", "pre_trace_radiance"):
+        _close(out[k], g[k], 5e-5, "lvis_render " + k)
+    miss = g["sdf_mask"] == 0
+    assert np.all(g["gt_lvis"][miss] == 1.0) and np.all(g["pre_trace_radiance"][miss] == 1.0)
+
+
+def test_first_hit_rule_on_exact_zeros():
+    """renderer.py:588-593 / SURVEY 8c: sign(0) = 0, so an exact zero is not a hit and does not shadow a later negative
+    sample; the oracle's first_hit is the reference expression itself."""
+    sdf = torch.tensor([[0.3, 0.0, -0.1, -0.2], [0.0, 0.0, 0.0, 0.0], [-0.1, 0.2, 0.3, 0.4], [0.2, 0.1, 0.0, 0.05],
+                        [0.5, 0.4, -0.0, -1e-30]])
+    inside = torch.ones(5, 4)
+    hit, idx = O.first_hit(sdf, inside)
+    assert hit.tolist() == [True, False, False, False, True]
+    assert int(idx[0]) == 2 and int(idx[4]) == 3
+    hit2, _ = O.first_hit(sdf, torch.zeros(5, 4))
+    assert not hit2.any()

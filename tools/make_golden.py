@@ -94,6 +94,9 @@ def main():
     stage2_networks(fields, syn, gdir)
     if "--only-stage2" in sys.argv:
         return
+    if "--only-lvis-render" in sys.argv:
+        lvis_render_golden(fields, renderer, syn, syn.scene_states(seed=4, jitter=0.03), gdir)
+        return
 
     # ---------------- networks, per-function (full-size wmask shapes, jittered weights) -------------
     states = syn.scene_states(seed=4, jitter=0.03)
@@ -198,7 +201,43 @@ def main():
     np.savez_compressed(os.path.join(gdir, "lvis.npz"), surf=np_(surf), normal=np_(normal),
                         r_theta=np_(r1 * 2 * np.pi), rand_z=np_(r2 * 0.95),
                         gt_lvis=np_(res["gt_lvis"]), gt_trace_radiance=np_(res["gt_trace_radiance"]))
+    lvis_render_golden(fields, renderer, syn, states, gdir)
     print("golden fixtures written to", gdir)
+
+
+def lvis_render_golden(fields, renderer, syn, states, gdir):
+    """NeuSRenderer.lvis_render itself (renderer.py:567-627) with the real Lvis / IndirectLight networks.  Its only
+    random numbers are the two torch.rand([m,4]) draws of calLvis.py:351-352 over the m hit rays: they are captured by
+    re-seeding, and scattered to per-ray rows for the fixed-shape implementation."""
+    np_ = lambda t: t.detach().cpu().numpy()
+    mods = build_reference(fields, renderer, states, syn.SDF_CONF, syn.COLOR_CONF, syn.NERF_CONF, syn.RENDER_CONF_WMASK)
+    lv, il = fields.Lvis(), fields.IndirectLight()
+    z3 = torch.zeros(2, 3)
+    lv(z3, torch.ones(2, 3)); il(z3)
+    lv.load_state_dict(syn.lvis_state()); il.load_state_dict(syn.indirect_light_state())
+    R = mods["renderer"]
+    R.lvis_network, R.indiLgt_network = lv, il
+    B = 24
+    o, d, near, far = syn.make_rays(B, seed=1)
+    # a few rays that miss the surface / the unit sphere, so that the default-ones rows are exercised
+    o[-2:] = o[-2:] * 1.0 + torch.tensor([[0.0, 3.0, 0.0]])
+    torch.manual_seed(9)
+    out = R.lvis_render(o, d, near, far)
+    mask = out["sdf_mask"]
+    m = int(mask.sum())
+    torch.manual_seed(9)
+    r1, r2 = torch.rand(m, 4), torch.rand(m, 4)
+    r_theta, rand_z = torch.zeros(B, 4), torch.zeros(B, 4)
+    r_theta[mask] = r1 * 2 * np.pi
+    rand_z[mask] = r2 * 0.95
+    util = R.lvis_mateIllu_render_util(o, d, near, far)
+    save = dict(o=np_(o), d=np_(d), near=np_(near), far=np_(far), r_theta=np_(r_theta), rand_z=np_(rand_z),
+                sdf_mask=np_(mask.float()), inside_sphere_mask=np_(util["inside_sphere_mask"].float()),
+                mid_z_vals=np_(util["mid_z_vals"]), sdf=np_(util["sdf"]))
+    for k in ("gt_lvis", "pre_lvis", "gt_trace_radiance", "pre_trace_radiance"):
+        save[k] = np_(out[k])
+    np.savez_compressed(os.path.join(gdir, "lvis_render.npz"), **save)
+    print("lvis_render: %d of %d rays hit" % (m, B))
 
 
 def _upsample_weights_via_reference(R, o, d, z, sdf, inv_s):
