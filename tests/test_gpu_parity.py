@@ -548,3 +548,115 @@ def test_ray_setup_glue_kernels_bit_exact():
     base = torch.arange(B, device=DEV) * 128
     rows_ref = torch.stack([base + idx - 1, base + idx], dim=1).reshape(-1)
     assert torch.equal(ops.hit_rows(hit, 128), rows_ref)
+
+
+# ------------------------------------------------------------------------------------------ stage 2 surface / lvis_render
+def _first_hit_reference(sdf, mid_z, pts, o, d):
+    """renderer.py:588-602 restated with the reference's own expressions (sign * ramp, torch.min)."""
+    B, n = sdf.shape
+    ramp = torch.arange(n, 0, -1).float().reshape(1, n)
+    val, idx = torch.min(torch.sign(sdf) * ramp, dim=-1)
+    inside = (torch.linalg.norm(pts.reshape(B, n, 3), ord=2, dim=-1) < 1.0).float()
+    mask = (val < 0.0) & (idx >= 1) & (inside.sum(-1) > 0.0)
+    ii = idx.clamp(1, n - 1).reshape(-1, 1)
+    z_lo, z_hi = mid_z.gather(1, ii - 1), mid_z.gather(1, ii)
+    s_lo, s_hi = sdf.gather(1, ii - 1), sdf.gather(1, ii)
+    zs = (s_lo * z_hi - s_hi * z_lo) / (s_lo - s_hi + 1e-10)
+    return mask, idx, zs, o + d * zs, inside
+
+
+def test_first_hit_secant_kernel_incl_exact_zeros():
+    """fneus_first_hit_secant vs the reference expressions on crafted rows: exact zeros (sign(0) = 0 is not a hit and
+    does not shadow a later negative sample), a negative FIRST sample (idx = 0: invalid), no negative sample, rays
+    entirely outside the unit sphere, -0.0, and random rows at n = 32 / 128 / 512."""
+    gen = torch.Generator().manual_seed(8)
+    for n in (32, 128, 512):
+        B = 64
+        sdf = torch.randn(B, n, generator=gen) * 0.3 + 0.2
+        sdf[0, :] = sdf[0, :].abs() + 0.01                 # never negative
+        sdf[1, 0] = -0.5                                   # negative at index 0 -> invalid
+        sdf[2, :] = sdf[2, :].abs() + 0.01
+        sdf[2, 5] = 0.0; sdf[2, 9] = -0.25                 # zero before the first negative
+        sdf[3, :] = 0.0                                    # all zeros
+        sdf[4, :] = sdf[4, :].abs() + 0.01
+        sdf[4, 7] = -0.0                                   # negative zero: sign(-0.0) = 0
+        mid_z = torch.sort(torch.rand(B, n, generator=gen) * 2 + 1.5, -1)[0]
+        o = 2.5 * torch.nn.functional.normalize(torch.randn(B, 3, generator=gen), dim=-1)
+        d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(B, 3, generator=gen), dim=-1)
+        o[5] = torch.tensor([0.0, 4.0, 0.0]); d[5] = torch.tensor([1.0, 0.0, 0.0])      # misses the unit sphere
+        pts = (o[:, None, :] + d[:, None, :] * mid_z[..., None]).reshape(-1, 3)
+        w = torch.rand(B, n, generator=gen) / n
+        mask, idx, zs, ps, inside = _first_hit_reference(sdf, mid_z, pts, o, d)
+        hit, z_k, p_k, lv, any_in = ops.first_hit_secant(_cu(sdf), _cu(mid_z), _cu(pts), _cu(o), _cu(d), weights=_cu(w))
+        assert torch.equal((hit >= 0).cpu(), mask), "hit mask differs at n=%d" % n
+        assert torch.equal(hit.cpu()[mask].long(), idx[mask])
+        assert torch.equal(any_in.cpu(), inside.sum(-1) > 0)
+        assert not mask[0] and not mask[1] and not mask[3] and not mask[4] and not mask[5]
+        assert bool(mask[2]) and int(hit[2]) == 9
+        assert torch.equal(z_k.cpu()[mask], zs[mask]), "secant root is not bit-equal at n=%d" % n
+        assert_close(p_k.cpu()[mask], ps[mask], 1e-6, "surface point")
+        assert_close(lv, 1.0 - (w * inside).sum(-1), 1e-6, "visibility reduction")
+
+
+def _stage2_modules(states):
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    lv, il = fn.Lvis(), fn.IndirectLight()
+    lv.load_state_dict(syn.lvis_state()); il.load_state_dict(syn.indirect_light_state())
+    R = m["renderer"]
+    R.lvis_network, R.indiLgt_network = lv.to(DEV), il.to(DEV)
+    return m, R
+
+
+def test_lvis_render_matches_reference(golden_dir, states):
+    """NeuSRenderer.lvis_render (renderer.py:567-627) against the reference's own output (fixture generated by
+    tools/make_golden.py from the imported reference): hit mask identical, all four outputs <= 1e-4, default rows = 1."""
+    g = _golden(golden_dir, "lvis_render.npz")
+    m, R = _stage2_modules(states)
+    util = R.lvis_mateIllu_render_util(_cu(g["o"]), _cu(g["d"]), _cu(g["near"]), _cu(g["far"]))
+    assert np.array_equal(util["inside_sphere_mask"].cpu().numpy().astype(np.float32), g["inside_sphere_mask"])
+    # inverse-CDF depths are ill-conditioned in near-empty bins (DESIGN.md 2): a few samples move by ~1e-4
+    dz = (util["mid_z_vals"].cpu() - torch.from_numpy(g["mid_z_vals"])).abs()
+    assert float(dz.max()) < 1e-3 and float((dz > 2e-5).float().mean()) < 0.01, "util mid_z_vals"
+    out = R.lvis_render(_cu(g["o"]), _cu(g["d"]), _cu(g["near"]), _cu(g["far"]), r_theta=_cu(g["r_theta"]),
+                        rand_z=_cu(g["rand_z"]))
+    assert np.array_equal(out["sdf_mask"].cpu().numpy().astype(np.float32), g["sdf_mask"])
+    for k in ("gt_lvis", "pre_lvis", "gt_trace_radiance", "pre_trace_radiance"):
+        print("lvis_render %s max err %.3e" % (k, max_err(out[k], g[k])))
+        assert_close(out[k], g[k], FP32_TOL, "lvis_render %s vs reference golden" % k)
+    miss = g["sdf_mask"] == 0
+    assert miss.any() and float((out["gt_lvis"].cpu()[torch.from_numpy(miss)] - 1.0).abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------ BASELINE-size step vs oracle
+def test_render_512_rays_fwd_bwd_vs_oracle(states):
+    """The benchmarked shape (512 rays x 128 samples = 65 536 points = 512 tiles) against the CPU oracle: end-to-end
+    render outputs, then render_core + stage-1 loss + backward on the SAME depths (inverse-CDF sampling is
+    ill-conditioned in empty bins) with every parameter gradient compared."""
+    B = 512
+    o, d, near, far = syn.make_rays(B, seed=21)
+    true_rgb, mask = syn.make_targets(B, seed=22)
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    R = m["renderer"]
+    od, dd = o.to(DEV), d.to(DEV)
+    out = R.render(od, dd, near.to(DEV), far.to(DEV), perturb_overwrite=0, cos_anneal_ratio=1.0)
+    ref_e2e = O.render({k: v for k, v in states.items()}, o, d, near, far, conf=O.RENDER_CONF_WMASK, perturb_overwrite=0,
+                       cos_anneal_ratio=1.0)
+    for k in ("color_fine", "surface_color", "weight_sum", "gradient_error"):
+        assert_close(out[k], ref_e2e[k].detach(), FP32_TOL, "512-ray render %s" % k)
+    lin = torch.linspace(0.0, 1.0, 64, device=DEV)
+    z = R._hierarchical(od, dd, ops.coarse_z(near.to(DEV), far.to(DEV), lin, None, 64))
+    P = grad_params(states)
+    ref = O.render(P, o, d, near, far, conf=O.RENDER_CONF_WMASK, perturb_overwrite=0, cos_anneal_ratio=1.0,
+                   z_override=z.cpu())
+    _stage1(ref, true_rgb, mask, 0.1).backward()
+    core = R.render_core(od, dd, z, 2.0 / 64, m["sdf"], m["var"], m["color"], m["ref"], cos_anneal_ratio=1.0)
+    for k, rk in (("color", "color_fine"), ("surface_color", "surface_color"), ("gradients", "gradients"),
+                  ("weights", "weights"), ("cdf", "cdf_fine"), ("gradient_error", "gradient_error")):
+        assert_close(core[k], ref[rk].detach(), FP32_TOL, "512-ray render_core %s" % k)
+    assert torch.equal(core["sdf_mask"].cpu(), ref["sdf_mask"])
+    w = core["weights"]
+    outd = dict(color_fine=core["color"], surface_color=core["surface_color"], sdf_mask=core["sdf_mask"],
+                weight_sum=w.sum(-1, keepdim=True), gradient_error=core["gradient_error"])
+    _stage1(outd, true_rgb.to(DEV), mask.to(DEV), 0.1).backward()
+    worst = compare_param_grads(m, P, ["sdf", "color", "var", "ref"], FP32_TOL, 1e-3, "512 rays")
+    print("512-ray step: worst param-grad abs err %.3e" % worst)

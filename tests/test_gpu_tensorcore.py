@@ -350,3 +350,108 @@ def test_bf16_chains_full_size_multi_tile_per_cta(bf16_mode):
     got = _color_ref_run(m, x, nrm, v, feat, probe)
     for k in ref:
         _fvl_check(k, got[k], ref[k], "full-size fused vs layered")
+
+
+# ------------------------------------------------------------------------------------------ tensor-core path: womask, stage 2, 512 rays
+def _grad_gate(m, P, nets, tag):
+    for net in nets:
+        for name, p in m[net].named_parameters():
+            refg = P[net][name].grad
+            refg = torch.zeros_like(P[net][name]) if refg is None else refg
+            scale = max(1e-3, float(refg.abs().max()))
+            err = max_err(p.grad if p.grad is not None else torch.zeros_like(p), refg)
+            assert err <= BF16_TOL * max(1.0, scale), "%s grad %s.%s err %.3e (scale %.3e)" % (tag, net, name, err, scale)
+
+
+def test_bf16_render_core_womask(bf16_mode, golden_dir):
+    """womask (outside NeRF, n_outside = 32, cos_anneal 0.3) on the tensor-core path: outputs vs the reference golden
+    and every gradient (incl. the NeRF's) vs the oracle at the 2e-2 gate -- mirror of test_render_core_fwd_bwd_womask."""
+    states = syn.scene_states(seed=4, jitter=0.03)
+    g = {k: v for k, v in np.load(os.path.join(golden_dir, "render_womask.npz")).items()}
+    B = g["color_fine"].shape[0]
+    o, d, near, far = syn.make_rays(B, seed=1)
+    true_rgb, mask = syn.make_targets(B, seed=2)
+    z = torch.from_numpy(g["z_vals"])
+    P = grad_params(states)
+    ref = O.render(P, o, d, near, far, conf=O.RENDER_CONF_WOMASK, perturb_overwrite=0, cos_anneal_ratio=0.3,
+                   z_override=z)
+    O.stage1_loss(ref, true_rgb, mask, 0.1, 0.1, 0.0)[0].backward()
+    m = build_modules(states, DEV, syn.RENDER_CONF_WOMASK)
+    R = m["renderer"]
+    od, dd, zd = o.to(DEV), d.to(DEV), z.to(DEV)
+    z_feed, _ = ops.merge_sorted(zd, O.outside_z(far, 32, 64).to(DEV).contiguous())
+    ro = R.render_core_outside(od, dd, z_feed, 2.0 / 64, m["nerf"])
+    core = R.render_core(od, dd, zd, 2.0 / 64, m["sdf"], m["var"], m["color"], m["ref"], background_alpha=ro["alpha"],
+                         background_sampled_color=ro["sampled_color"], cos_anneal_ratio=0.3)
+    assert core["weights"].shape == (B, 160)
+    for k, gk in (("color", "color_fine"), ("surface_color", "surface_color"), ("gradients", "gradients"),
+                  ("weights", "weights"), ("gradient_error", "gradient_error")):
+        print("tc womask %s max err %.3e" % (k, max_err(core[k], g[gk])))
+        assert_close(core[k], g[gk], BF16_TOL, "tc womask render_core %s" % k)
+    w = core["weights"]
+    out = dict(color_fine=core["color"], surface_color=core["surface_color"], sdf_mask=core["sdf_mask"],
+               weight_sum=w.sum(-1, keepdim=True), gradient_error=core["gradient_error"])
+    loss = O.stage1_loss(out, true_rgb.to(DEV), mask.to(DEV), 0.1, 0.1, 0.0)[0]
+    assert abs(loss.item() - float(g["loss"])) < BF16_TOL
+    loss.backward()
+    _grad_gate(m, P, ["sdf", "color", "var", "ref", "nerf"], "tc womask")
+    out2 = R.render(od, dd, near.to(DEV), far.to(DEV), perturb_overwrite=0, cos_anneal_ratio=0.3)
+    assert_close(out2["color_fine"], g["color_fine"], BF16_TOL, "tc womask e2e color_fine")
+
+
+def test_bf16_lvis_trace_and_render(bf16_mode, golden_dir):
+    """Stage-2 trace (calLvis.cal_indiLgt ground truth) and NeuSRenderer.lvis_render on the tensor-core path vs the
+    reference goldens at the 2e-2 gate."""
+    from factored_neus_b200 import lvis as LV
+    states = syn.scene_states(seed=4, jitter=0.03)
+    cu = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    g = {k: v for k, v in np.load(os.path.join(golden_dir, "lvis.npz")).items()}
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    lv, rad, _ = LV.trace_visibility(cu(g["surf"]), cu(g["normal"]), m["sdf"], m["var"], m["color"], cu(g["r_theta"]),
+                                     cu(g["rand_z"]))
+    print("tc lvis trace: gt_lvis err %.3e, radiance err %.3e" % (max_err(lv, g["gt_lvis"]), max_err(rad, g["gt_trace_radiance"])))
+    assert_close(lv, g["gt_lvis"], BF16_TOL, "tc gt_lvis")
+    assert_close(rad, g["gt_trace_radiance"], BF16_TOL, "tc gt_trace_radiance")
+    g = {k: v for k, v in np.load(os.path.join(golden_dir, "lvis_render.npz")).items()}
+    lvn, iln = fn.Lvis(), fn.IndirectLight()
+    lvn.load_state_dict(syn.lvis_state()); iln.load_state_dict(syn.indirect_light_state())
+    R = m["renderer"]
+    R.lvis_network, R.indiLgt_network = lvn.to(DEV), iln.to(DEV)
+    out = R.lvis_render(cu(g["o"]), cu(g["d"]), cu(g["near"]), cu(g["far"]), r_theta=cu(g["r_theta"]), rand_z=cu(g["rand_z"]))
+    assert np.array_equal(out["sdf_mask"].cpu().numpy().astype(np.float32), g["sdf_mask"])
+    for k in ("gt_lvis", "pre_lvis", "gt_trace_radiance", "pre_trace_radiance"):
+        print("tc lvis_render %s max err %.3e" % (k, max_err(out[k], g[k])))
+        assert_close(out[k], g[k], BF16_TOL, "tc lvis_render %s" % k)
+
+
+def test_bf16_render_512_rays_fwd_bwd_vs_oracle(bf16_mode):
+    """The benchmarked shape on the tensor-core path (512 tiles on 148 persistent CTAs: up to four tiles per CTA, the
+    regime bench.py times) against the CPU ORACLE -- not against another CUDA path: render outputs end to end, then
+    render_core + stage-1 loss + backward on the same depths with every parameter gradient at the 2e-2 gate."""
+    states = syn.scene_states(seed=4, jitter=0.03)
+    B = 512
+    o, d, near, far = syn.make_rays(B, seed=21)
+    true_rgb, mask = syn.make_targets(B, seed=22)
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    R = m["renderer"]
+    od, dd = o.to(DEV), d.to(DEV)
+    out = R.render(od, dd, near.to(DEV), far.to(DEV), perturb_overwrite=0, cos_anneal_ratio=1.0)
+    lin = torch.linspace(0.0, 1.0, 64, device=DEV)
+    z = R._hierarchical(od, dd, ops.coarse_z(near.to(DEV), far.to(DEV), lin, None, 64))
+    P = grad_params(states)
+    ref = O.render(P, o, d, near, far, conf=O.RENDER_CONF_WMASK, perturb_overwrite=0, cos_anneal_ratio=1.0,
+                   z_override=z.cpu())
+    O.stage1_loss(ref, true_rgb, mask, 0.1, 0.1, 0.1)[0].backward()
+    for k in ("color_fine", "surface_color", "weight_sum"):
+        print("tc 512-ray render %s max err %.3e" % (k, max_err(out[k], ref[k].detach())))
+        assert_close(out[k], ref[k].detach(), BF16_TOL, "tc 512-ray render %s" % k)
+    core = R.render_core(od, dd, z, 2.0 / 64, m["sdf"], m["var"], m["color"], m["ref"], cos_anneal_ratio=1.0)
+    for k, rk in (("color", "color_fine"), ("surface_color", "surface_color"), ("gradients", "gradients"),
+                  ("weights", "weights"), ("gradient_error", "gradient_error")):
+        print("tc 512-ray render_core %s max err %.3e" % (k, max_err(core[k], ref[rk].detach())))
+        assert_close(core[k], ref[rk].detach(), BF16_TOL, "tc 512-ray render_core %s" % k)
+    w = core["weights"]
+    outd = dict(color_fine=core["color"], surface_color=core["surface_color"], sdf_mask=core["sdf_mask"],
+                weight_sum=w.sum(-1, keepdim=True), gradient_error=core["gradient_error"])
+    O.stage1_loss(outd, true_rgb.to(DEV), mask.to(DEV), 0.1, 0.1, 0.1)[0].backward()
+    _grad_gate(m, P, ["sdf", "color", "var", "ref"], "tc 512 rays")
