@@ -137,8 +137,8 @@ _SIGNATURES = {
     "fneus_inverse_cdf": (c_int, [_P, _P, _P, _LL, c_int, c_int, _P, _P, _P]),
     "fneus_merge_sorted": (c_int, [_P, _P, _P, _P, _LL, c_int, c_int, _P, _P, _P]),
     "fneus_core_geometry": (c_int, [_P, _P, _P, _LL, c_int, c_float, _P, _P, _P, _P, _P]),
-    "fneus_composite_fwd": (c_int, [_P] * 9 + [_LL, c_int, c_int, _P, c_float] + [_P] * 10),
-    "fneus_composite_bwd": (c_int, [_P] * 9 + [_LL, c_int, c_int, _P, c_float] + [_P] * 14),
+    "fneus_composite_fwd": (c_int, [_P] * 9 + [_LL, c_int, c_int, _P, c_float] + [_P] * 11),
+    "fneus_composite_bwd": (c_int, [_P] * 9 + [_LL, c_int, c_int, _P, c_float] + [_P] * 15),
 }
 
 _lib = None

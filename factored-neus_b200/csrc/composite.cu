@@ -72,7 +72,8 @@ composite_fwd_kernel(const float* __restrict__ sdf, const float* __restrict__ nr
                      const float* __restrict__ dists, const float* __restrict__ pts, const float* __restrict__ rays_d,
                      const float* __restrict__ bg_alpha, const float* __restrict__ bg_color,
                      const float* __restrict__ bg_rgb, long long B, int n_in, int n_out,
-                     const float* __restrict__ inv_s_p, float car, float* __restrict__ color,
+                     const float* __restrict__ inv_s_p, float car_host, const float* __restrict__ car_dev,
+                     float* __restrict__ color,
                      float* __restrict__ weights, float* __restrict__ weight_sum, float* __restrict__ weight_max,
                      float* __restrict__ cdf, float* __restrict__ inside, float* __restrict__ eik_part,
                      int* __restrict__ hit_idx, float* __restrict__ w_pair) {
@@ -83,6 +84,7 @@ composite_fwd_kernel(const float* __restrict__ sdf, const float* __restrict__ nr
   const int n_tot = n_in + n_out;
   float* s_win = smem + (size_t)warp * n_in;   // inside-weights per sample (for the surface blend)
   const float s = __ldg(inv_s_p);
+  const float car = car_dev != nullptr ? __ldg(car_dev) : car_host;   // device scalar: the annealing schedule inside a CUDA graph
   const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
   const bool has_bg = bg_alpha != nullptr;
 
@@ -168,7 +170,8 @@ composite_bwd_kernel(const float* __restrict__ sdf, const float* __restrict__ nr
                      const float* __restrict__ dists, const float* __restrict__ pts, const float* __restrict__ rays_d,
                      const float* __restrict__ bg_alpha, const float* __restrict__ bg_color,
                      const float* __restrict__ bg_rgb, long long B, int n_in, int n_out,
-                     const float* __restrict__ inv_s_p, float car, const int* __restrict__ hit_idx,
+                     const float* __restrict__ inv_s_p, float car_host, const float* __restrict__ car_dev,
+                     const int* __restrict__ hit_idx,
                      const float* __restrict__ d_color, const float* __restrict__ d_weights,
                      const float* __restrict__ d_weight_sum, const float* __restrict__ d_w_pair,
                      const float* __restrict__ d_eik, const float* __restrict__ eik_denom, float* __restrict__ d_sdf,
@@ -185,6 +188,7 @@ composite_bwd_kernel(const float* __restrict__ sdf, const float* __restrict__ nr
   float* s_S = s_T + n_tot;
   float* s_Tin = s_S + n_tot;
   const float s = __ldg(inv_s_p);
+  const float car = car_dev != nullptr ? __ldg(car_dev) : car_host;   // device scalar: the annealing schedule inside a CUDA graph
   const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
   const bool has_bg = bg_alpha != nullptr;
   const float dcr = d_color ? d_color[ray * 3] : 0.f, dcg = d_color ? d_color[ray * 3 + 1] : 0.f,
@@ -358,7 +362,8 @@ extern "C" {
 int fneus_composite_fwd(const float* sdf, const float* normals, const float* rgb, const float* dists,
                         const float* pts, const float* rays_d, const float* bg_alpha, const float* bg_color,
                         const float* bg_rgb, long long B, int n_in, int n_out, const float* inv_s,
-                        float cos_anneal_ratio, float* color, float* weights, float* weight_sum, float* weight_max,
+                        float cos_anneal_ratio, const float* cos_anneal_dev, float* color, float* weights,
+                        float* weight_sum, float* weight_max,
                         float* cdf, float* inside, float* eik_part, int* hit_idx, float* w_pair, void* stream) {
   if (B == 0) return FNEUS_OK;
   if (!sdf || !normals || !rgb || !dists || !pts || !rays_d || !inv_s || !color || !weights || !weight_sum ||
@@ -376,7 +381,7 @@ int fneus_composite_fwd(const float* sdf, const float* normals, const float* rgb
   prof_begin(PC_COMPOSITE, 0.0, (double)B * ((n_in + n_out) * 44.0 + 100.0), (cudaStream_t)stream);
   composite_fwd_kernel<<<cdiv(B, COMP_WARPS), COMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
       sdf, normals, rgb, dists, pts, rays_d, bg_alpha, bg_color, bg_rgb, B, n_in, n_out, inv_s, cos_anneal_ratio,
-      color, weights, weight_sum, weight_max, cdf, inside, eik_part, hit_idx, w_pair);
+      cos_anneal_dev, color, weights, weight_sum, weight_max, cdf, inside, eik_part, hit_idx, w_pair);
   prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
@@ -385,7 +390,8 @@ int fneus_composite_fwd(const float* sdf, const float* normals, const float* rgb
 int fneus_composite_bwd(const float* sdf, const float* normals, const float* rgb, const float* dists,
                         const float* pts, const float* rays_d, const float* bg_alpha, const float* bg_color,
                         const float* bg_rgb, long long B, int n_in, int n_out, const float* inv_s,
-                        float cos_anneal_ratio, const int* hit_idx, const float* d_color, const float* d_weights,
+                        float cos_anneal_ratio, const float* cos_anneal_dev, const int* hit_idx, const float* d_color,
+                        const float* d_weights,
                         const float* d_weight_sum, const float* d_w_pair, const float* d_eik,
                         const float* eik_denom, float* d_sdf, float* d_normals, float* d_rgb, float* d_inv_s,
                         float* d_bg_alpha, float* d_bg_color, void* stream) {
@@ -403,7 +409,7 @@ int fneus_composite_bwd(const float* sdf, const float* normals, const float* rgb
   prof_begin(PC_COMPOSITE, 0.0, (double)B * ((n_in + n_out) * 64.0 + 100.0), (cudaStream_t)stream);
   composite_bwd_kernel<<<cdiv(B, COMP_WARPS), COMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
       sdf, normals, rgb, dists, pts, rays_d, bg_alpha, bg_color, bg_rgb, B, n_in, n_out, inv_s, cos_anneal_ratio,
-      hit_idx, d_color, d_weights, d_weight_sum, d_w_pair, d_eik, eik_denom, d_sdf, d_normals, d_rgb, d_inv_s,
+      cos_anneal_dev, hit_idx, d_color, d_weights, d_weight_sum, d_w_pair, d_eik, eik_denom, d_sdf, d_normals, d_rgb, d_inv_s,
       d_bg_alpha, d_bg_color);
   prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();

@@ -344,7 +344,7 @@ static int sdf_fused_launch(const fneus_sdf_cfg* c, const SdfPlan& p, const floa
 static bool sdf_chain_ok(const fneus_sdf_cfg* c, const SdfPlan& p) {
   if (!p.img || precision_mode() != 1 || tc_prepare() != 0 || sdf_chain_prepare() != 0) return false;
   if (tc_debug_flags() & 16) return false;                       // debug: layered execution
-  if (!sdf_fused_ok(p) || 2 * p.L + 1 > SC_MAXS || p.L + 1 > SC_BIAS_SLOTS) return false;
+  if (!sdf_fused_ok(p) || 2 * p.L + 1 > SC_MAXS || p.L + 1 > sc_bias_slots<FAM_SDF_FWD>()) return false;
   if (c->d_out - 1 != p.in[p.L] || p.in[p.L] > 256 || (c->d_out - 1) % 4 != 0) return false;
   for (int l = 0; l < p.L; l++)                                  // every activation image is 4 blocks wide
     if (cdiv(p.out[l], TC_BK) != 4 || cdiv(p.in[l + 1], TC_BK) != 4) return false;

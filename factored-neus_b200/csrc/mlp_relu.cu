@@ -48,18 +48,18 @@ static ImgArena arena_at(float* after_floats, size_t cap_bytes) {
   return ar;
 }
 
-// First-operand image ([generated blocks | memory blocks], at most SC_NAR of 64 columns) kept for the
+// First-operand image ([generated blocks | memory blocks], at most SC_OPB_RELU of 64 columns) kept for the
 // layer-0 weight gradient, and the per-layer dY images of the fused backward chain.
-static inline long long a0_img_floats(long long M) { return mat_floats(M, SC_NAR * 64, true) + 256; }
+static inline long long a0_img_floats(long long M) { return mat_floats(M, SC_OPB_RELU * 64, true) + 256; }
 
 // Fused-chain eligibility (sdf_chain.cuh, <5, false> instantiation): 256-wide hidden layers (4-block activation
 // images), first operand = at most one generated block + memory blocks, at most 5 blocks in all.
 static bool chain_fusable(const Lin* lin, int n_lin, const ASeg& a0, int hid) {
   if (precision_mode() != 1 || tc_prepare() != 0 || sdf_chain_prepare() != 0) return false;
   if (tc_debug_flags() & 8) return false;                        // debug: layered execution
-  if (n_lin < 2 || n_lin + 2 > SC_MAXS || n_lin > SC_BIAS_SLOTS || a0.gen.deriv) return false;
+  if (n_lin < 2 || n_lin + 2 > SC_MAXS || n_lin > sc_bias_slots<FAM_RELU>() || a0.gen.deriv) return false;
   const int kb0 = cdiv(a0.gen.ncols, TC_BK) + cdiv(a0.kmem, TC_BK);
-  if (kb0 < 1 || kb0 > SC_NAR || hid != 256 || a0.gen.ncols > TC_BK || a0.kmem > 256) return false;
+  if (kb0 < 1 || kb0 > SC_OPB_RELU || hid != 256 || a0.gen.ncols > TC_BK || a0.kmem > 256) return false;
   for (int l = 0; l < n_lin; l++) {
     if (lin[l].out > 256) return false;
     if (l > 0 && lin[l].in != hid) return false;
@@ -140,7 +140,7 @@ static int relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin, 
   // the forward pass took the fused chain (FP16 activation images) exactly when relu_fwd_fused held; the fused
   // backward must then be possible too (the layered path reads BF16 images)
   const bool fwd_fused = relu_fwd_fused(lin, n_lin, a0, ldh, EPI_SIGMOID);
-  const bool fused = fwd_fused && lin[n_lin - 1].out <= TC_BK * SC_NAR && n_lin >= 2 &&
+  const bool fused = fwd_fused && lin[n_lin - 1].out <= TC_BK * SC_OPB_RELU && n_lin >= 2 &&
                      (ld_small & 3) == 0 && (ld_feats & 3) == 0;
   if (fwd_fused && !fused) return FNEUS_ERR_UNSUPPORTED;
   if (fused) {

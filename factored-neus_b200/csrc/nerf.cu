@@ -4,11 +4,15 @@
 //   rgb_linear.
 #include "gemm_tc.cuh"
 #include "prof.cuh"
+#include "sdf_chain.cuh"
+#include <string.h>
 
 namespace fneus {
 
 int num_sms();
 __global__ void colsum_kernel(const float*, int, int, const float*, float, float*, float*, long long, int);
+void launch_colsum(const float* X, int ldx, int K, const float* w, float wscale, float* out, float* osum, long long M,
+                   cudaStream_t st, int f16);
 
 struct NerfPlan {
   int D, W, e_p, e_v, skip;   // skip: index i after whose output the embedded input is concatenated (4)
@@ -101,6 +105,224 @@ __global__ void pad3to4_kernel(const float* __restrict__ in, float* __restrict__
   out[idx] = j < 3 ? in[m * 3 + j] : 0.f;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core path: the whole NeRF as ONE fused chain per pass (sdf_chain.cuh, ReLU family).
+// PE(pts) (<= 2 blocks) and PE(views) (1 block) are generated once per tile into the auxiliary area and stay there:
+// layer 0 reads PE(pts) as its operand, the skip layer reads [hidden (4 blocks) | PE(pts)], views_linears reads
+// [feature (4 blocks) | PE(views)] -- the weight images put the matching column ranges of W in that block order.
+// alpha_linear is a 1-wide output step off the last hidden state, which then stays in place for feature_linear.
+// Forward operands / images FP16, backward BF16 (fneus_common.cuh).
+// ------------------------------------------------------------------------------------------------
+static bool nerf_chain_ok(const NerfPlan& p) {
+  if (precision_mode() != 1 || tc_prepare() != 0 || sdf_chain_prepare() != 0) return false;
+  if (tc_debug_flags() & 32) return false;                        // debug: layered execution
+  return p.W == 256 && p.D >= 2 && p.D + 4 <= SC_MAXS && p.D + 4 <= sc_bias_slots<FAM_RELU>() && p.e_p <= 128 &&
+         p.e_v <= 64 && cdiv(p.e_p, TC_BK) + 1 <= SC_AUXGEN_MAX;
+}
+static inline long long nerf_hf(long long M) { return mat_floats(M, 256, true) + 256; }
+static inline float* nerf_align(float* q) {
+  return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(q) + 1023) & ~(uintptr_t)1023);
+}
+// weight images of one pass: every layer in both forms is < 64 tiles of 32 KB
+static constexpr long long NERF_IMG_FLOATS = (64LL * TC_B_BYTES + 65536) / 4;
+struct NerfImgs { float* H[20]; float* feat; float* V; float* pe; float* arena; };
+static NerfImgs nerf_carve(const NerfPlan& p, float* saved, long long M) {
+  NerfImgs b;
+  float* ptr = nerf_align(saved);
+  const long long hf = nerf_hf(M);
+  for (int i = 1; i <= p.D; i++) { b.H[i] = ptr; ptr += hf; }
+  b.feat = ptr; ptr += hf;
+  b.V = ptr; ptr += hf;
+  b.pe = ptr; ptr += mat_floats(M, SC_AUXGEN_MAX * TC_BK, true) + 256;
+  b.arena = ptr;
+  return b;
+}
+static long long nerf_saved_img_floats(const NerfPlan& p, long long M) {
+  return (p.D + 2) * nerf_hf(M) + mat_floats(M, SC_AUXGEN_MAX * TC_BK, true) + 256 + NERF_IMG_FLOATS + 1024;
+}
+static long long nerf_scratch_img_floats(const NerfPlan& p, long long M) {
+  return (p.D + 2) * nerf_hf(M) + 4 * M + 256 + NERF_IMG_FLOATS + 1024;
+}
+// [W[:, c0 : c0 + k0] | W[:, c1 : c1 + k1]] as consecutive K-major tiles (the chain's weight loader walks one image)
+static const uint8_t* nerf_wimg2(ImgArena& ar, const float* W, int ldw, int N, int c0, int k0, int c1, int k1,
+                                 cudaStream_t st) {
+  const uint8_t* a = make_wimg(ar, false, W, ldw, 0, N, 0, 0, c0, k0, st, 1);
+  const uint8_t* b = make_wimg(ar, false, W, ldw, 0, N, 0, 0, c1, k1, st, 1);
+  if (!a || !b || b != a + wimg_bytes(N, 0, k0)) return nullptr;
+  return a;
+}
+static GenSpec nerf_gen_aux(const fneus_nerf_cfg* c, const NerfPlan& p, const float* pts, const float* views) {
+  GenSpec g = gen_none();
+  gen_add(g, pts, c->d_in, c->multires);
+  gen_add(g, views, 3, c->multires_view);
+  g.it[1].col0 = cdiv(p.e_p, TC_BK) * TC_BK;                      // PE(views) starts its own block
+  g.ncols = g.it[1].col0 + p.e_v;
+  return g;
+}
+
+static int nerf_fwd_chain(const fneus_nerf_cfg* cfg, const NerfPlan& p, const float* w, const float* pts,
+                          const float* views, long long M, float* density_out, float* rgb_out, float* saved,
+                          cudaStream_t st) {
+  NerfImgs b = nerf_carve(p, saved, M);
+  ImgArena ar = arena_make(reinterpret_cast<uint8_t*>(nerf_align(b.arena)), (size_t)(NERF_IMG_FLOATS - 512) * 4);
+  const int W = p.W, kbp = cdiv(p.e_p, TC_BK);
+  SdfChainArgs g;
+  memset(&g, 0, sizeof(g));
+  double flops = 0.0;
+  int ns = 0, slot = 0;
+  for (int i = 0; i < p.D; i++) {
+    const float* Wi = w + p.pts[i].woff;
+    const bool skip = i > 0 && i - 1 == p.skip;
+    const uint8_t* img = i == 0 ? make_wimg(ar, false, Wi, p.e_p, 0, W, 0, 0, 0, p.e_p, st, 1)
+                       : skip   ? nerf_wimg2(ar, Wi, W + p.e_p, W, p.e_p, W, 0, p.e_p, st)
+                                : make_wimg(ar, false, Wi, W, 0, W, 0, 0, 0, W, st, 1);
+    if (!img) return FNEUS_ERR_WORKSPACE;
+    SdfStep S = sdf_step(SC_RELU, img, i == 0 ? kbp : (skip ? 4 + kbp : 4), W, 0);
+    if (i == 0) { S.src = SRC_AUXGEN; S.kb_op = 0; S.aux_blk0 = 0; }
+    else if (skip) { S.kb_op = 4; S.aux_blk0 = 0; }
+    S.bias = w + p.pts[i].boff; S.bias_slot = slot++;
+    S.img_out = b.H[i + 1];
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * p.pts[i].in * W;
+  }
+  {
+    const uint8_t* img = make_wimg(ar, false, w + p.head.woff, W, 0, 1, 0, 0, 0, W, st, 1);
+    if (!img) return FNEUS_ERR_WORKSPACE;
+    SdfStep S = sdf_step(SC_OUT, img, 4, 1, 0);                    // alpha_linear: raw density, the operand stays
+    S.bias = w + p.head.boff; S.bias_slot = slot++;
+    S.out = density_out; S.ldo = 1;
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * W;
+  }
+  {
+    const uint8_t* img = make_wimg(ar, false, w + p.head.woff, W, 1, W, 0, 0, 0, W, st, 1);
+    if (!img) return FNEUS_ERR_WORKSPACE;
+    SdfStep S = sdf_step(SC_RELU, img, 4, W, 0);                   // feature_linear: no activation
+    S.act = 2;
+    S.bias = w + p.head.boff + 1; S.bias_slot = slot++;
+    S.img_out = b.feat;
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * W * W;
+  }
+  {
+    const uint8_t* img = nerf_wimg2(ar, w + p.views.woff, W + p.e_v, W / 2, 0, W, W, p.e_v, st);
+    if (!img) return FNEUS_ERR_WORKSPACE;
+    SdfStep S = sdf_step(SC_RELU, img, 5, W / 2, 0);               // views_linears.0 on [feature | PE(views)]
+    S.kb_op = 4; S.aux_blk0 = kbp;
+    S.bias = w + p.views.boff; S.bias_slot = slot++;
+    S.img_out = b.V;
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * (W + p.e_v) * (W / 2);
+  }
+  {
+    const uint8_t* img = make_wimg(ar, false, w + p.rgb.woff, W / 2, 0, 3, 0, 0, 0, W / 2, st, 1);
+    if (!img) return FNEUS_ERR_WORKSPACE;
+    SdfStep S = sdf_step(SC_OUT, img, cdiv(W / 2, TC_BK), 3, 0);   // rgb_linear: raw colour
+    S.bias = w + p.rgb.boff; S.bias_slot = slot++;
+    S.out = rgb_out; S.ldo = 3;
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * (W / 2) * 3;
+  }
+  ar.flush(st);
+  g.nsteps = ns;
+  g.gen = nerf_gen_aux(cfg, p, pts, views); g.gen_t = g.gen;
+  g.aux_gen_blocks = kbp + 1;
+  g.a0_img = b.pe;
+  g.f16 = 1;
+  g.beta = 1.f; g.M = M; g.dbg = 0;
+  g.xflags = (tc_debug_flags() >> 8) & 15;
+  sdf_chain_launch(g, flops, st, FAM_RELU);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+static int nerf_bwd_chain(const fneus_nerf_cfg* cfg, const NerfPlan& p, const float* w, long long M,
+                          const float* d_density, const float* d_rgb, float* saved, float* scratch, float* dw,
+                          cudaStream_t st) {
+  NerfImgs b = nerf_carve(p, saved, M);
+  const int W = p.W, kbp = cdiv(p.e_p, TC_BK), D = p.D;
+  const long long hf = nerf_hf(M);
+  float* base = nerf_align(scratch);
+  float* dz[20];
+  for (int i = 0; i < D; i++) dz[i] = base + (long long)i * hf;   // gradient wrt layer i's pre-activation
+  float* dfeat = base + (long long)D * hf;
+  float* aV = dfeat + hf;
+  float* argb = aV + hf;
+  ImgArena ar = arena_make(reinterpret_cast<uint8_t*>(nerf_align(argb + 4 * M + 256)), (size_t)(NERF_IMG_FLOATS - 512) * 4);
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  pad3to4_kernel<<<cdiv(M * 4, 256), 256, 0, st>>>(d_rgb, argb, M);
+  prof_end(st);
+  SdfChainArgs g;
+  memset(&g, 0, sizeof(g));
+  double flops = 0.0;
+  int ns = 0;
+  {
+    const uint8_t* img = make_wimg(ar, true, w + p.rgb.woff, W / 2, 0, W / 2, 0, 0, 0, 3, st);
+    if (!img) return FNEUS_ERR_WORKSPACE;
+    SdfStep S = sdf_step(SC_MASK, img, 1, W / 2, 1);               // a_V = (d_rgb W_rgb) * [V > 0]
+    S.src = SRC_MEM; S.h = b.V; S.img_out = aV;
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * 3 * (W / 2);
+  }
+  {
+    const uint8_t* img = make_wimg(ar, true, w + p.views.woff, W + p.e_v, 0, W, 0, 0, 0, W / 2, st);
+    if (!img) return FNEUS_ERR_WORKSPACE;
+    SdfStep S = sdf_step(SC_MASK, img, cdiv(W / 2, TC_BK), W, 1);  // d_feature = a_V W_views[:, :W] (no activation)
+    S.img_out = dfeat;
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * (W / 2) * W;
+  }
+  {
+    const uint8_t* img = make_wimg(ar, true, w + p.head.woff, W, 0, W, 0, 0, 1, W, st);
+    if (!img) return FNEUS_ERR_WORKSPACE;
+    SdfStep S = sdf_step(SC_MASK, img, 4, W, 1);                   // dz_{D-1} = (d_feature W_feat + d_density w_alpha) * [h_D > 0]
+    S.h = b.H[D]; S.use_rs = 1; S.img_out = dz[D - 1];
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * W * (W + 1);
+  }
+  for (int i = D - 1; i >= 1; i--) {
+    const bool skip = i - 1 == p.skip;
+    const uint8_t* img = make_wimg(ar, true, w + p.pts[i].woff, p.pts[i].in, skip ? p.e_p : 0, W, 0, 0, 0, W, st);
+    if (!img) return FNEUS_ERR_WORKSPACE;
+    SdfStep S = sdf_step(SC_MASK, img, 4, W, 1);                   // dz_{i-1} = (dz_i W_i[:, hidden part]) * [h_i > 0]
+    S.h = b.H[i]; S.img_out = dz[i - 1];
+    g.st[ns++] = S;
+    flops += 2.0 * (double)M * W * W;
+  }
+  ar.flush(st);
+  g.nsteps = ns;
+  g.gen = gen_none(); g.gen_t = g.gen;
+  g.mem = argb; g.ldm = 4; g.kmem = 3;
+  g.rvec = w + p.head.woff; g.rs = d_density; g.rscale = 1.f;
+  g.f16 = 0;
+  g.beta = 1.f; g.M = M; g.dbg = 0;
+  g.xflags = (tc_debug_flags() >> 8) & 15;
+  sdf_chain_launch(g, flops, st, FAM_RELU);
+  // ---- weight gradients, one grouped launch: dz / d_feature / a_V are BF16 images of this pass, the activations FP16 ----
+  WgradGroup wg;
+  wg.reset(M, num_sms());
+  const int pe_ld = -(kbp + 1);
+  wg.add(argb, 4, aseg_mem(b.V, -4, W / 2), dw + p.rgb.woff, W / 2, 0, dw + p.rgb.boff, 3, st, 0, 1);
+  wg.add(aV, -4, aseg_mem(b.feat, -4, W, 0), dw + p.views.woff, W + p.e_v, 0, dw + p.views.boff, W / 2, st, 0, 1);
+  wg.add(aV, -4, aseg_mem(b.pe + (size_t)kbp * (TC_A_BYTES / 4), pe_ld, p.e_v, W), dw + p.views.woff, W + p.e_v, 0, nullptr,
+         W / 2, st, 0, 1);
+  wg.add(dfeat, -4, aseg_mem(b.H[D], -4, W), dw + p.head.woff, W, 1, dw + p.head.boff, W, st, 0, 1);
+  for (int i = D - 1; i >= 0; i--) {
+    float* dW = dw + p.pts[i].woff;
+    float* db = dw + p.pts[i].boff;
+    if (i == 0) wg.add(dz[0], -4, aseg_mem(b.pe, pe_ld, p.e_p, 0), dW, p.e_p, 0, db, W, st, 0, 1);
+    else if (i - 1 == p.skip) {
+      wg.add(dz[i], -4, aseg_mem(b.H[i], -4, W, p.e_p), dW, W + p.e_p, 0, db, W, st, 0, 1);
+      wg.add(dz[i], -4, aseg_mem(b.pe, pe_ld, p.e_p, 0), dW, W + p.e_p, 0, nullptr, W, st, 0, 1);
+    } else wg.add(dz[i], -4, aseg_mem(b.H[i], -4, W), dW, W, 0, db, W, st, 0, 1);
+  }
+  wg.flush(st);
+  // alpha_linear: dW[0, :] += sum_m d_density[m] h_D[m, :], db[0] += sum_m d_density[m]
+  launch_colsum(b.H[D], -4, W, d_density, 1.f, dw + p.head.woff, dw + p.head.boff, M, st, 1);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
 static GenSpec nerf_gen_pts(const fneus_nerf_cfg* c, const float* pts) {
   GenSpec g = gen_none(); gen_add(g, pts, c->d_in, c->multires); return g;
 }
@@ -116,10 +338,14 @@ extern "C" {
 
 long long fneus_nerf_pack_floats(const fneus_nerf_cfg* cfg) { NerfPlan p = nerf_plan(cfg); return p.ok ? p.pack : -1; }
 long long fneus_nerf_saved_floats(const fneus_nerf_cfg* cfg, long long n) {
-  NerfPlan p = nerf_plan(cfg); return p.ok ? nerf_saved_per_point(p) * n : -1;
+  NerfPlan p = nerf_plan(cfg);
+  if (!p.ok) return -1;
+  return nerf_chain_ok(p) ? nerf_saved_img_floats(p, n) : nerf_saved_per_point(p) * n;
 }
 long long fneus_nerf_scratch_floats(const fneus_nerf_cfg* cfg, long long n) {
-  NerfPlan p = nerf_plan(cfg); return p.ok ? nerf_scratch_per_point(p) * n : -1;
+  NerfPlan p = nerf_plan(cfg);
+  if (!p.ok) return -1;
+  return nerf_chain_ok(p) ? nerf_scratch_img_floats(p, n) : nerf_scratch_per_point(p) * n;
 }
 
 int fneus_nerf_fwd(const fneus_nerf_cfg* cfg, const float* wpack, const float* pts, const float* views, long long M,
@@ -129,6 +355,7 @@ int fneus_nerf_fwd(const fneus_nerf_cfg* cfg, const float* wpack, const float* p
   if (M == 0) return FNEUS_OK;
   if (!wpack || !pts || !views || !density_out || !rgb_out || !saved) return FNEUS_ERR_NULL;
   cudaStream_t st = (cudaStream_t)stream;
+  if (nerf_chain_ok(p)) return nerf_fwd_chain(cfg, p, wpack, pts, views, M, density_out, rgb_out, saved, st);
   const int W = p.W;
   float* H[20];
   for (int i = 1; i <= p.D; i++) H[i] = saved + (long long)(i - 1) * M * W;
@@ -172,6 +399,7 @@ int fneus_nerf_bwd(const fneus_nerf_cfg* cfg, const float* wpack, const float* p
   if (M == 0) return FNEUS_OK;
   if (!wpack || !pts || !views || !d_density || !d_rgb || !saved || !scratch || !d_wpack) return FNEUS_ERR_NULL;
   cudaStream_t st = (cudaStream_t)stream;
+  if (nerf_chain_ok(p)) return nerf_bwd_chain(cfg, p, wpack, M, d_density, d_rgb, saved, scratch, d_wpack, st);
   const int sms = num_sms();
   const int W = p.W;
   float* H[20];

@@ -52,14 +52,22 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-constexpr int SC_THREADS = 640, SC_WSTAGES = 4, SC_MAXS = 20, SC_BIAS_SLOTS = 10, SC_EPI_THREADS = 512;
-constexpr int SC_NAR = 5;                                         // operand blocks a step may read (a_ready barriers)
+constexpr int SC_THREADS = 640, SC_WSTAGES = 4, SC_MAXS = 20, SC_EPI_THREADS = 512;
+constexpr int SC_NAR = 6;                                         // operand blocks a step may read (a_ready barriers)
+constexpr int SC_OPB_RELU = 5;                                    // running-operand blocks of the ReLU family
+constexpr int SC_AUXGEN_MAX = 3;                                  // generated blocks that may live in the auxiliary area
 // SDF modes (Softplus network) and the ReLU-network modes (RenderingNetwork / RefColor / Lvis chains):
 //   SC_RELU : y = max(acc + bias, 0) -> next operand (+ image)        SC_MASK : y = acc * [h > 0] -> next operand (+ image)
 //   SC_OUT  : FP32 result rows to HBM (bias, optional sigmoid, optional accumulate); the operand stays as it is
+// SC_RELU with act = 2 is a plain linear layer (bias only); SC_MASK without an h image passes the product through, and
+// with use_rs adds the rank-1 term rs[m] * rvec[n] before the mask (a 1-wide head next to a wide one: NeRF's alpha_linear).
 enum SdfStepMode { SC_SOFTPLUS = 0, SC_FEATQ, SC_SPMUL, SC_G0, SC_SWEEP, SC_SDFBWD, SC_RELU, SC_MASK, SC_OUT };
 // SRC_GENMEM: [one generated block | memory blocks (FP32 row-major, or an activation image when ldm < 0)]
-enum SdfStepSrc { SRC_CHAIN = 0, SRC_PE, SRC_TAN, SRC_MEM, SRC_GENMEM };
+// SRC_AUXGEN: up to SC_AUXGEN_MAX generated blocks written once per tile into the AUXILIARY area, where they stay for the
+//             whole chain: a step reads its first kb_op operand blocks from the running operand and the remaining
+//             KB - kb_op blocks from auxiliary blocks aux_blk0.. (the outside NeRF: PE(pts) is the input of layer 0 AND is
+//             concatenated to the hidden state at the skip, PE(views) joins the feature vector; fields.py:233-259)
+enum SdfStepSrc { SRC_CHAIN = 0, SRC_PE, SRC_TAN, SRC_MEM, SRC_GENMEM, SRC_AUXGEN };
 
 struct SdfStep {
   const uint8_t* wimg;  // weight image ([1 n-chunk][KB] tiles of 32 KB)
@@ -70,6 +78,7 @@ struct SdfStep {
   float* e_out;         // SWEEP: image e_l (rewritten over the h block in shared memory)
   float* out;           // FEATQ: features FP32 [M, ldo] ; G0: normal FP32 [M, d_in]
   int KB, N, mode, bmn, src;
+  int kb_op, aux_blk0;  // operand blocks [0, kb_op) come from the running operand, [kb_op, KB) from auxiliary block aux_blk0 + ..
   int ldo, csplit, append, dot, use_rs, bias_slot;
   int act, accumulate;  // OUT: act 1 = sigmoid ; accumulate: out += result
   int sync_stores;      // storer: wait for full completion of every store so far after this step (later steps read them back)
@@ -84,7 +93,9 @@ struct SdfChainArgs {
   const float* mem;     // SRC_MEM: FP32 [M, ldm], kmem columns
   int ldm, kmem;
   float* pe_img;        // optional 1-block image copy of the SRC_PE / SRC_TAN operand
-  float* a0_img;        // SRC_GENMEM: optional image copy of the whole first operand ([M, 1 + kb_mem blocks])
+  float* a0_img;        // SRC_GENMEM: optional image copy of the whole first operand ([M, 1 + kb_mem blocks]);
+                        // SRC_AUXGEN: optional image copy of the auxiliary generated blocks ([M, aux_gen_blocks blocks])
+  int aux_gen_blocks;   // SRC_AUXGEN: generated blocks in the auxiliary area (columns of `gen`, 64 per block)
   const float* rvec;    // row 0 of the last linear [<= 256]
   const float* b_last;  // its bias
   float* sdf_out;       // [M]
@@ -110,6 +121,8 @@ struct SCSmem {
 // Auxiliary slots (h block + q block, 32 KB each) and weight stages per family: the backward chain is HBM-bound and
 // needs bytes in flight (Little: 6.5 TB/s x ~1.2 us = 53 KB per SM), so it trades one weight stage for a third slot.
 template <int FAM> __host__ __device__ constexpr int sc_nslot() { return FAM == 1 ? 3 : 2; }
+// bias rows staged in shared memory: the ReLU family runs the 12-linear NeRF chain
+template <int FAM> __host__ __device__ constexpr int sc_bias_slots() { return FAM == 2 ? 12 : 10; }
 template <int FAM> __host__ __device__ constexpr int sc_wstages() { return FAM == 1 ? 3 : SC_WSTAGES; }
 constexpr int SC_PARK_LD = 41;                                   // odd row stride: thread-per-row accesses hit 32 banks
 // Three instantiations, each compiling only its own modes (the union was 127 KB of SASS and ran 15% slower on
@@ -118,10 +131,10 @@ constexpr int SC_PARK_LD = 41;                                   // odd row stri
 enum ChainFamily { FAM_SDF_FWD = 0, FAM_SDF_BWD = 1, FAM_RELU = 2 };
 template <int FAM>
 constexpr int sc_smem_bytes() {
-  constexpr int OPB = FAM == FAM_RELU ? 5 : 4;
+  constexpr int OPB = FAM == FAM_RELU ? SC_OPB_RELU : 4;
   constexpr bool PARK = FAM == FAM_SDF_FWD;
   return OPB * TC_A_BYTES + sc_wstages<FAM>() * CH_WBYTES + sc_nslot<FAM>() * 2 * TC_A_BYTES +
-         (SC_BIAS_SLOTS * 256 + 256 + 128 + (PARK ? 128 * SC_PARK_LD : 0)) * 4 + 1024 + 256;
+         (sc_bias_slots<FAM>() * 256 + 256 + 128 + (PARK ? 128 * SC_PARK_LD : 0)) * 4 + 1024 + 256;
 }
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float* out) { u16x8_to_f32(u, false, out); }
@@ -181,7 +194,7 @@ __device__ __forceinline__ int sdf_step_blocks(const SdfStep& S) {
 // The kernel body for CTA `cta` of `nctas` working on chain `g` (g lives in the kernel parameter space).
 template <int FAM>
 __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta, const int nctas) {
-  constexpr int OPB = FAM == FAM_RELU ? 5 : 4;
+  constexpr int OPB = FAM == FAM_RELU ? SC_OPB_RELU : 4;
   constexpr bool PARK = FAM == FAM_SDF_FWD;
   constexpr bool FWD = FAM == FAM_SDF_FWD, BWD = FAM == FAM_SDF_BWD;
   extern __shared__ uint8_t tc_smem_raw[];
@@ -191,8 +204,9 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
   uint8_t* sW0 = base + OPB * TC_A_BYTES;
   constexpr int NSLOT = sc_nslot<FAM>(), WST = sc_wstages<FAM>();
   uint8_t* sAux = sW0 + WST * CH_WBYTES;                         // slot i: h block at 2i, q block at 2i+1 (16 KB each)
-  float* sbias = reinterpret_cast<float*>(sAux + NSLOT * 2 * TC_A_BYTES);  // [SC_BIAS_SLOTS][256]
-  float* srvec = sbias + SC_BIAS_SLOTS * 256;                    // [256]
+  constexpr int NBIAS = sc_bias_slots<FAM>();
+  float* sbias = reinterpret_cast<float*>(sAux + NSLOT * 2 * TC_A_BYTES);  // [NBIAS][256]
+  float* srvec = sbias + NBIAS * 256;                            // [256]
   float* sdot = srvec + 256;                                     // [128]
   float* spark = sdot + 128;                                     // [128][SC_PARK_LD]: skip part of the input gradient
   SCSmem* ctl = reinterpret_cast<SCSmem*>(spark + (PARK ? 128 * SC_PARK_LD : 0));
@@ -276,7 +290,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
               mbar_wait(&ctl->wfull[stg], (kbg / WST) & 1);
               tc_fence_after();
               const uint32_t b_addr = smem_u32(sW0 + stg * CH_WBYTES);
-              const uint32_t a_addr = smem_u32(sOp) + kb * TC_A_BYTES;
+              const uint32_t a_addr = (SDF || kb < S.kb_op) ? smem_u32(sOp) + kb * TC_A_BYTES
+                                                            : smem_u32(sAux) + (S.aux_blk0 + kb - S.kb_op) * TC_A_BYTES;
 #pragma unroll
               for (int k = 0; k < 4; k++) {
                 const uint64_t bd = S.bmn ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
@@ -395,6 +410,22 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
               *reinterpret_cast<uint4*>(dst + ch0) = *reinterpret_cast<const uint4*>(rowA + ch0);
               *reinterpret_cast<uint4*>(dst + ch1) = *reinterpret_cast<const uint4*>(rowA + ch1);
             }
+          } else if (!SDF && S.src == SRC_AUXGEN) {
+            // generated blocks into the auxiliary area (they stay there for the whole chain of this tile); the previous
+            // tile's MMAs that read them are complete (its last epilogue has passed acc_full)
+#pragma unroll 1
+            for (int blk = 0; blk < g.aux_gen_blocks; blk++) {
+              uint8_t* rowA = sAux + blk * TC_A_BYTES + rowoff;
+              *reinterpret_cast<uint4*>(rowA + ch0) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(rowA + ch1) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            epi_bar();
+            if (valid)
+              gen_row_part(g.gen, m, cg, 4, [&](int j, float val) {
+                if (j < g.aux_gen_blocks * TC_BK)
+                  *reinterpret_cast<unsigned short*>(sAux + (j >> 6) * TC_A_BYTES + rowoff + (((((j & 63) >> 3) ^ r7) & 7) << 4) +
+                                                     ((j & 7) << 1)) = f32_to_u16_bits(val, opf16);
+              });
           } else if (!FWD) {
             uint8_t* sMem = sOp;                                           // first block of the memory segment
             if (!SDF && S.src == SRC_GENMEM) {
@@ -455,7 +486,16 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           }
           tc_fence_before();
           fence_proxy_async();
-          if (!SDF && (S.src == SRC_GENMEM || S.src == SRC_MEM) && g.a0_img != nullptr) {
+          if (!SDF && S.src == SRC_AUXGEN && g.a0_img != nullptr) {
+            // image copy of the generated blocks (the weight gradients of the layers that consume them read it back)
+            epi_bar();
+            if (et == 0) {
+              bulk_s2g(reinterpret_cast<uint8_t*>(g.a0_img) + (size_t)tile * g.aux_gen_blocks * TC_A_BYTES, sAux,
+                       (uint32_t)g.aux_gen_blocks * TC_A_BYTES);
+              bulk_commit();
+            }
+            a0_pending = true;
+          } else if (!SDF && (S.src == SRC_GENMEM || S.src == SRC_MEM) && g.a0_img != nullptr) {
             // image copy of the whole first operand (the layer-0 weight gradient reads it back): one bulk store; its
             // shared-memory reads are over before anybody overwrites the operand (barrier below)
             epi_bar();
@@ -485,7 +525,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
         const float ksg = -beta * S.hscale * 1.4426950408889634f;       // s(h) = 1 - 2^(ksg h)
         const float kz = beta * 1.4426950408889634f, kinv = 0.6931471805599453f * inv_beta;
         const int lim = (mode == SC_SPMUL || mode == SC_SDFBWD) ? csplit : N;
-        const float rsv = (mode == SC_SDFBWD && S.use_rs && valid) ? __ldg(g.rs + m) * g.rscale : 0.f;
+        const float rsv = ((mode == SC_SDFBWD || mode == SC_MASK) && S.use_rs && valid) ? __ldg(g.rs + m) * g.rscale : 0.f;
         float dot = 0.f;
         const uint32_t tacc = taddr + (uint32_t)((lg & 1) << 8);         // this step's accumulator buffer
         const bool feeds_next = s + 1 < g.nsteps && g.st[s + 1].src == SRC_CHAIN;
@@ -638,22 +678,27 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
               *reinterpret_cast<uint4*>(hb + (hf ? ch1 : ch0)) = f32x8_to_bf16(e);   // e_l leaves from where h_{l+1} arrived
             }
           } else if (!SDF && mode == SC_RELU) {
+            const float floor_v = S.act == 2 ? -3.0e38f : 0.f;            // act 2: plain linear layer
             if (full) {
 #pragma unroll
-              for (int j = 0; j < 16; j++) a[j] = fmaxf(a[j] + sb[n + j], 0.f);
+              for (int j = 0; j < 16; j++) a[j] = fmaxf(a[j] + sb[n + j], floor_v);
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? fmaxf(a[j] + sb[n + j], 0.f) : 0.f;
+              for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? fmaxf(a[j] + sb[n + j], floor_v) : 0.f;
             }
           } else if (!SDF && mode == SC_MASK) {
-            // dz_{l-1} = (dz_l W_l) * [h_l > 0]: the forward activation block arrived in the slot's h block
+            // dz_{l-1} = (dz_l W_l [+ rs rvec]) * [h_l > 0]: the forward activation block arrived in the slot's h block
+            const bool has_h = S.h != nullptr;
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
               bool pos[8];                                                               // forward image, either format
-              u16x8_positive(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), pos);
+              if (has_h) u16x8_positive(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), pos);
 #pragma unroll
-              for (int j = 0; j < 8; j++)
-                a[hf * 8 + j] = (pos[j] && (full || (valid && n + hf * 8 + j < N))) ? a[hf * 8 + j] : 0.f;
+              for (int j = 0; j < 8; j++) {
+                const int nn = n + hf * 8 + j;
+                const float v = S.use_rs ? fmaf(rsv, srvec[nn], a[hf * 8 + j]) : a[hf * 8 + j];
+                a[hf * 8 + j] = ((!has_h || pos[j]) && (full || (valid && nn < N))) ? v : 0.f;
+              }
             }
           } else if (!SDF && mode == SC_OUT) {
             if (N <= 16) {
@@ -814,6 +859,7 @@ inline SdfStep sdf_step(int mode, const uint8_t* wimg, int KB, int N, int bmn) {
   SdfStep S;
   memset(&S, 0, sizeof(S));
   S.mode = mode; S.wimg = wimg; S.KB = KB; S.N = N; S.bmn = bmn; S.src = SRC_CHAIN;
+  S.kb_op = KB; S.aux_blk0 = 0;
   S.csplit = N; S.bias_slot = -1; S.hscale = 1.f; S.oscale = 1.f; S.ldo = 4;
   return S;
 }

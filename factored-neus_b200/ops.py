@@ -506,6 +506,9 @@ class Composite(torch.autograd.Function):
             bgr = bgr.reshape(-1)[:3].contiguous()
         B = rd_c.shape[0]
         n_tot = n_in + n_out
+        # cos_anneal_ratio: a python float, or a DEVICE scalar tensor (read by the kernels: graph-capturable schedule)
+        car_dev = _f32c(car).reshape(-1)[:1].contiguous() if torch.is_tensor(car) else None
+        car = 0.0 if car_dev is not None else float(car)
         f32 = dict(dtype=torch.float32, device=dev)
         color = torch.empty(B, 3, **f32)
         weights = torch.empty(B, n_tot, **f32)
@@ -518,14 +521,15 @@ class Composite(torch.autograd.Function):
         wpair = torch.empty(B, 2, **f32)
         L.check(L.lib().fneus_composite_fwd(
             L.ptr(sdf_c), L.ptr(nrm_c), L.ptr(rgb_c), L.ptr(dists_c), L.ptr(pts_c), L.ptr(rd_c), L.ptr(bga),
-            L.ptr(bgc), L.ptr(bgr), B, n_in, n_out, L.ptr(inv_c), float(car), L.ptr(color), L.ptr(weights),
+            L.ptr(bgc), L.ptr(bgr), B, n_in, n_out, L.ptr(inv_c), car, L.ptr(car_dev), L.ptr(color), L.ptr(weights),
             L.ptr(wsum), L.ptr(wmax), L.ptr(cdf), L.ptr(inside), L.ptr(eik), L.ptr(hit), L.ptr(wpair),
             L.stream_ptr()), "fneus_composite_fwd")
         tot = eik.sum(0)
         eik_num, eik_den = tot[0].reshape(()), tot[1].reshape(())
         denom = torch.ones(1, dtype=torch.float32, device=dev)
         ctx.save_for_backward(sdf_c, nrm_c, rgb_c, inv_c, bga, bgc, dists_c, pts_c, rd_c, bgr, hit, denom)
-        ctx.dims = (B, n_in, n_out, float(car))
+        ctx.dims = (B, n_in, n_out, car)
+        ctx.car_dev = car_dev
         ctx.shapes = (sdf.shape, normals.shape, rgb.shape, inv_s.shape)
         ctx.mark_non_differentiable(wmax, cdf, inside, hit, eik_den)
         ctx.set_materialize_grads(False)
@@ -544,7 +548,7 @@ class Composite(torch.autograd.Function):
         d_eik_c = _f32c(d_eik).reshape(1) if d_eik is not None else None
         L.check(L.lib().fneus_composite_bwd(
             L.ptr(sdf_c), L.ptr(nrm_c), L.ptr(rgb_c), L.ptr(dists_c), L.ptr(pts_c), L.ptr(rd_c), L.ptr(bga),
-            L.ptr(bgc), L.ptr(bgr), B, n_in, n_out, L.ptr(inv_c), car, L.ptr(hit), L.ptr(_f32c(d_color)),
+            L.ptr(bgc), L.ptr(bgr), B, n_in, n_out, L.ptr(inv_c), car, L.ptr(ctx.car_dev), L.ptr(hit), L.ptr(_f32c(d_color)),
             L.ptr(_f32c(d_weights)), L.ptr(_f32c(d_wsum)), L.ptr(_f32c(d_wpair)), L.ptr(d_eik_c), L.ptr(denom),
             L.ptr(d_sdf), L.ptr(d_nrm), L.ptr(d_rgb), L.ptr(d_inv), L.ptr(d_bga), L.ptr(d_bgc), L.stream_ptr()),
             "fneus_composite_bwd")

@@ -108,7 +108,7 @@ class NeuSRenderer:
         n_out = 0 if background_alpha is None else background_alpha.shape[1] - n
         color, weights, wsum, wmax, cdf, inside, eik_num, eik_den, hit_idx, w_pair = ops.Composite.apply(
             sdf, normals, rgb, inv_s, background_alpha, background_sampled_color, dists, pts, rays_d,
-            background_rgb, n, n_out, float(cos_anneal_ratio))
+            background_rgb, n, n_out, cos_anneal_ratio if torch.is_tensor(cos_anneal_ratio) else float(cos_anneal_ratio))
         grad_err = eik_num / (eik_den + 1e-5)
         self.last_eikonal_parts = (eik_num, eik_den)     # for exact loss normalisation across ray shards
 

@@ -38,6 +38,9 @@ class Stage1Trainer:
         self._stream = torch.cuda.Stream(device=self.device) if use_graph else None
         self._warm = 0
         self.last_stats = None
+        # cos_anneal_ratio as a device scalar: written before every step, read by the compositing kernels, so that the
+        # annealed (womask, anneal_end > 0) schedule runs inside the captured step too
+        self._car_dev = torch.ones(1, dtype=torch.float32, device=self.device)
 
     # exp_runner.py:229-238
     def _lr_at(self, it):
@@ -57,8 +60,7 @@ class Stage1Trainer:
         from . import ops
         near, far = ops.near_far_from_sphere(ro, rd)                      # dataset.near_far_from_sphere
         bg = torch.ones([1, 3], device=batch.device) if self.use_white_bkgd else None
-        out = self.renderer.render(ro, rd, near, far, background_rgb=bg,
-                                   cos_anneal_ratio=self._car)
+        out = self.renderer.render(ro, rd, near, far, background_rgb=bg, cos_anneal_ratio=self._car_dev)
         loss, stats = stage1_loss_sharded(self.renderer, out, rgb, m, self.surface_weight, self.igr_weight,
                                           self.mask_weight)
         loss.backward()                                                  # the bucket is cleared by the optimiser step
@@ -69,8 +71,8 @@ class Stage1Trainer:
     def step(self, batch):
         """batch [B,10] = (rays_o, rays_d, true_rgb, mask) as produced by Dataset.gen_random_rays_at
         (dataset.py:133-151).  Returns the (local-shard) loss tensor."""
-        self._car = self.cos_anneal_ratio()
-        if not self.use_graph or self.anneal_end != 0:                     # a moving cos_anneal_ratio is a host scalar
+        self._car_dev.fill_(self.cos_anneal_ratio())                      # outside the graph: replays read the new value
+        if not self.use_graph:
             loss = self._eager_step(batch)
         else:
             cur = torch.cuda.current_stream()

@@ -247,11 +247,13 @@ int fneus_core_geometry(const float* rays_o, const float* rays_d, const float* z
  * bg_color [B,n_in+n_out,3] (NULL when n_out==0 and no background model), bg_rgb [3] or NULL.
  * Outputs: color [B,3], weights [B,n_in+n_out], weight_sum [B], weight_max [B], cdf [B,n_in],
  * inside [B,n_in], eik_part [B,2] (sum relax*(|g|-1)^2, sum relax), hit_idx [B] int32 (-1 = no surface hit),
- * w_pair [B,2] (inside-weights at hit_idx-1, hit_idx, +1e-5; 1 when no hit). */
+ * w_pair [B,2] (inside-weights at hit_idx-1, hit_idx, +1e-5; 1 when no hit).
+ * cos_anneal_dev: optional DEVICE scalar that overrides cos_anneal_ratio (exp_runner.py:223-227 moves it every iteration
+ * of womask; read from the device it can change between replays of a captured step). */
 int fneus_composite_fwd(const float* sdf, const float* normals, const float* rgb, const float* dists,
                         const float* pts, const float* rays_d, const float* bg_alpha, const float* bg_color,
                         const float* bg_rgb, long long n_rays, int n_in, int n_out, const float* inv_s,
-                        float cos_anneal_ratio, float* color, float* weights, float* weight_sum,
+                        float cos_anneal_ratio, const float* cos_anneal_dev, float* color, float* weights, float* weight_sum,
                         float* weight_max, float* cdf, float* inside, float* eik_part, int* hit_idx,
                         float* w_pair, void* stream);
 /* Backward.  Upstream: d_color [B,3], d_weights [B,n_in+n_out] (NULL ok), d_weight_sum [B] (NULL ok),
@@ -262,7 +264,7 @@ int fneus_composite_fwd(const float* sdf, const float* normals, const float* rgb
 int fneus_composite_bwd(const float* sdf, const float* normals, const float* rgb, const float* dists,
                         const float* pts, const float* rays_d, const float* bg_alpha, const float* bg_color,
                         const float* bg_rgb, long long n_rays, int n_in, int n_out, const float* inv_s,
-                        float cos_anneal_ratio, const int* hit_idx, const float* d_color,
+                        float cos_anneal_ratio, const float* cos_anneal_dev, const int* hit_idx, const float* d_color,
                         const float* d_weights, const float* d_weight_sum, const float* d_w_pair,
                         const float* d_eik, const float* eik_denom, float* d_sdf, float* d_normals,
                         float* d_rgb, float* d_inv_s, float* d_bg_alpha, float* d_bg_color, void* stream);
