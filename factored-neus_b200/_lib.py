@@ -86,6 +86,8 @@ _SIGNATURES = {
     "fneus_loss_norms": (c_int, [_P, _P, _P, _LL, c_int, _P, _P]),
     "fneus_stage1_loss": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, c_int, c_float, c_float, c_float, _P, _P, _P,
                                   _P, _P, _P]),
+    "fneus_stage2_loss": (c_int, [_P, _P, _P, _P, _P, _P, _LL, c_int, _P, _P, _P, _P]),
+    "fneus_gen_rays": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _LL, _P, _P, _P, _P]),
     "fneus_near_far": (c_int, [_P, _P, _LL, _P, _P, _P]),
     "fneus_coarse_z": (c_int, [_P, _P, _P, _P, _LL, c_int, c_float, _P, _P]),
     "fneus_hit_rows": (c_int, [_P, _LL, c_int, _P, _P]),

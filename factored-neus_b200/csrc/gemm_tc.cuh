@@ -1294,9 +1294,9 @@ inline void launch_tc_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, 
 inline int& tc_wgrad_group_waves() { static int v = 2; return v; }
 struct WgradGroup {
   WgradJobs jobs;
-  double flops;
+  double flops, bytes;               // algorithmic FLOPs; designed DRAM bytes (both operands once + the FP32 gradient)
   int num_sms;
-  void reset(long long M, int sms) { jobs.n = 0; jobs.M = (int)M; flops = 0.0; num_sms = sms; }
+  void reset(long long M, int sms) { jobs.n = 0; jobs.M = (int)M; flops = 0.0; bytes = 0.0; num_sms = sms; }
   void add(const float* dY, int ldy, const ASeg& a, float* dW, int ldw, int wout0, float* db, int N, cudaStream_t st,
            int y_f16 = 0, int x_f16 = 0) {
     const long long M = jobs.M;
@@ -1308,6 +1308,8 @@ struct WgradGroup {
     j.y_f16 = y_f16; j.x_f16 = x_f16;
     j.tiles = cdiv(N, 128) * kchunks;
     flops += 2.0 * (double)M * N * (a.gen.ncols + a.kmem);
+    bytes += (double)M * ((ldy < 0 ? 2.0 : 4.0) * N + (a.ldm < 0 ? 2.0 : 4.0) * a.kmem + 12.0 * (a.gen.ncols > 0 ? 1 : 0)) +
+             4.0 * (double)N * (a.gen.ncols + a.kmem);
   }
   void flush(cudaStream_t st) {
     if (jobs.n == 0) return;
@@ -1324,7 +1326,7 @@ struct WgradGroup {
     const int mps = round_up(cdiv(M, splits), TC_BK);
     splits = cdiv(M, mps);
     for (int i = 0; i < jobs.n; i++) { jobs.job[i].m_per_split = mps; jobs.job[i].splits = splits; }
-    prof_begin(PC_TC_MLP, flops, 0.0, st);
+    prof_begin(PC_TC_WGRAD, flops, bytes, st);
     tc_gemm_wgrad_group_kernel<<<dim3(max_tiles, splits, jobs.n), TC_THREADS, TC_SMEM_BYTES, st>>>(jobs);
     prof_end(st);
     reset(M, num_sms);

@@ -183,6 +183,63 @@ __global__ void adam_step_kernel(float* __restrict__ p, float* __restrict__ g, f
     upd(p[i], g[i], m[i], v[i]);
 }
 
+// ---- stage-2 loss (lvis.py:163-170), one block: ------------------------------------------------------------------
+//   lvis_loss = sum |gt_lvis - pre_lvis| / (k n_hit + 1e-6)                 (difference NOT masked: rows without a hit are
+//                                                                            ones on both sides in the reference)
+//   rad_loss  = sum |(gt_rad - pre_rad) * hit| / (3 k n_hit + 1e-6)
+// parts3 = [loss, lvis_loss, rad_loss]; d_pre_lvis / d_pre_rad = d loss / d prediction (sign / denominator).
+// den2: optional [k n_hit + 1e-6, 3 k n_hit + 1e-6] over the WHOLE batch (ray-sharded data parallelism), else local.
+__global__ void stage2_loss_kernel(const float* __restrict__ gt_lvis, const float* __restrict__ pre_lvis,
+                                   const float* __restrict__ gt_rad, const float* __restrict__ pre_rad,
+                                   const int* __restrict__ hit_idx, const float* __restrict__ den2, int B, int k,
+                                   float* __restrict__ parts3, float* __restrict__ d_pre_lvis,
+                                   float* __restrict__ d_pre_rad) {
+  __shared__ float red[3][32];
+  __shared__ float tot[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float nh = 0.f, sl = 0.f, sr = 0.f;
+  for (int b = tid; b < B; b += blockDim.x) {
+    const bool hit = hit_idx[b] >= 0;
+    nh += hit ? 1.f : 0.f;
+    for (int j = 0; j < k; j++) {
+      sl += fabsf(gt_lvis[b * k + j] - pre_lvis[b * k + j]);
+      if (hit)
+        for (int c = 0; c < 3; c++) sr += fabsf(gt_rad[(b * k + j) * 3 + c] - pre_rad[(b * k + j) * 3 + c]);
+    }
+  }
+  float v[3] = {nh, sl, sr};
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+    if (lane == 0) red[q][warp] = v[q];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      float x = lane < (int)(blockDim.x >> 5) ? red[q][lane] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0) tot[q] = x;
+    }
+  }
+  __syncthreads();
+  const float dl = den2 ? den2[0] : (float)k * tot[0] + 1e-6f;
+  const float dr = den2 ? den2[1] : 3.f * (float)k * tot[0] + 1e-6f;
+  if (tid == 0) {
+    const float a = tot[1] / dl, r = tot[2] / dr;
+    parts3[0] = a + r; parts3[1] = a; parts3[2] = r;
+  }
+  auto sgn = [](float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); };
+  for (int i = tid; i < B * k; i += blockDim.x) {
+    const bool hit = hit_idx[i / k] >= 0;
+    if (d_pre_lvis) d_pre_lvis[i] = sgn(pre_lvis[i] - gt_lvis[i]) / dl;
+    if (d_pre_rad)
+      for (int c = 0; c < 3; c++) d_pre_rad[i * 3 + c] = hit ? sgn(pre_rad[i * 3 + c] - gt_rad[i * 3 + c]) / dr : 0.f;
+  }
+}
+
 }  // namespace fneus
 
 using namespace fneus;
@@ -268,6 +325,20 @@ int fneus_adam_step(float* p, float* g, float* m, float* v, long long n, float* 
   if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
   prof_begin(PC_ELEMENTWISE, 0.0, 32.0 * (double)n, st);
   adam_step_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n4, n, state4, beta1, beta2, eps, grad_scale, zero_grad);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_stage2_loss(const float* gt_lvis, const float* pre_lvis, const float* gt_rad, const float* pre_rad,
+                      const int* hit_idx, const float* den2, long long B, int k, float* parts3, float* d_pre_lvis,
+                      float* d_pre_rad, void* stream) {
+  if (!gt_lvis || !pre_lvis || !gt_rad || !pre_rad || !hit_idx || !parts3) return FNEUS_ERR_NULL;
+  if (B < 0 || B > (1 << 26) || k < 1 || k > 64) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_COMPOSITE, 0.0, 0.0, st);
+  stage2_loss_kernel<<<1, 1024, 0, st>>>(gt_lvis, pre_lvis, gt_rad, pre_rad, hit_idx, den2, (int)B, k, parts3, d_pre_lvis,
+                                         d_pre_rad);
   prof_end(st);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;

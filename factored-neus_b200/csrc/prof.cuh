@@ -7,8 +7,10 @@
 
 namespace fneus {
 
+// PC_TC_MLP: single-layer tensor-core GEMMs; the fused chains and the grouped weight gradients have their own classes so
+// that bench.py can put each kernel on its own roofline (flops = algorithmic FLOPs, bytes = designed DRAM bytes).
 enum ProfClass { PC_GEMM_FWD = 0, PC_GEMM_BWD_DATA, PC_GEMM_WGRAD, PC_SAMPLING, PC_COMPOSITE, PC_ELEMENTWISE,
-                 PC_TC_MLP, PC_COUNT };
+                 PC_TC_MLP, PC_CHAIN_SDF_FWD, PC_CHAIN_SDF_BWD, PC_CHAIN_RELU, PC_TC_WGRAD, PC_COUNT };
 
 struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 struct ProfState {

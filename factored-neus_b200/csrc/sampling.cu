@@ -331,6 +331,47 @@ first_hit_secant_kernel(const float* __restrict__ sdf, const float* __restrict__
     if (any_inside) any_inside[ray] = any_in ? 1 : 0;
   }
 }
+// Rays of a pinhole camera from pixel coordinates (dataset.py:115-151, gen_rays_at / gen_random_rays_at) on the device:
+//   p = Kinv[:3,:3] (px, py, 1);  v = pose[:3,:3] (p / |p|);  o = pose[:3,3];  colour / mask looked up at (py, px)
+// out [B,10] = (o, v, rgb, mask) like Dataset.gen_random_rays_at; near / far = near_far_from_sphere (dataset.py:186-192).
+// The reference assembles these rows on the CPU and uploads them every iteration.
+__global__ void gen_rays_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                const float* __restrict__ kinv, const float* __restrict__ pose,
+                                const float* __restrict__ image, const float* __restrict__ mask, int H, int W,
+                                long long B, float* __restrict__ out10, float* __restrict__ near,
+                                float* __restrict__ far) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  const float x = px[r], y = py[r];
+  float p[3], v[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    p[i] = __fadd_rn(__fadd_rn(__fmul_rn(kinv[i * 4], x), __fmul_rn(kinv[i * 4 + 1], y)), kinv[i * 4 + 2]);
+  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(p[0], p[0]), __fmul_rn(p[1], p[1])), __fmul_rn(p[2], p[2])));
+#pragma unroll
+  for (int i = 0; i < 3; i++) p[i] = __fdiv_rn(p[i], nrm);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    v[i] = __fadd_rn(__fadd_rn(__fmul_rn(pose[i * 4], p[0]), __fmul_rn(pose[i * 4 + 1], p[1])), __fmul_rn(pose[i * 4 + 2], p[2]));
+  const float o[3] = {pose[3], pose[7], pose[11]};
+  float* row = out10 + r * 10;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { row[i] = o[i]; row[3 + i] = v[i]; }
+  int ix = (int)x, iy = (int)y;
+  ix = ix < 0 ? 0 : (ix >= W ? W - 1 : ix);
+  iy = iy < 0 ? 0 : (iy >= H ? H - 1 : iy);
+  const long long pix = ((long long)iy * W + ix) * 3;
+#pragma unroll
+  for (int i = 0; i < 3; i++) row[6 + i] = image ? image[pix + i] : 0.f;
+  row[9] = mask ? mask[pix] : 1.f;
+  if (near && far) {
+    const float a = __fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2]));
+    const float b = __fmul_rn(2.0f, __fadd_rn(__fadd_rn(__fmul_rn(o[0], v[0]), __fmul_rn(o[1], v[1])), __fmul_rn(o[2], v[2])));
+    const float mid = __fdiv_rn(__fmul_rn(0.5f, -b), a);
+    near[r] = __fsub_rn(mid, 1.0f);
+    far[r] = __fadd_rn(mid, 1.0f);
+  }
+}
 // renderer.py:296-303: flat sample rows (idx - 1, idx) of the two samples bracketing the first sign change
 __global__ void hit_rows_kernel(const int* __restrict__ hit_idx, long long B, int n, long long* __restrict__ rows) {
   long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -487,6 +528,21 @@ int fneus_hit_rows(const int* hit_idx, long long B, int n, long long* rows, void
   if (B < 0 || n < 2) return FNEUS_ERR_BAD_SHAPE;
   prof_begin(PC_SAMPLING, 0.0, (double)B * 20.0, (cudaStream_t)stream);
   hit_rows_kernel<<<cdiv(B, 256), 256, 0, (cudaStream_t)stream>>>(hit_idx, B, n, rows);
+  prof_end((cudaStream_t)stream);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_gen_rays(const float* px, const float* py, const float* intrinsics_inv, const float* pose,
+                   const float* image, const float* mask, int H, int W, long long B, float* out10, float* near,
+                   float* far, void* stream) {
+  if (B == 0) return FNEUS_OK;
+  if (!px || !py || !intrinsics_inv || !pose || !out10) return FNEUS_ERR_NULL;
+  if ((near == nullptr) != (far == nullptr)) return FNEUS_ERR_NULL;
+  if (B < 0 || ((image || mask) && (H < 1 || W < 1))) return FNEUS_ERR_BAD_SHAPE;
+  prof_begin(PC_SAMPLING, 0.0, (double)B * 56.0, (cudaStream_t)stream);
+  gen_rays_kernel<<<cdiv(B, 256), 256, 0, (cudaStream_t)stream>>>(px, py, intrinsics_inv, pose, image, mask, H, W, B,
+                                                                   out10, near, far);
   prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;

@@ -879,11 +879,36 @@ inline int sdf_chain_prepare() {
   done = 1;
   return 0;
 }
+// DRAM bytes one launch of a chain moves BY DESIGN (what bench.py reports next to the ncu figure): per tile and step the
+// auxiliary blocks loaded (h, q), the image blocks stored (result, e), FP32 rows read (first operand) and written
+// (features, normals, narrow outputs), plus every weight image once (they are re-read from L2 by each tile).
+inline double sdf_chain_bytes(const SdfChainArgs& g) {
+  const double ntiles = (double)((g.M + 127) / 128);
+  double per_tile = 0.0, weights = 0.0;
+  for (int s = 0; s < g.nsteps; s++) {
+    const SdfStep& S = g.st[s];
+    const int nb = S.mode == SC_G0 ? 1 : (S.mode == SC_OUT ? (S.N + 63) >> 6 : 4);
+    const int nload = (S.N + 63) >> 6 < nb ? (S.N + 63) >> 6 : nb;
+    per_tile += (double)((S.h ? 1 : 0) + (S.q ? 1 : 0)) * nload * TC_A_BYTES;
+    per_tile += (double)((S.img_out ? 1 : 0) + (S.e_out ? 1 : 0)) * nb * TC_A_BYTES;
+    if (S.out) per_tile += 128.0 * 4.0 * (S.mode == SC_G0 ? 3 : S.N) * (S.accumulate ? 2 : 1);
+    if (S.src == SRC_MEM || S.src == SRC_GENMEM)
+      per_tile += g.ldm < 0 ? (double)((g.kmem + 63) / 64) * TC_A_BYTES : 128.0 * 4.0 * g.kmem;
+    if (S.src != SRC_CHAIN) per_tile += 128.0 * 4.0 * 12;          // raw inputs of the generated columns (<= 4 items x 3)
+    weights += (double)S.KB * (double)(((S.N + 15) & ~15) * 128);
+  }
+  if (g.pe_img) per_tile += TC_A_BYTES;
+  if (g.a0_img) per_tile += (double)(g.aux_gen_blocks > 0 ? g.aux_gen_blocks : 1 + (g.kmem + 63) / 64) * TC_A_BYTES;
+  if (g.sdf_out) per_tile += 128.0 * 4.0;
+  return ntiles * per_tile + weights;
+}
+
 inline void sdf_chain_launch(const SdfChainArgs& g, double flops, cudaStream_t st, int family = FAM_SDF_FWD) {
   const long long ntiles = (g.M + 127) / 128;
   const int sms = tc_num_sms();
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  prof_begin(PC_TC_MLP, flops, 0.0, st);
+  prof_begin(family == FAM_RELU ? PC_CHAIN_RELU : (family == FAM_SDF_BWD ? PC_CHAIN_SDF_BWD : PC_CHAIN_SDF_FWD), flops,
+             sdf_chain_bytes(g), st);
   if (family == FAM_RELU) sdf_chain_kernel<FAM_RELU><<<grid, SC_THREADS, sc_smem_bytes<FAM_RELU>(), st>>>(g);
   else if (family == FAM_SDF_BWD) sdf_chain_kernel<FAM_SDF_BWD><<<grid, SC_THREADS, sc_smem_bytes<FAM_SDF_BWD>(), st>>>(g);
   else sdf_chain_kernel<FAM_SDF_FWD><<<grid, SC_THREADS, sc_smem_bytes<FAM_SDF_FWD>(), st>>>(g);
@@ -897,7 +922,7 @@ inline void relu_chain_pair_launch(const SdfChainArgs& a, const SdfChainArgs& b,
   const long long ta = (a.M + 127) / 128, tb = (b.M + 127) / 128;
   int ca = (int)(ta < sms / 2 ? ta : sms / 2), cb = (int)(tb < sms - ca ? tb : sms - ca);
   p.ctas_a = ca;
-  prof_begin(PC_TC_MLP, flops, 0.0, st);
+  prof_begin(PC_CHAIN_RELU, flops, sdf_chain_bytes(a) + sdf_chain_bytes(b), st);
   relu_chain_pair_kernel<<<ca + cb, SC_THREADS, sc_smem_bytes<FAM_RELU>(), st>>>(p);
   prof_end(st);
 }

@@ -629,6 +629,55 @@ class Stage1Loss(torch.autograd.Function):
                 None, None, None, None, None, None, None, None)
 
 
+class Stage2Loss(torch.autograd.Function):
+    """lvis.py:163-170 in one launch: parts3 = [loss, lvis_loss, radiance_loss]; gradients flow to pre_lvis and
+    pre_trace_radiance through parts3[0]."""
+
+    @staticmethod
+    def forward(ctx, pre_lvis, pre_rad, gt_lvis, gt_rad, hit_idx, den2):
+        _need_cuda(pre_lvis, "pre_lvis")
+        pl, pr, gl, gr = _f32c(pre_lvis), _f32c(pre_rad), _f32c(gt_lvis), _f32c(gt_rad)
+        B, k = pl.shape
+        parts = torch.empty(3, dtype=torch.float32, device=pl.device)
+        dl, dr = torch.empty_like(pl), torch.empty_like(pr)
+        L.check(L.lib().fneus_stage2_loss(L.ptr(gl), L.ptr(pl), L.ptr(gr), L.ptr(pr), L.ptr(hit_idx), L.ptr(_f32c(den2)), B, k,
+                                          L.ptr(parts), L.ptr(dl), L.ptr(dr), L.stream_ptr()), "fneus_stage2_loss")
+        ctx.save_for_backward(dl, dr)
+        return parts
+
+    @staticmethod
+    def backward(ctx, g_parts):
+        dl, dr = ctx.saved_tensors
+        g = g_parts[0]
+        return dl * g, dr * g, None, None, None, None
+
+
+def stage2_loss(out, den2=None):
+    """Loss of the stage-2 Runner (lvis.py:163-170) from a ``lvis_render`` output dict: (loss, stats)."""
+    hit_idx = torch.where(out["sdf_mask"], 1, -1).to(torch.int32)
+    parts = Stage2Loss.apply(out["pre_lvis"], out["pre_trace_radiance"], out["gt_lvis"], out["gt_trace_radiance"], hit_idx,
+                             den2)
+    st = parts.detach()
+    return parts[0], dict(lvis_loss=st[1], radiance_loss=st[2])
+
+
+def gen_rays(px, py, intrinsics_inv, pose, image=None, mask=None, with_near_far=True):
+    """dataset.py:115-151 on the device: [B,10] = (rays_o, rays_v, rgb, mask) from pixel coordinates, plus near / far
+    (dataset.py:186-192).  intrinsics_inv, pose: 4x4; image, mask: [H,W,3] device tensors or None."""
+    _need_cuda(px, "pixel coordinates")
+    x, y = _f32c(px).reshape(-1), _f32c(py).reshape(-1)
+    B = x.shape[0]
+    dev = x.device
+    out = torch.empty(B, 10, dtype=torch.float32, device=dev)
+    near = torch.empty(B, 1, dtype=torch.float32, device=dev) if with_near_far else None
+    far = torch.empty(B, 1, dtype=torch.float32, device=dev) if with_near_far else None
+    H, W = (image.shape[0], image.shape[1]) if image is not None else ((mask.shape[0], mask.shape[1]) if mask is not None else (0, 0))
+    L.check(L.lib().fneus_gen_rays(L.ptr(x), L.ptr(y), L.ptr(_f32c(intrinsics_inv)), L.ptr(_f32c(pose)), L.ptr(_f32c(image)),
+                                   L.ptr(_f32c(mask)), H, W, B, L.ptr(out), L.ptr(near), L.ptr(far), L.stream_ptr()),
+            "fneus_gen_rays")
+    return out, near, far
+
+
 def adam_step(p, g, m, v, state4, base_lr, lr_alpha, warm_up_end, end_iter, beta1=0.9, beta2=0.999, eps=1e-8,
               grad_scale=1.0, zero_grad=True):
     """Fused flat Adam with the on-device warm-up/cosine schedule (exp_runner.py:118,229-238); in place."""

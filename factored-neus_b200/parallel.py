@@ -59,6 +59,96 @@ def stage1_loss_sharded(renderer, out, true_rgb, mask, surface_weight=0.1, igr_w
     return loss, dict(color_loss=color_loss, surface_loss=surf_loss, eikonal=eik_loss, mask_loss=mask_loss)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Tile-sharded inference (BASELINE.json configs[4]): full-image rendering (exp_runner.py:374-426 renders an
+# image as a Python loop over 512-ray chunks) and the marching-cubes grid query (renderer.py:14-29: 64^3 chunks) have no
+# cross-ray / cross-voxel dependency: tiles go round-robin to the ranks, x-slabs of the grid in contiguous blocks, and one
+# gather brings the results to rank 0.  No other collective.
+# ---------------------------------------------------------------------------------------------------------------------
+def shard_tiles(n_tiles: int, rank: int, world: int):
+    """Tile indices owned by ``rank``: round-robin (neighbouring tiles of an image cost about the same, so every rank gets
+    the same mix of empty and surface tiles)."""
+    return list(range(rank, n_tiles, world))
+
+
+def gather_tiles(local, n_items: int, tile: int, rank: int, world: int, group=None, dst: int = 0):
+    """local [n_local_tiles * tile, C] (this rank's tiles in ``shard_tiles`` order, the last global tile possibly partial
+    but padded to ``tile`` rows) -> on ``dst`` the full [n_items, C] tensor in item order, elsewhere None."""
+    n_tiles = (n_items + tile - 1) // tile
+    if world == 1:
+        return local[:n_items]
+    per = (n_tiles + world - 1) // world                  # equal-sized messages: pad ranks that own one tile fewer
+    C = local.shape[1]
+    buf = local.new_zeros(per * tile, C)
+    buf[: local.shape[0]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    full = local.new_empty(n_tiles * tile, C)
+    view = full.view(n_tiles, tile, C)
+    for r in range(world):
+        idx = shard_tiles(n_tiles, r, world)
+        view[idx] = parts[r].view(per, tile, C)[: len(idx)]
+    return full[:n_items]
+
+
+def render_image_sharded(renderer, rays_o, rays_d, near=None, far=None, tile=4096, group=None,
+                         keys=("color_fine", "normals")):
+    """Full-image render (exp_runner.py:374-426 ``validate_image``): every rank renders its round-robin tiles of the ray
+    list, rank 0 receives [N, 3] per key.  ``normals`` = sum_samples gradients * weights[:, :n] * inside_sphere as the
+    reference accumulates them (exp_runner.py:418-424).  rays are [N,3] on this rank's device; N need not divide."""
+    from . import ops
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    N = rays_o.shape[0]
+    n_tiles = (N + tile - 1) // tile
+    outs = {k: [] for k in keys}
+    with torch.no_grad():
+        for t in shard_tiles(n_tiles, rank, world):
+            lo, hi = t * tile, min(N, (t + 1) * tile)
+            o, d = rays_o[lo:hi].contiguous(), rays_d[lo:hi].contiguous()
+            if near is None:
+                nr, fr = ops.near_far_from_sphere(o, d)
+            else:
+                nr, fr = near[lo:hi], far[lo:hi]
+            out = renderer.render(o, d, nr, fr, perturb_overwrite=0, cos_anneal_ratio=1.0)
+            n = renderer.n_samples + renderer.n_importance
+            for k in keys:
+                if k == "normals":
+                    v = (out["gradients"] * (out["weights"][:, :n] * out["inside_sphere"])[:, :, None]).sum(dim=1)
+                else:
+                    v = out[k]
+                if hi - lo < tile:
+                    v = torch.cat([v, v.new_zeros(tile - (hi - lo), v.shape[1])])
+                outs[k].append(v)
+    res = {}
+    for k in keys:
+        local = torch.cat(outs[k]) if outs[k] else rays_o.new_zeros(0, 3)
+        res[k] = gather_tiles(local, N, tile, rank, world, group)
+    return res
+
+
+def extract_fields_sharded(renderer, bound_min, bound_max, resolution, group=None, dst: int = 0):
+    """renderer.py:14-29 over all ranks: rank r evaluates the x-slab [r R / world, (r+1) R / world) of the R^3 grid on its
+    GPU; rank ``dst`` receives the whole u [R,R,R] (device tensor), the others None."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_rays(resolution, rank, world)
+    slab = renderer.extract_fields(bound_min, bound_max, resolution, ix0=lo, ix1=hi)
+    if world == 1:
+        return slab
+    per = (resolution + world - 1) // world
+    buf = slab.new_zeros(per, resolution, resolution)
+    buf[: hi - lo] = slab
+    parts = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([parts[r][: shard_rays(resolution, r, world)[1] - shard_rays(resolution, r, world)[0]]
+                      for r in range(world)])
+
+
 class GradBucket:
     """Single flat FP32 gradient bucket over a fixed parameter list; one all-reduce(sum) per step.
 

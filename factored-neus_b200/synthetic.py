@@ -189,3 +189,26 @@ def make_rays(B, seed=1, dtype=torch.float32):
 def make_targets(B, seed=2, dtype=torch.float32):
     rs = np.random.RandomState(seed)
     return _t(rs.uniform(0, 1, (B, 3)), dtype), torch.ones(B, 1, dtype=dtype)
+
+
+def pinhole_camera(H=1200, W=1600, focal=2900.0, distance=2.5, dtype=torch.float32):
+    """Synthetic DTU-like camera: principal point at the image centre, pose at ``distance`` on the +z
+    axis looking at the origin.  Returns (intrinsics_inv [4,4], pose [4,4]) in the layout of Dataset.intrinsics_all_inv /
+    pose_all (dataset.py:60-100)."""
+    K = np.eye(4)
+    K[0, 0] = K[1, 1] = focal
+    K[0, 2], K[1, 2] = (W - 1) * 0.5, (H - 1) * 0.5
+    pose = np.eye(4)
+    pose[:3, :3] = np.diag([1.0, -1.0, -1.0])          # camera looks down -z of the world, y flipped (image rows go down)
+    pose[:3, 3] = [0.0, 0.0, distance]
+    return _t(np.linalg.inv(K), dtype), _t(pose, dtype)
+
+
+def image_pixels(H, W, resolution_level=1, device="cpu"):
+    """Pixel coordinates of Dataset.gen_rays_at (dataset.py:115-131) in its OUTPUT order ([H//l, W//l] row-major):
+    px, py [H//l * W//l]."""
+    l = resolution_level
+    tx = torch.linspace(0, W - 1, W // l, device=device)
+    ty = torch.linspace(0, H - 1, H // l, device=device)
+    py, px = torch.meshgrid(ty, tx, indexing="ij")
+    return px.reshape(-1).contiguous(), py.reshape(-1).contiguous()

@@ -269,6 +269,14 @@ int fneus_composite_bwd(const float* sdf, const float* normals, const float* rgb
                         const float* d_eik, const float* eik_denom, float* d_sdf, float* d_normals,
                         float* d_rgb, float* d_inv_s, float* d_bg_alpha, float* d_bg_color, void* stream);
 
+/* Rays of a pinhole camera from pixel coordinates, on the device (dataset.py:115-151: gen_rays_at and
+ * gen_random_rays_at assemble them on the CPU and upload every iteration).  px, py [B] pixel coordinates (float);
+ * intrinsics_inv, pose: 4x4 row-major; image, mask: [H,W,3] or NULL.  out10 [B,10] = (rays_o, rays_v, rgb, mask[...,0]);
+ * near / far [B] = near_far_from_sphere (dataset.py:186-192), both or neither NULL. */
+int fneus_gen_rays(const float* px, const float* py, const float* intrinsics_inv, const float* pose,
+                   const float* image, const float* mask, int H, int W, long long n_rays, float* out10, float* near,
+                   float* far, void* stream);
+
 /* ---- per-ray tail of the training step ----------------------------------------------------------------------------
  * Surface-colour blend of the two bracketing RefColor evaluations per ray (renderer.py:328-343): c_* are [2B,3]
  * (rows 2b, 2b+1), w_pair [B,2], hit_idx [B] (< 0: no sign change -> ones).  Backward: g_* may be NULL (no gradient). */
@@ -299,6 +307,15 @@ int fneus_near_far(const float* rays_o, const float* rays_d, long long n_rays, f
 int fneus_coarse_z(const float* near, const float* far, const float* lin, const float* rnd, long long n_rays, int n,
                    float inv_n_samples, float* z, void* stream);
 int fneus_hit_rows(const int* hit_idx, long long n_rays, int n, long long* rows, void* stream);
+
+/* Stage-2 loss (lvis.py:163-170): parts3 = [loss, lvis_loss, radiance_loss] with
+ *   lvis_loss = sum |gt_lvis - pre_lvis| / (k n_hit + 1e-6)   (not masked: rows without a hit are ones on both sides)
+ *   radiance_loss = sum |(gt_rad - pre_rad) hit| / (3 k n_hit + 1e-6)
+ * gt_lvis, pre_lvis [B,k]; gt_rad, pre_rad [B,k,3]; hit_idx [B] int32 (< 0: no hit); den2 (device, optional) = the two
+ * denominators over the whole batch when rays are sharded; d_pre_lvis / d_pre_rad = d loss / d prediction (NULL ok). */
+int fneus_stage2_loss(const float* gt_lvis, const float* pre_lvis, const float* gt_rad, const float* pre_rad,
+                      const int* hit_idx, const float* den2, long long n_rays, int k, float* parts3,
+                      float* d_pre_lvis, float* d_pre_rad, void* stream);
 
 /* Optimiser of the stage-1 step (exp_runner.py:118 torch.optim.Adam, :229-238 update_learning_rate): one fused Adam
  * update over flat FP32 buffers p/g/m/v [n] (16-byte aligned).  state4 (device) = [iterations done, lr of the last

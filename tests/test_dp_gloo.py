@@ -107,3 +107,47 @@ def test_shard_rays_cover_batch():
         spans = [shard_rays(n, r, w) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+# ------------------------------------------------------------------------------------------ tile-sharded inference (host logic)
+def _tile_worker(rank, world, port, N, tile, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from factored_neus_b200.parallel import gather_tiles, shard_tiles
+    n_tiles = (N + tile - 1) // tile
+    mine = shard_tiles(n_tiles, rank, world)
+    rows = []
+    for t in mine:                                   # "render" of tile t: item index in column 0, 2 * index in column 1
+        idx = torch.arange(t * tile, (t + 1) * tile, dtype=torch.float32)
+        v = torch.stack([idx, 2 * idx], dim=1)
+        v[idx >= N] = 0.0
+        rows.append(v)
+    local = torch.cat(rows) if rows else torch.zeros(0, 2)
+    full = gather_tiles(local, N, tile, rank, world)
+    if rank == 0:
+        torch.save(full, tmp)
+    else:
+        assert full is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N,tile,world", [(130, 64, 3), (5, 8, 2)])
+def test_gather_tiles_restores_item_order(tmp_path, N, tile, world):
+    """Round-robin tile ownership + one gather == the unsharded result, incl. a partial last tile, ranks with one tile
+    fewer than others, and ranks with no tile at all."""
+    tmp = str(tmp_path / "tiles.pt")
+    mp.spawn(_tile_worker, args=(world, _free_port(), N, tile, tmp), nprocs=world, join=True)
+    full = torch.load(tmp)
+    idx = torch.arange(N, dtype=torch.float32)
+    assert full.shape == (N, 2)
+    assert torch.equal(full[:, 0], idx) and torch.equal(full[:, 1], 2 * idx)
+
+
+def test_shard_tiles_partition():
+    from factored_neus_b200.parallel import shard_tiles
+    for n, w in ((469, 8), (3, 8), (0, 2), (16, 4)):
+        owned = sorted(t for r in range(w) for t in shard_tiles(n, r, w))
+        assert owned == list(range(n))
+        sizes = [len(shard_tiles(n, r, w)) for r in range(w)]
+        assert max(sizes) - min(sizes) <= 1
