@@ -86,6 +86,11 @@ _SIGNATURES = {
     "fneus_loss_norms": (c_int, [_P, _P, _P, _LL, c_int, _P, _P]),
     "fneus_stage1_loss": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, c_int, c_float, c_float, c_float, _P, _P, _P,
                                   _P, _P, _P]),
+    "fneus_lvis_trace_workspace_floats": (_LL, [POINTER(SdfCfg), POINTER(ColorCfg), _LL, c_int, c_int]),
+    "fneus_lvis_trace": (c_int, [POINTER(SdfCfg), _P, POINTER(ColorCfg), _P, _P, _P, _LL, c_int, c_int, c_int, _P, _P, _P,
+                                 _P, _P, _P, _P, _LL, _LL, _P]),
+    "fneus_mc_classify": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
+    "fneus_mc_emit": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fneus_stage2_loss": (c_int, [_P, _P, _P, _P, _P, _P, _LL, c_int, _P, _P, _P, _P]),
     "fneus_gen_rays": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _LL, _P, _P, _P, _P]),
     "fneus_near_far": (c_int, [_P, _P, _LL, _P, _P, _P]),

@@ -296,10 +296,14 @@ __device__ __forceinline__ void epilogue_chunk(const Epi& e, float* wbuf, const 
   __syncwarp();
 }
 
+// The weight-gradient kernel runs ONE CTA per SM with a 4-deep ring: per stage the chain is bulk load (~2 us under load) ->
+// format conversion (mixed FP16 / BF16 operands) -> 4 MMAs, and with only two stages per CTA that latency chain, not
+// HBM, set the pace (measured +33% when the conversion joined it).
+constexpr int WG_STAGES = 4;
 struct TcSmem {
-  uint64_t full[TC_STAGES];
-  uint64_t empty[TC_STAGES];
-  uint64_t conv[TC_STAGES];           // weight-gradient kernel: stage converted to a common operand format
+  uint64_t full[WG_STAGES];
+  uint64_t empty[WG_STAGES];
+  uint64_t conv[WG_STAGES];           // weight-gradient kernel: stage converted to a common operand format
   uint64_t accum;
   uint32_t tmem_base;
 };
@@ -506,14 +510,14 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared
                                                  // address space (an integer round trip turned every access into a generic LD.E / ST.E)
-  uint8_t* sA[TC_STAGES];
-  uint8_t* sB[TC_STAGES];
+  uint8_t* sA[WG_STAGES];
+  uint8_t* sB[WG_STAGES];
 #pragma unroll
-  for (int s = 0; s < TC_STAGES; s++) {
+  for (int s = 0; s < WG_STAGES; s++) {
     sA[s] = base + s * (TC_A_BYTES + TC_B_BYTES);
     sB[s] = sA[s] + TC_A_BYTES;
   }
-  TcSmem* ctl = reinterpret_cast<TcSmem*>(base + TC_STAGES * (TC_A_BYTES + TC_B_BYTES));
+  TcSmem* ctl = reinterpret_cast<TcSmem*>(base + WG_STAGES * (TC_A_BYTES + TC_B_BYTES));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int kc_gen = (a.gen.ncols + 255) / 256, kc_mem = (a.kmem + 255) / 256;
@@ -545,7 +549,7 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
   if (tid == 0) {
     const int cnt = (need_prod ? 128 : 0) + ((y_img || x_img) ? 1 : 0);
 #pragma unroll
-    for (int s = 0; s < TC_STAGES; s++) {
+    for (int s = 0; s < WG_STAGES; s++) {
       mbar_init(&ctl->full[s], cnt); mbar_init(&ctl->empty[s], bias_smem ? 129 : 1); mbar_init(&ctl->conv[s], 128);
     }
     mbar_init(&ctl->accum, 1);
@@ -561,8 +565,8 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
     if (lane == 0 && (y_img || x_img)) {
       const int ykbs = -ldy, xkbs = -a.ldm;
       for (int kb = 0; kb < KB; kb++) {
-        const int s = kb % TC_STAGES;
-        if (kb >= TC_STAGES) mbar_wait(&ctl->empty[s], ((kb / TC_STAGES) - 1) & 1);
+        const int s = kb % WG_STAGES;
+        if (kb >= WG_STAGES) mbar_wait(&ctl->empty[s], ((kb / WG_STAGES) - 1) & 1);
         const long long mblk = (mbeg >> 6) + kb;               // 64-row block index
         const size_t half = (size_t)(mblk & 1) * 8192;
         mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)(yblocks + xblocks) * 8192u);
@@ -580,8 +584,8 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
     const int bn = (tid & 31) << 2;            // this thread always loads dY columns n0+bn..+3
     if (need_prod) {
       for (int kb = 0; kb < KB; kb++) {
-        const int s = kb % TC_STAGES;
-        if (kb >= TC_STAGES) mbar_wait(&ctl->empty[s], ((kb / TC_STAGES) - 1) & 1);
+        const int s = kb % WG_STAGES;
+        if (kb >= WG_STAGES) mbar_wait(&ctl->empty[s], ((kb / WG_STAGES) - 1) & 1);
         const long long mb = mbeg + (long long)kb * TC_BK;
         if (!y_img) {
           // A operand (dY^T), MN-major: 64 m-rows x 128 n
@@ -642,7 +646,7 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
         fence_proxy_async();
         mbar_arrive(&ctl->full[s]);
         if (any_conv || bias_smem) {
-          mbar_wait(&ctl->full[s], (kb / TC_STAGES) & 1);
+          mbar_wait(&ctl->full[s], (kb / WG_STAGES) & 1);
           if (any_conv) {
             wgrad_to_bf16(conv_y ? sA[s] : sB[s], (conv_y ? yblocks : xblocks) * 8192, tid);
             fence_proxy_async();
@@ -656,8 +660,8 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
       }
     } else if (any_conv || bias_smem) {
       for (int kb = 0; kb < KB; kb++) {
-        const int s = kb % TC_STAGES;
-        mbar_wait(&ctl->full[s], (kb / TC_STAGES) & 1);
+        const int s = kb % WG_STAGES;
+        mbar_wait(&ctl->full[s], (kb / WG_STAGES) & 1);
         if (any_conv) {
           wgrad_to_bf16(conv_y ? sA[s] : sB[s], (conv_y ? yblocks : xblocks) * 8192, tid);
           fence_proxy_async();
@@ -702,8 +706,8 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
   } else if (warp == 4 && lane == 0) {
     const uint32_t idesc = make_idesc(Nc, 1, 1, yf && !conv_y, xf && !conv_x);
     for (int kb = 0; kb < KB; kb++) {
-      const int s = kb % TC_STAGES;
-      mbar_wait(any_conv ? &ctl->conv[s] : &ctl->full[s], (kb / TC_STAGES) & 1);
+      const int s = kb % WG_STAGES;
+      mbar_wait(any_conv ? &ctl->conv[s] : &ctl->full[s], (kb / WG_STAGES) & 1);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(sA[s]), b_addr = smem_u32(sB[s]);
 #pragma unroll
@@ -724,7 +728,7 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, const __grid_constant__ ASeg a, float* __restrict__ dW,
                      int ldw, int wout0, float* __restrict__ db, int M, int N, int m_per_split) {
   wgrad_body(dY, ldy, a, dW, ldw, wout0, db, M, N, m_per_split, blockIdx.x, blockIdx.y);
@@ -742,7 +746,7 @@ struct WgradJob {
   int y_f16, x_f16;                  // element format of the image operands (0 = BF16, 1 = FP16)
 };
 struct WgradJobs { int n; int M; WgradJob job[WG_MAX_JOBS]; };
-__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_wgrad_group_kernel(const __grid_constant__ WgradJobs jobs) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_wgrad_group_kernel(const __grid_constant__ WgradJobs jobs) {
   const WgradJob& j = jobs.job[blockIdx.z];
   if ((int)blockIdx.x >= j.tiles || (int)blockIdx.y >= j.splits) return;
   wgrad_body(j.dY, j.ldy, j.a, j.dW, j.ldw, j.wout0, j.db, jobs.M, j.N, j.m_per_split, blockIdx.x, blockIdx.y, j.y_f16 != 0,
@@ -1220,8 +1224,9 @@ __global__ void pack_wimg_multi_kernel(PackJobs jobs) {
 }
 
 constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 + 256;
+constexpr int WG_SMEM_BYTES = WG_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 + 256;
 
-inline int& tc_wgrad_ctas_per_sm() { static int v = 2; return v; }
+inline int& tc_wgrad_ctas_per_sm() { static int v = 1; return v; }
 inline int tc_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -1237,9 +1242,9 @@ inline int tc_prepare() {
   if (done) return 0;
   cudaError_t e1 = cudaFuncSetAttribute(tc_gemm_mk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaError_t e2 = cudaFuncSetAttribute(tc_gemm_mk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  cudaError_t e3 = cudaFuncSetAttribute(tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  cudaError_t e3 = cudaFuncSetAttribute(tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
   if (e3 == cudaSuccess)
-    e3 = cudaFuncSetAttribute(tc_gemm_wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    e3 = cudaFuncSetAttribute(tc_gemm_wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
   cudaError_t e4 = cudaFuncSetAttribute(tc_gemm_mk_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
   cudaError_t e5 = cudaFuncSetAttribute(tc_gemm_mk_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) return 1;
@@ -1284,7 +1289,7 @@ inline void launch_tc_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, 
   splits = cdiv(M, mps);
   dim3 grid(tiles, splits);
   prof_begin(PC_TC_MLP, 2.0 * (double)M * N * (a.gen.ncols + a.kmem), 0.0, st);
-  tc_gemm_wgrad_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(dY, ldy, a, dW, ldw, wout0, db, (int)M, N, mps);
+  tc_gemm_wgrad_kernel<<<grid, TC_THREADS, WG_SMEM_BYTES, st>>>(dY, ldy, a, dW, ldw, wout0, db, (int)M, N, mps);
   prof_end(st);
 }
 
@@ -1319,7 +1324,9 @@ struct WgradGroup {
       total_tiles += jobs.job[i].tiles;
       if (jobs.job[i].tiles > max_tiles) max_tiles = jobs.job[i].tiles;
     }
-    int splits = (tc_wgrad_group_waves() * tc_wgrad_ctas_per_sm() * num_sms + total_tiles - 1) / total_tiles;
+    // whole waves: never more CTAs than `waves` rounds of the machine hold (a few CTAs spilling into an extra round cost a
+    // full round of latency)
+    int splits = (tc_wgrad_group_waves() * tc_wgrad_ctas_per_sm() * num_sms) / total_tiles;
     const int max_s = cdiv(M, 4 * TC_BK);
     if (splits > max_s) splits = max_s;
     if (splits < 1) splits = 1;
@@ -1327,7 +1334,7 @@ struct WgradGroup {
     splits = cdiv(M, mps);
     for (int i = 0; i < jobs.n; i++) { jobs.job[i].m_per_split = mps; jobs.job[i].splits = splits; }
     prof_begin(PC_TC_WGRAD, flops, bytes, st);
-    tc_gemm_wgrad_group_kernel<<<dim3(max_tiles, splits, jobs.n), TC_THREADS, TC_SMEM_BYTES, st>>>(jobs);
+    tc_gemm_wgrad_group_kernel<<<dim3(max_tiles, splits, jobs.n), TC_THREADS, WG_SMEM_BYTES, st>>>(jobs);
     prof_end(st);
     reset(M, num_sms);
   }

@@ -75,8 +75,8 @@ __device__ __forceinline__ void invert_cdf_warp(const float* sz, const float* sc
 
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
 upsample_step_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                     const float* __restrict__ z, const float* __restrict__ sdf, long long B, int n, int k,
-                     float inv_s_host, const float* __restrict__ inv_s_dev, const float* __restrict__ u_table,
+                     const float* __restrict__ z, long long z_stride, const float* __restrict__ sdf, long long B, int n,
+                     int k, float inv_s_host, const float* __restrict__ inv_s_dev, const float* __restrict__ u_table,
                      float* __restrict__ new_z, float* __restrict__ cdf_out, long long* __restrict__ inds_out) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -87,7 +87,7 @@ upsample_step_kernel(const float* __restrict__ rays_o, const float* __restrict__
   float* sf = sz + n;
   float* sc = sf + n;   // alpha, then cdf
   for (int j = lane; j < n; j += 32) {
-    sz[j] = __ldg(z + ray * n + j);
+    sz[j] = __ldg(z + ray * z_stride + j);             // z_stride 0: one depth table shared by all rays (stage 2)
     sf[j] = __ldg(sdf + ray * n + j);
   }
   __syncwarp();
@@ -234,6 +234,31 @@ __global__ void ray_points_kernel(const float* __restrict__ o, const float* __re
   float t = z[idx];
 #pragma unroll
   for (int c = 0; c < 3; c++) pts[idx * 3 + c] = __fadd_rn(o[b * 3 + c], __fmul_rn(d[b * 3 + c], t));
+}
+
+// stage 2: points of R = m k secondary rays on ONE shared depth table, origins = surface points repeated k times
+// (calLvis.py:357-366); also writes the expanded origins [R,3] once (first depth) for the later per-ray kernels
+__global__ void lvis_coarse_points_kernel(const float* __restrict__ surf, int k, const float* __restrict__ d,
+                                          const float* __restrict__ z_table, long long total, int n,
+                                          float* __restrict__ pts, float* __restrict__ o_out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long r = idx / n;
+  const int i = (int)(idx - r * n);
+  const float t = __ldg(z_table + i);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float oc = __ldg(surf + (r / k) * 3 + c);
+    pts[idx * 3 + c] = __fadd_rn(oc, __fmul_rn(__ldg(d + r * 3 + c), t));
+    if (i == 0) o_out[r * 3 + c] = oc;
+  }
+}
+// rgb_out = hit ? rgb : 0   (calLvis.py:200-203: rays without a first hit keep the zero radiance)
+__global__ void mask_rows3_kernel(const float* __restrict__ rgb, const int* __restrict__ hit, long long R,
+                                  float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * 3) return;
+  out[idx] = hit[idx / 3] >= 0 ? rgb[idx] : 0.f;
 }
 
 __global__ void core_geometry_kernel(const float* __restrict__ o, const float* __restrict__ d,
@@ -417,9 +442,12 @@ int fneus_first_hit_secant(const float* sdf, const float* mid_z, const float* pt
   return FNEUS_OK;
 }
 
-static int upsample_step_launch(const float* rays_o, const float* rays_d, const float* z, const float* sdf, long long B,
-                                int n, int k, float inv_s, const float* inv_s_dev, const float* u_table, float* new_z,
-                                float* cdf_out, long long* inds_out, void* stream) {
+}  // extern "C"
+
+namespace fneus {
+int upsample_step_launch(const float* rays_o, const float* rays_d, const float* z, const float* sdf, long long B,
+                         int n, int k, float inv_s, const float* inv_s_dev, const float* u_table, float* new_z,
+                         float* cdf_out, long long* inds_out, void* stream, int z_shared = 0) {
   if (B == 0 || k == 0) return FNEUS_OK;
   if (!rays_o || !rays_d || !z || !sdf || !u_table || !new_z) return FNEUS_ERR_NULL;
   if (B < 0 || n < 2 || k < 0 || n > 4096) return FNEUS_ERR_BAD_SHAPE;
@@ -430,11 +458,15 @@ static int upsample_step_launch(const float* rays_o, const float* rays_d, const 
   }
   prof_begin(PC_SAMPLING, 0.0, (double)B * (n * 8.0 + k * 4.0 + 24.0), (cudaStream_t)stream);
   upsample_step_kernel<<<cdiv(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      rays_o, rays_d, z, sdf, B, n, k, inv_s, inv_s_dev, u_table, new_z, cdf_out, inds_out);
+      rays_o, rays_d, z, z_shared ? 0 : (long long)n, sdf, B, n, k, inv_s, inv_s_dev, u_table, new_z, cdf_out, inds_out);
   prof_end((cudaStream_t)stream);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;
 }
+}  // namespace fneus
+
+extern "C" {
+
 int fneus_upsample_step(const float* rays_o, const float* rays_d, const float* z, const float* sdf, long long B,
                         int n, int k, float inv_s, const float* u_table, float* new_z, float* cdf_out,
                         long long* inds_out, void* stream) {

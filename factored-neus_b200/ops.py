@@ -450,6 +450,37 @@ def first_hit_secant(sdf, mid_z, pts, rays_o, rays_d, weights=None):
     return hit, zs, ps, lv, anyin != 0
 
 
+_LVIS_WS = {}
+
+
+def lvis_trace(sdf_cfg, sdf_w, color_cfg, color_w, surf, dirs, inv_s, z_table, u_table, rays_per_chunk=8192):
+    """calLvis.py:351-397 (ground truth of cal_indiLgt) in ONE library call: surf [m,3], dirs [m,k,3] ->
+    (gt_lvis [m,k], gt_trace_radiance [m,k,3], hit [m,k] int32).  The workspace is cached per (device, shape)."""
+    _need_cuda(surf, "surf")
+    s, d = _f32c(surf), _f32c(dirs)
+    m, k = d.shape[0], d.shape[1]
+    n_coarse, n_imp = z_table.numel(), u_table.numel()
+    dev = s.device
+    lib = L.lib()
+    chunk = max(k, min(rays_per_chunk, m * k) // k * k)
+    need = lib.fneus_lvis_trace_workspace_floats(sdf_cfg, color_cfg, chunk, n_coarse, n_imp)
+    if need < 0:
+        raise RuntimeError("fneus_lvis_trace: unsupported configuration")
+    key = (str(dev), chunk, n_coarse, n_imp, get_precision())
+    ws = _LVIS_WS.get(key)
+    if ws is None or ws.numel() < need:
+        _LVIS_WS.clear()
+        ws = _LVIS_WS[key] = torch.empty(int(need), dtype=torch.float32, device=dev)
+    lvis = torch.empty(m, k, dtype=torch.float32, device=dev)
+    rgb = torch.empty(m, k, 3, dtype=torch.float32, device=dev)
+    hit = torch.empty(m, k, dtype=torch.int32, device=dev)
+    L.check(lib.fneus_lvis_trace(sdf_cfg, L.ptr(_f32c(sdf_w)), color_cfg, L.ptr(_f32c(color_w)), L.ptr(s), L.ptr(d.reshape(-1, 3)),
+                                 m, k, n_coarse, n_imp, L.ptr(_f32c(inv_s).reshape(-1)[:1].contiguous()), L.ptr(z_table),
+                                 L.ptr(u_table), L.ptr(lvis), L.ptr(rgb), L.ptr(hit), L.ptr(ws), ws.numel(), chunk,
+                                 L.stream_ptr()), "fneus_lvis_trace")
+    return lvis, rgb, hit
+
+
 def inverse_cdf(bins, cdf, u_table):
     B, n = bins.shape
     k = u_table.numel()

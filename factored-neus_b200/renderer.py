@@ -269,19 +269,16 @@ class NeuSRenderer:
             return ops.sdf_grid(net.cfg, net.flat_weights().detach(), axes[0], axes[1], axes[2], ix0, ix1)
 
     def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0):
-        """renderer.py:32-40,729-734.  The SDF grid is evaluated on the GPU; marching cubes is the reference's
-        third-party CPU dependency (PyMCubes) and is used as-is when installed."""
-        u = self.extract_fields(bound_min, bound_max, resolution).cpu().numpy()
-        try:
-            import mcubes
-        except ImportError as e:
-            raise RuntimeError("extract_geometry: PyMCubes (mcubes) is not installed; use extract_fields() for the "
-                               "SDF grid") from e
-        vertices, triangles = mcubes.marching_cubes(u, threshold)
-        b_max = bound_max.detach().cpu().numpy()
-        b_min = bound_min.detach().cpu().numpy()
+        """renderer.py:32-40,729-734: SDF grid AND marching cubes on the GPU (the reference copies the 512^3 grid to the
+        host and runs PyMCubes there); only the mesh comes back.  Returns (vertices [V,3] float, triangles [T,3] int) as
+        numpy arrays like the reference, vertices rescaled to world coordinates with the reference's expression."""
+        from .mcubes import marching_cubes
+        u = self.extract_fields(bound_min, bound_max, resolution)
+        vertices, triangles = marching_cubes(u, threshold)
+        b_max = torch.as_tensor(bound_max).detach().to(vertices.device, torch.float32)
+        b_min = torch.as_tensor(bound_min).detach().to(vertices.device, torch.float32)
         vertices = vertices / (resolution - 1.0) * (b_max - b_min)[None, :] + b_min[None, :]
-        return vertices, triangles
+        return vertices.cpu().numpy(), triangles.cpu().numpy()
 
     def render_core_outside(self, rays_o, rays_d, z_vals, sample_dist, nerf, background_rgb=None):
         """renderer.py:112-149."""

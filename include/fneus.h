@@ -277,6 +277,38 @@ int fneus_gen_rays(const float* px, const float* py, const float* intrinsics_inv
                    const float* image, const float* mask, int H, int W, long long n_rays, float* out10, float* near,
                    float* far, void* stream);
 
+/* ---- stage-2 light visibility (calLvis.py:339-397: the ground-truth half of cal_indiLgt) as ONE call ----------------------
+ * surf [m,3] surface points, dirs [m*n_dirs,3] secondary-ray directions (sample_dirs, calLvis.py:302-320; ray r starts
+ * at surf[r / n_dirs]).  Per ray: n_coarse sdf evaluations on the shared depth table z_table [n_coarse]
+ * (torch.linspace(0,1,n_coarse) of the device under test), n_imp importance depths by the inverse CDF at inv_s (DEVICE
+ * scalar: the learned, clipped inv_s; u_table [n_imp] = linspace(0.5/n_imp, 1-0.5/n_imp, n_imp)), then on those n_imp
+ * sections only (the reference discards the coarse ones): lvis_out [m*n_dirs] = 1 - sum_i w_i [|p_i| < 1]
+ * (compute_weight, cos_anneal_ratio 0), hit_out [m*n_dirs] int32 = index of the first sign change (-1: none),
+ * rgb_out [m*n_dirs,3] = colour network at the secant root of the hit (0 without a hit).
+ * The rays are processed in chunks of rays_per_chunk (rounded down to whole surface points); ws must hold
+ * fneus_lvis_trace_workspace_floats(.., rays_per_chunk, ..) floats (16-byte aligned).  No host synchronisation, no
+ * allocation: CUDA-graph capturable.  Uses the precision mode in force (fneus_set_precision). */
+long long fneus_lvis_trace_workspace_floats(const fneus_sdf_cfg* sdf_cfg, const fneus_color_cfg* color_cfg,
+                                            long long rays_per_chunk, int n_coarse, int n_imp);
+int fneus_lvis_trace(const fneus_sdf_cfg* sdf_cfg, const float* sdf_wpack, const fneus_color_cfg* color_cfg,
+                     const float* color_wpack, const float* surf, const float* dirs, long long m, int n_dirs,
+                     int n_coarse, int n_imp, const float* inv_s, const float* z_table, const float* u_table,
+                     float* lvis_out, float* rgb_out, int* hit_out, float* ws, long long ws_floats,
+                     long long rays_per_chunk, void* stream);
+
+/* ---- marching cubes on the device (renderer.py:32-40 hands the grid to PyMCubes on the CPU) -------------------------------
+ * u [nx,ny,nz] (row-major, as extract_fields writes it); inside: u > isovalue.  Each grid point owns its +x/+y/+z edges.
+ * fneus_mc_classify: vmask [npts] (bit a: the owned edge along axis a is crossed), vcount [npts] = popcount(vmask),
+ * tcount [(nx-1)(ny-1)(nz-1)] = triangles of the cell's case (tri_count [256]).  The caller prefix-sums vcount / tcount
+ * (inclusive, int64) and calls fneus_mc_emit: verts [V,3] in grid-index coordinates (linear interpolation on the edge, like
+ * mcubes.marching_cubes), tris [T,3] int64 indices into verts (shared vertices); tri_edges [256, 3 * max_tris] lists the
+ * cube edges of each case's triangles (-1 padded).  The case table is derived in factored-neus_b200/mcubes.py. */
+int fneus_mc_classify(const float* u, int nx, int ny, int nz, float isovalue, const int* tri_count,
+                      unsigned char* vmask, int* vcount, int* tcount, void* stream);
+int fneus_mc_emit(const float* u, int nx, int ny, int nz, float isovalue, const int* tri_count, const int* tri_edges,
+                  int max_tris, const unsigned char* vmask, const int* vcount, const long long* voff_incl,
+                  const int* tcount, const long long* toff_incl, float* verts, long long* tris, void* stream);
+
 /* ---- per-ray tail of the training step ----------------------------------------------------------------------------
  * Surface-colour blend of the two bracketing RefColor evaluations per ray (renderer.py:328-343): c_* are [2B,3]
  * (rows 2b, 2b+1), w_pair [B,2], hit_idx [B] (< 0: no sign change -> ones).  Backward: g_* may be NULL (no gradient). */

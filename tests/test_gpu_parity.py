@@ -660,3 +660,70 @@ def test_render_512_rays_fwd_bwd_vs_oracle(states):
     _stage1(outd, true_rgb.to(DEV), mask.to(DEV), 0.1).backward()
     worst = compare_param_grads(m, P, ["sdf", "color", "var", "ref"], FP32_TOL, 1e-3, "512 rays")
     print("512-ray step: worst param-grad abs err %.3e" % worst)
+
+
+# ------------------------------------------------------------------------------------------ section 8f: rays on device, stage-2 loss
+def test_gen_rays_matches_dataset_formulas():
+    """fneus_gen_rays against the reference expressions of Dataset.gen_random_rays_at / gen_rays_at / near_far_from_sphere
+    (dataset.py:115-151,186-192) restated in torch."""
+    H, W, B = 48, 64, 333
+    g = torch.Generator().manual_seed(4)
+    kinv, pose = syn.pinhole_camera(H, W, focal=90.0)
+    rot = torch.linalg.qr(torch.randn(3, 3, generator=g))[0]
+    pose[:3, :3] = rot
+    pose[:3, 3] = torch.tensor([0.3, -0.2, 2.4])
+    image, mask = torch.rand(H, W, 3, generator=g), (torch.rand(H, W, 3, generator=g) > 0.4).float()
+    px = torch.randint(0, W, (B,), generator=g)
+    py = torch.randint(0, H, (B,), generator=g)
+    p = torch.stack([px, py, torch.ones_like(py)], dim=-1).float()
+    p = torch.matmul(kinv[None, :3, :3], p[:, :, None]).squeeze()
+    v = p / torch.linalg.norm(p, ord=2, dim=-1, keepdim=True)
+    v = torch.matmul(pose[None, :3, :3], v[:, :, None]).squeeze()
+    o = pose[None, :3, 3].expand(v.shape)
+    ref = torch.cat([o, v, image[(py, px)], mask[(py, px)][:, :1]], dim=-1)
+    a = torch.sum(v ** 2, dim=-1, keepdim=True)
+    b = 2.0 * torch.sum(o * v, dim=-1, keepdim=True)
+    mid = 0.5 * (-b) / a
+    out, near, far = ops.gen_rays(px.float().to(DEV), py.float().to(DEV), kinv.to(DEV), pose.to(DEV), image.to(DEV), mask.to(DEV))
+    assert_close(out, ref, 2e-6, "gen_rays rows")
+    assert torch.equal(out[:, 6:].cpu(), ref[:, 6:])                       # colour / mask look-ups are exact
+    assert_close(near, mid - 1.0, 3e-6, "near")
+    assert_close(far, mid + 1.0, 3e-6, "far")
+    # whole-image order of gen_rays_at (transposed meshgrid -> [H, W] row-major)
+    qx, qy = syn.image_pixels(H, W, 1, DEV)
+    full, _, _ = ops.gen_rays(qx, qy, kinv.to(DEV), pose.to(DEV), with_near_far=False)
+    tx, ty = torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H)
+    gx, gy = torch.meshgrid(tx, ty, indexing="ij")
+    pp = torch.stack([gx, gy, torch.ones_like(gy)], dim=-1)
+    pp = torch.matmul(kinv[None, None, :3, :3], pp[:, :, :, None]).squeeze()
+    rv = pp / torch.linalg.norm(pp, ord=2, dim=-1, keepdim=True)
+    rv = torch.matmul(pose[None, None, :3, :3], rv[:, :, :, None]).squeeze().transpose(0, 1)
+    assert_close(full[:, 3:6].reshape(H, W, 3), rv, 2e-6, "gen_rays_at directions")
+
+
+def test_stage2_loss_matches_oracle():
+    """fneus_stage2_loss (lvis.py:163-170) vs the oracle restatement: value, parts and gradients."""
+    B, k = 77, 4
+    g = torch.Generator().manual_seed(6)
+    hit = torch.rand(B, generator=g) > 0.3
+    gt_l, gt_r = torch.rand(B, k, generator=g), torch.rand(B, k, 3, generator=g)
+    pre_l = torch.rand(B, k, generator=g).requires_grad_(True)
+    pre_r = torch.rand(B, k, 3, generator=g).requires_grad_(True)
+    m1, m3 = hit[:, None], hit[:, None, None]
+    out_o = dict(gt_lvis=torch.where(m1, gt_l, torch.ones(B, k)), pre_lvis=torch.where(m1, pre_l, torch.ones(B, k)),
+                 gt_trace_radiance=torch.where(m3, gt_r, torch.ones(B, k, 3)),
+                 pre_trace_radiance=torch.where(m3, pre_r, torch.ones(B, k, 3)), sdf_mask=hit)
+    loss_o, st_o = O.stage2_loss(out_o)
+    loss_o.backward()
+    pl, pr = pre_l.detach().to(DEV).requires_grad_(True), pre_r.detach().to(DEV).requires_grad_(True)
+    hd = hit.to(DEV)
+    out_g = dict(gt_lvis=torch.where(hd[:, None], gt_l.to(DEV), torch.ones(B, k, device=DEV)),
+                 pre_lvis=torch.where(hd[:, None], pl, torch.ones(B, k, device=DEV)),
+                 gt_trace_radiance=torch.where(hd[:, None, None], gt_r.to(DEV), torch.ones(B, k, 3, device=DEV)),
+                 pre_trace_radiance=torch.where(hd[:, None, None], pr, torch.ones(B, k, 3, device=DEV)), sdf_mask=hd)
+    loss_g, st_g = ops.stage2_loss(out_g)
+    loss_g.backward()
+    assert abs(float(loss_g) - float(loss_o)) < 1e-6
+    assert abs(float(st_g["lvis_loss"]) - float(st_o["lvis_loss"])) < 1e-6
+    assert_close(pl.grad, pre_l.grad, 1e-7, "d pre_lvis")
+    assert_close(pr.grad, pre_r.grad, 1e-7, "d pre_trace_radiance")
