@@ -325,7 +325,12 @@ def bench_train(C, args, config, steps, stats_steps):
     mask_w = 0.0 if womask else 0.1
     R, nets = _build_nets(C, womask)
     params = [p for n in nets for p in n.parameters()]
-    bucket = GradBucket(params)
+    # gradient slices in the order they become final during backward: [variance, colour, RefColor] are complete when the SDF
+    # backward starts and travel (side stream) while it runs; the SDF (and NeRF) slices follow at the end
+    early = [p for n in nets[-3:] for p in n.parameters()]
+    late = [p for n in nets[:-3] for p in n.parameters()]
+    bucket = GradBucket(params, segments=[early, late])
+    _ops.SdfValueGrad.pre_backward_hook = (lambda: bucket.all_reduce_segment(0)) if C.world > 1 else None
     opt = FlatAdam(bucket, lr=5e-4, warm_up_end=5000, end_iter=300000)
     opt._moments_restored = True                                             # benchmark at the full learning rate
     opt.set_iteration(5000)
@@ -418,6 +423,7 @@ def bench_train(C, args, config, steps, stats_steps):
     if stat:
         stat["rays_per_s_at_median"] = B * C.world / (stat["median_ms"] * 1e-3)
         res["step_time_stats"] = stat
+    _ops.SdfValueGrad.pre_backward_hook = None
     del graph
     return res
 

@@ -21,26 +21,26 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 class SdfCfg(Structure):
     _fields_ = [("d_in", c_int), ("d_hidden", c_int), ("n_layers", c_int), ("d_out", c_int),
-                ("multires", c_int), ("skip_layer", c_int), ("scale", c_float), ("beta", c_float)]
+                ("multires", c_int), ("skip_layer", c_int), ("scale", c_float), ("beta", c_float), ("precision", c_int)]
 
 
 class ColorCfg(Structure):
     _fields_ = [("d_feature", c_int), ("d_hidden", c_int), ("n_layers", c_int), ("d_out", c_int),
-                ("multires_view", c_int)]
+                ("multires_view", c_int), ("precision", c_int)]
 
 
 class RefCfg(Structure):
-    _fields_ = [("d_feature", c_int), ("d_hidden", c_int)]
+    _fields_ = [("d_feature", c_int), ("d_hidden", c_int), ("precision", c_int)]
 
 
 class MlpCfg(Structure):
     _fields_ = [("n_inputs", c_int), ("in_dim", c_int * 2), ("in_multires", c_int * 2), ("d_hidden", c_int),
-                ("n_layers", c_int), ("d_out", c_int), ("last_act", c_int)]
+                ("n_layers", c_int), ("d_out", c_int), ("last_act", c_int), ("precision", c_int)]
 
 
 class NerfCfg(Structure):
     _fields_ = [("D", c_int), ("W", c_int), ("d_in", c_int), ("d_in_view", c_int), ("multires", c_int),
-                ("multires_view", c_int), ("skip", c_int)]
+                ("multires_view", c_int), ("skip", c_int), ("precision", c_int)]
 
 
 def source_digest() -> str:
@@ -79,8 +79,6 @@ _SIGNATURES = {
     "fneus_status_string": (ctypes.c_char_p, [c_int]),
     "fneus_abi_version": (c_int, []),
     "fneus_num_sms": (c_int, []),
-    "fneus_set_precision": (c_int, [c_int]),
-    "fneus_get_precision": (c_int, []),
     "fneus_surface_blend_fwd": (c_int, [_P, _P, _P, _P, _P, _LL, _P, _P, _P, _P]),
     "fneus_surface_blend_bwd": (c_int, [_P, _P, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fneus_loss_norms": (c_int, [_P, _P, _P, _LL, c_int, _P, _P]),
@@ -100,7 +98,7 @@ _SIGNATURES = {
                                 c_float, c_int, _P]),
     "fneus_debug_flags": (c_int, [c_int]),
     "fneus_debug_timeline": (c_int, [_P, c_int]),
-    "fneus_debug_gemm": (c_int, [c_int, _P, c_int, _P, c_int, _P, _LL, c_int, c_int, _P, c_int, _P]),
+    "fneus_debug_gemm": (c_int, [c_int, c_int, _P, c_int, _P, c_int, _P, _LL, c_int, c_int, _P, c_int, _P]),
     "fneus_prof_classes": (c_int, []),
     "fneus_prof_enable": (c_int, [c_int]),
     "fneus_prof_collect": (c_int, [_P, _P, _P, _P]),

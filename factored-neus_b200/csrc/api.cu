@@ -62,13 +62,6 @@ int fneus_prof_collect(double* ms, long long* launches, double* flops, double* b
 
 extern "C" {
 
-// 0 = FP32 SIMT (exactness anchor, default), 1 = BF16 tcgen05 tensor cores with FP32 accumulation
-int fneus_set_precision(int mode) {
-  if (mode != 0 && mode != 1) return FNEUS_ERR_UNSUPPORTED;
-  fneus::precision_mode() = mode;
-  return FNEUS_OK;
-}
-int fneus_get_precision(void) { return fneus::precision_mode(); }
 // debug/bisect switches of the persistent tensor-core kernel (bit0: skip A loads, bit1: skip epilogue, bit2: skip MMA)
 int fneus_debug_timeline(unsigned long long* host_dst, int n) {
   if (!host_dst || n <= 0 || n > 8192) return FNEUS_ERR_BAD_SHAPE;
@@ -85,9 +78,10 @@ int fneus_debug_flags(int flags) {
 // Raw dense-layer contractions in the current precision mode (test hook for the two GEMM engines).
 // kind 0: C[M,N] = A[M,K] W[N,K]^T + bias ; kind 1: C[M,N] = A[M,K] W[K,N] ; kind 2: C[N,K] += Y[M,N]^T A[M,K],
 // bias[N] += colsum(Y)  (for kind 2 the `W` argument is Y with leading dimension ldw).
-int fneus_debug_gemm(int kind, const float* A, int lda, const float* W, int ldw, float* bias, long long M, int N,
-                     int K, float* C, int ldc, void* stream) {
+int fneus_debug_gemm(int precision, int kind, const float* A, int lda, const float* W, int ldw, float* bias, long long M,
+                     int N, int K, float* C, int ldc, void* stream) {
   using namespace fneus;
+  PrecScope prec_scope_(precision);
   if (!A || !W || !C) return FNEUS_ERR_NULL;
   if (lda % 4 != 0) return FNEUS_ERR_MISALIGNED;
   cudaStream_t st = (cudaStream_t)stream;

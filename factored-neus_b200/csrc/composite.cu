@@ -56,13 +56,13 @@ __device__ __forceinline__ SampleFwd sample_forward(float f, float gx, float gy,
   float half = o.ic * delta * 0.5f;
   o.em = f - half;
   o.ep = f + half;
-  o.P = sigmoidf_(o.em * s);
-  o.N = sigmoidf_(o.ep * s);
+  o.P = sigmoid_bw(o.em * s);
+  o.N = sigmoid_bw(o.ep * s);
   o.araw = (o.P - o.N + 1e-5f) / (o.P + 1e-5f);
   o.a = fminf(fmaxf(o.araw, 0.f), 1.f);
-  float rad = sqrtf(px * px + py * py + pz * pz);
-  o.in = rad < 1.0f ? 1.f : 0.f;
-  o.relax = rad < 1.2f ? 1.f : 0.f;
+  const float rad2 = px * px + py * py + pz * pz;        // |p| < 1, |p| < 1.2 as tests on the squared radius
+  o.in = radius_lt_1(rad2) ? 1.f : 0.f;
+  o.relax = radius_lt_1p2(rad2) ? 1.f : 0.f;
   o.gn = sqrtf(gx * gx + gy * gy + gz * gz);
   return o;
 }
@@ -244,7 +244,7 @@ composite_bwd_kernel(const float* __restrict__ sdf, const float* __restrict__ nr
         cr_ = __ldg(rgb + q * 3); cg_ = __ldg(rgb + q * 3 + 1); cb_ = __ldg(rgb + q * 3 + 2);
         if (has_bg) {
           float px = __ldg(pts + q * 3), py = __ldg(pts + q * 3 + 1), pz = __ldg(pts + q * 3 + 2);
-          float in = sqrtf(px * px + py * py + pz * pz) < 1.0f ? 1.f : 0.f, om = 1.0f - in;
+          float in = radius_lt_1(px * px + py * py + pz * pz) ? 1.f : 0.f, om = 1.0f - in;
           long long qb = ray * n_tot + i;
           cr_ = cr_ * in + __ldg(bg_color + qb * 3) * om;
           cg_ = cg_ * in + __ldg(bg_color + qb * 3 + 1) * om;

@@ -218,6 +218,14 @@ __device__ __forceinline__ float softplus_grad_from_act(float h, float beta) {
   return z > 20.f ? 1.f : -expm1f(-z);
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// Bandwidth kernels (sampling, compositing): accurate expf, reciprocal by MUFU.RCP + one multiply (<= 2 ulp) instead of
+// the ~12-instruction IEEE division -- the result feeds a 1e-4 (FP32 gate) / 2e-6 (CDF) comparison, not a bit-exact one.
+__device__ __forceinline__ float sigmoid_bw(float x) { return __fdividef(1.f, 1.f + expf(-x)); }
+// sqrtf(x2) < 1.0f and sqrtf(x2) < 1.2f without the square root: sqrtf is correctly rounded and monotone, so each test is
+// a threshold on x2 -- 1.0f itself, and 0x3FB851EC = 1.44000006f, the smallest float whose root reaches 1.2f (both checked
+// exhaustively around the thresholds, tests/test_cpu_host.py).
+__device__ __forceinline__ bool radius_lt_1(float x2) { return x2 < 1.0f; }
+__device__ __forceinline__ bool radius_lt_1p2(float x2) { return x2 < __uint_as_float(0x3FB851ECu); }
 
 // MUFU-based, branch-free variants for the BF16 tensor-core path (results are consumed at BF16 precision; the
 // FP32 anchor path keeps the accurate library versions above).  One ex2/lg2/rcp.approx.ftz each, no range fix-ups,

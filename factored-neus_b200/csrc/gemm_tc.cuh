@@ -11,6 +11,7 @@
 //                                              FP32 RED.ADD epilogue
 #pragma once
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "gemm_simt.cuh"
 
@@ -503,21 +504,22 @@ __device__ __forceinline__ void wgrad_to_bf16(uint8_t* tile, int bytes, int tid)
 // (a mixed descriptor raises an illegal-instruction fault on sm_100a), so when exactly one operand is an FP16 image the
 // otherwise idle warps 0-3 rewrite that stage FP16 -> BF16 in place (exact for |v| >= 2^-14 up to BF16's 8 bits; the
 // gradient operand keeps its BF16 exponent range) and hand the stage on through `conv`.
+template <int WG_ST>
 __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy, const ASeg& a, float* __restrict__ dW,
                                            int ldw, int wout0, float* __restrict__ db, int M, int N, int m_per_split,
                                            const int bx, const int by, const bool y_f16 = false,
-                                           const bool x_f16 = false) {
+                                           const bool x_f16 = false, const bool no_conv = false) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared
                                                  // address space (an integer round trip turned every access into a generic LD.E / ST.E)
-  uint8_t* sA[WG_STAGES];
-  uint8_t* sB[WG_STAGES];
+  uint8_t* sA[WG_ST];
+  uint8_t* sB[WG_ST];
 #pragma unroll
-  for (int s = 0; s < WG_STAGES; s++) {
+  for (int s = 0; s < WG_ST; s++) {
     sA[s] = base + s * (TC_A_BYTES + TC_B_BYTES);
     sB[s] = sA[s] + TC_A_BYTES;
   }
-  TcSmem* ctl = reinterpret_cast<TcSmem*>(base + WG_STAGES * (TC_A_BYTES + TC_B_BYTES));
+  TcSmem* ctl = reinterpret_cast<TcSmem*>(base + WG_ST * (TC_A_BYTES + TC_B_BYTES));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int kc_gen = (a.gen.ncols + 255) / 256, kc_mem = (a.kmem + 255) / 256;
@@ -542,14 +544,14 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
   // image dY: the bias gradient is summed from the shared-memory tile by warps 0-3 (they hold the stage open)
   const bool bias_smem = db != nullptr && kc == 0 && y_img;
   const bool yf = y_img && y_f16, xf = x_img && x_f16;
-  const bool conv_y = yf && !xf, conv_x = xf && !yf, any_conv = conv_y || conv_x;
+  const bool conv_y = yf && !xf && !no_conv, conv_x = xf && !yf && !no_conv, any_conv = conv_y || conv_x;
   const int yblocks = y_img ? min(2, -ldy - nt * 2) : 0;
   const int xblocks = x_img ? min((Nc + 63) / 64, -a.ldm - (k0 >> 6)) : 0;
 
   if (tid == 0) {
     const int cnt = (need_prod ? 128 : 0) + ((y_img || x_img) ? 1 : 0);
 #pragma unroll
-    for (int s = 0; s < WG_STAGES; s++) {
+    for (int s = 0; s < WG_ST; s++) {
       mbar_init(&ctl->full[s], cnt); mbar_init(&ctl->empty[s], bias_smem ? 129 : 1); mbar_init(&ctl->conv[s], 128);
     }
     mbar_init(&ctl->accum, 1);
@@ -565,8 +567,8 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
     if (lane == 0 && (y_img || x_img)) {
       const int ykbs = -ldy, xkbs = -a.ldm;
       for (int kb = 0; kb < KB; kb++) {
-        const int s = kb % WG_STAGES;
-        if (kb >= WG_STAGES) mbar_wait(&ctl->empty[s], ((kb / WG_STAGES) - 1) & 1);
+        const int s = kb % WG_ST;
+        if (kb >= WG_ST) mbar_wait(&ctl->empty[s], ((kb / WG_ST) - 1) & 1);
         const long long mblk = (mbeg >> 6) + kb;               // 64-row block index
         const size_t half = (size_t)(mblk & 1) * 8192;
         mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)(yblocks + xblocks) * 8192u);
@@ -584,8 +586,8 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
     const int bn = (tid & 31) << 2;            // this thread always loads dY columns n0+bn..+3
     if (need_prod) {
       for (int kb = 0; kb < KB; kb++) {
-        const int s = kb % WG_STAGES;
-        if (kb >= WG_STAGES) mbar_wait(&ctl->empty[s], ((kb / WG_STAGES) - 1) & 1);
+        const int s = kb % WG_ST;
+        if (kb >= WG_ST) mbar_wait(&ctl->empty[s], ((kb / WG_ST) - 1) & 1);
         const long long mb = mbeg + (long long)kb * TC_BK;
         if (!y_img) {
           // A operand (dY^T), MN-major: 64 m-rows x 128 n
@@ -646,7 +648,7 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
         fence_proxy_async();
         mbar_arrive(&ctl->full[s]);
         if (any_conv || bias_smem) {
-          mbar_wait(&ctl->full[s], (kb / WG_STAGES) & 1);
+          mbar_wait(&ctl->full[s], (kb / WG_ST) & 1);
           if (any_conv) {
             wgrad_to_bf16(conv_y ? sA[s] : sB[s], (conv_y ? yblocks : xblocks) * 8192, tid);
             fence_proxy_async();
@@ -660,8 +662,8 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
       }
     } else if (any_conv || bias_smem) {
       for (int kb = 0; kb < KB; kb++) {
-        const int s = kb % WG_STAGES;
-        mbar_wait(&ctl->full[s], (kb / WG_STAGES) & 1);
+        const int s = kb % WG_ST;
+        mbar_wait(&ctl->full[s], (kb / WG_ST) & 1);
         if (any_conv) {
           wgrad_to_bf16(conv_y ? sA[s] : sB[s], (conv_y ? yblocks : xblocks) * 8192, tid);
           fence_proxy_async();
@@ -704,10 +706,10 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
     }
     tc_fence_before();
   } else if (warp == 4 && lane == 0) {
-    const uint32_t idesc = make_idesc(Nc, 1, 1, yf && !conv_y, xf && !conv_x);
+    const uint32_t idesc = make_idesc(Nc, 1, 1, yf && !conv_y && !no_conv, xf && !conv_x && !no_conv);
     for (int kb = 0; kb < KB; kb++) {
-      const int s = kb % WG_STAGES;
-      mbar_wait(any_conv ? &ctl->conv[s] : &ctl->full[s], (kb / WG_STAGES) & 1);
+      const int s = kb % WG_ST;
+      mbar_wait(any_conv ? &ctl->conv[s] : &ctl->full[s], (kb / WG_ST) & 1);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(sA[s]), b_addr = smem_u32(sB[s]);
 #pragma unroll
@@ -728,10 +730,10 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, const __grid_constant__ ASeg a, float* __restrict__ dW,
                      int ldw, int wout0, float* __restrict__ db, int M, int N, int m_per_split) {
-  wgrad_body(dY, ldy, a, dW, ldw, wout0, db, M, N, m_per_split, blockIdx.x, blockIdx.y);
+  wgrad_body<TC_STAGES>(dY, ldy, a, dW, ldw, wout0, db, M, N, m_per_split, blockIdx.x, blockIdx.y);
 }
 
 // Grouped variant: the weight gradients of all layers of one chain in ONE launch (blockIdx.z = job).  Every job
@@ -745,12 +747,13 @@ struct WgradJob {
   int N, m_per_split, tiles, splits;
   int y_f16, x_f16;                  // element format of the image operands (0 = BF16, 1 = FP16)
 };
-struct WgradJobs { int n; int M; WgradJob job[WG_MAX_JOBS]; };
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_wgrad_group_kernel(const __grid_constant__ WgradJobs jobs) {
+struct WgradJobs { int n; int M; int no_conv; WgradJob job[WG_MAX_JOBS]; };
+template <int WG_ST>
+__global__ void __launch_bounds__(TC_THREADS, WG_ST == 2 ? 2 : 1) tc_gemm_wgrad_group_kernel(const __grid_constant__ WgradJobs jobs) {
   const WgradJob& j = jobs.job[blockIdx.z];
   if ((int)blockIdx.x >= j.tiles || (int)blockIdx.y >= j.splits) return;
-  wgrad_body(j.dY, j.ldy, j.a, j.dW, j.ldw, j.wout0, j.db, jobs.M, j.N, j.m_per_split, blockIdx.x, blockIdx.y, j.y_f16 != 0,
-             j.x_f16 != 0);
+  wgrad_body<WG_ST>(j.dY, j.ldy, j.a, j.dW, j.ldw, j.wout0, j.db, jobs.M, j.N, j.m_per_split, blockIdx.x, blockIdx.y,
+                    j.y_f16 != 0, j.x_f16 != 0, jobs.no_conv != 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1226,7 +1229,12 @@ __global__ void pack_wimg_multi_kernel(PackJobs jobs) {
 constexpr int TC_SMEM_BYTES = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 + 256;
 constexpr int WG_SMEM_BYTES = WG_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 + 256;
 
-inline int& tc_wgrad_ctas_per_sm() { static int v = 1; return v; }
+// development knobs (environment, read once): FNEUS_WG_STAGES = 2 | 4 (ring depth; 2 -> two CTAs per SM),
+// FNEUS_WG_NOCONV = 1 (timing experiment only: skips the operand-format conversion, results are wrong)
+inline int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+inline int& tc_wgrad_stages() { static int v = env_int("FNEUS_WG_STAGES", 2) == 4 ? 4 : 2; return v; }
+inline int& tc_wgrad_noconv() { static int v = env_int("FNEUS_WG_NOCONV", 0); return v; }
+inline int& tc_wgrad_ctas_per_sm() { static int v = tc_wgrad_stages() == 4 ? 1 : 2; return v; }
 inline int tc_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -1242,9 +1250,11 @@ inline int tc_prepare() {
   if (done) return 0;
   cudaError_t e1 = cudaFuncSetAttribute(tc_gemm_mk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaError_t e2 = cudaFuncSetAttribute(tc_gemm_mk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  cudaError_t e3 = cudaFuncSetAttribute(tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+  cudaError_t e3 = cudaFuncSetAttribute(tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e3 == cudaSuccess)
-    e3 = cudaFuncSetAttribute(tc_gemm_wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    e3 = cudaFuncSetAttribute(tc_gemm_wgrad_group_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (e3 == cudaSuccess)
+    e3 = cudaFuncSetAttribute(tc_gemm_wgrad_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
   cudaError_t e4 = cudaFuncSetAttribute(tc_gemm_mk_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
   cudaError_t e5 = cudaFuncSetAttribute(tc_gemm_mk_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) return 1;
@@ -1289,7 +1299,7 @@ inline void launch_tc_wgrad(const float* dY, int ldy, const ASeg& a, float* dW, 
   splits = cdiv(M, mps);
   dim3 grid(tiles, splits);
   prof_begin(PC_TC_MLP, 2.0 * (double)M * N * (a.gen.ncols + a.kmem), 0.0, st);
-  tc_gemm_wgrad_kernel<<<grid, TC_THREADS, WG_SMEM_BYTES, st>>>(dY, ldy, a, dW, ldw, wout0, db, (int)M, N, mps);
+  tc_gemm_wgrad_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(dY, ldy, a, dW, ldw, wout0, db, (int)M, N, mps);
   prof_end(st);
 }
 
@@ -1326,7 +1336,8 @@ struct WgradGroup {
     }
     // whole waves: never more CTAs than `waves` rounds of the machine hold (a few CTAs spilling into an extra round cost a
     // full round of latency)
-    int splits = (tc_wgrad_group_waves() * tc_wgrad_ctas_per_sm() * num_sms) / total_tiles;
+    int splits = env_int("FNEUS_WG_CEIL", 0) ? (tc_wgrad_group_waves() * tc_wgrad_ctas_per_sm() * num_sms + total_tiles - 1) / total_tiles
+                                             : (tc_wgrad_group_waves() * tc_wgrad_ctas_per_sm() * num_sms) / total_tiles;
     const int max_s = cdiv(M, 4 * TC_BK);
     if (splits > max_s) splits = max_s;
     if (splits < 1) splits = 1;
@@ -1334,7 +1345,11 @@ struct WgradGroup {
     splits = cdiv(M, mps);
     for (int i = 0; i < jobs.n; i++) { jobs.job[i].m_per_split = mps; jobs.job[i].splits = splits; }
     prof_begin(PC_TC_WGRAD, flops, bytes, st);
-    tc_gemm_wgrad_group_kernel<<<dim3(max_tiles, splits, jobs.n), TC_THREADS, WG_SMEM_BYTES, st>>>(jobs);
+    jobs.no_conv = tc_wgrad_noconv();
+    if (tc_wgrad_stages() == 4)
+      tc_gemm_wgrad_group_kernel<4><<<dim3(max_tiles, splits, jobs.n), TC_THREADS, WG_SMEM_BYTES, st>>>(jobs);
+    else
+      tc_gemm_wgrad_group_kernel<2><<<dim3(max_tiles, splits, jobs.n), TC_THREADS, TC_SMEM_BYTES, st>>>(jobs);
     prof_end(st);
     reset(M, num_sms);
   }
@@ -1343,7 +1358,14 @@ struct WgradGroup {
 // ---------------------------------------------------------------------------------------------
 // precision dispatch: 0 = FP32 SIMT (exactness anchor), 1 = BF16 tcgen05 (FP32 accumulate)
 // ---------------------------------------------------------------------------------------------
-inline int& precision_mode() { static int m = 0; return m; }
+// The precision of a call comes from its configuration struct (include/fneus.h: fneus_*_cfg.precision) and is held in a
+// thread-local for the duration of that ABI call (PrecScope) -- no process-global state, calls are re-entrant.
+inline int& precision_mode() { static thread_local int m = 0; return m; }
+struct PrecScope {
+  int saved;
+  explicit PrecScope(int p) : saved(precision_mode()) { precision_mode() = (p == 1) ? 1 : 0; }
+  ~PrecScope() { precision_mode() = saved; }
+};
 
 // A bump allocator over a caller-provided byte region for the weight images of one ABI call.  make_wimg only
 // RECORDS the packing job; ImgArena::flush packs every recorded image in one launch and must be called before the

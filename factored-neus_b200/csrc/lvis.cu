@@ -10,7 +10,7 @@
 //
 // A single monolithic kernel would not move fewer bytes that matter: the per-chunk intermediates (sdf of the coarse
 // samples, 2 KB per ray) stay in L2, and every phase is already one persistent tile kernel.
-#include "fneus_common.cuh"
+#include "gemm_tc.cuh"
 #include "prof.cuh"
 
 namespace fneus {
@@ -54,6 +54,7 @@ extern "C" {
 
 long long fneus_lvis_trace_workspace_floats(const fneus_sdf_cfg* sdf_cfg, const fneus_color_cfg* color_cfg,
                                             long long rays_per_chunk, int n_coarse, int n_imp) {
+  PrecScope prec_scope_(sdf_cfg ? sdf_cfg->precision : 0);
   if (!sdf_cfg || !color_cfg || rays_per_chunk < 1 || n_coarse < 2 || n_imp < 2) return -1;
   if (fneus_sdf_saved_floats(sdf_cfg, 1) < 0 || fneus_color_scratch_floats(color_cfg, 1) < 0) return -1;
   return lvis_layout(sdf_cfg, color_cfg, rays_per_chunk, n_coarse, n_imp).total;
@@ -64,6 +65,7 @@ int fneus_lvis_trace(const fneus_sdf_cfg* sdf_cfg, const float* sdf_wpack, const
                      int n_coarse, int n_imp, const float* inv_s, const float* z_table, const float* u_table,
                      float* lvis_out, float* rgb_out, int* hit_out, float* ws, long long ws_floats,
                      long long rays_per_chunk, void* stream) {
+  PrecScope prec_scope_(sdf_cfg ? sdf_cfg->precision : 0);
   if (m == 0) return FNEUS_OK;
   if (!sdf_cfg || !sdf_wpack || !color_cfg || !color_wpack || !surf || !dirs || !inv_s || !z_table || !u_table ||
       !lvis_out || !rgb_out || !hit_out || !ws)

@@ -450,20 +450,24 @@ using namespace fneus;
 extern "C" {
 
 long long fneus_sdf_pack_floats(const fneus_sdf_cfg* cfg) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   SdfPlan p = sdf_plan(cfg);
   return p.ok ? p.pack : -1;
 }
 long long fneus_sdf_saved_floats(const fneus_sdf_cfg* cfg, long long n) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   SdfPlan p = sdf_plan(cfg);
   return p.ok ? sdf_saved_floats(p, n) : -1;
 }
 long long fneus_sdf_scratch_floats(const fneus_sdf_cfg* cfg, long long n) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   SdfPlan p = sdf_plan(cfg);
   return p.ok ? sdf_scratch_floats(p, n) : -1;
 }
 
 int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long n, float* sdf_out,
                   float* feat_out, float* scratch, long long scratch_floats, void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   SdfPlan p = sdf_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (n == 0) return FNEUS_OK;
@@ -511,6 +515,7 @@ int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
 int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax, const float* ay, const float* az,
                    int nx, int ny, int nz, int ix0, int ix1, float* u_out, float* scratch, long long scratch_floats,
                    void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   SdfPlan p = sdf_plan(cfg);
   if (!p.ok || cfg->d_in != 3) return FNEUS_ERR_UNSUPPORTED;
   if (!wpack || !ax || !ay || !az || !u_out || !scratch) return FNEUS_ERR_NULL;
@@ -548,6 +553,7 @@ int fneus_sdf_grid(const fneus_sdf_cfg* cfg, const float* wpack, const float* ax
 
 int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long M, float* sdf_out,
                        float* feat_out, float* normal_out, float* saved, float* scratch, void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   SdfPlan p = sdf_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (M == 0) return FNEUS_OK;
@@ -659,6 +665,7 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
 int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long M, const float* d_sdf,
                   const float* d_feat, const float* d_normal, float* saved, float* scratch, float* d_wpack,
                   void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   SdfPlan p = sdf_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (M == 0) return FNEUS_OK;

@@ -429,15 +429,18 @@ using namespace fneus;
 extern "C" {
 
 long long fneus_color_pack_floats(const fneus_color_cfg* cfg) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   ColorPlan p = color_plan(cfg);
   return p.ok ? p.pack : -1;
 }
 // saved: H_1..H_n ; scratch: 2 abufs + dsmall + a_last
 long long fneus_color_saved_floats(const fneus_color_cfg* cfg, long long n) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   ColorPlan p = color_plan(cfg);
   return p.ok ? (long long)cfg->n_layers * hid_floats(n, p.hid, p.img) + (p.img ? a0_img_floats(n) : 0) + 1024 : -1;
 }
 long long fneus_color_scratch_floats(const fneus_color_cfg* cfg, long long n) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   ColorPlan p = color_plan(cfg);
   if (!p.ok) return -1;
   return color_scratch_main(cfg, p, n) + (long long)(relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols) / 4) + 256;
@@ -446,6 +449,7 @@ long long fneus_color_scratch_floats(const fneus_color_cfg* cfg, long long n) {
 int fneus_color_fwd(const fneus_color_cfg* cfg, const float* wpack, const float* points, const float* normals,
                     const float* view_dirs, const float* feats, long long M, float* rgb_out, float* saved,
                     float* scratch, void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   ColorPlan p = color_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (M == 0) return FNEUS_OK;
@@ -467,6 +471,7 @@ int fneus_color_fwd(const fneus_color_cfg* cfg, const float* wpack, const float*
 int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float* points, const float* normals,
                     const float* view_dirs, const float* feats, long long M, const float* rgb, const float* d_rgb,
                     float* d_normals, float* d_feats, float* saved, float* scratch, float* d_wpack, void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   ColorPlan p = color_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (M == 0) return FNEUS_OK;
@@ -499,16 +504,19 @@ int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float*
 }
 
 long long fneus_ref_pack_floats(const fneus_ref_cfg* cfg) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   RefPlan p = ref_plan(cfg);
   return p.ok ? p.pack : -1;
 }
 // saved: cd H1..H4, cs G1..G4, yd [M,4], ys [M,4], refl [M,4]
 long long fneus_ref_saved_floats(const fneus_ref_cfg* cfg, long long n) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   RefPlan p = ref_plan(cfg);
   return p.ok ? 8LL * hid_floats(n, p.hid, p.img) + 12 * n + 2048 + (p.img ? 2 * a0_img_floats(n) + 512 : 0) : -1;
 }
 // scratch: 2 abufs, dsmall_cd [M,32], dsmall_cs [M,36], a_cd [M,4], a_cs [M,4]
 long long fneus_ref_scratch_floats(const fneus_ref_cfg* cfg, long long n) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   RefPlan p = ref_plan(cfg);
   if (!p.ok) return -1;
   Lin chain[5] = {p.vd[0], p.vd[1], p.vd[2], p.vd[3], p.cs};
@@ -546,6 +554,7 @@ ASeg ref_cs_a0(const fneus_ref_cfg* c, const float* pts, const float* nrm, const
 int fneus_ref_fwd(const fneus_ref_cfg* cfg, const float* wpack, const float* points, const float* feats,
                   const float* dirs, const float* normals, long long M, float* rgb_out, float* spec_out,
                   float* diff_out, float* saved, float* scratch, void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   RefPlan p = ref_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (M == 0) return FNEUS_OK;
@@ -588,6 +597,7 @@ int fneus_ref_bwd(const fneus_ref_cfg* cfg, const float* wpack, const float* poi
                   const float* dirs, const float* normals, long long M, const float* d_rgb, const float* d_spec,
                   const float* d_diff, float* d_feats, float* d_normals, float* saved, float* scratch,
                   float* d_wpack, void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   RefPlan p = ref_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (M == 0) return FNEUS_OK;
@@ -684,16 +694,19 @@ extern "C" {
 
 long long fneus_mlp_pack_floats(const fneus_mlp_cfg* cfg) { MlpPlan p = mlp_plan(cfg); return p.ok ? p.pack : -1; }
 long long fneus_mlp_saved_floats(const fneus_mlp_cfg* cfg, long long n) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   MlpPlan p = mlp_plan(cfg);
   return p.ok ? (long long)cfg->n_layers * hid_floats(n, p.hid, p.img) + (p.img ? a0_img_floats(n) : 0) + 1024 : -1;
 }
 long long fneus_mlp_scratch_floats(const fneus_mlp_cfg* cfg, long long n) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   MlpPlan p = mlp_plan(cfg);
   return p.ok ? mlp_scratch_main(cfg, p, n) + (long long)(relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols) / 4) + 256 : -1;
 }
 
 int fneus_mlp_fwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0, const float* in1, long long M,
                   float* out, float* saved, float* scratch, void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   MlpPlan p = mlp_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (M == 0) return FNEUS_OK;
@@ -713,6 +726,7 @@ int fneus_mlp_fwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0
 
 int fneus_mlp_bwd(const fneus_mlp_cfg* cfg, const float* wpack, const float* in0, const float* in1, long long M,
                   const float* out, const float* d_out, float* saved, float* scratch, float* d_wpack, void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   MlpPlan p = mlp_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (M == 0) return FNEUS_OK;

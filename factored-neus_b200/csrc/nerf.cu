@@ -338,11 +338,13 @@ extern "C" {
 
 long long fneus_nerf_pack_floats(const fneus_nerf_cfg* cfg) { NerfPlan p = nerf_plan(cfg); return p.ok ? p.pack : -1; }
 long long fneus_nerf_saved_floats(const fneus_nerf_cfg* cfg, long long n) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   NerfPlan p = nerf_plan(cfg);
   if (!p.ok) return -1;
   return nerf_chain_ok(p) ? nerf_saved_img_floats(p, n) : nerf_saved_per_point(p) * n;
 }
 long long fneus_nerf_scratch_floats(const fneus_nerf_cfg* cfg, long long n) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   NerfPlan p = nerf_plan(cfg);
   if (!p.ok) return -1;
   return nerf_chain_ok(p) ? nerf_scratch_img_floats(p, n) : nerf_scratch_per_point(p) * n;
@@ -350,6 +352,7 @@ long long fneus_nerf_scratch_floats(const fneus_nerf_cfg* cfg, long long n) {
 
 int fneus_nerf_fwd(const fneus_nerf_cfg* cfg, const float* wpack, const float* pts, const float* views, long long M,
                    float* density_out, float* rgb_out, float* saved, void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   NerfPlan p = nerf_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (M == 0) return FNEUS_OK;
@@ -394,6 +397,7 @@ int fneus_nerf_fwd(const fneus_nerf_cfg* cfg, const float* wpack, const float* p
 int fneus_nerf_bwd(const fneus_nerf_cfg* cfg, const float* wpack, const float* pts, const float* views, long long M,
                    const float* d_density, const float* d_rgb, float* saved, float* scratch, float* d_wpack,
                    void* stream) {
+  PrecScope prec_scope_(cfg ? cfg->precision : 0);
   NerfPlan p = nerf_plan(cfg);
   if (!p.ok) return FNEUS_ERR_UNSUPPORTED;
   if (M == 0) return FNEUS_OK;

@@ -93,29 +93,37 @@ upsample_step_kernel(const float* __restrict__ rays_o, const float* __restrict__
   __syncwarp();
   const float ox = rays_o[ray * 3], oy = rays_o[ray * 3 + 1], oz = rays_o[ray * 3 + 2];
   const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
-  auto radius = [&](float t) {
+  // |o + d t| < 1 as a test on the squared radius (radius_lt_1: identical to comparing the rounded square root)
+  auto in_sphere = [&](float t) {
     float px = __fadd_rn(ox, __fmul_rn(dx, t)), py = __fadd_rn(oy, __fmul_rn(dy, t)),
           pz = __fadd_rn(oz, __fmul_rn(dz, t));
-    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+    return radius_lt_1(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
   };
   auto slope = [&](int j) { return (sf[j + 1] - sf[j]) / (sz[j + 1] - sz[j] + 1e-5f); };
   const int ni = n - 1;  // intervals
-  // pass 1: alpha_j, transmittance scan, weights; accumulate sum(w + 1e-5)
-  float carry = 1.f, wsum = 0.f;
+  // pass 1: alpha_j, transmittance scan, weights; accumulate sum(w + 1e-5).  Each lane evaluates ITS interval's slope and
+  // its left end point's sphere test once; the neighbour's values come by shuffle (the previous chunk's last ones are carried).
+  float carry = 1.f, wsum = 0.f, slope_carry = 0.f;
   for (int c0 = 0; c0 < ni; c0 += 32) {
     int j = c0 + lane;
     float alpha = 0.f;
-    if (j < ni) {
-      bool inside = (radius(sz[j]) < 1.0f) || (radius(sz[j + 1]) < 1.0f);
-      float cosv = slope(j);
-      float prev = j == 0 ? 0.f : slope(j - 1);
+    const bool act = j < ni;
+    const float cosv = act ? slope(j) : 0.f;
+    const bool in_l = j < n ? in_sphere(sz[j]) : false;
+    float prev = __shfl_up_sync(0xffffffffu, cosv, 1);
+    if (lane == 0) prev = slope_carry;                                  // 0 for the first interval of the ray
+    int in_r = __shfl_down_sync(0xffffffffu, (int)in_l, 1);
+    if (lane == 31) in_r = (j + 1 < n) ? (int)in_sphere(sz[j + 1]) : 0;
+    slope_carry = __shfl_sync(0xffffffffu, cosv, 31);
+    if (act) {
+      bool inside = in_l || (in_r != 0);
       float cm = fminf(prev, cosv);
       cm = fminf(fmaxf(cm, -1e3f), 0.f) * (inside ? 1.f : 0.f);
       float dist = sz[j + 1] - sz[j];
       float mid = (sf[j] + sf[j + 1]) * 0.5f;
       float half = __fmul_rn(__fmul_rn(cm, dist), 0.5f);
-      float pc = sigmoidf_(__fmul_rn(mid - half, inv_s));
-      float nc = sigmoidf_(__fmul_rn(mid + half, inv_s));
+      float pc = sigmoid_bw(__fmul_rn(mid - half, inv_s));
+      float nc = sigmoid_bw(__fmul_rn(mid + half, inv_s));
       alpha = (pc - nc + 1e-5f) / (pc + 1e-5f);
     }
     float fac = j < ni ? (1.f - alpha + 1e-7f) : 1.f;
@@ -331,7 +339,7 @@ first_hit_secant_kernel(const float* __restrict__ sdf, const float* __restrict__
     const long long q = ray * n + i;
     if (__ldg(sdf + q) < 0.f && i < first) first = i;
     const float px = __ldg(pts + q * 3), py = __ldg(pts + q * 3 + 1), pz = __ldg(pts + q * 3 + 2);
-    const bool in = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz))) < 1.0f;
+    const bool in = radius_lt_1(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
     any_in = any_in || in;
     if (weights != nullptr && in) occ += __ldg(weights + ray * ldw + i);
   }

@@ -134,7 +134,7 @@ constexpr int sc_smem_bytes() {
   constexpr int OPB = FAM == FAM_RELU ? SC_OPB_RELU : 4;
   constexpr bool PARK = FAM == FAM_SDF_FWD;
   return OPB * TC_A_BYTES + sc_wstages<FAM>() * CH_WBYTES + sc_nslot<FAM>() * 2 * TC_A_BYTES +
-         (sc_bias_slots<FAM>() * 256 + 256 + 128 + (PARK ? 128 * SC_PARK_LD : 0)) * 4 + 1024 + 256;
+         (sc_bias_slots<FAM>() * 256 + 256 + (PARK ? 512 : 128) + (PARK ? 128 * SC_PARK_LD : 0)) * 4 + 1024 + 256;
 }
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float* out) { u16x8_to_f32(u, false, out); }
@@ -207,8 +207,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
   constexpr int NBIAS = sc_bias_slots<FAM>();
   float* sbias = reinterpret_cast<float*>(sAux + NSLOT * 2 * TC_A_BYTES);  // [NBIAS][256]
   float* srvec = sbias + NBIAS * 256;                            // [256]
-  float* sdot = srvec + 256;                                     // [128]
-  float* spark = sdot + 128;                                     // [128][SC_PARK_LD]: skip part of the input gradient
+  float* sdot = srvec + 256;                                     // [4][128] partial row-dots of the four column groups (forward family)
+  float* spark = sdot + (FWD ? 512 : 128);                       // [128][SC_PARK_LD]: skip part of the input gradient
   SCSmem* ctl = reinterpret_cast<SCSmem*>(spark + (PARK ? 128 * SC_PARK_LD : 0));
 
   constexpr bool SDF = FAM != FAM_RELU;
@@ -824,11 +824,13 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           for (int b = pub_blocks ? nb : 0; b < SC_NAR; b++) mbar_arrive(&ctl->a_ready[b]);
         if (s_dot) {
           // sdf = h_L . W_L[0] + b: the four column groups of a row meet in shared memory
-          if (cg == 0) sdot[r] = dot;
+          // (fixed summation order: the value must not depend on which warp arrives first -- inverse-CDF sampling
+          // amplifies a last-bit difference of the sdf into visibly different sample depths)
+          sdot[cg * 128 + r] = dot;
           epi_bar();
-          if (cg != 0) atomicAdd(&sdot[r], dot);
-          epi_bar();
-          if (cg == 0 && valid) g.sdf_out[m] = (sdot[r] + __ldg(g.b_last)) * g.sdf_scale;
+          if (cg == 0 && valid)
+            g.sdf_out[m] = ((((sdot[r] + sdot[128 + r]) + sdot[256 + r]) + sdot[384 + r]) + __ldg(g.b_last)) * g.sdf_scale;
+          epi_bar();                                                         // the partials are rewritten by the next tile
         }
         SC_STAMP(7);
       }

@@ -100,6 +100,7 @@ class SDFNetwork(nn.Module):
             setattr(self, "lin" + str(l), WNLinear(lin) if weight_norm else PlainLinear(lin))
         self.cfg = L.SdfCfg(d_in=d_in, d_hidden=d_hidden, n_layers=n_layers, d_out=d_out, multires=multires,
                             skip_layer=(skip_in[0] if skip_in else -1), scale=float(scale), beta=100.0)
+        ops.register_module(self)
         self.d_out = d_out
 
     def flat_weights(self):
@@ -149,6 +150,7 @@ class RenderingNetwork(nn.Module):
             setattr(self, "lin" + str(l), WNLinear(lin) if weight_norm else PlainLinear(lin))
         self.cfg = L.ColorCfg(d_feature=d_feature, d_hidden=d_hidden, n_layers=n_layers, d_out=d_out,
                               multires_view=multires_view)
+        ops.register_module(self)
 
     def flat_weights(self):
         return _flat_pack([getattr(self, "lin" + str(l)) for l in range(self.num_layers - 1)])
@@ -180,6 +182,7 @@ class NeRF(nn.Module):
         self.rgb_linear = nn.Linear(W // 2, 3)
         self.cfg = L.NerfCfg(D=D, W=W, d_in=d_in, d_in_view=d_in_view, multires=multires,
                              multires_view=multires_view, skip=(skips[0] if skips else -1))
+        ops.register_module(self)
 
     def flat_weights(self):
         if self.rgb_linear.bias.is_cuda:
@@ -233,6 +236,7 @@ class RefColor(nn.Module):
         self.viewdir_mlp = nn.ModuleList([nn.Linear(33 + Fd if i == 0 else H, H) for i in range(4)])
         self.net_cs = nn.Sequential(nn.Linear(H, 1), nn.Sigmoid())
         self.cfg = L.RefCfg(d_feature=Fd, d_hidden=H)
+        ops.register_module(self)
 
     def flat_weights(self):
         layers = [self.net_cd[i] for i in (0, 2, 4, 6, 8)] + list(self.viewdir_mlp) + [self.net_cs[0]]
@@ -252,6 +256,7 @@ class Lvis(nn.Module):
                                   nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 1), nn.Sigmoid())
         self.cfg = L.MlpCfg(n_inputs=2, in_dim=(3, 3), in_multires=(10, 4), d_hidden=256, n_layers=4, d_out=1,
                             last_act=1)
+        ops.register_module(self)
 
     def flat_weights(self):
         return _flat_pack([self.lvis[i] for i in (0, 2, 4, 6, 8)])
@@ -271,6 +276,7 @@ class IndirectLight(nn.Module):
                                   nn.ReLU(), nn.Linear(512, 512), nn.ReLU(), nn.Linear(512, num_lgt_sgs * 6))
         self.cfg = L.MlpCfg(n_inputs=1, in_dim=(3, 0), in_multires=(10, 0), d_hidden=512, n_layers=4,
                             d_out=num_lgt_sgs * 6, last_act=0)
+        ops.register_module(self)
 
     def flat_weights(self):
         return _flat_pack([self.indi[i] for i in (0, 2, 4, 6, 8)])

@@ -31,14 +31,35 @@ def _empty(n, like):
 # ---------------------------------------------------------------------------------------------
 # precision switch + raw GEMM test hook
 # ---------------------------------------------------------------------------------------------
-def set_precision(mode):
-    """'fp32' (CUDA-core exactness anchor, default) or 'bf16' (tcgen05 tensor cores, FP32 accumulate)."""
-    m = {"fp32": 0, "bf16": 1, 0: 0, 1: 1}[mode]
-    L.check(L.lib().fneus_set_precision(m), "fneus_set_precision")
+_PRECISION = {"default": 0}
+_LIVE_MODULES = __import__("weakref").WeakSet()      # network modules whose cfg carries a precision field
+
+
+def _prec_code(mode):
+    return {"fp32": 0, "bf16": 1, "tc": 1, 0: 0, 1: 1}[mode]
+
+
+def register_module(m):
+    """Networks register themselves so that ``set_precision`` can retarget them; their cfg starts at the default."""
+    m.cfg.precision = _PRECISION["default"]
+    _LIVE_MODULES.add(m)
+
+
+def set_precision(mode, modules=None):
+    """'fp32' (CUDA-core exactness anchor, default) or 'bf16' / 'tc' (tcgen05 tensor cores: FP16 forward / BF16 backward
+    operands, FP32 accumulate).  The precision is a field of each network's configuration struct -- the C library keeps no
+    global mode.  With ``modules`` only those networks are retargeted (two renderers of one process may differ);
+    without, the default for new networks AND every live network are set (convenience for scripts and tests)."""
+    code = _prec_code(mode)
+    if modules is None:
+        _PRECISION["default"] = code
+        modules = list(_LIVE_MODULES)
+    for m in modules:
+        m.cfg.precision = code
 
 
 def get_precision():
-    return "bf16" if L.lib().fneus_get_precision() == 1 else "fp32"
+    return "bf16" if _PRECISION["default"] == 1 else "fp32"
 
 
 def debug_gemm(kind, A, W, bias=None, out=None):
@@ -55,7 +76,7 @@ def debug_gemm(kind, A, W, bias=None, out=None):
     else:
         N = W.shape[1]
         C = out if out is not None else torch.zeros(N, K, dtype=torch.float32, device=A.device)
-    L.check(L.lib().fneus_debug_gemm(kind, A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), L.ptr(bias), M, N, K,
+    L.check(L.lib().fneus_debug_gemm(_PRECISION["default"], kind, A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), L.ptr(bias), M, N, K,
                                      L.ptr(C), C.stride(0), L.stream_ptr()), "fneus_debug_gemm")
     return C
 
@@ -202,8 +223,15 @@ class SdfValueGrad(torch.autograd.Function):
             ctx.mark_non_differentiable(normal)
         return sdf, feat, normal
 
+    # called (if set) when the SDF backward is about to start: everything autograd created AFTER the SDF forward -- the
+    # colour / RefColor / variance gradients -- is final by then (parallel.GradBucket.all_reduce_segment uses it to send
+    # that slice while the SDF backward runs)
+    pre_backward_hook = None
+
     @staticmethod
     def backward(ctx, d_sdf, d_feat, d_normal):
+        if SdfValueGrad.pre_backward_hook is not None and ctx.want_normal:
+            SdfValueGrad.pre_backward_hook()
         if ctx.consumed:
             raise RuntimeError("fneus SdfValueGrad: backward twice is not supported (saved activations are "
                                "consumed in place)")
@@ -346,8 +374,12 @@ class NerfMLP(torch.autograd.Function):
         ctx.save_for_backward(w, p, v, saved)
         return dens, rgb
 
+    pre_backward_hook = None       # the NeRF backward starts after the SDF backward: the SDF slice is final by then
+
     @staticmethod
     def backward(ctx, d_dens, d_rgb):
+        if NerfMLP.pre_backward_hook is not None:
+            NerfMLP.pre_backward_hook()
         w, p, v, saved = ctx.saved_tensors
         cfg = ctx.cfg
         N = p.shape[0]
@@ -466,7 +498,7 @@ def lvis_trace(sdf_cfg, sdf_w, color_cfg, color_w, surf, dirs, inv_s, z_table, u
     need = lib.fneus_lvis_trace_workspace_floats(sdf_cfg, color_cfg, chunk, n_coarse, n_imp)
     if need < 0:
         raise RuntimeError("fneus_lvis_trace: unsupported configuration")
-    key = (str(dev), chunk, n_coarse, n_imp, get_precision())
+    key = (str(dev), chunk, n_coarse, n_imp, int(sdf_cfg.precision))
     ws = _LVIS_WS.get(key)
     if ws is None or ws.numel() < need:
         _LVIS_WS.clear()

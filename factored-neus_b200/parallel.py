@@ -150,32 +150,85 @@ def extract_fields_sharded(renderer, bound_min, bound_max, resolution, group=Non
 
 
 class GradBucket:
-    """Single flat FP32 gradient bucket over a fixed parameter list; one all-reduce(sum) per step.
+    """Single flat FP32 gradient bucket over a fixed parameter list; the parameters' ``.grad`` are views into it.
 
-    ``direct=True`` (default) additionally registers the parameters for direct accumulation: the weight-pack
-    backward (``ops.PackWeights``) then adds into the bucket views itself and hands autograd no gradient tensors.
-    Tensor / post-accumulate hooks, ``torch.autograd.grad`` and DDP do not see those gradients; pass
-    ``direct=False`` to keep plain autograd semantics (the ``.grad`` views still alias the bucket)."""
+    ``direct=True`` (default) additionally registers the parameters for direct accumulation: the weight-pack backward
+    (``ops.PackWeights``) then adds into the bucket views itself and hands autograd no gradient tensors.  Tensor /
+    post-accumulate hooks, ``torch.autograd.grad`` and DDP do not see those gradients; pass ``direct=False`` to keep plain
+    autograd semantics (the ``.grad`` views still alias the bucket).
 
-    def __init__(self, params, group=None, direct=True):
+    ``segments``: optional list of parameter lists (a partition of ``params``) in the order their gradients become FINAL
+    during backward.  The bucket is laid out segment by segment and ``all_reduce_segment(i)`` reduces segment i on a side
+    stream as soon as the caller knows it is final, so that the transfer overlaps the rest of the backward pass
+    (the colour / RefColor slice travels while the SDF backward runs); ``all_reduce()`` reduces whatever has
+    not been reduced yet and joins the side stream.  ``params`` keeps its own order (optimizer state-dict order)."""
+
+    def __init__(self, params, group=None, direct=True, segments=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.direct = direct
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:          # parameters' .grad become views into the bucket: backward writes in place
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
-            p._fneus_direct_grad = bool(direct)
-            off += p.numel()
+        ids = {id(p) for p in self.params}
+        if segments is None:
+            segments = [self.params]
+        segments = [[p for p in seg if id(p) in ids] for seg in segments]
+        placed = [id(p) for seg in segments for p in seg]
+        if sorted(placed) != sorted(ids):
+            raise ValueError("GradBucket: `segments` must partition the trainable parameters")
+        self.offsets, self.seg_span, off = {}, [], 0
+        for seg in segments:
+            lo = off
+            for p in seg:          # parameters' .grad become views into the bucket: backward writes in place
+                self.offsets[id(p)] = off
+                p.grad = self.flat[off: off + p.numel()].view_as(p)
+                p._fneus_direct_grad = bool(direct)
+                off += p.numel()
+            self.seg_span.append((lo, off))
+        self._reduced = [False] * len(self.seg_span)
+        self._side = None
+
+    def offset_of(self, p):
+        return self.offsets[id(p)]
 
     def zero(self):
         self.flat.zero_()
 
+    def _world(self):
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def all_reduce_segment(self, i):
+        """Segment i is final: reduce it on the side stream (fork from the current stream; ``all_reduce`` joins)."""
+        if self._world() == 1 or self._reduced[i]:
+            return
+        lo, hi = self.seg_span[i]
+        if hi == lo:
+            self._reduced[i] = True
+            return
+        if self.flat.is_cuda:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.flat.device)
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                dist.all_reduce(self.flat[lo:hi], group=self.group)
+        else:
+            dist.all_reduce(self.flat[lo:hi], group=self.group)
+        self._reduced[i] = True
+
     def all_reduce(self):
-        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.flat, group=self.group)
+        """Reduce every segment not reduced yet (on the current stream) and wait for the side stream."""
+        if self._world() > 1:
+            pend = [sp for sp, done in zip(self.seg_span, self._reduced) if not done and sp[1] > sp[0]]
+            if len(pend) == len(self.seg_span):
+                dist.all_reduce(self.flat, group=self.group)
+            else:
+                for lo, hi in pend:
+                    dist.all_reduce(self.flat[lo:hi], group=self.group)
+            if self._side is not None and any(self._reduced):
+                torch.cuda.current_stream().wait_stream(self._side)
+        self._reduced = [False] * len(self.seg_span)
 
 
 class FlatAdam:
@@ -193,13 +246,11 @@ class FlatAdam:
         n = bucket.flat.numel()
         dev = bucket.flat.device
         self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
-        off = 0
         with torch.no_grad():
-            for p in bucket.params:
-                k = p.numel()
+            for p in bucket.params:                      # same placement as the gradient bucket
+                k, off = p.numel(), bucket.offset_of(p)
                 self.flat_p[off: off + k].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[off: off + k].view_as(p)
-                off += k
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
         self.state = torch.zeros(4, dtype=torch.float32, device=dev)
@@ -233,13 +284,12 @@ class FlatAdam:
         the reference's ``save_checkpoint`` / ``load_checkpoint`` (exp_runner.py:253-278) work unchanged and
         checkpoints move freely between the two implementations."""
         it = float(self._host_it)
-        state, off = {}, 0
+        state = {}
         for i, p in enumerate(self.bucket.params):
-            k = p.numel()
+            k, off = p.numel(), self.bucket.offset_of(p)
             if it > 0:
                 state[i] = {"step": torch.tensor(it), "exp_avg": self.m[off: off + k].view_as(p).clone(),
                             "exp_avg_sq": self.v[off: off + k].view_as(p).clone()}
-            off += k
         return {"state": state, "param_groups": [dict(self.param_groups[0], foreach=None, maximize=False,
                                                       capturable=False, differentiable=False, fused=None)]}
 
@@ -251,10 +301,10 @@ class FlatAdam:
         if len(order) != len(self.bucket.params):
             raise ValueError("FlatAdam.load_state_dict: %d parameters in the checkpoint, %d here"
                              % (len(order), len(self.bucket.params)))
-        steps, off = set(), 0
+        steps = set()
         with torch.no_grad():
             for idx, p in zip(order, self.bucket.params):
-                k = p.numel()
+                k, off = p.numel(), self.bucket.offset_of(p)
                 st = sd["state"].get(idx)
                 if st is None:
                     self.m[off: off + k].zero_()
@@ -266,7 +316,6 @@ class FlatAdam:
                     self.m[off: off + k].copy_(st["exp_avg"].reshape(-1))
                     self.v[off: off + k].copy_(st["exp_avg_sq"].reshape(-1))
                     steps.add(int(float(st["step"])))
-                off += k
         if len(steps) > 1:
             raise ValueError("FlatAdam.load_state_dict: parameters disagree on the step count %s" % sorted(steps))
         self._set_it(steps.pop() if steps else 0)

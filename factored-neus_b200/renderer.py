@@ -32,6 +32,13 @@ class NeuSRenderer:
         self.perturb = perturb
         self._tables = {}
 
+    def set_precision(self, mode):
+        """Precision of THIS renderer's networks ('fp32' | 'bf16'): a per-network configuration field, not a process
+        switch -- another renderer of the same process keeps its own."""
+        nets = [self.nerf, self.sdf_network, self.color_network, self.refColor_network, self.lvis_network,
+                self.indiLgt_network]
+        ops.set_precision(mode, [n for n in nets if n is not None and hasattr(n, "cfg")])
+
     # ------------------------------------------------------------------ helpers
     def _linspace(self, lo, hi, n, device):
         """Small constant tables come from torch.linspace on the device under test."""

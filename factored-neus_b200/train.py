@@ -29,7 +29,13 @@ class Stage1Trainer:
         self.iter_step = 0
         params = [p for n in self.networks for p in n.parameters()]
         self.device = params[0].device
-        self.bucket = GradBucket(params)
+        # everything but the SDF network and the outside NeRF has its gradient complete when the SDF backward starts: that
+        # slice is all-reduced on a side stream underneath it (parallel.GradBucket)
+        sdf_net, nerf_net = renderer.sdf_network, renderer.nerf
+        late = [p for n in self.networks if n is sdf_net or n is nerf_net for p in n.parameters()]
+        late_ids = {id(p) for p in late}
+        early = [p for p in params if id(p) not in late_ids]
+        self.bucket = GradBucket(params, segments=[early, late])
         self.optimizer = FlatAdam(self.bucket, lr=lr, lr_alpha=lr_alpha, warm_up_end=warm_up_end, end_iter=end_iter)
         self.use_graph = use_graph
         self._graph = None
@@ -63,7 +69,12 @@ class Stage1Trainer:
         out = self.renderer.render(ro, rd, near, far, background_rgb=bg, cos_anneal_ratio=self._car_dev)
         loss, stats = stage1_loss_sharded(self.renderer, out, rgb, m, self.surface_weight, self.igr_weight,
                                           self.mask_weight)
-        loss.backward()                                                  # the bucket is cleared by the optimiser step
+        from .ops import SdfValueGrad
+        SdfValueGrad.pre_backward_hook = lambda: self.bucket.all_reduce_segment(0)
+        try:
+            loss.backward()                                              # the bucket is cleared by the optimiser step
+        finally:
+            SdfValueGrad.pre_backward_hook = None
         self.bucket.all_reduce()
         self.optimizer.step()
         return loss

@@ -37,23 +37,28 @@ const char* fneus_status_string(int status);
 int fneus_abi_version(void);
 int fneus_num_sms(void);
 
-/* Compute precision of the dense layers: 0 = FP32 on CUDA cores (exactness anchor, <=1e-4 vs the reference,
- * default), 1 = BF16 operands on tcgen05 tensor cores with FP32 accumulation in TMEM (<=2e-2). */
-int fneus_set_precision(int mode);
-int fneus_get_precision(void);
-/* Bisect switches of the persistent tensor-core kernel (profiling only; results are wrong when non-zero). */
+/* Compute precision of the dense layers.  It is a field of every network configuration struct (no process-global
+ * state: two renderers of one process may run different precisions, and a call is fully described by its arguments):
+ *   FNEUS_PREC_FP32: FP32 on CUDA cores -- the exactness anchor, <= 1e-4 vs the reference;
+ *   FNEUS_PREC_TC  : tcgen05 tensor cores, FP32 accumulation in TMEM; forward-path operands FP16 (11-bit significand),
+ *                    backward-path operands BF16 -- <= 2e-2 and within 0.1 dB PSNR of the FP32 path after 1k iterations. */
+typedef enum { FNEUS_PREC_FP32 = 0, FNEUS_PREC_TC = 1 } fneus_precision;
+
+/* ---- development hooks (NOT part of the production surface: process-wide switches for bisecting and profiling) --------
+ * Bisect switches of the tensor-core kernels (results may be wrong when non-zero). */
 int fneus_debug_flags(int flags);
 /* debug: copy the first n entries (n <= 8192) of the fused-chain timeline buffer (clock stamps, flag bit 6) */
 int fneus_debug_timeline(unsigned long long* host_dst, int n);
-/* Test hook: one raw dense-layer contraction in the current precision mode.  kind 0: C[M,N] = A[M,K] W[N,K]^T
+/* Test hook: one raw dense-layer contraction in the given precision.  kind 0: C[M,N] = A[M,K] W[N,K]^T
  * + bias; kind 1: C[M,N] = A[M,K] W[K,N]; kind 2: C[N,K] += Y[M,N]^T A[M,K], bias[N] += colsum(Y) (W := Y). */
-int fneus_debug_gemm(int kind, const float* A, int lda, const float* W, int ldw, float* bias, long long M, int N,
-                     int K, float* C, int ldc, void* stream);
+int fneus_debug_gemm(int precision, int kind, const float* A, int lda, const float* W, int ldw, float* bias, long long M,
+                     int N, int K, float* C, int ldc, void* stream);
 
 /* Profiling hooks used by bench.py: when enabled every kernel launch is bracketed by CUDA events on its own
  * stream.  fneus_prof_collect synchronises those events and ADDS per-class milliseconds, launch counts and
  * algorithmic flops/bytes into arrays of length fneus_prof_classes() (classes: 0 gemm fwd, 1 gemm bwd-data,
- * 2 gemm bwd-weight, 3 sampling, 4 compositing, 5 elementwise, 6 tensor-core MLP), then resets. */
+ * 2 gemm bwd-weight, 3 sampling, 4 compositing, 5 elementwise, 6 single-layer tensor-core GEMMs, 7 SDF forward chain,
+ * 8 SDF backward chain, 9 ReLU chains, 10 grouped weight gradients), then resets.  Development hook like the above. */
 int fneus_prof_classes(void);
 int fneus_prof_enable(int on);
 int fneus_prof_collect(double* ms, long long* launches, double* flops, double* bytes);
@@ -80,6 +85,7 @@ typedef struct {
   int skip_layer; /* 4: input of this linear is cat([h, PE(x)])/sqrt(2); -1 = none */
   float scale;    /* 1.0 */
   float beta;     /* Softplus beta = 100 */
+  int precision; /* FNEUS_PREC_FP32 (CUDA-core exactness anchor) or FNEUS_PREC_TC (tcgen05 tensor cores) */
 } fneus_sdf_cfg;
 
 long long fneus_sdf_pack_floats(const fneus_sdf_cfg* cfg);
@@ -119,6 +125,7 @@ typedef struct {
   int n_layers;      /* 4 hidden -> n_layers+1 linears */
   int d_out;         /* 3 */
   int multires_view; /* 4 */
+  int precision; /* FNEUS_PREC_FP32 (CUDA-core exactness anchor) or FNEUS_PREC_TC (tcgen05 tensor cores) */
 } fneus_color_cfg;
 
 long long fneus_color_pack_floats(const fneus_color_cfg* cfg);
@@ -141,6 +148,7 @@ int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float*
 typedef struct {
   int d_feature; /* 256 */
   int d_hidden;  /* 256 */
+  int precision; /* FNEUS_PREC_FP32 (CUDA-core exactness anchor) or FNEUS_PREC_TC (tcgen05 tensor cores) */
 } fneus_ref_cfg;
 long long fneus_ref_pack_floats(const fneus_ref_cfg* cfg);
 long long fneus_ref_saved_floats(const fneus_ref_cfg* cfg, long long n_points);
@@ -164,6 +172,7 @@ typedef struct {
   int n_layers;
   int d_out;
   int last_act;
+  int precision; /* FNEUS_PREC_FP32 (CUDA-core exactness anchor) or FNEUS_PREC_TC (tcgen05 tensor cores) */
 } fneus_mlp_cfg;
 long long fneus_mlp_pack_floats(const fneus_mlp_cfg* cfg);
 long long fneus_mlp_saved_floats(const fneus_mlp_cfg* cfg, long long n_points);
@@ -185,6 +194,7 @@ typedef struct {
   int multires;      /* 10 */
   int multires_view; /* 4 */
   int skip;          /* 4: embedded input is concatenated after pts_linears[skip]; -1 = none */
+  int precision; /* FNEUS_PREC_FP32 (CUDA-core exactness anchor) or FNEUS_PREC_TC (tcgen05 tensor cores) */
 } fneus_nerf_cfg;
 long long fneus_nerf_pack_floats(const fneus_nerf_cfg* cfg);
 long long fneus_nerf_saved_floats(const fneus_nerf_cfg* cfg, long long n_points);
@@ -287,7 +297,7 @@ int fneus_gen_rays(const float* px, const float* py, const float* intrinsics_inv
  * rgb_out [m*n_dirs,3] = colour network at the secant root of the hit (0 without a hit).
  * The rays are processed in chunks of rays_per_chunk (rounded down to whole surface points); ws must hold
  * fneus_lvis_trace_workspace_floats(.., rays_per_chunk, ..) floats (16-byte aligned).  No host synchronisation, no
- * allocation: CUDA-graph capturable.  Uses the precision mode in force (fneus_set_precision). */
+ * allocation: CUDA-graph capturable.  Runs in sdf_cfg->precision. */
 long long fneus_lvis_trace_workspace_floats(const fneus_sdf_cfg* sdf_cfg, const fneus_color_cfg* color_cfg,
                                             long long rays_per_chunk, int n_coarse, int n_imp);
 int fneus_lvis_trace(const fneus_sdf_cfg* sdf_cfg, const float* sdf_wpack, const fneus_color_cfg* color_cfg,

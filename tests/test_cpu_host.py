@@ -163,3 +163,13 @@ def test_pack_weights_direct_mode_is_opt_in():
     assert p[0].grad is not None and not p[0]._fneus_direct_grad
     GradBucket(p)
     assert p[0]._fneus_direct_grad and p[1]._fneus_direct_grad
+
+
+def test_sqrt_free_radius_thresholds_are_exact():
+    """csrc/fneus_common.cuh radius_lt_1 / radius_lt_1p2: `sqrtf(x) < c` (what the reference's `norm < c` does) equals
+    `x < T(c)` with T(1) = 1 and T(1.2f) = 0x3FB851EC, checked on every float within 2^17 ulps of the thresholds."""
+    import numpy as np
+    for c, bits in ((1.0, 0x3F800000), (1.2, 0x3FB851EC)):
+        t = np.uint32(bits).view(np.float32)
+        a = np.arange(bits - (1 << 17), bits + (1 << 17), dtype=np.uint32).view(np.float32)
+        assert np.array_equal(np.sqrt(a) < np.float32(c), a < t)

@@ -84,7 +84,7 @@ def _worker(rank, world, port, B, precision, tmp):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precision,rtol", [("fp32", 2e-5), ("bf16", 1e-3)])
+@pytest.mark.parametrize("precision,rtol", [("fp32", 2e-5), ("bf16", 5e-5)])
 def test_two_rank_nccl_step_equals_full_batch(tmp_path, precision, rtol):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

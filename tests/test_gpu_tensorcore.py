@@ -508,3 +508,45 @@ def test_bf16_nerf_chain(bf16_mode, N):
         assert err <= BF16_TOL * max(1.0, scale), "nerf chain grad %s err %.3e (scale %.3e)" % (name, err, scale)
         assert err <= max(5e-2 * scale, 1.2 * err_l), "nerf chain grad %s: fused %.3e vs layered %.3e (scale %.3e)" % (
             name, err, err_l, scale)
+
+
+def test_bf16_step_is_reproducible_and_batch_invariant(bf16_mode):
+    """The same rays give the same per-ray results and the same gradients (up to the FP32 summation order of the weight
+    gradients) when run twice, and when run as two half batches whose gradients are added -- tiles, persistent-CTA tile
+    assignment and split boundaries of the weight-gradient kernel must not matter."""
+    states = syn.scene_states(seed=4, jitter=0.03)
+    B = 44
+    o, d, near, far = [t.to(DEV) for t in syn.make_rays(B, seed=1)]
+    true_rgb, mask = [t.to(DEV) for t in syn.make_targets(B, seed=2)]
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    R = m["renderer"]
+    nets = ("sdf", "color", "var", "ref")
+
+    def run(lo, hi, scale):
+        out = R.render(o[lo:hi], d[lo:hi], near[lo:hi], far[lo:hi], perturb_overwrite=0, cos_anneal_ratio=1.0)
+        loss = ((out["color_fine"] - true_rgb[lo:hi]).abs().sum() + (out["surface_color"] - true_rgb[lo:hi]).abs().sum() * 0.1
+                + out["gradient_error"] * 0.1 * (hi - lo)) * scale
+        loss.backward()
+        return out["color_fine"].detach().clone()
+
+    def grads():
+        g = {"%s.%s" % (n, k): p.grad.detach().clone() for n in nets for k, p in m[n].named_parameters()}
+        for n in nets:
+            for p in m[n].parameters():
+                p.grad = None
+        return g
+
+    c1 = run(0, B, 1.0); g1 = grads()
+    c2 = run(0, B, 1.0); g2 = grads()
+    assert torch.equal(c1, c2), "render is not reproducible"
+    ca = run(0, B // 2, 1.0); cb = run(B // 2, B, 1.0); g3 = grads()          # two half batches, gradients accumulate
+    assert torch.equal(torch.cat([ca, cb]), c1), "per-ray colours depend on the batch composition"
+    worst_rep, worst_split = 0.0, 0.0
+    for k in g1:
+        scale = max(1e-6, float(g1[k].abs().max()))
+        worst_rep = max(worst_rep, float((g1[k] - g2[k]).abs().max()) / scale)
+        worst_split = max(worst_split, float((g1[k] - g3[k]).abs().max()) / scale)
+    print("reproducibility: repeat %.3e, half batches %.3e (relative to each tensor's max)" % (worst_rep, worst_split))
+    assert worst_rep <= 2e-5, "gradients differ between identical runs: %.3e" % worst_rep
+    # (all samples of these rays lie inside the relaxed sphere, so the eikonal mean of the halves adds up to the full one)
+    assert worst_split <= 2e-5, "gradients depend on the batch composition: %.3e" % worst_split

