@@ -305,6 +305,8 @@ struct TcSmem {
   uint64_t full[WG_STAGES];
   uint64_t empty[WG_STAGES];
   uint64_t conv[WG_STAGES];           // weight-gradient kernel: stage converted to a common operand format
+  uint64_t fullc[WG_STAGES];          // ... and the landing of the operand that needs the conversion (it is fetched first,
+                                      // so that it is converted while the other operand is still in flight)
   uint64_t accum;
   uint32_t tmem_base;
 };
@@ -492,6 +494,26 @@ __device__ __forceinline__ void wgrad_to_bf16(uint8_t* tile, int bytes, int tid)
   }
 }
 
+// Warps 0-3, one stage: convert the FP16 image operand once IT has landed (`fullc`; the other operand may still be in
+// flight), then the bias column sums off the dY tile (an image: BF16 after the conversion, or never FP16 to begin with).
+__device__ __forceinline__ void wgrad_convert_and_bias(TcSmem* ctl, uint8_t* sAs, uint8_t* sBs, int s, uint32_t parity,
+                                                       bool conv_y, bool conv_x, int yblocks, int xblocks,
+                                                       bool bias_smem, bool yf, int tid, float& bcol) {
+  const bool any_conv = conv_y || conv_x;
+  if (any_conv) {
+    mbar_wait(&ctl->fullc[s], parity);
+    wgrad_to_bf16(conv_y ? sAs : sBs, (conv_y ? yblocks : xblocks) * 8192, tid);
+    fence_proxy_async();
+    mbar_arrive(&ctl->conv[s]);
+  }
+  if (bias_smem) {
+    // the dY tile must be complete (and, if it was converted, by ALL threads): conv when it was the converted operand
+    mbar_wait(conv_y ? &ctl->conv[s] : &ctl->full[s], parity);
+    bcol += wgrad_col_sum(sAs, tid, yf && !conv_y);
+    mbar_arrive(&ctl->empty[s]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // dW[(wout0+n)*ldw + wred + k] += sum_m dY[m][n] * A[m][k] ; db += sum_m dY[m][n]
 // grid.x = n_tiles(128) * k_chunks(256 per phase), grid.y = splits over m (multiples of 64 rows).
@@ -548,11 +570,15 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
   const int yblocks = y_img ? min(2, -ldy - nt * 2) : 0;
   const int xblocks = x_img ? min((Nc + 63) / 64, -a.ldm - (k0 >> 6)) : 0;
 
+  // `full` covers the produced operand and the image operand that needs no conversion; `fullc` the image operand that does
+  const bool ld_y_full = y_img && !conv_y, ld_x_full = x_img && !conv_x;
+  const bool use_full = need_prod || ld_y_full || ld_x_full;
   if (tid == 0) {
-    const int cnt = (need_prod ? 128 : 0) + ((y_img || x_img) ? 1 : 0);
+    const int cnt = (need_prod ? 128 : 0) + ((ld_y_full || ld_x_full) ? 1 : 0);
 #pragma unroll
     for (int s = 0; s < WG_ST; s++) {
-      mbar_init(&ctl->full[s], cnt); mbar_init(&ctl->empty[s], bias_smem ? 129 : 1); mbar_init(&ctl->conv[s], 128);
+      mbar_init(&ctl->full[s], cnt > 0 ? cnt : 1); mbar_init(&ctl->empty[s], bias_smem ? 129 : 1);
+      mbar_init(&ctl->conv[s], 128); mbar_init(&ctl->fullc[s], 1);
     }
     mbar_init(&ctl->accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -571,13 +597,31 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
         if (kb >= WG_ST) mbar_wait(&ctl->empty[s], ((kb / WG_ST) - 1) & 1);
         const long long mblk = (mbeg >> 6) + kb;               // 64-row block index
         const size_t half = (size_t)(mblk & 1) * 8192;
-        mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)(yblocks + xblocks) * 8192u);
-        for (int b = 0; b < yblocks; b++)
-          bulk_g2s(sA[s] + b * 8192, reinterpret_cast<const uint8_t*>(dY) + ((size_t)(mblk >> 1) * ykbs + nt * 2 + b) * 16384 + half,
-                   8192, &ctl->full[s]);
-        for (int b = 0; b < xblocks; b++)
-          bulk_g2s(sB[s] + b * 8192, reinterpret_cast<const uint8_t*>(a.mem) + ((size_t)(mblk >> 1) * xkbs + (k0 >> 6) + b) * 16384 + half,
-                   8192, &ctl->full[s]);
+        uint64_t* ybar = conv_y ? &ctl->fullc[s] : &ctl->full[s];
+        uint64_t* xbar = conv_x ? &ctl->fullc[s] : &ctl->full[s];
+        auto load_y = [&]() {
+          for (int b = 0; b < yblocks; b++)
+            bulk_g2s(sA[s] + b * 8192, reinterpret_cast<const uint8_t*>(dY) + ((size_t)(mblk >> 1) * ykbs + nt * 2 + b) * 16384 + half,
+                     8192, ybar);
+        };
+        auto load_x = [&]() {
+          for (int b = 0; b < xblocks; b++)
+            bulk_g2s(sB[s] + b * 8192, reinterpret_cast<const uint8_t*>(a.mem) + ((size_t)(mblk >> 1) * xkbs + (k0 >> 6) + b) * 16384 + half,
+                     8192, xbar);
+        };
+        if (any_conv) {                                          // the operand to convert goes first, on its own barrier
+          mbar_arrive_expect_tx(&ctl->fullc[s], (uint32_t)(conv_y ? yblocks : xblocks) * 8192u);
+          if (conv_y) load_y(); else load_x();
+          const int rest = conv_y ? xblocks : yblocks;
+          if (rest > 0) {
+            mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)rest * 8192u);
+            if (conv_y) load_x(); else load_y();
+          }
+        } else {
+          mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)(yblocks + xblocks) * 8192u);
+          load_y();
+          load_x();
+        }
       }
     }
   } else if (warp < 4) {
@@ -647,32 +691,12 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
         }
         fence_proxy_async();
         mbar_arrive(&ctl->full[s]);
-        if (any_conv || bias_smem) {
-          mbar_wait(&ctl->full[s], (kb / WG_ST) & 1);
-          if (any_conv) {
-            wgrad_to_bf16(conv_y ? sA[s] : sB[s], (conv_y ? yblocks : xblocks) * 8192, tid);
-            fence_proxy_async();
-            mbar_arrive(&ctl->conv[s]);
-          }
-          if (bias_smem) {
-            bcol += wgrad_col_sum(sA[s], tid, yf && !conv_y);
-            mbar_arrive(&ctl->empty[s]);
-          }
-        }
+        wgrad_convert_and_bias(ctl, sA[s], sB[s], s, (kb / WG_ST) & 1, conv_y, conv_x, yblocks, xblocks, bias_smem, yf, tid, bcol);
       }
     } else if (any_conv || bias_smem) {
       for (int kb = 0; kb < KB; kb++) {
         const int s = kb % WG_ST;
-        mbar_wait(&ctl->full[s], (kb / WG_ST) & 1);
-        if (any_conv) {
-          wgrad_to_bf16(conv_y ? sA[s] : sB[s], (conv_y ? yblocks : xblocks) * 8192, tid);
-          fence_proxy_async();
-          mbar_arrive(&ctl->conv[s]);
-        }
-        if (bias_smem) {
-          bcol += wgrad_col_sum(sA[s], tid, yf && !conv_y);
-          mbar_arrive(&ctl->empty[s]);
-        }
+        wgrad_convert_and_bias(ctl, sA[s], sB[s], s, (kb / WG_ST) & 1, conv_y, conv_x, yblocks, xblocks, bias_smem, yf, tid, bcol);
       }
     }
     mbar_wait(&ctl->accum, 0);
@@ -709,7 +733,8 @@ __device__ __forceinline__ void wgrad_body(const float* __restrict__ dY, int ldy
     const uint32_t idesc = make_idesc(Nc, 1, 1, yf && !conv_y && !no_conv, xf && !conv_x && !no_conv);
     for (int kb = 0; kb < KB; kb++) {
       const int s = kb % WG_ST;
-      mbar_wait(any_conv ? &ctl->conv[s] : &ctl->full[s], (kb / WG_ST) & 1);
+      if (use_full) mbar_wait(&ctl->full[s], (kb / WG_ST) & 1);
+      if (any_conv) mbar_wait(&ctl->conv[s], (kb / WG_ST) & 1);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(sA[s]), b_addr = smem_u32(sB[s]);
 #pragma unroll

@@ -65,3 +65,40 @@ def test_clock_sampler_windows_its_samples():
     assert r["window"] == "nearest samples" and r["samples"] == 3
     s.rows = []
     assert s.summary()["reasons"] == ["unavailable"]
+
+
+def test_round2_bench_lines_carry_every_baseline_configuration():
+    """Round 2: ONE line per run with the headline (wmask512) and the other BASELINE.json configurations under
+    extra_configs, each with its own roofline / e2e; the 1-GPU line also times the CPU port per configuration."""
+    base = None
+    for gpus in (1, 2, 4, 8):
+        d = json.loads(open(os.path.join(PROF, "r2_bench_line_%dgpu.json" % gpus)).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks", "step_time_stats"):
+            assert k in d, (gpus, k)
+        assert d["n_gpus"] == gpus and d["metric"] == "train_rays_per_s" and d["warmup"] >= 3
+        assert d["step_time_stats"]["n"] >= 200
+        assert d["roofline"]["traffic"] and d["roofline"]["traffic"] > 1e9           # live designed bytes, not a constant table
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        ex = d["extra_configs"]
+        for name in ("womask4096", "render_image", "grid512", "lvis"):
+            assert "error" not in ex[name], (gpus, name, ex[name])
+            assert ex[name]["value"] > 0 and 0.0 < ex[name]["roofline"]["frac"] < 1.0 and "e2e" in ex[name]
+        if gpus == 1:
+            base = d
+            assert d["cpu_baseline"]["kind"] == "port"
+            assert "bandwidth" in ex and len(ex["bandwidth"]["kernels"]) >= 5
+            assert all("cpu_baseline" in ex[n] for n in ("womask4096", "render_image", "grid512", "lvis"))
+        else:
+            assert d["value"] / (gpus * base["value"]) > 0.9                               # >= 7x at 8 GPUs
+            assert ex["womask4096"]["value"] / (gpus * base["extra_configs"]["womask4096"]["value"]) > 0.9
+
+
+def test_round2_ncu_exports_parse():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"),
+                          os.path.join(PROF, "r2_ncu_chain_full_raw.csv")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rows = [l for l in out.stdout.splitlines() if l.startswith("| `")]
+    assert len(rows) == 14 and any("sdf_chain_kernel<1>" in r for r in rows) and any("wgrad_group" in r for r in rows)
+    hist = open(os.path.join(PROF, "r2_sass_histogram.md")).read()
+    assert "UTCHMMA" in hist and "| **all tensor-core kernels**" in hist
