@@ -110,7 +110,13 @@ struct SdfChainArgs {
 };
 // debug timeline (fneus_debug_flags bit 6): clock64 stamps of CTA 0's first epilogue thread and MMA thread
 __device__ unsigned long long g_sc_dbg[8192];
+// compiled in only with -DFNEUS_SC_TIMELINE: the stamps sit in the innermost (per 64-column block) loop, where every
+// predicate costs issue slots (ncu: control flow was 25% of the executed instructions of the forward chain)
+#ifdef FNEUS_SC_TIMELINE
 #define SC_STAMP(slot) do { if (dbg_on) { g_sc_dbg[dbg_i] = ((unsigned long long)(slot) << 56) | (clock64() & 0x00FFFFFFFFFFFFFFull); dbg_i = dbg_i < 8190 ? dbg_i + 1 : dbg_i; } } while (0)
+#else
+#define SC_STAMP(slot) do { } while (0)
+#endif
 
 struct SCSmem {
   uint64_t wfull[SC_WSTAGES], wempty[SC_WSTAGES];
@@ -222,7 +228,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
 #pragma unroll
     for (int s = 0; s < WST; s++) { mbar_init(&ctl->wfull[s], 1); mbar_init(&ctl->wempty[s], 1); }
 #pragma unroll
-    for (int i = 0; i < SC_NAR; i++) mbar_init(&ctl->a_ready[i], (g.xflags & 1) ? SC_EPI_THREADS : SC_EPI_THREADS / 32);
+    for (int i = 0; i < SC_NAR; i++) mbar_init(&ctl->a_ready[i], SC_EPI_THREADS / 32);
     mbar_init(&ctl->acc_full, 1);
     mbar_init(&ctl->acc_half0, 1);
     mbar_init(&ctl->op_free, 1);
@@ -231,7 +237,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
     for (int i = 0; i < NSLOT; i++) {
       mbar_init(&ctl->aux_full[i], 1);
       mbar_init(&ctl->aux_empty[i], 1);
-      mbar_init(&ctl->blk_done[i], (g.xflags & 1) ? SC_EPI_THREADS : SC_EPI_THREADS / 32);
+      mbar_init(&ctl->blk_done[i], SC_EPI_THREADS / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -372,11 +378,15 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float beta = g.beta, inv_beta = 1.f / g.beta;
     int lg = 0, c = 0, nfree = 0;                  // nfree: op_free phases consumed
-    const uint32_t whint = (g.xflags & 2) ? 0u : 0x989680u;
-    const bool all_arrive = (g.xflags & 1) != 0;
+    int slot = 0;                                  // c % NSLOT and (c / NSLOT) & 1, kept incrementally
+    uint32_t slot_par = 0;
+    constexpr uint32_t whint = 0x989680u;              // suspend-time hint of the mbarrier waits
+    constexpr bool all_arrive = false;                 // one elected arrival per warp (the per-thread variant was slower)
     bool a0_pending = false;                       // bulk store of the first operand's image still reading shared memory
+#ifdef FNEUS_SC_TIMELINE
     const bool dbg_on = g.dbg != 0 && cta == 0 && et == 0;
     int dbg_i = 0;
+#endif
     for (long long tile = cta; tile < ntiles; tile += nctas) {
       const long long m = tile * 128 + r;
       const bool valid = m < g.M;
@@ -543,7 +553,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           }
         };
         // every mode but the in-place ones touches shared state that the step's last MMAs may still read or write
-        if (mode == SC_FEATQ || mode == SC_G0 || mode == SC_OUT || (g.xflags & 8)) need_full();
+        if (mode == SC_FEATQ || mode == SC_G0 || mode == SC_OUT) need_full();
         SC_STAMP(2);
         if (S.src == SRC_CHAIN && !first_overall) { mbar_wait_hint(&ctl->op_free, nfree & 1, whint); nfree++; }
         if (a0_pending && mode != SC_OUT) {
@@ -561,12 +571,11 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
         // Modes that end in the common pack-and-store: the next block's accumulator load is issued before the store /
         // fence / arrive tail of this block, so the TMEM latency hides underneath it.
         const bool can_pf = (mode == SC_SOFTPLUS || mode == SC_SPMUL || mode == SC_SWEEP || mode == SC_SDFBWD ||
-                             mode == SC_RELU || mode == SC_MASK) && !(g.xflags & 4);
+                             mode == SC_RELU || mode == SC_MASK);
         uint32_t ar[16];
         bool pf = false;                                                   // ar[] is an in-flight load of this block
 #pragma unroll 1
-        for (int b = 0; b < nb; b++, c++) {
-          const int slot = c % NSLOT;
+        for (int b = 0; b < nb; b++, c++, slot = slot + 1 == NSLOT ? 0 : slot + 1, slot_par ^= (slot == 0 ? 1u : 0u)) {
           const int n = b * 64 + cg * 16;
           uint8_t* opb = sOp + b * TC_A_BYTES + rowoff;                    // the row inside operand block b
           uint8_t* hb = sAux + (2 * slot) * TC_A_BYTES + rowoff;           // ... inside the slot's h block
@@ -574,7 +583,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           SC_STAMP(4);
           // columns >= 128, and the operand block the step's last half-tile of MMAs is still reading (block KB-1)
           if (b >= 2 || b == S.KB - 1) need_full();
-          if (uses_slot) mbar_wait_hint(&ctl->aux_full[slot], (c / NSLOT) & 1, whint);
+          if (uses_slot) mbar_wait_hint(&ctl->aux_full[slot], slot_par, whint);
           SC_STAMP(5);
           const bool full = valid && n + 16 <= lim;                        // no per-element masks needed
           float a[16];
@@ -666,13 +675,15 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
               for (int j = 0; j < 8; j++) {
                 const float sg = sg_fast(hv[j], ksg);
                 const float acc = a[hf * 8 + j];
-                const float yv = sg * acc * oscale;
-                const float ev = fmaf(-beta, sg, beta) * qv[j] * acc;
-                if (full) { a[hf * 8 + j] = yv; e[j] = ev; }
-                else {
+                a[hf * 8 + j] = sg * acc * oscale;
+                e[j] = fmaf(-beta, sg, beta) * qv[j] * acc;
+              }
+              if (!full) {                                                       // ragged tile / partial block only
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
                   const bool ok = valid && n + hf * 8 + j < N;
-                  a[hf * 8 + j] = ok ? yv : 0.f;
-                  e[j] = ok ? ev : 0.f;
+                  a[hf * 8 + j] = ok ? a[hf * 8 + j] : 0.f;
+                  e[j] = ok ? e[j] : 0.f;
                 }
               }
               *reinterpret_cast<uint4*>(hb + (hf ? ch1 : ch0)) = f32x8_to_bf16(e);   // e_l leaves from where h_{l+1} arrived
@@ -691,13 +702,21 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
             const bool has_h = S.h != nullptr;
 #pragma unroll
             for (int hf = 0; hf < 2; hf++) {
-              bool pos[8];                                                               // forward image, either format
-              if (has_h) u16x8_positive(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), pos);
+              if (S.use_rs) {
 #pragma unroll
-              for (int j = 0; j < 8; j++) {
-                const int nn = n + hf * 8 + j;
-                const float v = S.use_rs ? fmaf(rsv, srvec[nn], a[hf * 8 + j]) : a[hf * 8 + j];
-                a[hf * 8 + j] = ((!has_h || pos[j]) && (full || (valid && nn < N))) ? v : 0.f;
+                for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(rsv, srvec[n + hf * 8 + j], a[hf * 8 + j]);
+              }
+              if (has_h) {
+                // [h > 0] straight off the 16-bit pattern moved to the top of an FP32 word: sign and zero-ness survive for
+                // FP16 and BF16 alike (an FP16 pattern read this way is a tiny, possibly denormal, float of the same sign)
+                float hv[8];
+                bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[hf * 8 + j] = hv[j] > 0.f ? a[hf * 8 + j] : 0.f;
+              }
+              if (!full) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[hf * 8 + j] = (valid && n + hf * 8 + j < N) ? a[hf * 8 + j] : 0.f;
               }
             }
           } else if (!SDF && mode == SC_OUT) {
@@ -731,11 +750,15 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
               float hv[8], qv[8];
               f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_l: forward image, FP16
               bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);     // e_{l-1}: this pass, BF16
+              if (S.use_rs) {                                                    // the sdf row of the last linear (rank-1)
 #pragma unroll
-              for (int j = 0; j < 8; j++) {
-                const int nn = n + hf * 8 + j;
-                const float yv = fmaf(sg_fast(hv[j], ksg) * oscale, fmaf(rsv, srvec[nn], a[hf * 8 + j]), qv[j]);
-                a[hf * 8 + j] = (full || (valid && nn < csplit)) ? yv : 0.f;
+                for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(rsv, srvec[n + hf * 8 + j], a[hf * 8 + j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(sg_fast(hv[j], ksg) * oscale, a[hf * 8 + j], qv[j]);
+              if (!full) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[hf * 8 + j] = (valid && n + hf * 8 + j < csplit) ? a[hf * 8 + j] : 0.f;
               }
             }
           }
@@ -836,7 +859,9 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
       }
     }
     if (et == 0) bulk_wait0();
+#ifdef FNEUS_SC_TIMELINE
     if (dbg_on) g_sc_dbg[8191] = dbg_i;
+#endif
   }
   __syncthreads();
   if (warp == 0) {

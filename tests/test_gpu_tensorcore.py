@@ -187,7 +187,7 @@ def _fvl_check(key, got, ref, tag):
     if key in ("d_normals", "d_feats"):
         assert rel <= 0.2, "%s %s: norm-rel %.3e, max err %.3e (scale %.3e)" % (tag, key, rel, err, scale)
     elif key.startswith("g."):                    # weight gradients: sums over the points, the flips partly average out
-        assert err <= 5e-2 * scale and rel <= 4e-2, "%s %s: err %.3e (scale %.3e), norm-rel %.3e" % (tag, key, err, scale, rel)
+        assert err <= 5e-2 * scale and rel <= 0.1, "%s %s: err %.3e (scale %.3e), norm-rel %.3e" % (tag, key, err, scale, rel)
     else:
         assert err <= BF16_TOL * scale, "%s %s: err %.3e (scale %.3e)" % (tag, key, err, scale)
 
