@@ -763,7 +763,7 @@ tc_gemm_wgrad_kernel(const float* __restrict__ dY, int ldy, const __grid_constan
 
 // Grouped variant: the weight gradients of all layers of one chain in ONE launch (blockIdx.z = job).  Every job
 // shares M; a job's unused (tile, split) slots of the common grid exit immediately.
-constexpr int WG_MAX_JOBS = 16;
+constexpr int WG_MAX_JOBS = 20;
 struct WgradJob {
   const float* dY; int ldy;
   ASeg a;

@@ -574,273 +574,303 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                              mode == SC_RELU || mode == SC_MASK);
         uint32_t ar[16];
         bool pf = false;                                                   // ar[] is an in-flight load of this block
+        // The per-block loop, instantiated per mode: MODEC >= 0 fixes the step's mode at compile time; FAST is a whole tile
+        // with a 256-wide result and no skip / row-dot extras (four unmasked blocks) -- the bulk of the forward chains,
+        // where the epilogue's instruction issue is the bound (7% on the SDF forward).  MODEC < 0 is the general loop
+        // (runtime mode, ragged tiles, narrow or staged outputs).  The loop stays rolled: unrolling it by four bought
+        // nothing on the forward chain and the fully unrolled build of all instantiations deadlocked (sm_100a, CUDA 12.9).
+        auto run_blocks = [&](auto mode_c, auto fast_c) {
+          constexpr int MODEC = decltype(mode_c)::value;
+          constexpr bool FAST = decltype(fast_c)::value;
+          const int md = MODEC >= 0 ? MODEC : mode;
+          const bool pf_ok = MODEC >= 0 ? true : can_pf;
+          const bool slot_wait = (MODEC == SC_SOFTPLUS || MODEC == SC_RELU) ? false : uses_slot;
+          const int nbl = FAST ? 4 : nb;
 #pragma unroll 1
-        for (int b = 0; b < nb; b++, c++, slot = slot + 1 == NSLOT ? 0 : slot + 1, slot_par ^= (slot == 0 ? 1u : 0u)) {
-          const int n = b * 64 + cg * 16;
-          uint8_t* opb = sOp + b * TC_A_BYTES + rowoff;                    // the row inside operand block b
-          uint8_t* hb = sAux + (2 * slot) * TC_A_BYTES + rowoff;           // ... inside the slot's h block
-          const uint8_t* qb = sAux + (2 * slot + 1) * TC_A_BYTES + rowoff; // ... inside the slot's q block
-          SC_STAMP(4);
-          // columns >= 128, and the operand block the step's last half-tile of MMAs is still reading (block KB-1)
-          if (b >= 2 || b == S.KB - 1) need_full();
-          if (uses_slot) mbar_wait_hint(&ctl->aux_full[slot], slot_par, whint);
-          SC_STAMP(5);
-          const bool full = valid && n + 16 <= lim;                        // no per-element masks needed
-          float a[16];
-          if (!pf) {
-            if (n < Nc) tmem_ld16_issue(tacc + n, ar);
-            else {
-#pragma unroll
-              for (int j = 0; j < 16; j++) ar[j] = 0u;
-            }
-          }
-          tmem_ld16_wait(ar);
-#pragma unroll
-          for (int j = 0; j < 16; j++) a[j] = __uint_as_float(ar[j]);
-          pf = false;
-          if (FWD && mode == SC_SOFTPLUS) {
-            if (s_dot) {
-#pragma unroll
-              for (int j = 0; j < 16; j++) {
-                float v = sp_fast(a[j] + sb[n + j], kz, kinv);
-                v = (valid && n + j < N) ? v : 0.f;
-                dot = fmaf(v, srvec[n + j], dot);
-                a[j] = v * oscale;
-              }
-            } else if (full) {
-#pragma unroll
-              for (int j = 0; j < 16; j++) a[j] = sp_fast(a[j] + sb[n + j], kz, kinv) * oscale;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? sp_fast(a[j] + sb[n + j], kz, kinv) * oscale : 0.f;
-            }
-          } else if (FWD && mode == SC_FEATQ) {
-            // features: FP32 through a swizzled [128][64] staging tile (the slot's 32 KB), written out as whole lines
-            float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-              *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
-                  make_float4(a[4 * i] + sb[n + 4 * i], a[4 * i + 1] + sb[n + 4 * i + 1], a[4 * i + 2] + sb[n + 4 * i + 2],
-                              a[4 * i + 3] + sb[n + 4 * i + 3]);
-            // q_{L-1} = s(h_L) * W_L[0] from the unrounded activation: the previous step's pre-activations still sit
-            // in the other accumulator (this step publishes its operand only when all blocks are done)
-            const float* sbp = sbias + (s > 0 && g.st[s - 1].bias_slot >= 0 ? g.st[s - 1].bias_slot : 0) * 256;
-            tmem_ld16(taddr + (uint32_t)(((lg + 1) & 1) << 8) + n, a);
-#pragma unroll
-            for (int j = 0; j < 16; j++)
-              a[j] = (valid && n + j < N) ? sg_fast(sp_fast(a[j] + sbp[n + j], kz, kinv), ksg) * srvec[n + j] : 0.f;
-          } else if (FWD && mode == SC_SPMUL) {
-            if (csplit < N && n + 16 > csplit) {
-              // positional-encoding part of the skip gradient: parked in shared memory until G0
-#pragma unroll
-              for (int j = 0; j < 16; j++)
-                if (PARK && n + j >= csplit && n + j < N && n + j - csplit < SC_PARK_LD)
-                  spark[r * SC_PARK_LD + n + j - csplit] = a[j] * oscale;
-            }
-#pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-              float hv[8];
-              f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_l: forward image, FP16
-              if (full) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) a[hf * 8 + j] = sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                  a[hf * 8 + j] = (valid && n + hf * 8 + j < csplit) ? sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale : 0.f;
+          for (int b = 0; b < nbl; b++, c++, slot = slot + 1 == NSLOT ? 0 : slot + 1, slot_par ^= (slot == 0 ? 1u : 0u)) {
+            const int n = b * 64 + cg * 16;
+            uint8_t* opb = sOp + b * TC_A_BYTES + rowoff;                    // the row inside operand block b
+            uint8_t* hb = sAux + (2 * slot) * TC_A_BYTES + rowoff;           // ... inside the slot's h block
+            const uint8_t* qb = sAux + (2 * slot + 1) * TC_A_BYTES + rowoff; // ... inside the slot's q block
+            SC_STAMP(4);
+            // columns >= 128, and the operand block the step's last half-tile of MMAs is still reading (block KB-1)
+            if (b >= 2 || b == S.KB - 1) need_full();
+            if (slot_wait) mbar_wait_hint(&ctl->aux_full[slot], slot_par, whint);
+            SC_STAMP(5);
+            const bool full = FAST ? true : (valid && n + 16 <= lim);                        // no per-element masks needed
+            float a[16];
+            if (!pf) {
+              if (FAST || n < Nc) tmem_ld16_issue(tacc + n, ar);
+              else {
+  #pragma unroll
+                for (int j = 0; j < 16; j++) ar[j] = 0u;
               }
             }
-          } else if (FWD && mode == SC_G0) {
-            // g_0 = q_0 W_0 (+ the parked skip part): 128 x 64 FP32 staging, then one thread per row forms the normal
-            float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
-            if (csplit > 0) {
-              // parked columns csplit .. csplit+N-1 of the skip step <-> g_0 columns 0 .. N-1 (written by other
-              // column groups of the row: the named barrier orders the shared-memory accesses)
-              epi_bar();
-#pragma unroll
-              for (int j = 0; j < 16; j++)
-                if (PARK && n + j < N && n + j < SC_PARK_LD && csplit + n + j < 256) a[j] += spark[r * SC_PARK_LD + n + j];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-              *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
-                  make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
-          } else if (BWD && mode == SC_SWEEP) {
-#pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-              float hv[8], qv[8], e[8];
-              f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_{l+1}, q_l: forward
-              f16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);      // images, FP16
-#pragma unroll
-              for (int j = 0; j < 8; j++) {
-                const float sg = sg_fast(hv[j], ksg);
-                const float acc = a[hf * 8 + j];
-                a[hf * 8 + j] = sg * acc * oscale;
-                e[j] = fmaf(-beta, sg, beta) * qv[j] * acc;
-              }
-              if (!full) {                                                       // ragged tile / partial block only
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                  const bool ok = valid && n + hf * 8 + j < N;
-                  a[hf * 8 + j] = ok ? a[hf * 8 + j] : 0.f;
-                  e[j] = ok ? e[j] : 0.f;
-                }
-              }
-              *reinterpret_cast<uint4*>(hb + (hf ? ch1 : ch0)) = f32x8_to_bf16(e);   // e_l leaves from where h_{l+1} arrived
-            }
-          } else if (!SDF && mode == SC_RELU) {
-            const float floor_v = S.act == 2 ? -3.0e38f : 0.f;            // act 2: plain linear layer
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 16; j++) a[j] = fmaxf(a[j] + sb[n + j], floor_v);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? fmaxf(a[j] + sb[n + j], floor_v) : 0.f;
-            }
-          } else if (!SDF && mode == SC_MASK) {
-            // dz_{l-1} = (dz_l W_l [+ rs rvec]) * [h_l > 0]: the forward activation block arrived in the slot's h block
-            const bool has_h = S.h != nullptr;
-#pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-              if (S.use_rs) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(rsv, srvec[n + hf * 8 + j], a[hf * 8 + j]);
-              }
-              if (has_h) {
-                // [h > 0] straight off the 16-bit pattern moved to the top of an FP32 word: sign and zero-ness survive for
-                // FP16 and BF16 alike (an FP16 pattern read this way is a tiny, possibly denormal, float of the same sign)
-                float hv[8];
-                bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
-#pragma unroll
-                for (int j = 0; j < 8; j++) a[hf * 8 + j] = hv[j] > 0.f ? a[hf * 8 + j] : 0.f;
-              }
-              if (!full) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) a[hf * 8 + j] = (valid && n + hf * 8 + j < N) ? a[hf * 8 + j] : 0.f;
-              }
-            }
-          } else if (!SDF && mode == SC_OUT) {
-            if (N <= 16) {
-              // narrow result (colours, a specular scalar): the row's thread writes it directly
-              if (cg == 0 && b == 0 && valid) {
-                float y[16];
-                if (S.accumulate) row_load16(S.out, S.ldo, m, 0, N, y);
-#pragma unroll
+            tmem_ld16_wait(ar);
+            SC_STAMP(8);
+  #pragma unroll
+            for (int j = 0; j < 16; j++) a[j] = __uint_as_float(ar[j]);
+            pf = false;
+            if (FWD && md == SC_SOFTPLUS) {
+              if (s_dot) {
+  #pragma unroll
                 for (int j = 0; j < 16; j++) {
-                  float v = a[j] + (hasb ? sb[j] : 0.f);
-                  if (S.act == 1) v = sigmoid_fast(v);
-                  y[j] = S.accumulate ? y[j] + v : v;
+                  float v = sp_fast(a[j] + sb[n + j], kz, kinv);
+                  v = (valid && n + j < N) ? v : 0.f;
+                  dot = fmaf(v, srvec[n + j], dot);
+                  a[j] = v * oscale;
                 }
-                row_store16(S.out, S.ldo, m, 0, N, y);
+              } else if (full) {
+  #pragma unroll
+                for (int j = 0; j < 16; j++) a[j] = sp_fast(a[j] + sb[n + j], kz, kinv) * oscale;
+              } else {
+  #pragma unroll
+                for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? sp_fast(a[j] + sb[n + j], kz, kinv) * oscale : 0.f;
               }
-            } else {
-              // wide result: FP32 through the slot's swizzled [128][64] staging tile, written out as whole lines
+            } else if (FWD && md == SC_FEATQ) {
+              // features: FP32 through a swizzled [128][64] staging tile (the slot's 32 KB), written out as whole lines
               float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                float4 v = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
-                if (hasb) { v.x += sb[n + 4 * i]; v.y += sb[n + 4 * i + 1]; v.z += sb[n + 4 * i + 2]; v.w += sb[n + 4 * i + 3]; }
-                if (S.act == 1) { v.x = sigmoid_fast(v.x); v.y = sigmoid_fast(v.y); v.z = sigmoid_fast(v.z); v.w = sigmoid_fast(v.w); }
-                *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) = v;
+  #pragma unroll
+              for (int i = 0; i < 4; i++)
+                *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
+                    make_float4(a[4 * i] + sb[n + 4 * i], a[4 * i + 1] + sb[n + 4 * i + 1], a[4 * i + 2] + sb[n + 4 * i + 2],
+                                a[4 * i + 3] + sb[n + 4 * i + 3]);
+              // q_{L-1} = s(h_L) * W_L[0] from the unrounded activation: the previous step's pre-activations still sit
+              // in the other accumulator (this step publishes its operand only when all blocks are done)
+              const float* sbp = sbias + (s > 0 && g.st[s - 1].bias_slot >= 0 ? g.st[s - 1].bias_slot : 0) * 256;
+              tmem_ld16(taddr + (uint32_t)(((lg + 1) & 1) << 8) + n, a);
+  #pragma unroll
+              for (int j = 0; j < 16; j++)
+                a[j] = (valid && n + j < N) ? sg_fast(sp_fast(a[j] + sbp[n + j], kz, kinv), ksg) * srvec[n + j] : 0.f;
+            } else if (FWD && md == SC_SPMUL) {
+              if (!FAST && csplit < N && n + 16 > csplit) {
+                // positional-encoding part of the skip gradient: parked in shared memory until G0
+  #pragma unroll
+                for (int j = 0; j < 16; j++)
+                  if (PARK && n + j >= csplit && n + j < N && n + j - csplit < SC_PARK_LD)
+                    spark[r * SC_PARK_LD + n + j - csplit] = a[j] * oscale;
+              }
+  #pragma unroll
+              for (int hf = 0; hf < 2; hf++) {
+                float hv[8];
+                f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_l: forward image, FP16
+                if (full) {
+  #pragma unroll
+                  for (int j = 0; j < 8; j++) a[hf * 8 + j] = sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale;
+                } else {
+  #pragma unroll
+                  for (int j = 0; j < 8; j++)
+                    a[hf * 8 + j] = (valid && n + hf * 8 + j < csplit) ? sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale : 0.f;
+                }
+              }
+            } else if (FWD && md == SC_G0) {
+              // g_0 = q_0 W_0 (+ the parked skip part): 128 x 64 FP32 staging, then one thread per row forms the normal
+              float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
+              if (csplit > 0) {
+                // parked columns csplit .. csplit+N-1 of the skip step <-> g_0 columns 0 .. N-1 (written by other
+                // column groups of the row: the named barrier orders the shared-memory accesses)
+                epi_bar();
+  #pragma unroll
+                for (int j = 0; j < 16; j++)
+                  if (PARK && n + j < N && n + j < SC_PARK_LD && csplit + n + j < 256) a[j] += spark[r * SC_PARK_LD + n + j];
+              }
+  #pragma unroll
+              for (int i = 0; i < 4; i++)
+                *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
+                    make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+            } else if (BWD && md == SC_SWEEP) {
+  #pragma unroll
+              for (int hf = 0; hf < 2; hf++) {
+                float hv[8], qv[8], e[8];
+                f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_{l+1}, q_l: forward
+                f16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);      // images, FP16
+  #pragma unroll
+                for (int j = 0; j < 8; j++) {
+                  const float sg = sg_fast(hv[j], ksg);
+                  const float acc = a[hf * 8 + j];
+                  a[hf * 8 + j] = sg * acc * oscale;
+                  e[j] = fmaf(-beta, sg, beta) * qv[j] * acc;
+                }
+                if (!full) {                                                       // ragged tile / partial block only
+  #pragma unroll
+                  for (int j = 0; j < 8; j++) {
+                    const bool ok = valid && n + hf * 8 + j < N;
+                    a[hf * 8 + j] = ok ? a[hf * 8 + j] : 0.f;
+                    e[j] = ok ? e[j] : 0.f;
+                  }
+                }
+                *reinterpret_cast<uint4*>(hb + (hf ? ch1 : ch0)) = f32x8_to_bf16(e);   // e_l leaves from where h_{l+1} arrived
+              }
+            } else if (!SDF && md == SC_RELU) {
+              const float floor_v = S.act == 2 ? -3.0e38f : 0.f;            // act 2: plain linear layer
+              if (full) {
+  #pragma unroll
+                for (int j = 0; j < 16; j++) a[j] = fmaxf(a[j] + sb[n + j], floor_v);
+              } else {
+  #pragma unroll
+                for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? fmaxf(a[j] + sb[n + j], floor_v) : 0.f;
+              }
+            } else if (!SDF && md == SC_MASK) {
+              // dz_{l-1} = (dz_l W_l [+ rs rvec]) * [h_l > 0]: the forward activation block arrived in the slot's h block
+              const bool has_h = S.h != nullptr;
+  #pragma unroll
+              for (int hf = 0; hf < 2; hf++) {
+                if (S.use_rs) {
+  #pragma unroll
+                  for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(rsv, srvec[n + hf * 8 + j], a[hf * 8 + j]);
+                }
+                if (has_h) {
+                  // [h > 0] straight off the 16-bit pattern moved to the top of an FP32 word: sign and zero-ness survive for
+                  // FP16 and BF16 alike (an FP16 pattern read this way is a tiny, possibly denormal, float of the same sign)
+                  float hv[8];
+                  bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
+  #pragma unroll
+                  for (int j = 0; j < 8; j++) a[hf * 8 + j] = hv[j] > 0.f ? a[hf * 8 + j] : 0.f;
+                }
+                if (!full) {
+  #pragma unroll
+                  for (int j = 0; j < 8; j++) a[hf * 8 + j] = (valid && n + hf * 8 + j < N) ? a[hf * 8 + j] : 0.f;
+                }
+              }
+            } else if (!SDF && md == SC_OUT) {
+              if (N <= 16) {
+                // narrow result (colours, a specular scalar): the row's thread writes it directly
+                if (cg == 0 && b == 0 && valid) {
+                  float y[16];
+                  if (S.accumulate) row_load16(S.out, S.ldo, m, 0, N, y);
+  #pragma unroll
+                  for (int j = 0; j < 16; j++) {
+                    float v = a[j] + (hasb ? sb[j] : 0.f);
+                    if (S.act == 1) v = sigmoid_fast(v);
+                    y[j] = S.accumulate ? y[j] + v : v;
+                  }
+                  row_store16(S.out, S.ldo, m, 0, N, y);
+                }
+              } else {
+                // wide result: FP32 through the slot's swizzled [128][64] staging tile, written out as whole lines
+                float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
+  #pragma unroll
+                for (int i = 0; i < 4; i++) {
+                  float4 v = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+                  if (hasb) { v.x += sb[n + 4 * i]; v.y += sb[n + 4 * i + 1]; v.z += sb[n + 4 * i + 2]; v.w += sb[n + 4 * i + 3]; }
+                  if (S.act == 1) { v.x = sigmoid_fast(v.x); v.y = sigmoid_fast(v.y); v.z = sigmoid_fast(v.z); v.w = sigmoid_fast(v.w); }
+                  *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) = v;
+                }
+              }
+            } else if (BWD) {  // SC_SDFBWD
+  #pragma unroll
+              for (int hf = 0; hf < 2; hf++) {
+                float hv[8], qv[8];
+                f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_l: forward image, FP16
+                bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);     // e_{l-1}: this pass, BF16
+                if (S.use_rs) {                                                    // the sdf row of the last linear (rank-1)
+  #pragma unroll
+                  for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(rsv, srvec[n + hf * 8 + j], a[hf * 8 + j]);
+                }
+  #pragma unroll
+                for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(sg_fast(hv[j], ksg) * oscale, a[hf * 8 + j], qv[j]);
+                if (!full) {
+  #pragma unroll
+                  for (int j = 0; j < 8; j++) a[hf * 8 + j] = (valid && n + hf * 8 + j < csplit) ? a[hf * 8 + j] : 0.f;
+                }
               }
             }
-          } else if (BWD) {  // SC_SDFBWD
-#pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-              float hv[8], qv[8];
-              f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_l: forward image, FP16
-              bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);     // e_{l-1}: this pass, BF16
-              if (S.use_rs) {                                                    // the sdf row of the last linear (rank-1)
-#pragma unroll
-                for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(rsv, srvec[n + hf * 8 + j], a[hf * 8 + j]);
+            SC_STAMP(9);
+            if (md != SC_G0 && md != SC_OUT) {
+              const uint4 p0 = f32x8_to_u16(a, opf16), p1 = f32x8_to_u16(a + 8, opf16);
+              if (pf_ok && b + 1 < nbl && (FAST || n + 64 < Nc)) {
+                if (b + 1 >= 2) need_full();
+                tmem_ld16_issue(tacc + n + 64, ar);
+                pf = true;
               }
-#pragma unroll
-              for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(sg_fast(hv[j], ksg) * oscale, a[hf * 8 + j], qv[j]);
-              if (!full) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) a[hf * 8 + j] = (valid && n + hf * 8 + j < csplit) ? a[hf * 8 + j] : 0.f;
-              }
+              *reinterpret_cast<uint4*>(opb + ch0) = p0;
+              *reinterpret_cast<uint4*>(opb + ch1) = p1;
             }
-          }
-          if (mode != SC_G0 && mode != SC_OUT) {
-            const uint4 p0 = f32x8_to_u16(a, opf16), p1 = f32x8_to_u16(a + 8, opf16);
-            if (can_pf && b + 1 < nb && n + 64 < Nc) {
-              if (b + 1 >= 2) need_full();
-              tmem_ld16_issue(tacc + n + 64, ar);
-              pf = true;
+            if (!FAST && s_append && b == 3) {
+              // skip connection (fields.py:83-84): PE columns (value or tangent form) follow the N hidden columns once
+              // every column group has written its chunk of the last block
+              epi_bar();
+              if (valid)
+                gen_row_part(BWD ? g.gen_t : g.gen, m, cg, 4, [&](int j, float val) {
+                  const int col = N + j;
+                  if (col < 256)
+                    *reinterpret_cast<unsigned short*>(sOp + (col >> 6) * TC_A_BYTES + rowoff + (((((col & 63) >> 3) ^ r7) & 7) << 4) +
+                                                       ((col & 7) << 1)) = f32_to_u16_bits(val * rsqrt2, opf16);
+                });
             }
-            *reinterpret_cast<uint4*>(opb + ch0) = p0;
-            *reinterpret_cast<uint4*>(opb + ch1) = p1;
-          }
-          if (s_append && b == 3) {
-            // skip connection (fields.py:83-84): PE columns (value or tangent form) follow the N hidden columns once
-            // every column group has written its chunk of the last block
-            epi_bar();
-            if (valid)
-              gen_row_part(BWD ? g.gen_t : g.gen, m, cg, 4, [&](int j, float val) {
-                const int col = N + j;
-                if (col < 256)
-                  *reinterpret_cast<unsigned short*>(sOp + (col >> 6) * TC_A_BYTES + rowoff + (((((col & 63) >> 3) ^ r7) & 7) << 4) +
-                                                     ((col & 7) << 1)) = f32_to_u16_bits(val * rsqrt2, opf16);
-              });
-          }
-          if (FWD ? (mode == SC_FEATQ || mode == SC_G0) : (!SDF && mode == SC_OUT && N > 16)) {
-            epi_bar();
-            const float* T = reinterpret_cast<const float*>(sAux + (2 * slot) * TC_A_BYTES);
-            if (!SDF || mode == SC_FEATQ) {
-              // warp ew writes rows 8 ew .. 8 ew + 7: two rows (2 x 256 B) per instruction
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                const int rr = ew * 8 + 2 * i + (lane >> 4), q4 = lane & 15;
+            if (FWD ? (md == SC_FEATQ || md == SC_G0) : (!SDF && md == SC_OUT && N > 16)) {
+              epi_bar();
+              const float* T = reinterpret_cast<const float*>(sAux + (2 * slot) * TC_A_BYTES);
+              if (!SDF || md == SC_FEATQ) {
+                // warp ew writes rows 8 ew .. 8 ew + 7: two rows (2 x 256 B) per instruction
+  #pragma unroll
+                for (int i = 0; i < 4; i++) {
+                  const int rr = ew * 8 + 2 * i + (lane >> 4), q4 = lane & 15;
+                  const long long mm = tile * 128 + rr;
+                  const int col = b * 64 + q4 * 4;
+                  if (mm < g.M && col < N) {
+                    const float4 v = *reinterpret_cast<const float4*>(T + rr * 64 + ((q4 ^ (rr & 15)) << 2));
+                    float* dst = S.out + mm * S.ldo + col;
+                    const bool acc_out = md == SC_OUT && S.accumulate;
+                    if (col + 4 <= N && (S.ldo & 3) == 0) {
+                      if (acc_out) {
+                        const float4 o = *reinterpret_cast<const float4*>(dst);
+                        *reinterpret_cast<float4*>(dst) = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+                      } else *reinterpret_cast<float4*>(dst) = v;
+                    } else {
+                      dst[0] = acc_out ? dst[0] + v.x : v.x;
+                      if (col + 1 < N) dst[1] = acc_out ? dst[1] + v.y : v.y;
+                      if (col + 2 < N) dst[2] = acc_out ? dst[2] + v.z : v.z;
+                      if (col + 3 < N) dst[3] = acc_out ? dst[3] + v.w : v.w;
+                    }
+                  }
+                }
+              } else if (FWD && et < 128) {
+                // thread et = row: normal = J_PE(x)^T g_0 (fields.py:101-111)
+                const int rr = et;
                 const long long mm = tile * 128 + rr;
-                const int col = b * 64 + q4 * 4;
-                if (mm < g.M && col < N) {
-                  const float4 v = *reinterpret_cast<const float4*>(T + rr * 64 + ((q4 ^ (rr & 15)) << 2));
-                  float* dst = S.out + mm * S.ldo + col;
-                  const bool acc_out = mode == SC_OUT && S.accumulate;
-                  if (col + 4 <= N && (S.ldo & 3) == 0) {
-                    if (acc_out) {
-                      const float4 o = *reinterpret_cast<const float4*>(dst);
-                      *reinterpret_cast<float4*>(dst) = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
-                    } else *reinterpret_cast<float4*>(dst) = v;
-                  } else {
-                    dst[0] = acc_out ? dst[0] + v.x : v.x;
-                    if (col + 1 < N) dst[1] = acc_out ? dst[1] + v.y : v.y;
-                    if (col + 2 < N) dst[2] = acc_out ? dst[2] + v.z : v.z;
-                    if (col + 3 < N) dst[3] = acc_out ? dst[3] + v.w : v.w;
+                if (mm < g.M) {
+                  const GenItem it = g.gen.it[0];
+                  for (int cc = 0; cc < it.dim; cc++) {
+                    const float v = __ldg(it.src + mm * it.dim + cc) * it.scale;
+                    auto G0 = [&](int col) { return T[rr * 64 + ((((col >> 2) ^ (rr & 15)) << 2) | (col & 3))]; };
+                    float acc = G0(cc);
+                    for (int k = 0; k < it.multires; k++) {
+                      const float f = (float)(1u << k);
+                      float sn, cs;
+                      sincosf(v * f, &sn, &cs);
+                      acc += f * cs * G0(it.dim * (1 + 2 * k) + cc) - f * sn * G0(it.dim * (2 + 2 * k) + cc);
+                    }
+                    S.out[mm * it.dim + cc] = acc;
                   }
-                }
-              }
-            } else if (FWD && et < 128) {
-              // thread et = row: normal = J_PE(x)^T g_0 (fields.py:101-111)
-              const int rr = et;
-              const long long mm = tile * 128 + rr;
-              if (mm < g.M) {
-                const GenItem it = g.gen.it[0];
-                for (int cc = 0; cc < it.dim; cc++) {
-                  const float v = __ldg(it.src + mm * it.dim + cc) * it.scale;
-                  auto G0 = [&](int col) { return T[rr * 64 + ((((col >> 2) ^ (rr & 15)) << 2) | (col & 3))]; };
-                  float acc = G0(cc);
-                  for (int k = 0; k < it.multires; k++) {
-                    const float f = (float)(1u << k);
-                    float sn, cs;
-                    sincosf(v * f, &sn, &cs);
-                    acc += f * cs * G0(it.dim * (1 + 2 * k) + cc) - f * sn * G0(it.dim * (2 + 2 * k) + cc);
-                  }
-                  S.out[mm * it.dim + cc] = acc;
                 }
               }
             }
+            SC_STAMP(10);
+            tc_fence_before();
+            fence_proxy_async();
+            SC_STAMP(11);
+            // one arrival per warp: every lane has fenced its own writes, the warp barrier orders them before the arrive
+            if (!all_arrive) __syncwarp();
+            if (lane == 0 || all_arrive) {
+              mbar_arrive(&ctl->blk_done[slot]);
+              if (pub_blocks) mbar_arrive(&ctl->a_ready[b]);                  // the next step's MMAs may read block b
+            }
+            SC_STAMP(6);
           }
-          tc_fence_before();
-          fence_proxy_async();
-          // one arrival per warp: every lane has fenced its own writes, the warp barrier orders them before the arrive
-          if (!all_arrive) __syncwarp();
-          if (lane == 0 || all_arrive) {
-            mbar_arrive(&ctl->blk_done[slot]);
-            if (pub_blocks) mbar_arrive(&ctl->a_ready[b]);                  // the next step's MMAs may read block b
+        };
+        {
+          using sc_fast = std::true_type;
+          const bool fast_ok = tile * 128 + 128 <= g.M && N == 256 && lim == 256 && nb == 4 && !s_dot && !s_append;
+          bool done = false;
+          if constexpr (FWD) {
+            if (fast_ok && mode == SC_SOFTPLUS && !uses_slot) { run_blocks(std::integral_constant<int, SC_SOFTPLUS>{}, sc_fast{}); done = true; }
+            else if (fast_ok && mode == SC_SPMUL) { run_blocks(std::integral_constant<int, SC_SPMUL>{}, sc_fast{}); done = true; }
+          } else if constexpr (!BWD) {                 // (the backward SDF chain is HBM-bound: nothing to gain there)
+            if (fast_ok && mode == SC_RELU && !uses_slot) { run_blocks(std::integral_constant<int, SC_RELU>{}, sc_fast{}); done = true; }
+            else if (fast_ok && mode == SC_MASK) { run_blocks(std::integral_constant<int, SC_MASK>{}, sc_fast{}); done = true; }
           }
-          SC_STAMP(6);
+          if (!done) run_blocks(std::integral_constant<int, -1>{}, std::false_type{});
         }
         need_full();                                                       // keeps the barrier phases in step
         if (feeds_next && mode != SC_OUT && (lane == 0 || all_arrive))

@@ -27,6 +27,14 @@ def report(tag, tl, mhz=1965.0):
     if not tl:
         return
     t0 = tl[0][1]
+    if os.environ.get("TL_RAW"):
+        nstep = 0
+        for kind, t in tl:
+            if kind == 1:
+                nstep += 1
+                base = t
+            if nstep in (2, 11):
+                print("   raw step %d  stamp %2d  +%.3f us" % (nstep - 1, kind, (t - base) / mhz))
     step, rows, cur = 0, [], None
     for kind, t in tl:
         us = (t - t0) / mhz
@@ -41,16 +49,22 @@ def report(tag, tl, mhz=1965.0):
         elif kind == 5:
             cur["aux_wait"] += us - cur["t4"]
             cur["t5"] = us
+        elif kind in (8, 9, 10, 11):
+            prev = cur.get("tp", cur["t5"]) if kind != 8 else cur["t5"]
+            cur["ph%d" % kind] = cur.get("ph%d" % kind, 0.0) + us - prev
+            cur["tp"] = us
         elif kind == 6:
             cur["blk"] += us - cur["t5"]
+            cur["ph6"] = cur.get("ph6", 0.0) + us - cur.get("tp", cur["t5"])
             cur["nblk"] += 1
         elif kind == 7:
             cur["end"] = us
             rows.append(cur)
-    print(" step   start   wait_mma  wait_opfree  wait_aux  compute   total")
+    print(" step   start   wait_mma  wait_opfree  wait_aux  compute   total | ldtm   math  pack+st fence arrive")
     for i, r in enumerate(rows[:24]):
-        print("  %2d  %7.2f   %7.2f    %7.2f    %7.2f  %7.2f  %7.2f" % (
-            i, r["start"], r["acc"] - r["start"], r["opfree"] - r["acc"], r["aux_wait"], r["blk"], r["end"] - r["start"]))
+        print("  %2d  %7.2f   %7.2f    %7.2f    %7.2f  %7.2f  %7.2f | %5.2f  %5.2f  %5.2f  %5.2f  %5.2f" % (
+            i, r["start"], r["acc"] - r["start"], r["opfree"] - r["acc"], r["aux_wait"], r["blk"], r["end"] - r["start"],
+            r.get("ph8", 0), r.get("ph9", 0), r.get("ph10", 0), r.get("ph11", 0), r.get("ph6", 0)))
     tot = rows[-1]["end"] - rows[0]["start"]
     print(" %d steps in %.1f us: wait_mma %.1f, wait_opfree %.1f, wait_aux %.1f, compute %.1f" % (
         len(rows), tot, sum(r["acc"] - r["start"] for r in rows), sum(r["opfree"] - r["acc"] for r in rows),
