@@ -21,12 +21,13 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 class SdfCfg(Structure):
     _fields_ = [("d_in", c_int), ("d_hidden", c_int), ("n_layers", c_int), ("d_out", c_int),
-                ("multires", c_int), ("skip_layer", c_int), ("scale", c_float), ("beta", c_float), ("precision", c_int)]
+                ("multires", c_int), ("skip_layer", c_int), ("scale", c_float), ("beta", c_float), ("precision", c_int),
+                ("feat_image", c_int)]
 
 
 class ColorCfg(Structure):
     _fields_ = [("d_feature", c_int), ("d_hidden", c_int), ("n_layers", c_int), ("d_out", c_int),
-                ("multires_view", c_int), ("precision", c_int)]
+                ("multires_view", c_int), ("precision", c_int), ("feat_image", c_int)]
 
 
 class RefCfg(Structure):
@@ -102,6 +103,11 @@ _SIGNATURES = {
     "fneus_prof_classes": (c_int, []),
     "fneus_prof_enable": (c_int, [c_int]),
     "fneus_prof_collect": (c_int, [_P, _P, _P, _P]),
+    "fneus_image_bytes": (_LL, [_LL, c_int]),
+    "fneus_image_gather_rows": (c_int, [_P, c_int, c_int, _P, _LL, _P, _P]),
+    "fneus_image_scatter_add_rows": (c_int, [_P, c_int, _P, _LL, _P, _P]),
+    "fneus_sdf_feat_image_ok": (c_int, [POINTER(SdfCfg)]),
+    "fneus_color_feat_image_ok": (c_int, [POINTER(ColorCfg)]),
     "fneus_pack_max_segments": (c_int, []),
     "fneus_pack_fwd": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P]),
     "fneus_pack_bwd": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),

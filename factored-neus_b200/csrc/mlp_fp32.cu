@@ -372,7 +372,8 @@ static void sdf_chain_value_launch(const fneus_sdf_cfg* c, const SdfPlan& p, con
   if (feat_out) {
     SdfStep S = sdf_step(SC_FEATQ, im.F[L], cdiv(p.in[L], TC_BK), c->d_out - 1, 0);
     S.bias = w + p.boff[L] + 1; S.bias_slot = L;
-    S.out = feat_out; S.ldo = c->d_out - 1;
+    if (c->feat_image) S.e_out = feat_out;                      // FP16 operand image instead of FP32 rows
+    else { S.out = feat_out; S.ldo = c->d_out - 1; }
     g.st[ns++] = S;
     flops += 2.0 * (double)M * p.in[L] * (c->d_out - 1);
   }
@@ -502,6 +503,7 @@ int fneus_sdf_fwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     FNEUS_CHECK_LAUNCH();
     return FNEUS_OK;
   }
+  if (cfg->feat_image && feat_out) return FNEUS_ERR_UNSUPPORTED;   // the image hand-over exists on the chain kernel only
   for (long long m0 = 0; m0 < n; m0 += chunk) {
     long long M = n - m0 < chunk ? n - m0 : chunk;
     sdf_zero_images(p, scratch, 2LL * sdf_buf_floats(p, M), M, st);
@@ -573,6 +575,7 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
   const bool use_chain = sdf_chain_ok(cfg, p) && normal_out != nullptr;
   SdfImgs im = sdf_make_images(cfg, p, wpack, true, true, normal_out != nullptr, false, ar, st, use_chain ? 1 : 0);
   if (use_chain && (im.F[p.L] == nullptr || im.B[0] == nullptr)) return FNEUS_ERR_WORKSPACE;
+  if (cfg->feat_image && (!use_chain || cfg->d_out - 1 != 256)) return FNEUS_ERR_UNSUPPORTED;
   if (use_chain) {
     const int L = p.L;
     const float rsqrt2 = 0.70710678118654752440f, sqrt2 = 1.41421356237309504880f;
@@ -593,7 +596,8 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
     {
       SdfStep S = sdf_step(SC_FEATQ, im.F[L], cdiv(p.in[L], TC_BK), cfg->d_out - 1, 0);
       S.bias = wpack + p.boff[L] + 1; S.bias_slot = L;
-      S.out = feat_out; S.ldo = cfg->d_out - 1;
+      if (cfg->feat_image) S.e_out = feat_out;                  // FP16 operand image instead of FP32 rows
+      else { S.out = feat_out; S.ldo = cfg->d_out - 1; }
       S.img_out = b.Q[L - 1];
       S.sync_stores = normal_out ? 1 : 0;             // the reverse chain reads the h images back
       g.st[ns++] = S;
@@ -662,6 +666,13 @@ int fneus_sdf_fwd_grad(const fneus_sdf_cfg* cfg, const float* wpack, const float
   return FNEUS_OK;
 }
 
+int fneus_sdf_feat_image_ok(const fneus_sdf_cfg* cfg) {
+  if (!cfg) return 0;
+  PrecScope prec_scope_(cfg->precision);
+  SdfPlan p = sdf_plan(cfg);
+  return (p.ok && sdf_chain_ok(cfg, p) && cfg->d_out - 1 == 256) ? 1 : 0;
+}
+
 int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, long long M, const float* d_sdf,
                   const float* d_feat, const float* d_normal, float* saved, float* scratch, float* d_wpack,
                   void* stream) {
@@ -693,6 +704,7 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
   // same predicate as fneus_sdf_fwd_grad: the forward pass of a value + normal graph left FP16 images
   const bool fwd_was_chain = sdf_chain_ok(cfg, p) && d_normal != nullptr;
   if (fwd_was_chain && (!d_feat || b.H[0] == nullptr || im.F[0] == nullptr || im.B[L] == nullptr)) return FNEUS_ERR_UNSUPPORTED;
+  if (cfg->feat_image && !fwd_was_chain) return FNEUS_ERR_UNSUPPORTED;
   if (fwd_was_chain) {
     float* G[20]; float* E[20]; float* A[20];
     for (int l = 0; l <= L; l++) G[l] = scratch + (long long)l * bf;
@@ -728,7 +740,7 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     g.nsteps = ns;
     g.gen = sdf_gen(cfg, x, nullptr); g.gen_t = sdf_gen(cfg, x, d_normal);
     g.pe_img = G[0];
-    g.mem = d_feat; g.ldm = cfg->d_out - 1; g.kmem = cfg->d_out - 1;
+    g.mem = d_feat; g.ldm = cfg->feat_image ? -4 : cfg->d_out - 1; g.kmem = cfg->d_out - 1;
     g.rvec = wpack + p.woff[L]; g.b_last = wpack + p.boff[L];
     g.rs = d_sdf; g.rscale = 1.f / cfg->scale;
     g.beta = cfg->beta; g.M = M; g.dbg = (tc_debug_flags() & 64) ? 1 : 0;
@@ -743,7 +755,7 @@ int fneus_sdf_bwd(const fneus_sdf_cfg* cfg, const float* wpack, const float* x, 
     for (int l = L - 1; l >= 0; l--)
       wg.add(A[l], p.ldout[l], aseg_mem(l == 0 ? b.H[0] : b.H[l], l == 0 ? -1 : p.ldin[l], p.in[l]), d_wpack + p.woff[l],
              p.in[l], 0, d_wpack + p.boff[l], p.out[l], st, 0, /*h_l: forward image*/ 1);
-    wg.add(d_feat, cfg->d_out - 1, aseg_mem(b.H[L], p.ldin[L], p.in[L]), d_wpack + p.woff[L], p.in[L], 1,
+    wg.add(d_feat, cfg->feat_image ? -4 : cfg->d_out - 1, aseg_mem(b.H[L], p.ldin[L], p.in[L]), d_wpack + p.woff[L], p.in[L], 1,
            d_wpack + p.boff[L], cfg->d_out - 1, st, 0, 1);
     wg.flush(st);
     launch_colsum(G[L], p.ldin[L], p.in[L], nullptr, 1.f, d_wpack + p.woff[L], nullptr, M, st);

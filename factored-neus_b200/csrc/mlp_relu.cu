@@ -116,6 +116,7 @@ static int relu_chain_fwd(const float* w, const Lin* lin, int n_lin, const ASeg&
     sdf_chain_launch(g, flops, st, FAM_RELU);
     return FNEUS_OK;
   }
+  if (a0.ldm < 0) return FNEUS_ERR_UNSUPPORTED;              // an image first operand exists on the fused chain only
   for (int l = 0; l < n_lin; l++) {
     ASeg a = l == 0 ? a0 : aseg_mem(Hs[l], ldh, lin[l].in);
     Epi e = epi_default();
@@ -143,6 +144,7 @@ static int relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin, 
   const bool fused = fwd_fused && lin[n_lin - 1].out <= TC_BK * SC_OPB_RELU && n_lin >= 2 &&
                      (ld_small & 3) == 0 && (ld_feats & 3) == 0;
   if (fwd_fused && !fused) return FNEUS_ERR_UNSUPPORTED;
+  if ((a0.ldm < 0 || ld_feats < 0) && (!fused || accumulate_feats)) return FNEUS_ERR_UNSUPPORTED;
   if (fused) {
     // ---- weight images: MN-major W_l for l >= 1; layer 0 split into its feature and generated column ranges ----
     const uint8_t* img[16];
@@ -178,7 +180,8 @@ static int relu_chain_bwd(const float* w, float* dw, const Lin* lin, int n_lin, 
       }
       if (img_feat) {
         SdfStep S = sdf_step(SC_OUT, img_feat, cdiv(lin[0].out, TC_BK), a0.kmem, 1);
-        S.out = d_feats; S.ldo = ld_feats; S.accumulate = accumulate_feats;
+        if (ld_feats < 0) { S.e_out = d_feats; }                    // BF16 operand image (feat_image): see SC_OUT
+        else { S.out = d_feats; S.ldo = ld_feats; S.accumulate = accumulate_feats; }
         g.st[ns++] = S;
         flops += 2.0 * (double)M * a0.kmem * lin[0].out;
       }
@@ -288,7 +291,8 @@ static ASeg color_a0(const fneus_color_cfg* c, const ColorPlan& p, const float* 
   gen_add(g, pts, 3, 0);
   gen_add(g, view, 3, c->multires_view);
   gen_add(g, nrm, 3, 0);
-  return aseg_gen_mem(g, 0, feats, c->d_feature, c->d_feature, p.gen_cols);
+  // feat_image: the features arrive as the SDF chain's FP16 operand image (one tile = 4 blocks of 128 x 64)
+  return aseg_gen_mem(g, 0, feats, c->feat_image ? -4 : c->d_feature, c->d_feature, p.gen_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -446,6 +450,17 @@ long long fneus_color_scratch_floats(const fneus_color_cfg* cfg, long long n) {
   return color_scratch_main(cfg, p, n) + (long long)(relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols) / 4) + 256;
 }
 
+int fneus_color_feat_image_ok(const fneus_color_cfg* cfg) {
+  if (!cfg) return 0;
+  PrecScope prec_scope_(cfg->precision);
+  ColorPlan p = color_plan(cfg);
+  if (!p.ok || cfg->d_feature != 256) return 0;
+  fneus_color_cfg c = *cfg;
+  c.feat_image = 1;
+  const ASeg a0 = color_a0(&c, p, nullptr, nullptr, nullptr, nullptr);
+  return (relu_fwd_fused(p.lin, p.n_lin, a0, p.ldh, EPI_SIGMOID) && p.lin[p.n_lin - 1].out <= TC_BK * SC_OPB_RELU) ? 1 : 0;
+}
+
 int fneus_color_fwd(const fneus_color_cfg* cfg, const float* wpack, const float* points, const float* normals,
                     const float* view_dirs, const float* feats, long long M, float* rgb_out, float* saved,
                     float* scratch, void* stream) {
@@ -492,7 +507,7 @@ int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float*
   prof_end(st);
   ImgArena ar = arena_at(scratch + color_scratch_main(cfg, p, M), relu_chain_img_bytes(p.lin, p.n_lin, p.gen_cols));
   { const int rc_ = relu_chain_bwd(wpack, d_wpack, p.lin, p.n_lin, color_a0(cfg, p, points, normals, view_dirs, feats), Hs, p.ldh,
-                 alast, 4, ab0, hf, d_normals ? dsmall : nullptr, lds, d_feats, cfg->d_feature, 0, M, st, ar,
+                 alast, 4, ab0, hf, d_normals ? dsmall : nullptr, lds, d_feats, cfg->feat_image ? -4 : cfg->d_feature, 0, M, st, ar,
                  p.img ? align1k(saved) + (long long)cfg->n_layers * hf : nullptr); if (rc_) return rc_; }
   if (d_normals) {
     prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);

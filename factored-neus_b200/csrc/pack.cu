@@ -71,6 +71,55 @@ __global__ void pack_bwd_kernel(PackArgs a, const float* __restrict__ dflat) {
   }
 }
 
+// ---- rows of a 16-bit operand image <-> FP32 rows (include/fneus.h: fneus_image_*) ----
+// one thread per 8 consecutive columns (one 16-byte chunk of the swizzled row)
+__global__ void image_gather_rows_kernel(const uint8_t* __restrict__ img, int is_fp16, int kbs, int n_cols,
+                                         const long long* __restrict__ rows, long long n_sel, float* __restrict__ out) {
+  const int cpr = n_cols >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sel * cpr) return;
+  const long long sel = i / cpr, m = rows[sel];
+  const int k = (int)(i % cpr) * 8;
+  const uint4 u = *reinterpret_cast<const uint4*>(img + img_off(m, k, kbs));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  float v[8];
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    if (is_fp16) {
+      const float2 f = unpack_f16x2(w[t]);
+      v[2 * t] = f.x; v[2 * t + 1] = f.y;
+    } else {
+      v[2 * t] = __uint_as_float(w[t] << 16); v[2 * t + 1] = __uint_as_float(w[t] & 0xFFFF0000u);
+    }
+  }
+  float* o = out + sel * n_cols + k;
+  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__global__ void image_scatter_add_rows_kernel(uint8_t* __restrict__ img, int kbs, int n_cols,
+                                              const long long* __restrict__ rows, long long n_sel,
+                                              const float* __restrict__ vals) {
+  const int cpr = n_cols >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sel * cpr) return;
+  const long long sel = i / cpr, m = rows[sel];
+  const int k = (int)(i % cpr) * 8;
+  uint4* p = reinterpret_cast<uint4*>(img + img_off(m, k, kbs));
+  const uint4 u = *p;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  const float* a = vals + sel * n_cols + k;
+  uint32_t r[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const float lo = __uint_as_float(w[t] << 16) + a[2 * t], hi = __uint_as_float(w[t] & 0xFFFF0000u) + a[2 * t + 1];
+    uint32_t ul = __float_as_uint(lo), uh = __float_as_uint(hi);
+    ul += 0x7FFFu + ((ul >> 16) & 1u);                  // round to nearest even (finite inputs)
+    uh += 0x7FFFu + ((uh >> 16) & 1u);
+    r[t] = (ul >> 16) | (uh & 0xFFFF0000u);
+  }
+  *p = make_uint4(r[0], r[1], r[2], r[3]);
+}
+
 }  // namespace fneus
 
 using namespace fneus;
@@ -117,6 +166,39 @@ int fneus_pack_bwd(int nseg, const float* const* g, const float* const* v, float
   dim3 grid(cdiv(maxrows, 8), nseg);
   prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
   pack_bwd_kernel<<<grid, 256, 0, st>>>(a, dflat);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+long long fneus_image_bytes(long long n_rows, int n_cols) {
+  if (n_rows < 0 || n_cols <= 0) return 0;
+  return ((n_rows + 127) / 128) * (long long)((n_cols + 63) / 64) * 16384;
+}
+
+int fneus_image_gather_rows(const void* image, int is_fp16, int n_cols, const long long* rows, long long n_sel, float* out,
+                            void* stream) {
+  if (n_sel == 0) return FNEUS_OK;
+  if (!image || !rows || !out) return FNEUS_ERR_NULL;
+  if (n_sel < 0 || n_cols <= 0 || (n_cols & 63)) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  image_gather_rows_kernel<<<(int)cdiv(n_sel * (n_cols >> 3), 256), 256, 0, st>>>(
+      reinterpret_cast<const uint8_t*>(image), is_fp16, n_cols >> 6, n_cols, rows, n_sel, out);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_image_scatter_add_rows(void* image_bf16, int n_cols, const long long* rows, long long n_sel, const float* vals,
+                                 void* stream) {
+  if (n_sel == 0) return FNEUS_OK;
+  if (!image_bf16 || !rows || !vals) return FNEUS_ERR_NULL;
+  if (n_sel < 0 || n_cols <= 0 || (n_cols & 63)) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  image_scatter_add_rows_kernel<<<(int)cdiv(n_sel * (n_cols >> 3), 256), 256, 0, st>>>(
+      reinterpret_cast<uint8_t*>(image_bf16), n_cols >> 6, n_cols, rows, n_sel, vals);
   prof_end(st);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;

@@ -455,12 +455,20 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                 });
             }
             const int kb_mem = (g.kmem + TC_BK - 1) / TC_BK;
-            if (!SDF && g.ldm < 0) {
+            if (g.ldm < 0) {
               // image source: the tile's bytes are the operand blocks
               const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(g.mem) +
                                                                 (size_t)tile * (size_t)(-g.ldm) * TC_A_BYTES);
               const int nvec = kb_mem * (TC_A_BYTES / 16);
-              for (int i = et; i < nvec; i += SC_EPI_THREADS) reinterpret_cast<uint4*>(sMem)[i] = __ldg(src + i);
+              // four independent 16-byte loads in flight per thread (two 64-column blocks per round)
+              for (int i0 = et; i0 < nvec; i0 += 4 * SC_EPI_THREADS) {
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[k] = i0 + k * SC_EPI_THREADS < nvec ? __ldg(src + i0 + k * SC_EPI_THREADS) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  if (i0 + k * SC_EPI_THREADS < nvec) reinterpret_cast<uint4*>(sMem)[i0 + k * SC_EPI_THREADS] = v[k];
+              }
             }
             // FP32 row-major source: each warp converts 8 rows, a lane 8 consecutive columns at a time (whole lines)
             const bool vec_ok = (g.ldm & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mem) & 15) == 0;
@@ -605,18 +613,18 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
             if (!pf) {
               if (FAST || n < Nc) tmem_ld16_issue(tacc + n, ar);
               else {
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 16; j++) ar[j] = 0u;
               }
             }
             tmem_ld16_wait(ar);
             SC_STAMP(8);
-  #pragma unroll
+#pragma unroll
             for (int j = 0; j < 16; j++) a[j] = __uint_as_float(ar[j]);
             pf = false;
             if (FWD && md == SC_SOFTPLUS) {
               if (s_dot) {
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 16; j++) {
                   float v = sp_z(fmaf(a[j], kz, sb[n + j])) * kinv;
                   v = (valid && n + j < N) ? v : 0.f;
@@ -624,47 +632,57 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                   a[j] = v * oscale;
                 }
               } else if (full) {
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 16; j++) a[j] = sp_z(fmaf(a[j], kz, sb[n + j])) * ko;
               } else {
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? sp_z(fmaf(a[j], kz, sb[n + j])) * ko : 0.f;
               }
             } else if (FWD && md == SC_FEATQ) {
-              // features: FP32 through a swizzled [128][64] staging tile (the slot's 32 KB), written out as whole lines
-              float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
-  #pragma unroll
-              for (int i = 0; i < 4; i++)
-                *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
-                    make_float4(a[4 * i] + sb[n + 4 * i], a[4 * i + 1] + sb[n + 4 * i + 1], a[4 * i + 2] + sb[n + 4 * i + 2],
-                                a[4 * i + 3] + sb[n + 4 * i + 3]);
+              if (S.out == nullptr) {
+                // image hand-over (fneus_sdf_cfg.feat_image): the features leave as one more FP16 operand block, from the
+                // slot's h block (the storer sends it to S.e_out) -- the colour chain's first operand reads it as is
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) f[j] = (valid && n + j < N) ? a[j] + sb[n + j] : 0.f;
+                *reinterpret_cast<uint4*>(hb + ch0) = f32x8_to_u16(f, true);
+                *reinterpret_cast<uint4*>(hb + ch1) = f32x8_to_u16(f + 8, true);
+              } else {
+                // features: FP32 through a swizzled [128][64] staging tile (the slot's 32 KB), written out as whole lines
+                float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                  *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
+                      make_float4(a[4 * i] + sb[n + 4 * i], a[4 * i + 1] + sb[n + 4 * i + 1], a[4 * i + 2] + sb[n + 4 * i + 2],
+                                  a[4 * i + 3] + sb[n + 4 * i + 3]);
+              }
               // q_{L-1} = s(h_L) * W_L[0] from the unrounded activation: the previous step's pre-activations still sit
               // in the other accumulator (this step publishes its operand only when all blocks are done)
               const float* sbp = sbias + (s > 0 && g.st[s - 1].bias_slot >= 0 ? g.st[s - 1].bias_slot : 0) * 256;
               tmem_ld16(taddr + (uint32_t)(((lg + 1) & 1) << 8) + n, a);
-  #pragma unroll
+#pragma unroll
               for (int j = 0; j < 16; j++)
                 a[j] = (valid && n + j < N) ? sg_fast(sp_z(fmaf(a[j], kz, sbp[n + j])) * kinv, ksg) * srvec[n + j] : 0.f;
             } else if (FWD && md == SC_SPMUL) {
               if (!FAST && csplit < N && n + 16 > csplit) {
                 // positional-encoding part of the skip gradient: parked in shared memory until G0
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 16; j++)
                   if (PARK && n + j >= csplit && n + j < N && n + j - csplit < SC_PARK_LD)
                     spark[r * SC_PARK_LD + n + j - csplit] = a[j] * oscale;
               }
-  #pragma unroll
+#pragma unroll
               for (int hf = 0; hf < 2; hf++) {
                 float hv[8];
                 f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_l: forward image, FP16
                 if (full) {
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 8; j++) {                                    // s(h) a oscale = ao - 2^(ksg h) ao
                     const float ao = a[hf * 8 + j] * oscale;
                     a[hf * 8 + j] = fmaf(-ex2_approx(hv[j] * ksg), ao, ao);
                   }
                 } else {
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 8; j++)
                     a[hf * 8 + j] = (valid && n + hf * 8 + j < csplit) ? sg_fast(hv[j], ksg) * a[hf * 8 + j] * oscale : 0.f;
                 }
@@ -676,21 +694,21 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                 // parked columns csplit .. csplit+N-1 of the skip step <-> g_0 columns 0 .. N-1 (written by other
                 // column groups of the row: the named barrier orders the shared-memory accesses)
                 epi_bar();
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 16; j++)
                   if (PARK && n + j < N && n + j < SC_PARK_LD && csplit + n + j < 256) a[j] += spark[r * SC_PARK_LD + n + j];
               }
-  #pragma unroll
+#pragma unroll
               for (int i = 0; i < 4; i++)
                 *reinterpret_cast<float4*>(T + r * 64 + (((cg * 4 + i) ^ (r & 15)) << 2)) =
                     make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
             } else if (BWD && md == SC_SWEEP) {
-  #pragma unroll
+#pragma unroll
               for (int hf = 0; hf < 2; hf++) {
                 float hv[8], qv[8], e[8];
                 f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_{l+1}, q_l: forward
                 f16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);      // images, FP16
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 8; j++) {
                   const float sg = sg_fast(hv[j], ksg);
                   const float acc = a[hf * 8 + j];
@@ -698,7 +716,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                   e[j] = fmaf(-beta, sg, beta) * qv[j] * acc;
                 }
                 if (!full) {                                                       // ragged tile / partial block only
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 8; j++) {
                     const bool ok = valid && n + hf * 8 + j < N;
                     a[hf * 8 + j] = ok ? a[hf * 8 + j] : 0.f;
@@ -710,19 +728,19 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
             } else if (!SDF && md == SC_RELU) {
               const float floor_v = S.act == 2 ? -3.0e38f : 0.f;            // act 2: plain linear layer
               if (full) {
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 16; j++) a[j] = fmaxf(a[j] + sb[n + j], floor_v);
               } else {
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 16; j++) a[j] = (valid && n + j < N) ? fmaxf(a[j] + sb[n + j], floor_v) : 0.f;
               }
             } else if (!SDF && md == SC_MASK) {
               // dz_{l-1} = (dz_l W_l [+ rs rvec]) * [h_l > 0]: the forward activation block arrived in the slot's h block
               const bool has_h = S.h != nullptr;
-  #pragma unroll
+#pragma unroll
               for (int hf = 0; hf < 2; hf++) {
                 if (S.use_rs) {
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(rsv, srvec[n + hf * 8 + j], a[hf * 8 + j]);
                 }
                 if (has_h) {
@@ -730,11 +748,11 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                   // FP16 and BF16 alike (an FP16 pattern read this way is a tiny, possibly denormal, float of the same sign)
                   float hv[8];
                   bf16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 8; j++) a[hf * 8 + j] = hv[j] > 0.f ? a[hf * 8 + j] : 0.f;
                 }
                 if (!full) {
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 8; j++) a[hf * 8 + j] = (valid && n + hf * 8 + j < N) ? a[hf * 8 + j] : 0.f;
                 }
               }
@@ -744,7 +762,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                 if (cg == 0 && b == 0 && valid) {
                   float y[16];
                   if (S.accumulate) row_load16(S.out, S.ldo, m, 0, N, y);
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 16; j++) {
                     float v = a[j] + (hasb ? sb[j] : 0.f);
                     if (S.act == 1) v = sigmoid_fast(v);
@@ -752,10 +770,22 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                   }
                   row_store16(S.out, S.ldo, m, 0, N, y);
                 }
+              } else if (S.out == nullptr) {
+                // wide result handed over as an operand image (the feature gradient, fneus_color_cfg.feat_image): packed
+                // into the slot's h block, which the storer sends to S.e_out
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                  float v = a[j] + (hasb ? sb[n + j] : 0.f);
+                  if (S.act == 1) v = sigmoid_fast(v);
+                  f[j] = (valid && n + j < N) ? v : 0.f;
+                }
+                *reinterpret_cast<uint4*>(hb + ch0) = f32x8_to_u16(f, opf16);
+                *reinterpret_cast<uint4*>(hb + ch1) = f32x8_to_u16(f + 8, opf16);
               } else {
                 // wide result: FP32 through the slot's swizzled [128][64] staging tile, written out as whole lines
                 float* T = reinterpret_cast<float*>(sAux + (2 * slot) * TC_A_BYTES);
-  #pragma unroll
+#pragma unroll
                 for (int i = 0; i < 4; i++) {
                   float4 v = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
                   if (hasb) { v.x += sb[n + 4 * i]; v.y += sb[n + 4 * i + 1]; v.z += sb[n + 4 * i + 2]; v.w += sb[n + 4 * i + 3]; }
@@ -764,19 +794,19 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                 }
               }
             } else if (BWD) {  // SC_SDFBWD
-  #pragma unroll
+#pragma unroll
               for (int hf = 0; hf < 2; hf++) {
                 float hv[8], qv[8];
                 f16x8_to_f32(*reinterpret_cast<const uint4*>(hb + (hf ? ch1 : ch0)), hv);      // h_l: forward image, FP16
                 bf16x8_to_f32(*reinterpret_cast<const uint4*>(qb + (hf ? ch1 : ch0)), qv);     // e_{l-1}: this pass, BF16
                 if (S.use_rs) {                                                    // the sdf row of the last linear (rank-1)
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(rsv, srvec[n + hf * 8 + j], a[hf * 8 + j]);
                 }
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 8; j++) a[hf * 8 + j] = fmaf(sg_fast(hv[j], ksg) * oscale, a[hf * 8 + j], qv[j]);
                 if (!full) {
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 8; j++) a[hf * 8 + j] = (valid && n + hf * 8 + j < csplit) ? a[hf * 8 + j] : 0.f;
                 }
               }
@@ -804,12 +834,12 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
                                                        ((col & 7) << 1)) = f32_to_u16_bits(val * rsqrt2, opf16);
                 });
             }
-            if (FWD ? (md == SC_FEATQ || md == SC_G0) : (!SDF && md == SC_OUT && N > 16)) {
+            if (FWD ? ((md == SC_FEATQ && S.out != nullptr) || md == SC_G0) : (!SDF && md == SC_OUT && N > 16 && S.out != nullptr)) {
               epi_bar();
               const float* T = reinterpret_cast<const float*>(sAux + (2 * slot) * TC_A_BYTES);
               if (!SDF || md == SC_FEATQ) {
                 // warp ew writes rows 8 ew .. 8 ew + 7: two rows (2 x 256 B) per instruction
-  #pragma unroll
+#pragma unroll
                 for (int i = 0; i < 4; i++) {
                   const int rr = ew * 8 + 2 * i + (lane >> 4), q4 = lane & 15;
                   const long long mm = tile * 128 + rr;

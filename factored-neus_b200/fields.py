@@ -106,10 +106,15 @@ class SDFNetwork(nn.Module):
     def flat_weights(self):
         return _flat_pack([getattr(self, "lin" + str(l)) for l in range(self.num_layers - 1)])
 
-    def value_feature_normal(self, x, want_normal=True, w=None):
+    def value_feature_normal(self, x, want_normal=True, w=None, feat_image=False):
         """One fused pass: (sdf [N,1], feature [N,d_out-1], d sdf/dx [N,3]); all differentiable w.r.t. weights.
-        ``w``: an already packed ``flat_weights()`` tensor of THIS network (the renderer packs once per render)."""
-        return ops.SdfValueGrad.apply(self.flat_weights() if w is None else w, x, self.cfg, want_normal)
+        ``w``: an already packed ``flat_weights()`` tensor of THIS network (the renderer packs once per render).
+        ``feat_image``: hand the features over as an operand image (an opaque tensor only RenderingNetwork's
+        ``feat_image=True`` and ops.GatherRows can read; see supports_feature_image)."""
+        return ops.SdfValueGrad.apply(self.flat_weights() if w is None else w, x, self.cfg, want_normal, feat_image)
+
+    def supports_feature_image(self):
+        return bool(L.lib().fneus_sdf_feat_image_ok(self.cfg))
 
     def forward(self, inputs, iter_step=0):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
@@ -155,8 +160,12 @@ class RenderingNetwork(nn.Module):
     def flat_weights(self):
         return _flat_pack([getattr(self, "lin" + str(l)) for l in range(self.num_layers - 1)])
 
-    def forward(self, points, normals, view_dirs, feature_vectors):
-        return ops.ColorMLP.apply(self.flat_weights(), points, normals, view_dirs, feature_vectors, self.cfg)
+    def forward(self, points, normals, view_dirs, feature_vectors, feat_image=False):
+        return ops.ColorMLP.apply(self.flat_weights(), points, normals, view_dirs, feature_vectors, self.cfg,
+                                  feat_image)
+
+    def supports_feature_image(self):
+        return bool(L.lib().fneus_color_feat_image_ok(self.cfg))
 
 
 class NeRF(nn.Module):

@@ -199,18 +199,44 @@ def sdf_grid(cfg, wflat, ax, ay, az, ix0=0, ix1=None, max_chunk=1 << 18):
     return u
 
 
+def _image_cfg(cfg):
+    """Copy of a network configuration with the feature hand-over switched to operand images (fneus.h: feat_image)."""
+    c = type(cfg).from_buffer_copy(cfg)
+    c.feat_image = 1
+    return c
+
+
+def feature_image_floats(n_rows, n_cols=256):
+    """Size, in float32 words, of the opaque tensor that carries an [n_rows, n_cols] 16-bit operand image."""
+    return int(L.lib().fneus_image_bytes(int(n_rows), int(n_cols))) // 4
+
+
+def image_gather_rows(image, rows, n_cols=256, is_fp16=True):
+    """FP32 rows [len(rows), n_cols] out of an operand image (no autograd; see GatherRows)."""
+    out = torch.empty(rows.shape[0], n_cols, dtype=torch.float32, device=image.device)
+    L.check(L.lib().fneus_image_gather_rows(L.ptr(image), 1 if is_fp16 else 0, n_cols, L.ptr(rows), rows.shape[0],
+                                            L.ptr(out), L.stream_ptr()), "fneus_image_gather_rows")
+    return out
+
+
 class SdfValueGrad(torch.autograd.Function):
     """(wflat, x) -> (sdf [N,1], feat [N,d_out-1], normal [N,3]); fields.py:74-111 with create_graph=True
     semantics: all three outputs are differentiable w.r.t. the weights (double backward for the normal)."""
 
     @staticmethod
-    def forward(ctx, wflat, x, cfg, want_normal):
+    def forward(ctx, wflat, x, cfg, want_normal, feat_image=False):
         _need_cuda(x, "x")
         xc, w = _f32c(x), _f32c(wflat)
         N = xc.shape[0]
         lib = L.lib()
         sdf = torch.empty(N, 1, dtype=torch.float32, device=x.device)
-        feat = torch.empty(N, cfg.d_out - 1, dtype=torch.float32, device=x.device)
+        if feat_image:
+            # the features leave as an FP16 operand image inside an opaque float32 tensor; its gradient comes back as a
+            # BF16 image in a tensor of the same shape (ColorMLP / FanOut / GatherRows know the convention)
+            cfg = _image_cfg(cfg)
+            feat = torch.empty(feature_image_floats(N, cfg.d_out - 1), dtype=torch.float32, device=x.device)
+        else:
+            feat = torch.empty(N, cfg.d_out - 1, dtype=torch.float32, device=x.device)
         normal = torch.empty(N, 3, dtype=torch.float32, device=x.device) if want_normal else None
         saved = _empty(lib.fneus_sdf_saved_floats(cfg, N), x)
         scratch = _empty(lib.fneus_sdf_scratch_floats(cfg, N), x)
@@ -246,7 +272,7 @@ class SdfValueGrad(torch.autograd.Function):
         d_normal = _f32c(d_normal) if ctx.want_normal else None
         L.check(lib.fneus_sdf_bwd(cfg, L.ptr(w), L.ptr(xc), N, L.ptr(d_sdf), L.ptr(d_feat), L.ptr(d_normal),
                                   L.ptr(saved), L.ptr(scratch), L.ptr(dw), L.stream_ptr()), "fneus_sdf_bwd")
-        return dw, None, None, None
+        return dw, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -256,9 +282,11 @@ class ColorMLP(torch.autograd.Function):
     """RenderingNetwork.forward (fields.py:150-175): grads for weights, normals and features."""
 
     @staticmethod
-    def forward(ctx, wflat, points, normals, view_dirs, feats, cfg):
+    def forward(ctx, wflat, points, normals, view_dirs, feats, cfg, feat_image=False):
         _need_cuda(points, "points")
         w, p, n, v, f = _f32c(wflat), _f32c(points), _f32c(normals), _f32c(view_dirs), _f32c(feats)
+        if feat_image:                                  # `feats` is SdfValueGrad's operand image
+            cfg = _image_cfg(cfg)
         N = p.shape[0]
         lib = L.lib()
         rgb = torch.empty(N, cfg.d_out, dtype=torch.float32, device=p.device)
@@ -285,7 +313,7 @@ class ColorMLP(torch.autograd.Function):
         L.check(lib.fneus_color_bwd(cfg, L.ptr(w), L.ptr(p), L.ptr(n), L.ptr(v), L.ptr(f), N, L.ptr(rgb),
                                     L.ptr(_f32c(d_rgb)), L.ptr(d_n), L.ptr(d_f), L.ptr(saved), L.ptr(scratch),
                                     L.ptr(dw), L.stream_ptr()), "fneus_color_bwd")
-        return dw, None, d_n, None, d_f, None
+        return dw, None, d_n, None, d_f, None, None
 
 
 class RefColorMLP(torch.autograd.Function):
@@ -813,7 +841,12 @@ class FanOut(torch.autograd.Function):
                 g = torch.zeros(shape, dtype=vals.dtype, device=vals.device)
             elif not g.is_contiguous():
                 g = g.contiguous()
-            g.index_add_(0, rows, vals)
+            if stash.get("feat_image"):
+                # `g` is the colour network's BF16 gradient image: the sparse rows are added into it in place
+                L.check(L.lib().fneus_image_scatter_add_rows(L.ptr(g), vals.shape[1], L.ptr(rows), rows.shape[0],
+                                                             L.ptr(vals), L.stream_ptr()), "fneus_image_scatter_add_rows")
+            else:
+                g.index_add_(0, rows, vals)
         return g, None
 
 
@@ -825,6 +858,8 @@ class GatherRows(torch.autograd.Function):
     def forward(ctx, x, rows, stash):
         ctx.save_for_backward(rows)
         ctx.stash, ctx.shape = stash, x.shape
+        if stash.get("feat_image"):
+            return image_gather_rows(x, rows)
         return x.index_select(0, rows)
 
     @staticmethod

@@ -13,6 +13,9 @@ from . import ops
 class NeuSRenderer:
     # route the sparse (RefColor) gradient of `feature` into the colour network's dense one in place (ops.FanOut)
     fuse_feature_fanout = True
+    # hand `feature_vector` from the SDF network to the colour network as an operand image whenever both networks can
+    # (tensor-core precision, 256 features); False keeps the FP32 [N,256] tensor of the reference
+    feature_image = True
 
     def __init__(self, n_samples, n_importance, n_outside, up_sample_steps, perturb, nerf=None, sdf_network=None,
                  deviation_network=None, color_network=None, refColor_network=None, lvis_network=None,
@@ -100,17 +103,25 @@ class NeuSRenderer:
         dists, mid_z, pts, dirs = ops.core_geometry(rays_o, rays_d, z_vals, sample_dist)
 
         w_sdf = getattr(self, "_w_sdf", None) if sdf_network is self.sdf_network else None
-        sdf, feat, normals = sdf_network.value_feature_normal(pts, want_normal=True, w=w_sdf)
+        # tensor-core path: `feature_vector` goes from the SDF chain to the colour chain as an operand image (never as an
+        # FP32 [B*n,256] tensor in HBM); RefColor's two rows per ray are read out of the image
+        img = bool(self.feature_image and getattr(sdf_network, "supports_feature_image", lambda: False)() and
+                   getattr(color_network, "supports_feature_image", lambda: False)())
+        if img:
+            sdf, feat, normals = sdf_network.value_feature_normal(pts, want_normal=True, w=w_sdf, feat_image=True)
+        else:
+            sdf, feat, normals = sdf_network.value_feature_normal(pts, want_normal=True, w=w_sdf)
         if hasattr(deviation_network, "variance"):
             # SingleVarianceNetwork.forward (fields.py:267-268) on one row: ones * exp(10 variance), without the ones
             inv_s = torch.exp(deviation_network.variance * 10.0).clip(1e-6, 1e6).reshape(1, 1)
         else:
             inv_s = deviation_network(torch.zeros([1, 3], device=dev))[:, :1].clip(1e-6, 1e6)   # [1,1]
         # `feat` feeds the colour network (all rows) and RefColor (2 rows per ray): see ops.FanOut
-        stash = {}
-        fan = self.fuse_feature_fanout and feat.requires_grad
+        stash = {"feat_image": img}
+        fan = (self.fuse_feature_fanout or img) and feat.requires_grad
         feat_dense, feat_sparse = ops.FanOut.apply(feat, stash) if fan else (feat, feat)
-        rgb = color_network(pts, normals, dirs, feat_dense)                                       # [B*n,3]
+        rgb = (color_network(pts, normals, dirs, feat_dense, feat_image=True) if img else
+               color_network(pts, normals, dirs, feat_dense))                                     # [B*n,3]
 
         n_out = 0 if background_alpha is None else background_alpha.shape[1] - n
         color, weights, wsum, wmax, cdf, inside, eik_num, eik_den, hit_idx, w_pair = ops.Composite.apply(
@@ -124,7 +135,7 @@ class NeuSRenderer:
         hit = hit_idx >= 0
         rows = ops.hit_rows(hit_idx, n)                                                          # [2B]
         r_rgb, r_spec, r_diff = self._ref_rows(refColor_network, pts, feat_sparse, dirs, normals, rows,
-                                               stash if fan else None)
+                                               stash if fan else None, img)
         surf_rgb, surf_spec, surf_diff = ops.SurfaceBlend.apply(r_rgb, r_spec, r_diff, w_pair, hit_idx)
         self.last_hit_idx = hit_idx
         self.last_weight_sum = wsum
@@ -148,8 +159,11 @@ class NeuSRenderer:
         }
 
     @staticmethod
-    def _ref_rows(net, pts, feat, dirs, normals, rows, stash=None):
-        f_rows = feat.index_select(0, rows) if stash is None else ops.GatherRows.apply(feat, rows, stash)
+    def _ref_rows(net, pts, feat, dirs, normals, rows, stash=None, feat_image=False):
+        if stash is not None:
+            f_rows = ops.GatherRows.apply(feat, rows, stash)
+        else:
+            f_rows = ops.image_gather_rows(feat, rows) if feat_image else feat.index_select(0, rows)
         d = net(pts.index_select(0, rows), f_rows, dirs.index_select(0, rows), normals.index_select(0, rows))
         return d["rgb"], d["specular_rgb"], d["diffuse_rgb"]
 

@@ -86,6 +86,10 @@ typedef struct {
   float scale;    /* 1.0 */
   float beta;     /* Softplus beta = 100 */
   int precision; /* FNEUS_PREC_FP32 (CUDA-core exactness anchor) or FNEUS_PREC_TC (tcgen05 tensor cores) */
+  int feat_image; /* 0: features / feature gradients are FP32 rows [n, d_out-1].  1 (FNEUS_PREC_TC, d_out-1 == 256, value +
+                   * normal graph): `feat_out` of fneus_sdf_fwd / fneus_sdf_fwd_grad is an FP16 operand image and `d_feat` of
+                   * fneus_sdf_bwd a BF16 one (fneus_image_bytes(n, 256) bytes each) -- the layout the colour chain's first
+                   * MMA operand and the weight-gradient kernel read as they are; see fneus_image_* below */
 } fneus_sdf_cfg;
 
 long long fneus_sdf_pack_floats(const fneus_sdf_cfg* cfg);
@@ -126,6 +130,8 @@ typedef struct {
   int d_out;         /* 3 */
   int multires_view; /* 4 */
   int precision; /* FNEUS_PREC_FP32 (CUDA-core exactness anchor) or FNEUS_PREC_TC (tcgen05 tensor cores) */
+  int feat_image; /* 1: `feats` is the FP16 operand image written by the SDF chain (fneus_sdf_cfg.feat_image) and `d_feats`
+                   * of fneus_color_bwd leaves as a BF16 operand image; 0: FP32 rows [n, d_feature] */
 } fneus_color_cfg;
 
 long long fneus_color_pack_floats(const fneus_color_cfg* cfg);
@@ -142,6 +148,20 @@ int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float*
                     const float* view_dirs, const float* feats, long long n_points, const float* rgb,
                     const float* d_rgb, float* d_normals, float* d_feats, float* saved, float* scratch,
                     float* d_wpack, void* stream);
+
+/* ---- operand images: the hand-over format of `feature_vector` between the SDF and the colour network on the tensor-core
+ * path (renderer.py:225-232 passes it as an FP32 [n,256] tensor; here it never takes that form in HBM).  An image holds
+ * ceil(n/128) row tiles x (n_cols/64) blocks of 128 rows x 64 columns of 16-bit elements in the 128-byte-swizzled K-major
+ * shared-memory layout of tcgen05 operands.  gather: FP32 rows out of an image (RefColor reads 2 rows per ray,
+ * renderer.py:296-327); scatter_add: FP32 rows added into a BF16 image (their gradient); rows must be distinct. */
+/* 1 when a configuration can take / produce the image form (tensor-core precision, chain-kernel shapes), else 0 */
+int fneus_sdf_feat_image_ok(const fneus_sdf_cfg* cfg);
+int fneus_color_feat_image_ok(const fneus_color_cfg* cfg);
+long long fneus_image_bytes(long long n_rows, int n_cols);
+int fneus_image_gather_rows(const void* image, int is_fp16, int n_cols, const long long* rows, long long n_sel,
+                            float* out /* [n_sel, n_cols] */, void* stream);
+int fneus_image_scatter_add_rows(void* image_bf16, int n_cols, const long long* rows, long long n_sel,
+                                 const float* vals /* [n_sel, n_cols] */, void* stream);
 
 /* RefColor.forward (fields.py:303-335).  Pack order: net_cd.{0,2,4,6,8}, viewdir_mlp.{0..3}, net_cs.0.
  * Outputs rgb/specular_rgb/diffuse_rgb [n,3]. */

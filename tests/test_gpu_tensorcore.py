@@ -550,3 +550,76 @@ def test_bf16_step_is_reproducible_and_batch_invariant(bf16_mode):
     assert worst_rep <= 2e-5, "gradients differ between identical runs: %.3e" % worst_rep
     # (all samples of these rays lie inside the relaxed sphere, so the eikonal mean of the halves adds up to the full one)
     assert worst_split <= 2e-5, "gradients depend on the batch composition: %.3e" % worst_split
+
+
+@pytest.mark.parametrize("B", [44, 512])
+def test_bf16_feature_image_matches_fp32_handover(bf16_mode, B):
+    """`feature_vector` handed from the SDF chain to the colour chain as an operand image (fneus_sdf_cfg.feat_image) against
+    the FP32 [N,256] hand-over of the reference (renderer.py:225-232): the colour chain rounds the FP32 features to the
+    same FP16 values, so every forward output is bit-identical; the gradients differ only by the BF16 rounding of the
+    feature gradient at RefColor's two rows per ray (an FP32 sum rounded once vs. a rounded value plus an FP32 term)."""
+    states = syn.scene_states(seed=4, jitter=0.03)
+    o, d, near, far = [t.to(DEV) for t in syn.make_rays(B, seed=31)]
+    true_rgb, mask = [t.to(DEV) for t in syn.make_targets(B, seed=32)]
+    m = build_modules(states, DEV, syn.RENDER_CONF_WMASK)
+    R = m["renderer"]
+    nets = ("sdf", "color", "var", "ref")
+    assert m["sdf"].supports_feature_image() and m["color"].supports_feature_image()
+
+    def run(image):
+        R.feature_image = image
+        out = R.render(o, d, near, far, perturb_overwrite=0, cos_anneal_ratio=1.0)
+        loss = ((out["color_fine"] - true_rgb).abs().sum() + (out["surface_color"] - true_rgb).abs().sum() * 0.1
+                + out["gradient_error"] * 0.1 * B)
+        loss.backward()
+        g = {"%s.%s" % (n, k): p.grad.detach().clone() for n in nets for k, p in m[n].named_parameters()}
+        for n in nets:
+            for p in m[n].parameters():
+                p.grad = None
+        return {k: out[k].detach().clone() for k in ("color_fine", "surface_color", "weight_sum", "gradients")}, g
+
+    try:
+        o_img, g_img = run(True)
+        o_f32, g_f32 = run(False)
+    finally:
+        R.feature_image = True
+    for k in o_img:
+        assert torch.equal(o_img[k], o_f32[k]), "feature image changes the forward output %s: %.3e" % (
+            k, max_err(o_img[k], o_f32[k]))
+    worst = 0.0
+    for k in g_img:
+        scale = max(1e-6, float(g_f32[k].abs().max()))
+        worst = max(worst, float((g_img[k] - g_f32[k]).abs().max()) / scale)
+    print("feature image vs FP32 hand-over (B=%d): worst gradient difference %.3e of the tensor's max" % (B, worst))
+    assert worst <= 2e-3, "gradients differ between the two hand-over forms: %.3e" % worst
+
+
+def test_image_rows_gather_scatter():
+    """fneus_image_gather_rows / fneus_image_scatter_add_rows against the layout formula (fneus_common.cuh img_off)."""
+    import numpy as np
+    N, C = 300, 256
+    g = torch.Generator().manual_seed(5)
+    dense = torch.randn(N, C, generator=g)
+    nfl = ops.feature_image_floats(N, C)
+    assert nfl * 4 == ((N + 127) // 128) * (C // 64) * 16384
+    img = np.zeros(nfl * 2, dtype=np.uint16)
+    bits = dense.to(torch.bfloat16).view(torch.int16).numpy().astype(np.uint16)
+    mm, kk = np.meshgrid(np.arange(N), np.arange(C), indexing="ij")
+    off = ((mm >> 7) * (C // 64) + (kk >> 6)) * 16384 + ((mm & 127) >> 3) * 1024 + (mm & 7) * 128 + \
+          ((((kk & 63) >> 3) ^ (mm & 7)) << 4) + ((kk & 7) << 1)
+    img[off // 2] = bits
+    image = torch.from_numpy(img.view(np.float32).copy()).to(DEV)
+    rows = torch.tensor([0, 5, 127, 128, 299, 131], dtype=torch.int64, device=DEV)
+    got = ops.image_gather_rows(image, rows, C, is_fp16=False)
+    want = dense.to(torch.bfloat16).float()[rows.cpu()]
+    assert torch.equal(got.cpu(), want)
+    vals = torch.randn(rows.shape[0], C, generator=g)
+    vals_dev = vals.to(DEV)
+    L = fn._lib
+    L.check(L.lib().fneus_image_scatter_add_rows(L.ptr(image), C, L.ptr(rows), rows.shape[0], L.ptr(vals_dev),
+                                                 L.stream_ptr()), "scatter")
+    got2 = ops.image_gather_rows(image, rows, C, is_fp16=False)
+    assert torch.equal(got2.cpu(), (want + vals).to(torch.bfloat16).float())
+    untouched = torch.tensor([1, 129, 298], dtype=torch.int64, device=DEV)
+    assert torch.equal(ops.image_gather_rows(image, untouched, C, is_fp16=False).cpu(),
+                       dense.to(torch.bfloat16).float()[untouched.cpu()])
