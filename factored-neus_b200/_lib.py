@@ -103,6 +103,11 @@ _SIGNATURES = {
     "fneus_prof_classes": (c_int, []),
     "fneus_prof_enable": (c_int, [c_int]),
     "fneus_prof_collect": (c_int, [_P, _P, _P, _P]),
+    "fneus_split_batch": (c_int, [_P, _LL, _P, _P, _P, _P, _P]),
+    "fneus_inv_s": (c_int, [_P, _P, _P, _P]),
+    "fneus_composite_post": (c_int, [_P, _P, _LL, _P, _P, _P]),
+    "fneus_gather_rows3": (c_int, [_P, _P, _P, _P, _LL, _P, _P, _P, _P]),
+    "fneus_scatter_rows3": (c_int, [_P, _P, _LL, _P, _P]),
     "fneus_image_bytes": (_LL, [_LL, c_int]),
     "fneus_image_gather_rows": (c_int, [_P, c_int, c_int, _P, _LL, _P, _P]),
     "fneus_image_scatter_add_rows": (c_int, [_P, c_int, _P, _LL, _P, _P]),

@@ -240,6 +240,58 @@ __global__ void stage2_loss_kernel(const float* __restrict__ gt_lvis, const floa
   }
 }
 
+// ---- step glue: the small per-ray / per-scalar pieces around the render path that the reference leaves to ATen ----------
+// (each of them was 1-7 launches of a few microseconds inside the 2 ms step)
+// batch [B,10] = (rays_o, rays_d, rgb, mask) of Dataset.gen_random_rays_at (dataset.py:133-151) -> four dense tensors
+__global__ void split_batch_kernel(const float* __restrict__ batch, long long B, float* __restrict__ ro,
+                                   float* __restrict__ rd, float* __restrict__ rgb, float* __restrict__ mask) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 10) return;
+  const long long b = i / 10;
+  const int c = (int)(i % 10);
+  const float v = batch[i];
+  if (c < 3) ro[b * 3 + c] = v;
+  else if (c < 6) rd[b * 3 + c - 3] = v;
+  else if (c < 9) rgb[b * 3 + c - 6] = v;
+  else mask[b] = v;
+}
+// inv_s = clip(exp(10 variance), 1e-6, 1e6) (fields.py:267-268, renderer.py:238) and its derivative
+__global__ void inv_s_kernel(const float* __restrict__ variance, const float* __restrict__ d_inv_s, float* __restrict__ out) {
+  const float e = expf(variance[0] * 10.f);
+  if (d_inv_s == nullptr) out[0] = fminf(fmaxf(e, 1e-6f), 1e6f);
+  else out[0] = (e >= 1e-6f && e <= 1e6f) ? d_inv_s[0] * e * 10.f : 0.f;
+}
+// after the compositing kernel: eikonal totals over the rays (fixed order), their quotient (renderer.py:282) and the
+// sign-change mask (renderer.py:286)
+__global__ void composite_post_kernel(const float* __restrict__ eik, const int* __restrict__ hit_idx, int B,
+                                      float* __restrict__ tot3, unsigned char* __restrict__ hit_mask) {
+  __shared__ float red[32];
+  float s0 = 0.f, s1 = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    s0 += eik[2 * b];
+    s1 += eik[2 * b + 1];
+    hit_mask[b] = hit_idx[b] >= 0 ? 1 : 0;
+  }
+  s0 = block_sum(s0, red);
+  s1 = block_sum(s1, red);
+  if (threadIdx.x == 0) { tot3[0] = s0; tot3[1] = s1; tot3[2] = s0 / (s1 + 1e-5f); }
+}
+// rows of three [N,3] tensors (the surface samples RefColor sees, renderer.py:296-327) and the scatter of a gradient
+__global__ void gather_rows3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                    const long long* __restrict__ rows, long long n, float* __restrict__ oa,
+                                    float* __restrict__ ob, float* __restrict__ oc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 3) return;
+  const long long src = rows[i / 3] * 3 + i % 3;
+  oa[i] = a[src]; ob[i] = b[src]; oc[i] = c[src];
+}
+__global__ void scatter_rows3_kernel(const float* __restrict__ vals, const long long* __restrict__ rows, long long n,
+                                     float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 3) return;
+  out[rows[i / 3] * 3 + i % 3] += vals[i];
+}
+
 }  // namespace fneus
 
 using namespace fneus;
@@ -339,6 +391,65 @@ int fneus_stage2_loss(const float* gt_lvis, const float* pre_lvis, const float* 
   prof_begin(PC_COMPOSITE, 0.0, 0.0, st);
   stage2_loss_kernel<<<1, 1024, 0, st>>>(gt_lvis, pre_lvis, gt_rad, pre_rad, hit_idx, den2, (int)B, k, parts3, d_pre_lvis,
                                          d_pre_rad);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_split_batch(const float* batch, long long B, float* rays_o, float* rays_d, float* rgb, float* mask, void* stream) {
+  if (B == 0) return FNEUS_OK;
+  if (!batch || !rays_o || !rays_d || !rgb || !mask) return FNEUS_ERR_NULL;
+  if (B < 0) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  split_batch_kernel<<<(int)cdiv(B * 10, 256), 256, 0, st>>>(batch, B, rays_o, rays_d, rgb, mask);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_inv_s(const float* variance, const float* d_inv_s, float* out, void* stream) {
+  if (!variance || !out) return FNEUS_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  inv_s_kernel<<<1, 1, 0, st>>>(variance, d_inv_s, out);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_composite_post(const float* eik, const int* hit_idx, long long B, float* tot3, unsigned char* hit_mask,
+                         void* stream) {
+  if (!eik || !hit_idx || !tot3 || !hit_mask) return FNEUS_ERR_NULL;
+  if (B < 0 || B > (1 << 28)) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_COMPOSITE, 0.0, 0.0, st);
+  composite_post_kernel<<<1, 1024, 0, st>>>(eik, hit_idx, (int)B, tot3, hit_mask);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_gather_rows3(const float* a, const float* b, const float* c, const long long* rows, long long n, float* oa,
+                       float* ob, float* oc, void* stream) {
+  if (n == 0) return FNEUS_OK;
+  if (!a || !b || !c || !rows || !oa || !ob || !oc) return FNEUS_ERR_NULL;
+  if (n < 0) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  gather_rows3_kernel<<<(int)cdiv(n * 3, 256), 256, 0, st>>>(a, b, c, rows, n, oa, ob, oc);
+  prof_end(st);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
+}
+
+int fneus_scatter_rows3(const float* vals, const long long* rows, long long n, float* out, void* stream) {
+  if (n == 0) return FNEUS_OK;
+  if (!vals || !rows || !out) return FNEUS_ERR_NULL;
+  if (n < 0) return FNEUS_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PC_ELEMENTWISE, 0.0, 0.0, st);
+  scatter_rows3_kernel<<<(int)cdiv(n * 3, 256), 256, 0, st>>>(vals, rows, n, out);
   prof_end(st);
   FNEUS_CHECK_LAUNCH();
   return FNEUS_OK;

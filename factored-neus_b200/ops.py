@@ -577,6 +577,81 @@ def core_geometry(rays_o, rays_d, z, sample_dist):
 # ---------------------------------------------------------------------------------------------
 # compositing
 # ---------------------------------------------------------------------------------------------
+_ONES = {}
+
+
+def _ones1(dev):
+    """A cached [1] tensor of ones per device (never written)."""
+    t = _ONES.get(dev)
+    if t is None:
+        t = _ONES[dev] = torch.ones(1, dtype=torch.float32, device=dev)
+    return t
+
+
+def split_batch(batch):
+    """[B,10] rows of Dataset.gen_random_rays_at (dataset.py:133-151) -> rays_o, rays_d, rgb [B,3], mask [B,1] as dense
+    tensors in one launch (slicing the columns costs one strided copy per consumer)."""
+    _need_cuda(batch, "batch")
+    bc = _f32c(batch)
+    B = bc.shape[0]
+    f32 = dict(dtype=torch.float32, device=bc.device)
+    ro, rd, rgb, m = torch.empty(B, 3, **f32), torch.empty(B, 3, **f32), torch.empty(B, 3, **f32), torch.empty(B, 1, **f32)
+    L.check(L.lib().fneus_split_batch(L.ptr(bc), B, L.ptr(ro), L.ptr(rd), L.ptr(rgb), L.ptr(m), L.stream_ptr()),
+            "fneus_split_batch")
+    return ro, rd, rgb, m
+
+
+class InvS(torch.autograd.Function):
+    """variance (scalar parameter) -> inv_s [1,1] = clip(exp(10 variance), 1e-6, 1e6): SingleVarianceNetwork.forward on one
+    row (fields.py:267-268) with the clip of renderer.py:238, one launch each way."""
+
+    @staticmethod
+    def forward(ctx, variance):
+        _need_cuda(variance, "variance")
+        v = _f32c(variance).reshape(1)
+        out = torch.empty(1, 1, dtype=torch.float32, device=v.device)
+        L.check(L.lib().fneus_inv_s(L.ptr(v), None, L.ptr(out), L.stream_ptr()), "fneus_inv_s")
+        ctx.save_for_backward(v)
+        ctx.shape = variance.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, d_inv_s):
+        (v,) = ctx.saved_tensors
+        d = torch.empty(1, dtype=torch.float32, device=v.device)
+        L.check(L.lib().fneus_inv_s(L.ptr(v), L.ptr(_f32c(d_inv_s).reshape(1)), L.ptr(d), L.stream_ptr()), "fneus_inv_s")
+        return d.reshape(ctx.shape)
+
+
+class GatherRows3(torch.autograd.Function):
+    """(pts, dirs, normals)[rows] in one launch (renderer.py:296-327 gathers the two samples around the sign change);
+    only the normals carry a gradient."""
+
+    @staticmethod
+    def forward(ctx, pts, dirs, normals, rows):
+        _need_cuda(pts, "pts")
+        a, b, c = _f32c(pts).reshape(-1, 3), _f32c(dirs).reshape(-1, 3), _f32c(normals).reshape(-1, 3)
+        n = rows.shape[0]
+        outs = [torch.empty(n, 3, dtype=torch.float32, device=a.device) for _ in range(3)]
+        L.check(L.lib().fneus_gather_rows3(L.ptr(a), L.ptr(b), L.ptr(c), L.ptr(rows), n, L.ptr(outs[0]), L.ptr(outs[1]),
+                                           L.ptr(outs[2]), L.stream_ptr()), "fneus_gather_rows3")
+        ctx.save_for_backward(rows)
+        ctx.nshape = normals.shape
+        ctx.mark_non_differentiable(outs[0], outs[1])
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, _gp, _gd, g_n):
+        if g_n is None:
+            return None, None, None, None
+        (rows,) = ctx.saved_tensors
+        g = torch.zeros(ctx.nshape, dtype=torch.float32, device=g_n.device)
+        L.check(L.lib().fneus_scatter_rows3(L.ptr(_f32c(g_n)), L.ptr(rows), rows.shape[0], L.ptr(g), L.stream_ptr()),
+                "fneus_scatter_rows3")
+        return None, None, g, None
+
+
 class Composite(torch.autograd.Function):
     """renderer.py:245-274,328-332,350-372 fused; differentiable in sdf, normals, rgb, inv_s, bg_alpha, bg_color.
 
@@ -615,20 +690,29 @@ class Composite(torch.autograd.Function):
             L.ptr(bgc), L.ptr(bgr), B, n_in, n_out, L.ptr(inv_c), car, L.ptr(car_dev), L.ptr(color), L.ptr(weights),
             L.ptr(wsum), L.ptr(wmax), L.ptr(cdf), L.ptr(inside), L.ptr(eik), L.ptr(hit), L.ptr(wpair),
             L.stream_ptr()), "fneus_composite_fwd")
-        tot = eik.sum(0)
-        eik_num, eik_den = tot[0].reshape(()), tot[1].reshape(())
-        denom = torch.ones(1, dtype=torch.float32, device=dev)
-        ctx.save_for_backward(sdf_c, nrm_c, rgb_c, inv_c, bga, bgc, dists_c, pts_c, rd_c, bgr, hit, denom)
+        # ray totals of the eikonal term, their quotient and the sign-change mask: one launch (fixed summation order)
+        tot = torch.empty(3, **f32)
+        hit_mask = torch.empty(B, dtype=torch.bool, device=dev)
+        L.check(L.lib().fneus_composite_post(L.ptr(eik), L.ptr(hit), B, L.ptr(tot), L.ptr(hit_mask), L.stream_ptr()),
+                "fneus_composite_post")
+        eik_num, eik_den, grad_err = tot[0].reshape(()), tot[1].reshape(()), tot[2].reshape(())
+        denom = _ones1(dev)
+        ctx.save_for_backward(sdf_c, nrm_c, rgb_c, inv_c, bga, bgc, dists_c, pts_c, rd_c, bgr, hit, denom, tot)
         ctx.dims = (B, n_in, n_out, car)
         ctx.car_dev = car_dev
         ctx.shapes = (sdf.shape, normals.shape, rgb.shape, inv_s.shape)
-        ctx.mark_non_differentiable(wmax, cdf, inside, hit, eik_den)
+        ctx.mark_non_differentiable(wmax, cdf, inside, hit, eik_den, hit_mask)
         ctx.set_materialize_grads(False)
-        return color, weights, wsum, wmax, cdf, inside, eik_num, eik_den, hit, wpair
+        return color, weights, wsum, wmax, cdf, inside, eik_num, eik_den, hit, wpair, grad_err, hit_mask
 
     @staticmethod
-    def backward(ctx, d_color, d_weights, d_wsum, _wmax, _cdf, _inside, d_eik, _eik_den, _hit, d_wpair):
-        sdf_c, nrm_c, rgb_c, inv_c, bga, bgc, dists_c, pts_c, rd_c, bgr, hit, denom = ctx.saved_tensors
+    def backward(ctx, d_color, d_weights, d_wsum, _wmax, _cdf, _inside, d_eik, _eik_den, _hit, d_wpair, d_gerr, _hm):
+        sdf_c, nrm_c, rgb_c, inv_c, bga, bgc, dists_c, pts_c, rd_c, bgr, hit, denom, tot = ctx.saved_tensors
+        if d_gerr is not None:
+            # gradient_error = eik_num / (eik_den + 1e-5) (renderer.py:282) used directly in a loss: fold it into the
+            # numerator's gradient (the denominator is not differentiable, as in the reference: relax_inside_sphere is a mask)
+            extra = d_gerr.reshape(()) / (tot[1] + 1e-5)
+            d_eik = extra if d_eik is None else d_eik.reshape(()) + extra
         B, n_in, n_out, car = ctx.dims
         d_sdf = torch.empty_like(sdf_c)
         d_nrm = torch.empty_like(nrm_c)
@@ -701,22 +785,24 @@ class Stage1Loss(torch.autograd.Function):
         t, m = _f32c(true_rgb), _f32c(mask).reshape(-1)
         B = c.shape[0]
         parts = torch.empty(5, dtype=torch.float32, device=c.device)
-        dc, ds, dw = torch.empty_like(c), torch.empty_like(s_), torch.empty_like(w)
-        de = torch.empty(1, dtype=torch.float32, device=c.device)
+        # the four gradients live in one buffer so that the backward scales them with one launch
+        gbuf = torch.empty(7 * B + 1, dtype=torch.float32, device=c.device)
+        dc, ds, dw, de = gbuf[:3 * B].view(B, 3), gbuf[3 * B:6 * B].view(B, 3), gbuf[6 * B:7 * B], gbuf[7 * B:]
         L.check(L.lib().fneus_stage1_loss(L.ptr(c), L.ptr(s_), L.ptr(w), L.ptr(t), L.ptr(m), L.ptr(hit_idx), L.ptr(e),
                                           L.ptr(den4), B, 1 if use_mask else 0, float(sw), float(iw), float(mw),
                                           L.ptr(parts), L.ptr(dc), L.ptr(ds), L.ptr(dw), L.ptr(de), L.stream_ptr()),
                 "fneus_stage1_loss")
-        ctx.save_for_backward(dc, ds, dw, de)
+        ctx.save_for_backward(gbuf)
         ctx.shapes = (color.shape, surf.shape, wsum.shape, eik_num.shape)
         return parts
 
     @staticmethod
     def backward(ctx, g_parts):
-        dc, ds, dw, de = ctx.saved_tensors
-        g = g_parts[0]
+        (gbuf,) = ctx.saved_tensors
+        B = (gbuf.shape[0] - 1) // 7
+        g = gbuf * g_parts[0]
         sc, ss, sw_, se = ctx.shapes
-        return ((dc * g).reshape(sc), (ds * g).reshape(ss), (dw * g).reshape(sw_), (de * g).reshape(se),
+        return (g[:3 * B].reshape(sc), g[3 * B:6 * B].reshape(ss), g[6 * B:7 * B].reshape(sw_), g[7 * B:].reshape(se),
                 None, None, None, None, None, None, None, None)
 
 

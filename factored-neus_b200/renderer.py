@@ -113,7 +113,7 @@ class NeuSRenderer:
             sdf, feat, normals = sdf_network.value_feature_normal(pts, want_normal=True, w=w_sdf)
         if hasattr(deviation_network, "variance"):
             # SingleVarianceNetwork.forward (fields.py:267-268) on one row: ones * exp(10 variance), without the ones
-            inv_s = torch.exp(deviation_network.variance * 10.0).clip(1e-6, 1e6).reshape(1, 1)
+            inv_s = ops.InvS.apply(deviation_network.variance)
         else:
             inv_s = deviation_network(torch.zeros([1, 3], device=dev))[:, :1].clip(1e-6, 1e6)   # [1,1]
         # `feat` feeds the colour network (all rows) and RefColor (2 rows per ray): see ops.FanOut
@@ -124,15 +124,13 @@ class NeuSRenderer:
                color_network(pts, normals, dirs, feat_dense))                                     # [B*n,3]
 
         n_out = 0 if background_alpha is None else background_alpha.shape[1] - n
-        color, weights, wsum, wmax, cdf, inside, eik_num, eik_den, hit_idx, w_pair = ops.Composite.apply(
+        color, weights, wsum, wmax, cdf, inside, eik_num, eik_den, hit_idx, w_pair, grad_err, hit = ops.Composite.apply(
             sdf, normals, rgb, inv_s, background_alpha, background_sampled_color, dists, pts, rays_d,
             background_rgb, n, n_out, cos_anneal_ratio if torch.is_tensor(cos_anneal_ratio) else float(cos_anneal_ratio))
-        grad_err = eik_num / (eik_den + 1e-5)
         self.last_eikonal_parts = (eik_num, eik_den)     # for exact loss normalisation across ray shards
 
         # surface term (renderer.py:284-343) with fixed shapes: every ray evaluates RefColor at the two
         # bracketing samples, rays without a sign change are masked to the reference's default of ones.
-        hit = hit_idx >= 0
         rows = ops.hit_rows(hit_idx, n)                                                          # [2B]
         r_rgb, r_spec, r_diff = self._ref_rows(refColor_network, pts, feat_sparse, dirs, normals, rows,
                                                stash if fan else None, img)
@@ -154,6 +152,7 @@ class NeuSRenderer:
             "gradient_error": grad_err,
             "inside_sphere": inside,
             "weight_sum": wsum,
+            "weight_max": wmax,
             "specular_color": surf_spec,
             "diffuse_color": surf_diff,
         }
@@ -164,7 +163,8 @@ class NeuSRenderer:
             f_rows = ops.GatherRows.apply(feat, rows, stash)
         else:
             f_rows = ops.image_gather_rows(feat, rows) if feat_image else feat.index_select(0, rows)
-        d = net(pts.index_select(0, rows), f_rows, dirs.index_select(0, rows), normals.index_select(0, rows))
+        p_rows, d_rows, n_rows = ops.GatherRows3.apply(pts, dirs, normals, rows)
+        d = net(p_rows, f_rows, d_rows, n_rows)
         return d["rgb"], d["specular_rgb"], d["diffuse_rgb"]
 
     # ------------------------------------------------------------------ render
@@ -222,7 +222,8 @@ class NeuSRenderer:
                                     cos_anneal_ratio=cos_anneal_ratio)
         self._w_sdf = None
         weights = ret_fine["weights"]
-        s_val = ret_fine["s_val"].reshape(batch_size, n_samples).mean(dim=-1, keepdim=True)
+        # (the mean over a ray of a constant: renderer.py:474 averages the [B*n,1] expansion of 1 / inv_s)
+        s_val = ret_fine["s_val"][:1].expand(batch_size, 1)
         return {
             "color_fine": ret_fine["color"],
             "surface_color": ret_fine["surface_color"],
@@ -230,7 +231,7 @@ class NeuSRenderer:
             "s_val": s_val,
             "cdf_fine": ret_fine["cdf"],
             "weight_sum": ret_fine["weight_sum"],
-            "weight_max": torch.max(weights, dim=-1, keepdim=True)[0],
+            "weight_max": ret_fine["weight_max"],
             "gradients": ret_fine["gradients"],
             "weights": weights,
             "gradient_error": ret_fine["gradient_error"],

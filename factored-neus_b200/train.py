@@ -62,8 +62,8 @@ class Stage1Trainer:
         return 1.0 if self.anneal_end == 0 else min(1.0, self.iter_step / self.anneal_end)
 
     def _eager_step(self, batch):
-        ro, rd, rgb, m = batch[:, :3], batch[:, 3:6], batch[:, 6:9], batch[:, 9:10]
         from . import ops
+        ro, rd, rgb, m = ops.split_batch(batch)
         near, far = ops.near_far_from_sphere(ro, rd)                      # dataset.near_far_from_sphere
         bg = torch.ones([1, 3], device=batch.device) if self.use_white_bkgd else None
         out = self.renderer.render(ro, rd, near, far, background_rgb=bg, cos_anneal_ratio=self._car_dev)

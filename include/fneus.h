@@ -149,6 +149,22 @@ int fneus_color_bwd(const fneus_color_cfg* cfg, const float* wpack, const float*
                     const float* d_rgb, float* d_normals, float* d_feats, float* saved, float* scratch,
                     float* d_wpack, void* stream);
 
+/* ---- step glue: the small per-ray / per-scalar pieces around the render path that the reference leaves to ATen --------
+ * split_batch: [B,10] rows of Dataset.gen_random_rays_at (dataset.py:133-151) -> rays_o, rays_d, rgb [B,3], mask [B].
+ * inv_s: out = clip(exp(10 variance), 1e-6, 1e6) (fields.py:267-268, renderer.py:238) when d_inv_s is NULL, else the
+ *        gradient d_variance = d_inv_s * 10 exp(10 variance) inside the clip range.
+ * composite_post: eik [B,2] (per-ray numerator / denominator of renderer.py:282) -> tot3 = (sum num, sum den,
+ *        num / (den + 1e-5)) in a fixed summation order; hit_mask[b] = hit_idx[b] >= 0 (renderer.py:286).
+ * gather_rows3 / scatter_rows3: rows of three [N,3] tensors (points, directions, normals of the surface samples,
+ *        renderer.py:296-327) in one launch; scatter adds vals [n,3] into out [N,3] at distinct rows. */
+int fneus_split_batch(const float* batch, long long B, float* rays_o, float* rays_d, float* rgb, float* mask, void* stream);
+int fneus_inv_s(const float* variance, const float* d_inv_s, float* out, void* stream);
+int fneus_composite_post(const float* eik, const int* hit_idx, long long B, float* tot3, unsigned char* hit_mask,
+                         void* stream);
+int fneus_gather_rows3(const float* a, const float* b, const float* c, const long long* rows, long long n, float* oa,
+                       float* ob, float* oc, void* stream);
+int fneus_scatter_rows3(const float* vals, const long long* rows, long long n, float* out, void* stream);
+
 /* ---- operand images: the hand-over format of `feature_vector` between the SDF and the colour network on the tensor-core
  * path (renderer.py:225-232 passes it as an FP32 [n,256] tensor; here it never takes that form in HBM).  An image holds
  * ceil(n/128) row tiles x (n_cols/64) blocks of 128 rows x 64 columns of 16-bit elements in the 128-byte-swizzled K-major

@@ -238,10 +238,12 @@ def test_composite_fwd_bwd(n_out, car, use_bg_rgb):
     cu = lambda t: None if t is None else t.to(DEV)
     leaves = [t.to(DEV).requires_grad_(True) for t in (sdf, nrm, rgb, var)]
     bl = [t.to(DEV).requires_grad_(True) for t in (bga, bgc)] if n_out else [None, None]
-    inv_s = torch.exp(leaves[3] * 10.0).clip(1e-6, 1e6).reshape(1, 1)
-    color, w, wsum, wmax, cdf, inside, eik_num, eik_den, hit_idx, pair = ops.Composite.apply(
+    inv_s = ops.InvS.apply(leaves[3])               # clip(exp(10 variance)) as one launch (fields.py:267-268)
+    assert float((inv_s.detach().cpu() - torch.exp(var * 10.0).clip(1e-6, 1e6)).abs().max()) <= 1e-6 * float(inv_s)
+    color, w, wsum, wmax, cdf, inside, eik_num, eik_den, hit_idx, pair, eik, hit_mask = ops.Composite.apply(
         leaves[0], leaves[1], leaves[2], inv_s, bl[0], bl[1], cu(dists), cu(pts), cu(d), cu(bgr), n, n_out, car)
-    eik = eik_num / (eik_den + 1e-5)
+    assert torch.equal(hit_mask, hit_idx >= 0)
+    assert abs(float(eik) - float(eik_num / (eik_den + 1e-5))) <= 1e-6 * abs(float(eik)) + 1e-12
     assert_close(color, ref["color"], 1e-5, "color")
     assert_close(w, ref["weights"], 1e-5, "weights")
     assert_close(wsum, ref["weights"].sum(-1, keepdim=True), 1e-5, "weight_sum")
