@@ -341,7 +341,7 @@ def bench_train(C, args, config, steps, stats_steps):
     dev_batch = host.to(C.dev)
 
     def step(batch):
-        ro, rd, rgb, m = batch[:, :3], batch[:, 3:6], batch[:, 6:9], batch[:, 9:10]
+        ro, rd, rgb, m = _ops.split_batch(batch)                             # as train.Stage1Trainer._eager_step
         nr, fr = _ops.near_far_from_sphere(ro, rd)                           # dataset.near_far_from_sphere
         out = R.render(ro, rd, nr, fr, cos_anneal_ratio=car)
         loss, _ = stage1_loss_sharded(R, out, rgb, m, SURFACE_W, IGR_W, mask_w)
@@ -732,7 +732,8 @@ def run_ours(args):
     except Exception as ex:
         if args.config in ("wmask512", "womask4096") and not args.no_graph and C.world == 1:
             # a failed capture leaves the CUDA RNG in capture mode: re-run this process eagerly instead
-            print("bench: graphed step failed (%s); re-running with --no-graph" % str(ex).splitlines()[0], file=sys.stderr)
+            print("bench: graphed step failed (%s%s); re-running with --no-graph" % (str(ex).splitlines()[0], _hang_note()),
+                  file=sys.stderr)
             sys.stdout.flush()
             os.dup2(real_stdout, 1)
             os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
@@ -746,7 +747,7 @@ def run_ours(args):
             try:
                 extras[name] = run_config(name, False)
             except Exception as ex:                                          # an extra must never cost the headline line
-                extras[name] = {"error": str(ex).splitlines()[0][:300]}
+                extras[name] = {"error": (str(ex).splitlines()[0][:300] + _hang_note())[:2000]}
     sampler.mark_end()
     sampler.stop_flag = True
 
@@ -784,6 +785,23 @@ def run_ours(args):
         os._exit(0)
 
 
+def _hang_note():
+    """The library's wait watchdog record, if a kernel trapped on a wait that never completed (csrc/api.cu)."""
+    try:
+        import factored_neus_b200 as fn
+        rec = (ctypes.c_ulonglong * 64)()
+        fn._lib.lib().fneus_debug_hang_record(ctypes.cast(rec, ctypes.c_void_p))
+        if rec[0]:
+            return (" | wait watchdog: block (%d,%d,%d) thread %d of grid %d x %d threads, barrier smem 0x%x parity %d, "
+                    "complete %x, smem words %s" % (
+                        rec[1] >> 32, rec[4] >> 32, rec[4] & 0xFFFFFFFF, rec[1] & 0xFFFFFFFF, rec[2] >> 32,
+                        rec[2] & 0xFFFFFFFF, rec[3] >> 32, rec[3] & 0xFFFFFFFF, rec[5],
+                        " ".join("%x" % rec[8 + i] for i in range(48))))
+    except Exception:
+        pass
+    return ""
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -809,6 +827,18 @@ def main():
                     help="dense layers: bf16 = tcgen05 tensor cores (FP16 forward / BF16 backward operands, FP32 accumulate), "
                          "fp32 = CUDA-core anchor")
     args = ap.parse_args()
+    try:
+        # `kill -USR1 <pid>` (or `timeout -s USR1 ...`) dumps every thread's Python stack to stderr: where a stuck run is
+        import faulthandler
+        import signal
+        faulthandler.register(signal.SIGUSR1, all_threads=True)
+    except (ImportError, AttributeError, ValueError):
+        pass
+    wd = int(os.environ.get("FNEUS_BENCH_WATCHDOG", "0"))
+    if wd > 0:
+        # development aid: dump every thread's Python stack to stderr and exit if the run is still going after `wd` seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -98,6 +98,7 @@ _SIGNATURES = {
     "fneus_adam_step": (c_int, [_P, _P, _P, _P, _LL, _P, c_float, c_float, c_float, c_float, c_float, c_float, c_float,
                                 c_float, c_int, _P]),
     "fneus_debug_flags": (c_int, [c_int]),
+    "fneus_debug_hang_record": (c_int, [_P]),
     "fneus_debug_timeline": (c_int, [_P, c_int]),
     "fneus_debug_gemm": (c_int, [c_int, c_int, _P, c_int, _P, c_int, _P, _LL, c_int, c_int, _P, c_int, _P]),
     "fneus_prof_classes": (c_int, []),

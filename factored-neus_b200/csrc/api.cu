@@ -68,6 +68,16 @@ int fneus_debug_timeline(unsigned long long* host_dst, int n) {
   cudaError_t e = cudaMemcpyFromSymbol(host_dst, fneus::g_sc_dbg, (size_t)n * 8, (size_t)(8192 - n) * 8 * 0);
   return e == cudaSuccess ? FNEUS_OK : fneus::fneus_cuda_error((int)e);
 }
+// The wait watchdog's record (gemm_tc.cuh mbar_hang): out8[0] != 0 when a kernel of this library trapped on a wait that
+// never completed; [1] = blockIdx.x << 32 | threadIdx.x, [2] = gridDim.x << 32 | blockDim.x, [3] = barrier shared-memory
+// address << 32 | parity, [4] = blockIdx.y << 32 | blockIdx.z, [5] = 0x600DD06 once complete, [8..55] = the 64-bit words
+// of shared memory [barrier - 128, barrier + 256).  64 words.  Works after the CUDA context has died.
+int fneus_debug_hang_record(unsigned long long* out64) {
+  if (!out64) return FNEUS_ERR_NULL;
+  const volatile unsigned long long* h = fneus::hang_rec_host();
+  for (int i = 0; i < 64; i++) out64[i] = h ? h[i] : 0ull;
+  return FNEUS_OK;
+}
 int fneus_debug_flags(int flags) {
   fneus::tc_debug_flags() = flags & 0xFF;
   int w = (flags >> 8) & 0xF;                      // bits 8-11: weight-gradient CTAs per SM (tuning knob), 0 = keep

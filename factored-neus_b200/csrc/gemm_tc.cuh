@@ -29,25 +29,70 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Every mbarrier wait is bounded: a wait that has not completed after FNEUS_WAIT_LIMIT_NS (far beyond the run time of any
+// kernel of this library) records who waits on what in a host-mapped record (fneus_debug_hang_record) and traps -- a
+// protocol error surfaces as a CUDA launch failure with a diagnosis instead of a hung GPU.
+#ifndef FNEUS_WAIT_LIMIT_NS
+#define FNEUS_WAIT_LIMIT_NS 4000000000ull
+#endif
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ unsigned long long* g_hang_rec = nullptr;     // 64 words of host-mapped memory (tc_prepare), or null
+__device__ __noinline__ void mbar_hang(uint32_t bar_addr, uint32_t parity) {
+  volatile unsigned long long* r = g_hang_rec;
+  if (r != nullptr && atomicCAS(g_hang_rec, 0ull, 1ull) == 0ull) {
+    r[1] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+    r[2] = ((unsigned long long)gridDim.x << 32) | blockDim.x;
+    r[3] = ((unsigned long long)bar_addr << 32) | parity;
+    r[4] = ((unsigned long long)blockIdx.y << 32) | blockIdx.z;
+    // the 64-bit state words of the shared-memory neighbourhood [bar - 128, bar + 256): the control block of the kernel
+    // (which barriers are incomplete, and by how many arrivals)
+    for (int i = 0; i < 48; i++) {
+      unsigned long long w;
+      const uint32_t a = bar_addr - 128u + 8u * i;
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(a));
+      r[8 + i] = w;
+    }
+    __threadfence_system();
+    r[5] = 0x600DD06ull;                                  // record complete
+    __threadfence_system();
+    const unsigned long long t0 = global_ns();
+    while (global_ns() - t0 < 2000000ull) { }             // let the writes reach the host before the context dies
+    __trap();
+  }
+  // every other stuck thread leaves the trap to the recorder (a trap kills the kernel at once, record or not)
+  const unsigned long long t1 = global_ns();
+  while (global_ns() - t1 < 50000000ull) { }
+  __trap();
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar_addr, uint32_t parity, uint32_t hint) {
+  uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: the
-  // hardware parks the warp until the phase flips instead of re-polling (spin loops were 45% of the issued instructions)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar_addr), "r"(parity), "r"(hint) : "memory");
+  return ok != 0;
 }
+// suspend-time hint: the hardware parks the warp until the phase flips instead of re-polling (spin loops were 45% of the
+// issued instructions)
 __device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(hint) : "memory");
+  const uint32_t a = smem_u32(bar);
+  if (mbar_try_wait(a, parity, hint)) return;
+  unsigned long long t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(a, parity, hint)) {
+    if ((++spins & 1023u) == 0u) {
+      const unsigned long long t = global_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > FNEUS_WAIT_LIMIT_NS) mbar_hang(a, parity);
+    }
+  }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_hint(bar, parity, 0x989680u); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
                "r"(bytes)
@@ -1270,9 +1315,22 @@ inline int tc_num_sms() {
   }
   return n;
 }
+inline unsigned long long*& hang_rec_host() { static unsigned long long* p = nullptr; return p; }
 inline int tc_prepare() {
   static int done = 0;
   if (done) return 0;
+  if (hang_rec_host() == nullptr) {
+    // host-mapped record of the wait watchdog (readable after a trap has killed the context)
+    unsigned long long* h = nullptr;
+    unsigned long long* d = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), 64 * 8, cudaHostAllocMapped) == cudaSuccess && h != nullptr) {
+      for (int i = 0; i < 64; i++) h[i] = 0ull;
+      if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) == cudaSuccess &&
+          cudaMemcpyToSymbol(g_hang_rec, &d, sizeof(d)) == cudaSuccess)
+        hang_rec_host() = h;
+    }
+    (void)cudaGetLastError();
+  }
   cudaError_t e1 = cudaFuncSetAttribute(tc_gemm_mk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaError_t e2 = cudaFuncSetAttribute(tc_gemm_mk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   cudaError_t e3 = cudaFuncSetAttribute(tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);

@@ -121,7 +121,7 @@ __device__ unsigned long long g_sc_dbg[8192];
 struct SCSmem {
   uint64_t wfull[SC_WSTAGES], wempty[SC_WSTAGES];
   uint64_t a_ready[SC_NAR], acc_full, acc_half0, op_free, st_sync;
-  uint64_t aux_full[3], aux_empty[3], blk_done[3];
+  uint64_t aux_full[3], aux_empty[3], blk_done[4];   // blk_done: by block counter & 3 (see the epilogue's slot comment)
   uint32_t tmem_base;
 };
 // Auxiliary slots (h block + q block, 32 KB each) and weight stages per family: the backward chain is HBM-bound and
@@ -237,8 +237,9 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
     for (int i = 0; i < NSLOT; i++) {
       mbar_init(&ctl->aux_full[i], 1);
       mbar_init(&ctl->aux_empty[i], 1);
-      mbar_init(&ctl->blk_done[i], SC_EPI_THREADS / 32);
     }
+#pragma unroll
+    for (int i = 0; i < 4; i++) mbar_init(&ctl->blk_done[i], SC_EPI_THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int s = 0; s < g.nsteps; s++) {
@@ -354,7 +355,10 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
           const int nb = sdf_step_blocks(S);
           for (int b = 0; b < nb; b++, c++) {
             const int slot = c % NSLOT;
-            mbar_wait(&ctl->blk_done[slot], (c / NSLOT) & 1);
+            // the storer consumes the loader's phase of the slot too (whether the epilogue needed the slot or not): loader
+            // and storer then never run more than NSLOT blocks apart, whatever the epilogue does
+            mbar_wait(&ctl->aux_full[slot], (c / NSLOT) & 1);
+            mbar_wait(&ctl->blk_done[c & 3], (c >> 2) & 1);
             const size_t off = ((size_t)tile * 4 + b) * TC_A_BYTES;
             bool any = false;
             if (S.img_out != nullptr) { bulk_s2g(reinterpret_cast<uint8_t*>(S.img_out) + off, sOp + b * TC_A_BYTES, TC_A_BYTES); any = true; }
@@ -541,6 +545,12 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
         const bool s_append = SDF && S.append != 0, s_dot = FWD && S.dot != 0;
         const int csplit = S.csplit;
         // slots are only waited for when the step reads auxiliary blocks or stages through the slot
+        // slots are only waited for when the step reads auxiliary blocks or stages through the slot.  The epilogue of a
+        // step that needs no slot runs up to four blocks (one step: op_free) ahead of the storer, so "block done" is
+        // signalled on FOUR barriers indexed by the block counter: with one barrier per slot (two slots) the epilogue
+        // could complete TWO phases of the same barrier while the storer still waited for the first -- a parity wait
+        // cannot tell those apart and never returns (seen on cold first launches of the ReLU forward chain, where the first
+        // bulk stores take microseconds; diagnosed with the wait watchdog, gemm_tc.cuh mbar_hang).
         const bool uses_slot = S.h != nullptr || S.q != nullptr || mode == SC_FEATQ || mode == SC_G0 || mode == SC_OUT;
         const float oscale = S.oscale;
         const float ksg = -beta * S.hscale * 1.4426950408889634f;       // s(h) = 1 - 2^(ksg h)
@@ -889,7 +899,7 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
             // one arrival per warp: every lane has fenced its own writes, the warp barrier orders them before the arrive
             if (!all_arrive) __syncwarp();
             if (lane == 0 || all_arrive) {
-              mbar_arrive(&ctl->blk_done[slot]);
+              mbar_arrive(&ctl->blk_done[c & 3]);
               if (pub_blocks) mbar_arrive(&ctl->a_ready[b]);                  // the next step's MMAs may read block b
             }
             SC_STAMP(6);

@@ -46,6 +46,7 @@ typedef enum { FNEUS_PREC_FP32 = 0, FNEUS_PREC_TC = 1 } fneus_precision;
 
 /* ---- development hooks (NOT part of the production surface: process-wide switches for bisecting and profiling) --------
  * Bisect switches of the tensor-core kernels (results may be wrong when non-zero). */
+int fneus_debug_hang_record(unsigned long long* out64); /* wait watchdog: see csrc/api.cu (development hook) */
 int fneus_debug_flags(int flags);
 /* debug: copy the first n entries (n <= 8192) of the fused-chain timeline buffer (clock stamps, flag bit 6) */
 int fneus_debug_timeline(unsigned long long* host_dst, int n);

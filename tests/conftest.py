@@ -10,9 +10,20 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "timeout: wall-clock limit of a test (pytest-timeout)")
 
 
 def pytest_collection_modifyitems(config, items):
+    # every GPU test runs under a wall-clock limit (pytest-timeout, thread method: it also ends a test stuck inside a CUDA
+    # call): a kernel that never returns fails its test instead of hanging the session
+    if config.pluginmanager.hasplugin("timeout"):
+        for item in items:
+            if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(600, method="thread"))
+    _skip_gpu_without_cuda(items)
+
+
+def _skip_gpu_without_cuda(items):
     """Tests marked ``gpu`` need a CUDA device AND the built library: skip them elsewhere (CPU CI runs plain
     ``pytest tests``).  On a GPU box a missing library is a hard error, not a skip."""
     import torch
