@@ -99,6 +99,7 @@ def test_round2_ncu_exports_parse():
                           os.path.join(PROF, "r2_ncu_chain_full_raw.csv")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     rows = [l for l in out.stdout.splitlines() if l.startswith("| `")]
-    assert len(rows) == 14 and any("sdf_chain_kernel<1>" in r for r in rows) and any("wgrad_group" in r for r in rows)
+    # one step = 5 SDF-forward + 2 colour + 2 RefColor-pair + 1 SDF-backward chain launches and 3 weight-gradient groups
+    assert len(rows) == 13 and any("sdf_chain_kernel<1>" in r for r in rows) and any("wgrad_group" in r for r in rows)
     hist = open(os.path.join(PROF, "r2_sass_histogram.md")).read()
     assert "UTCHMMA" in hist and "| **all tensor-core kernels**" in hist
