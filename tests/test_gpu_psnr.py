@@ -25,6 +25,8 @@ B = 512
 EVAL_SPAN, EVAL_EVERY = 200, 10
 GATE_DB = 0.1
 REPEATS = int(os.environ.get("FNEUS_PSNR_REPEATS", "2"))
+WARM_UP_END = int(os.environ.get("FNEUS_PSNR_WARM_UP_END", "100"))
+END_ITER = int(os.environ.get("FNEUS_PSNR_END_ITER", str(ITERS)))
 
 
 def _render_rgb(R, o, d, near, far):
@@ -55,8 +57,8 @@ def test_bf16_training_tracks_fp32_psnr():
         ops.set_precision(prec)
         m = build_modules(syn.scene_states(seed=4), DEV, syn.RENDER_CONF_WMASK)
         # both arms run the captured step: identical launch sequence and identical Philox offsets for the perturbation
-        tr = Stage1Trainer(m["renderer"], [m["sdf"], m["var"], m["color"], m["ref"]], B, warm_up_end=100,
-                           end_iter=ITERS, use_graph=True)
+        tr = Stage1Trainer(m["renderer"], [m["sdf"], m["var"], m["color"], m["ref"]], B, warm_up_end=WARM_UP_END,
+                           end_iter=END_ITER, use_graph=True)
         torch.manual_seed(11)
         evals, evals32 = [], []
         for it in range(ITERS):
