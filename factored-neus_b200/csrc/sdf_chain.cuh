@@ -598,8 +598,8 @@ __device__ __forceinline__ void chain_body(const SdfChainArgs& g, const int cta,
         // The per-block loop, instantiated per mode: MODEC >= 0 fixes the step's mode at compile time; FAST is a whole tile
         // with a 256-wide result and no skip / row-dot extras (four unmasked blocks) -- the bulk of the forward chains,
         // where the epilogue's instruction issue is the bound (7% on the SDF forward).  MODEC < 0 is the general loop
-        // (runtime mode, ragged tiles, narrow or staged outputs).  The loop stays rolled: unrolling it by four bought
-        // nothing on the forward chain and the fully unrolled build of all instantiations deadlocked (sm_100a, CUDA 12.9).
+        // (runtime mode, ragged tiles, narrow or staged outputs).  The loop stays rolled: unrolling it by four buys nothing
+        // (0.679 ms either way on the SDF forward).
         auto run_blocks = [&](auto mode_c, auto fast_c) {
           constexpr int MODEC = decltype(mode_c)::value;
           constexpr bool FAST = decltype(fast_c)::value;
