@@ -1,6 +1,5 @@
-"""north_star gate for the tensor-core path: PSNR after 1k training iterations within 0.1 dB of the FP32 path, end to end
-(trained AND rendered on the tensor-core path), compared as ensemble means with the measurement's own resolution stated
-(the run-to-run spread of ONE arm is of the size of the bound: see the comment at the repeats).
+"""north_star gate for the tensor-core path, AS WRITTEN: PSNR after 1k training iterations within 0.1 dB of the FP32
+path, end to end (trained AND rendered on the tensor-core path); two runs per arm, ensemble means, no allowance for noise.
 
 Teacher = the same architecture at another random init (seed 123) rendered unperturbed on the FP32 path; both
 students start from seed 4, see the identical ray order and identical perturbation random numbers, and are
@@ -20,13 +19,18 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 ITERS = int(os.environ.get("FNEUS_PSNR_ITERS", "1000"))
 B = 512
-# A single held-out PSNR reading after 1k Adam steps moves by +-0.2 dB when ANY rounding changes (two trajectories of a
-# non-convex optimisation diverge), so the reading compared is the mean over the checkpoints of the last 200 iterations.
+# A single checkpoint's held-out PSNR moves by a few 0.1 dB from one checkpoint to the next (minibatch noise), so the reading
+# compared is the mean over the checkpoints of the last 200 iterations.
 EVAL_SPAN, EVAL_EVERY = 200, 10
 GATE_DB = 0.1
 REPEATS = int(os.environ.get("FNEUS_PSNR_REPEATS", "2"))
 WARM_UP_END = int(os.environ.get("FNEUS_PSNR_WARM_UP_END", "100"))
 END_ITER = int(os.environ.get("FNEUS_PSNR_END_ITER", str(ITERS)))
+# Peak learning rate of both arms: 1e-4 = what the reference's schedule (5e-4 with a 5000-iteration warm-up,
+# exp_runner.py:229-238) reaches at iteration 1000.  At 5e-4 from iteration 100 on (an earlier version of this test) the
+# optimisation is chaotic enough that two runs of the SAME arm end 0.1-0.25 dB apart (the weight gradients are summed with
+# FP32 atomics) -- the bound could not be resolved; at 1e-4 both arms reach the same ~50.6 dB and repeat to ~0.04 dB.
+LR = float(os.environ.get("FNEUS_PSNR_LR", "1e-4"))
 
 
 def _render_rgb(R, o, d, near, far):
@@ -57,7 +61,7 @@ def test_bf16_training_tracks_fp32_psnr():
         ops.set_precision(prec)
         m = build_modules(syn.scene_states(seed=4), DEV, syn.RENDER_CONF_WMASK)
         # both arms run the captured step: identical launch sequence and identical Philox offsets for the perturbation
-        tr = Stage1Trainer(m["renderer"], [m["sdf"], m["var"], m["color"], m["ref"]], B, warm_up_end=WARM_UP_END,
+        tr = Stage1Trainer(m["renderer"], [m["sdf"], m["var"], m["color"], m["ref"]], B, lr=LR, warm_up_end=WARM_UP_END,
                            end_iter=END_ITER, use_graph=True)
         torch.manual_seed(11)
         evals, evals32 = [], []
@@ -74,11 +78,8 @@ def test_bf16_training_tracks_fp32_psnr():
                     ops.set_precision("bf16")
         return evals, evals32
 
-    # Two runs per arm.  The weight gradients are summed with FP32 atomics (split-K), so two runs of the SAME arm follow
-    # different trajectories: measured on this scene, the window mean of one arm moves by ~0.1-0.2 dB from run to run
-    # (FP32 against FP32 included).  A single pair of runs therefore cannot resolve a 0.1 dB bound; the ensemble means
-    # are compared, and the resolution of that comparison (two standard errors, from the spread of the repeated runs) is
-    # stated next to the bound instead of being ignored.
+    # Two runs per arm: the weight gradients are summed with FP32 atomics (split-K), so two runs of the same arm are not
+    # bit-identical; the spread between the repeats is printed next to the difference it has to be read against.
     mean = lambda v: sum(v) / len(v)
     fmt = lambda v: " ".join("%.2f" % x for x in v)
     runs32, runs16, runs16_as32 = [], [], []
@@ -99,10 +100,10 @@ def test_bf16_training_tracks_fp32_psnr():
           "run-to-run spread fp32 %.3f, tensor-core %.3f -> standard error of the difference %.3f dB"
           % (ITERS, REPEATS, p32, fmt(runs32), p16, fmt(runs16), p16 - p32, p16_as32, p16_as32 - p32, p16 - p16_as32,
              spread32, spread16, se))
-    # The north_star bound: end to end, |difference| <= 0.1 dB -- at the resolution this measurement has.
-    assert abs(p16 - p32) <= GATE_DB + 2.0 * se, (
-        "tensor-core end-to-end PSNR %.3f vs fp32 %.3f: outside %.1f dB (+ 2 x %.3f standard error)" % (p16, p32, GATE_DB, se))
-    assert abs(p16_as32 - p32) <= GATE_DB + 2.0 * se, (
+    # The north_star bound AS WRITTEN: end to end, |difference| <= 0.1 dB (ensemble means, no allowance for the spread).
+    assert abs(p16 - p32) <= GATE_DB, (
+        "tensor-core end-to-end PSNR %.3f vs fp32 %.3f: outside %.1f dB (standard error %.3f)" % (p16, p32, GATE_DB, se))
+    assert abs(p16_as32 - p32) <= GATE_DB, (
         "tensor-core-trained weights (fp32 render) %.3f vs fp32 %.3f" % (p16_as32, p32))
     # the deterministic component: what the tensor-core renderer's operand rounding costs on FIXED weights (no trajectory
     # noise in this one: the same weights rendered by both paths)
