@@ -79,15 +79,28 @@ __global__ void colsum_img_kernel(const uint8_t* __restrict__ img, int kbs, int 
   const int g = threadIdx.x & 7, rsub = threadIdx.x >> 3;     // 256 threads: 32 row lanes x 8 column groups
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float ws = 0.f;
-  for (long long m = mbeg + rsub; m < mend; m += 32) {
-    const float wm = w ? __ldg(w + m) * wscale : 1.f;
-    const uint8_t* p = img + ((size_t)(m >> 7) * kbs + cb) * 16384 + (((m & 127) >> 3) * 1024 + (m & 7) * 128) +
-                       (((g ^ (int)(m & 7)) & 7) << 4);
-    float v[8];
-    u16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(p)), f16 != 0, v);
+  // four rows per round: the loads of a round are issued before any of them is used (the kernel is pure streaming)
+  for (long long m0 = mbeg + rsub; m0 < mend; m0 += 128) {
+    uint4 u[4];
+    float wm[4];
 #pragma unroll
-    for (int t = 0; t < 8; t++) acc[t] += wm * v[t];
-    if (g == 0) ws += wm;
+    for (int i = 0; i < 4; i++) {
+      const long long m = m0 + 32 * i;
+      const bool ok = m < mend;
+      const long long mc = ok ? m : m0;
+      const uint8_t* p = img + ((size_t)(mc >> 7) * kbs + cb) * 16384 + (((mc & 127) >> 3) * 1024 + (mc & 7) * 128) +
+                         (((g ^ (int)(mc & 7)) & 7) << 4);
+      u[i] = __ldg(reinterpret_cast<const uint4*>(p));
+      wm[i] = ok ? (w ? __ldg(w + mc) * wscale : 1.f) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float v[8];
+      u16x8_to_f32(u[i], f16 != 0, v);
+#pragma unroll
+      for (int t = 0; t < 8; t++) acc[t] += wm[i] * v[t];
+      if (g == 0) ws += wm[i];
+    }
   }
   __shared__ float red[64];
   __shared__ float redw;
