@@ -919,6 +919,9 @@ class FanOut(torch.autograd.Function):
         stash = ctx.stash
         g = g_dense
         if g_other is not None:
+            if stash.get("feat_image"):
+                # an operand image is an opaque byte pattern: two of them cannot be added as float32 tensors
+                raise RuntimeError("fneus FanOut: the sparse branch of a feature IMAGE may only feed ops.GatherRows")
             g = g_other if g is None else g + g_other
         pend = stash.pop("rows_grad", None)
         if pend is not None:
