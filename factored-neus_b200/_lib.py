@@ -104,6 +104,7 @@ _SIGNATURES = {
     "fneus_prof_classes": (c_int, []),
     "fneus_prof_enable": (c_int, [c_int]),
     "fneus_prof_collect": (c_int, [_P, _P, _P, _P]),
+    "fneus_upsample_iter": (c_int, [_P, _P, _P, _P, _LL, c_int, _P, _P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P]),
     "fneus_split_batch": (c_int, [_P, _LL, _P, _P, _P, _P, _P]),
     "fneus_inv_s": (c_int, [_P, _P, _P, _P]),
     "fneus_composite_post": (c_int, [_P, _P, _LL, _P, _P, _P]),

@@ -58,8 +58,10 @@ __device__ __forceinline__ int count_leq(const float* c, int n, float v) {
   return lo;
 }
 
+// pts (optional, [k,3]) with o3 / d3 = the ray: the new samples' positions, rounded exactly like ray_points_kernel
 __device__ __forceinline__ void invert_cdf_warp(const float* sz, const float* scdf, int n, int k,
-                                                const float* u_table, float* out, long long* inds, int lane) {
+                                                const float* u_table, float* out, long long* inds, int lane,
+                                                float* pts = nullptr, const float* o3 = nullptr, const float* d3 = nullptr) {
   for (int m = lane; m < k; m += 32) {
     float u = __ldg(u_table + m);
     int idx = upper_bound(scdf, n, u);
@@ -68,29 +70,22 @@ __device__ __forceinline__ void invert_cdf_warp(const float* sz, const float* sc
     float den = scdf[hi] - scdf[lo];
     if (den < 1e-5f) den = 1.f;
     float t = (u - scdf[lo]) / den;
-    out[m] = __fadd_rn(sz[lo], __fmul_rn(t, sz[hi] - sz[lo]));
+    const float zn = __fadd_rn(sz[lo], __fmul_rn(t, sz[hi] - sz[lo]));
+    out[m] = zn;
     if (inds) inds[m] = idx;
+    if (pts) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) pts[m * 3 + c] = __fadd_rn(o3[c], __fmul_rn(d3[c], zn));
+    }
   }
 }
 
-__global__ void __launch_bounds__(SAMP_WARPS * 32)
-upsample_step_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                     const float* __restrict__ z, long long z_stride, const float* __restrict__ sdf, long long B, int n,
-                     int k, float inv_s_host, const float* __restrict__ inv_s_dev, const float* __restrict__ u_table,
-                     float* __restrict__ new_z, float* __restrict__ cdf_out, long long* __restrict__ inds_out) {
-  extern __shared__ float smem[];
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const long long ray = (long long)blockIdx.x * SAMP_WARPS + warp;
-  if (ray >= B) return;
-  const float inv_s = inv_s_dev != nullptr ? __ldg(inv_s_dev) : inv_s_host;   // device scalar: the learned inv_s of stage 2
-  float* sz = smem + (size_t)warp * 3 * n;
-  float* sf = sz + n;
-  float* sc = sf + n;   // alpha, then cdf
-  for (int j = lane; j < n; j += 32) {
-    sz[j] = __ldg(z + ray * z_stride + j);             // z_stride 0: one depth table shared by all rays (stage 2)
-    sf[j] = __ldg(sdf + ray * n + j);
-  }
-  __syncwarp();
+// One up-sampling step on a ray whose depths / sdf values sit in shared memory (sz, sf; sc: scratch for alpha, then the CDF):
+// up_sample + sample_pdf (renderer.py:152-189, 43-77).  Shared by the single-step kernel and the fused iteration kernel.
+__device__ __forceinline__ void upsample_row(float* sz, float* sf, float* sc, int n, const float* __restrict__ rays_o,
+                                             const float* __restrict__ rays_d, long long ray, float inv_s, int k,
+                                             const float* __restrict__ u_table, float* new_z_row, float* cdf_row,
+                                             long long* inds_row, float* pts_row, int lane) {
   const float ox = rays_o[ray * 3], oy = rays_o[ray * 3 + 1], oz = rays_o[ray * 3 + 2];
   const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
   // |o + d t| < 1 as a test on the squared radius (radius_lt_1: identical to comparing the rounded square root)
@@ -150,9 +145,32 @@ upsample_step_kernel(const float* __restrict__ rays_o, const float* __restrict__
   }
   if (lane == 0) sc[0] = 0.f;
   __syncwarp();
-  if (cdf_out)
-    for (int j = lane; j < n; j += 32) cdf_out[ray * n + j] = sc[j];
-  invert_cdf_warp(sz, sc, n, k, u_table, new_z + ray * k, inds_out ? inds_out + ray * k : nullptr, lane);
+  if (cdf_row)
+    for (int j = lane; j < n; j += 32) cdf_row[j] = sc[j];
+  const float o3[3] = {ox, oy, oz}, d3[3] = {dx, dy, dz};
+  invert_cdf_warp(sz, sc, n, k, u_table, new_z_row, inds_row, lane, pts_row, o3, d3);
+}
+
+__global__ void __launch_bounds__(SAMP_WARPS * 32)
+upsample_step_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                     const float* __restrict__ z, long long z_stride, const float* __restrict__ sdf, long long B, int n,
+                     int k, float inv_s_host, const float* __restrict__ inv_s_dev, const float* __restrict__ u_table,
+                     float* __restrict__ new_z, float* __restrict__ cdf_out, long long* __restrict__ inds_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long long ray = (long long)blockIdx.x * SAMP_WARPS + warp;
+  if (ray >= B) return;
+  const float inv_s = inv_s_dev != nullptr ? __ldg(inv_s_dev) : inv_s_host;   // device scalar: the learned inv_s of stage 2
+  float* sz = smem + (size_t)warp * 3 * n;
+  float* sf = sz + n;
+  float* sc = sf + n;   // alpha, then cdf
+  for (int j = lane; j < n; j += 32) {
+    sz[j] = __ldg(z + ray * z_stride + j);             // z_stride 0: one depth table shared by all rays (stage 2)
+    sf[j] = __ldg(sdf + ray * n + j);
+  }
+  __syncwarp();
+  upsample_row(sz, sf, sc, n, rays_o, rays_d, ray, inv_s, k, u_table, new_z + ray * k, cdf_out ? cdf_out + ray * n : nullptr,
+               inds_out ? inds_out + ray * k : nullptr, nullptr, lane);
 }
 
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
@@ -174,6 +192,51 @@ inverse_cdf_kernel(const float* __restrict__ bins, const float* __restrict__ cdf
 // (new element: its ordinal among the set bits; old element: position minus the set bits below it), so all stores are
 // coalesced in output order.  Ties: old samples first, each list in its own order (what a stable sort of the
 // concatenation [old, new] gives).
+// Rank merge of two sorted rows in shared memory (cat_z_vals, renderer.py:191-205): every new sample goes to position
+// j + #(old <= new_j), the old ones fill the gaps in order; the riding sdf values follow.  Results to global rows zo / so
+// (so may be null) and, when dz is given, also to the shared rows dz / df (the next step's input).
+__device__ __forceinline__ void merge_row(const float* sa, const float* sb, const float* sfa, const float* sfb, int n, int k,
+                                          unsigned* mask, unsigned* pre, bool carry, float* zo, float* so, float* dz,
+                                          float* df, int lane) {
+  const int tot = n + k, W = (tot + 31) >> 5;
+  for (int w = lane; w < W; w += 32) mask[w] = 0u;
+  __syncwarp();
+  for (int j = lane; j < k; j += 32) {
+    const int pos = j + count_leq(sa, n, sb[j]);
+    atomicOr(&mask[pos >> 5], 1u << (pos & 31));
+  }
+  __syncwarp();
+  unsigned run = 0u;
+  for (int w0 = 0; w0 < W; w0 += 32) {
+    const int w = w0 + lane;
+    const unsigned c = w < W ? (unsigned)__popc(mask[w]) : 0u;
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (w < W) pre[w] = run + incl - c;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  for (int q = lane; q < tot; q += 32) {
+    const unsigned m = mask[q >> 5];
+    const int bit = q & 31;
+    const int below = (int)pre[q >> 5] + __popc(m & ((1u << bit) - 1u));
+    const bool from_b = (m >> bit) & 1u;
+    const int i = from_b ? below : q - below;
+    const float zv = from_b ? sb[i] : sa[i];
+    zo[q] = zv;
+    if (dz) dz[q] = zv;
+    if (carry) {
+      const float fv = from_b ? sfb[i] : sfa[i];
+      so[q] = fv;
+      if (df) df[q] = fv;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
 merge_sorted_kernel(const float* __restrict__ z, const float* __restrict__ new_z, const float* __restrict__ sdf,
                     const float* __restrict__ new_sdf, long long B, int n, int k, float* __restrict__ z_out,
@@ -198,42 +261,43 @@ merge_sorted_kernel(const float* __restrict__ z, const float* __restrict__ new_z
     sb[j] = new_z[ray * k + j];
     if (carry) sfb[j] = new_sdf[ray * k + j];
   }
-  for (int w = lane; w < W; w += 32) mask[w] = 0u;
-  __syncwarp();
-  for (int j = lane; j < k; j += 32) {
-    const int pos = j + count_leq(sa, n, sb[j]);
-    atomicOr(&mask[pos >> 5], 1u << (pos & 31));
+  merge_row(sa, sb, sfa, sfb, n, k, mask, pre, carry, z_out + ray * tot, carry ? sdf_out + ray * tot : nullptr, nullptr,
+            nullptr, lane);
+}
+
+// One iteration of the hierarchical sampling loop (renderer.py:166-176) in one launch: merge the previous iteration's kp new
+// samples (with their sdf values) into the ray's sorted row, up-sample k new depths from the merged row, and emit their
+// positions for the next SDF pass.  kp = 0: no merge (first iteration).  Same arithmetic as the three separate kernels.
+__global__ void __launch_bounds__(SAMP_WARPS * 32)
+upsample_iter_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z,
+                     const float* __restrict__ sdf, long long B, int n, const float* __restrict__ prev_z,
+                     const float* __restrict__ prev_sdf, int kp, int k, float inv_s, const float* __restrict__ u_table,
+                     float* __restrict__ z_out, float* __restrict__ sdf_out, float* __restrict__ new_z,
+                     float* __restrict__ pts_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long long ray = (long long)blockIdx.x * SAMP_WARPS + warp;
+  if (ray >= B) return;
+  const int tot = n + kp, W = (tot + 31) >> 5;
+  float* sz = smem + (size_t)warp * (5 * tot + 2 * W);   // merged row: z, sdf, scratch; then the two inputs of the merge
+  float* sf = sz + tot;
+  float* sc = sf + tot;
+  float* sa = sc + tot;
+  float* sb = sa + n;
+  float* sfa = sb + kp;
+  float* sfb = sfa + n;
+  unsigned* mask = reinterpret_cast<unsigned*>(sfb + kp);
+  unsigned* pre = mask + W;
+  if (kp > 0) {
+    for (int j = lane; j < n; j += 32) { sa[j] = z[ray * n + j]; sfa[j] = sdf[ray * n + j]; }
+    for (int j = lane; j < kp; j += 32) { sb[j] = prev_z[ray * kp + j]; sfb[j] = prev_sdf[ray * kp + j]; }
+    merge_row(sa, sb, sfa, sfb, n, kp, mask, pre, true, z_out + ray * tot, sdf_out + ray * tot, sz, sf, lane);
+  } else {
+    for (int j = lane; j < n; j += 32) { sz[j] = __ldg(z + ray * n + j); sf[j] = __ldg(sdf + ray * n + j); }
   }
   __syncwarp();
-  unsigned run = 0u;
-  for (int w0 = 0; w0 < W; w0 += 32) {
-    const int w = w0 + lane;
-    const unsigned c = w < W ? (unsigned)__popc(mask[w]) : 0u;
-    unsigned incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (w < W) pre[w] = run + incl - c;
-    run += __shfl_sync(0xffffffffu, incl, 31);
-  }
-  __syncwarp();
-  float* zo = z_out + ray * tot;
-  float* so = carry ? sdf_out + ray * tot : nullptr;
-  for (int q = lane; q < tot; q += 32) {
-    const unsigned m = mask[q >> 5];
-    const int bit = q & 31;
-    const int below = (int)pre[q >> 5] + __popc(m & ((1u << bit) - 1u));
-    if ((m >> bit) & 1u) {
-      zo[q] = sb[below];
-      if (carry) so[q] = sfb[below];
-    } else {
-      const int i = q - below;
-      zo[q] = sa[i];
-      if (carry) so[q] = sfa[i];
-    }
-  }
+  upsample_row(sz, sf, sc, tot, rays_o, rays_d, ray, inv_s, k, u_table, new_z + ray * k, nullptr, nullptr,
+               pts_out ? pts_out + ray * k * 3 : nullptr, lane);
 }
 
 __global__ void ray_points_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ z,
@@ -487,6 +551,27 @@ int fneus_upsample_step_dev(const float* rays_o, const float* rays_d, const floa
                             int n, int k, const float* inv_s_dev, const float* u_table, float* new_z, void* stream) {
   if (!inv_s_dev) return FNEUS_ERR_NULL;
   return upsample_step_launch(rays_o, rays_d, z, sdf, B, n, k, 0.f, inv_s_dev, u_table, new_z, nullptr, nullptr, stream);
+}
+
+int fneus_upsample_iter(const float* rays_o, const float* rays_d, const float* z, const float* sdf, long long B, int n,
+                        const float* prev_z, const float* prev_sdf, int kp, int k, float inv_s, const float* u_table,
+                        float* z_out, float* sdf_out, float* new_z, float* pts_out, void* stream) {
+  if (B == 0 || k == 0) return FNEUS_OK;
+  if (!rays_o || !rays_d || !z || !sdf || !u_table || !new_z) return FNEUS_ERR_NULL;
+  if (kp > 0 && (!prev_z || !prev_sdf || !z_out || !sdf_out)) return FNEUS_ERR_NULL;
+  if (B < 0 || n < 2 || k < 0 || kp < 0 || n + kp > 4096) return FNEUS_ERR_BAD_SHAPE;
+  const int tot = n + kp;
+  size_t smem = (size_t)SAMP_WARPS * (5 * tot + 2 * ((tot + 31) / 32)) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(upsample_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fneus_cuda_error((int)e);
+  }
+  prof_begin(PC_SAMPLING, 0.0, (double)B * (tot * 16.0 + kp * 8.0 + k * 16.0 + 24.0), (cudaStream_t)stream);
+  upsample_iter_kernel<<<cdiv(B, SAMP_WARPS), SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      rays_o, rays_d, z, sdf, B, n, prev_z, prev_sdf, kp, k, inv_s, u_table, z_out, sdf_out, new_z, pts_out);
+  prof_end((cudaStream_t)stream);
+  FNEUS_CHECK_LAUNCH();
+  return FNEUS_OK;
 }
 
 int fneus_inverse_cdf(const float* bins, const float* cdf, const float* u_table, long long B, int n, int k,

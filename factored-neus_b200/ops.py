@@ -490,6 +490,29 @@ def upsample_step_dev(rays_o, rays_d, z, sdf, k, inv_s_dev, u_table):
     return new_z
 
 
+def upsample_iter(rays_o, rays_d, z, sdf, prev_z, prev_sdf, k, inv_s, u_table, want_pts=True):
+    """One iteration of the hierarchical sampling loop (renderer.py:166-176) in one launch: merge (prev_z, prev_sdf) into
+    (z, sdf) when given, up-sample k new depths from the merged row and return their positions for the next SDF pass.
+    -> (z_merged, sdf_merged, new_z [B,k], pts [B*k,3] or None).  Bit-identical to merge_sorted + upsample_step + ray_points."""
+    _need_cuda(z, "z")
+    B, n = z.shape
+    kp = 0 if prev_z is None else prev_z.shape[1]
+    f32 = dict(dtype=torch.float32, device=z.device)
+    zc, sc = _f32c(z), _f32c(sdf).reshape(B, n)
+    if kp:
+        z_out, sdf_out = torch.empty(B, n + kp, **f32), torch.empty(B, n + kp, **f32)
+        pz, ps = _f32c(prev_z), _f32c(prev_sdf).reshape(B, kp)
+    else:
+        z_out, sdf_out, pz, ps = zc, sc, None, None
+    new_z = torch.empty(B, k, **f32)
+    pts = torch.empty(B * k, 3, **f32) if want_pts else None
+    L.check(L.lib().fneus_upsample_iter(L.ptr(_f32c(rays_o)), L.ptr(_f32c(rays_d)), L.ptr(zc), L.ptr(sc), B, n, L.ptr(pz),
+                                        L.ptr(ps), kp, int(k), float(inv_s), L.ptr(_f32c(u_table)),
+                                        L.ptr(z_out) if kp else None, L.ptr(sdf_out) if kp else None, L.ptr(new_z),
+                                        L.ptr(pts), L.stream_ptr()), "fneus_upsample_iter")
+    return z_out, sdf_out, new_z, pts
+
+
 def first_hit_secant(sdf, mid_z, pts, rays_o, rays_d, weights=None):
     """renderer.py:588-602 / calLvis.py:180-196 with fixed shapes: (hit_idx [B] int32, -1 = no hit; z_surf [B,1];
     pts_surf [B,3]; lvis [B] = 1 - sum w * inside when ``weights`` is given, else None; any_inside [B] bool)."""

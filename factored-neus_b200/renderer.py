@@ -81,15 +81,23 @@ class NeuSRenderer:
                                     new_sdf.contiguous())
 
     def _hierarchical(self, rays_o, rays_d, z_vals):
+        """renderer.py:166-176: up_sample / cat_z_vals `up_sample_steps` times.  One launch per iteration between the SDF
+        passes (ops.upsample_iter: the previous iteration's merge, this iteration's inverse-CDF depths and their positions);
+        `up_sample` / `cat_z_vals` above stay as the reference's own entry points."""
         B = z_vals.shape[0]
+        k = self.n_importance // self.up_sample_steps
         with torch.no_grad():
+            u = self._linspace(0.5 / k, 1.0 - 0.5 / k, k, z_vals.device)
             pts = ops.ray_points(rays_o, rays_d, z_vals)
             sdf = self._sdf_nograd(pts).reshape(B, self.n_samples)
+            new_z = new_sdf = None
             for i in range(self.up_sample_steps):
-                new_z = self.up_sample(rays_o, rays_d, z_vals, sdf, self.n_importance // self.up_sample_steps,
-                                       64 * 2 ** i)
-                z_vals, sdf = self.cat_z_vals(rays_o, rays_d, z_vals, new_z, sdf,
-                                              last=(i + 1 == self.up_sample_steps))
+                last = i + 1 == self.up_sample_steps
+                z_vals, sdf, new_z, pts = ops.upsample_iter(rays_o, rays_d, z_vals, sdf, new_z, new_sdf, k,
+                                                            float(64 * 2 ** i), u, want_pts=not last)
+                if not last:
+                    new_sdf = self._sdf_nograd(pts).reshape(B, k)
+            z_vals, _ = ops.merge_sorted(z_vals, new_z)           # the last new depths need no sdf (renderer.py:174-176)
         return z_vals
 
     # ------------------------------------------------------------------ core

@@ -277,6 +277,14 @@ int fneus_upsample_step_dev(const float* rays_o, const float* rays_d, const floa
 int fneus_first_hit_secant(const float* sdf, const float* mid_z, const float* pts, const float* rays_o,
                            const float* rays_d, const float* weights, int ldw, long long n_rays, int n,
                            int* hit_idx, float* z_surf, float* pts_surf, float* lvis, int* any_inside, void* stream);
+/* One iteration of the hierarchical sampling loop (renderer.py:166-176) in one launch: merge the previous iteration's kp new
+ * depths prev_z [B,kp] with their sdf values prev_sdf into the sorted rows z / sdf [B,n] (cat_z_vals, :191-205; results
+ * z_out / sdf_out [B,n+kp]; kp = 0: no merge), up-sample k depths new_z [B,k] from the merged row (up_sample + sample_pdf,
+ * :152-189, 43-77) and emit their positions pts_out [B,k,3] = o + d z (may be NULL).  Bit-identical to fneus_merge_sorted +
+ * fneus_upsample_step + fneus_ray_points. */
+int fneus_upsample_iter(const float* rays_o, const float* rays_d, const float* z, const float* sdf, long long B, int n,
+                        const float* prev_z, const float* prev_sdf, int kp, int k, float inv_s, const float* u_table,
+                        float* z_out, float* sdf_out, float* new_z, float* pts_out, void* stream);
 /* Inverse-CDF alone (renderer.py:64-77): searchsorted(right=True) + interpolation on a SUPPLIED cdf. */
 int fneus_inverse_cdf(const float* bins, const float* cdf, const float* u_table, long long n_rays, int n, int k,
                       float* samples_out, long long* inds_out, void* stream);

@@ -729,3 +729,33 @@ def test_stage2_loss_matches_oracle():
     assert abs(float(st_g["lvis_loss"]) - float(st_o["lvis_loss"])) < 1e-6
     assert_close(pl.grad, pre_l.grad, 1e-7, "d pre_lvis")
     assert_close(pr.grad, pre_r.grad, 1e-7, "d pre_trace_radiance")
+
+
+@pytest.mark.parametrize("B,n,kp,k", [(37, 64, 0, 16), (37, 64, 16, 16), (5, 112, 16, 16), (3, 40, 7, 9)])
+def test_upsample_iter_is_the_three_kernels_in_one(B, n, kp, k):
+    """fneus_upsample_iter (one launch per iteration of the hierarchical loop) against the separate kernels it fuses --
+    merge_sorted, upsample_step, ray_points -- bit for bit, on rows with ties between old and new depths."""
+    g = torch.Generator().manual_seed(100 * n + kp)
+    o, d, near, far = syn.make_rays(B, seed=3)
+    z = torch.sort(near + (far - near) * torch.rand(B, n, generator=g), dim=-1)[0]
+    sdf = torch.randn(B, n, generator=g) * 0.3
+    prev_z = prev_sdf = None
+    if kp:
+        prev_z = torch.sort(near + (far - near) * torch.rand(B, kp, generator=g), dim=-1)[0]
+        prev_z[:, 0] = z[:, n // 2]                                   # a tie: the new sample goes AFTER the equal old one
+        prev_z = torch.sort(prev_z, dim=-1)[0]
+        prev_sdf = torch.randn(B, kp, generator=g) * 0.3
+    u = torch.linspace(0.5 / k, 1.0 - 0.5 / k, k)
+    cu = lambda t: None if t is None else t.to(DEV).contiguous()
+    od, dd, zd, sd, pzd, psd, ud = map(cu, (o, d, z, sdf, prev_z, prev_sdf, u))
+    if kp:
+        z_ref, s_ref = ops.merge_sorted(zd, pzd, sd, psd)
+    else:
+        z_ref, s_ref = zd, sd
+    nz_ref = ops.upsample_step(od, dd, z_ref, s_ref, k, 64.0, ud)
+    p_ref = ops.ray_points(od, dd, nz_ref)
+    z_got, s_got, nz_got, p_got = ops.upsample_iter(od, dd, zd, sd, pzd, psd, k, 64.0, ud)
+    assert torch.equal(z_got, z_ref) and torch.equal(s_got, s_ref)
+    assert torch.equal(nz_got, nz_ref)
+    assert torch.equal(p_got.reshape(-1), p_ref.reshape(-1))
+    assert ops.upsample_iter(od, dd, zd, sd, pzd, psd, k, 64.0, ud, want_pts=False)[3] is None
