@@ -26,7 +26,7 @@ def load(path):
 
 def main():
     seq = load(sys.argv[1])
-    idx = [i for i, s in enumerate(seq) if "upsample_step" in s[0]]
+    idx = [i for i, s in enumerate(seq) if "upsample_step" in s[0] or "upsample_iter" in s[0]]
     start, end = idx[-8], idx[-4]          # 4 up-sampling launches per step: the last complete step
     step = seq[start:end]
     tot = sum(v for _, v, _ in step)
